@@ -1,0 +1,136 @@
+/*
+ * jbugs_cuda.h -- C ABI of libjbugs_cuda, the B200 (sm_100a) batched evaluator for
+ * `LogDensityProblems.logdensity` / `logdensity_and_gradient` on a compiled BUGS model.
+ *
+ * Each entry point names the reference interface it stands in for (paths relative to
+ * /root/reference/JuliaBUGS).  The reference evaluates ONE theta per call on the CPU; this
+ * library evaluates a batch of C parameter vectors (HMC chains) per launch.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative jbugs_status; nothing throws across the ABI;
+ *     jbugs_last_error() returns a thread-local message for the last failure.
+ *   - plain pointers and sizes only.  `theta`, `grad`, `logp`, `status` may be HOST or DEVICE
+ *     pointers (detected with cudaPointerGetAttributes).  Host buffers are copied through
+ *     library-owned staging inside the call; device buffers are used in place.
+ *   - the library owns the device copies of the model data, and (jbugs_batch_alloc) the theta /
+ *     gradient batch.  Caller-owned memory is only read/written during a call.
+ *   - a plan handle is not thread-safe; distinct handles are.
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point fails
+ *     with JBUGS_ERR_CUDA.
+ */
+#ifndef JBUGS_CUDA_H
+#define JBUGS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "jbugs_plan.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jbugs_plan_s jbugs_plan;
+
+enum jbugs_status {
+    JBUGS_OK = 0,
+    JBUGS_ERR_INVALID = -1,     /* malformed plan / bad argument            */
+    JBUGS_ERR_UNSUPPORTED = -2, /* valid plan the kernels cannot run (yet)  */
+    JBUGS_ERR_CUDA = -3,        /* CUDA runtime failure (incl. "no device") */
+    JBUGS_ERR_NCCL = -4,        /* NCCL failure / libnccl not loadable      */
+    JBUGS_ERR_STATE = -5        /* e.g. data slot not uploaded              */
+};
+
+/* theta/grad batch layouts.  D = jbugs_dim(plan), C = number of chains.
+ *   CHAIN_FAST : element (d, c) at  d * ld + c   (ld >= C)  -- the library's native layout:
+ *                every parameter is a contiguous row over chains (coalesced for any theta order).
+ *   PARAM_FAST : element (d, c) at  c * ld + d   (ld >= D)  -- a Julia `Matrix{Float64}(D, C)`,
+ *                one column per chain, what `logdensity_and_gradient(m, x)` sees for C = 1. */
+enum jbugs_layout { JBUGS_LAYOUT_CHAIN_FAST = 0, JBUGS_LAYOUT_PARAM_FAST = 1 };
+
+/* per-chain status written by jbugs_eval_batch */
+enum jbugs_chain_status {
+    JBUGS_CHAIN_OK = 0,
+    JBUGS_CHAIN_DOMAIN = 1 /* a distribution argument left its domain: logp = -Inf, grad = NaN
+                              (logdensityproblems.jl:22-26, 226-229) */
+};
+
+const char* jbugs_last_error(void);
+int jbugs_version(void);
+
+/* Number of CUDA devices visible (0 on a CPU-only box; never fails). */
+int jbugs_device_count(void);
+
+/* Replaces: set_evaluation_mode(model, mode) building the evaluator state
+ * (src/model/bugsmodel.jl:736-801) from the lowered program (src/source_gen.jl:459-552).
+ * `plan_blob` is the serialized jbugs_plan_header + records (jbugs_plan.h); it is copied. */
+int jbugs_plan_create(const void* plan_blob, size_t nbytes, int device, jbugs_plan** out);
+
+/* Replaces: dropping `log_density_computation_function` on condition/fix/decondition
+ * (src/model/abstractppl.jl:796-799).  Frees every device buffer the plan owns. */
+int jbugs_plan_destroy(jbugs_plan* plan);
+
+/* Replaces: LogDensityProblems.dimension(model) (src/model/logdensityproblems.jl:29-51). */
+int64_t jbugs_dim(const jbugs_plan* plan);
+
+/* Replaces: the `evaluation_env` argument of the generated function (src/source_gen.jl:673-674)
+ * and `set_observed_values!` (src/model/abstractppl.jl:872-888): (re)uploads one data slot.
+ * `src` is a host or device pointer to `nbytes` bytes of float64 (dtype 0) or int64 (dtype 1,
+ * index arrays). */
+int jbugs_plan_upload_data(jbugs_plan* plan, int slot, const void* src, size_t nbytes, int dtype);
+
+/* Observation sharding: this rank owns groups [i0, i1) of plate `plate`; group-local
+ * theta slots outside the range are neither read nor written.  Globals are replicated.  With a
+ * communicator attached (jbugs_comm_init) the per-chain logp and global gradients are summed
+ * over ranks in a fixed order.  Default: the whole plate. */
+int jbugs_plan_set_shard(jbugs_plan* plan, int plate, int64_t i0, int64_t i1);
+
+/* Replaces: LogDensityProblems.logdensity (src/model/logdensityproblems.jl:19-27) and
+ * logdensity_and_gradient (:219-232) -> evaluate_with_values!! (src/model/evaluation.jl:217-275)
+ * plus the AD backend, for C chains at once.
+ *   theta  : D x C batch in `layout` with leading dimension `ld` (read only)
+ *   logp   : C doubles out
+ *   grad   : same layout/ld as theta, out (ignored when want_grad == 0; may be NULL then)
+ *   status : C int32 out (jbugs_chain_status), may be NULL
+ *   stream : cudaStream_t (NULL = default stream).  The call returns after the stream has been
+ *            synchronized unless flags & JBUGS_EVAL_ASYNC and every buffer is a device pointer. */
+#define JBUGS_EVAL_ASYNC 1
+int jbugs_eval_batch(jbugs_plan* plan, const double* theta, int64_t ld, int64_t C, int layout,
+                     double* logp, double* grad, int32_t* status, int want_grad, int flags,
+                     void* stream);
+
+/* Library-owned theta / gradient batch (north_star: "owns the device buffers for data, the theta
+ * batch and the gradients").  Returns device pointers in CHAIN_FAST layout with *ld >= C padded so
+ * that every row is 128-byte aligned. */
+int jbugs_batch_alloc(jbugs_plan* plan, int64_t C, double** theta_dev, double** grad_dev,
+                      double** logp_dev, int32_t** status_dev, int64_t* ld);
+int jbugs_batch_free(jbugs_plan* plan);
+
+/* Pinned host memory for callers that stage from the host (bench e2e path). */
+int jbugs_host_alloc(void** ptr, size_t nbytes);
+int jbugs_host_free(void* ptr);
+
+/* Multi-GPU (one process per GPU).  Replaces: AbstractMCMC MCMCThreads/MCMCDistributed chain
+ * parallelism (docs/src/inference/parallel.md) -- which needs nothing here, chains shard with no
+ * collective -- and adds observation sharding, which needs one all-reduce of C x (1 + G) doubles.
+ * `unique_id` is the 128-byte ncclUniqueId produced by rank 0 with jbugs_comm_unique_id. */
+int jbugs_comm_unique_id(void* unique_id_128);
+int jbugs_comm_init(jbugs_plan* plan, int nranks, int rank, const void* unique_id_128);
+int jbugs_comm_destroy(jbugs_plan* plan);
+
+/* Introspection used by tests/bench: number of kernels launched so far by this plan, and a
+ * human-readable description of the kernel variants selected for each plate. */
+int64_t jbugs_launch_count(const jbugs_plan* plan);
+int jbugs_plan_describe(const jbugs_plan* plan, char* buf, size_t nbuf);
+
+/* Tuning knobs (tests force the generic interpreter path with "dynamic=1"). Unknown keys fail. */
+int jbugs_plan_set_option(jbugs_plan* plan, const char* key, int64_t value);
+
+/* Device-side timing of the last jbugs_eval_batch on this plan: milliseconds spent in the plate
+ * kernels and in total between the first and last enqueue (CUDA events on the call's stream). */
+int jbugs_last_timing(const jbugs_plan* plan, float* plate_ms, float* total_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JBUGS_CUDA_H */

@@ -1,0 +1,203 @@
+"""Example models in BUGS syntax (classic BUGS Vol. 1), written out here as model text.
+
+The numeric fixtures (data, inits) live in `tests/golden/examples_vol1.json`, extracted from the
+reference tree by `tests/golden/make_fixtures.py`.  The reference ships the same models as `@bugs`
+expressions in `JuliaBUGS/src/BUGSExamples/Volume_1/` (`01_Rats.jl:3-19`, `02_Pumps.jl:3-11`,
+`03_Dogs.jl:3-21`, `04_Seeds.jl:3-16`, `05_Surgical.jl:4-9,31-41`, `11_Epil.jl:3-45`,
+`12_Blocker.jl:3-16`, `15_Bones.jl:3-22`).
+"""
+
+RATS = """
+model {
+    for (i in 1:N) {
+        for (j in 1:T) {
+            Y[i, j] ~ dnorm(mu[i, j], tau.c)
+            mu[i, j] <- alpha[i] + beta[i] * (x[j] - xbar)
+        }
+        alpha[i] ~ dnorm(alpha.c, alpha.tau)
+        beta[i] ~ dnorm(beta.c, beta.tau)
+    }
+    tau.c ~ dgamma(0.001, 0.001)
+    sigma <- 1 / sqrt(tau.c)
+    alpha.c ~ dnorm(0.0, 1.0E-6)
+    alpha.tau ~ dgamma(0.001, 0.001)
+    beta.c ~ dnorm(0.0, 1.0E-6)
+    beta.tau ~ dgamma(0.001, 0.001)
+    alpha0 <- alpha.c - xbar * beta.c
+}
+"""
+
+PUMPS = """
+model {
+    for (i in 1:N) {
+        theta[i] ~ dgamma(alpha, beta)
+        lambda[i] <- theta[i] * t[i]
+        x[i] ~ dpois(lambda[i])
+    }
+    alpha ~ dexp(1)
+    beta ~ dgamma(0.1, 1.0)
+}
+"""
+
+DOGS = """
+model {
+    for (i in 1:Dogs) {
+        xa[i, 1] <- 0
+        xs[i, 1] <- 0
+        p[i, 1] <- 0
+        for (j in 2:Trials) {
+            xa[i, j] <- sum(Y[i, 1:(j - 1)])
+            xs[i, j] <- j - 1 - xa[i, j]
+            log(p[i, j]) <- alpha * xa[i, j] + beta * xs[i, j]
+            y[i, j] <- 1 - Y[i, j]
+            y[i, j] ~ dbern(p[i, j])
+        }
+    }
+    alpha ~ dunif(-10, -0.00001)
+    beta ~ dunif(-10, -0.00001)
+    A <- exp(alpha)
+    B <- exp(beta)
+}
+"""
+
+SEEDS = """
+model {
+    for (i in 1:N) {
+        r[i] ~ dbin(p[i], n[i])
+        b[i] ~ dnorm(0.0, tau)
+        logit(p[i]) <- alpha0 + alpha1 * x1[i] + alpha2 * x2[i] + alpha12 * x1[i] * x2[i] + b[i]
+    }
+    alpha0 ~ dnorm(0.0, 1.0E-6)
+    alpha1 ~ dnorm(0.0, 1.0E-6)
+    alpha2 ~ dnorm(0.0, 1.0E-6)
+    alpha12 ~ dnorm(0.0, 1.0E-6)
+    tau ~ dgamma(0.001, 0.001)
+    sigma <- 1 / sqrt(tau)
+}
+"""
+
+SURGICAL_SIMPLE = """
+model {
+    for (i in 1:N) {
+        p[i] ~ dbeta(1.0, 1.0)
+        r[i] ~ dbin(p[i], n[i])
+    }
+}
+"""
+
+SURGICAL_REALISTIC = """
+model {
+    for (i in 1:N) {
+        b[i] ~ dnorm(mu, tau)
+        r[i] ~ dbin(p[i], n[i])
+        logit(p[i]) <- b[i]
+    }
+    pop.mean <- exp(mu) / (1 + exp(mu))
+    mu ~ dnorm(0.0, 1.0E-6)
+    sigma <- 1 / sqrt(tau)
+    tau ~ dgamma(0.001, 0.001)
+}
+"""
+
+EPIL = """
+model {
+    for (j in 1:N) {
+        for (k in 1:T) {
+            log(mu[j, k]) <- a0 + alpha.Base * (log.Base4[j] - log.Base4.bar)
+                + alpha.Trt * (Trt[j] - Trt.bar)
+                + alpha.BT * (BT[j] - BT.bar)
+                + alpha.Age * (log.Age[j] - log.Age.bar)
+                + alpha.V4 * (V4[k] - V4.bar) + b1[j] + b[j, k]
+            y[j, k] ~ dpois(mu[j, k])
+            b[j, k] ~ dnorm(0.0, tau.b)
+        }
+        b1[j] ~ dnorm(0.0, tau.b1)
+        BT[j] <- Trt[j] * log.Base4[j]
+        log.Base4[j] <- log(Base[j] / 4)
+        log.Age[j] <- log(Age[j])
+    }
+    log.Age.bar <- mean(log.Age[])
+    Trt.bar <- mean(Trt[])
+    BT.bar <- mean(BT[])
+    log.Base4.bar <- mean(log.Base4[])
+    V4.bar <- mean(V4[])
+    a0 ~ dnorm(0.0, 1.0E-4)
+    alpha.Base ~ dnorm(0.0, 1.0E-4)
+    alpha.Trt ~ dnorm(0.0, 1.0E-4)
+    alpha.BT ~ dnorm(0.0, 1.0E-4)
+    alpha.Age ~ dnorm(0.0, 1.0E-4)
+    alpha.V4 ~ dnorm(0.0, 1.0E-4)
+    tau.b1 ~ dgamma(1.0E-3, 1.0E-3)
+    sigma.b1 <- 1.0 / sqrt(tau.b1)
+    tau.b ~ dgamma(1.0E-3, 1.0E-3)
+    sigma.b <- 1.0 / sqrt(tau.b)
+    alpha0 <- a0 - alpha.Base * log.Base4.bar - alpha.Trt * Trt.bar - alpha.BT * BT.bar
+        - alpha.Age * log.Age.bar - alpha.V4 * V4.bar
+}
+"""
+
+BLOCKERS = """
+model {
+    for (i in 1:Num) {
+        rc[i] ~ dbin(pc[i], nc[i])
+        rt[i] ~ dbin(pt[i], nt[i])
+        logit(pc[i]) <- mu[i]
+        logit(pt[i]) <- mu[i] + delta[i]
+        mu[i] ~ dnorm(0.0, 1.0E-5)
+        delta[i] ~ dnorm(d, tau)
+    }
+    d ~ dnorm(0.0, 1.0E-6)
+    tau ~ dgamma(0.001, 0.001)
+    delta.new ~ dnorm(d, tau)
+    sigma <- 1 / sqrt(tau)
+}
+"""
+
+BONES = """
+model {
+    for (i in 1:nChild) {
+        theta[i] ~ dnorm(0.0, 0.001)
+        for (j in 1:nInd) {
+            for (k in 1:ncat[j] - 1) {
+                logit(Q[i, j, k]) <- delta[j] * (theta[i] - gamma[j, k])
+            }
+        }
+        for (j in 1:nInd) {
+            p[i, j, 1] <- 1 - Q[i, j, 1]
+            for (k in 2:ncat[j] - 1) {
+                p[i, j, k] <- Q[i, j, k - 1] - Q[i, j, k]
+            }
+            p[i, j, ncat[j]] <- Q[i, j, ncat[j] - 1]
+            grade[i, j] ~ dcat(p[i, j, 1:ncat[j]])
+        }
+    }
+}
+"""
+
+# Dense hierarchical logistic regression (BASELINE.json config 4): inprod -> GEMM path
+DENSE_LOGISTIC = """
+model {
+    for (i in 1:N) {
+        y[i] ~ dbern(p[i])
+        logit(p[i]) <- inprod(X[i, 1:P], beta[1:P])
+    }
+    for (j in 1:P) {
+        beta[j] ~ dnorm(mu.b, tau.b)
+    }
+    mu.b ~ dnorm(0.0, 1.0E-6)
+    tau.b ~ dgamma(0.001, 0.001)
+}
+"""
+
+MODELS = {
+    "rats": RATS,
+    "pumps": PUMPS,
+    "dogs": DOGS,
+    "seeds": SEEDS,
+    "surgical_simple": SURGICAL_SIMPLE,
+    "surgical_realistic": SURGICAL_REALISTIC,
+    "epil": EPIL,
+    "blockers": BLOCKERS,
+    "bones": BONES,
+    "dense_logistic": DENSE_LOGISTIC,
+}

@@ -1,0 +1,853 @@
+"""Plate-level lowering: BUGS program + data -> flat kernel plan (`plan.Plan`).
+
+This is the new compiler pass the north star asks for.  It works at STATEMENT granularity --
+never one vertex per scalar node, which is what makes the reference's `compile` unusable at
+10^6 groups (`JuliaBUGS/src/compiler_pass.jl:29-36` unrolls every loop) -- and mirrors the passes
+of the reference's own generated-function lowering:
+
+  * transformed-data folding to a fixpoint   JuliaBUGS/src/compiler_pass.jl:497-547, JuliaBUGS.jl:175-187
+  * statement ids / coarse statement graph   JuliaBUGS/src/source_gen.jl:5-20, 110-127
+  * full loop fission, DFS topological sort of statements, regrouping of consecutive
+    statements with identical loop nests     JuliaBUGS/src/source_gen.jl:160-223
+  * per-statement observed / parameter / generated-quantity classes
+                                             JuliaBUGS/src/source_gen.jl:615-666, graphs.jl:27-71
+  * theta layout = program order of the reconstructed program
+                                             JuliaBUGS/src/model/bugsmodel.jl:770-799
+  * link rewrite / logical-parent inlining   JuliaBUGS/src/parser/bugs_macro.jl:159-182,
+                                             JuliaBUGS/src/compiler_pass.jl:751-814
+
+What it adds: each observed stochastic statement is matched, together with its inlined logical
+parents, to a *plate* (linear predictor term tape + inverse-link tape + family + local priors)
+that one fused forward+reverse CUDA kernel evaluates for a whole batch of chains.
+
+Models outside the supported class raise `LoweringError` -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import plan as P
+from .parser import BinOp, Call, Colon, Det, For, Index, Neg, Num, Range, Stoch, Var, free_vars, parse
+
+
+class LoweringError(NotImplementedError):
+    """The model is valid BUGS but outside the plate class the CUDA path evaluates."""
+
+
+# ----------------------------------------------------------------------------- statements
+
+
+@dataclass
+class Stmt:
+    sid: int                       # 1-based statement id in program order (source_gen.jl:5-20)
+    node: object                   # Stoch | Det
+    loops: Tuple[Tuple[str, object, object], ...]  # (var, lo_expr, hi_expr) outermost first
+    extents: Tuple[Tuple[int, int], ...] = ()      # evaluated (lo, hi)
+    kind: str = ""                 # 'tdata' | 'obs' | 'param' | 'logical'
+    is_gq: bool = False
+
+    @property
+    def name(self):
+        return self.node.lhs.name
+
+    @property
+    def loop_vars(self):
+        return tuple(l[0] for l in self.loops)
+
+    @property
+    def shape(self):
+        return tuple(hi - lo + 1 for lo, hi in self.extents)
+
+    @property
+    def size(self):
+        n = 1
+        for s in self.shape:
+            n *= s
+        return n
+
+
+def _flatten(stmts, loops=(), out=None):
+    if out is None:
+        out = []
+    for s in stmts:
+        if isinstance(s, For):
+            _flatten(s.body, loops + ((s.var, s.lo, s.hi),), out)
+        else:
+            out.append(Stmt(len(out) + 1, s, loops))
+    return out
+
+
+# ----------------------------------------------------------------------------- vectorised evaluation
+
+_NP_FUNCS = {
+    "exp": np.exp, "log": np.log, "sqrt": np.sqrt, "abs": np.abs, "sin": np.sin, "cos": np.cos,
+    "logistic": lambda x: 1.0 / (1.0 + np.exp(-x)), "ilogit": lambda x: 1.0 / (1.0 + np.exp(-x)),
+    "logit": lambda x: np.log(x / (1.0 - x)),
+    "cexpexp": lambda x: -np.expm1(-np.exp(x)), "icloglog": lambda x: -np.expm1(-np.exp(x)),
+    "cloglog": lambda x: np.log(-np.log1p(-x)),
+    "step": lambda x: (np.asarray(x) >= 0).astype(float),
+}
+
+
+class DataEval:
+    """Evaluate a data-only expression for every point of a loop domain at once (numpy
+    broadcasting); loop variables are integer index grids."""
+
+    def __init__(self, data: Dict[str, object]):
+        self.data = data
+
+    def known(self, e, loop_vars=()) -> bool:
+        return all((v in self.data) or (v in loop_vars) for v in free_vars(e))
+
+    def ev(self, e, lv: Dict[str, np.ndarray]):
+        if isinstance(e, Num):
+            return e.value
+        if isinstance(e, Var):
+            if e.name in lv:
+                return lv[e.name]
+            return self.data[e.name]
+        if isinstance(e, Neg):
+            return -self.ev(e.a, lv)
+        if isinstance(e, BinOp):
+            a, b = self.ev(e.a, lv), self.ev(e.b, lv)
+            if e.op == "+":
+                return a + b
+            if e.op == "-":
+                return a - b
+            if e.op == "*":
+                return a * b
+            if e.op == "/":
+                return a / b
+            if e.op == "^":
+                return a ** b
+        if isinstance(e, Index):
+            arr = np.asarray(self.data[e.name])
+            idx = []
+            for ie in e.idx:
+                if isinstance(ie, Colon):
+                    idx.append(slice(None))
+                elif isinstance(ie, Range):
+                    lo, hi = self.ev(ie.lo, lv), self.ev(ie.hi, lv)
+                    if np.ndim(lo) or np.ndim(hi):
+                        raise LoweringError("loop-dependent index range in a data expression")
+                    idx.append(slice(int(lo) - 1, int(hi)))
+                else:
+                    v = self.ev(ie, lv)
+                    iv = np.asarray(v)
+                    if not np.all(iv == np.floor(iv)):
+                        raise LoweringError("non-integer array index")
+                    idx.append(iv.astype(np.int64) - 1 if iv.ndim else int(iv) - 1)
+            return arr[tuple(idx)]
+        if isinstance(e, Call):
+            args = [self.ev(a, lv) for a in e.args]
+            if e.fn in _NP_FUNCS:
+                return _NP_FUNCS[e.fn](*args)
+            if e.fn == "pow":
+                return args[0] ** args[1]
+            if e.fn == "mean":
+                return float(np.mean(args[0]))
+            if e.fn == "sum":
+                return float(np.sum(args[0]))
+            if e.fn == "sd":
+                return float(np.std(args[0], ddof=1))
+            if e.fn == "inprod":
+                return float(np.dot(np.ravel(args[0]), np.ravel(args[1])))
+            if e.fn == "max":
+                return np.maximum(args[0], args[1])
+            if e.fn == "min":
+                return np.minimum(args[0], args[1])
+            if e.fn == "equals":
+                return (np.asarray(args[0]) == np.asarray(args[1])).astype(float)
+            if e.fn == "phi":
+                from math import erfc, sqrt
+                return np.vectorize(lambda v: 0.5 * erfc(-v / sqrt(2.0)))(args[0])
+            if e.fn == "loggam":
+                return np.vectorize(math.lgamma)(args[0])
+            if e.fn == "logfact":
+                return np.vectorize(lambda v: math.lgamma(v + 1.0))(args[0])
+            raise LoweringError(f"function {e.fn} is not supported in data expressions")
+        raise LoweringError(f"cannot evaluate {e!r}")
+
+
+def _grids(extents, names):
+    """integer index grids, one per loop variable, broadcastable to the loop domain shape."""
+    lv = {}
+    nd = len(extents)
+    for d, ((lo, hi), nm) in enumerate(zip(extents, names)):
+        shp = [1] * nd
+        shp[d] = hi - lo + 1
+        lv[nm] = np.arange(lo, hi + 1, dtype=np.int64).reshape(shp)
+    return lv
+
+
+# ----------------------------------------------------------------------------- linear predictor
+
+
+class _Lin:
+    """const + sum_k coef_k * cov_k with symbolic (data-only) const / cov expressions."""
+
+    def __init__(self, const=None, terms=None):
+        self.const = const            # Expr | None (None == 0)
+        self.terms = terms or {}      # ref -> cov Expr ; ref = ('g', name) | ('l', name, idx exprs)
+
+    @staticmethod
+    def _add(a, b):
+        if a is None:
+            return b
+        if b is None:
+            return a
+        return BinOp("+", a, b)
+
+    def add(self, o, sign=1):
+        r = _Lin(self.const, dict(self.terms))
+        oc = o.const if sign > 0 or o.const is None else Neg(o.const)
+        r.const = self._add(r.const, oc)
+        for k, v in o.terms.items():
+            v2 = v if sign > 0 else Neg(v)
+            r.terms[k] = self._add(r.terms.get(k), v2)
+        return r
+
+    def scale(self, c, divide=False):
+        f = (lambda x: BinOp("/", x, c)) if divide else (lambda x: BinOp("*", x, c))
+        return _Lin(None if self.const is None else f(self.const), {k: f(v) for k, v in self.terms.items()})
+
+
+ONE = Num(1.0)
+
+
+# ----------------------------------------------------------------------------- the pass
+
+
+class Lowering:
+    def __init__(self, model_text, data, transformed=True, theta_order=None):
+        self.stmts_ast = parse(model_text) if isinstance(model_text, str) else tuple(model_text)
+        self.transformed = transformed
+        self.data: Dict[str, object] = {}
+        for k, v in data.items():
+            if isinstance(v, (list, tuple)):
+                v = np.asarray(v, dtype=np.float64)
+            if isinstance(v, np.ndarray):
+                v = np.asarray(v, dtype=np.float64)
+            else:
+                v = float(v)
+            self.data[k] = v
+        self.de = DataEval(self.data)
+        self.stmts: List[Stmt] = _flatten(self.stmts_ast)
+        self.theta_order = theta_order
+        self._bounds()
+        self._fold_transformed_data()
+        self._classify()
+        self._order_parameters()
+        self._build_plan()
+
+    # ---- A. loop bounds ----------------------------------------------------------------------
+    def _bounds(self):
+        for s in self.stmts:
+            ext = []
+            for (var, lo, hi) in s.loops:
+                if not (self.de.known(lo) and self.de.known(hi)):
+                    raise LoweringError(f"loop bounds of '{var}' must depend on data only (rectangular plates)")
+                ext.append((int(self.de.ev(lo, {})), int(self.de.ev(hi, {}))))
+            s.extents = tuple(ext)
+
+    # ---- C. transformed data ------------------------------------------------------------------
+    def _lhs_loopvars(self, s: Stmt):
+        """LHS must be `name` or `name[v1, v2, ...]` with the statement's loop variables (any order)
+        or data-only index expressions."""
+        lhs = s.node.lhs
+        if isinstance(lhs, Var):
+            return ()
+        return lhs.idx
+
+    def _fold_transformed_data(self):
+        changed = True
+        while changed:
+            changed = False
+            for s in self.stmts:
+                if s.kind or not isinstance(s.node, Det):
+                    continue
+                if any(hi < lo for lo, hi in s.extents):
+                    s.kind = "tdata"
+                    continue
+                if not self.de.known(s.node.rhs, s.loop_vars):
+                    continue
+                lhs = s.node.lhs
+                lv = _grids(s.extents, s.loop_vars)
+                try:
+                    val = self.de.ev(s.node.rhs, lv)
+                except LoweringError:
+                    val = self._fold_pointwise(s)
+                if isinstance(lhs, Var):
+                    self.data[lhs.name] = float(val)
+                else:
+                    idx = [np.asarray(self.de.ev(ie, lv)).astype(np.int64) for ie in lhs.idx]
+                    shp = np.broadcast_shapes(*[i.shape for i in idx], np.shape(val))
+                    idx = [np.broadcast_to(i, shp) for i in idx]
+                    top = tuple(int(i.max()) for i in idx)
+                    cur = self.data.get(lhs.name)
+                    if cur is None or not isinstance(cur, np.ndarray):
+                        cur = np.full(top, np.nan)
+                    elif any(c < t for c, t in zip(cur.shape, top)):
+                        new = np.full(tuple(max(c, t) for c, t in zip(cur.shape, top)), np.nan)
+                        new[tuple(slice(0, c) for c in cur.shape)] = cur
+                        cur = new
+                    cur[tuple(i - 1 for i in idx)] = np.broadcast_to(val, shp)
+                    self.data[lhs.name] = cur
+                s.kind = "tdata"
+                changed = True
+
+    def _fold_pointwise(self, s: Stmt):
+        """slow path for data expressions with loop-dependent slices (e.g. running sums)."""
+        if s.size > 200000:
+            raise LoweringError("loop-dependent slice in a large transformed-data statement")
+        out = np.empty(s.shape)
+        for pos in np.ndindex(*s.shape):
+            lv = {nm: np.int64(lo + p) for nm, (lo, _), p in zip(s.loop_vars, s.extents, pos)}
+            out[pos] = self.de.ev(s.node.rhs, lv)
+        return out
+
+    # ---- D. classification -----------------------------------------------------------------------
+    def _defs(self, name):
+        return [s for s in self.stmts if s.name == name and s.kind != "tdata"]
+
+    def _classify(self):
+        for s in self.stmts:
+            if s.kind:
+                continue
+            if isinstance(s.node, Det):
+                s.kind = "logical"
+                continue
+            nm = s.name
+            if nm in self.data:
+                arr = self.data[nm]
+                if isinstance(arr, np.ndarray):
+                    lv = _grids(s.extents, s.loop_vars)
+                    lhs = s.node.lhs
+                    sub = arr if isinstance(lhs, Var) else self.de.ev(lhs, lv)
+                    miss = np.isnan(sub)
+                    if miss.all():
+                        s.kind = "param"
+                    elif miss.any():
+                        raise LoweringError(
+                            f"'{nm}' is partially observed: mixed observation/parameter statements "
+                            "are outside the plate class")
+                    else:
+                        s.kind = "obs"
+                else:
+                    s.kind = "param" if math.isnan(arr) else "obs"
+            else:
+                s.kind = "param"
+        # statement-level dependence edges: parent statement -> child statement
+        self.children: Dict[int, set] = {s.sid: set() for s in self.stmts}
+        by_name: Dict[str, List[Stmt]] = {}
+        for s in self.stmts:
+            if s.kind in ("param", "logical"):
+                by_name.setdefault(s.name, []).append(s)
+        for s in self.stmts:
+            if s.kind == "tdata":
+                continue
+            rhs = s.node.rhs if isinstance(s.node, Det) else s.node.dist
+            for v in free_vars(rhs):
+                for parent in by_name.get(v, []):
+                    if parent.sid != s.sid:
+                        self.children[parent.sid].add(s.sid)
+                    elif s.kind in ("param", "logical"):
+                        raise LoweringError(f"loop-carried self dependence in statement {s.sid} ({s.name})")
+        # generated quantities: statements from which no observation is reachable (graphs.jl:27-71)
+        memo: Dict[int, bool] = {}
+        by_sid = {s.sid: s for s in self.stmts}
+
+        def reach(sid):
+            if sid in memo:
+                return memo[sid]
+            memo[sid] = False
+            r = by_sid[sid].kind == "obs" or any(reach(c) for c in sorted(self.children[sid]))
+            memo[sid] = r
+            return r
+
+        has_obs = any(s.kind == "obs" for s in self.stmts)
+        for s in self.stmts:
+            if s.kind in ("param", "logical"):
+                s.is_gq = not reach(s.sid)
+        if not has_obs:
+            # bugsmodel.jl:181-199: without observations stochastic nodes stay parameters
+            for s in self.stmts:
+                if s.kind == "param":
+                    s.is_gq = False
+                elif s.kind == "logical":
+                    s.is_gq = not any(by_sid[c].kind == "param" or not by_sid[c].is_gq
+                                      for c in self.children[s.sid])
+
+    # ---- E. parameter order -----------------------------------------------------------------------
+    @staticmethod
+    def _toposort(out, n):
+        color = [0] * n
+        verts = []
+        for v in range(n):
+            if color[v]:
+                continue
+            stack = [v]
+            color[v] = 1
+            while stack:
+                u = stack[-1]
+                w = -1
+                for x in out[u]:
+                    if color[x] == 1:
+                        raise LoweringError("cyclic statement dependence: needs loop fusion, outside the plate class")
+                    if color[x] == 0:
+                        w = x
+                        break
+                if w >= 0:
+                    color[w] = 1
+                    stack.append(w)
+                else:
+                    color[u] = 2
+                    verts.append(u)
+                    stack.pop()
+        return verts[::-1]
+
+    def _order_parameters(self):
+        n = len(self.stmts)
+        out = [sorted(c - 1 for c in self.children[s.sid]) for s in self.stmts]
+        topo = self._toposort(out, n)
+        self.stmt_order = [self.stmts[k] for k in topo if self.stmts[k].kind != "tdata"]
+        # regroup consecutive statements with identical loop nests (source_gen.jl:192-223)
+        groups: List[Tuple[tuple, List[Stmt]]] = []
+        for s in self.stmt_order:
+            if groups and groups[-1][0] == s.loops:
+                groups[-1][1].append(s)
+            else:
+                groups.append((s.loops, [s]))
+        self.groups = groups
+        # theta slots: program order of the reconstructed program, parameters only
+        self.theta_map: Dict[int, Tuple[int, Tuple[int, ...]]] = {}  # sid -> (base, strides per loop)
+        base = 0
+        for loops, body in groups:
+            params = [s for s in body if s.kind == "param" and not s.is_gq]
+            m = len(params)
+            if m == 0:
+                continue
+            shape = body[0].shape
+            size = body[0].size
+            strides = []
+            acc = m
+            for d in range(len(shape) - 1, -1, -1):
+                strides.append(acc)
+                acc *= shape[d]
+            strides = tuple(reversed(strides))
+            for q, s in enumerate(params):
+                self.theta_map[s.sid] = (base + q, strides)
+            base += m * size
+        self.D = base
+
+    # ---- labels ----------------------------------------------------------------------------------------
+    def _labels_for(self, s: Stmt):
+        """variable labels of a parameter statement's instances in iteration order (small models only)."""
+        lhs = s.node.lhs
+        if isinstance(lhs, Var):
+            return [lhs.name]
+        lv = _grids(s.extents, s.loop_vars)
+        idx = [np.broadcast_to(np.asarray(self.de.ev(ie, lv)), s.shape).ravel() for ie in lhs.idx]
+        return [f"{lhs.name}[{','.join(str(int(i[k])) for i in idx)}]" for k in range(s.size)]
+
+    def param_names(self, limit=2_000_000):
+        if self.D > limit:
+            raise LoweringError("param_names on a very large model")
+        names = [None] * self.D
+        for s in self.stmts:
+            if s.sid not in self.theta_map:
+                continue
+            idx = self.theta_index(s).ravel()
+            for lab, t in zip(self._labels_for(s), idx):
+                names[int(t)] = lab
+        return names
+
+    def theta_index(self, s: Stmt) -> np.ndarray:
+        """theta slot of every instance of parameter statement `s` (array over its loop domain)."""
+        if self.theta_order is not None:
+            return self._theta_index_custom(s)
+        base, strides = self.theta_map[s.sid]
+        idx = np.full(s.shape if s.shape else (), base, dtype=np.int64)
+        for d, st in enumerate(strides):
+            shp = [1] * len(s.shape)
+            shp[d] = s.shape[d]
+            idx = idx + (np.arange(s.shape[d], dtype=np.int64) * st).reshape(shp)
+        return idx
+
+    def _theta_index_custom(self, s: Stmt):
+        pos = {lab: k for k, lab in enumerate(self.theta_order)}
+        labs = self._labels_for(s)
+        try:
+            return np.asarray([pos[l] for l in labs], dtype=np.int64).reshape(s.shape if s.shape else ())
+        except KeyError as e:
+            raise LoweringError(f"theta_order lacks parameter {e}") from None
+
+    # ---- F/G. plan construction ---------------------------------------------------------------------------
+    def _slot(self, key, values, rank=1, dim0=0):
+        if key in self._slot_ids:
+            return self._slot_ids[key]
+        vals = np.ascontiguousarray(values)
+        self.plan.data.append(P.DataSlot(key, vals, dim0=dim0, rank=rank))
+        self._slot_ids[key] = len(self.plan.data) - 1
+        return self._slot_ids[key]
+
+    def _inline(self, e, depth=0):
+        """substitute references to logical (deterministic) variables by their rhs
+        (the node functions of compiler_pass.jl:751-814 composed along the parent chain)."""
+        if depth > 32:
+            raise LoweringError("logical nodes nest too deeply")
+        if isinstance(e, (Num, Colon)):
+            return e
+        if isinstance(e, Var):
+            if e.name in self._gval_ids:
+                return e  # scalar logical node of globals: lives on the gtape, referenced by slot
+            defs = [s for s in self._defs(e.name) if s.kind == "logical"]
+            if defs:
+                if len(defs) != 1 or defs[0].loops:
+                    raise LoweringError(f"cannot inline '{e.name}'")
+                return self._inline(defs[0].node.rhs, depth + 1)
+            return e
+        if isinstance(e, Index):
+            idx = tuple(self._inline(i, depth + 1) for i in e.idx)
+            defs = [s for s in self._defs(e.name) if s.kind == "logical"]
+            if defs:
+                if len(defs) != 1:
+                    raise LoweringError(f"'{e.name}' is defined by several statements")
+                d = defs[0]
+                lhs = d.node.lhs
+                sub = {}
+                for li, ri in zip(lhs.idx, idx):
+                    if not isinstance(li, Var) or li.name not in d.loop_vars:
+                        raise LoweringError(f"lhs index of logical '{e.name}' must be a loop variable")
+                    sub[li.name] = ri
+                return self._inline(_subst(d.node.rhs, sub), depth + 1)
+            return Index(e.name, idx)
+        if isinstance(e, Neg):
+            return Neg(self._inline(e.a, depth))
+        if isinstance(e, BinOp):
+            return BinOp(e.op, self._inline(e.a, depth), self._inline(e.b, depth))
+        if isinstance(e, Call):
+            return Call(e.fn, tuple(self._inline(a, depth) for a in e.args))
+        if isinstance(e, Range):
+            return Range(self._inline(e.lo, depth), self._inline(e.hi, depth))
+        raise LoweringError(f"cannot inline {e!r}")
+
+    def _is_data(self, e, loop_vars):
+        return self.de.known(e, loop_vars)
+
+    def _linearize(self, e, loop_vars) -> _Lin:
+        if self._is_data(e, loop_vars):
+            return _Lin(const=e)
+        if isinstance(e, Var):
+            return _Lin(terms={("g", e.name): ONE})
+        if isinstance(e, Index):
+            return _Lin(terms={("l", e.name, e.idx): ONE})
+        if isinstance(e, Neg):
+            z = self._linearize(e.a, loop_vars)
+            return _Lin().add(z, -1)
+        if isinstance(e, BinOp):
+            if e.op in "+-":
+                a, b = self._linearize(e.a, loop_vars), self._linearize(e.b, loop_vars)
+                return a.add(b, 1 if e.op == "+" else -1)
+            if e.op == "*":
+                if self._is_data(e.a, loop_vars):
+                    return self._linearize(e.b, loop_vars).scale(e.a)
+                if self._is_data(e.b, loop_vars):
+                    return self._linearize(e.a, loop_vars).scale(e.b)
+                # (param * data) * data style products: try to move data factors together
+                a, b = self._linearize(e.a, loop_vars), self._linearize(e.b, loop_vars)
+                raise LoweringError("the linear predictor is not linear in the parameters")
+            if e.op == "/" and self._is_data(e.b, loop_vars):
+                return self._linearize(e.a, loop_vars).scale(e.b, divide=True)
+        raise LoweringError(f"unsupported expression in a linear predictor: {e!r}")
+
+    def _gval_of(self, name) -> int:
+        if name in self._gval_ids:
+            return self._gval_ids[name]
+        raise LoweringError(f"'{name}' is not a scalar parameter or scalar logical node")
+
+    def _scalar_arg(self, e, loop_vars, shape, lv_names) -> P.Arg:
+        """prior / aux argument: CONST | GVAL | data array indexed by the plate's loop variables."""
+        e = e if self._is_data(e, loop_vars) else self._inline_scalar_logical(e)
+        if self._is_data(e, loop_vars):
+            return self._data_arg(e, loop_vars, shape, lv_names)
+        if isinstance(e, Var) and e.name in self._gval_ids:
+            return P.Arg.gval(self._gval_ids[e.name])
+        raise LoweringError(f"distribution argument {e!r} must be a constant, data, or a scalar parameter")
+
+    def _inline_scalar_logical(self, e):
+        return e
+
+    def _data_arg(self, e, loop_vars, shape, lv_names) -> P.Arg:
+        used = [v for v in free_vars(e) if v in loop_vars]
+        if not used:
+            v = float(self.de.ev(e, {}))
+            return P.Arg.one() if v == 1.0 and isinstance(e, Num) else P.Arg.const(v)
+        ext = self._cur_extents
+        lv = _grids(ext, lv_names)
+        key = f"{_show(e)}|{lv_names}|{ext}"
+        if len(lv_names) == 1:
+            vals = np.broadcast_to(self.de.ev(e, lv), shape).astype(np.float64).ravel()
+            return P.Arg(P.ARG_DATA_I, self._slot(key, vals))
+        i_name, j_name = lv_names
+        if j_name not in used:
+            vals = np.broadcast_to(self.de.ev(e, {i_name: lv[i_name].ravel()}), (shape[0],)).astype(np.float64)
+            return P.Arg(P.ARG_DATA_I, self._slot(key + "|I", vals))
+        if i_name not in used:
+            vals = np.broadcast_to(self.de.ev(e, {j_name: lv[j_name].ravel()}), (shape[1],)).astype(np.float64)
+            return P.Arg(P.ARG_DATA_J, self._slot(key + "|J", vals))
+        vals = np.broadcast_to(self.de.ev(e, lv), shape).astype(np.float64)
+        return P.Arg(P.ARG_DATA_IJ, self._slot(key + "|IJ", np.asfortranarray(vals).ravel(order="F"),
+                                               rank=2, dim0=shape[0]))
+
+    def _transform_of(self, fam, args_expr):
+        """Bijectors.bijector(dist): support-based (identity when the model is untransformed)."""
+        lb, ub = -np.inf, np.inf
+        if fam in (P.FAM_GAMMA, P.FAM_EXPONENTIAL, P.FAM_LOGNORMAL):
+            lb = 0.0
+        elif fam == P.FAM_BETA:
+            lb, ub = 0.0, 1.0
+        elif fam == P.FAM_UNIFORM:
+            a, b = args_expr
+            if not (self._is_data(a, ()) and self._is_data(b, ())):
+                raise LoweringError("dunif bounds must be constants")
+            lb, ub = float(self.de.ev(a, {})), float(self.de.ev(b, {}))
+        if not self.transformed or fam in P.DISCRETE:
+            return P.TR_IDENTITY, lb, ub
+        if math.isfinite(lb) and math.isfinite(ub):
+            return P.TR_LOGIT, lb, ub
+        if math.isfinite(lb):
+            return P.TR_LOG, lb, ub
+        return P.TR_IDENTITY, lb, ub
+
+    def _family(self, call: Call):
+        if call.fn not in P.FAMILY_OF:
+            raise LoweringError(f"distribution {call.fn} is outside the supported univariate families")
+        fam = P.FAMILY_OF[call.fn]
+        if len(call.args) != P.FAMILY_NARGS[fam]:
+            raise LoweringError(f"{call.fn} expects {P.FAMILY_NARGS[fam]} arguments")
+        return fam
+
+    def _build_plan(self):
+        self.plan = P.Plan(D=self.D, transformed=self.transformed)
+        self._slot_ids: Dict[str, int] = {}
+        self._gval_ids: Dict[str, int] = {}
+        self._cur_extents = ()
+        by_sid = {s.sid: s for s in self.stmts}
+        # ---- globals, in statement order (parents first thanks to the topological order)
+        scalar_params = [s for s in self.stmt_order if s.kind == "param" and not s.is_gq and not s.loops]
+        scalar_logicals = [s for s in self.stmt_order if s.kind == "logical" and not s.is_gq and not s.loops]
+        for s in scalar_params:
+            self._gval_ids[s.name] = len(self._gval_ids)
+        # scalar logical nodes of globals -> gtape (appended after the globals)
+        self._gtape_pending = scalar_logicals
+        for s in scalar_params:
+            fam = self._family(s.node.dist)
+            tr, lb, ub = self._transform_of(fam, s.node.dist.args)
+            self.plan.globals.append(P.Global(s.name, int(self.theta_index(s)), tr, fam, [], lb, ub))
+        for s in scalar_logicals:
+            self._emit_gtape(s.name, s.node.rhs)
+        for g, s in zip(self.plan.globals, scalar_params):
+            g.args = [self._scalar_arg(a, (), (), ()) for a in s.node.dist.args]
+        # ---- plates: one per observed stochastic statement
+        used_locals = set()
+        for s in self.stmt_order:
+            if s.kind == "obs":
+                self.plan.plates.append(self._build_plate(s, used_locals))
+        # parameter statements in loops that no observation plate consumed -> prior-only plates
+        for s in self.stmt_order:
+            if s.kind == "param" and not s.is_gq and s.loops and s.sid not in used_locals:
+                raise LoweringError(
+                    f"parameter '{s.name}' is not a direct parent of an observation plate "
+                    "(latent-only layers are outside the plate class)")
+        self.plan.param_names = None
+
+    # ---- gtape ---------------------------------------------------------------------------------------------
+    def _emit_gtape(self, name, e):
+        a = self._gexpr(e)
+        if a.kind != P.ARG_GVAL or a.id < len(self.plan.globals):
+            # alias / constant: materialise through an identity op so the name has its own slot
+            self.plan.gtape.append(P.GOp(P.OP_IDENTITY, a, name=name))
+            a = P.Arg.gval(len(self.plan.globals) + len(self.plan.gtape) - 1)
+        self._gval_ids[name] = a.id
+
+    def _gpush(self, op, a, b=P.ZERO_ARG):
+        self.plan.gtape.append(P.GOp(op, a, b))
+        return P.Arg.gval(len(self.plan.globals) + len(self.plan.gtape) - 1)
+
+    def _gexpr(self, e) -> P.Arg:
+        if self._is_data(e, ()):
+            return P.Arg.const(float(self.de.ev(e, {})))
+        if isinstance(e, Var):
+            return P.Arg.gval(self._gval_of(e.name))
+        if isinstance(e, Neg):
+            return self._gpush(P.OP_NEG, self._gexpr(e.a))
+        if isinstance(e, BinOp):
+            op = {"+": P.OP_ADD, "-": P.OP_SUB, "*": P.OP_MUL, "/": P.OP_DIV, "^": P.OP_POW}[e.op]
+            return self._gpush(op, self._gexpr(e.a), self._gexpr(e.b))
+        if isinstance(e, Call):
+            if e.fn == "pow":
+                return self._gpush(P.OP_POW, self._gexpr(e.args[0]), self._gexpr(e.args[1]))
+            if e.fn in P.UNARY_OF and len(e.args) == 1:
+                return self._gpush(P.UNARY_OF[e.fn], self._gexpr(e.args[0]))
+        raise LoweringError(f"unsupported scalar logical expression {e!r}")
+
+    # ---- one plate ----------------------------------------------------------------------------------------------
+    def _build_plate(self, s: Stmt, used_locals) -> P.Plate:
+        if len(s.loops) > 2:
+            raise LoweringError("observation plates deeper than two loops are outside the plate class")
+        lv_names = s.loop_vars
+        shape = s.shape
+        self._cur_extents = s.extents
+        N = shape[0] if shape else 1
+        T = shape[1] if len(shape) == 2 else 1
+        fam = self._family(s.node.dist)
+        eta_arg = {P.FAM_GAMMA: 1}.get(fam, 0)
+        if fam in (P.FAM_UNIFORM, P.FAM_BETA, P.FAM_FLAT):
+            raise LoweringError(f"{s.node.dist.fn} as an observation family is outside the plate class")
+        plate = P.Plate(N=N, T=T, family=fam, eta_arg=eta_arg, name=f"{s.name}~{s.node.dist.fn}")
+        # y
+        lhs = s.node.lhs
+        yarg = self._data_arg(lhs if isinstance(lhs, Index) else Var(lhs.name), lv_names, shape, lv_names) \
+            if shape else P.Arg.const(float(self.data[lhs.name]))
+        if yarg.kind == P.ARG_CONST and shape:
+            raise LoweringError("observation does not vary over its plate")
+        plate.y = yarg
+        # link tape + linear predictor
+        args = [self._inline(a) for a in s.node.dist.args]
+        eta = args[eta_arg]
+        link = []
+        while isinstance(eta, Call) and eta.fn in P.LINK_OF and len(eta.args) == 1 \
+                and not self._is_data(eta, lv_names):
+            link.append(P.LINK_OF[eta.fn])
+            eta = eta.args[0]
+        plate.link = link[::-1] if link else []
+        lin = self._linearize(eta, lv_names)
+        # aux args
+        aux = []
+        for k, a in enumerate(args):
+            if k == eta_arg:
+                aux.append(P.ZERO_ARG)
+            else:
+                aux.append(self._scalar_arg(a, lv_names, shape, lv_names))
+        plate.aux = aux
+        # terms: globals first (order of first appearance), then locals, then the data offset
+        gterms, lterms = [], []
+        for ref, cov in lin.terms.items():
+            (gterms if ref[0] == "g" else lterms).append((ref, cov))
+        for ref, cov in gterms:
+            plate.terms.append(P.Term(P.Arg.gval(self._gval_of(ref[1])),
+                                      self._data_arg(cov, lv_names, shape, lv_names)))
+        for ref, cov in lterms:
+            li = self._local_index(plate, s, ref, used_locals)
+            plate.terms.append(P.Term(P.Arg.local(li), self._data_arg(cov, lv_names, shape, lv_names)))
+        if lin.const is not None:
+            c = self._data_arg(lin.const, lv_names, shape, lv_names)
+            if not (c.kind == P.ARG_CONST and c.value == 0.0):
+                plate.terms.append(P.Term(P.Arg.const(1.0), c))
+        return plate
+
+    def _local_index(self, plate: P.Plate, obs: Stmt, ref, used_locals) -> int:
+        _, name, idx = ref
+        for k, l in enumerate(plate.locals):
+            if l.name == name:
+                return k
+        defs = [d for d in self._defs(name) if d.kind == "param"]
+        if len(defs) != 1:
+            raise LoweringError(f"'{name}' must be defined by exactly one stochastic statement")
+        d = defs[0]
+        if d.is_gq:
+            raise LoweringError(f"'{name}' feeds an observation but was classified as generated quantity")
+        if d.sid in used_locals:
+            raise LoweringError(f"'{name}' is a parent of more than one observation plate")
+        # the reference must be name[v...] with v the observation's loop variables, and the defining
+        # statement's loop nest must be a prefix of the observation's with identical extents
+        if len(d.loops) > len(obs.loops) or not d.loops:
+            raise LoweringError(f"'{name}': unsupported nesting")
+        if d.extents != obs.extents[:len(d.loops)]:
+            raise LoweringError(f"'{name}': loop ranges differ from the observation plate's")
+        dl = d.node.lhs
+        if not isinstance(dl, Index) or len(dl.idx) != len(d.loops) or len(idx) != len(dl.idx):
+            raise LoweringError(f"'{name}': lhs must be indexed by its loop variables")
+        for pos, (li, ri) in enumerate(zip(dl.idx, idx)):
+            if not (isinstance(li, Var) and li.name == d.loop_vars[pos]):
+                raise LoweringError(f"'{name}': lhs index {pos + 1} must be loop variable '{d.loop_vars[pos]}'")
+            if not (isinstance(ri, Var) and ri.name == obs.loop_vars[pos]):
+                raise LoweringError(f"'{name}': must be referenced with the plate's own loop variables")
+        level = P.LEVEL_OBS if (len(d.loops) == 2) else P.LEVEL_GROUP
+        fam = self._family(d.node.dist)
+        tr, lb, ub = self._transform_of(fam, d.node.dist.args)
+        tidx = self.theta_index(d)
+        base, si, sj, idx_slot = _affine_or_index(tidx)
+        if idx_slot is not None:
+            idx_slot = self._slot(f"theta_index|{name}", np.asfortranarray(tidx).ravel(order="F").astype(np.int64),
+                                  rank=tidx.ndim, dim0=tidx.shape[0])
+        self._cur_extents = d.extents
+        pargs = [self._scalar_arg(a, d.loop_vars, d.shape, d.loop_vars) for a in d.node.dist.args]
+        self._cur_extents = obs.extents
+        plate.locals.append(P.Local(name, level, tr, base, si, sj, fam, pargs, lb, ub,
+                                    -1 if idx_slot is None else idx_slot))
+        used_locals.add(d.sid)
+        return len(plate.locals) - 1
+
+
+def _affine_or_index(tidx: np.ndarray):
+    """compress a theta-index array over the loop domain to base + stride_i*i + stride_j*j when exact."""
+    if tidx.ndim == 0:
+        return int(tidx), 0, 0, None
+    if tidx.ndim == 1:
+        base = int(tidx[0])
+        si = int(tidx[1] - tidx[0]) if tidx.shape[0] > 1 else 0
+        ok = np.array_equal(tidx, base + si * np.arange(tidx.shape[0], dtype=np.int64))
+        return (base, si, 0, None) if ok else (0, 0, 0, True)
+    base = int(tidx[0, 0])
+    si = int(tidx[1, 0] - tidx[0, 0]) if tidx.shape[0] > 1 else 0
+    sj = int(tidx[0, 1] - tidx[0, 0]) if tidx.shape[1] > 1 else 0
+    fit = base + si * np.arange(tidx.shape[0], dtype=np.int64)[:, None] \
+        + sj * np.arange(tidx.shape[1], dtype=np.int64)[None, :]
+    return (base, si, sj, None) if np.array_equal(tidx, fit) else (0, 0, 0, True)
+
+
+def _subst(e, sub):
+    if isinstance(e, Var):
+        return sub.get(e.name, e)
+    if isinstance(e, Index):
+        return Index(e.name, tuple(_subst(i, sub) for i in e.idx))
+    if isinstance(e, Neg):
+        return Neg(_subst(e.a, sub))
+    if isinstance(e, BinOp):
+        return BinOp(e.op, _subst(e.a, sub), _subst(e.b, sub))
+    if isinstance(e, Call):
+        return Call(e.fn, tuple(_subst(a, sub) for a in e.args))
+    if isinstance(e, Range):
+        return Range(_subst(e.lo, sub), _subst(e.hi, sub))
+    return e
+
+
+def _show(e) -> str:
+    if isinstance(e, Num):
+        return repr(e.value)
+    if isinstance(e, Var):
+        return e.name
+    if isinstance(e, Index):
+        return f"{e.name}[{','.join(_show(i) for i in e.idx)}]"
+    if isinstance(e, Neg):
+        return f"(-{_show(e.a)})"
+    if isinstance(e, BinOp):
+        return f"({_show(e.a)}{e.op}{_show(e.b)})"
+    if isinstance(e, Call):
+        return f"{e.fn}({','.join(_show(a) for a in e.args)})"
+    if isinstance(e, Range):
+        return f"{_show(e.lo)}:{_show(e.hi)}"
+    if isinstance(e, Colon):
+        return ":"
+    return repr(e)
+
+
+def lower(model_text, data, transformed=True, theta_order=None) -> Tuple[P.Plan, Lowering]:
+    lw = Lowering(model_text, data, transformed=transformed, theta_order=theta_order)
+    return lw.plan, lw

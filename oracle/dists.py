@@ -1,0 +1,280 @@
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product path.
+
+Restatement of the arithmetic the reference delegates to third-party Julia
+packages that are NOT vendored under /root/reference (no Manifest; compat
+ranges in `JuliaBUGS/Project.toml:53-84`):
+
+* BUGS -> Distributions.jl parameterisation: `JuliaBUGS/src/BUGSPrimitives/distributions.jl`
+  (`dnorm :11-18`, `dexp :186-188`, `dgamma :200-203`, `dunif :343-345`, `dbeta :357-359`,
+  `dbern :442-444`, `dbin :458-460`, `dcat :472-474`, `dpois :486-488`, `dlnorm`, `dweib`, ...).
+* `Distributions.logpdf` (Distributions 0.25 / StatsFuns 1.x published formulas:
+  `normlogpdf`, `gammalogpdf`, `betalogpdf`, `binomlogpdf`, `poislogpdf`).
+* `Bijectors.bijector` / `with_logabsdet_jacobian` (Bijectors 0.13-0.16): support-based
+  `TruncatedBijector(lb, ub)` for continuous univariates, identity for discrete; call site
+  `JuliaBUGS/src/model/evaluation.jl:243-257`.
+
+Every distribution is a small object with `logpdf(M, x)`, `support()` -> (lb, ub, discrete)
+and parameter checks that raise `DomainError` exactly where Distributions' `@check_args`
+(or the explicit throw in `dnorm`) would.
+"""
+from __future__ import annotations
+
+import math
+
+from numeric import DomainError, _val
+
+
+def _check(cond, msg):
+    if not cond:
+        raise DomainError(msg)
+
+
+class Dist:
+    discrete = False
+
+    def support(self):
+        return (-math.inf, math.inf)
+
+
+class Normal(Dist):
+    def __init__(self, M, mu, tau):
+        # distributions.jl:11-18: throws for tau < 0, sigma = sqrt(1/tau)
+        _check(not (_val(tau) < 0), "dnorm requires tau > 0")
+        self.mu = mu
+        self.sigma = M.sqrt(1.0 / tau)
+
+    def logpdf(self, M, x):
+        z = (x - self.mu) / self.sigma
+        return -(z * z + M.log2pi) / 2 - M.log(self.sigma)
+
+
+class Gamma(Dist):
+    def __init__(self, M, a, b):
+        # distributions.jl:200-203: Gamma(a, 1/b); Distributions checks shape>0, scale>0
+        self.k = a
+        self.theta = 1.0 / b
+        _check(_val(a) > 0 and _val(self.theta) > 0, "Gamma requires shape > 0 and scale > 0")
+
+    def support(self):
+        return (0.0, math.inf)
+
+    def logpdf(self, M, x):
+        if _val(x) < 0:
+            return -M.inf
+        xt = x / self.theta
+        # StatsFuns.gammalogpdf: -loggamma(k) + xlogy(k-1, x/theta) - log(theta) - x/theta
+        km1 = self.k - 1
+        xl = 0.0 if (_val(km1) == 0 and not (_val(xt) != _val(xt))) else km1 * M.log(xt)
+        return -M.lgamma(self.k) + xl - M.log(self.theta) - xt
+
+
+class Exponential(Dist):
+    def __init__(self, M, lam):
+        # distributions.jl:186-188: Exponential(1/lam); scale must be > 0
+        self.theta = 1.0 / lam
+        _check(_val(self.theta) > 0, "Exponential requires scale > 0")
+
+    def support(self):
+        return (0.0, math.inf)
+
+    def logpdf(self, M, x):
+        if _val(x) < 0:
+            return -M.inf
+        rate = 1.0 / self.theta
+        return M.log(rate) - rate * x
+
+
+class Uniform(Dist):
+    def __init__(self, M, a, b):
+        _check(_val(a) < _val(b), "Uniform requires a < b")
+        self.a, self.b = a, b
+
+    def support(self):
+        return (self.a, self.b)
+
+    def logpdf(self, M, x):
+        if _val(self.a) <= _val(x) <= _val(self.b):
+            return -M.log(self.b - self.a)
+        return -M.inf
+
+
+def _logbeta(M, a, b):
+    return M.lgamma(a) + M.lgamma(b) - M.lgamma(a + b)
+
+
+def _xlogy(M, x, y):
+    return 0.0 if _val(x) == 0 else x * M.log(y)
+
+
+def _xlog1py(M, x, y):
+    return 0.0 if _val(x) == 0 else x * M.log1p(y)
+
+
+def _betalogpdf(M, a, b, x):
+    # StatsFuns.betalogpdf
+    return _xlogy(M, a - 1, x) + _xlog1py(M, b - 1, -x) - _logbeta(M, a, b)
+
+
+class Beta(Dist):
+    def __init__(self, M, a, b):
+        _check(_val(a) > 0 and _val(b) > 0, "Beta requires a, b > 0")
+        self.a, self.b = a, b
+
+    def support(self):
+        return (0.0, 1.0)
+
+    def logpdf(self, M, x):
+        if not (0 <= _val(x) <= 1):
+            return -M.inf
+        return _betalogpdf(M, self.a, self.b, x)
+
+
+class LogNormal(Dist):
+    def __init__(self, M, mu, tau):
+        self.mu = mu
+        self.sigma = M.sqrt(1.0 / tau)
+        _check(_val(self.sigma) > 0, "LogNormal requires sigma > 0")
+
+    def support(self):
+        return (0.0, math.inf)
+
+    def logpdf(self, M, x):
+        if _val(x) <= 0:
+            return -M.inf
+        lx = M.log(x)
+        z = (lx - self.mu) / self.sigma
+        return -(z * z + M.log2pi) / 2 - M.log(self.sigma) - lx
+
+
+class Bernoulli(Dist):
+    discrete = True
+
+    def __init__(self, M, p):
+        _check(0 <= _val(p) <= 1, "Bernoulli requires 0 <= p <= 1")
+        self.p = p
+
+    def logpdf(self, M, x):
+        xv = _val(x)
+        if xv == 0:
+            return M.log(1.0 - self.p)
+        if xv == 1:
+            return M.log(self.p)
+        return -M.inf
+
+
+class Binomial(Dist):
+    discrete = True
+
+    def __init__(self, M, p, n):
+        # distributions.jl:458-460 swaps the arguments: dbin(p, n) = Binomial(n, p)
+        _check(_val(n) >= 0, "Binomial requires n >= 0")
+        _check(0 <= _val(p) <= 1, "Binomial requires 0 <= p <= 1")
+        self.p, self.n = p, n
+
+    def logpdf(self, M, k):
+        kv, nv = _val(k), _val(self.n)
+        if not (0 <= kv <= nv) or not M.isint(k):
+            return -M.inf
+        # StatsFuns.binomlogpdf: betalogpdf(k+1, n-k+1, p) - log(n+1)
+        return _betalogpdf(M, k + 1, self.n - k + 1, self.p) - M.log(self.n + 1)
+
+
+class Poisson(Dist):
+    discrete = True
+
+    def __init__(self, M, lam):
+        _check(_val(lam) >= 0, "Poisson requires lambda >= 0")
+        self.lam = lam
+
+    def logpdf(self, M, k):
+        if _val(k) < 0 or not M.isint(k):
+            return -M.inf
+        # StatsFuns.poislogpdf: xlogy(x, lambda) - lambda - loggamma(x+1)
+        return _xlogy(M, k, self.lam) - self.lam - M.lgamma(k + 1)
+
+
+class Categorical(Dist):
+    discrete = True
+
+    def __init__(self, M, p):
+        s = 0.0
+        for pi in p:
+            _check(_val(pi) >= 0, "Categorical requires p >= 0")
+            s = s + pi
+        _check(abs(_val(s) - 1.0) < 1e-8, "Categorical requires sum(p) == 1")
+        self.p = list(p)
+
+    def logpdf(self, M, k):
+        kv = int(_val(k))
+        if not (1 <= kv <= len(self.p)):
+            return -M.inf
+        return M.log(self.p[kv - 1])
+
+
+class Flat(Dist):
+    def logpdf(self, M, x):
+        return 0.0 * x
+
+
+def make_dist(M, name, args):
+    """BUGS distribution call -> distribution object (BUGSPrimitives/distributions.jl)."""
+    if name == "dnorm":
+        return Normal(M, *args)
+    if name == "dgamma":
+        return Gamma(M, *args)
+    if name == "dexp":
+        return Exponential(M, *args)
+    if name == "dunif":
+        return Uniform(M, *args)
+    if name == "dbeta":
+        return Beta(M, *args)
+    if name == "dlnorm":
+        return LogNormal(M, *args)
+    if name == "dbern":
+        return Bernoulli(M, *args)
+    if name == "dbin":
+        return Binomial(M, *args)
+    if name == "dpois":
+        return Poisson(M, *args)
+    if name == "dcat":
+        return Categorical(M, *args)
+    if name == "dflat":
+        return Flat()
+    raise NotImplementedError(f"distribution {name} is outside the restated subset")
+
+
+# --------------------------------------------------------------------------- bijectors
+
+
+def link(M, dist, x):
+    """constrained value -> unconstrained slot (Bijectors.bijector(dist)(x)); used by getparams,
+    `JuliaBUGS/src/model/bugsmodel.jl:619-665`."""
+    if dist.discrete:
+        return x
+    lb, ub = dist.support()
+    lo, hi = math.isfinite(_val(lb)), math.isfinite(_val(ub))
+    if lo and hi:
+        u = (x - lb) / (ub - lb)
+        return M.log(u) - M.log(1.0 - u)
+    if lo:
+        return M.log(x - lb)
+    if hi:
+        return M.log(ub - x)
+    return x
+
+
+def invlink_with_logjac(M, dist, y):
+    """unconstrained slot -> (value, logabsdetjac) -- `with_logabsdet_jacobian(inverse(bijector(d)), y)`
+    at `evaluation.jl:244-251`."""
+    if dist.discrete:
+        return y, 0.0
+    lb, ub = dist.support()
+    lo, hi = math.isfinite(_val(lb)), math.isfinite(_val(ub))
+    if lo and hi:
+        x = lb + (ub - lb) * M.logistic(y)
+        return x, M.log((x - lb) * (ub - x) / (ub - lb))
+    if lo:
+        return M.exp(y) + lb, y
+    if hi:
+        return ub - M.exp(y), y
+    return y, 0.0

@@ -1,0 +1,483 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- never linked, imported or executed by the product path.
+ *
+ * jbugs_oracle.c : scalar CPU restatement of the reference's *generated* evaluator
+ * `__compute_log_density__` (JuliaBUGS/src/source_gen.jl:670-774): real `for` loops over the
+ * plates, one theta at a time, Float64 throughout, `logpdf` per statement instance
+ * (`:738-741` observe, `:747-774` parameters incl. inverse bijector + logabsdetjac), same
+ * DomainError -> (-Inf, NaN) mapping as JuliaBUGS/src/model/logdensityproblems.jl:22-26,226-229.
+ * The gradient is the analytic reverse sweep of that same straight-line program (what the
+ * reference obtains from its AD backend, logdensityproblems.jl:219-232).
+ *
+ * The arithmetic follows the third-party packages the reference delegates to (NOT vendored under
+ * /root/reference, only compat ranges in JuliaBUGS/Project.toml:53-84): Distributions 0.25 /
+ * StatsFuns 1.x (`normlogpdf`, `gammalogpdf`, `betalogpdf`, `binomlogpdf`, `poislogpdf`),
+ * LogExpFunctions 0.3 (`logistic` incl. its saturation bounds, `cexpexp`), Bijectors 0.13-0.16
+ * (support-based log / scaled-logit maps).
+ *
+ * It interprets the same flat plan (include/jbugs_plan.h) the CUDA library consumes; the
+ * plan/lowering itself is validated against the per-node graph oracle (oracle/graph_oracle.py),
+ * which is pinned to the reference's golden constants (tests/test_oracle_goldens.py).
+ *
+ * Used as: the checker in tests/, smoke(), and the `cpu_baseline` / `--impl reference` leg of
+ * bench.py (OpenMP over chains; one chain per thread exactly like MCMCThreads runs the reference).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/jbugs_plan.h"
+
+#define LOG2PI 1.8378770664093454835606594728112
+#define LOGISTIC_LOWER (-744.4400719213812)
+#define LOGISTIC_UPPER (36.7368005696771)
+
+typedef struct jbo_plan {
+    jbugs_plan_header h;
+    jbugs_global* globals;
+    jbugs_gop* gtape;
+    jbugs_data_desc* data;
+    jbugs_plate* plates;
+    jbugs_local* locals;
+    jbugs_term* terms;
+    const void** slots; /* borrowed pointers */
+    int64_t* shard_i0;  /* per plate */
+    int64_t* shard_i1;
+    int n_gvals;
+} jbo_plan;
+
+/* ---------------------------------------------------------------- special functions */
+
+static double digamma(double x) {
+    /* asymptotic series after upward recurrence; |err| < 1e-15 for x > 0 */
+    double r = 0.0;
+    if (x <= 0.0) { /* reflection */
+        if (x == floor(x)) return NAN;
+        return digamma(1.0 - x) - M_PI / tan(M_PI * x);
+    }
+    while (x < 10.0) {
+        r -= 1.0 / x;
+        x += 1.0;
+    }
+    double f = 1.0 / (x * x);
+    double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 +
+               f * (-1.0 / 132.0 + f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
+    return r + log(x) - 0.5 / x + t;
+}
+
+static double logistic(double x) {
+    /* LogExpFunctions.logistic for Float64 */
+    if (x < LOGISTIC_LOWER) return 0.0;
+    if (x > LOGISTIC_UPPER) return 1.0;
+    double e = exp(x);
+    return e / (1.0 + e);
+}
+
+static double normcdf(double x) { return 0.5 * erfc(-x * M_SQRT1_2); }
+static double normpdf(double x) { return exp(-0.5 * x * x) / sqrt(2.0 * M_PI); }
+static double xlogy(double x, double y) { return x == 0.0 ? 0.0 : x * log(y); }
+static double xlog1py(double x, double y) { return x == 0.0 ? 0.0 : x * log1p(y); }
+static double logbeta(double a, double b) { return lgamma(a) + lgamma(b) - lgamma(a + b); }
+
+/* unary op: value and derivative */
+static int unary(uint32_t op, double x, double* v, double* d) {
+    switch (op) {
+    case JBUGS_OP_IDENTITY: *v = x; *d = 1.0; return 0;
+    case JBUGS_OP_EXP: *v = exp(x); *d = *v; return 0;
+    case JBUGS_OP_LOGISTIC: *v = logistic(x); *d = *v * (1.0 - *v); return 0;
+    case JBUGS_OP_CEXPEXP: *v = -expm1(-exp(x)); *d = exp(x - exp(x)); return 0;
+    case JBUGS_OP_PHI: *v = normcdf(x); *d = normpdf(x); return 0;
+    case JBUGS_OP_LOG: if (x < 0) return 1; *v = log(x); *d = 1.0 / x; return 0;
+    case JBUGS_OP_SQRT: if (x < 0) return 1; *v = sqrt(x); *d = 0.5 / *v; return 0;
+    case JBUGS_OP_NEG: *v = -x; *d = -1.0; return 0;
+    default: return 2;
+    }
+}
+
+/* log density of `fam` at x with arguments a[0..2]; partials dx, da[]; returns 1 on DomainError */
+static int fam_logpdf(uint32_t fam, double x, const double* a, double* lp, double* dx, double* da) {
+    da[0] = da[1] = da[2] = 0.0;
+    *dx = 0.0;
+    switch (fam) {
+    case JBUGS_FAM_NORMAL: { /* distributions.jl:11-18 */
+        double mu = a[0], tau = a[1];
+        if (tau < 0.0) return 1;
+        double sigma = sqrt(1.0 / tau);
+        double z = (x - mu) / sigma;
+        *lp = -(z * z + LOG2PI) / 2.0 - log(sigma);
+        double r = x - mu;
+        *dx = -tau * r;
+        da[0] = tau * r;
+        da[1] = 0.5 / tau - 0.5 * r * r;
+        return 0;
+    }
+    case JBUGS_FAM_GAMMA: { /* distributions.jl:200-203 -> Gamma(a, 1/b) */
+        double k = a[0], b = a[1];
+        double theta = 1.0 / b;
+        if (!(k > 0.0) || !(theta > 0.0)) return 1;
+        if (x < 0.0) { *lp = -INFINITY; return 0; }
+        double xt = x / theta;
+        *lp = -lgamma(k) + xlogy(k - 1.0, xt) - log(theta) - xt;
+        *dx = (k - 1.0) / x - b;
+        da[0] = -digamma(k) + log(xt);
+        da[1] = k / b - x;
+        return 0;
+    }
+    case JBUGS_FAM_EXPONENTIAL: { /* :186-188 -> Exponential(1/lambda) */
+        double theta = 1.0 / a[0];
+        if (!(theta > 0.0)) return 1;
+        if (x < 0.0) { *lp = -INFINITY; return 0; }
+        double rate = 1.0 / theta;
+        *lp = log(rate) - rate * x;
+        *dx = -rate;
+        da[0] = 1.0 / a[0] - x;
+        return 0;
+    }
+    case JBUGS_FAM_UNIFORM: {
+        if (!(a[0] < a[1])) return 1;
+        if (x < a[0] || x > a[1]) { *lp = -INFINITY; return 0; }
+        *lp = -log(a[1] - a[0]);
+        da[0] = 1.0 / (a[1] - a[0]);
+        da[1] = -1.0 / (a[1] - a[0]);
+        return 0;
+    }
+    case JBUGS_FAM_BETA: {
+        if (!(a[0] > 0.0) || !(a[1] > 0.0)) return 1;
+        if (x < 0.0 || x > 1.0) { *lp = -INFINITY; return 0; }
+        *lp = xlogy(a[0] - 1.0, x) + xlog1py(a[1] - 1.0, -x) - logbeta(a[0], a[1]);
+        *dx = (a[0] - 1.0) / x - (a[1] - 1.0) / (1.0 - x);
+        double pab = digamma(a[0] + a[1]);
+        da[0] = log(x) - digamma(a[0]) + pab;
+        da[1] = log1p(-x) - digamma(a[1]) + pab;
+        return 0;
+    }
+    case JBUGS_FAM_LOGNORMAL: {
+        double mu = a[0], tau = a[1];
+        if (tau < 0.0) return 1;
+        double sigma = sqrt(1.0 / tau);
+        if (!(sigma > 0.0)) return 1;
+        if (x <= 0.0) { *lp = -INFINITY; return 0; }
+        double lx = log(x), z = (lx - mu) / sigma, r = lx - mu;
+        *lp = -(z * z + LOG2PI) / 2.0 - log(sigma) - lx;
+        *dx = -(tau * r + 1.0) / x;
+        da[0] = tau * r;
+        da[1] = 0.5 / tau - 0.5 * r * r;
+        return 0;
+    }
+    case JBUGS_FAM_BERNOULLI: {
+        double p = a[0];
+        if (!(p >= 0.0 && p <= 1.0)) return 1;
+        if (x == 0.0) { *lp = log(1.0 - p); da[0] = -1.0 / (1.0 - p); }
+        else if (x == 1.0) { *lp = log(p); da[0] = 1.0 / p; }
+        else *lp = -INFINITY;
+        return 0;
+    }
+    case JBUGS_FAM_BINOMIAL: { /* :458-460 -> Binomial(n, p) */
+        double p = a[0], n = a[1];
+        if (!(n >= 0.0) || !(p >= 0.0 && p <= 1.0)) return 1;
+        if (x < 0.0 || x > n || x != floor(x)) { *lp = -INFINITY; return 0; }
+        /* StatsFuns.binomlogpdf = betalogpdf(k+1, n-k+1, p) - log(n+1) */
+        *lp = xlogy(x, p) + xlog1py(n - x, -p) - logbeta(x + 1.0, n - x + 1.0) - log(n + 1.0);
+        da[0] = (x == 0.0 ? 0.0 : x / p) - (n - x == 0.0 ? 0.0 : (n - x) / (1.0 - p));
+        return 0;
+    }
+    case JBUGS_FAM_POISSON: {
+        double lam = a[0];
+        if (!(lam >= 0.0)) return 1;
+        if (x < 0.0 || x != floor(x)) { *lp = -INFINITY; return 0; }
+        *lp = xlogy(x, lam) - lam - lgamma(x + 1.0);
+        da[0] = (x == 0.0 ? 0.0 : x / lam) - 1.0;
+        return 0;
+    }
+    case JBUGS_FAM_FLAT: *lp = 0.0; return 0;
+    default: return 2;
+    }
+}
+
+/* slot y -> constrained value x, logjac, dx/dy, dlogjac/dy (Bijectors, evaluation.jl:243-251) */
+static void transform(uint32_t tr, double lb, double ub, double y, double* x, double* lj, double* dxdy,
+                      double* dljdy) {
+    switch (tr) {
+    case JBUGS_TR_LOG: { double e = exp(y); *x = lb + e; *lj = y; *dxdy = e; *dljdy = 1.0; return; }
+    case JBUGS_TR_UPPER: { double e = exp(y); *x = ub - e; *lj = y; *dxdy = -e; *dljdy = 1.0; return; }
+    case JBUGS_TR_LOGIT: {
+        double s = logistic(y), w = ub - lb;
+        *x = lb + w * s;
+        *lj = log((*x - lb) * (ub - *x) / w);
+        *dxdy = w * s * (1.0 - s);
+        *dljdy = 1.0 - 2.0 * s;
+        return;
+    }
+    default: *x = y; *lj = 0.0; *dxdy = 1.0; *dljdy = 0.0; return;
+    }
+}
+
+/* ---------------------------------------------------------------- plan handling */
+
+jbo_plan* jbo_plan_create(const void* blob, size_t nbytes) {
+    if (nbytes < sizeof(jbugs_plan_header)) return NULL;
+    jbo_plan* p = (jbo_plan*)calloc(1, sizeof(jbo_plan));
+    memcpy(&p->h, blob, sizeof(jbugs_plan_header));
+    if (memcmp(p->h.magic, JBUGS_PLAN_MAGIC, 8) != 0 || p->h.version != JBUGS_PLAN_VERSION) { free(p); return NULL; }
+    size_t need = sizeof(jbugs_plan_header) + p->h.n_globals * sizeof(jbugs_global) + p->h.n_gtape * sizeof(jbugs_gop) +
+                  p->h.n_data * sizeof(jbugs_data_desc) + p->h.n_plates * sizeof(jbugs_plate) +
+                  p->h.n_locals * sizeof(jbugs_local) + p->h.n_terms * sizeof(jbugs_term);
+    if (need != nbytes) { free(p); return NULL; }
+    const char* c = (const char*)blob + sizeof(jbugs_plan_header);
+#define TAKE(field, type, n) \
+    p->field = (type*)malloc((n) * sizeof(type) + 1); memcpy(p->field, c, (n) * sizeof(type)); c += (n) * sizeof(type)
+    TAKE(globals, jbugs_global, p->h.n_globals);
+    TAKE(gtape, jbugs_gop, p->h.n_gtape);
+    TAKE(data, jbugs_data_desc, p->h.n_data);
+    TAKE(plates, jbugs_plate, p->h.n_plates);
+    TAKE(locals, jbugs_local, p->h.n_locals);
+    TAKE(terms, jbugs_term, p->h.n_terms);
+#undef TAKE
+    p->slots = (const void**)calloc(p->h.n_data + 1, sizeof(void*));
+    p->shard_i0 = (int64_t*)calloc(p->h.n_plates + 1, sizeof(int64_t));
+    p->shard_i1 = (int64_t*)calloc(p->h.n_plates + 1, sizeof(int64_t));
+    for (uint32_t k = 0; k < p->h.n_plates; ++k) p->shard_i1[k] = p->plates[k].N;
+    p->n_gvals = (int)(p->h.n_globals + p->h.n_gtape);
+    return p;
+}
+
+void jbo_plan_destroy(jbo_plan* p) {
+    if (!p) return;
+    free(p->globals); free(p->gtape); free(p->data); free(p->plates); free(p->locals); free(p->terms);
+    free(p->slots); free(p->shard_i0); free(p->shard_i1); free(p);
+}
+
+int64_t jbo_dim(const jbo_plan* p) { return p->h.D; }
+
+/* borrowed pointer: the caller keeps the array alive */
+int jbo_plan_set_data(jbo_plan* p, int slot, const void* ptr, size_t nbytes) {
+    if (slot < 0 || (uint32_t)slot >= p->h.n_data) return -1;
+    if (nbytes != (size_t)p->data[slot].len * 8) return -1;
+    p->slots[slot] = ptr;
+    return 0;
+}
+
+int jbo_plan_set_shard(jbo_plan* p, int plate, int64_t i0, int64_t i1) {
+    if (plate < 0 || (uint32_t)plate >= p->h.n_plates || i0 < 0 || i1 > p->plates[plate].N || i0 > i1) return -1;
+    p->shard_i0[plate] = i0;
+    p->shard_i1[plate] = i1;
+    return 0;
+}
+
+/* ---------------------------------------------------------------- one chain */
+
+#define MAXG 256
+#define MAXL 16
+
+typedef struct {
+    const double* th; int64_t sth; /* theta[d * sth] */
+    double* g; int64_t sg;         /* grad[d * sg]   */
+} chain_io;
+
+static inline double argval(const jbo_plan* p, const jbugs_arg* a, const double* gval, const double* lx,
+                            int64_t i, int64_t j, int64_t N) {
+    switch (a->kind) {
+    case JBUGS_ARG_CONST: return a->value;
+    case JBUGS_ARG_ONE: return 1.0;
+    case JBUGS_ARG_GVAL: return gval[a->id];
+    case JBUGS_ARG_LOCAL: return lx[a->id];
+    case JBUGS_ARG_DATA_I: return ((const double*)p->slots[a->id])[i];
+    case JBUGS_ARG_DATA_J: return ((const double*)p->slots[a->id])[j];
+    case JBUGS_ARG_DATA_IJ: return ((const double*)p->slots[a->id])[i + N * j];
+    default: return NAN;
+    }
+}
+
+static inline void argadj(const jbugs_arg* a, double d, double* gadj, double* ladj) {
+    if (a->kind == JBUGS_ARG_GVAL) gadj[a->id] += d;
+    else if (a->kind == JBUGS_ARG_LOCAL) ladj[a->id] += d;
+}
+
+static inline int64_t local_slot(const jbo_plan* p, const jbugs_local* l, int64_t i, int64_t j, int64_t N) {
+    if (l->idx_slot >= 0) {
+        const int64_t* ix = (const int64_t*)p->slots[l->idx_slot];
+        return l->level == JBUGS_LEVEL_OBS ? ix[i + N * j] : ix[i];
+    }
+    return l->theta_base + l->stride_i * i + l->stride_j * j;
+}
+
+/* returns 0 ok, 1 domain error */
+static int eval_chain(const jbo_plan* p, chain_io io, int want_grad, double* logp_out) {
+    double gval[MAXG], gadj[MAXG], gdxdy[MAXG], gdlj[MAXG];
+    const int H = (int)p->h.n_globals, NG = p->n_gvals;
+    double logp = 0.0;
+    for (int k = 0; k < NG; ++k) gadj[k] = 0.0;
+    /* globals: inverse bijector + logjac (source_gen.jl:747-768) */
+    for (int h = 0; h < H; ++h) {
+        const jbugs_global* g = &p->globals[h];
+        double lj;
+        transform(g->transform, g->lb, g->ub, io.th[g->theta_idx * io.sth], &gval[h], &lj, &gdxdy[h], &gdlj[h]);
+        logp += lj;
+    }
+    /* scalar logical nodes of globals */
+    double tv_d1[MAXG], tv_d2[MAXG];
+    for (uint32_t k = 0; k < p->h.n_gtape; ++k) {
+        const jbugs_gop* o = &p->gtape[k];
+        double a = argval(p, &o->a, gval, NULL, 0, 0, 0), v, d1 = 0, d2 = 0;
+        if (o->op < 16) {
+            if (unary(o->op, a, &v, &d1)) return 1;
+        } else {
+            double b = argval(p, &o->b, gval, NULL, 0, 0, 0);
+            switch (o->op) {
+            case JBUGS_OP_ADD: v = a + b; d1 = 1; d2 = 1; break;
+            case JBUGS_OP_SUB: v = a - b; d1 = 1; d2 = -1; break;
+            case JBUGS_OP_MUL: v = a * b; d1 = b; d2 = a; break;
+            case JBUGS_OP_DIV: v = a / b; d1 = 1.0 / b; d2 = -a / (b * b); break;
+            case JBUGS_OP_POW:
+                if (a < 0 && b != floor(b)) return 1;
+                v = pow(a, b); d1 = b * pow(a, b - 1.0); d2 = (a > 0) ? v * log(a) : 0.0; break;
+            default: return 1;
+            }
+        }
+        gval[H + k] = v; tv_d1[k] = d1; tv_d2[k] = d2;
+    }
+    /* priors of the globals */
+    for (int h = 0; h < H; ++h) {
+        const jbugs_global* g = &p->globals[h];
+        double a[3], da[3], lp, dx;
+        for (int q = 0; q < 3; ++q) a[q] = argval(p, &g->args[q], gval, NULL, 0, 0, 0);
+        if (fam_logpdf(g->family, gval[h], a, &lp, &dx, da)) return 1;
+        logp += lp;
+        gadj[h] += dx;
+        for (int q = 0; q < 3; ++q) argadj(&g->args[q], da[q], gadj, NULL);
+    }
+    /* plates */
+    for (uint32_t pi = 0; pi < p->h.n_plates; ++pi) {
+        const jbugs_plate* pl = &p->plates[pi];
+        const jbugs_local* L = p->locals + pl->first_local;
+        const jbugs_term* Tm = p->terms + pl->first_term;
+        const int nl = (int)pl->n_locals, nt = (int)pl->n_terms;
+        const int64_t N = pl->N, T = pl->T;
+        double lx[MAXL], ladj[MAXL], ldx[MAXL], ldlj[MAXL];
+        int64_t lslot[MAXL];
+        for (int64_t i = p->shard_i0[pi]; i < p->shard_i1[pi]; ++i) {
+            /* group-level locals */
+            for (int l = 0; l < nl; ++l) {
+                if (L[l].level != JBUGS_LEVEL_GROUP) continue;
+                double lj;
+                lslot[l] = local_slot(p, &L[l], i, 0, N);
+                transform(L[l].transform, L[l].lb, L[l].ub, io.th[lslot[l] * io.sth], &lx[l], &lj, &ldx[l], &ldlj[l]);
+                logp += lj;
+                ladj[l] = 0.0;
+            }
+            for (int l = 0; l < nl; ++l) {
+                if (L[l].level != JBUGS_LEVEL_GROUP) continue;
+                double a[3], da[3], lp, dx;
+                for (int q = 0; q < 3; ++q) a[q] = argval(p, &L[l].args[q], gval, lx, i, 0, N);
+                if (fam_logpdf(L[l].family, lx[l], a, &lp, &dx, da)) return 1;
+                logp += lp;
+                ladj[l] += dx;
+                for (int q = 0; q < 3; ++q) argadj(&L[l].args[q], da[q], gadj, ladj);
+            }
+            for (int64_t j = 0; j < T; ++j) {
+                for (int l = 0; l < nl; ++l) {
+                    if (L[l].level != JBUGS_LEVEL_OBS) continue;
+                    double lj;
+                    lslot[l] = local_slot(p, &L[l], i, j, N);
+                    transform(L[l].transform, L[l].lb, L[l].ub, io.th[lslot[l] * io.sth], &lx[l], &lj, &ldx[l], &ldlj[l]);
+                    logp += lj;
+                    ladj[l] = 0.0;
+                }
+                for (int l = 0; l < nl; ++l) {
+                    if (L[l].level != JBUGS_LEVEL_OBS) continue;
+                    double a[3], da[3], lp, dx;
+                    for (int q = 0; q < 3; ++q) a[q] = argval(p, &L[l].args[q], gval, lx, i, j, N);
+                    if (fam_logpdf(L[l].family, lx[l], a, &lp, &dx, da)) return 1;
+                    logp += lp;
+                    ladj[l] += dx;
+                    for (int q = 0; q < 3; ++q) argadj(&L[l].args[q], da[q], gadj, ladj);
+                }
+                if (pl->has_obs) {
+                    /* linear predictor, link tape, observation (source_gen.jl:738-741) */
+                    double eta = 0.0;
+                    for (int t = 0; t < nt; ++t)
+                        eta += argval(p, &Tm[t].coef, gval, lx, i, j, N) * argval(p, &Tm[t].cov, gval, lx, i, j, N);
+                    double v = eta, dv = 1.0;
+                    for (uint32_t q = 0; q < pl->n_link; ++q) {
+                        double nv, d;
+                        if (unary(pl->link[q], v, &nv, &d)) return 1;
+                        v = nv; dv *= d;
+                    }
+                    double a[3], da[3], lp, dx;
+                    for (int q = 0; q < 3; ++q)
+                        a[q] = (q == (int)pl->eta_arg) ? v : argval(p, &pl->aux[q], gval, lx, i, j, N);
+                    double y = argval(p, &pl->y, gval, lx, i, j, N);
+                    if (fam_logpdf(pl->family, y, a, &lp, &dx, da)) return 1;
+                    logp += lp;
+                    double deta = da[pl->eta_arg] * dv;
+                    for (int q = 0; q < 3; ++q)
+                        if (q != (int)pl->eta_arg) argadj(&pl->aux[q], da[q], gadj, ladj);
+                    for (int t = 0; t < nt; ++t)
+                        argadj(&Tm[t].coef, deta * argval(p, &Tm[t].cov, gval, lx, i, j, N), gadj, ladj);
+                }
+                if (want_grad)
+                    for (int l = 0; l < nl; ++l)
+                        if (L[l].level == JBUGS_LEVEL_OBS) io.g[lslot[l] * io.sg] = ladj[l] * ldx[l] + ldlj[l];
+            }
+            if (want_grad)
+                for (int l = 0; l < nl; ++l)
+                    if (L[l].level == JBUGS_LEVEL_GROUP) io.g[lslot[l] * io.sg] = ladj[l] * ldx[l] + ldlj[l];
+        }
+    }
+    /* reverse sweep over the gtape, then through the bijectors of the globals */
+    for (int k = (int)p->h.n_gtape - 1; k >= 0; --k) {
+        const jbugs_gop* o = &p->gtape[k];
+        double ad = gadj[H + k];
+        argadj(&o->a, ad * tv_d1[k], gadj, NULL);
+        if (o->op >= 16) argadj(&o->b, ad * tv_d2[k], gadj, NULL);
+    }
+    if (want_grad)
+        for (int h = 0; h < H; ++h) io.g[p->globals[h].theta_idx * io.sg] = gadj[h] * gdxdy[h] + gdlj[h];
+    *logp_out = logp;
+    return 0;
+}
+
+/* theta/grad: layout 0 = CHAIN_FAST (d * ld + c), 1 = PARAM_FAST (c * ld + d) */
+int jbo_eval_batch(const jbo_plan* p, const double* theta, int64_t ld, int64_t C, int layout, double* logp,
+                   double* grad, int32_t* status, int want_grad, int nthreads) {
+    if (p->n_gvals > MAXG) return -2;
+    for (uint32_t k = 0; k < p->h.n_plates; ++k)
+        if (p->plates[k].n_locals > MAXL) return -2;
+    for (uint32_t k = 0; k < p->h.n_data; ++k)
+        if (!p->slots[k]) return -5;
+    const int64_t D = p->h.D;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int64_t c = 0; c < C; ++c) {
+        chain_io io;
+        if (layout == 0) { io.th = theta + c; io.sth = ld; io.g = grad ? grad + c : NULL; io.sg = ld; }
+        else { io.th = theta + c * ld; io.sth = 1; io.g = grad ? grad + c * ld : NULL; io.sg = 1; }
+        double lp = 0.0;
+        int st = eval_chain(p, io, want_grad && grad, &lp);
+        /* NaN anywhere in theta poisons logp; map like the boundary does */
+        if (st) {
+            logp[c] = -INFINITY;
+            if (want_grad && grad)
+                for (int64_t d = 0; d < D; ++d) io.g[d * io.sg] = NAN;
+        } else {
+            logp[c] = lp;
+        }
+        if (status) status[c] = st ? 1 : 0;
+    }
+    return 0;
+}
+
+int jbo_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
