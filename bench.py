@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- logdensity+gradient obs-evals/s of the batched B200 evaluator (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload rats|seeds|epil|pumps]
+
+A "step" is one batched `logdensity_and_gradient` (jbugs_eval_batch) over the whole synthetic data
+plate for every chain of the batch.  Default workload = BASELINE.json configs[1]: Rats scaled to
+10^6 rats x 5 timepoints, 4096 chains, fp64, one B200.  With N > 1 (torchrun) chains shard across
+GPUs with no data-path collective (weak scaling: 4096 chains per GPU).
+
+  value     obs-evals/s with theta/grad resident in HBM (CUDA events around exactly K steps)
+  e2e       same metric through the C ABI with pinned HOST buffers (H2D of theta, D2H of grad/logp
+            inside the timed region) on a bounded chain sample
+  roofline  algorithmic bytes (2*8*C*D) / measured plate-kernel time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the C restatement of the reference evaluator (oracle/) on the host cores, bounded sample
+
+`--impl reference` times that CPU restatement alone (Julia is not installed here or on the GPU box,
+so the reference itself cannot run; kind = "port").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "juliabugs.jl_b200"))
+
+METRIC = "logdensity+gradient obs-evals/s"
+UNIT = "obs-evals/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------- workloads
+def make_workload(name, groups):
+    """returns (model_text, data, theta0 (D,), description)"""
+    from jbugs import examples as ex
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import synth_rats, synth_seeds
+    if name == "rats":
+        N = groups or 1_000_000
+        data, alpha, beta = synth_rats(N)
+        D = 2 * N + 5
+        th0 = np.empty(D)
+        th0[:5] = [np.log(4.0), 6.2, np.log(1 / 196.0), 242.0, np.log(1 / 36.0)]  # beta.tau, beta.c, alpha.tau, alpha.c, tau.c
+        th0[5::2] = beta
+        th0[6::2] = alpha
+        return ex.RATS, data, th0, f"rats N={N} T=5"
+    if name == "seeds":
+        N = groups or 10_000_000
+        data, b = synth_seeds(N)
+        th0 = np.empty(N + 5)
+        th0[:5] = [np.log(1 / 0.09), -0.84, 1.36, 0.09, -0.55]  # tau, alpha12, alpha2, alpha1, alpha0
+        th0[5:] = b
+        return ex.SEEDS, data, th0, f"seeds N={N}"
+    raise SystemExit(f"unknown workload {name}")
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.samples:
+            if not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sample in the timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_baseline(plan, th0, n_obs, budget_s=15.0, seed=7):
+    """the C restatement of the reference evaluator on the host cores, one chain per thread."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from c_oracle import COracle
+    co = COracle(plan)
+    cores = co.max_threads()
+    rng = np.random.default_rng(seed)
+
+    def run(C):
+        theta = np.ascontiguousarray(th0[:, None] + 0.05 * rng.standard_normal((th0.size, C)))
+        t = time.perf_counter()
+        co.eval_batch(theta, layout="param_fast", want_grad=True)
+        return time.perf_counter() - t
+
+    t1 = run(cores)  # one chain per thread
+    reps = int(max(1, min(64, budget_s / max(t1, 1e-3))))
+    C = cores * reps
+    if reps > 1:
+        t1 = run(C)
+    else:
+        C = cores
+    return {"value": n_obs * C / t1, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{C} chains x {n_obs} obs, one chain per thread, {t1:.2f} s"}
+
+
+# ----------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rats")
+    ap.add_argument("--groups", type=int, default=0, help="plate size override (default: the BASELINE config)")
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default 4096 for rats, 256 for seeds)")
+    ap.add_argument("--e2e-chains", type=int, default=256)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dynamic", type=int, default=0, help="1 = force the interpreter kernel")
+    ap.add_argument("--tile", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, world)
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+    C = args.chains or {"rats": 4096, "seeds": 256}.get(args.workload, 1024)
+
+    import jbugs
+    model_text, data, th0, desc = make_workload(args.workload, args.groups)
+    t0 = time.time()
+    model = jbugs.compile(model_text, data)
+    plan = model.plan
+    n_obs = plan.n_obs()
+    D = plan.D
+    log(f"[bench] lowered {desc}: D={D} obs={n_obs} in {time.time() - t0:.1f}s")
+    config = {"workload": f"{desc} x {C} chains/GPU, fp64, theta+grad resident in HBM (chain-fast layout)",
+              "chains_per_gpu": C, "D": D, "n_obs": n_obs, "parallelism": f"chains sharded x{n_gpus}, no collective",
+              "l2": "inputs (theta+grad = %.1f GB/GPU) exceed the 126 MB L2; no flush needed" % (2 * 8 * C * D / 1e9)}
+
+    # ---------------- reference arm: CPU restatement only (rank 0)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vals = []
+        for _ in range(W):
+            cpu_baseline(plan, th0, n_obs, budget_s=2.0)
+        for _ in range(K):
+            vals.append(cpu_baseline(plan, th0, n_obs, budget_s=max(5.0, 60.0 / K)))
+        v = float(np.mean([x["value"] for x in vals]))
+        cb = dict(vals[-1], value=v)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": n_gpus,
+                          "steps": K, "warmup": W, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "note": "Julia is not installed: the reference arm is the C restatement of the reference's "
+                                  "generated evaluator (oracle/jbugs_oracle.c), OpenMP one chain per thread"}))
+        return
+
+    # ---------------- our arm
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    model = jbugs.set_evaluation_mode(model, jbugs.UseCUDABatch(device=local_rank))
+    cp = model.cuda
+    if args.dynamic:
+        cp.set_option("dynamic", 1)
+    if args.tile:
+        cp.set_option("tile", args.tile)
+    ld = (C + 15) // 16 * 16
+    theta = torch.empty((D, ld), dtype=torch.float64, device=dev)
+    grad = torch.empty((D, ld), dtype=torch.float64, device=dev)
+    logp = torch.empty(ld, dtype=torch.float64, device=dev)
+    status = torch.empty(ld, dtype=torch.int32, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    th0_d = torch.from_numpy(th0).to(dev)
+    rows = max(1, (1 << 28) // (8 * ld))
+    for r0 in range(0, D, rows):
+        r1 = min(D, r0 + rows)
+        theta[r0:r1] = th0_d[r0:r1, None] + 0.05 * torch.randn((r1 - r0, ld), dtype=torch.float64, device=dev, generator=g)
+    grad.zero_()
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(flags=1):
+        cp.eval_raw(theta.data_ptr(), ld, C, 0, logp.data_ptr(), grad.data_ptr(), status.data_ptr(), True, flags, stream)
+
+    launches0 = cp.launch_count()
+    step(0)
+    launches_per_step = cp.launch_count() - launches0
+    log("[bench] " + cp.describe().replace("\n", " | "))
+    for _ in range(W):
+        step(0)
+    plate_ms = []
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.time()
+    e0.record()
+    for _ in range(K):
+        step(1)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    tw1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    # per-kernel time of the dominant (plate) kernel: the library's own CUDA events on the launch stream
+    for _ in range(min(K, 5)):
+        step(0)
+        plate_ms.append(cp.last_timing()[0])
+    clocks = sampler.stop(tw0, tw1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / K
+    value = n_obs * C * world / (ms_per_step * 1e-3)
+    lp_host = logp[:C].cpu().numpy()
+    st_host = status[:C].cpu().numpy()
+    if not (np.all(np.isfinite(lp_host)) and np.all(st_host == 0)):
+        raise SystemExit("bench produced non-finite log densities: invalid run")
+
+    # roofline of the plate kernel
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, which = 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
+    alg_bytes = 2.0 * 8.0 * C * D
+    pk_ms = float(np.mean(plate_ms))
+    achieved = alg_bytes / (pk_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "plate_kernel", "kernel_ms": pk_ms,
+                "algorithmic_bytes": alg_bytes, "peak_source": which}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "roofline": roofline,
+           "gpu_launches": launches_per_step * K}
+
+    # e2e: host pinned theta -> C ABI -> host grad, bounded chain sample
+    if rank == 0 or world > 1:
+        if not args.no_e2e:
+            Ce = min(args.e2e_chains, C)
+            th_h = torch.empty((D, Ce), dtype=torch.float64).pin_memory()
+            g_h = torch.empty((D, Ce), dtype=torch.float64).pin_memory()
+            lp_h = torch.empty(Ce, dtype=torch.float64).pin_memory()
+            st_h = torch.empty(Ce, dtype=torch.int32).pin_memory()
+            th_h.copy_(theta[:, :Ce])
+            torch.cuda.synchronize()
+
+            def e2e_step():
+                cp.eval_raw(th_h.data_ptr(), Ce, Ce, 0, lp_h.data_ptr(), g_h.data_ptr(), st_h.data_ptr(), True, 0, stream)
+
+            for _ in range(2):
+                e2e_step()
+            reps = max(2, min(K, 5))
+            if world > 1:
+                dist.barrier()
+            t = time.perf_counter()
+            for _ in range(reps):
+                e2e_step()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t) / reps
+            if world > 1:
+                tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            ok = bool(np.allclose(lp_h.numpy(), lp_host[:Ce], rtol=1e-12, atol=0))
+            out["e2e"] = {"value": n_obs * Ce * world / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * D * Ce,
+                          "d2h_bytes_per_step": 8 * D * Ce + 12 * Ce, "chains": Ce, "ms_per_step": dt * 1e3,
+                          "matches_resident": ok,
+                          "sample": f"{Ce} of {C} chains per GPU through jbugs_eval_batch with pinned host buffers"}
+            del th_h, g_h
+    if rank == 0 and not args.no_cpu and world == 1:
+        try:
+            out["cpu_baseline"] = cpu_baseline(plan, th0, n_obs)
+        except Exception as e:  # the oracle is a checker; never let it break the bench line
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e}"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,728 @@
+// jbugs_cuda.cu -- host side of libjbugs_cuda: plan handling, device buffers, kernel selection and the
+// C ABI declared in include/jbugs_cuda.h.  No torch types, no CPU fallback.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/jbugs_cuda.h"
+#include "jbugs_kernels.cuh"
+#include "jbugs_specs.cuh"
+
+using namespace jbugs;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(JBUGS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ NCCL (dlopen'ed)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+    if (g_nccl.h) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    if (!g_nccl.h) return fail(JBUGS_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(g_nccl.h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(g_nccl.h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(g_nccl.h, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(g_nccl.h, "ncclAllReduce");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce)
+        return fail(JBUGS_ERR_NCCL, "libnccl lacks a required symbol");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ plan object
+struct PlateRt {
+    PlateParams pp;        // device-side description (pointers resolved)
+    int variant = 0;       // index into the spec table (0 = dynamic interpreter)
+    long long n_tiles = 1; // for the current capacity
+    long long partial_offset = 0;
+    double obs_const = 0.0;
+};
+
+struct jbugs_plan_s {
+    int device = 0;
+    int num_sms = 148;
+    jbugs_plan_header h{};
+    std::vector<jbugs_global> globals;
+    std::vector<jbugs_gop> gtape;
+    std::vector<jbugs_data_desc> data;
+    std::vector<jbugs_plate> plates;
+    std::vector<jbugs_local> locals;
+    std::vector<jbugs_term> terms;
+    std::vector<void*> d_slots;
+    std::vector<char> uploaded;
+    std::vector<PlateRt> rt;
+    std::vector<long long> shard_i0, shard_i1;
+    GlobalsParams gp{};
+    GTapeParams tp{};
+    // workspaces sized for cap_C chains
+    long long cap_C = 0, ldg = 0;
+    double* d_gvals = nullptr;
+    double* d_partial = nullptr;
+    size_t partial_bytes = 0;
+    double* d_red = nullptr;   // [1 + NG][ldg] reduced partials (multi-GPU path)
+    int* d_flags = nullptr;
+    int* d_any_bad = nullptr;
+    // staging for host pointers / PARAM_FAST
+    double *s_theta = nullptr, *s_grad = nullptr, *s_theta_t = nullptr, *s_grad_t = nullptr, *s_logp = nullptr;
+    int* s_status = nullptr;
+    long long s_C = 0;
+    // library-owned batch
+    double *b_theta = nullptr, *b_grad = nullptr, *b_logp = nullptr;
+    int* b_status = nullptr;
+    // options / stats
+    int force_dynamic = 0;
+    long long tile_override = 0;
+    long long launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float last_plate_ms = 0.f, last_total_ms = 0.f;
+    bool timing = true;
+    // comm
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+static int set_device(const jbugs_plan* p) {
+    CU(cudaSetDevice(p->device));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ plate lowering to device params
+static int resolve_arg(const jbugs_plan* p, const jbugs_arg& a, ArgS& s, ArgV& v, std::vector<int>& gref, int max_local) {
+    s.kind = (int)a.kind;
+    s.id = 0;
+    v.ptr = nullptr;
+    v.value = a.value;
+    switch (a.kind) {
+    case JBUGS_ARG_CONST:
+    case JBUGS_ARG_ONE: return 0;
+    case JBUGS_ARG_GVAL: {
+        if (a.id < 0 || a.id >= (int)(p->h.n_globals + p->h.n_gtape)) return fail(JBUGS_ERR_INVALID, "gval id out of range");
+        auto it = std::find(gref.begin(), gref.end(), a.id);
+        if (it == gref.end()) {
+            gref.push_back(a.id);
+            s.id = (int)gref.size() - 1;
+        } else {
+            s.id = (int)(it - gref.begin());
+        }
+        return 0;
+    }
+    case JBUGS_ARG_LOCAL:
+        if (a.id < 0 || a.id >= max_local) return fail(JBUGS_ERR_INVALID, "local id out of range");
+        s.id = a.id;
+        return 0;
+    case JBUGS_ARG_DATA_I:
+    case JBUGS_ARG_DATA_J:
+    case JBUGS_ARG_DATA_IJ:
+        if (a.id < 0 || a.id >= (int)p->h.n_data) return fail(JBUGS_ERR_INVALID, "data slot out of range");
+        if (p->data[a.id].dtype != 0) return fail(JBUGS_ERR_INVALID, "data slot %d is not float64", a.id);
+        v.ptr = (const double*)p->d_slots[a.id];
+        return 0;
+    default: return fail(JBUGS_ERR_INVALID, "unknown argument kind %u", a.kind);
+    }
+}
+
+static int check_len(const jbugs_plan* p, const jbugs_arg& a, long long N, long long T, const char* what) {
+    long long need = 0;
+    if (a.kind == JBUGS_ARG_DATA_I) need = N;
+    else if (a.kind == JBUGS_ARG_DATA_J) need = T;
+    else if (a.kind == JBUGS_ARG_DATA_IJ) need = N * T;
+    else return 0;
+    if (p->data[a.id].len < need) return fail(JBUGS_ERR_INVALID, "%s: data slot %d has %lld elements, plate needs %lld", what, a.id, (long long)p->data[a.id].len, need);
+    return 0;
+}
+
+static int build_plate(jbugs_plan* p, int k) {
+    const jbugs_plate& pl = p->plates[k];
+    PlateRt& r = p->rt[k];
+    PlateParams& pp = r.pp;
+    memset(&pp, 0, sizeof pp);
+    if (pl.N < 0 || pl.T < 1) return fail(JBUGS_ERR_INVALID, "plate %d: bad extents", k);
+    if (pl.n_locals > (uint32_t)MAX_LOC) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: more than %d locals", k, MAX_LOC);
+    if (pl.n_link > JBUGS_MAX_LINK) return fail(JBUGS_ERR_INVALID, "plate %d: link tape too long", k);
+    if (pl.family >= JBUGS_FAM_COUNT) return fail(JBUGS_ERR_INVALID, "plate %d: unknown family", k);
+    if (pl.eta_arg > 1) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: eta_arg > 1", k);
+    const jbugs_local* L = p->locals.data() + pl.first_local;
+    const jbugs_term* T = p->terms.data() + pl.first_term;
+    std::vector<int> gref;
+    // canonical term order: GVAL-coef terms, then one term per local (in local order), then an offset
+    int t = 0, kg = 0, nl = 0, has_off = 0;
+    while (t < (int)pl.n_terms && T[t].coef.kind == JBUGS_ARG_GVAL) { ++t; ++kg; }
+    while (t < (int)pl.n_terms && T[t].coef.kind == JBUGS_ARG_LOCAL && T[t].coef.id == nl) { ++t; ++nl; }
+    if (t < (int)pl.n_terms && T[t].coef.kind == JBUGS_ARG_CONST && T[t].coef.value == 1.0) { ++t; has_off = 1; }
+    if (t != (int)pl.n_terms || (pl.has_obs && nl != (int)pl.n_locals))
+        return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: terms are not in canonical order (global terms, one term per local, offset)", k);
+    if (kg > MAX_GT) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: more than %d global terms", k, MAX_GT);
+    PlateShape& sh = pp.sh;
+    PlateVals& V = pp.v;
+    sh.kg = kg; sh.nl = (int)pl.n_locals; sh.has_off = has_off;
+    sh.family = (int)pl.family; sh.eta_arg = (int)pl.eta_arg; sh.has_obs = (int)pl.has_obs; sh.n_link = (int)pl.n_link;
+    for (int q = 0; q < JBUGS_MAX_LINK; ++q) sh.link[q] = q < (int)pl.n_link ? (int)pl.link[q] : 0;
+    V.N = pl.N; V.T = pl.T;
+    int rc;
+    for (int q = 0; q < kg; ++q) {
+        ArgS s; ArgV v;
+        if ((rc = resolve_arg(p, T[q].coef, s, v, gref, 0))) return rc;
+        if (s.id != q) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: a global appears in two terms", k);
+    }
+    for (int q = 0; q < (int)pl.n_terms; ++q) {
+        if ((rc = resolve_arg(p, T[q].cov, sh.cov[q], V.cov[q], gref, 0))) return rc;
+        if (sh.cov[q].kind == JBUGS_ARG_GVAL || sh.cov[q].kind == JBUGS_ARG_LOCAL)
+            return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: covariates must be data", k);
+        if ((rc = check_len(p, T[q].cov, pl.N, pl.T, "covariate"))) return rc;
+    }
+    if (pl.has_obs) {
+        if ((rc = resolve_arg(p, pl.y, sh.y, V.y, gref, 0))) return rc;
+        if ((rc = check_len(p, pl.y, pl.N, pl.T, "y"))) return rc;
+        for (int q = 0; q < 2; ++q) {
+            if (q == (int)pl.eta_arg) continue;
+            if ((rc = resolve_arg(p, pl.aux[q], sh.aux[q], V.aux[q], gref, (int)pl.n_locals))) return rc;
+            if ((rc = check_len(p, pl.aux[q], pl.N, pl.T, "aux"))) return rc;
+        }
+    }
+    for (int l = 0; l < (int)pl.n_locals; ++l) {
+        LocalS& ls = sh.loc[l];
+        LocalV& lv = V.loc[l];
+        if (L[l].family >= JBUGS_FAM_COUNT) return fail(JBUGS_ERR_INVALID, "plate %d local %d: unknown family", k, l);
+        ls.level = (int)L[l].level; ls.transform = (int)L[l].transform; ls.family = (int)L[l].family;
+        ls.has_idx = L[l].idx_slot >= 0;
+        lv.base = L[l].theta_base; lv.si = L[l].stride_i; lv.sj = L[l].stride_j;
+        lv.lb = L[l].lb; lv.ub = L[l].ub; lv.idx = nullptr;
+        if (ls.has_idx) {
+            if (L[l].idx_slot >= (int)p->h.n_data || p->data[L[l].idx_slot].dtype != 1)
+                return fail(JBUGS_ERR_INVALID, "plate %d local %d: index slot must be int64", k, l);
+            const long long need = ls.level == JBUGS_LEVEL_OBS ? pl.N * pl.T : pl.N;
+            if (p->data[L[l].idx_slot].len < need) return fail(JBUGS_ERR_INVALID, "plate %d local %d: index array too short", k, l);
+            lv.idx = (const long long*)p->d_slots[L[l].idx_slot];
+        } else {
+            // every addressed slot must lie inside [0, D)
+            const long long jmax = ls.level == JBUGS_LEVEL_OBS ? pl.T - 1 : 0;
+            const long long c[4] = {lv.base, lv.base + lv.si * (pl.N - 1), lv.base + lv.sj * jmax,
+                                    lv.base + lv.si * (pl.N - 1) + lv.sj * jmax};
+            for (long long x : c)
+                if (pl.N > 0 && (x < 0 || x >= p->h.D)) return fail(JBUGS_ERR_INVALID, "plate %d local %d: theta slot out of range", k, l);
+        }
+        for (int q = 0; q < 2; ++q) {
+            if ((rc = resolve_arg(p, L[l].args[q], ls.args[q], lv.args[q], gref, (int)pl.n_locals))) return rc;
+            if (ls.level == JBUGS_LEVEL_GROUP && (L[l].args[q].kind == JBUGS_ARG_DATA_J || L[l].args[q].kind == JBUGS_ARG_DATA_IJ))
+                return fail(JBUGS_ERR_INVALID, "plate %d local %d: group-level prior indexed by j", k, l);
+            if ((rc = check_len(p, L[l].args[q], pl.N, pl.T, "prior argument"))) return rc;
+        }
+    }
+    if ((int)gref.size() > MAX_GREF) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d references more than %d global values", k, MAX_GREF);
+    sh.n_gref = (int)gref.size();
+    for (int q = 0; q < MAX_GREF; ++q) V.gref[q] = q < (int)gref.size() ? gref[q] : 0;
+    V.i0 = p->shard_i0[k]; V.i1 = p->shard_i1[k];
+    r.variant = p->force_dynamic ? 0 : select_spec(sh);
+    return 0;
+}
+
+static int rebuild_plates(jbugs_plan* p) {
+    for (int k = 0; k < (int)p->h.n_plates; ++k) {
+        int rc = build_plate(p, k);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI: basics
+extern "C" const char* jbugs_last_error(void) { return g_err.c_str(); }
+extern "C" int jbugs_version(void) { return 100; }
+
+extern "C" int jbugs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int jbugs_plan_create(const void* blob, size_t nbytes, int device, jbugs_plan** out) {
+    if (!blob || !out) return fail(JBUGS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (nbytes < sizeof(jbugs_plan_header)) return fail(JBUGS_ERR_INVALID, "plan blob shorter than its header");
+    jbugs_plan_header h;
+    memcpy(&h, blob, sizeof h);
+    if (memcmp(h.magic, JBUGS_PLAN_MAGIC, 8) != 0) return fail(JBUGS_ERR_INVALID, "bad plan magic");
+    if (h.version != JBUGS_PLAN_VERSION) return fail(JBUGS_ERR_INVALID, "plan version %u, library speaks %u", h.version, JBUGS_PLAN_VERSION);
+    const size_t need = sizeof h + h.n_globals * sizeof(jbugs_global) + h.n_gtape * sizeof(jbugs_gop) +
+                        h.n_data * sizeof(jbugs_data_desc) + h.n_plates * sizeof(jbugs_plate) +
+                        h.n_locals * sizeof(jbugs_local) + h.n_terms * sizeof(jbugs_term);
+    if (need != nbytes) return fail(JBUGS_ERR_INVALID, "plan blob is %zu bytes, records need %zu", nbytes, need);
+    if (h.D < 0) return fail(JBUGS_ERR_INVALID, "negative dimension");
+    if (h.n_globals + h.n_gtape > (uint32_t)MAX_GVALS) return fail(JBUGS_ERR_UNSUPPORTED, "more than %d global values", MAX_GVALS);
+    if (h.n_plates > 8) return fail(JBUGS_ERR_UNSUPPORTED, "more than 8 plates");
+    int ndev = jbugs_device_count();
+    if (ndev <= 0) return fail(JBUGS_ERR_CUDA, "no CUDA device is available (libjbugs_cuda has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(JBUGS_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+
+    jbugs_plan* p = new jbugs_plan_s();
+    p->device = device;
+    p->h = h;
+    const char* c = (const char*)blob + sizeof h;
+    auto take = [&](auto& vec, size_t n) {
+        vec.resize(n);
+        if (n) memcpy(vec.data(), c, n * sizeof(vec[0]));
+        c += n * sizeof(vec[0]);
+    };
+    take(p->globals, h.n_globals);
+    take(p->gtape, h.n_gtape);
+    take(p->data, h.n_data);
+    take(p->plates, h.n_plates);
+    take(p->locals, h.n_locals);
+    take(p->terms, h.n_terms);
+    auto destroy = [&](int rc) {
+        jbugs_plan_destroy(p);
+        return rc;
+    };
+    // validation of record ranges
+    for (auto& pl : p->plates) {
+        if ((size_t)pl.first_local + pl.n_locals > p->locals.size() || (size_t)pl.first_term + pl.n_terms > p->terms.size())
+            return destroy(fail(JBUGS_ERR_INVALID, "plate record ranges exceed the blob"));
+    }
+    for (size_t k = 0; k < p->globals.size(); ++k) {
+        const auto& g = p->globals[k];
+        if (g.theta_idx < 0 || g.theta_idx >= h.D) return destroy(fail(JBUGS_ERR_INVALID, "global %zu: theta slot out of range", k));
+        if (g.family >= JBUGS_FAM_COUNT) return destroy(fail(JBUGS_ERR_INVALID, "global %zu: unknown family", k));
+        for (int q = 0; q < 2; ++q)
+            if (g.args[q].kind == JBUGS_ARG_GVAL && (g.args[q].id < 0 || g.args[q].id >= (int)(h.n_globals + h.n_gtape)))
+                return destroy(fail(JBUGS_ERR_INVALID, "global %zu: argument out of range", k));
+            else if (g.args[q].kind != JBUGS_ARG_GVAL && g.args[q].kind != JBUGS_ARG_CONST && g.args[q].kind != JBUGS_ARG_ONE)
+                return destroy(fail(JBUGS_ERR_INVALID, "global %zu: prior arguments must be constants or global values", k));
+    }
+    for (size_t k = 0; k < p->gtape.size(); ++k) {
+        const auto& o = p->gtape[k];
+        const int lim = (int)(h.n_globals + k);  // may only look backwards
+        if ((o.a.kind == JBUGS_ARG_GVAL && (o.a.id < 0 || o.a.id >= lim)) ||
+            (o.op >= 16 && o.b.kind == JBUGS_ARG_GVAL && (o.b.id < 0 || o.b.id >= lim)))
+            return destroy(fail(JBUGS_ERR_INVALID, "gtape op %zu references a later value", k));
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return destroy(fail(JBUGS_ERR_CUDA, "cudaSetDevice(%d) failed", device));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return destroy(fail(JBUGS_ERR_CUDA, "cudaGetDeviceProperties failed"));
+    p->num_sms = prop.multiProcessorCount;
+    p->d_slots.assign(h.n_data, nullptr);
+    p->uploaded.assign(h.n_data, 0);
+    for (uint32_t k = 0; k < h.n_data; ++k) {
+        if (p->data[k].len < 0) return destroy(fail(JBUGS_ERR_INVALID, "data slot %u: negative length", k));
+        const size_t bytes = (size_t)std::max<long long>(p->data[k].len, 1) * 8;
+        if (cudaMalloc(&p->d_slots[k], bytes) != cudaSuccess) return destroy(fail(JBUGS_ERR_CUDA, "cudaMalloc of data slot %u (%zu bytes) failed", k, bytes));
+    }
+    p->rt.resize(h.n_plates);
+    p->shard_i0.assign(h.n_plates, 0);
+    p->shard_i1.resize(h.n_plates);
+    for (uint32_t k = 0; k < h.n_plates; ++k) p->shard_i1[k] = p->plates[k].N;
+    p->gp.n_globals = (int)h.n_globals;
+    p->gp.n_gtape = (int)h.n_gtape;
+    p->gp.transformed = (h.flags & JBUGS_FLAG_TRANSFORMED) != 0;
+    for (uint32_t k = 0; k < h.n_globals; ++k) p->gp.g[k] = p->globals[k];
+    for (uint32_t k = 0; k < h.n_gtape; ++k) p->tp.op[k] = p->gtape[k];
+    int rc = rebuild_plates(p);
+    if (rc) return destroy(rc);
+    for (auto& e : p->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) return destroy(fail(JBUGS_ERR_CUDA, "cudaEventCreate failed"));
+    if (cudaMalloc(&p->d_any_bad, sizeof(int)) != cudaSuccess) return destroy(fail(JBUGS_ERR_CUDA, "cudaMalloc failed"));
+    *out = p;
+    return JBUGS_OK;
+}
+
+static void free_workspace(jbugs_plan* p) {
+    cudaFree(p->d_gvals); p->d_gvals = nullptr;
+    cudaFree(p->d_partial); p->d_partial = nullptr; p->partial_bytes = 0;
+    cudaFree(p->d_red); p->d_red = nullptr;
+    cudaFree(p->d_flags); p->d_flags = nullptr;
+    p->cap_C = 0;
+}
+
+static void free_staging(jbugs_plan* p) {
+    cudaFree(p->s_theta); cudaFree(p->s_grad); cudaFree(p->s_theta_t); cudaFree(p->s_grad_t); cudaFree(p->s_logp); cudaFree(p->s_status);
+    p->s_theta = p->s_grad = p->s_theta_t = p->s_grad_t = p->s_logp = nullptr;
+    p->s_status = nullptr;
+    p->s_C = 0;
+}
+
+extern "C" int jbugs_batch_free(jbugs_plan* p) {
+    if (!p) return fail(JBUGS_ERR_INVALID, "null plan");
+    cudaSetDevice(p->device);
+    cudaFree(p->b_theta); cudaFree(p->b_grad); cudaFree(p->b_logp); cudaFree(p->b_status);
+    p->b_theta = p->b_grad = p->b_logp = nullptr;
+    p->b_status = nullptr;
+    return JBUGS_OK;
+}
+
+extern "C" int jbugs_comm_destroy(jbugs_plan* p) {
+    if (!p) return fail(JBUGS_ERR_INVALID, "null plan");
+    if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
+    p->comm = nullptr;
+    p->nranks = 1;
+    p->rank = 0;
+    return JBUGS_OK;
+}
+
+extern "C" int jbugs_plan_destroy(jbugs_plan* p) {
+    if (!p) return JBUGS_OK;
+    cudaSetDevice(p->device);
+    jbugs_comm_destroy(p);
+    for (void* d : p->d_slots) cudaFree(d);
+    free_workspace(p);
+    free_staging(p);
+    jbugs_batch_free(p);
+    cudaFree(p->d_any_bad);
+    for (auto& e : p->ev)
+        if (e) cudaEventDestroy(e);
+    delete p;
+    return JBUGS_OK;
+}
+
+extern "C" int64_t jbugs_dim(const jbugs_plan* p) { return p ? p->h.D : -1; }
+extern "C" int64_t jbugs_launch_count(const jbugs_plan* p) { return p ? p->launches : -1; }
+
+extern "C" int jbugs_plan_upload_data(jbugs_plan* p, int slot, const void* src, size_t nbytes, int dtype) {
+    if (!p || !src) return fail(JBUGS_ERR_INVALID, "null argument");
+    if (slot < 0 || slot >= (int)p->h.n_data) return fail(JBUGS_ERR_INVALID, "data slot %d out of range", slot);
+    if ((int)p->data[slot].dtype != dtype) return fail(JBUGS_ERR_INVALID, "data slot %d: dtype %d expected", slot, (int)p->data[slot].dtype);
+    if (nbytes != (size_t)p->data[slot].len * 8) return fail(JBUGS_ERR_INVALID, "data slot %d: %zu bytes given, %zu expected", slot, nbytes, (size_t)p->data[slot].len * 8);
+    int rc = set_device(p);
+    if (rc) return rc;
+    CU(cudaMemcpy(p->d_slots[slot], src, nbytes, cudaMemcpyDefault));
+    p->uploaded[slot] = 1;
+    return JBUGS_OK;
+}
+
+extern "C" int jbugs_plan_set_shard(jbugs_plan* p, int plate, int64_t i0, int64_t i1) {
+    if (!p) return fail(JBUGS_ERR_INVALID, "null plan");
+    if (plate < 0 || plate >= (int)p->h.n_plates) return fail(JBUGS_ERR_INVALID, "plate %d out of range", plate);
+    if (i0 < 0 || i1 > p->plates[plate].N || i0 > i1) return fail(JBUGS_ERR_INVALID, "shard [%lld, %lld) outside [0, %lld)", (long long)i0, (long long)i1, (long long)p->plates[plate].N);
+    p->shard_i0[plate] = i0;
+    p->shard_i1[plate] = i1;
+    p->rt[plate].pp.v.i0 = i0;
+    p->rt[plate].pp.v.i1 = i1;
+    p->cap_C = 0;  // force re-tiling
+    return JBUGS_OK;
+}
+
+extern "C" int jbugs_plan_set_option(jbugs_plan* p, const char* key, int64_t value) {
+    if (!p || !key) return fail(JBUGS_ERR_INVALID, "null argument");
+    if (!strcmp(key, "dynamic")) {
+        p->force_dynamic = value != 0;
+        return rebuild_plates(p);
+    }
+    if (!strcmp(key, "tile")) {
+        if (value < 0) return fail(JBUGS_ERR_INVALID, "tile must be >= 0");
+        p->tile_override = value;
+        p->cap_C = 0;
+        return JBUGS_OK;
+    }
+    if (!strcmp(key, "timing")) {
+        p->timing = value != 0;
+        return JBUGS_OK;
+    }
+    return fail(JBUGS_ERR_INVALID, "unknown option '%s'", key);
+}
+
+extern "C" int jbugs_plan_describe(const jbugs_plan* p, char* buf, size_t nbuf) {
+    if (!p || !buf || !nbuf) return fail(JBUGS_ERR_INVALID, "null argument");
+    std::string s;
+    char line[256];
+    snprintf(line, sizeof line, "D=%lld globals=%u gtape=%u plates=%u sms=%d\n", (long long)p->h.D, p->h.n_globals, p->h.n_gtape, p->h.n_plates, p->num_sms);
+    s += line;
+    for (size_t k = 0; k < p->rt.size(); ++k) {
+        const auto& r = p->rt[k];
+        snprintf(line, sizeof line, "plate %zu: N=%lld T=%lld kernel=%s tiles=%lld tile=%lld gref=%d\n", k, r.pp.v.N, r.pp.v.T,
+                 spec_name(r.variant), r.n_tiles, r.pp.v.tile, r.pp.sh.n_gref);
+        s += line;
+    }
+    snprintf(buf, nbuf, "%s", s.c_str());
+    return JBUGS_OK;
+}
+
+extern "C" int jbugs_last_timing(const jbugs_plan* p, float* plate_ms, float* total_ms) {
+    if (!p) return fail(JBUGS_ERR_INVALID, "null plan");
+    if (plate_ms) *plate_ms = p->last_plate_ms;
+    if (total_ms) *total_ms = p->last_total_ms;
+    return JBUGS_OK;
+}
+
+extern "C" int jbugs_host_alloc(void** ptr, size_t nbytes) {
+    if (!ptr) return fail(JBUGS_ERR_INVALID, "null argument");
+    CU(cudaHostAlloc(ptr, nbytes, cudaHostAllocDefault));
+    return JBUGS_OK;
+}
+extern "C" int jbugs_host_free(void* ptr) {
+    CU(cudaFreeHost(ptr));
+    return JBUGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ workspaces
+static long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+static int ensure_workspace(jbugs_plan* p, long long C) {
+    if (C <= p->cap_C) return 0;
+    free_workspace(p);
+    const long long ldg = round_up(C, 16);
+    const int NG = (int)(p->h.n_globals + p->h.n_gtape);
+    const long long chain_tiles = (C + BLOCK - 1) / BLOCK;
+    // tiling: enough CTAs for ~4 full waves at 16 CTAs/SM, tiles no smaller than 4 groups
+    const long long target = (long long)p->num_sms * 16 * 4;
+    long long rows = 0;
+    for (size_t k = 0; k < p->rt.size(); ++k) {
+        PlateRt& r = p->rt[k];
+        const long long n = std::max<long long>(r.pp.v.i1 - r.pp.v.i0, 0);
+        long long nt = std::max<long long>(1, std::min<long long>((target + chain_tiles - 1) / chain_tiles, (n + 3) / 4));
+        long long tile = std::max<long long>(1, (n + nt - 1) / nt);
+        if (p->tile_override > 0) tile = p->tile_override;
+        nt = std::max<long long>(1, (n + tile - 1) / tile);
+        if (nt > 65535) { tile = (n + 65534) / 65535; nt = (n + tile - 1) / tile; }
+        r.pp.v.tile = tile;
+        r.n_tiles = nt;
+        r.partial_offset = rows;
+        rows += nt * (1 + r.pp.sh.n_gref);
+    }
+    CU(cudaMalloc(&p->d_gvals, (size_t)std::max(NG, 1) * ldg * 8));
+    p->partial_bytes = (size_t)std::max<long long>(rows, 1) * ldg * 8;
+    CU(cudaMalloc(&p->d_partial, p->partial_bytes));
+    CU(cudaMalloc(&p->d_red, (size_t)(1 + std::max(NG, 1)) * ldg * 8));
+    CU(cudaMalloc(&p->d_flags, (size_t)ldg * sizeof(int)));
+    p->cap_C = C;
+    p->ldg = ldg;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ evaluation on device-resident CHAIN_FAST buffers
+static int eval_device(jbugs_plan* p, const double* theta, long long ld, long long C, double* logp, double* grad,
+                       int* status, int want_grad, cudaStream_t st) {
+    if (C == 0) return 0;
+    for (uint32_t k = 0; k < p->h.n_data; ++k)
+        if (!p->uploaded[k]) return fail(JBUGS_ERR_STATE, "data slot %u has not been uploaded", k);
+    int rc = ensure_workspace(p, C);
+    if (rc) return rc;
+    const long long ldg = p->ldg;
+    const unsigned chain_tiles = (unsigned)((C + BLOCK - 1) / BLOCK);
+    if (p->timing) CU(cudaEventRecord(p->ev[0], st));
+    prologue_kernel<<<chain_tiles, BLOCK, 0, st>>>(p->gp, p->tp, theta, ld, C, p->d_gvals, ldg, p->d_flags, p->d_any_bad);
+    p->launches++;
+    if (p->timing) CU(cudaEventRecord(p->ev[1], st));
+    FinalParams fp{};
+    fp.n_plates = (int)p->rt.size();
+    for (size_t k = 0; k < p->rt.size(); ++k) {
+        PlateRt& r = p->rt[k];
+        fp.p[k].n_tiles = (int)r.n_tiles;
+        fp.p[k].n_gref = r.pp.sh.n_gref;
+        fp.p[k].offset = r.partial_offset;
+        fp.p[k].obs_const = 0.0;
+        for (int q = 0; q < MAX_GREF; ++q) fp.p[k].gref[q] = r.pp.v.gref[q];
+        if (r.pp.v.i1 <= r.pp.v.i0) { fp.p[k].n_tiles = 0; continue; }
+        dim3 grid(chain_tiles, (unsigned)r.n_tiles);
+        launch_plate(r.variant, grid, st, r.pp, theta, grad, ld, C, p->d_gvals, ldg,
+                     p->d_partial + r.partial_offset * ldg, p->d_flags, want_grad && grad);
+        p->launches++;
+    }
+    if (p->timing) CU(cudaEventRecord(p->ev[2], st));
+    finalize_kernel<<<chain_tiles, BLOCK, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, p->d_partial,
+                                                   p->d_flags, logp, status, p->d_any_bad, want_grad && grad, 1);
+    p->launches++;
+    if (want_grad && grad) {
+        dim3 grid(chain_tiles, (unsigned)std::min<long long>(std::max<long long>(p->h.D, 1), 1024));
+        poison_kernel<<<grid, BLOCK, 0, st>>>(grad, ld, C, p->h.D, p->d_flags, p->d_any_bad);
+        p->launches++;
+    }
+    if (p->timing) CU(cudaEventRecord(p->ev[3], st));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static bool is_device_ptr(const void* ptr) {
+    if (!ptr) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static int ensure_staging(jbugs_plan* p, long long Cc, bool need_t) {
+    const long long D = std::max<long long>(p->h.D, 1);
+    if (Cc > p->s_C) {
+        free_staging(p);
+        const long long ldc = round_up(Cc, 16);
+        CU(cudaMalloc(&p->s_theta, (size_t)D * ldc * 8));
+        CU(cudaMalloc(&p->s_grad, (size_t)D * ldc * 8));
+        CU(cudaMalloc(&p->s_logp, (size_t)ldc * 8));
+        CU(cudaMalloc(&p->s_status, (size_t)ldc * 4));
+        p->s_C = Cc;
+    }
+    if (need_t && !p->s_theta_t) {
+        CU(cudaMalloc(&p->s_theta_t, (size_t)D * p->s_C * 8));
+        CU(cudaMalloc(&p->s_grad_t, (size_t)D * p->s_C * 8));
+    }
+    return 0;
+}
+
+extern "C" int jbugs_eval_batch(jbugs_plan* p, const double* theta, int64_t ld, int64_t C, int layout, double* logp,
+                                double* grad, int32_t* status, int want_grad, int flags, void* stream) {
+    if (!p || !theta || !logp) return fail(JBUGS_ERR_INVALID, "null argument");
+    if (C < 0) return fail(JBUGS_ERR_INVALID, "negative chain count");
+    if (want_grad && !grad) return fail(JBUGS_ERR_INVALID, "want_grad set but grad is null");
+    if (layout != JBUGS_LAYOUT_CHAIN_FAST && layout != JBUGS_LAYOUT_PARAM_FAST) return fail(JBUGS_ERR_INVALID, "unknown layout %d", layout);
+    const long long D = p->h.D;
+    if (layout == JBUGS_LAYOUT_CHAIN_FAST ? ld < C : ld < D) return fail(JBUGS_ERR_INVALID, "leading dimension %lld too small", (long long)ld);
+    int rc = set_device(p);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 0) return JBUGS_OK;
+    const bool dev_io = is_device_ptr(theta) && is_device_ptr(logp) && is_device_ptr(grad) && is_device_ptr(status);
+    if (dev_io && layout == JBUGS_LAYOUT_CHAIN_FAST) {
+        rc = eval_device(p, theta, ld, C, logp, grad, status, want_grad, st);
+        if (rc) return rc;
+        if (!(flags & JBUGS_EVAL_ASYNC)) {
+            CU(cudaStreamSynchronize(st));
+            if (p->timing) {
+                cudaEventElapsedTime(&p->last_plate_ms, p->ev[1], p->ev[2]);
+                cudaEventElapsedTime(&p->last_total_ms, p->ev[0], p->ev[3]);
+            }
+        }
+        return JBUGS_OK;
+    }
+    // host buffers and/or PARAM_FAST: go through library staging in chunks of chains
+    const bool theta_dev = is_device_ptr(theta), logp_dev = is_device_ptr(logp), grad_dev = is_device_ptr(grad), status_dev = is_device_ptr(status);
+    const long long budget = 1LL << 31;  // bytes per staging buffer
+    long long Cc = std::max<long long>(1, std::min<long long>(C, budget / (8 * std::max<long long>(D, 1))));
+    if (Cc >= 16) Cc = Cc / 16 * 16;
+    const bool pf = layout == JBUGS_LAYOUT_PARAM_FAST;
+    rc = ensure_staging(p, Cc, pf);
+    if (rc) return rc;
+    const long long ldc = round_up(p->s_C, 16);
+    float plate_ms = 0.f, total_ms = 0.f;
+    for (long long c0 = 0; c0 < C; c0 += Cc) {
+        const long long n = std::min<long long>(Cc, C - c0);
+        if (pf) {
+            // chains [c0, c0+n) are n contiguous columns of length D (stride ld)
+            const double* src = theta + c0 * ld;
+            if (ld == D) CU(cudaMemcpyAsync(p->s_theta_t, src, (size_t)n * D * 8, cudaMemcpyDefault, st));
+            else CU(cudaMemcpy2DAsync(p->s_theta_t, (size_t)D * 8, src, (size_t)ld * 8, (size_t)D * 8, (size_t)n, cudaMemcpyDefault, st));
+            dim3 g((unsigned)((D + 31) / 32), (unsigned)((n + 31) / 32));
+            transpose_kernel<<<g, 256, 0, st>>>(p->s_theta_t, D, p->s_theta, ldc, n, D);
+            p->launches++;
+        } else {
+            CU(cudaMemcpy2DAsync(p->s_theta, (size_t)ldc * 8, theta + c0, (size_t)ld * 8, (size_t)n * 8, (size_t)D, cudaMemcpyDefault, st));
+        }
+        (void)theta_dev;
+        rc = eval_device(p, p->s_theta, ldc, n, p->s_logp, want_grad ? p->s_grad : nullptr, p->s_status, want_grad, st);
+        if (rc) return rc;
+        if (want_grad) {
+            if (pf) {
+                dim3 g((unsigned)((n + 31) / 32), (unsigned)((D + 31) / 32));
+                transpose_kernel<<<g, 256, 0, st>>>(p->s_grad, ldc, p->s_grad_t, D, D, n);
+                p->launches++;
+                double* dst = grad + c0 * ld;
+                if (ld == D) CU(cudaMemcpyAsync(dst, p->s_grad_t, (size_t)n * D * 8, cudaMemcpyDefault, st));
+                else CU(cudaMemcpy2DAsync(dst, (size_t)ld * 8, p->s_grad_t, (size_t)D * 8, (size_t)D * 8, (size_t)n, cudaMemcpyDefault, st));
+            } else {
+                CU(cudaMemcpy2DAsync(grad + c0, (size_t)ld * 8, p->s_grad, (size_t)ldc * 8, (size_t)n * 8, (size_t)D, cudaMemcpyDefault, st));
+            }
+        }
+        (void)grad_dev; (void)logp_dev; (void)status_dev;
+        CU(cudaMemcpyAsync(logp + c0, p->s_logp, (size_t)n * 8, cudaMemcpyDefault, st));
+        if (status) CU(cudaMemcpyAsync(status + c0, p->s_status, (size_t)n * 4, cudaMemcpyDefault, st));
+        CU(cudaStreamSynchronize(st));
+        if (p->timing) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, p->ev[1], p->ev[2]);
+            cudaEventElapsedTime(&b, p->ev[0], p->ev[3]);
+            plate_ms += a;
+            total_ms += b;
+        }
+    }
+    p->last_plate_ms = plate_ms;
+    p->last_total_ms = total_ms;
+    return JBUGS_OK;
+}
+
+extern "C" int jbugs_batch_alloc(jbugs_plan* p, int64_t C, double** theta_dev, double** grad_dev, double** logp_dev,
+                                 int32_t** status_dev, int64_t* ld) {
+    if (!p || !theta_dev || !grad_dev || !logp_dev || !ld) return fail(JBUGS_ERR_INVALID, "null argument");
+    if (C <= 0) return fail(JBUGS_ERR_INVALID, "C must be positive");
+    int rc = set_device(p);
+    if (rc) return rc;
+    jbugs_batch_free(p);
+    const long long ldc = round_up(C, 16);
+    const size_t bytes = (size_t)std::max<long long>(p->h.D, 1) * ldc * 8;
+    CU(cudaMalloc(&p->b_theta, bytes));
+    CU(cudaMalloc(&p->b_grad, bytes));
+    CU(cudaMalloc(&p->b_logp, (size_t)ldc * 8));
+    CU(cudaMalloc(&p->b_status, (size_t)ldc * 4));
+    *theta_dev = p->b_theta;
+    *grad_dev = p->b_grad;
+    *logp_dev = p->b_logp;
+    if (status_dev) *status_dev = p->b_status;
+    *ld = ldc;
+    return JBUGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ comm
+extern "C" int jbugs_comm_unique_id(void* out) {
+    if (!out) return fail(JBUGS_ERR_INVALID, "null argument");
+    int rc = load_nccl();
+    if (rc) return rc;
+    ncclUniqueId id;
+    int e = g_nccl.GetUniqueId(&id);
+    if (e) return fail(JBUGS_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+    memcpy(out, &id, sizeof id);
+    return JBUGS_OK;
+}
+
+extern "C" int jbugs_comm_init(jbugs_plan* p, int nranks, int rank, const void* unique_id) {
+    if (!p || !unique_id) return fail(JBUGS_ERR_INVALID, "null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(JBUGS_ERR_INVALID, "bad rank %d of %d", rank, nranks);
+    int rc = load_nccl();
+    if (rc) return rc;
+    rc = set_device(p);
+    if (rc) return rc;
+    jbugs_comm_destroy(p);
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof id);
+    int e = g_nccl.CommInitRank(&p->comm, nranks, id, rank);
+    if (e) return fail(JBUGS_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+    p->nranks = nranks;
+    p->rank = rank;
+    return JBUGS_OK;
+}

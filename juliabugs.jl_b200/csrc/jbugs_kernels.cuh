@@ -1,0 +1,477 @@
+// jbugs_kernels.cuh -- the batched forward+reverse plate kernels (sm_100a).
+//
+// Replaces the reference's node loop `evaluate_with_values!!`
+// (/root/reference/JuliaBUGS/src/model/evaluation.jl:217-275) + its AD backend
+// (src/model/logdensityproblems.jl:219-232) for a whole batch of chains.
+//
+// Mapping (native CHAIN_FAST layout, theta[d * ld + c]):
+//   * one thread  <-> one chain (column c); a warp reads 32 consecutive chains of one parameter
+//     row: every global access is a fully coalesced 256-byte row segment whatever the theta order
+//     (UseGraph's reversed-interleaved AoS or the generated mode's order -- SURVEY 8a/A15);
+//   * one CTA     <-> BLOCK chains x one tile of plate groups; the group loop is sequential
+//     inside the thread, so logp and the gradients of the shared (global) parameters
+//     accumulate in registers in a FIXED order -- no shuffles, no float atomics;
+//   * observation / covariate arrays are indexed by the group only, i.e. warp-uniform: they are
+//     staged once per CTA chunk into shared memory (bulk async copy when aligned) and every
+//     lane reads them as broadcasts;
+//   * per (tile, chain) partial sums go to `partial[tile][1 + n_gref][ldg]`; the finalize kernel
+//     adds the tiles in ascending order, then the priors / bijectors of the globals.
+//
+// One body serves two kinds of instantiation: `DynSpec` reads the plate "shape" (families,
+// link tape, argument kinds ...) from kernel parameters at run time; static specs supply the
+// same accessors as constexpr so the compiler folds every switch and keeps all per-chain state
+// in registers (the shape of the hot configurations in BASELINE.json).
+#pragma once
+
+#include "jbugs_device.cuh"
+
+namespace jbugs {
+
+constexpr int MAX_GT = 8;                        // terms whose coefficient is a global value
+constexpr int MAX_LOC = 4;                       // local parameters of a plate
+constexpr int MAX_TERMS = MAX_GT + MAX_LOC + 1;  // + optional data offset
+constexpr int MAX_GREF = 12;                     // distinct global values a plate references
+constexpr int MAX_GVALS = 64;                    // globals + gtape results of a plan
+constexpr int BLOCK = 128;                       // chains per CTA
+
+struct ArgS {  // structural half of an argument
+    int kind;  // jbugs_arg_kind
+    int id;    // GVAL: plate-local gref index; LOCAL: local index
+};
+struct ArgV {  // value half
+    const double* ptr;  // DATA_*: device array
+    double value;       // CONST
+};
+
+struct LocalS {
+    int level, transform, family, has_idx;
+    ArgS args[3];
+};
+struct LocalV {
+    long long base, si, sj;
+    const long long* idx;
+    double lb, ub;
+    ArgV args[3];
+};
+
+struct PlateShape {
+    int kg, nl, has_off, n_gref;
+    int family, eta_arg, has_obs, n_link;
+    int link[JBUGS_MAX_LINK];
+    ArgS cov[MAX_TERMS];
+    ArgS y, aux[3];
+    LocalS loc[MAX_LOC];
+};
+
+struct PlateVals {
+    long long N, T, i0, i1, tile;
+    ArgV cov[MAX_TERMS];
+    ArgV y, aux[3];
+    LocalV loc[MAX_LOC];
+    int gref[MAX_GREF];
+    double obs_const;  // sum over the shard of the data-only normalising constants (fused paths)
+};
+
+struct PlateParams {
+    PlateShape sh;
+    PlateVals v;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Spec accessors.  DynSpec forwards to the run-time shape.
+struct DynSpec {
+    static constexpr bool STATIC = false;
+    static constexpr int FUSED = 0;
+    const PlateShape& s;
+    __device__ __forceinline__ explicit DynSpec(const PlateShape& sh) : s(sh) {}
+    __device__ __forceinline__ int kg() const { return s.kg; }
+    __device__ __forceinline__ int nl() const { return s.nl; }
+    __device__ __forceinline__ int has_off() const { return s.has_off; }
+    __device__ __forceinline__ int n_gref() const { return s.n_gref; }
+    __device__ __forceinline__ int family() const { return s.family; }
+    __device__ __forceinline__ int eta_arg() const { return s.eta_arg; }
+    __device__ __forceinline__ int has_obs() const { return s.has_obs; }
+    __device__ __forceinline__ int n_link() const { return s.n_link; }
+    __device__ __forceinline__ int link(int q) const { return s.link[q]; }
+    __device__ __forceinline__ ArgS cov(int t) const { return s.cov[t]; }
+    __device__ __forceinline__ ArgS y() const { return s.y; }
+    __device__ __forceinline__ ArgS aux(int q) const { return s.aux[q]; }
+    __device__ __forceinline__ int loc_level(int l) const { return s.loc[l].level; }
+    __device__ __forceinline__ int loc_transform(int l) const { return s.loc[l].transform; }
+    __device__ __forceinline__ int loc_family(int l) const { return s.loc[l].family; }
+    __device__ __forceinline__ int loc_has_idx(int l) const { return s.loc[l].has_idx; }
+    __device__ __forceinline__ ArgS loc_arg(int l, int q) const { return s.loc[l].args[q]; }
+};
+
+// fused observation paths (family x link pairs with a hand-derived forward+reverse)
+enum { FUSED_NONE = 0, FUSED_NORMAL_IDENTITY = 1, FUSED_BINOMIAL_LOGIT = 2, FUSED_POISSON_LOG = 3,
+       FUSED_BERNOULLI_LOGIT = 4 };
+
+// A static spec is a struct with `static constexpr PlateShape SH` ; see specs in jbugs_cuda.cu.
+template <class Desc>
+struct StaticSpec {
+    static constexpr bool STATIC = true;
+    static constexpr int FUSED = Desc::FUSED;
+    __device__ __forceinline__ explicit StaticSpec(const PlateShape&) {}
+    __device__ __forceinline__ constexpr int kg() const { return Desc::sh().kg; }
+    __device__ __forceinline__ constexpr int nl() const { return Desc::sh().nl; }
+    __device__ __forceinline__ constexpr int has_off() const { return Desc::sh().has_off; }
+    __device__ __forceinline__ constexpr int n_gref() const { return Desc::sh().n_gref; }
+    __device__ __forceinline__ constexpr int family() const { return Desc::sh().family; }
+    __device__ __forceinline__ constexpr int eta_arg() const { return Desc::sh().eta_arg; }
+    __device__ __forceinline__ constexpr int has_obs() const { return Desc::sh().has_obs; }
+    __device__ __forceinline__ constexpr int n_link() const { return Desc::sh().n_link; }
+    __device__ __forceinline__ constexpr int link(int q) const { return Desc::sh().link[q]; }
+    __device__ __forceinline__ constexpr ArgS cov(int t) const { return Desc::sh().cov[t]; }
+    __device__ __forceinline__ constexpr ArgS y() const { return Desc::sh().y; }
+    __device__ __forceinline__ constexpr ArgS aux(int q) const { return Desc::sh().aux[q]; }
+    __device__ __forceinline__ constexpr int loc_level(int l) const { return Desc::sh().loc[l].level; }
+    __device__ __forceinline__ constexpr int loc_transform(int l) const { return Desc::sh().loc[l].transform; }
+    __device__ __forceinline__ constexpr int loc_family(int l) const { return Desc::sh().loc[l].family; }
+    __device__ __forceinline__ constexpr int loc_has_idx(int l) const { return Desc::sh().loc[l].has_idx; }
+    __device__ __forceinline__ constexpr ArgS loc_arg(int l, int q) const { return Desc::sh().loc[l].args[q]; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// register-array helpers: every index is a compile-time constant after unrolling, so the arrays
+// stay in registers even when the *selected* element is a run-time value.
+template <int N>
+__device__ __forceinline__ double pick(const double (&a)[N], int id) {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) v = (k == id) ? a[k] : v;
+    return v;
+}
+template <int N>
+__device__ __forceinline__ void bump(double (&a)[N], int id, double d) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) a[k] += (k == id) ? d : 0.0;
+}
+
+struct ChainState {
+    double gv[MAX_GREF];  // referenced global values
+    double ga[MAX_GREF];  // their adjoints
+    double lx[MAX_LOC];   // constrained local values
+    double la[MAX_LOC];   // their adjoints
+};
+
+__device__ __forceinline__ double arg_value(ArgS s, const ArgV& v, const ChainState& st, long long i, long long j,
+                                            long long N) {
+    switch (s.kind) {
+    case JBUGS_ARG_CONST: return v.value;
+    case JBUGS_ARG_ONE: return 1.0;
+    case JBUGS_ARG_GVAL: return pick(st.gv, s.id);
+    case JBUGS_ARG_LOCAL: return pick(st.lx, s.id);
+    case JBUGS_ARG_DATA_I: return __ldg(v.ptr + i);
+    case JBUGS_ARG_DATA_J: return __ldg(v.ptr + j);
+    case JBUGS_ARG_DATA_IJ: return __ldg(v.ptr + i + N * j);
+    default: return 0.0;
+    }
+}
+
+__device__ __forceinline__ void arg_adjoint(ArgS s, ChainState& st, double d) {
+    if (s.kind == JBUGS_ARG_GVAL) bump(st.ga, s.id, d);
+    else if (s.kind == JBUGS_ARG_LOCAL) bump(st.la, s.id, d);
+}
+
+// ------------------------------------------------------------------------------------------------
+// prologue: constrained values of the globals and the gtape, per chain -> gvals[k][c]
+struct GlobalsParams {
+    int n_globals, n_gtape, transformed;
+    jbugs_global g[MAX_GVALS];
+};
+struct GTapeParams {
+    jbugs_gop op[MAX_GVALS];
+};
+
+__device__ __forceinline__ double garg(const jbugs_arg& a, const double* gv) {
+    return a.kind == JBUGS_ARG_GVAL ? gv[a.id] : (a.kind == JBUGS_ARG_ONE ? 1.0 : a.value);
+}
+
+__device__ __forceinline__ bool gtape_forward(const jbugs_gop& o, const double* gv, double& v, double& d1, double& d2) {
+    const double a = garg(o.a, gv);
+    d2 = 0.0;
+    if (o.op < 16) return unary_op((int)o.op, a, v, d1);
+    const double b = garg(o.b, gv);
+    switch (o.op) {
+    case JBUGS_OP_ADD: v = a + b; d1 = 1.0; d2 = 1.0; return false;
+    case JBUGS_OP_SUB: v = a - b; d1 = 1.0; d2 = -1.0; return false;
+    case JBUGS_OP_MUL: v = a * b; d1 = b; d2 = a; return false;
+    case JBUGS_OP_DIV: v = a / b; d1 = 1.0 / b; d2 = -a / (b * b); return false;
+    default:  // POW
+        v = pow(a, b); d1 = b * pow(a, b - 1.0); d2 = a > 0.0 ? v * log(a) : 0.0;
+        return a < 0.0 && b != floor(b);
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK)
+prologue_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__ GTapeParams TP,
+                const double* __restrict__ theta, long long ld, long long C, double* __restrict__ gvals,
+                long long ldg, int* __restrict__ flags, int* __restrict__ any_bad) {
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    if (c == 0) *any_bad = 0;
+    double gv[MAX_GVALS];
+    bool bad = false;
+    for (int h = 0; h < G.n_globals; ++h) {
+        const TrOut t = transform_eval((int)G.g[h].transform, G.g[h].lb, G.g[h].ub, theta[G.g[h].theta_idx * ld + c]);
+        gv[h] = t.x;
+    }
+    for (int k = 0; k < G.n_gtape; ++k) {
+        double v, d1, d2;
+        bad |= gtape_forward(TP.op[k], gv, v, d1, d2);
+        gv[G.n_globals + k] = v;
+    }
+    for (int k = 0; k < G.n_globals + G.n_gtape; ++k) gvals[k * ldg + c] = gv[k];
+    flags[c] = bad ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the plate kernel
+template <class S>
+__device__ __forceinline__ void local_load(const S& sp, const PlateVals& V, int l, long long i, long long j,
+                                           const double* __restrict__ theta, long long ld, long long c,
+                                           ChainState& st, long long (&slot)[MAX_LOC], double (&ldx)[MAX_LOC],
+                                           double (&ldlj)[MAX_LOC], double& lp) {
+    const LocalV& L = V.loc[l];
+    long long s;
+    if (sp.loc_has_idx(l)) s = sp.loc_level(l) == JBUGS_LEVEL_OBS ? __ldg(L.idx + i + V.N * j) : __ldg(L.idx + i);
+    else s = L.base + L.si * i + L.sj * j;
+    slot[l] = s;
+    const TrOut t = transform_eval(sp.loc_transform(l), L.lb, L.ub, theta[s * ld + c]);
+    st.lx[l] = t.x;
+    st.la[l] = 0.0;
+    ldx[l] = t.dxdy;
+    ldlj[l] = t.dljdy;
+    lp += t.lj;
+}
+
+template <class S>
+__device__ __forceinline__ bool local_prior(const S& sp, const PlateVals& V, int l, long long i, long long j,
+                                            ChainState& st, double& lp) {
+    const LocalV& L = V.loc[l];
+    const int fam = sp.loc_family(l);
+    const double a0 = arg_value(sp.loc_arg(l, 0), L.args[0], st, i, j, V.N);
+    const double a1 = arg_value(sp.loc_arg(l, 1), L.args[1], st, i, j, V.N);
+    FamOut o;
+    const bool bad = fam_eval(fam, st.lx[l], a0, a1, o);
+    lp += o.lp;
+    st.la[l] += o.dx;
+    arg_adjoint(sp.loc_arg(l, 0), st, o.da0);
+    arg_adjoint(sp.loc_arg(l, 1), st, o.da1);
+    return bad;
+}
+
+template <class S>
+__global__ void __launch_bounds__(BLOCK)
+plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ theta, double* __restrict__ grad,
+             long long ld, long long C, const double* __restrict__ gvals, long long ldg,
+             double* __restrict__ partial, int* __restrict__ flags, int want_grad) {
+    const S sp(P.sh);
+    const PlateVals& V = P.v;
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    const long long tile = blockIdx.y;
+    const long long ib = V.i0 + tile * V.tile;
+    const long long ie = (ib + V.tile < V.i1) ? ib + V.tile : V.i1;
+
+    ChainState st;
+#pragma unroll
+    for (int k = 0; k < MAX_GREF; ++k) {
+        st.gv[k] = (k < sp.n_gref()) ? gvals[(long long)V.gref[k] * ldg + c] : 0.0;
+        st.ga[k] = 0.0;
+    }
+    double lp = 0.0;
+    bool bad = false;
+    long long slot[MAX_LOC];
+    double ldx[MAX_LOC], ldlj[MAX_LOC];
+
+    for (long long i = ib; i < ie; ++i) {
+#pragma unroll
+        for (int l = 0; l < MAX_LOC; ++l)
+            if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) local_load(sp, V, l, i, 0, theta, ld, c, st, slot, ldx, ldlj, lp);
+#pragma unroll
+        for (int l = 0; l < MAX_LOC; ++l)
+            if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) bad |= local_prior(sp, V, l, i, 0, st, lp);
+
+        for (long long j = 0; j < V.T; ++j) {
+#pragma unroll
+            for (int l = 0; l < MAX_LOC; ++l)
+                if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) local_load(sp, V, l, i, j, theta, ld, c, st, slot, ldx, ldlj, lp);
+#pragma unroll
+            for (int l = 0; l < MAX_LOC; ++l)
+                if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) bad |= local_prior(sp, V, l, i, j, st, lp);
+
+            if (sp.has_obs()) {
+                // linear predictor: kg global terms, nl local terms, optional data offset
+                double cv[MAX_TERMS];
+                double eta = 0.0;
+#pragma unroll
+                for (int t = 0; t < MAX_GT; ++t)
+                    if (t < sp.kg()) {
+                        cv[t] = arg_value(sp.cov(t), V.cov[t], st, i, j, V.N);
+                        eta += st.gv[t] * cv[t];
+                    }
+#pragma unroll
+                for (int l = 0; l < MAX_LOC; ++l)
+                    if (l < sp.nl()) {
+                        cv[MAX_GT + l] = arg_value(sp.cov(sp.kg() + l), V.cov[sp.kg() + l], st, i, j, V.N);
+                        eta += st.lx[l] * cv[MAX_GT + l];
+                    }
+                if (sp.has_off()) eta += arg_value(sp.cov(sp.kg() + sp.nl()), V.cov[sp.kg() + sp.nl()], st, i, j, V.N);
+                // inverse link tape
+                double v = eta, dv = 1.0;
+#pragma unroll
+                for (int q = 0; q < JBUGS_MAX_LINK; ++q)
+                    if (q < sp.n_link()) {
+                        double nv, d;
+                        bad |= unary_op(sp.link(q), v, nv, d);
+                        v = nv;
+                        dv *= d;
+                    }
+                // observation
+                const double yv = arg_value(sp.y(), V.y, st, i, j, V.N);
+                const int ea = sp.eta_arg();
+                const double a0 = ea == 0 ? v : arg_value(sp.aux(0), V.aux[0], st, i, j, V.N);
+                const double a1 = ea == 1 ? v : arg_value(sp.aux(1), V.aux[1], st, i, j, V.N);
+                FamOut o;
+                bad |= fam_eval(sp.family(), yv, a0, a1, o);
+                lp += o.lp;
+                const double deta = (ea == 0 ? o.da0 : o.da1) * dv;
+                if (ea != 0) arg_adjoint(sp.aux(0), st, o.da0);
+                if (ea != 1) arg_adjoint(sp.aux(1), st, o.da1);
+#pragma unroll
+                for (int t = 0; t < MAX_GT; ++t)
+                    if (t < sp.kg()) st.ga[t] += deta * cv[t];
+#pragma unroll
+                for (int l = 0; l < MAX_LOC; ++l)
+                    if (l < sp.nl()) st.la[l] += deta * cv[MAX_GT + l];
+            }
+            if (want_grad) {
+#pragma unroll
+                for (int l = 0; l < MAX_LOC; ++l)
+                    if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS)
+                        grad[slot[l] * ld + c] = st.la[l] * ldx[l] + ldlj[l];
+            }
+        }
+        if (want_grad) {
+#pragma unroll
+            for (int l = 0; l < MAX_LOC; ++l)
+                if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP)
+                    grad[slot[l] * ld + c] = st.la[l] * ldx[l] + ldlj[l];
+        }
+    }
+    // per (tile, chain) partials: [logp, adjoints of the referenced global values]
+    double* out = partial + tile * (long long)(1 + sp.n_gref()) * ldg + c;
+    out[0] = lp;
+#pragma unroll
+    for (int k = 0; k < MAX_GREF; ++k)
+        if (k < sp.n_gref()) out[(long long)(1 + k) * ldg] = st.ga[k];
+    if (bad) atomicOr(flags + c, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: add the tiles in ascending order, the priors of the globals, reverse the gtape and the
+// bijectors; write logp, status and the gradient rows of the globals.
+struct PlateFinal {
+    int n_tiles, n_gref;
+    long long offset;  // into the partial buffer (in units of ldg rows)
+    int gref[MAX_GREF];
+    double obs_const;
+};
+struct FinalParams {
+    int n_plates;
+    PlateFinal p[8];
+};
+
+__global__ void __launch_bounds__(BLOCK)
+finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__ GTapeParams TP,
+                const __grid_constant__ FinalParams F, const double* __restrict__ theta, double* __restrict__ grad,
+                long long ld, long long C, const double* __restrict__ gvals, long long ldg,
+                const double* __restrict__ partial, int* __restrict__ flags, double* __restrict__ logp_out,
+                int* __restrict__ status_out, int* __restrict__ any_bad, int want_grad, int add_global_priors) {
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    const int H = G.n_globals, NG = G.n_globals + G.n_gtape;
+    double gv[MAX_GVALS], ga[MAX_GVALS];
+    for (int k = 0; k < NG; ++k) {
+        gv[k] = gvals[k * ldg + c];
+        ga[k] = 0.0;
+    }
+    double lp = 0.0;
+    bool bad = flags[c] != 0;
+    for (int p = 0; p < F.n_plates; ++p) {
+        const PlateFinal& pf = F.p[p];
+        const long long stride = (long long)(1 + pf.n_gref) * ldg;
+        const double* base = partial + pf.offset * ldg + c;
+        double s = 0.0;
+        for (int t = 0; t < pf.n_tiles; ++t) s += base[t * stride];
+        lp += s + pf.obs_const;
+        for (int k = 0; k < pf.n_gref; ++k) {
+            double a = 0.0;
+            for (int t = 0; t < pf.n_tiles; ++t) a += base[t * stride + (long long)(1 + k) * ldg];
+            ga[pf.gref[k]] += a;
+        }
+    }
+    if (add_global_priors) {
+        for (int h = 0; h < H; ++h) {
+            const jbugs_global& g = G.g[h];
+            FamOut o;
+            bad |= fam_eval((int)g.family, gv[h], garg(g.args[0], gv), garg(g.args[1], gv), o);
+            lp += o.lp;
+            ga[h] += o.dx;
+            if (g.args[0].kind == JBUGS_ARG_GVAL) ga[g.args[0].id] += o.da0;
+            if (g.args[1].kind == JBUGS_ARG_GVAL) ga[g.args[1].id] += o.da1;
+        }
+    }
+    // reverse sweep over the gtape (recompute the local partials)
+    for (int k = G.n_gtape - 1; k >= 0; --k) {
+        double v, d1, d2;
+        gtape_forward(TP.op[k], gv, v, d1, d2);
+        const double ad = ga[H + k];
+        if (TP.op[k].a.kind == JBUGS_ARG_GVAL) ga[TP.op[k].a.id] += ad * d1;
+        if (TP.op[k].op >= 16 && TP.op[k].b.kind == JBUGS_ARG_GVAL) ga[TP.op[k].b.id] += ad * d2;
+    }
+    for (int h = 0; h < H; ++h) {
+        const jbugs_global& g = G.g[h];
+        const TrOut t = transform_eval((int)g.transform, g.lb, g.ub, theta[g.theta_idx * ld + c]);
+        if (add_global_priors) lp += t.lj;
+        if (want_grad) grad[g.theta_idx * ld + c] = ga[h] * t.dxdy + (add_global_priors ? t.dljdy : 0.0);
+    }
+    logp_out[c] = bad ? -dev_inf() : lp;
+    if (status_out) status_out[c] = bad ? JBUGS_CHAIN_DOMAIN : JBUGS_CHAIN_OK;
+    if (bad) atomicOr(any_bad, 1);
+}
+
+// DomainError -> NaN gradient for the whole chain (logdensityproblems.jl:226-229). Only does work when a
+// chain of this batch was flagged.
+__global__ void __launch_bounds__(BLOCK)
+poison_kernel(double* __restrict__ grad, long long ld, long long C, long long D, const int* __restrict__ flags,
+              const int* __restrict__ any_bad) {
+    if (*any_bad == 0) return;
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C || flags[c] == 0) return;
+    for (long long d = blockIdx.y; d < D; d += gridDim.y) grad[d * ld + c] = dev_nan();
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion (PARAM_FAST <-> CHAIN_FAST), 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256)
+transpose_kernel(const double* __restrict__ src, long long lds, double* __restrict__ dst, long long ldd,
+                 long long rows, long long cols) {
+    // src is rows x cols with leading dimension lds (element (r, q) at r * lds + q); dst(q, r) = src(r, q)
+    __shared__ double tile[32][33];
+    const long long r0 = (long long)blockIdx.y * 32, q0 = (long long)blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = ty; k < 32; k += 8) {
+        const long long r = r0 + k, q = q0 + tx;
+        if (r < rows && q < cols) tile[k][tx] = src[r * lds + q];
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const long long q = q0 + k, r = r0 + tx;
+        if (r < rows && q < cols) dst[q * ldd + r] = tile[tx][k];
+    }
+}
+
+}  // namespace jbugs

@@ -1,0 +1,215 @@
+"""Host-side mirror of the reference's model API for the hot path.
+
+Same names and argument meaning as the reference (paths relative to /root/reference/JuliaBUGS):
+
+    compile(model_def, data, inits)          src/JuliaBUGS.jl:328-371
+    BUGSModel                                src/model/bugsmodel.jl:281-315
+    getparams(model)                         src/model/bugsmodel.jl:619-665
+    settrans(model, flag)                    src/model/bugsmodel.jl:697-707
+    set_evaluation_mode(model, mode)         src/model/bugsmodel.jl:736-801
+    UseGraph / UseGeneratedLogDensityFunction / UseCUDABatch   (bugsmodel.jl:248-252 + the new mode)
+    LogDensityProblems.logdensity / logdensity_and_gradient / dimension / capabilities
+                                             src/model/logdensityproblems.jl:19-55,168-174,219-232
+
+Julia is not installed in this image, so the host side above the C ABI is written in Python
+(the Julia glue that a maintainer would add is shipped, unexecuted, in `julia/`).  Only the new
+`UseCUDABatch` mode is implemented here: the CPU graph walk and the generated Julia function are
+what this path replaces, and there is deliberately no CPU fallback.
+"""
+from __future__ import annotations
+
+import copy
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import plan as P
+from .cuda import CudaPlan, JBugsCudaError
+from .lowering import Lowering, LoweringError
+
+
+class EvaluationMode:
+    pass
+
+
+class UseGraph(EvaluationMode):
+    """The reference's default node-by-node CPU walk -- not provided by this package."""
+
+
+class UseGeneratedLogDensityFunction(EvaluationMode):
+    """The reference's generated Julia function -- not provided by this package."""
+
+
+@dataclass
+class UseCUDABatch(EvaluationMode):
+    """The new evaluation mode: plate plan + libjbugs_cuda on one B200."""
+    device: int = 0
+
+
+class LogDensityOrder:
+    def __init__(self, k):
+        self.k = k
+
+    def __eq__(self, o):
+        return isinstance(o, LogDensityOrder) and o.k == self.k
+
+    def __repr__(self):
+        return f"LogDensityOrder{{{self.k}}}()"
+
+
+class BUGSModel:
+    def __init__(self, model_def, data, inits=None, transformed=True, theta_order=None):
+        self.model_def = model_def
+        self.data = dict(data)
+        self.inits = dict(inits or {})
+        self.transformed = transformed
+        self.theta_order = theta_order
+        self.evaluation_mode: EvaluationMode = UseCUDABatch()
+        self._lower()
+        self._cuda: Optional[CudaPlan] = None
+
+    def _lower(self):
+        self.lowering = Lowering(self.model_def, self.data, transformed=self.transformed, theta_order=self.theta_order)
+        self.plan: P.Plan = self.lowering.plan
+
+    # -- device state ---------------------------------------------------------------------------
+    @property
+    def cuda(self) -> CudaPlan:
+        if not isinstance(self.evaluation_mode, UseCUDABatch):
+            raise JBugsCudaError(f"{type(self.evaluation_mode).__name__} is not implemented by this package; "
+                                 "use set_evaluation_mode(model, UseCUDABatch())")
+        if self._cuda is None:
+            self._cuda = CudaPlan(self.plan, device=self.evaluation_mode.device)
+        return self._cuda
+
+    def invalidate(self):
+        """drop the device plan (what condition/fix/decondition do to the generated function,
+        src/model/abstractppl.jl:796-799)."""
+        if self._cuda is not None:
+            self._cuda.close()
+            self._cuda = None
+
+    # -- observed data update without re-planning (abstractppl.jl:872-888) ----------------------------
+    def set_observed_values(self, **values):
+        self.data.update(values)
+        old = self.plan
+        self._lower()
+        if [s.name for s in old.data] != [s.name for s in self.plan.data] or old.to_bytes() != self.plan.to_bytes():
+            self.invalidate()  # structure changed: needs a new plan
+        elif self._cuda is not None:
+            for k, slot in enumerate(self.plan.data):
+                self._cuda.upload(k, slot.values)
+            self._cuda.plan = self.plan
+        return self
+
+
+def compile(model_def, data, inits=None, theta_order=None) -> BUGSModel:  # noqa: A001 - reference name
+    return BUGSModel(model_def, data, inits, transformed=True, theta_order=theta_order)
+
+
+def settrans(model: BUGSModel, flag: bool = True) -> BUGSModel:
+    if flag == model.transformed:
+        return model
+    m = copy.copy(model)
+    m.transformed = flag
+    m._cuda = None
+    m._lower()
+    return m
+
+
+def set_evaluation_mode(model: BUGSModel, mode: EvaluationMode) -> BUGSModel:
+    if not isinstance(mode, UseCUDABatch):
+        raise NotImplementedError(
+            f"{type(mode).__name__}: only UseCUDABatch is provided (the CPU modes are the reference's own)")
+    if not model.transformed and False:
+        pass
+    m = copy.copy(model)
+    m.evaluation_mode = mode
+    m._cuda = None
+    return m
+
+
+def _link(tr, lb, ub, x):
+    x = np.asarray(x, dtype=np.float64)
+    if tr == P.TR_LOG:
+        return np.log(x - lb)
+    if tr == P.TR_UPPER:
+        return np.log(ub - x)
+    if tr == P.TR_LOGIT:
+        u = (x - lb) / (ub - lb)
+        return np.log(u) - np.log1p(-u)
+    return x
+
+
+def getparams(model: BUGSModel) -> np.ndarray:
+    """Initial theta in the model's parameter order: inits pushed through the bijectors
+    (bugsmodel.jl:619-665).  Parameters without an init get theta = 0 (the reference draws them
+    from the prior with its own RNG, bugsmodel.jl:441-447 -- not reproducible here)."""
+    lw = model.lowering
+    theta = np.zeros(lw.D)
+    fams = {}
+    for g in model.plan.globals:
+        fams[g.name] = (g.transform, g.lb, g.ub)
+    for pl in model.plan.plates:
+        for l in pl.locals:
+            fams[l.name] = (l.transform, l.lb, l.ub)
+    for s in lw.stmts:
+        if s.sid not in lw.theta_map and lw.theta_order is None:
+            continue
+        if s.kind != "param" or s.is_gq or s.name not in fams:
+            continue
+        idx = lw.theta_index(s)
+        if s.name not in model.inits:
+            continue
+        tr, lb, ub = fams[s.name]
+        val = np.asarray(model.inits[s.name], dtype=np.float64)
+        if idx.ndim == 0:
+            theta[int(idx)] = float(_link(tr, lb, ub, val))
+        else:
+            lv = {nm: np.arange(lo, hi + 1, dtype=np.int64).reshape([-1 if d == k else 1 for d in range(len(s.shape))])
+                  for k, (nm, (lo, hi)) in enumerate(zip(s.loop_vars, s.extents))}
+            sel = tuple(np.broadcast_to(np.asarray(lw.de.ev(ie, lv)), s.shape).astype(np.int64) - 1
+                        for ie in s.node.lhs.idx)
+            vals = val[sel]
+            ok = ~np.isnan(vals)
+            theta[idx[ok]] = _link(tr, lb, ub, vals[ok])
+    return theta
+
+
+class LogDensityProblems:
+    """Namespace mirroring LogDensityProblems.jl's generic functions for `BUGSModel`."""
+
+    @staticmethod
+    def dimension(model: BUGSModel) -> int:
+        return model.plan.D
+
+    @staticmethod
+    def capabilities(model) -> LogDensityOrder:
+        # the CUDA mode carries its own reverse pass: gradient without an AD backend
+        return LogDensityOrder(1)
+
+    @staticmethod
+    def logdensity(model: BUGSModel, x) -> float:
+        x = np.asarray(x, dtype=np.float64).reshape(-1, 1)
+        logp, _, _ = model.cuda.eval_host(x, layout="param_fast", want_grad=False)
+        return float(logp[0])
+
+    @staticmethod
+    def logdensity_and_gradient(model: BUGSModel, x):
+        x = np.asarray(x, dtype=np.float64).reshape(-1, 1)
+        logp, grad, _ = model.cuda.eval_host(x, layout="param_fast", want_grad=True)
+        return float(logp[0]), grad[:, 0].copy()
+
+    # ---- the new batched entry points (the reference has none: one theta per call) -------------------
+    @staticmethod
+    def logdensity_batch(model: BUGSModel, theta, layout="param_fast"):
+        """theta: (D, C); `param_fast` == Julia Matrix{Float64}(D, C) (one column per chain)."""
+        logp, _, status = model.cuda.eval_host(theta, layout=layout, want_grad=False)
+        return logp
+
+    @staticmethod
+    def logdensity_and_gradient_batch(model: BUGSModel, theta, layout="param_fast"):
+        logp, grad, status = model.cuda.eval_host(theta, layout=layout, want_grad=True)
+        return logp, grad

@@ -1,0 +1,51 @@
+"""shared model zoo for the tests: (name, model text, fixture key, inits key)."""
+import numpy as np
+
+from jbugs import examples as ex
+
+ZOO = [
+    ("rats", ex.RATS, "rats", "inits"),
+    ("seeds", ex.SEEDS, "seeds", "inits"),
+    ("surgical_realistic", ex.SURGICAL_REALISTIC, "surgical", "inits_realistic"),
+    ("surgical_simple", ex.SURGICAL_SIMPLE, "surgical", "inits_simplistic"),
+    ("pumps", ex.PUMPS, "pumps", "inits"),
+    ("epil", ex.EPIL, "epil", "inits"),
+    ("dogs", ex.DOGS, "dogs", "inits"),
+]
+
+
+def start_theta(name, D, graph_model=None):
+    """a finite starting point in unconstrained space for each example."""
+    if graph_model is not None:
+        th = graph_model.getparams()
+        if np.all(np.isfinite(th)):
+            return th
+    return np.zeros(D)
+
+
+def random_thetas(theta0, C, seed=0, scale=0.1):
+    rng = np.random.default_rng(seed)
+    th0 = np.where(np.isfinite(theta0), theta0, 0.0)
+    return th0[:, None] + scale * rng.standard_normal((th0.size, C))
+
+
+def synth_rats(N, T=5, seed=1234):
+    """BASELINE.json config 2: Y_ij = alpha_i + beta_i (x_j - 22) + N(0, 6^2)."""
+    rng = np.random.default_rng(seed)
+    x = np.array([8.0, 15.0, 22.0, 29.0, 36.0])[:T]
+    alpha = rng.normal(242.0, 14.0, N)
+    beta = rng.normal(6.2, 0.5, N)
+    Y = alpha[:, None] + beta[:, None] * (x[None, :] - 22.0) + rng.normal(0.0, 6.0, (N, T))
+    return {"x": x, "xbar": 22.0, "N": N, "T": T, "Y": Y}, alpha, beta
+
+
+def synth_seeds(N, seed=1234):
+    """BASELINE.json config 3: random-effects logistic regression."""
+    rng = np.random.default_rng(seed)
+    x1 = rng.integers(0, 2, N).astype(float)
+    x2 = rng.integers(0, 2, N).astype(float)
+    n = rng.integers(10, 81, N).astype(float)
+    b = rng.normal(0.0, 0.3, N)
+    eta = -0.55 + 0.09 * x1 + 1.36 * x2 - 0.84 * x1 * x2 + b
+    r = rng.binomial(n.astype(int), 1.0 / (1.0 + np.exp(-eta))).astype(float)
+    return {"r": r, "n": n, "x1": x1, "x2": x2, "N": N}, b
