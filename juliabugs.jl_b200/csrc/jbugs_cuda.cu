@@ -12,6 +12,7 @@
 
 #include "../../include/jbugs_cuda.h"
 #include "jbugs_kernels.cuh"
+#include "jbugs_obsconst.cuh"
 #include "jbugs_specs.cuh"
 
 using namespace jbugs;
@@ -74,6 +75,7 @@ struct PlateRt {
     long long n_tiles = 1; // for the current capacity
     long long partial_offset = 0;
     double obs_const = 0.0;
+    bool const_dirty = true;  // obs_const must be recomputed (new data / shard / kernel variant)
 };
 
 struct jbugs_plan_s {
@@ -251,6 +253,35 @@ static int build_plate(jbugs_plan* p, int k) {
     for (int q = 0; q < MAX_GREF; ++q) V.gref[q] = q < (int)gref.size() ? gref[q] : 0;
     V.i0 = p->shard_i0[k]; V.i1 = p->shard_i1[k];
     r.variant = p->force_dynamic ? 0 : select_spec(sh);
+    r.const_dirty = true;
+    r.obs_const = 0.0;
+    return 0;
+}
+
+// data-only normalising constants of a fused plate (and validation of the data the fused formulas assume)
+static int refresh_obs_const(jbugs_plan* p, int k, cudaStream_t st) {
+    PlateRt& r = p->rt[k];
+    if (!r.const_dirty) return 0;
+    r.obs_const = 0.0;
+    r.const_dirty = false;
+    const int fused = g_specs[r.variant].fused;
+    if (fused != FUSED_BINOMIAL_LOGIT && fused != FUSED_POISSON_LOG && fused != FUSED_BERNOULLI_LOGIT) return 0;
+    const PlateParams& pp = r.pp;
+    if (pp.v.i1 <= pp.v.i0) return 0;
+    double* d_out = p->d_gvals ? p->d_red : nullptr;  // d_red has room for >= 2 doubles once a workspace exists
+    if (!d_out) return fail(JBUGS_ERR_STATE, "internal: workspace missing");
+    obs_const_kernel<<<1, 1024, 0, st>>>(fused, pp.v.y.ptr, pp.v.aux[1].ptr, pp.sh.y.kind == JBUGS_ARG_DATA_IJ,
+                                         pp.sh.aux[1].kind, pp.v.aux[1].value, pp.v.N, pp.v.T, pp.v.i0, pp.v.i1, d_out);
+    p->launches++;
+    double h[2] = {0.0, 0.0};
+    CU(cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h[1] != 0.0) {
+        r.variant = 0;  // data outside the fused formulas' domain: the interpreter reproduces the -Inf semantics
+        r.obs_const = 0.0;
+    } else {
+        r.obs_const = h[0];
+    }
     return 0;
 }
 
@@ -424,6 +455,12 @@ extern "C" int jbugs_plan_upload_data(jbugs_plan* p, int slot, const void* src, 
     if (rc) return rc;
     CU(cudaMemcpy(p->d_slots[slot], src, nbytes, cudaMemcpyDefault));
     p->uploaded[slot] = 1;
+    // new observations: constants of the fused paths (and their validity check) must be redone
+    if (!p->force_dynamic)
+        for (size_t k = 0; k < p->rt.size(); ++k) {
+            p->rt[k].variant = select_spec(p->rt[k].pp.sh);
+            p->rt[k].const_dirty = true;
+        }
     return JBUGS_OK;
 }
 
@@ -435,6 +472,7 @@ extern "C" int jbugs_plan_set_shard(jbugs_plan* p, int plate, int64_t i0, int64_
     p->shard_i1[plate] = i1;
     p->rt[plate].pp.v.i0 = i0;
     p->rt[plate].pp.v.i1 = i1;
+    p->rt[plate].const_dirty = true;
     p->cap_C = 0;  // force re-tiling
     return JBUGS_OK;
 }
@@ -536,6 +574,8 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
     if (rc) return rc;
     const long long ldg = p->ldg;
     const unsigned chain_tiles = (unsigned)((C + BLOCK - 1) / BLOCK);
+    for (size_t k = 0; k < p->rt.size(); ++k)
+        if ((rc = refresh_obs_const(p, (int)k, st))) return rc;
     if (p->timing) CU(cudaEventRecord(p->ev[0], st));
     prologue_kernel<<<chain_tiles, BLOCK, 0, st>>>(p->gp, p->tp, theta, ld, C, p->d_gvals, ldg, p->d_flags, p->d_any_bad);
     p->launches++;
@@ -547,7 +587,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         fp.p[k].n_tiles = (int)r.n_tiles;
         fp.p[k].n_gref = r.pp.sh.n_gref;
         fp.p[k].offset = r.partial_offset;
-        fp.p[k].obs_const = 0.0;
+        fp.p[k].obs_const = r.obs_const;
         for (int q = 0; q < MAX_GREF; ++q) fp.p[k].gref[q] = r.pp.v.gref[q];
         if (r.pp.v.i1 <= r.pp.v.i0) { fp.p[k].n_tiles = 0; continue; }
         dim3 grid(chain_tiles, (unsigned)r.n_tiles);

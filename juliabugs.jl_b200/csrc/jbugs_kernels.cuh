@@ -82,6 +82,9 @@ struct PlateParams {
 struct DynSpec {
     static constexpr bool STATIC = false;
     static constexpr int FUSED = 0;
+    static constexpr int UNROLL = 1;
+    static constexpr int MIN_BLOCKS = 2;
+    __device__ __forceinline__ bool prior_fused(int) const { return false; }
     const PlateShape& s;
     __device__ __forceinline__ explicit DynSpec(const PlateShape& sh) : s(sh) {}
     __device__ __forceinline__ int kg() const { return s.kg; }
@@ -112,6 +115,14 @@ template <class Desc>
 struct StaticSpec {
     static constexpr bool STATIC = true;
     static constexpr int FUSED = Desc::FUSED;
+    static constexpr int UNROLL = Desc::UNROLL;
+    static constexpr int MIN_BLOCKS = Desc::MIN_BLOCKS;
+    // a dnorm prior whose arguments do not vary over the plate keeps sufficient statistics
+    __device__ __forceinline__ constexpr bool prior_fused(int l) const {
+        return Desc::sh().loc[l].family == JBUGS_FAM_NORMAL &&
+               (Desc::sh().loc[l].args[0].kind == JBUGS_ARG_GVAL || Desc::sh().loc[l].args[0].kind == JBUGS_ARG_CONST) &&
+               (Desc::sh().loc[l].args[1].kind == JBUGS_ARG_GVAL || Desc::sh().loc[l].args[1].kind == JBUGS_ARG_CONST);
+    }
     __device__ __forceinline__ explicit StaticSpec(const PlateShape&) {}
     __device__ __forceinline__ constexpr int kg() const { return Desc::sh().kg; }
     __device__ __forceinline__ constexpr int nl() const { return Desc::sh().nl; }
@@ -226,149 +237,11 @@ prologue_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
     flags[c] = bad ? 1 : 0;
 }
 
-// ------------------------------------------------------------------------------------------------
-// the plate kernel
-template <class S>
-__device__ __forceinline__ void local_load(const S& sp, const PlateVals& V, int l, long long i, long long j,
-                                           const double* __restrict__ theta, long long ld, long long c,
-                                           ChainState& st, long long (&slot)[MAX_LOC], double (&ldx)[MAX_LOC],
-                                           double (&ldlj)[MAX_LOC], double& lp) {
-    const LocalV& L = V.loc[l];
-    long long s;
-    if (sp.loc_has_idx(l)) s = sp.loc_level(l) == JBUGS_LEVEL_OBS ? __ldg(L.idx + i + V.N * j) : __ldg(L.idx + i);
-    else s = L.base + L.si * i + L.sj * j;
-    slot[l] = s;
-    const TrOut t = transform_eval(sp.loc_transform(l), L.lb, L.ub, theta[s * ld + c]);
-    st.lx[l] = t.x;
-    st.la[l] = 0.0;
-    ldx[l] = t.dxdy;
-    ldlj[l] = t.dljdy;
-    lp += t.lj;
-}
+}  // namespace jbugs
 
-template <class S>
-__device__ __forceinline__ bool local_prior(const S& sp, const PlateVals& V, int l, long long i, long long j,
-                                            ChainState& st, double& lp) {
-    const LocalV& L = V.loc[l];
-    const int fam = sp.loc_family(l);
-    const double a0 = arg_value(sp.loc_arg(l, 0), L.args[0], st, i, j, V.N);
-    const double a1 = arg_value(sp.loc_arg(l, 1), L.args[1], st, i, j, V.N);
-    FamOut o;
-    const bool bad = fam_eval(fam, st.lx[l], a0, a1, o);
-    lp += o.lp;
-    st.la[l] += o.dx;
-    arg_adjoint(sp.loc_arg(l, 0), st, o.da0);
-    arg_adjoint(sp.loc_arg(l, 1), st, o.da1);
-    return bad;
-}
+#include "jbugs_plate.cuh"
 
-template <class S>
-__global__ void __launch_bounds__(BLOCK)
-plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ theta, double* __restrict__ grad,
-             long long ld, long long C, const double* __restrict__ gvals, long long ldg,
-             double* __restrict__ partial, int* __restrict__ flags, int want_grad) {
-    const S sp(P.sh);
-    const PlateVals& V = P.v;
-    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
-    if (c >= C) return;
-    const long long tile = blockIdx.y;
-    const long long ib = V.i0 + tile * V.tile;
-    const long long ie = (ib + V.tile < V.i1) ? ib + V.tile : V.i1;
-
-    ChainState st;
-#pragma unroll
-    for (int k = 0; k < MAX_GREF; ++k) {
-        st.gv[k] = (k < sp.n_gref()) ? gvals[(long long)V.gref[k] * ldg + c] : 0.0;
-        st.ga[k] = 0.0;
-    }
-    double lp = 0.0;
-    bool bad = false;
-    long long slot[MAX_LOC];
-    double ldx[MAX_LOC], ldlj[MAX_LOC];
-
-    for (long long i = ib; i < ie; ++i) {
-#pragma unroll
-        for (int l = 0; l < MAX_LOC; ++l)
-            if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) local_load(sp, V, l, i, 0, theta, ld, c, st, slot, ldx, ldlj, lp);
-#pragma unroll
-        for (int l = 0; l < MAX_LOC; ++l)
-            if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) bad |= local_prior(sp, V, l, i, 0, st, lp);
-
-        for (long long j = 0; j < V.T; ++j) {
-#pragma unroll
-            for (int l = 0; l < MAX_LOC; ++l)
-                if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) local_load(sp, V, l, i, j, theta, ld, c, st, slot, ldx, ldlj, lp);
-#pragma unroll
-            for (int l = 0; l < MAX_LOC; ++l)
-                if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) bad |= local_prior(sp, V, l, i, j, st, lp);
-
-            if (sp.has_obs()) {
-                // linear predictor: kg global terms, nl local terms, optional data offset
-                double cv[MAX_TERMS];
-                double eta = 0.0;
-#pragma unroll
-                for (int t = 0; t < MAX_GT; ++t)
-                    if (t < sp.kg()) {
-                        cv[t] = arg_value(sp.cov(t), V.cov[t], st, i, j, V.N);
-                        eta += st.gv[t] * cv[t];
-                    }
-#pragma unroll
-                for (int l = 0; l < MAX_LOC; ++l)
-                    if (l < sp.nl()) {
-                        cv[MAX_GT + l] = arg_value(sp.cov(sp.kg() + l), V.cov[sp.kg() + l], st, i, j, V.N);
-                        eta += st.lx[l] * cv[MAX_GT + l];
-                    }
-                if (sp.has_off()) eta += arg_value(sp.cov(sp.kg() + sp.nl()), V.cov[sp.kg() + sp.nl()], st, i, j, V.N);
-                // inverse link tape
-                double v = eta, dv = 1.0;
-#pragma unroll
-                for (int q = 0; q < JBUGS_MAX_LINK; ++q)
-                    if (q < sp.n_link()) {
-                        double nv, d;
-                        bad |= unary_op(sp.link(q), v, nv, d);
-                        v = nv;
-                        dv *= d;
-                    }
-                // observation
-                const double yv = arg_value(sp.y(), V.y, st, i, j, V.N);
-                const int ea = sp.eta_arg();
-                const double a0 = ea == 0 ? v : arg_value(sp.aux(0), V.aux[0], st, i, j, V.N);
-                const double a1 = ea == 1 ? v : arg_value(sp.aux(1), V.aux[1], st, i, j, V.N);
-                FamOut o;
-                bad |= fam_eval(sp.family(), yv, a0, a1, o);
-                lp += o.lp;
-                const double deta = (ea == 0 ? o.da0 : o.da1) * dv;
-                if (ea != 0) arg_adjoint(sp.aux(0), st, o.da0);
-                if (ea != 1) arg_adjoint(sp.aux(1), st, o.da1);
-#pragma unroll
-                for (int t = 0; t < MAX_GT; ++t)
-                    if (t < sp.kg()) st.ga[t] += deta * cv[t];
-#pragma unroll
-                for (int l = 0; l < MAX_LOC; ++l)
-                    if (l < sp.nl()) st.la[l] += deta * cv[MAX_GT + l];
-            }
-            if (want_grad) {
-#pragma unroll
-                for (int l = 0; l < MAX_LOC; ++l)
-                    if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS)
-                        grad[slot[l] * ld + c] = st.la[l] * ldx[l] + ldlj[l];
-            }
-        }
-        if (want_grad) {
-#pragma unroll
-            for (int l = 0; l < MAX_LOC; ++l)
-                if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP)
-                    grad[slot[l] * ld + c] = st.la[l] * ldx[l] + ldlj[l];
-        }
-    }
-    // per (tile, chain) partials: [logp, adjoints of the referenced global values]
-    double* out = partial + tile * (long long)(1 + sp.n_gref()) * ldg + c;
-    out[0] = lp;
-#pragma unroll
-    for (int k = 0; k < MAX_GREF; ++k)
-        if (k < sp.n_gref()) out[(long long)(1 + k) * ldg] = st.ga[k];
-    if (bad) atomicOr(flags + c, 1);
-}
+namespace jbugs {
 
 // ------------------------------------------------------------------------------------------------
 // finalize: add the tiles in ascending order, the priors of the globals, reverse the gtape and the

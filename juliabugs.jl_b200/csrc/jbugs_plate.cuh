@@ -1,0 +1,281 @@
+// jbugs_plate.cuh -- the plate kernel: fused forward + reverse over one tile of groups for BLOCK chains.
+// (see the mapping notes at the top of jbugs_kernels.cuh)
+#pragma once
+
+namespace jbugs {
+
+// chain-invariant argument kinds (a value that is the same for every group of the plate)
+__device__ __forceinline__ constexpr bool invariant_kind(int k) {
+    return k == JBUGS_ARG_GVAL || k == JBUGS_ARG_CONST || k == JBUGS_ARG_ONE;
+}
+
+// Per-thread accumulators of the fused (sufficient-statistic) paths.  Unused members are dead code
+// in instantiations that do not take the corresponding path.
+struct FusedAcc {
+    double ss;            // sum r^2 over the tile's observations            (normal / identity)
+    double sg[MAX_GT];    // sum r * cov_t for the global terms               (normal / identity)
+    double pss[MAX_LOC];  // sum (x_l - mu_l)^2 over the tile                 (normal prior, invariant args)
+    double ps[MAX_LOC];   // sum (x_l - mu_l)
+    double cnt[MAX_LOC];  // number of instances of local l in the tile
+};
+
+template <class S>
+__device__ __forceinline__ long long local_slot(const S& sp, const PlateVals& V, int l, long long i, long long j) {
+    const LocalV& L = V.loc[l];
+    if (sp.loc_has_idx(l)) return sp.loc_level(l) == JBUGS_LEVEL_OBS ? __ldg(L.idx + i + V.N * j) : __ldg(L.idx + i);
+    return L.base + L.si * i + L.sj * j;
+}
+
+// constrained value + logjac of local l from its raw theta slot value
+template <class S>
+__device__ __forceinline__ void local_enter(const S& sp, const PlateVals& V, int l, double raw, ChainState& st,
+                                            double (&ldx)[MAX_LOC], double (&ldlj)[MAX_LOC], double& lp) {
+    const TrOut t = transform_eval(sp.loc_transform(l), V.loc[l].lb, V.loc[l].ub, raw);
+    st.lx[l] = t.x;
+    st.la[l] = 0.0;
+    ldx[l] = t.dxdy;
+    ldlj[l] = t.dljdy;
+    lp += t.lj;
+}
+
+template <class S>
+__device__ __forceinline__ bool local_prior(const S& sp, const PlateVals& V, int l, long long i, long long j,
+                                            ChainState& st, FusedAcc& fa, double& lp) {
+    const LocalV& L = V.loc[l];
+    const double a0 = arg_value(sp.loc_arg(l, 0), L.args[0], st, i, j, V.N);
+    const double a1 = arg_value(sp.loc_arg(l, 1), L.args[1], st, i, j, V.N);
+    if (sp.prior_fused(l)) {
+        // dnorm(mu, tau) with chain-invariant arguments: keep sufficient statistics, expand at tile end
+        const double d = st.lx[l] - a0;
+        fa.pss[l] = fma(d, d, fa.pss[l]);
+        fa.ps[l] += d;
+        fa.cnt[l] += 1.0;
+        st.la[l] -= a1 * d;
+        return false;
+    }
+    FamOut o;
+    const bool bad = fam_eval(sp.loc_family(l), st.lx[l], a0, a1, o);
+    lp += o.lp;
+    st.la[l] += o.dx;
+    arg_adjoint(sp.loc_arg(l, 0), st, o.da0);
+    arg_adjoint(sp.loc_arg(l, 1), st, o.da1);
+    return bad;
+}
+
+// one observation: linear predictor, inverse link, family; accumulates adjoints
+template <class S>
+__device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, long long i, long long j, ChainState& st,
+                                        FusedAcc& fa, double (&sl)[MAX_LOC], double& lp) {
+    double cv[MAX_TERMS];
+    double eta = 0.0;
+    bool bad = false;
+#pragma unroll
+    for (int t = 0; t < MAX_GT; ++t)
+        if (t < sp.kg()) {
+            cv[t] = arg_value(sp.cov(t), V.cov[t], st, i, j, V.N);
+            eta = fma(st.gv[t], cv[t], eta);
+        }
+#pragma unroll
+    for (int l = 0; l < MAX_LOC; ++l)
+        if (l < sp.nl()) {
+            cv[MAX_GT + l] = arg_value(sp.cov(sp.kg() + l), V.cov[sp.kg() + l], st, i, j, V.N);
+            eta = fma(st.lx[l], cv[MAX_GT + l], eta);
+        }
+    if (sp.has_off()) eta += arg_value(sp.cov(sp.kg() + sp.nl()), V.cov[sp.kg() + sp.nl()], st, i, j, V.N);
+    const double yv = arg_value(sp.y(), V.y, st, i, j, V.N);
+
+    if (S::FUSED == FUSED_NORMAL_IDENTITY) {
+        // y ~ dnorm(eta, tau), tau chain-invariant: d/d eta = tau * r; tau is factored out of every sum
+        const double r = yv - eta;
+        fa.ss = fma(r, r, fa.ss);
+#pragma unroll
+        for (int t = 0; t < MAX_GT; ++t)
+            if (t < sp.kg()) fa.sg[t] = fma(r, cv[t], fa.sg[t]);
+#pragma unroll
+        for (int l = 0; l < MAX_LOC; ++l)
+            if (l < sp.nl()) sl[l] = fma(r, cv[MAX_GT + l], sl[l]);
+        return false;
+    }
+
+    double deta;
+    if (S::FUSED == FUSED_BINOMIAL_LOGIT || S::FUSED == FUSED_BERNOULLI_LOGIT) {
+        // k ~ dbin(logistic(eta), n): log p = -softplus(-eta), log(1-p) = -softplus(eta); one exp, one log1p.
+        // The data-only constant -logbeta(k+1, n-k+1) - log(n+1) is added once per plate (obs_const).
+        const double n = S::FUSED == FUSED_BERNOULLI_LOGIT ? 1.0 : arg_value(sp.aux(1), V.aux[1], st, i, j, V.N);
+        const double ax = fabs(eta);
+        const double e = exp(-ax);
+        const double l1p = log1p(e);
+        const double inv = 1.0 / (1.0 + e);
+        const double p = eta >= 0.0 ? inv : e * inv;                 // logistic(eta)
+        const double lsp = -((eta >= 0.0 ? 0.0 : ax) + l1p);          // log p
+        const double lsq = -((eta >= 0.0 ? ax : 0.0) + l1p);          // log(1 - p)
+        const double m = n - yv;
+        // reference semantics in the saturated tails (LogExpFunctions.logistic returns exactly 0 / 1)
+        const bool sat_hi = eta > kLogisticUpper, sat_lo = eta < kLogisticLower;
+        double term = (yv == 0.0 ? 0.0 : yv * lsp) + (m == 0.0 ? 0.0 : m * lsq);
+        if (sat_hi && m != 0.0) term = -dev_inf();
+        if (sat_lo && yv != 0.0) term = -dev_inf();
+        lp += term;
+        deta = yv - n * p;
+    } else if (S::FUSED == FUSED_POISSON_LOG) {
+        // k ~ dpois(exp(eta)): k * eta - exp(eta); -lgamma(k+1) goes to obs_const
+        const double lam = exp(eta);
+        // xlogy(k, lambda) saturates to -Inf once exp underflows to 0 (reference semantics)
+        lp += (yv == 0.0 ? 0.0 : (lam == 0.0 ? -dev_inf() : yv * eta)) - lam;
+        deta = yv - lam;
+    } else {
+        double v = eta, dv = 1.0;
+#pragma unroll
+        for (int q = 0; q < JBUGS_MAX_LINK; ++q)
+            if (q < sp.n_link()) {
+                double nv, d;
+                bad |= unary_op(sp.link(q), v, nv, d);
+                v = nv;
+                dv *= d;
+            }
+        const int ea = sp.eta_arg();
+        const double a0 = ea == 0 ? v : arg_value(sp.aux(0), V.aux[0], st, i, j, V.N);
+        const double a1 = ea == 1 ? v : arg_value(sp.aux(1), V.aux[1], st, i, j, V.N);
+        FamOut o;
+        bad |= fam_eval(sp.family(), yv, a0, a1, o);
+        lp += o.lp;
+        deta = (ea == 0 ? o.da0 : o.da1) * dv;
+        if (ea != 0) arg_adjoint(sp.aux(0), st, o.da0);
+        if (ea != 1) arg_adjoint(sp.aux(1), st, o.da1);
+    }
+#pragma unroll
+    for (int t = 0; t < MAX_GT; ++t)
+        if (t < sp.kg()) st.ga[t] = fma(deta, cv[t], st.ga[t]);
+#pragma unroll
+    for (int l = 0; l < MAX_LOC; ++l)
+        if (l < sp.nl()) st.la[l] = fma(deta, cv[MAX_GT + l], st.la[l]);
+    return bad;
+}
+
+template <class S>
+__global__ void __launch_bounds__(BLOCK, S::MIN_BLOCKS)
+plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ theta, double* __restrict__ grad,
+             long long ld, long long C, const double* __restrict__ gvals, long long ldg,
+             double* __restrict__ partial, int* __restrict__ flags, int want_grad) {
+    const S sp(P.sh);
+    const PlateVals& V = P.v;
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    const long long tile = blockIdx.y;
+    const long long ib = V.i0 + tile * V.tile;
+    const long long ie = (ib + V.tile < V.i1) ? ib + V.tile : V.i1;
+    constexpr int U = S::UNROLL;
+
+    ChainState st;
+#pragma unroll
+    for (int k = 0; k < MAX_GREF; ++k) {
+        st.gv[k] = (k < sp.n_gref()) ? gvals[(long long)V.gref[k] * ldg + c] : 0.0;
+        st.ga[k] = 0.0;
+    }
+    FusedAcc fa;
+    fa.ss = 0.0;
+#pragma unroll
+    for (int t = 0; t < MAX_GT; ++t) fa.sg[t] = 0.0;
+#pragma unroll
+    for (int l = 0; l < MAX_LOC; ++l) fa.pss[l] = fa.ps[l] = fa.cnt[l] = 0.0;
+
+    double lp = 0.0;
+    bool bad = false;
+    // precision of a fused normal observation (chain-invariant by construction of the spec)
+    const double obs_tau = (S::FUSED == FUSED_NORMAL_IDENTITY)
+                               ? (sp.aux(1).kind == JBUGS_ARG_GVAL ? pick(st.gv, sp.aux(1).id) : V.aux[1].value)
+                               : 0.0;
+    const double* __restrict__ th = theta + c;
+    double* __restrict__ gr = grad + c;
+
+    for (long long i0 = ib; i0 < ie; i0 += U) {
+        // issue the theta loads of U groups before touching any of them (memory-level parallelism)
+        double raw[U][MAX_LOC];
+        long long slot[U][MAX_LOC];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int l = 0; l < MAX_LOC; ++l)
+                if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP && i0 + u < ie) {
+                    slot[u][l] = local_slot(sp, V, l, i0 + u, 0);
+                    raw[u][l] = th[slot[u][l] * ld];
+                }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u;
+            if (i < ie) {
+                double ldx[MAX_LOC], ldlj[MAX_LOC], sl[MAX_LOC];
+#pragma unroll
+                for (int l = 0; l < MAX_LOC; ++l) {
+                    sl[l] = 0.0;
+                    if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) local_enter(sp, V, l, raw[u][l], st, ldx, ldlj, lp);
+                }
+#pragma unroll
+                for (int l = 0; l < MAX_LOC; ++l)
+                    if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) bad |= local_prior(sp, V, l, i, 0, st, fa, lp);
+
+                for (long long j = 0; j < V.T; ++j) {
+                    long long oslot[MAX_LOC];
+#pragma unroll
+                    for (int l = 0; l < MAX_LOC; ++l)
+                        if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) {
+                            oslot[l] = local_slot(sp, V, l, i, j);
+                            local_enter(sp, V, l, th[oslot[l] * ld], st, ldx, ldlj, lp);
+                        }
+#pragma unroll
+                    for (int l = 0; l < MAX_LOC; ++l)
+                        if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) bad |= local_prior(sp, V, l, i, j, st, fa, lp);
+                    if (sp.has_obs()) bad |= observe(sp, V, i, j, st, fa, sl, lp);
+#pragma unroll
+                    for (int l = 0; l < MAX_LOC; ++l)
+                        if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) {
+                            if (S::FUSED == FUSED_NORMAL_IDENTITY) {
+                                st.la[l] = fma(obs_tau, sl[l], st.la[l]);
+                                sl[l] = 0.0;
+                            }
+                            if (want_grad) gr[oslot[l] * ld] = fma(st.la[l], ldx[l], ldlj[l]);
+                        }
+                }
+#pragma unroll
+                for (int l = 0; l < MAX_LOC; ++l)
+                    if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) {
+                        if (S::FUSED == FUSED_NORMAL_IDENTITY) st.la[l] = fma(obs_tau, sl[l], st.la[l]);
+                        if (want_grad) gr[slot[u][l] * ld] = fma(st.la[l], ldx[l], ldlj[l]);
+                    }
+            }
+        }
+    }
+
+    // expand the sufficient statistics of the fused paths
+    const double n_obs = (double)((ie - ib) * V.T);
+    if (S::FUSED == FUSED_NORMAL_IDENTITY) {
+        const bool tg = sp.aux(1).kind == JBUGS_ARG_GVAL;
+        const double tau = obs_tau;
+        bad |= tau < 0.0;
+        lp += n_obs * (0.5 * log(tau) - 0.5 * kLog2Pi) - 0.5 * tau * fa.ss;
+        if (tg) bump(st.ga, sp.aux(1).id, n_obs * 0.5 / tau - 0.5 * fa.ss);
+#pragma unroll
+        for (int t = 0; t < MAX_GT; ++t)
+            if (t < sp.kg()) st.ga[t] = fma(tau, fa.sg[t], st.ga[t]);
+    }
+#pragma unroll
+    for (int l = 0; l < MAX_LOC; ++l)
+        if (l < sp.nl() && sp.prior_fused(l)) {
+            const ArgS a0 = sp.loc_arg(l, 0), a1 = sp.loc_arg(l, 1);
+            const double tau = a1.kind == JBUGS_ARG_GVAL ? pick(st.gv, a1.id) : V.loc[l].args[1].value;
+            bad |= tau < 0.0;
+            lp += fa.cnt[l] * (0.5 * log(tau) - 0.5 * kLog2Pi) - 0.5 * tau * fa.pss[l];
+            if (a0.kind == JBUGS_ARG_GVAL) bump(st.ga, a0.id, tau * fa.ps[l]);
+            if (a1.kind == JBUGS_ARG_GVAL) bump(st.ga, a1.id, fa.cnt[l] * 0.5 / tau - 0.5 * fa.pss[l]);
+        }
+
+    // per (tile, chain) partials: [logp, adjoints of the referenced global values]
+    double* out = partial + tile * (long long)(1 + sp.n_gref()) * ldg + c;
+    out[0] = lp;
+#pragma unroll
+    for (int k = 0; k < MAX_GREF; ++k)
+        if (k < sp.n_gref()) out[(long long)(1 + k) * ldg] = st.ga[k];
+    if (bad) atomicOr(flags + c, 1);
+}
+
+}  // namespace jbugs

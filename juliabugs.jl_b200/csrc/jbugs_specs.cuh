@@ -26,6 +26,7 @@ struct SpecEntry {
     const char* name;
     plate_launch_fn launch;
     bool (*matches)(const PlateShape&);
+    int fused;  // FUSED_* code: tells the host whether the plate needs obs_const
 };
 
 static bool match_never(const PlateShape&) { return false; }
@@ -33,7 +34,7 @@ static bool match_never(const PlateShape&) { return false; }
 #include "jbugs_static_specs.inc"
 
 static const SpecEntry g_specs[] = {
-    {"dynamic", &launch_plate_t<DynSpec>, &match_never},
+    {"dynamic", &launch_plate_t<DynSpec>, &match_never, FUSED_NONE},
     JBUGS_STATIC_SPEC_ENTRIES
 };
 static const int g_num_specs = (int)(sizeof(g_specs) / sizeof(g_specs[0]));
