@@ -76,6 +76,7 @@ struct PlateRt {
     long long partial_offset = 0;
     double obs_const = 0.0;
     bool const_dirty = true;  // obs_const must be recomputed (new data / shard / kernel variant)
+    size_t smem_bytes = 0;    // dynamic shared memory of the plate kernel (J region + two stages)
 };
 
 struct jbugs_plan_s {
@@ -127,11 +128,37 @@ static int set_device(const jbugs_plan* p) {
 }
 
 // ------------------------------------------------------------------------------------------------ plate lowering to device params
-static int resolve_arg(const jbugs_plan* p, const jbugs_arg& a, ArgS& s, ArgV& v, std::vector<int>& gref, int max_local) {
+struct StreamBuilder {
+    PlateVals* V;
+    long long T;
+    int chunk_acc = 0;  // doubles per group so far
+    int j_acc = 0;      // doubles in the J region so far
+    int add(const double* ptr, int kind) {  // returns soff, or -1 when the table is full
+        for (int k = 0; k < V->n_streams; ++k)
+            if (V->streams[k].ptr == ptr && V->streams[k].kind == kind) return V->streams[k].soff;
+        if (V->n_streams >= MAX_STREAMS) return -1;
+        Stream& s = V->streams[V->n_streams++];
+        s.ptr = ptr;
+        s.kind = kind;
+        if (kind == JBUGS_ARG_DATA_J) {
+            s.soff = j_acc;
+            j_acc += (int)T;
+        } else {
+            s.soff = chunk_acc * STAGE_G;
+            chunk_acc += kind == JBUGS_ARG_DATA_IJ ? (int)T : 1;
+        }
+        return s.soff;
+    }
+};
+
+static int resolve_arg(const jbugs_plan* p, const jbugs_arg& a, ArgS& s, ArgV& v, std::vector<int>& gref, int max_local,
+                       StreamBuilder& sb) {
     s.kind = (int)a.kind;
     s.id = 0;
     v.ptr = nullptr;
     v.value = a.value;
+    v.soff = 0;
+    v.pad = 0;
     switch (a.kind) {
     case JBUGS_ARG_CONST:
     case JBUGS_ARG_ONE: return 0;
@@ -156,6 +183,8 @@ static int resolve_arg(const jbugs_plan* p, const jbugs_arg& a, ArgS& s, ArgV& v
         if (a.id < 0 || a.id >= (int)p->h.n_data) return fail(JBUGS_ERR_INVALID, "data slot out of range");
         if (p->data[a.id].dtype != 0) return fail(JBUGS_ERR_INVALID, "data slot %d is not float64", a.id);
         v.ptr = (const double*)p->d_slots[a.id];
+        v.soff = sb.add(v.ptr, (int)a.kind);
+        if (v.soff < 0) return fail(JBUGS_ERR_UNSUPPORTED, "a plate uses more than %d distinct data streams", MAX_STREAMS);
         return 0;
     default: return fail(JBUGS_ERR_INVALID, "unknown argument kind %u", a.kind);
     }
@@ -198,24 +227,27 @@ static int build_plate(jbugs_plan* p, int k) {
     sh.family = (int)pl.family; sh.eta_arg = (int)pl.eta_arg; sh.has_obs = (int)pl.has_obs; sh.n_link = (int)pl.n_link;
     for (int q = 0; q < JBUGS_MAX_LINK; ++q) sh.link[q] = q < (int)pl.n_link ? (int)pl.link[q] : 0;
     V.N = pl.N; V.T = pl.T;
+    StreamBuilder sb;
+    sb.V = &V;
+    sb.T = pl.T;
     int rc;
     for (int q = 0; q < kg; ++q) {
         ArgS s; ArgV v;
-        if ((rc = resolve_arg(p, T[q].coef, s, v, gref, 0))) return rc;
+        if ((rc = resolve_arg(p, T[q].coef, s, v, gref, 0, sb))) return rc;
         if (s.id != q) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: a global appears in two terms", k);
     }
     for (int q = 0; q < (int)pl.n_terms; ++q) {
-        if ((rc = resolve_arg(p, T[q].cov, sh.cov[q], V.cov[q], gref, 0))) return rc;
+        if ((rc = resolve_arg(p, T[q].cov, sh.cov[q], V.cov[q], gref, 0, sb))) return rc;
         if (sh.cov[q].kind == JBUGS_ARG_GVAL || sh.cov[q].kind == JBUGS_ARG_LOCAL)
             return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: covariates must be data", k);
         if ((rc = check_len(p, T[q].cov, pl.N, pl.T, "covariate"))) return rc;
     }
     if (pl.has_obs) {
-        if ((rc = resolve_arg(p, pl.y, sh.y, V.y, gref, 0))) return rc;
+        if ((rc = resolve_arg(p, pl.y, sh.y, V.y, gref, 0, sb))) return rc;
         if ((rc = check_len(p, pl.y, pl.N, pl.T, "y"))) return rc;
         for (int q = 0; q < 2; ++q) {
             if (q == (int)pl.eta_arg) continue;
-            if ((rc = resolve_arg(p, pl.aux[q], sh.aux[q], V.aux[q], gref, (int)pl.n_locals))) return rc;
+            if ((rc = resolve_arg(p, pl.aux[q], sh.aux[q], V.aux[q], gref, (int)pl.n_locals, sb))) return rc;
             if ((rc = check_len(p, pl.aux[q], pl.N, pl.T, "aux"))) return rc;
         }
     }
@@ -242,7 +274,7 @@ static int build_plate(jbugs_plan* p, int k) {
                 if (pl.N > 0 && (x < 0 || x >= p->h.D)) return fail(JBUGS_ERR_INVALID, "plate %d local %d: theta slot out of range", k, l);
         }
         for (int q = 0; q < 2; ++q) {
-            if ((rc = resolve_arg(p, L[l].args[q], ls.args[q], lv.args[q], gref, (int)pl.n_locals))) return rc;
+            if ((rc = resolve_arg(p, L[l].args[q], ls.args[q], lv.args[q], gref, (int)pl.n_locals, sb))) return rc;
             if (ls.level == JBUGS_LEVEL_GROUP && (L[l].args[q].kind == JBUGS_ARG_DATA_J || L[l].args[q].kind == JBUGS_ARG_DATA_IJ))
                 return fail(JBUGS_ERR_INVALID, "plate %d local %d: group-level prior indexed by j", k, l);
             if ((rc = check_len(p, L[l].args[q], pl.N, pl.T, "prior argument"))) return rc;
@@ -252,7 +284,12 @@ static int build_plate(jbugs_plan* p, int k) {
     sh.n_gref = (int)gref.size();
     for (int q = 0; q < MAX_GREF; ++q) V.gref[q] = q < (int)gref.size() ? gref[q] : 0;
     V.i0 = p->shard_i0[k]; V.i1 = p->shard_i1[k];
-    r.variant = p->force_dynamic ? 0 : select_spec(sh);
+    V.per_group = sb.chunk_acc;
+    V.j_doubles = (sb.j_acc + 1) / 2 * 2;
+    r.smem_bytes = (size_t)(V.j_doubles + 2 * V.per_group * STAGE_G) * sizeof(double);
+    if (r.smem_bytes > 200 * 1024)
+        return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: %zu bytes of staged data per chunk exceed shared memory (inner extent too large)", k, r.smem_bytes);
+    r.variant = p->force_dynamic ? 0 : select_spec(sh, pl.T);
     r.const_dirty = true;
     r.obs_const = 0.0;
     return 0;
@@ -458,7 +495,7 @@ extern "C" int jbugs_plan_upload_data(jbugs_plan* p, int slot, const void* src, 
     // new observations: constants of the fused paths (and their validity check) must be redone
     if (!p->force_dynamic)
         for (size_t k = 0; k < p->rt.size(); ++k) {
-            p->rt[k].variant = select_spec(p->rt[k].pp.sh);
+            p->rt[k].variant = select_spec(p->rt[k].pp.sh, p->rt[k].pp.v.T);
             p->rt[k].const_dirty = true;
         }
     return JBUGS_OK;
@@ -591,8 +628,15 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         for (int q = 0; q < MAX_GREF; ++q) fp.p[k].gref[q] = r.pp.v.gref[q];
         if (r.pp.v.i1 <= r.pp.v.i0) { fp.p[k].n_tiles = 0; continue; }
         dim3 grid(chain_tiles, (unsigned)r.n_tiles);
-        launch_plate(r.variant, grid, st, r.pp, theta, grad, ld, C, p->d_gvals, ldg,
-                     p->d_partial + r.partial_offset * ldg, p->d_flags, want_grad && grad);
+        PlateParams pp = r.pp;  // per-launch copy: slot maps in element offsets of this batch's leading dimension
+        for (int l = 0; l < pp.sh.nl; ++l) {
+            pp.v.loc[l].row0 = pp.v.loc[l].base * ld;
+            pp.v.loc[l].step_i = pp.v.loc[l].si * ld;
+            pp.v.loc[l].step_j = pp.v.loc[l].sj * ld;
+        }
+        cudaError_t le = g_specs[r.variant].launch(grid, r.smem_bytes, st, pp, theta, grad, ld, C, p->d_gvals, ldg,
+                                                   p->d_partial + r.partial_offset * ldg, p->d_flags, want_grad && grad);
+        if (le != cudaSuccess) return fail(JBUGS_ERR_CUDA, "plate kernel launch failed: %s", cudaGetErrorString(le));
         p->launches++;
     }
     if (p->timing) CU(cudaEventRecord(p->ev[2], st));

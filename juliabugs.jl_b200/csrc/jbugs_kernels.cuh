@@ -39,8 +39,22 @@ struct ArgS {  // structural half of an argument
     int id;    // GVAL: plate-local gref index; LOCAL: local index
 };
 struct ArgV {  // value half
-    const double* ptr;  // DATA_*: device array
+    const double* ptr;  // DATA_*: device array (host-side bookkeeping / obs_const kernel)
     double value;       // CONST
+    int soff;           // DATA_*: offset (in doubles) of the stream inside the staged chunk / J region
+    int pad;
+};
+
+// Shared-memory staging of the plate's data (observations, covariates, data-valued prior arguments).
+// All of it is indexed by the group (and inner) index only, i.e. identical for every chain of the CTA:
+// it is copied once per chunk of STAGE_G groups with cp.async (double buffered) and read back as
+// warp-wide broadcasts.  A stream is one distinct (data slot, index kind) pair.
+constexpr int STAGE_G = 32;      // groups per staged chunk
+constexpr int MAX_STREAMS = 20;
+struct Stream {
+    const double* ptr;
+    int kind;  // DATA_I | DATA_J | DATA_IJ
+    int soff;
 };
 
 struct LocalS {
@@ -49,6 +63,7 @@ struct LocalS {
 };
 struct LocalV {
     long long base, si, sj;
+    long long row0, step_i, step_j;  // base * ld, si * ld, sj * ld: filled per launch (element offsets)
     const long long* idx;
     double lb, ub;
     ArgV args[3];
@@ -70,6 +85,11 @@ struct PlateVals {
     LocalV loc[MAX_LOC];
     int gref[MAX_GREF];
     double obs_const;  // sum over the shard of the data-only normalising constants (fused paths)
+    int n_streams;     // staged data streams
+    int per_group;     // doubles per group in a staged chunk (I streams: 1, IJ streams: T)
+    int j_doubles;     // size of the J region (J streams: T each), rounded up to even
+    int pad;
+    Stream streams[MAX_STREAMS];
 };
 
 struct PlateParams {
@@ -84,6 +104,7 @@ struct DynSpec {
     static constexpr int FUSED = 0;
     static constexpr int UNROLL = 1;
     static constexpr int MIN_BLOCKS = 2;
+    static constexpr int T_STATIC = 0;  // inner extent read at run time
     __device__ __forceinline__ bool prior_fused(int) const { return false; }
     const PlateShape& s;
     __device__ __forceinline__ explicit DynSpec(const PlateShape& sh) : s(sh) {}
@@ -117,6 +138,7 @@ struct StaticSpec {
     static constexpr int FUSED = Desc::FUSED;
     static constexpr int UNROLL = Desc::UNROLL;
     static constexpr int MIN_BLOCKS = Desc::MIN_BLOCKS;
+    static constexpr int T_STATIC = Desc::T_STATIC;  // > 0: inner loop fully unrolled
     // a dnorm prior whose arguments do not vary over the plate keeps sufficient statistics
     __device__ __forceinline__ constexpr bool prior_fused(int l) const {
         return Desc::sh().loc[l].family == JBUGS_FAM_NORMAL &&
@@ -166,16 +188,22 @@ struct ChainState {
     double la[MAX_LOC];   // their adjoints
 };
 
-__device__ __forceinline__ double arg_value(ArgS s, const ArgV& v, const ChainState& st, long long i, long long j,
-                                            long long N) {
+// where the staged data of the current chunk lives (shared memory)
+struct StageView {
+    const double* chunk;  // [per_group][STAGE_G]
+    const double* jreg;   // J region
+};
+
+// g = group index inside the staged chunk, j = inner index
+__device__ __forceinline__ double arg_value(ArgS s, const ArgV& v, const ChainState& st, const StageView& sv, int g, int j) {
     switch (s.kind) {
     case JBUGS_ARG_CONST: return v.value;
     case JBUGS_ARG_ONE: return 1.0;
     case JBUGS_ARG_GVAL: return pick(st.gv, s.id);
     case JBUGS_ARG_LOCAL: return pick(st.lx, s.id);
-    case JBUGS_ARG_DATA_I: return __ldg(v.ptr + i);
-    case JBUGS_ARG_DATA_J: return __ldg(v.ptr + j);
-    case JBUGS_ARG_DATA_IJ: return __ldg(v.ptr + i + N * j);
+    case JBUGS_ARG_DATA_I: return sv.chunk[v.soff + g];
+    case JBUGS_ARG_DATA_J: return sv.jreg[v.soff + j];
+    case JBUGS_ARG_DATA_IJ: return sv.chunk[v.soff + j * STAGE_G + g];
     default: return 0.0;
     }
 }

@@ -1,13 +1,16 @@
 // jbugs_plate.cuh -- the plate kernel: fused forward + reverse over one tile of groups for BLOCK chains.
 // (see the mapping notes at the top of jbugs_kernels.cuh)
+//
+// Structure of one CTA:
+//   tile of groups [ib, ie)  ->  chunks of STAGE_G groups
+//     chunk k+1's observation / covariate streams are copied global -> shared with cp.async while chunk k is
+//     being evaluated (two stages, one __syncthreads per chunk);
+//     inside a chunk the group loop runs UNROLL groups at a time: all theta loads of the UNROLL groups are issued
+//     before any is used, then each group is evaluated from registers + shared-memory broadcasts and its
+//     gradient rows are stored.
 #pragma once
 
 namespace jbugs {
-
-// chain-invariant argument kinds (a value that is the same for every group of the plate)
-__device__ __forceinline__ constexpr bool invariant_kind(int k) {
-    return k == JBUGS_ARG_GVAL || k == JBUGS_ARG_CONST || k == JBUGS_ARG_ONE;
-}
 
 // Per-thread accumulators of the fused (sufficient-statistic) paths.  Unused members are dead code
 // in instantiations that do not take the corresponding path.
@@ -18,6 +21,28 @@ struct FusedAcc {
     double ps[MAX_LOC];   // sum (x_l - mu_l)
     double cnt[MAX_LOC];  // number of instances of local l in the tile
 };
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// copy the streams of groups [i, i + cnt) into one stage
+__device__ __forceinline__ void stage_chunk(const PlateVals& V, double* dst, long long i, int cnt, int T, int tid) {
+    for (int s = 0; s < V.n_streams; ++s) {
+        const Stream sm = V.streams[s];
+        if (sm.kind == JBUGS_ARG_DATA_I) {
+            for (int q = tid; q < cnt; q += BLOCK) cp_async8(dst + sm.soff + q, sm.ptr + i + q);
+        } else if (sm.kind == JBUGS_ARG_DATA_IJ) {
+            for (int q = tid; q < T * STAGE_G; q += BLOCK) {
+                const int j = q / STAGE_G, g = q % STAGE_G;
+                if (g < cnt) cp_async8(dst + sm.soff + q, sm.ptr + i + g + V.N * (long long)j);
+            }
+        }
+    }
+}
 
 template <class S>
 __device__ __forceinline__ long long local_slot(const S& sp, const PlateVals& V, int l, long long i, long long j) {
@@ -39,11 +64,11 @@ __device__ __forceinline__ void local_enter(const S& sp, const PlateVals& V, int
 }
 
 template <class S>
-__device__ __forceinline__ bool local_prior(const S& sp, const PlateVals& V, int l, long long i, long long j,
+__device__ __forceinline__ bool local_prior(const S& sp, const PlateVals& V, int l, const StageView& sv, int g, int j,
                                             ChainState& st, FusedAcc& fa, double& lp) {
     const LocalV& L = V.loc[l];
-    const double a0 = arg_value(sp.loc_arg(l, 0), L.args[0], st, i, j, V.N);
-    const double a1 = arg_value(sp.loc_arg(l, 1), L.args[1], st, i, j, V.N);
+    const double a0 = arg_value(sp.loc_arg(l, 0), L.args[0], st, sv, g, j);
+    const double a1 = arg_value(sp.loc_arg(l, 1), L.args[1], st, sv, g, j);
     if (sp.prior_fused(l)) {
         // dnorm(mu, tau) with chain-invariant arguments: keep sufficient statistics, expand at tile end
         const double d = st.lx[l] - a0;
@@ -64,25 +89,25 @@ __device__ __forceinline__ bool local_prior(const S& sp, const PlateVals& V, int
 
 // one observation: linear predictor, inverse link, family; accumulates adjoints
 template <class S>
-__device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, long long i, long long j, ChainState& st,
-                                        FusedAcc& fa, double (&sl)[MAX_LOC], double& lp) {
+__device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const StageView& sv, int g, int j,
+                                        ChainState& st, FusedAcc& fa, double (&sl)[MAX_LOC], double& lp) {
     double cv[MAX_TERMS];
     double eta = 0.0;
     bool bad = false;
 #pragma unroll
     for (int t = 0; t < MAX_GT; ++t)
         if (t < sp.kg()) {
-            cv[t] = arg_value(sp.cov(t), V.cov[t], st, i, j, V.N);
+            cv[t] = arg_value(sp.cov(t), V.cov[t], st, sv, g, j);
             eta = fma(st.gv[t], cv[t], eta);
         }
 #pragma unroll
     for (int l = 0; l < MAX_LOC; ++l)
         if (l < sp.nl()) {
-            cv[MAX_GT + l] = arg_value(sp.cov(sp.kg() + l), V.cov[sp.kg() + l], st, i, j, V.N);
+            cv[MAX_GT + l] = arg_value(sp.cov(sp.kg() + l), V.cov[sp.kg() + l], st, sv, g, j);
             eta = fma(st.lx[l], cv[MAX_GT + l], eta);
         }
-    if (sp.has_off()) eta += arg_value(sp.cov(sp.kg() + sp.nl()), V.cov[sp.kg() + sp.nl()], st, i, j, V.N);
-    const double yv = arg_value(sp.y(), V.y, st, i, j, V.N);
+    if (sp.has_off()) eta += arg_value(sp.cov(sp.kg() + sp.nl()), V.cov[sp.kg() + sp.nl()], st, sv, g, j);
+    const double yv = arg_value(sp.y(), V.y, st, sv, g, j);
 
     if (S::FUSED == FUSED_NORMAL_IDENTITY) {
         // y ~ dnorm(eta, tau), tau chain-invariant: d/d eta = tau * r; tau is factored out of every sum
@@ -101,7 +126,7 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, long lo
     if (S::FUSED == FUSED_BINOMIAL_LOGIT || S::FUSED == FUSED_BERNOULLI_LOGIT) {
         // k ~ dbin(logistic(eta), n): log p = -softplus(-eta), log(1-p) = -softplus(eta); one exp, one log1p.
         // The data-only constant -logbeta(k+1, n-k+1) - log(n+1) is added once per plate (obs_const).
-        const double n = S::FUSED == FUSED_BERNOULLI_LOGIT ? 1.0 : arg_value(sp.aux(1), V.aux[1], st, i, j, V.N);
+        const double n = S::FUSED == FUSED_BERNOULLI_LOGIT ? 1.0 : arg_value(sp.aux(1), V.aux[1], st, sv, g, j);
         const double ax = fabs(eta);
         const double e = exp(-ax);
         const double l1p = log1p(e);
@@ -134,8 +159,8 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, long lo
                 dv *= d;
             }
         const int ea = sp.eta_arg();
-        const double a0 = ea == 0 ? v : arg_value(sp.aux(0), V.aux[0], st, i, j, V.N);
-        const double a1 = ea == 1 ? v : arg_value(sp.aux(1), V.aux[1], st, i, j, V.N);
+        const double a0 = ea == 0 ? v : arg_value(sp.aux(0), V.aux[0], st, sv, g, j);
+        const double a1 = ea == 1 ? v : arg_value(sp.aux(1), V.aux[1], st, sv, g, j);
         FamOut o;
         bad |= fam_eval(sp.family(), yv, a0, a1, o);
         lp += o.lp;
@@ -152,19 +177,116 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, long lo
     return bad;
 }
 
+// UU consecutive groups starting at chunk-local index g (global group index i): loads first, then math
+template <class S, int UU>
+__device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, const StageView& sv, int g, long long i,
+                                            int T, const double* __restrict__ th, double* __restrict__ gr,
+                                            long long ld, bool store, double obs_tau, long long (&pos)[MAX_LOC],
+                                            ChainState& st, FusedAcc& fa, double& lp) {
+    bool bad = false;
+    double raw[UU][MAX_LOC];
+    long long off[UU][MAX_LOC];  // element offset of the slot's row: slot * ld
+    // `pos[l]` walks the affine slot map incrementally (row0 + step_i * i [+ step_j * j], in elements)
+#pragma unroll
+    for (int u = 0; u < UU; ++u)
+#pragma unroll
+        for (int l = 0; l < MAX_LOC; ++l)
+            if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) {
+                if (sp.loc_has_idx(l)) {
+                    off[u][l] = local_slot(sp, V, l, i + u, 0) * ld;
+                } else {
+                    off[u][l] = pos[l];
+                    pos[l] += V.loc[l].step_i;
+                }
+                raw[u][l] = th[off[u][l]];
+            }
+#pragma unroll
+    for (int u = 0; u < UU; ++u) {
+        double ldx[MAX_LOC], ldlj[MAX_LOC], sl[MAX_LOC];
+#pragma unroll
+        for (int l = 0; l < MAX_LOC; ++l) {
+            sl[l] = 0.0;
+            if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) local_enter(sp, V, l, raw[u][l], st, ldx, ldlj, lp);
+        }
+#pragma unroll
+        for (int l = 0; l < MAX_LOC; ++l)
+            if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) bad |= local_prior(sp, V, l, sv, g + u, 0, st, fa, lp);
+
+        long long opos[MAX_LOC];
+#pragma unroll
+        for (int l = 0; l < MAX_LOC; ++l) opos[l] = pos[l];
+#pragma unroll(S::T_STATIC > 0 ? S::T_STATIC : 1)
+        for (int j = 0; j < T; ++j) {
+            long long ooff[MAX_LOC];
+#pragma unroll
+            for (int l = 0; l < MAX_LOC; ++l)
+                if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) {
+                    if (sp.loc_has_idx(l)) {
+                        ooff[l] = local_slot(sp, V, l, i + u, j) * ld;
+                    } else {
+                        ooff[l] = opos[l];
+                        opos[l] += V.loc[l].step_j;
+                    }
+                    local_enter(sp, V, l, th[ooff[l]], st, ldx, ldlj, lp);
+                }
+#pragma unroll
+            for (int l = 0; l < MAX_LOC; ++l)
+                if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) bad |= local_prior(sp, V, l, sv, g + u, j, st, fa, lp);
+            if (sp.has_obs()) bad |= observe(sp, V, sv, g + u, j, st, fa, sl, lp);
+#pragma unroll
+            for (int l = 0; l < MAX_LOC; ++l)
+                if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) {
+                    if (S::FUSED == FUSED_NORMAL_IDENTITY) {
+                        st.la[l] = fma(obs_tau, sl[l], st.la[l]);
+                        sl[l] = 0.0;
+                    }
+                    if (store) gr[ooff[l]] = fma(st.la[l], ldx[l], ldlj[l]);
+                }
+        }
+#pragma unroll
+        for (int l = 0; l < MAX_LOC; ++l) {
+            if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) pos[l] += V.loc[l].step_i;
+            if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) {
+                if (S::FUSED == FUSED_NORMAL_IDENTITY) st.la[l] = fma(obs_tau, sl[l], st.la[l]);
+                if (store) gr[off[u][l]] = fma(st.la[l], ldx[l], ldlj[l]);
+            }
+        }
+    }
+    return bad;
+}
+
 template <class S>
 __global__ void __launch_bounds__(BLOCK, S::MIN_BLOCKS)
 plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ theta, double* __restrict__ grad,
              long long ld, long long C, const double* __restrict__ gvals, long long ldg,
              double* __restrict__ partial, int* __restrict__ flags, int want_grad) {
+    extern __shared__ double smem[];
     const S sp(P.sh);
     const PlateVals& V = P.v;
-    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
-    if (c >= C) return;
+    const int tid = threadIdx.x;
+    const long long c_raw = (long long)blockIdx.x * BLOCK + tid;
+    const bool active = c_raw < C;           // inactive lanes still take part in staging and barriers
+    const long long c = active ? c_raw : C - 1;
     const long long tile = blockIdx.y;
     const long long ib = V.i0 + tile * V.tile;
     const long long ie = (ib + V.tile < V.i1) ? ib + V.tile : V.i1;
     constexpr int U = S::UNROLL;
+    const int T = S::T_STATIC > 0 ? S::T_STATIC : (int)V.T;
+
+    // shared memory: J region, then two stages of [per_group][STAGE_G]
+    double* jreg = smem;
+    double* stage0 = smem + V.j_doubles;
+    const int stage_doubles = V.per_group * STAGE_G;
+    for (int s = 0; s < V.n_streams; ++s) {
+        const Stream sm = V.streams[s];
+        if (sm.kind == JBUGS_ARG_DATA_J)
+            for (int q = tid; q < T; q += BLOCK) jreg[sm.soff + q] = __ldg(sm.ptr + q);
+    }
+    {
+        const long long rem = ie - ib;
+        stage_chunk(V, stage0, ib, rem < STAGE_G ? (int)rem : STAGE_G, T, tid);
+        cp_async_commit();
+    }
 
     ChainState st;
 #pragma unroll
@@ -187,63 +309,36 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
                                : 0.0;
     const double* __restrict__ th = theta + c;
     double* __restrict__ gr = grad + c;
+    const bool store = want_grad && active;
 
-    for (long long i0 = ib; i0 < ie; i0 += U) {
-        // issue the theta loads of U groups before touching any of them (memory-level parallelism)
-        double raw[U][MAX_LOC];
-        long long slot[U][MAX_LOC];
+    long long pos[MAX_LOC];
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int l = 0; l < MAX_LOC; ++l)
-                if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP && i0 + u < ie) {
-                    slot[u][l] = local_slot(sp, V, l, i0 + u, 0);
-                    raw[u][l] = th[slot[u][l] * ld];
-                }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u;
-            if (i < ie) {
-                double ldx[MAX_LOC], ldlj[MAX_LOC], sl[MAX_LOC];
-#pragma unroll
-                for (int l = 0; l < MAX_LOC; ++l) {
-                    sl[l] = 0.0;
-                    if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) local_enter(sp, V, l, raw[u][l], st, ldx, ldlj, lp);
-                }
-#pragma unroll
-                for (int l = 0; l < MAX_LOC; ++l)
-                    if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) bad |= local_prior(sp, V, l, i, 0, st, fa, lp);
+    for (int l = 0; l < MAX_LOC; ++l) pos[l] = V.loc[l].row0 + V.loc[l].step_i * ib;
 
-                for (long long j = 0; j < V.T; ++j) {
-                    long long oslot[MAX_LOC];
-#pragma unroll
-                    for (int l = 0; l < MAX_LOC; ++l)
-                        if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) {
-                            oslot[l] = local_slot(sp, V, l, i, j);
-                            local_enter(sp, V, l, th[oslot[l] * ld], st, ldx, ldlj, lp);
-                        }
-#pragma unroll
-                    for (int l = 0; l < MAX_LOC; ++l)
-                        if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) bad |= local_prior(sp, V, l, i, j, st, fa, lp);
-                    if (sp.has_obs()) bad |= observe(sp, V, i, j, st, fa, sl, lp);
-#pragma unroll
-                    for (int l = 0; l < MAX_LOC; ++l)
-                        if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) {
-                            if (S::FUSED == FUSED_NORMAL_IDENTITY) {
-                                st.la[l] = fma(obs_tau, sl[l], st.la[l]);
-                                sl[l] = 0.0;
-                            }
-                            if (want_grad) gr[oslot[l] * ld] = fma(st.la[l], ldx[l], ldlj[l]);
-                        }
-                }
-#pragma unroll
-                for (int l = 0; l < MAX_LOC; ++l)
-                    if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) {
-                        if (S::FUSED == FUSED_NORMAL_IDENTITY) st.la[l] = fma(obs_tau, sl[l], st.la[l]);
-                        if (want_grad) gr[slot[u][l] * ld] = fma(st.la[l], ldx[l], ldlj[l]);
-                    }
-            }
+    cp_async_wait_all();
+    __syncthreads();
+
+    int cur = 0;
+    for (long long i0 = ib; i0 < ie; i0 += STAGE_G) {
+        const long long rem = ie - i0;
+        const int cnt = rem < STAGE_G ? (int)rem : STAGE_G;
+        if (i0 + STAGE_G < ie) {  // prefetch the next chunk into the other stage
+            const long long rem2 = ie - (i0 + STAGE_G);
+            stage_chunk(V, stage0 + (cur ^ 1) * stage_doubles, i0 + STAGE_G, rem2 < STAGE_G ? (int)rem2 : STAGE_G, T, tid);
         }
+        cp_async_commit();
+        StageView sv;
+        sv.chunk = stage0 + cur * stage_doubles;
+        sv.jreg = jreg;
+        int g = 0;
+        for (; g + U <= cnt; g += U)
+            bad |= eval_groups<S, U>(sp, V, sv, g, i0 + g, T, th, gr, ld, store, obs_tau, pos, st, fa, lp);
+        if (U > 1)
+            for (; g < cnt; ++g)
+                bad |= eval_groups<S, 1>(sp, V, sv, g, i0 + g, T, th, gr, ld, store, obs_tau, pos, st, fa, lp);
+        cp_async_wait_all();
+        __syncthreads();
+        cur ^= 1;
     }
 
     // expand the sufficient statistics of the fused paths
@@ -269,6 +364,7 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
             if (a1.kind == JBUGS_ARG_GVAL) bump(st.ga, a1.id, fa.cnt[l] * 0.5 / tau - 0.5 * fa.pss[l]);
         }
 
+    if (!active) return;
     // per (tile, chain) partials: [logp, adjoints of the referenced global values]
     double* out = partial + tile * (long long)(1 + sp.n_gref()) * ldg + c;
     out[0] = lp;

@@ -11,25 +11,33 @@
 
 namespace jbugs {
 
-typedef void (*plate_launch_fn)(dim3 grid, cudaStream_t st, const PlateParams& pp, const double* theta, double* grad,
-                                long long ld, long long C, const double* gvals, long long ldg, double* partial,
-                                int* flags, int want_grad);
+typedef cudaError_t (*plate_launch_fn)(dim3 grid, size_t smem, cudaStream_t st, const PlateParams& pp,
+                                       const double* theta, double* grad, long long ld, long long C,
+                                       const double* gvals, long long ldg, double* partial, int* flags,
+                                       int want_grad);
 
 template <class S>
-static void launch_plate_t(dim3 grid, cudaStream_t st, const PlateParams& pp, const double* theta, double* grad,
-                           long long ld, long long C, const double* gvals, long long ldg, double* partial, int* flags,
-                           int want_grad) {
-    plate_kernel<S><<<grid, BLOCK, 0, st>>>(pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
+static cudaError_t launch_plate_t(dim3 grid, size_t smem, cudaStream_t st, const PlateParams& pp, const double* theta,
+                                  double* grad, long long ld, long long C, const double* gvals, long long ldg,
+                                  double* partial, int* flags, int want_grad) {
+    static size_t opted_in = 48 * 1024;  // dynamic shared memory above 48 KB needs an opt-in per kernel
+    if (smem > opted_in) {
+        cudaError_t e = cudaFuncSetAttribute(plate_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        opted_in = smem;
+    }
+    plate_kernel<S><<<grid, BLOCK, smem, st>>>(pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
+    return cudaGetLastError();
 }
 
 struct SpecEntry {
     const char* name;
     plate_launch_fn launch;
-    bool (*matches)(const PlateShape&);
+    bool (*matches)(const PlateShape&, long long T);
     int fused;  // FUSED_* code: tells the host whether the plate needs obs_const
 };
 
-static bool match_never(const PlateShape&) { return false; }
+static bool match_never(const PlateShape&, long long) { return false; }
 
 #include "jbugs_static_specs.inc"
 
@@ -39,17 +47,11 @@ static const SpecEntry g_specs[] = {
 };
 static const int g_num_specs = (int)(sizeof(g_specs) / sizeof(g_specs[0]));
 
-static int select_spec(const PlateShape& sh) {
+static int select_spec(const PlateShape& sh, long long T) {
     for (int k = 1; k < g_num_specs; ++k)
-        if (g_specs[k].matches(sh)) return k;
+        if (g_specs[k].matches(sh, T)) return k;
     return 0;
 }
 static const char* spec_name(int variant) { return g_specs[variant].name; }
-
-static void launch_plate(int variant, dim3 grid, cudaStream_t st, const PlateParams& pp, const double* theta,
-                         double* grad, long long ld, long long C, const double* gvals, long long ldg, double* partial,
-                         int* flags, int want_grad) {
-    g_specs[variant].launch(grid, st, pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
-}
 
 }  // namespace jbugs
