@@ -253,6 +253,8 @@ class Lowering:
                     raise LoweringError(f"loop bounds of '{var}' must depend on data only (rectangular plates)")
                 ext.append((int(self.de.ev(lo, {})), int(self.de.ev(hi, {}))))
             s.extents = tuple(ext)
+            if any(hi < lo for lo, hi in ext):
+                s.kind = "tdata"  # BUGS skips a loop whose lower bound exceeds its upper bound (compiler_pass.jl:21-27)
 
     # ---- C. transformed data ------------------------------------------------------------------
     def _lhs_loopvars(self, s: Stmt):

@@ -1,0 +1,94 @@
+"""The C ABI library loads on a CPU-only box and exports every symbol include/jbugs_cuda.h declares; the plan
+records have the byte layout of include/jbugs_plan.h; compute entry points fail loudly without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import jbugs
+from jbugs import cuda, plan as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(cuda.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return cuda.load()
+
+
+def test_header_symbols_are_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "jbugs_cuda.h")).read()
+    declared = set(re.findall(r"\b(jbugs_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(cuda.SYMBOLS), declared ^ set(cuda.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+
+
+def test_struct_layout_matches_header():
+    src = r'''
+    #include <stdio.h>
+    #include "jbugs_plan.h"
+    int main(void) {
+        printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(jbugs_arg), sizeof(jbugs_global), sizeof(jbugs_gop),
+               sizeof(jbugs_data_desc), sizeof(jbugs_local), sizeof(jbugs_term), sizeof(jbugs_plate),
+               sizeof(jbugs_plan_header));
+        return 0;
+    }'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = list(map(int, subprocess.check_output([exe]).split()))
+    assert sizes == [P.ARG_DT.itemsize, P.GLOBAL_DT.itemsize, P.GOP_DT.itemsize, P.DATA_DT.itemsize,
+                     P.LOCAL_DT.itemsize, P.TERM_DT.itemsize, P.PLATE_DT.itemsize, P.HEADER_DT.itemsize]
+
+
+def test_no_cpu_fallback(lib, fixtures):
+    if cuda.device_count() > 0:
+        pytest.skip("a GPU is present")
+    m = jbugs.compile(jbugs.examples.RATS, fixtures["rats"]["data"], fixtures["rats"]["inits"])
+    with pytest.raises(cuda.JBugsCudaError, match="no CUDA device"):
+        jbugs.LogDensityProblems.logdensity(m, jbugs.getparams(m))
+
+
+def test_plan_create_rejects_garbage(lib):
+    h = ctypes.c_void_p()
+    assert lib.jbugs_plan_create(b"x" * 10, 10, 0, ctypes.byref(h)) == -1
+    assert b"shorter" in lib.jbugs_last_error()
+    blob = bytearray(jbugs.lower(jbugs.examples.PUMPS, {"N": 2, "t": np.ones(2), "x": np.ones(2)})[0].to_bytes())
+    blob[0:8] = b"NOTAPLAN"
+    assert lib.jbugs_plan_create(bytes(blob), len(blob), 0, ctypes.byref(h)) == -1
+    assert b"magic" in lib.jbugs_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "juliabugs.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inc", ".jl")):
+                text = open(os.path.join(dirpath, f)).read()
+                hit = re.search(r"(import|from|include|dlopen|CDLL|ccall)[^\n]*oracle|oracle/|c_oracle|graph_oracle|jbo_|libjbugs_oracle",
+                                text)
+                assert hit is None, (os.path.join(dirpath, f), hit.group(0))
+
+
+def test_host_api_mirrors_reference(fixtures):
+    fx = fixtures["rats"]
+    m = jbugs.compile(jbugs.examples.RATS, fx["data"], fx["inits"])
+    assert jbugs.LogDensityProblems.dimension(m) == 65
+    assert jbugs.LogDensityProblems.capabilities(m) == jbugs.LogDensityOrder(1)
+    th = jbugs.getparams(m)
+    assert th[:5].tolist() == [0.0, 10.0, 0.0, 150.0, 0.0] and th[5] == 6.0 and th[6] == 250.0
+    mu = jbugs.settrans(m, False)
+    assert jbugs.getparams(mu)[:5].tolist() == [1.0, 10.0, 1.0, 150.0, 1.0]
+    with pytest.raises(NotImplementedError):
+        jbugs.set_evaluation_mode(m, jbugs.UseGraph())
+    assert isinstance(jbugs.set_evaluation_mode(m, jbugs.UseCUDABatch(device=0)).evaluation_mode, jbugs.UseCUDABatch)
