@@ -153,7 +153,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dynamic", type=int, default=0, help="1 = force the interpreter kernel")
     ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--shard", default="", choices=["", "chains", "obs"],
+                    help="N>1: 'chains' = every GPU its own chains (weak, no collective; default for rats); "
+                         "'obs' = the data plate is split by observation + NCCL all-reduce (strong; default for seeds)")
     args = ap.parse_args()
+    shard = args.shard or ("obs" if args.workload == "seeds" else "chains")
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -171,9 +175,14 @@ def main():
     n_obs = plan.n_obs()
     D = plan.D
     log(f"[bench] lowered {desc}: D={D} obs={n_obs} in {time.time() - t0:.1f}s")
-    config = {"workload": f"{desc} x {C} chains/GPU, fp64, theta+grad resident in HBM (chain-fast layout)",
-              "chains_per_gpu": C, "D": D, "n_obs": n_obs, "parallelism": f"chains sharded x{n_gpus}, no collective",
-              "l2": "inputs (theta+grad = %.1f GB/GPU) exceed the 126 MB L2; no flush needed" % (2 * 8 * C * D / 1e9)}
+    obs_sharded = shard == "obs" and world > 1
+    par = (f"data plate sharded by observation x{n_gpus} + ncclAllReduce of C x (1+G) doubles" if shard == "obs"
+           else f"chains sharded x{n_gpus}, no collective")
+    config = {"workload": f"{desc} x {C} chains{'' if shard == 'obs' else '/GPU'}, fp64, theta+grad resident in HBM (chain-fast layout)",
+              "chains_per_gpu": C, "D": D, "n_obs": n_obs, "parallelism": par,
+              "l2": "inputs (theta+grad = %.1f GB/GPU) exceed the 126 MB L2; no flush needed"
+                    % (2 * 8 * C * D / 1e9 / (world if obs_sharded else 1))}
+    scaling = "strong" if shard == "obs" else "weak"
 
     # ---------------- reference arm: CPU restatement only (rank 0)
     if args.impl == "reference":
@@ -187,7 +196,7 @@ def main():
         v = float(np.mean([x["value"] for x in vals]))
         cb = dict(vals[-1], value=v)
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": n_gpus,
-                          "steps": K, "warmup": W, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+                          "steps": K, "warmup": W, "ms_per_step": None, "higher_is_better": True, "scaling": scaling,
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                           "cpu_baseline": cb,
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -210,13 +219,21 @@ def main():
         cp.set_option("dynamic", 1)
     if args.tile:
         cp.set_option("tile", args.tile)
+    local_groups = [pl.N for pl in plan.plates]
+    if obs_sharded:
+        from jbugs.dist import shard_bounds, shard_observations
+        shard_observations(model, rank, world)
+        local_groups = [b - a for a, b in (shard_bounds(pl.N, world, rank) for pl in plan.plates)]
+    # theta rows this rank really reads / writes: the globals + the locals of its groups
+    D_local = len(plan.globals) + sum(
+        ng * sum(pl.T if l.level == 1 else 1 for l in pl.locals) for ng, pl in zip(local_groups, plan.plates))
     ld = (C + 15) // 16 * 16
     theta = torch.empty((D, ld), dtype=torch.float64, device=dev)
     grad = torch.empty((D, ld), dtype=torch.float64, device=dev)
     logp = torch.empty(ld, dtype=torch.float64, device=dev)
     status = torch.empty(ld, dtype=torch.int32, device=dev)
     g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
+    g.manual_seed(1234 + (0 if obs_sharded else rank))  # observation sharding: every rank holds the SAME chains
     th0_d = torch.from_numpy(th0).to(dev)
     rows = max(1, (1 << 28) // (8 * ld))
     for r0 in range(0, D, rows):
@@ -263,7 +280,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_per_step = ms_total / K
-    value = n_obs * C * world / (ms_per_step * 1e-3)
+    value = n_obs * C * (1 if obs_sharded else world) / (ms_per_step * 1e-3)
     lp_host = logp[:C].cpu().numpy()
     st_host = status[:C].cpu().numpy()
     if not (np.all(np.isfinite(lp_host)) and np.all(st_host == 0)):
@@ -275,28 +292,32 @@ def main():
         peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, which = 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
-    alg_bytes = 2.0 * 8.0 * C * D
+    alg_bytes = 2.0 * 8.0 * C * D_local
     pk_ms = float(np.mean(plate_ms))
     achieved = alg_bytes / (pk_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and not args.groups:
         try:
-            traffic = json.load(open(tpath)).get(args.workload)
+            t = json.load(open(tpath)).get(args.workload)
+            # the ncu --set full capture replays the kernel ~40x and must save/restore what it writes, so it was
+            # taken at fewer chains than fit beside a 131 GB working set; DRAM bytes are linear in the chain count
+            traffic = t["dram_bytes_per_launch"] * C / t["chains"]
+            traffic_note = f"dram__bytes_read+write from {t['source']} (captured at {t['chains']} chains, scaled to {C})"
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "plate_kernel", "kernel_ms": pk_ms,
+                "traffic": traffic, "traffic_note": traffic_note, "kernel": "plate_kernel", "kernel_ms": pk_ms,
                 "algorithmic_bytes": alg_bytes, "peak_source": which}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
-           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "roofline": roofline,
            "gpu_launches": launches_per_step * K}
 
     # e2e: host pinned theta -> C ABI -> host grad, bounded chain sample
     if rank == 0 or world > 1:
-        if not args.no_e2e:
+        if not args.no_e2e and not obs_sharded:
             Ce = min(args.e2e_chains, C)
             th_h = torch.empty((D, Ce), dtype=torch.float64).pin_memory()
             g_h = torch.empty((D, Ce), dtype=torch.float64).pin_memory()

@@ -594,7 +594,7 @@ static int ensure_workspace(jbugs_plan* p, long long C) {
     CU(cudaMalloc(&p->d_gvals, (size_t)std::max(NG, 1) * ldg * 8));
     p->partial_bytes = (size_t)std::max<long long>(rows, 1) * ldg * 8;
     CU(cudaMalloc(&p->d_partial, p->partial_bytes));
-    CU(cudaMalloc(&p->d_red, (size_t)(1 + std::max(NG, 1)) * ldg * 8));
+    CU(cudaMalloc(&p->d_red, (size_t)(2 + std::max(NG, 1)) * ldg * 8));
     CU(cudaMalloc(&p->d_flags, (size_t)ldg * sizeof(int)));
     p->cap_C = C;
     p->ldg = ldg;
@@ -640,9 +640,23 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         p->launches++;
     }
     if (p->timing) CU(cudaEventRecord(p->ev[2], st));
-    finalize_kernel<<<chain_tiles, BLOCK, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, p->d_partial,
-                                                   p->d_flags, logp, status, p->d_any_bad, want_grad && grad, 1);
-    p->launches++;
+    if (p->comm && p->nranks > 1) {
+        // observation-sharded: reduce this rank's tiles, all-reduce [logp part, global adjoints, flag] over NVLink,
+        // then add the priors of the globals once and finish
+        const int NG = (int)(p->h.n_globals + p->h.n_gtape);
+        finalize_kernel<<<chain_tiles, BLOCK, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, p->d_partial,
+                                                       p->d_flags, logp, status, p->d_any_bad, want_grad && grad, 1, p->d_red);
+        p->launches++;
+        const int e = g_nccl.AllReduce(p->d_red, p->d_red, (size_t)(2 + NG) * ldg, /*ncclDouble*/ 8, /*ncclSum*/ 0, p->comm, st);
+        if (e) return fail(JBUGS_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+        finalize_kernel<<<chain_tiles, BLOCK, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, p->d_partial,
+                                                       p->d_flags, logp, status, p->d_any_bad, want_grad && grad, 2, p->d_red);
+        p->launches++;
+    } else {
+        finalize_kernel<<<chain_tiles, BLOCK, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, p->d_partial,
+                                                       p->d_flags, logp, status, p->d_any_bad, want_grad && grad, 0, p->d_red);
+        p->launches++;
+    }
     if (want_grad && grad) {
         dim3 grid(chain_tiles, (unsigned)std::min<long long>(std::max<long long>(p->h.D, 1), 1024));
         poison_kernel<<<grid, BLOCK, 0, st>>>(grad, ld, C, p->h.D, p->d_flags, p->d_any_bad);

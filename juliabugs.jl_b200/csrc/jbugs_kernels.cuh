@@ -290,7 +290,12 @@ finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
                 const __grid_constant__ FinalParams F, const double* __restrict__ theta, double* __restrict__ grad,
                 long long ld, long long C, const double* __restrict__ gvals, long long ldg,
                 const double* __restrict__ partial, int* __restrict__ flags, double* __restrict__ logp_out,
-                int* __restrict__ status_out, int* __restrict__ any_bad, int want_grad, int add_global_priors) {
+                int* __restrict__ status_out, int* __restrict__ any_bad, int want_grad, int mode,
+                double* __restrict__ red) {
+    // mode 0: single GPU, everything in one pass.
+    // mode 1: observation-sharded, first half: write this rank's reduced partials red[0] = logp part,
+    //         red[1 + k] = adjoint of global value k, red[1 + NG] = DomainError flag; the host all-reduces `red`.
+    // mode 2: second half: read the all-reduced `red`, add the priors of the globals ONCE, finish.
     const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (c >= C) return;
     const int H = G.n_globals, NG = G.n_globals + G.n_gtape;
@@ -301,7 +306,12 @@ finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
     }
     double lp = 0.0;
     bool bad = flags[c] != 0;
-    for (int p = 0; p < F.n_plates; ++p) {
+    if (mode == 2) {
+        lp = red[c];
+        for (int k = 0; k < NG; ++k) ga[k] = red[(long long)(1 + k) * ldg + c];
+        bad = red[(long long)(1 + NG) * ldg + c] != 0.0;
+    }
+    for (int p = 0; p < (mode == 2 ? 0 : F.n_plates); ++p) {
         const PlateFinal& pf = F.p[p];
         const long long stride = (long long)(1 + pf.n_gref) * ldg;
         const double* base = partial + pf.offset * ldg + c;
@@ -314,16 +324,21 @@ finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
             ga[pf.gref[k]] += a;
         }
     }
-    if (add_global_priors) {
-        for (int h = 0; h < H; ++h) {
-            const jbugs_global& g = G.g[h];
-            FamOut o;
-            bad |= fam_eval((int)g.family, gv[h], garg(g.args[0], gv), garg(g.args[1], gv), o);
-            lp += o.lp;
-            ga[h] += o.dx;
-            if (g.args[0].kind == JBUGS_ARG_GVAL) ga[g.args[0].id] += o.da0;
-            if (g.args[1].kind == JBUGS_ARG_GVAL) ga[g.args[1].id] += o.da1;
-        }
+    if (mode == 1) {
+        red[c] = lp;
+        for (int k = 0; k < NG; ++k) red[(long long)(1 + k) * ldg + c] = ga[k];
+        red[(long long)(1 + NG) * ldg + c] = bad ? 1.0 : 0.0;
+        return;
+    }
+    flags[c] = bad ? 1 : 0;  // (mode 2: the flag now reflects every rank's shard)
+    for (int h = 0; h < H; ++h) {
+        const jbugs_global& g = G.g[h];
+        FamOut o;
+        bad |= fam_eval((int)g.family, gv[h], garg(g.args[0], gv), garg(g.args[1], gv), o);
+        lp += o.lp;
+        ga[h] += o.dx;
+        if (g.args[0].kind == JBUGS_ARG_GVAL) ga[g.args[0].id] += o.da0;
+        if (g.args[1].kind == JBUGS_ARG_GVAL) ga[g.args[1].id] += o.da1;
     }
     // reverse sweep over the gtape (recompute the local partials)
     for (int k = G.n_gtape - 1; k >= 0; --k) {
@@ -336,9 +351,10 @@ finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
     for (int h = 0; h < H; ++h) {
         const jbugs_global& g = G.g[h];
         const TrOut t = transform_eval((int)g.transform, g.lb, g.ub, theta[g.theta_idx * ld + c]);
-        if (add_global_priors) lp += t.lj;
-        if (want_grad) grad[g.theta_idx * ld + c] = ga[h] * t.dxdy + (add_global_priors ? t.dljdy : 0.0);
+        lp += t.lj;
+        if (want_grad) grad[g.theta_idx * ld + c] = ga[h] * t.dxdy + t.dljdy;
     }
+    if (bad) flags[c] = 1;
     logp_out[c] = bad ? -dev_inf() : lp;
     if (status_out) status_out[c] = bad ? JBUGS_CHAIN_DOMAIN : JBUGS_CHAIN_OK;
     if (bad) atomicOr(any_bad, 1);
