@@ -73,7 +73,7 @@ struct PlateRt {
     PlateParams pp;        // device-side description (pointers resolved)
     int variant = 0;       // index into the spec table (0 = dynamic interpreter)
     long long n_tiles = 1; // for the current capacity
-    long long partial_offset = 0;
+    long long partial_offset = 0, partial2_offset = 0;
     double obs_const = 0.0;
     bool const_dirty = true;  // obs_const must be recomputed (new data / shard / kernel variant)
     size_t smem_bytes = 0;    // dynamic shared memory of the plate kernel (J region + two stages)
@@ -99,7 +99,8 @@ struct jbugs_plan_s {
     long long cap_C = 0, ldg = 0;
     double* d_gvals = nullptr;
     double* d_partial = nullptr;
-    size_t partial_bytes = 0;
+    double* d_partial2 = nullptr;  // super-tile level of the fixed-order reduction
+    size_t partial_bytes = 0, partial2_bytes = 0, gvals_bytes = 0, red_bytes = 0, flags_bytes = 0;
     double* d_red = nullptr;   // [1 + NG][ldg] reduced partials (multi-GPU path)
     int* d_flags = nullptr;
     int* d_any_bad = nullptr;
@@ -433,10 +434,11 @@ extern "C" int jbugs_plan_create(const void* blob, size_t nbytes, int device, jb
 }
 
 static void free_workspace(jbugs_plan* p) {
-    cudaFree(p->d_gvals); p->d_gvals = nullptr;
+    cudaFree(p->d_gvals); p->d_gvals = nullptr; p->gvals_bytes = 0;
     cudaFree(p->d_partial); p->d_partial = nullptr; p->partial_bytes = 0;
-    cudaFree(p->d_red); p->d_red = nullptr;
-    cudaFree(p->d_flags); p->d_flags = nullptr;
+    cudaFree(p->d_partial2); p->d_partial2 = nullptr; p->partial2_bytes = 0;
+    cudaFree(p->d_red); p->d_red = nullptr; p->red_bytes = 0;
+    cudaFree(p->d_flags); p->d_flags = nullptr; p->flags_bytes = 0;
     p->cap_C = 0;
 }
 
@@ -569,33 +571,48 @@ extern "C" int jbugs_host_free(void* ptr) {
 // ------------------------------------------------------------------------------------------------ workspaces
 static long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
+static int grow(void** ptr, size_t* cap, size_t need) {
+    if (need <= *cap && *ptr) return 0;
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    CU(cudaMalloc(ptr, need));
+    *cap = need;
+    return 0;
+}
+
+// (re)tile the plates for a batch of C chains and make sure the workspaces are large enough (grow only)
 static int ensure_workspace(jbugs_plan* p, long long C) {
-    if (C <= p->cap_C) return 0;
-    free_workspace(p);
+    if (C == p->cap_C) return 0;
     const long long ldg = round_up(C, 16);
     const int NG = (int)(p->h.n_globals + p->h.n_gtape);
-    const long long chain_tiles = (C + BLOCK - 1) / BLOCK;
-    // tiling: enough CTAs for ~4 full waves at 16 CTAs/SM, tiles no smaller than 4 groups
-    const long long target = (long long)p->num_sms * 16 * 4;
-    long long rows = 0;
+    const int blk = plate_block(C);
+    const long long chain_tiles = (C + blk - 1) / blk;
+    // tiling: enough CTAs for ~4 full waves of 2048 resident threads per SM; tiles are whole staged chunks
+    const long long target = (long long)p->num_sms * (2048 / blk) * 4;
+    long long rows = 0, rows2 = 0;
     for (size_t k = 0; k < p->rt.size(); ++k) {
         PlateRt& r = p->rt[k];
         const long long n = std::max<long long>(r.pp.v.i1 - r.pp.v.i0, 0);
         long long nt = std::max<long long>(1, std::min<long long>((target + chain_tiles - 1) / chain_tiles, (n + 3) / 4));
         long long tile = std::max<long long>(1, (n + nt - 1) / nt);
+        if (tile > STAGE_G) tile = round_up(tile, STAGE_G);
         if (p->tile_override > 0) tile = p->tile_override;
         nt = std::max<long long>(1, (n + tile - 1) / tile);
-        if (nt > 65535) { tile = (n + 65534) / 65535; nt = (n + tile - 1) / tile; }
+        if (nt > 65535) { tile = round_up((n + 65534) / 65535, STAGE_G); nt = (n + tile - 1) / tile; }
         r.pp.v.tile = tile;
         r.n_tiles = nt;
         r.partial_offset = rows;
+        r.partial2_offset = rows2;
         rows += nt * (1 + r.pp.sh.n_gref);
+        rows2 += (long long)REDUCE_R * (1 + r.pp.sh.n_gref);
     }
-    CU(cudaMalloc(&p->d_gvals, (size_t)std::max(NG, 1) * ldg * 8));
-    p->partial_bytes = (size_t)std::max<long long>(rows, 1) * ldg * 8;
-    CU(cudaMalloc(&p->d_partial, p->partial_bytes));
-    CU(cudaMalloc(&p->d_red, (size_t)(2 + std::max(NG, 1)) * ldg * 8));
-    CU(cudaMalloc(&p->d_flags, (size_t)ldg * sizeof(int)));
+    int rc;
+    if ((rc = grow((void**)&p->d_gvals, &p->gvals_bytes, (size_t)std::max(NG, 1) * ldg * 8))) return rc;
+    if ((rc = grow((void**)&p->d_partial, &p->partial_bytes, (size_t)std::max<long long>(rows, 1) * ldg * 8))) return rc;
+    if ((rc = grow((void**)&p->d_partial2, &p->partial2_bytes, (size_t)std::max<long long>(rows2, 1) * ldg * 8))) return rc;
+    if ((rc = grow((void**)&p->d_red, &p->red_bytes, (size_t)(2 + std::max(NG, 1)) * ldg * 8))) return rc;
+    if ((rc = grow((void**)&p->d_flags, &p->flags_bytes, (size_t)ldg * sizeof(int)))) return rc;
     p->cap_C = C;
     p->ldg = ldg;
     return 0;
@@ -610,7 +627,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
     int rc = ensure_workspace(p, C);
     if (rc) return rc;
     const long long ldg = p->ldg;
-    const unsigned chain_tiles = (unsigned)((C + BLOCK - 1) / BLOCK);
+    const unsigned chain_tiles = (unsigned)((C + BLOCK - 1) / BLOCK);  // thread-per-chain helper kernels
     for (size_t k = 0; k < p->rt.size(); ++k)
         if ((rc = refresh_obs_const(p, (int)k, st))) return rc;
     if (p->timing) CU(cudaEventRecord(p->ev[0], st));
@@ -618,6 +635,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
     p->launches++;
     if (p->timing) CU(cudaEventRecord(p->ev[1], st));
     FinalParams fp{};
+    std::vector<int> reduce_plates;
     fp.n_plates = (int)p->rt.size();
     for (size_t k = 0; k < p->rt.size(); ++k) {
         PlateRt& r = p->rt[k];
@@ -627,33 +645,52 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         fp.p[k].obs_const = r.obs_const;
         for (int q = 0; q < MAX_GREF; ++q) fp.p[k].gref[q] = r.pp.v.gref[q];
         if (r.pp.v.i1 <= r.pp.v.i0) { fp.p[k].n_tiles = 0; continue; }
-        dim3 grid(chain_tiles, (unsigned)r.n_tiles);
         PlateParams pp = r.pp;  // per-launch copy: slot maps in element offsets of this batch's leading dimension
         for (int l = 0; l < pp.sh.nl; ++l) {
             pp.v.loc[l].row0 = pp.v.loc[l].base * ld;
             pp.v.loc[l].step_i = pp.v.loc[l].si * ld;
             pp.v.loc[l].step_j = pp.v.loc[l].sj * ld;
         }
-        cudaError_t le = g_specs[r.variant].launch(grid, r.smem_bytes, st, pp, theta, grad, ld, C, p->d_gvals, ldg,
+        cudaError_t le = g_specs[r.variant].launch(r.n_tiles, r.smem_bytes, st, pp, theta, grad, ld, C, p->d_gvals, ldg,
                                                    p->d_partial + r.partial_offset * ldg, p->d_flags, want_grad && grad);
         if (le != cudaSuccess) return fail(JBUGS_ERR_CUDA, "plate kernel launch failed: %s", cudaGetErrorString(le));
         p->launches++;
+        reduce_plates.push_back((int)k);
     }
     if (p->timing) CU(cudaEventRecord(p->ev[2], st));
+    const double* partial_in = p->d_partial;
+    {
+        // many tiles: first level of the fixed-order tree (super-tiles), so that finalize's serial loop stays short
+        bool any = false;
+        for (int k : reduce_plates) any |= p->rt[k].n_tiles > 2 * REDUCE_R;
+        if (any) {
+            for (int k : reduce_plates) {
+                PlateRt& r = p->rt[k];
+                const int rows = 1 + r.pp.sh.n_gref;
+                dim3 g2(chain_tiles, (unsigned)rows, REDUCE_R);
+                reduce_tiles_kernel<<<g2, BLOCK, 0, st>>>(p->d_partial + r.partial_offset * ldg, p->d_partial2 + r.partial2_offset * ldg,
+                                                          (int)r.n_tiles, rows, C, ldg);
+                p->launches++;
+                fp.p[k].n_tiles = REDUCE_R;
+                fp.p[k].offset = r.partial2_offset;
+            }
+            partial_in = p->d_partial2;
+        }
+    }
     if (p->comm && p->nranks > 1) {
         // observation-sharded: reduce this rank's tiles, all-reduce [logp part, global adjoints, flag] over NVLink,
         // then add the priors of the globals once and finish
         const int NG = (int)(p->h.n_globals + p->h.n_gtape);
-        finalize_kernel<<<chain_tiles, BLOCK, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, p->d_partial,
+        finalize_kernel<<<chain_tiles, BLOCK, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, partial_in,
                                                        p->d_flags, logp, status, p->d_any_bad, want_grad && grad, 1, p->d_red);
         p->launches++;
         const int e = g_nccl.AllReduce(p->d_red, p->d_red, (size_t)(2 + NG) * ldg, /*ncclDouble*/ 8, /*ncclSum*/ 0, p->comm, st);
         if (e) return fail(JBUGS_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
-        finalize_kernel<<<chain_tiles, BLOCK, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, p->d_partial,
+        finalize_kernel<<<chain_tiles, BLOCK, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, partial_in,
                                                        p->d_flags, logp, status, p->d_any_bad, want_grad && grad, 2, p->d_red);
         p->launches++;
     } else {
-        finalize_kernel<<<chain_tiles, BLOCK, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, p->d_partial,
+        finalize_kernel<<<chain_tiles, BLOCK, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, partial_in,
                                                        p->d_flags, logp, status, p->d_any_bad, want_grad && grad, 0, p->d_red);
         p->launches++;
     }

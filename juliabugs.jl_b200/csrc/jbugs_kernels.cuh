@@ -360,6 +360,24 @@ finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
     if (bad) atomicOr(any_bad, 1);
 }
 
+// First level of the fixed-order tile reduction, used when a plate has many tiles: super-tile r adds the tiles
+// [r * n / R, (r + 1) * n / R) in ascending order; finalize_kernel then adds the R super-tiles in ascending order.
+// Same layout in and out ([tile][row][ldg]), so finalize_kernel does not care which level it reads.
+constexpr int REDUCE_R = 64;
+__global__ void __launch_bounds__(BLOCK)
+reduce_tiles_kernel(const double* __restrict__ partial, double* __restrict__ out, int n_tiles, int rows, long long C,
+                    long long ldg) {
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    const int row = blockIdx.y, r = blockIdx.z;
+    const int t0 = (int)((long long)r * n_tiles / REDUCE_R), t1 = (int)((long long)(r + 1) * n_tiles / REDUCE_R);
+    const double* src = partial + (long long)row * ldg + c;
+    const long long stride = (long long)rows * ldg;
+    double s = 0.0;
+    for (int t = t0; t < t1; ++t) s += src[t * stride];
+    out[((long long)r * rows + row) * ldg + c] = s;
+}
+
 // DomainError -> NaN gradient for the whole chain (logdensityproblems.jl:226-229). Only does work when a
 // chain of this batch was flagged.
 __global__ void __launch_bounds__(BLOCK)

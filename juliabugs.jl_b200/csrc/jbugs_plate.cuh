@@ -30,13 +30,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // copy the streams of groups [i, i + cnt) into one stage
+template <int BLK>
 __device__ __forceinline__ void stage_chunk(const PlateVals& V, double* dst, long long i, int cnt, int T, int tid) {
     for (int s = 0; s < V.n_streams; ++s) {
         const Stream sm = V.streams[s];
         if (sm.kind == JBUGS_ARG_DATA_I) {
-            for (int q = tid; q < cnt; q += BLOCK) cp_async8(dst + sm.soff + q, sm.ptr + i + q);
+            for (int q = tid; q < cnt; q += BLK) cp_async8(dst + sm.soff + q, sm.ptr + i + q);
         } else if (sm.kind == JBUGS_ARG_DATA_IJ) {
-            for (int q = tid; q < T * STAGE_G; q += BLOCK) {
+            for (int q = tid; q < T * STAGE_G; q += BLK) {
                 const int j = q / STAGE_G, g = q % STAGE_G;
                 if (g < cnt) cp_async8(dst + sm.soff + q, sm.ptr + i + g + V.N * (long long)j);
             }
@@ -255,8 +256,9 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
     return bad;
 }
 
-template <class S>
-__global__ void __launch_bounds__(BLOCK, S::MIN_BLOCKS)
+// BLK = chains per CTA (128, or 64 / 32 for small batches so that no lane idles)
+template <class S, int BLK>
+__global__ void __launch_bounds__(BLK, (S::MIN_BLOCKS * (128 / BLK) > 24 ? 24 : S::MIN_BLOCKS * (128 / BLK)))
 plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ theta, double* __restrict__ grad,
              long long ld, long long C, const double* __restrict__ gvals, long long ldg,
              double* __restrict__ partial, int* __restrict__ flags, int want_grad) {
@@ -264,7 +266,7 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
     const S sp(P.sh);
     const PlateVals& V = P.v;
     const int tid = threadIdx.x;
-    const long long c_raw = (long long)blockIdx.x * BLOCK + tid;
+    const long long c_raw = (long long)blockIdx.x * BLK + tid;
     const bool active = c_raw < C;           // inactive lanes still take part in staging and barriers
     const long long c = active ? c_raw : C - 1;
     const long long tile = blockIdx.y;
@@ -280,11 +282,11 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
     for (int s = 0; s < V.n_streams; ++s) {
         const Stream sm = V.streams[s];
         if (sm.kind == JBUGS_ARG_DATA_J)
-            for (int q = tid; q < T; q += BLOCK) jreg[sm.soff + q] = __ldg(sm.ptr + q);
+            for (int q = tid; q < T; q += BLK) jreg[sm.soff + q] = __ldg(sm.ptr + q);
     }
     {
         const long long rem = ie - ib;
-        stage_chunk(V, stage0, ib, rem < STAGE_G ? (int)rem : STAGE_G, T, tid);
+        stage_chunk<BLK>(V, stage0, ib, rem < STAGE_G ? (int)rem : STAGE_G, T, tid);
         cp_async_commit();
     }
 
@@ -324,7 +326,7 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
         const int cnt = rem < STAGE_G ? (int)rem : STAGE_G;
         if (i0 + STAGE_G < ie) {  // prefetch the next chunk into the other stage
             const long long rem2 = ie - (i0 + STAGE_G);
-            stage_chunk(V, stage0 + (cur ^ 1) * stage_doubles, i0 + STAGE_G, rem2 < STAGE_G ? (int)rem2 : STAGE_G, T, tid);
+            stage_chunk<BLK>(V, stage0 + (cur ^ 1) * stage_doubles, i0 + STAGE_G, rem2 < STAGE_G ? (int)rem2 : STAGE_G, T, tid);
         }
         cp_async_commit();
         StageView sv;

@@ -11,23 +11,38 @@
 
 namespace jbugs {
 
-typedef cudaError_t (*plate_launch_fn)(dim3 grid, size_t smem, cudaStream_t st, const PlateParams& pp,
+// chains per CTA for a batch of C chains: no idle lanes for small batches
+static inline int plate_block(long long C) { return C <= 32 ? 32 : (C <= 64 ? 64 : 128); }
+
+typedef cudaError_t (*plate_launch_fn)(long long n_tiles, size_t smem, cudaStream_t st, const PlateParams& pp,
                                        const double* theta, double* grad, long long ld, long long C,
                                        const double* gvals, long long ldg, double* partial, int* flags,
                                        int want_grad);
 
-template <class S>
-static cudaError_t launch_plate_t(dim3 grid, size_t smem, cudaStream_t st, const PlateParams& pp, const double* theta,
-                                  double* grad, long long ld, long long C, const double* gvals, long long ldg,
-                                  double* partial, int* flags, int want_grad) {
+template <class S, int BLK>
+static cudaError_t launch_plate_blk(long long n_tiles, size_t smem, cudaStream_t st, const PlateParams& pp,
+                                    const double* theta, double* grad, long long ld, long long C, const double* gvals,
+                                    long long ldg, double* partial, int* flags, int want_grad) {
     static size_t opted_in = 48 * 1024;  // dynamic shared memory above 48 KB needs an opt-in per kernel
     if (smem > opted_in) {
-        cudaError_t e = cudaFuncSetAttribute(plate_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(plate_kernel<S, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         opted_in = smem;
     }
-    plate_kernel<S><<<grid, BLOCK, smem, st>>>(pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
+    dim3 grid((unsigned)((C + BLK - 1) / BLK), (unsigned)n_tiles);
+    plate_kernel<S, BLK><<<grid, BLK, smem, st>>>(pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
     return cudaGetLastError();
+}
+
+template <class S>
+static cudaError_t launch_plate_t(long long n_tiles, size_t smem, cudaStream_t st, const PlateParams& pp,
+                                  const double* theta, double* grad, long long ld, long long C, const double* gvals,
+                                  long long ldg, double* partial, int* flags, int want_grad) {
+    switch (plate_block(C)) {
+    case 32: return launch_plate_blk<S, 32>(n_tiles, smem, st, pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
+    case 64: return launch_plate_blk<S, 64>(n_tiles, smem, st, pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
+    default: return launch_plate_blk<S, 128>(n_tiles, smem, st, pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
+    }
 }
 
 struct SpecEntry {
