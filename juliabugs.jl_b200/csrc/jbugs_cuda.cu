@@ -11,8 +11,10 @@
 #include <vector>
 
 #include "../../include/jbugs_cuda.h"
+#define JBUGS_HOST_TU
 #include "jbugs_kernels.cuh"
 #include "jbugs_obsconst.cuh"
+#define JBUGS_SPEC_TABLE
 #include "jbugs_specs.cuh"
 
 using namespace jbugs;

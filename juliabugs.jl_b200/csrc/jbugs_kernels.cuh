@@ -243,6 +243,7 @@ __device__ __forceinline__ bool gtape_forward(const jbugs_gop& o, const double* 
     }
 }
 
+#ifdef JBUGS_HOST_TU  // the non-template kernels are compiled once, in the host translation unit
 __global__ void __launch_bounds__(BLOCK)
 prologue_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__ GTapeParams TP,
                 const double* __restrict__ theta, long long ld, long long C, double* __restrict__ gvals,
@@ -264,6 +265,7 @@ prologue_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
     for (int k = 0; k < G.n_globals + G.n_gtape; ++k) gvals[k * ldg + c] = gv[k];
     flags[c] = bad ? 1 : 0;
 }
+#endif  // JBUGS_HOST_TU
 
 }  // namespace jbugs
 
@@ -271,6 +273,7 @@ prologue_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
 
 namespace jbugs {
 
+#ifdef JBUGS_HOST_TU
 // ------------------------------------------------------------------------------------------------
 // finalize: add the tiles in ascending order, the priors of the globals, reverse the gtape and the
 // bijectors; write logp, status and the gradient rows of the globals.
@@ -408,5 +411,6 @@ transpose_kernel(const double* __restrict__ src, long long lds, double* __restri
         if (r < rows && q < cols) dst[q * ldd + r] = tile[tx][k];
     }
 }
+#endif  // JBUGS_HOST_TU
 
 }  // namespace jbugs

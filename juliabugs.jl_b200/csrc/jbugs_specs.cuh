@@ -3,6 +3,9 @@
 // Variant 0 is the interpreter (`DynSpec`): any plate of the plan class.  The other variants are
 // compile-time specialisations of the SAME kernel body for the plate shapes of the configurations
 // named in BASELINE.json; they are selected when the run-time shape is identical to the static one.
+//
+// The kernels are instantiated in separate translation units (spec_*.cu) so that they compile in
+// parallel; this header only declares their launchers.
 #pragma once
 
 #include <cstring>
@@ -14,36 +17,21 @@ namespace jbugs {
 // chains per CTA for a batch of C chains: no idle lanes for small batches
 static inline int plate_block(long long C) { return C <= 32 ? 32 : (C <= 64 ? 64 : 128); }
 
-typedef cudaError_t (*plate_launch_fn)(long long n_tiles, size_t smem, cudaStream_t st, const PlateParams& pp,
-                                       const double* theta, double* grad, long long ld, long long C,
-                                       const double* gvals, long long ldg, double* partial, int* flags,
-                                       int want_grad);
+#define JBUGS_LAUNCH_PARAMS                                                                                     \
+    long long n_tiles, size_t smem, cudaStream_t st, const PlateParams &pp, const double *theta, double *grad, \
+        long long ld, long long C, const double *gvals, long long ldg, double *partial, int *flags, int want_grad
+#define JBUGS_LAUNCH_ARGS n_tiles, smem, st, pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad
 
-template <class S, int BLK>
-static cudaError_t launch_plate_blk(long long n_tiles, size_t smem, cudaStream_t st, const PlateParams& pp,
-                                    const double* theta, double* grad, long long ld, long long C, const double* gvals,
-                                    long long ldg, double* partial, int* flags, int want_grad) {
-    static size_t opted_in = 48 * 1024;  // dynamic shared memory above 48 KB needs an opt-in per kernel
-    if (smem > opted_in) {
-        cudaError_t e = cudaFuncSetAttribute(plate_kernel<S, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        opted_in = smem;
-    }
-    dim3 grid((unsigned)((C + BLK - 1) / BLK), (unsigned)n_tiles);
-    plate_kernel<S, BLK><<<grid, BLK, smem, st>>>(pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
-    return cudaGetLastError();
-}
+typedef cudaError_t (*plate_launch_fn)(JBUGS_LAUNCH_PARAMS);
 
-template <class S>
-static cudaError_t launch_plate_t(long long n_tiles, size_t smem, cudaStream_t st, const PlateParams& pp,
-                                  const double* theta, double* grad, long long ld, long long C, const double* gvals,
-                                  long long ldg, double* partial, int* flags, int want_grad) {
-    switch (plate_block(C)) {
-    case 32: return launch_plate_blk<S, 32>(n_tiles, smem, st, pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
-    case 64: return launch_plate_blk<S, 64>(n_tiles, smem, st, pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
-    default: return launch_plate_blk<S, 128>(n_tiles, smem, st, pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
-    }
-}
+// defined in spec_dyn.cu / spec_rats.cu / spec_glm.cu / spec_epil.cu
+cudaError_t launch_dyn(JBUGS_LAUNCH_PARAMS);
+cudaError_t launch_rats_t5(JBUGS_LAUNCH_PARAMS);
+cudaError_t launch_rats(JBUGS_LAUNCH_PARAMS);
+cudaError_t launch_seeds(JBUGS_LAUNCH_PARAMS);
+cudaError_t launch_surgical(JBUGS_LAUNCH_PARAMS);
+cudaError_t launch_pumps(JBUGS_LAUNCH_PARAMS);
+cudaError_t launch_epil(JBUGS_LAUNCH_PARAMS);
 
 struct SpecEntry {
     const char* name;
@@ -52,13 +40,19 @@ struct SpecEntry {
     int fused;  // FUSED_* code: tells the host whether the plate needs obs_const
 };
 
-static bool match_never(const PlateShape&, long long) { return false; }
-
 #include "jbugs_static_specs.inc"
 
+#ifdef JBUGS_SPEC_TABLE  // only the host translation unit owns the table
+static bool match_never(const PlateShape&, long long) { return false; }
+
 static const SpecEntry g_specs[] = {
-    {"dynamic", &launch_plate_t<DynSpec>, &match_never, FUSED_NONE},
-    JBUGS_STATIC_SPEC_ENTRIES
+    {"dynamic", &launch_dyn, &match_never, FUSED_NONE},
+    {"rats_normal_identity_T5", &launch_rats_t5, &RatsDesc<5>::matches, RatsDesc<5>::FUSED},
+    {"rats_normal_identity", &launch_rats, &RatsDesc<0>::matches, RatsDesc<0>::FUSED},
+    {"seeds_binomial_logit", &launch_seeds, &SeedsDesc::matches, SeedsDesc::FUSED},
+    {"surgical_binomial_logit", &launch_surgical, &SurgicalDesc::matches, SurgicalDesc::FUSED},
+    {"epil_poisson_log", &launch_epil, &EpilDesc<0>::matches, EpilDesc<0>::FUSED},
+    {"pumps_poisson_gamma", &launch_pumps, &PumpsDesc::matches, PumpsDesc::FUSED},
 };
 static const int g_num_specs = (int)(sizeof(g_specs) / sizeof(g_specs[0]));
 
@@ -68,5 +62,6 @@ static int select_spec(const PlateShape& sh, long long T) {
     return 0;
 }
 static const char* spec_name(int variant) { return g_specs[variant].name; }
+#endif
 
 }  // namespace jbugs
