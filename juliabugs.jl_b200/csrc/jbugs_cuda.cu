@@ -110,6 +110,15 @@ struct jbugs_plan_s {
     double *s_theta = nullptr, *s_grad = nullptr, *s_theta_t = nullptr, *s_grad_t = nullptr, *s_logp = nullptr;
     int* s_status = nullptr;
     long long s_C = 0;
+    // pipelined host path: two staging slots, copy-in / copy-out streams, per-slot events
+    struct Slot {
+        double *theta = nullptr, *grad = nullptr, *theta_t = nullptr, *grad_t = nullptr, *logp = nullptr;
+        int* status = nullptr;
+        cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
+    } slot[2];
+    long long slot_C = 0;
+    bool slot_t = false;
+    cudaStream_t st_in = nullptr, st_out = nullptr;
     // library-owned batch
     double *b_theta = nullptr, *b_grad = nullptr, *b_logp = nullptr;
     int* b_status = nullptr;
@@ -124,6 +133,8 @@ struct jbugs_plan_s {
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
 };
+
+static void free_slots(jbugs_plan* p);
 
 static int set_device(const jbugs_plan* p) {
     CU(cudaSetDevice(p->device));
@@ -476,6 +487,14 @@ extern "C" int jbugs_plan_destroy(jbugs_plan* p) {
     for (void* d : p->d_slots) cudaFree(d);
     free_workspace(p);
     free_staging(p);
+    free_slots(p);
+    for (auto& s : p->slot) {
+        if (s.in_done) cudaEventDestroy(s.in_done);
+        if (s.comp_done) cudaEventDestroy(s.comp_done);
+        if (s.out_done) cudaEventDestroy(s.out_done);
+    }
+    if (p->st_in) cudaStreamDestroy(p->st_in);
+    if (p->st_out) cudaStreamDestroy(p->st_out);
     jbugs_batch_free(p);
     cudaFree(p->d_any_bad);
     for (auto& e : p->ev)
@@ -734,6 +753,8 @@ static int ensure_staging(jbugs_plan* p, long long Cc, bool need_t) {
     return 0;
 }
 
+#include "jbugs_staged.inc"
+
 extern "C" int jbugs_eval_batch(jbugs_plan* p, const double* theta, int64_t ld, int64_t C, int layout, double* logp,
                                 double* grad, int32_t* status, int want_grad, int flags, void* stream) {
     if (!p || !theta || !logp) return fail(JBUGS_ERR_INVALID, "null argument");
@@ -759,7 +780,9 @@ extern "C" int jbugs_eval_batch(jbugs_plan* p, const double* theta, int64_t ld, 
         }
         return JBUGS_OK;
     }
-    // host buffers and/or PARAM_FAST: go through library staging in chunks of chains
+    // host buffers and/or PARAM_FAST: pipelined through library staging in chunks of chains
+    return eval_staged(p, theta, ld, C, layout, logp, grad, status, want_grad, st);
+#if 0  // superseded serial staging path
     const bool theta_dev = is_device_ptr(theta), logp_dev = is_device_ptr(logp), grad_dev = is_device_ptr(grad), status_dev = is_device_ptr(status);
     const long long budget = 1LL << 31;  // bytes per staging buffer
     long long Cc = std::max<long long>(1, std::min<long long>(C, budget / (8 * std::max<long long>(D, 1))));
@@ -812,6 +835,7 @@ extern "C" int jbugs_eval_batch(jbugs_plan* p, const double* theta, int64_t ld, 
     p->last_plate_ms = plate_ms;
     p->last_total_ms = total_ms;
     return JBUGS_OK;
+#endif
 }
 
 extern "C" int jbugs_batch_alloc(jbugs_plan* p, int64_t C, double** theta_dev, double** grad_dev, double** logp_dev,

@@ -1,0 +1,22 @@
+// spec_dispatch.cu -- per-spec launchers: pick the CTA width (chains per CTA) from the batch size.
+#include "jbugs_specs.cuh"
+namespace jbugs {
+#define JB_DISPATCH(name)                                        \
+    cudaError_t name##_32(JBUGS_LAUNCH_PARAMS);                  \
+    cudaError_t name##_64(JBUGS_LAUNCH_PARAMS);                  \
+    cudaError_t name##_128(JBUGS_LAUNCH_PARAMS);                 \
+    cudaError_t name(JBUGS_LAUNCH_PARAMS) {                      \
+        switch (plate_block(C)) {                                \
+        case 32: return name##_32(JBUGS_LAUNCH_ARGS);            \
+        case 64: return name##_64(JBUGS_LAUNCH_ARGS);            \
+        default: return name##_128(JBUGS_LAUNCH_ARGS);           \
+        }                                                        \
+    }
+JB_DISPATCH(launch_dyn)
+JB_DISPATCH(launch_rats_t5)
+JB_DISPATCH(launch_rats)
+JB_DISPATCH(launch_seeds)
+JB_DISPATCH(launch_surgical)
+JB_DISPATCH(launch_pumps)
+JB_DISPATCH(launch_epil)
+}  // namespace jbugs
