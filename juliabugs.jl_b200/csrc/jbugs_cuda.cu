@@ -125,6 +125,7 @@ struct jbugs_plan_s {
     // options / stats
     int force_dynamic = 0;
     long long tile_override = 0;
+    long long host_chunk = 0;  // chains per pipelined chunk of the host path (0 = automatic)
     long long launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_plate_ms = 0.f, last_total_ms = 0.f;
@@ -547,6 +548,11 @@ extern "C" int jbugs_plan_set_option(jbugs_plan* p, const char* key, int64_t val
         if (value < 0) return fail(JBUGS_ERR_INVALID, "tile must be >= 0");
         p->tile_override = value;
         p->cap_C = 0;
+        return JBUGS_OK;
+    }
+    if (!strcmp(key, "host_chunk")) {
+        if (value < 0) return fail(JBUGS_ERR_INVALID, "host_chunk must be >= 0");
+        p->host_chunk = value;
         return JBUGS_OK;
     }
     if (!strcmp(key, "timing")) {

@@ -1,0 +1,159 @@
+# JuliaBUGSCUDABatch.jl -- the Julia side of the drop-in: what a JuliaBUGS maintainer adds (as a package
+# extension or `src/model/cuda_batch.jl`) to bind libjbugs_cuda.  SHIPPED UNEXECUTED: Julia is not installed
+# in the build image; the same ABI is exercised from Python (`jbugs/cuda.py`) by the test-suite.
+#
+# Reference plug-in points (paths relative to JuliaBUGS/):
+#   EvaluationMode subtypes            src/model/bugsmodel.jl:248-252
+#   set_evaluation_mode                src/model/bugsmodel.jl:736-801
+#   _eval_logdensity dispatch          src/model/logdensityproblems.jl:3-17
+#   LogDensityProblems methods         src/model/logdensityproblems.jl:19-55, 168-174, 219-232
+#   cache invalidation on condition    src/model/abstractppl.jl:796-799
+#   set_observed_values!               src/model/abstractppl.jl:872-888
+module JuliaBUGSCUDABatch
+
+using JuliaBUGS
+using JuliaBUGS: BUGSModel
+using JuliaBUGS.Model: EvaluationMode
+using LogDensityProblems
+
+const libjbugs = get(ENV, "JBUGS_CUDA_LIB", "libjbugs_cuda")
+
+# ---------------------------------------------------------------------------------------------- ABI (include/jbugs_cuda.h)
+const LAYOUT_CHAIN_FAST = Cint(0)   # element (d, c) at d*ld + c : a Julia Matrix{Float64}(C, D)  (ld = C)
+const LAYOUT_PARAM_FAST = Cint(1)   # element (d, c) at c*ld + d : a Julia Matrix{Float64}(D, C)  (ld = D)
+
+struct JBugsError <: Exception
+    code::Cint
+    msg::String
+end
+_check(rc) = rc == 0 ? nothing : throw(JBugsError(rc, unsafe_string(ccall((:jbugs_last_error, libjbugs), Cstring, ()))))
+
+mutable struct PlanHandle
+    ptr::Ptr{Cvoid}
+    function PlanHandle(blob::Vector{UInt8}, device::Integer)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        _check(ccall((:jbugs_plan_create, libjbugs), Cint, (Ptr{UInt8}, Csize_t, Cint, Ref{Ptr{Cvoid}}),
+                     blob, length(blob), device, out))
+        h = new(out[])
+        finalizer(h -> (h.ptr == C_NULL || ccall((:jbugs_plan_destroy, libjbugs), Cint, (Ptr{Cvoid},), h.ptr); h.ptr = C_NULL), h)
+        return h
+    end
+end
+
+dim(h::PlanHandle) = Int(ccall((:jbugs_dim, libjbugs), Int64, (Ptr{Cvoid},), h.ptr))
+
+function upload!(h::PlanHandle, slot::Integer, values::Vector{Float64})
+    _check(ccall((:jbugs_plan_upload_data, libjbugs), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t, Cint),
+                 h.ptr, slot, values, sizeof(values), 0))
+end
+function upload!(h::PlanHandle, slot::Integer, values::Vector{Int64})
+    _check(ccall((:jbugs_plan_upload_data, libjbugs), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t, Cint),
+                 h.ptr, slot, values, sizeof(values), 1))
+end
+
+"""
+    eval_batch!(h, θ::Matrix{Float64}, logp, grad, status; want_grad=true)
+
+`θ` is `D × C` (one column per chain, Julia's native layout == PARAM_FAST).  Host arrays are staged by the
+library; pass `CuArray` pointers (CHAIN_FAST, see `batch_alloc`) to evaluate in place on the device.
+"""
+function eval_batch!(h::PlanHandle, θ::Matrix{Float64}, logp::Vector{Float64}, grad::Matrix{Float64},
+                     status::Vector{Int32}; want_grad::Bool=true)
+    D, C = size(θ)
+    _check(ccall((:jbugs_eval_batch, libjbugs), Cint,
+                 (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Cint, Cint, Ptr{Cvoid}),
+                 h.ptr, θ, D, C, LAYOUT_PARAM_FAST, logp, grad, status, want_grad, 0, C_NULL))
+    return logp, grad, status
+end
+
+# ---------------------------------------------------------------------------------------------- the evaluation mode
+"""
+    UseCUDABatch(; device=0)
+
+New `EvaluationMode`: the model is lowered at statement/plate granularity to a flat kernel plan
+(`include/jbugs_plan.h`) and evaluated by libjbugs_cuda for a whole batch of chains per launch.
+"""
+struct UseCUDABatch <: EvaluationMode
+    device::Int
+end
+UseCUDABatch(; device=0) = UseCUDABatch(device)
+
+# Per-model device state, keyed like `log_density_computation_function`: dropped whenever the graph changes.
+const _PLANS = WeakKeyDict{Any,PlanHandle}()
+
+"""
+    lower_to_plan(model::BUGSModel) -> (blob::Vector{UInt8}, slots::Vector{Vector})
+
+Statement-level lowering.  It starts from exactly what `_generate_lowered_model_def`
+(src/source_gen.jl:459-552) already computes -- statement ids, the coarse statement graph, the fissioned and
+sorted statements with their loop nests, and the per-statement observed / parameter / generated-quantity
+classes (`:615-666`) -- and, instead of emitting Julia `for` loops, emits for every observed statement one
+plate record (term tape of the inlined linear predictor, inverse-link tape, family, local priors with their
+affine theta-slot maps) plus the data slots.  The record layout is `include/jbugs_plan.h`; the reference
+implementation of this pass, byte-for-byte the same plan, is `jbugs/lowering.py`.
+"""
+function lower_to_plan end   # provided by the maintainer-side port of jbugs/lowering.py (see INTEGRATION.md)
+
+function plan_handle(model::BUGSModel)
+    mode = model.evaluation_mode::UseCUDABatch
+    get!(_PLANS, model) do
+        blob, slots = lower_to_plan(model)
+        h = PlanHandle(blob, mode.device)
+        foreach(((k, v),) -> upload!(h, k - 1, v), enumerate(slots))
+        h
+    end
+end
+
+# set_evaluation_mode(model, UseCUDABatch()) : same contract as the generated mode (transformed space only,
+# parameter order rebuilt from the reconstructed program, bugsmodel.jl:770-799)
+function JuliaBUGS.set_evaluation_mode(model::BUGSModel, mode::UseCUDABatch)
+    model.transformed || error("UseCUDABatch evaluates in transformed (unconstrained) space; call settrans(model, true)")
+    model = JuliaBUGS.set_evaluation_mode(model, JuliaBUGS.UseGeneratedLogDensityFunction())  # fixes sorted_nodes
+    return JuliaBUGS.BangBang.setproperty!!(model, :evaluation_mode, mode)
+end
+
+# condition / fix / decondition create a new model object (abstractppl.jl:740-809): the WeakKeyDict entry of the
+# old object dies with it.  set_observed_values! keeps the structure: re-upload, do not re-plan.
+function reupload!(model::BUGSModel)
+    h = plan_handle(model)
+    _, slots = lower_to_plan(model)
+    foreach(((k, v),) -> upload!(h, k - 1, v), enumerate(slots))
+    return model
+end
+
+# ---------------------------------------------------------------------------------------------- LogDensityProblems
+function JuliaBUGS.Model._eval_logdensity(model::BUGSModel, ::UseCUDABatch, x::AbstractVector)
+    logp = Vector{Float64}(undef, 1)
+    eval_batch!(plan_handle(model), reshape(collect(Float64, x), :, 1), logp, Matrix{Float64}(undef, 0, 0),
+                Vector{Int32}(undef, 1); want_grad=false)
+    return logp[1]          # -Inf on DomainError, exactly like logdensityproblems.jl:22-26
+end
+
+# the CUDA mode carries its own reverse pass: first-order capability without an AD backend
+struct CUDABatchModel{M<:BUGSModel}
+    base_model::M
+end
+LogDensityProblems.capabilities(::Type{<:CUDABatchModel}) = LogDensityProblems.LogDensityOrder{1}()
+LogDensityProblems.dimension(m::CUDABatchModel) = LogDensityProblems.dimension(m.base_model)
+LogDensityProblems.logdensity(m::CUDABatchModel, x::AbstractVector) = LogDensityProblems.logdensity(m.base_model, x)
+
+function LogDensityProblems.logdensity_and_gradient(m::CUDABatchModel, x::AbstractVector)
+    θ = reshape(collect(Float64, x), :, 1)
+    logp, grad, _ = eval_batch!(plan_handle(m.base_model), θ, Vector{Float64}(undef, 1), similar(θ), Vector{Int32}(undef, 1))
+    return logp[1], vec(grad)            # fresh copy; (-Inf, NaN...) on DomainError (logdensityproblems.jl:226-229)
+end
+
+"""
+    logdensity_and_gradient_batch(m, θ::AbstractMatrix) -> (logp::Vector, grad::Matrix)
+
+The new batched entry point (the reference has none: one θ per call, logdensityproblems.jl:19,219):
+`θ` is `D × C`, one column per chain.
+"""
+function logdensity_and_gradient_batch(m::CUDABatchModel, θ::AbstractMatrix)
+    θ = Matrix{Float64}(θ)
+    C = size(θ, 2)
+    logp, grad, status = eval_batch!(plan_handle(m.base_model), θ, Vector{Float64}(undef, C), similar(θ), Vector{Int32}(undef, C))
+    return logp, grad
+end
+
+end # module
