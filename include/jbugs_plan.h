@@ -16,7 +16,7 @@
  *
  * The blob is a header followed by packed arrays of the records below, in this order:
  *   header | globals[n_globals] | gtape[n_gtape] | data[n_data] | plates[n_plates]
- *          | locals[n_locals] | terms[n_terms]
+ *          | locals[n_locals] | terms[n_terms] | dense[n_dense]
  * All integers little-endian, all reals IEEE-754 binary64 (the reference computes in Float64,
  * indices in Int64).  Arrays of observations/covariates are NOT in the blob: they are uploaded
  * per data slot (jbugs_plan_upload_data) so that `set_observed_values!`
@@ -156,6 +156,17 @@ typedef struct jbugs_plate {
     jbugs_arg aux[3];              /* the family's arguments; aux[eta_arg] is ignored */
 } jbugs_plate;                     /* 128 bytes */
 
+/* Dense linear predictor:  y[i] ~ dbern|dbin(logistic(inprod(X[i, 1:P], beta[1:P])) [, n[i]])
+ * (`inprod`: JuliaBUGS/src/BUGSPrimitives/functions.jl:33-35).  beta's prior is an ordinary prior-only plate
+ * (has_obs = 0) over j in [0, P); this record adds the likelihood and its gradient w.r.t. beta, evaluated as two
+ * FP64 tensor-core GEMMs over all chains. */
+typedef struct jbugs_dense {
+    int64_t N, P;                      /* observations, coefficients                       */
+    int64_t theta_base, theta_stride;  /* slot of beta[j] = theta_base + theta_stride * j  */
+    int32_t x_slot, y_slot, n_slot;    /* X: N x P column-major; n_slot < 0: Bernoulli     */
+    uint32_t family, link, pad;        /* BERNOULLI | BINOMIAL, JBUGS_OP_LOGISTIC          */
+} jbugs_dense;                         /* 56 bytes */
+
 typedef struct jbugs_plan_header {
     char magic[8];
     uint32_t version;
@@ -167,7 +178,9 @@ typedef struct jbugs_plan_header {
     uint32_t n_plates;
     uint32_t n_locals;
     uint32_t n_terms;
-    uint64_t reserved[2];
+    uint32_t n_dense; /* jbugs_dense records appended after terms[] */
+    uint32_t reserved32;
+    uint64_t reserved;
 } jbugs_plan_header; /* 64 bytes */
 
 #ifdef __cplusplus

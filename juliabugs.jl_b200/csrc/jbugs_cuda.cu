@@ -14,6 +14,7 @@
 #define JBUGS_HOST_TU
 #include "jbugs_kernels.cuh"
 #include "jbugs_obsconst.cuh"
+#include "jbugs_dense.cuh"
 #define JBUGS_SPEC_TABLE
 #include "jbugs_specs.cuh"
 
@@ -91,6 +92,15 @@ struct jbugs_plan_s {
     std::vector<jbugs_plate> plates;
     std::vector<jbugs_local> locals;
     std::vector<jbugs_term> terms;
+    std::vector<jbugs_dense> dense;
+    // dense predictors: residual matrix R [N x ldr], split-K partials of X^T R, per-chain logp partial rows
+    double* d_R = nullptr;
+    double* d_Gp = nullptr;
+    size_t R_bytes = 0, Gp_bytes = 0;
+    long long dense_partial_offset = 0;  // rows (of ldg) inside d_partial
+    int dense_row_groups = 0, dense_splits = 0;
+    double dense_const = 0.0;
+    bool dense_const_dirty = true;
     std::vector<void*> d_slots;
     std::vector<char> uploaded;
     std::vector<PlateRt> rt;
@@ -368,11 +378,13 @@ extern "C" int jbugs_plan_create(const void* blob, size_t nbytes, int device, jb
     if (h.version != JBUGS_PLAN_VERSION) return fail(JBUGS_ERR_INVALID, "plan version %u, library speaks %u", h.version, JBUGS_PLAN_VERSION);
     const size_t need = sizeof h + h.n_globals * sizeof(jbugs_global) + h.n_gtape * sizeof(jbugs_gop) +
                         h.n_data * sizeof(jbugs_data_desc) + h.n_plates * sizeof(jbugs_plate) +
-                        h.n_locals * sizeof(jbugs_local) + h.n_terms * sizeof(jbugs_term);
+                        h.n_locals * sizeof(jbugs_local) + h.n_terms * sizeof(jbugs_term) +
+                        h.n_dense * sizeof(jbugs_dense);
     if (need != nbytes) return fail(JBUGS_ERR_INVALID, "plan blob is %zu bytes, records need %zu", nbytes, need);
     if (h.D < 0) return fail(JBUGS_ERR_INVALID, "negative dimension");
     if (h.n_globals + h.n_gtape > (uint32_t)MAX_GVALS) return fail(JBUGS_ERR_UNSUPPORTED, "more than %d global values", MAX_GVALS);
-    if (h.n_plates > 8) return fail(JBUGS_ERR_UNSUPPORTED, "more than 8 plates");
+    if (h.n_plates + h.n_dense > 8) return fail(JBUGS_ERR_UNSUPPORTED, "more than 8 plates");
+    if (h.n_dense > 1) return fail(JBUGS_ERR_UNSUPPORTED, "more than one dense predictor");
     int ndev = jbugs_device_count();
     if (ndev <= 0) return fail(JBUGS_ERR_CUDA, "no CUDA device is available (libjbugs_cuda has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(JBUGS_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
@@ -392,6 +404,7 @@ extern "C" int jbugs_plan_create(const void* blob, size_t nbytes, int device, jb
     take(p->plates, h.n_plates);
     take(p->locals, h.n_locals);
     take(p->terms, h.n_terms);
+    take(p->dense, h.n_dense);
     auto destroy = [&](int rc) {
         jbugs_plan_destroy(p);
         return rc;
@@ -440,6 +453,19 @@ extern "C" int jbugs_plan_create(const void* blob, size_t nbytes, int device, jb
     for (uint32_t k = 0; k < h.n_gtape; ++k) p->tp.op[k] = p->gtape[k];
     int rc = rebuild_plates(p);
     if (rc) return destroy(rc);
+    for (size_t k = 0; k < p->dense.size(); ++k) {
+        const jbugs_dense& dn = p->dense[k];
+        auto slot_ok = [&](int s, long long need) { return s >= 0 && s < (int)h.n_data && p->data[s].dtype == 0 && p->data[s].len >= need; };
+        if (dn.N < 0 || dn.P < 1) return destroy(fail(JBUGS_ERR_INVALID, "dense %zu: bad extents", k));
+        if (!slot_ok(dn.x_slot, dn.N * dn.P) || !slot_ok(dn.y_slot, dn.N) || (dn.n_slot >= 0 && !slot_ok(dn.n_slot, dn.N)))
+            return destroy(fail(JBUGS_ERR_INVALID, "dense %zu: data slot missing or too short", k));
+        const long long last = dn.theta_base + dn.theta_stride * (dn.P - 1);
+        if (dn.theta_base < 0 || dn.theta_base >= h.D || last < 0 || last >= h.D)
+            return destroy(fail(JBUGS_ERR_INVALID, "dense %zu: coefficient slots out of range", k));
+        if (dn.link != JBUGS_OP_LOGISTIC || (dn.family != JBUGS_FAM_BERNOULLI && dn.family != JBUGS_FAM_BINOMIAL) ||
+            (dn.family == JBUGS_FAM_BINOMIAL) != (dn.n_slot >= 0))
+            return destroy(fail(JBUGS_ERR_UNSUPPORTED, "dense %zu: only dbern / dbin with a logit link", k));
+    }
     for (auto& e : p->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return destroy(fail(JBUGS_ERR_CUDA, "cudaEventCreate failed"));
     if (cudaMalloc(&p->d_any_bad, sizeof(int)) != cudaSuccess) return destroy(fail(JBUGS_ERR_CUDA, "cudaMalloc failed"));
@@ -453,6 +479,8 @@ static void free_workspace(jbugs_plan* p) {
     cudaFree(p->d_partial2); p->d_partial2 = nullptr; p->partial2_bytes = 0;
     cudaFree(p->d_red); p->d_red = nullptr; p->red_bytes = 0;
     cudaFree(p->d_flags); p->d_flags = nullptr; p->flags_bytes = 0;
+    cudaFree(p->d_R); p->d_R = nullptr; p->R_bytes = 0;
+    cudaFree(p->d_Gp); p->d_Gp = nullptr; p->Gp_bytes = 0;
     p->cap_C = 0;
 }
 
@@ -517,6 +545,7 @@ extern "C" int jbugs_plan_upload_data(jbugs_plan* p, int slot, const void* src, 
     CU(cudaMemcpy(p->d_slots[slot], src, nbytes, cudaMemcpyDefault));
     p->uploaded[slot] = 1;
     // new observations: constants of the fused paths (and their validity check) must be redone
+    p->dense_const_dirty = true;
     if (!p->force_dynamic)
         for (size_t k = 0; k < p->rt.size(); ++k) {
             p->rt[k].variant = select_spec(p->rt[k].pp.sh, p->rt[k].pp.v.T);
@@ -635,6 +664,19 @@ static int ensure_workspace(jbugs_plan* p, long long C) {
         rows2 += (long long)REDUCE_R * (1 + r.pp.sh.n_gref);
     }
     int rc;
+    if (!p->dense.empty()) {
+        // dense predictor: one logp partial row per forward-GEMM row group; R and the split-K partials of X^T R
+        const jbugs_dense& dn = p->dense[0];
+        const long long col_blocks = (C + DG_BN - 1) / DG_BN;
+        const long long m_tiles = std::max<long long>(1, (dn.N + DG_BM - 1) / DG_BM);
+        p->dense_row_groups = (int)std::max<long long>(1, std::min<long long>(m_tiles, (2LL * p->num_sms + col_blocks - 1) / col_blocks));
+        const long long out_tiles = col_blocks * ((dn.P + DG_BM - 1) / DG_BM);
+        p->dense_splits = (int)std::max<long long>(1, std::min<long long>((dn.N + 4 * DG_BK - 1) / (4 * DG_BK), (2LL * p->num_sms + out_tiles - 1) / out_tiles));
+        p->dense_partial_offset = rows;
+        rows += p->dense_row_groups;
+        if ((rc = grow((void**)&p->d_R, &p->R_bytes, (size_t)std::max<long long>(dn.N, 1) * ldg * 8))) return rc;
+        if ((rc = grow((void**)&p->d_Gp, &p->Gp_bytes, (size_t)p->dense_splits * dn.P * ldg * 8))) return rc;
+    }
     if ((rc = grow((void**)&p->d_gvals, &p->gvals_bytes, (size_t)std::max(NG, 1) * ldg * 8))) return rc;
     if ((rc = grow((void**)&p->d_partial, &p->partial_bytes, (size_t)std::max<long long>(rows, 1) * ldg * 8))) return rc;
     if ((rc = grow((void**)&p->d_partial2, &p->partial2_bytes, (size_t)std::max<long long>(rows2, 1) * ldg * 8))) return rc;
@@ -683,6 +725,60 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         if (le != cudaSuccess) return fail(JBUGS_ERR_CUDA, "plate kernel launch failed: %s", cudaGetErrorString(le));
         p->launches++;
         reduce_plates.push_back((int)k);
+    }
+    if (!p->dense.empty()) {
+        if (p->comm && p->nranks > 1) return fail(JBUGS_ERR_UNSUPPORTED, "dense predictors are not observation-sharded yet");
+        const jbugs_dense& dn = p->dense[0];
+        const unsigned col_blocks = (unsigned)((C + DG_BN - 1) / DG_BN);
+        static bool opted = false;
+        if (!opted) {
+            CU(cudaFuncSetAttribute(dense_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM_BYTES));
+            CU(cudaFuncSetAttribute(dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM_BYTES));
+            opted = true;
+        }
+        const double* X = (const double*)p->d_slots[dn.x_slot];
+        DenseFwdParams fw{};
+        fw.op.A = X; fw.op.lda = dn.N;
+        fw.op.B = theta + dn.theta_base * ld; fw.op.ldb = dn.theta_stride * ld;
+        fw.op.M = dn.N; fw.op.N = C; fw.op.K = dn.P;
+        fw.y = (const double*)p->d_slots[dn.y_slot];
+        fw.n = dn.n_slot >= 0 ? (const double*)p->d_slots[dn.n_slot] : nullptr;
+        fw.R = p->d_R; fw.ldr = ldg;
+        fw.partial = p->d_partial + p->dense_partial_offset * ldg; fw.ldg = ldg;
+        fw.flags = p->d_flags;
+        dense_fwd_kernel<<<dim3(col_blocks, (unsigned)p->dense_row_groups), DG_THREADS, DG_SMEM_BYTES, st>>>(fw);
+        p->launches++;
+        const int k_fp = (int)p->rt.size();
+        fp.p[k_fp].n_tiles = p->dense_row_groups;
+        fp.p[k_fp].n_gref = 0;
+        fp.p[k_fp].offset = p->dense_partial_offset;
+        if (p->dense_const_dirty) {
+            // data-only normaliser of the binomial (0 for Bernoulli) + validation of the counts, once per upload
+            double h2[2] = {0.0, 0.0};
+            obs_const_kernel<<<1, 1024, 0, st>>>(dn.n_slot >= 0 ? FUSED_BINOMIAL_LOGIT : FUSED_BERNOULLI_LOGIT, fw.y, fw.n, 0,
+                                                 JBUGS_ARG_DATA_I, 1.0, dn.N, 1, 0, dn.N, p->d_red);
+            p->launches++;
+            CU(cudaMemcpyAsync(h2, p->d_red, sizeof h2, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (h2[1] != 0.0) return fail(JBUGS_ERR_UNSUPPORTED, "dense predictor: observations outside the support of the family");
+            p->dense_const = h2[0];
+            p->dense_const_dirty = false;
+        }
+        fp.p[k_fp].obs_const = p->dense_const;
+        fp.n_plates = k_fp + 1;
+        if (want_grad && grad) {
+            DenseBwdParams bw{};
+            bw.op.A = X; bw.op.lda = dn.N;
+            bw.op.B = p->d_R; bw.op.ldb = ldg;
+            bw.op.M = dn.P; bw.op.N = C; bw.op.K = dn.N;
+            bw.Gp = p->d_Gp; bw.ldg = ldg;
+            bw.k_per_split = ((dn.N + p->dense_splits - 1) / p->dense_splits + DG_BK - 1) / DG_BK * DG_BK;
+            dense_bwd_kernel<<<dim3(col_blocks, (unsigned)((dn.P + DG_BM - 1) / DG_BM), (unsigned)p->dense_splits), DG_THREADS, DG_SMEM_BYTES, st>>>(bw);
+            p->launches++;
+            dense_grad_reduce_kernel<<<dim3(chain_tiles, (unsigned)dn.P), BLOCK, 0, st>>>(p->d_Gp, p->dense_splits, dn.P, ldg, grad, ld,
+                                                                                       dn.theta_base, dn.theta_stride, C, 1);
+            p->launches++;
+        }
     }
     if (p->timing) CU(cudaEventRecord(p->ev[2], st));
     const double* partial_in = p->d_partial;

@@ -659,7 +659,9 @@ class Lowering:
         used_locals = set()
         for s in self.stmt_order:
             if s.kind == "obs":
-                self.plan.plates.append(self._build_plate(s, used_locals))
+                pl = self._build_plate(s, used_locals)
+                if pl is not None:
+                    self.plan.plates.append(pl)
         # parameter statements in loops that no observation plate consumed -> prior-only plates
         for s in self.stmt_order:
             if s.kind == "param" and not s.is_gq and s.loops and s.sid not in used_locals:
@@ -728,6 +730,9 @@ class Lowering:
             link.append(P.LINK_OF[eta.fn])
             eta = eta.args[0]
         plate.link = link[::-1] if link else []
+        if isinstance(eta, Call) and eta.fn == "inprod":
+            self._build_dense(s, fam, plate, eta, args, used_locals)
+            return None
         lin = self._linearize(eta, lv_names)
         # aux args
         aux = []
@@ -752,6 +757,65 @@ class Lowering:
             if not (c.kind == P.ARG_CONST and c.value == 0.0):
                 plate.terms.append(P.Term(P.Arg.const(1.0), c))
         return plate
+
+    # ---- dense linear predictor: inprod(X[i, 1:P], beta[1:P]) -> FP64 GEMMs over all chains -------------------
+    def _build_dense(self, s: Stmt, fam, plate: P.Plate, eta: Call, args, used_locals):
+        if len(s.loops) != 1 or plate.link != [P.OP_LOGISTIC] or fam not in (P.FAM_BERNOULLI, P.FAM_BINOMIAL):
+            raise LoweringError("inprod predictors are lowered for dbern/dbin with a logit link in a single loop")
+        i_name = s.loop_vars[0]
+        a, b = eta.args
+        if self._is_data(b, s.loop_vars) and not self._is_data(a, s.loop_vars):
+            a, b = b, a
+        ok = (isinstance(a, Index) and len(a.idx) == 2 and isinstance(a.idx[0], Var) and a.idx[0].name == i_name
+              and isinstance(a.idx[1], (Range, Colon)) and self._is_data(a, s.loop_vars)
+              and isinstance(b, Index) and len(b.idx) == 1 and isinstance(b.idx[0], (Range, Colon)))
+        if not ok:
+            raise LoweringError("inprod must have the form inprod(X[i, 1:P], beta[1:P]) with X data")
+        defs = [d for d in self._defs(b.name) if d.kind == "param"]
+        if len(defs) != 1 or len(defs[0].loops) != 1 or defs[0].is_gq:
+            raise LoweringError(f"'{b.name}' must be defined by one stochastic statement in a single loop")
+        d = defs[0]
+        if d.sid in used_locals:
+            raise LoweringError(f"'{b.name}' is a parent of more than one plate")
+        Pn = d.shape[0]
+        N = s.shape[0]
+        # X[i, lo:hi] for every i: N x P, column-major
+        lv = _grids(s.extents, s.loop_vars)
+        arr = self.data[a.name]
+        whole = (isinstance(arr, np.ndarray) and arr.shape == (N, Pn) and s.extents[0] == (1, N)
+                 and (isinstance(a.idx[1], Colon) or (self.de.ev(a.idx[1].lo, {}) == 1 and self.de.ev(a.idx[1].hi, {}) == Pn)))
+        if whole:
+            X = arr  # the whole matrix: no gather (17 GB at the BASELINE size)
+        else:
+            X = np.asarray(self.de.ev(Index(a.name, (Var(i_name), a.idx[1])), {i_name: lv[i_name].ravel()}), dtype=np.float64)
+        if X.shape != (N, Pn):
+            raise LoweringError(f"inprod: X slice is {X.shape}, expected {(N, Pn)}")
+        xf = X.ravel(order="F") if X.flags.f_contiguous else np.asfortranarray(X).ravel(order="F")
+        x_slot = self._slot(f"dense|{_show(a)}", xf, rank=2, dim0=N)
+        yv = np.broadcast_to(self.de.ev(s.node.lhs, lv), s.shape).astype(np.float64).ravel()
+        y_slot = self._slot(f"dense|y|{_show(s.node.lhs)}", yv)
+        n_slot = -1
+        if fam == P.FAM_BINOMIAL:
+            nv = np.broadcast_to(self.de.ev(args[1], lv), s.shape).astype(np.float64).ravel()
+            n_slot = self._slot(f"dense|n|{_show(args[1])}", nv)
+        tidx = self.theta_index(d)
+        base, si, _, idx_slot = _affine_or_index(tidx)
+        if idx_slot is not None:
+            raise LoweringError("the coefficient vector of a dense predictor needs an affine theta-slot map")
+        # the prior of beta: an ordinary prior-only plate over j
+        pfam = self._family(d.node.dist)
+        tr, lb, ub = self._transform_of(pfam, d.node.dist.args)
+        if tr != P.TR_IDENTITY:
+            raise LoweringError("coefficients of a dense predictor must live on the real line")
+        self._cur_extents = d.extents
+        pargs = [self._scalar_arg(x, d.loop_vars, d.shape, d.loop_vars) for x in d.node.dist.args]
+        self._cur_extents = s.extents
+        prior = P.Plate(N=Pn, T=1, has_obs=False, family=P.FAM_FLAT, name=f"{b.name}~{d.node.dist.fn} (prior)")
+        prior.locals.append(P.Local(b.name, P.LEVEL_GROUP, tr, base, si, 0, pfam, pargs, lb, ub, -1))
+        self.plan.plates.append(prior)
+        used_locals.add(d.sid)
+        self.plan.dense.append(P.Dense(N=N, P=Pn, theta_base=base, theta_stride=si, x_slot=x_slot, y_slot=y_slot,
+                                       n_slot=n_slot, family=fam, link=P.OP_LOGISTIC, name=plate.name))
 
     def _local_index(self, plate: P.Plate, obs: Stmt, ref, used_locals) -> int:
         _, name, idx = ref

@@ -56,10 +56,13 @@ PLATE_DT = np.dtype([("N", "<i8"), ("T", "<i8"), ("first_local", "<u4"), ("n_loc
 HEADER_DT = np.dtype([("magic", "S8"), ("version", "<u4"), ("flags", "<u4"), ("D", "<i8"),
                       ("n_globals", "<u4"), ("n_gtape", "<u4"), ("n_data", "<u4"),
                       ("n_plates", "<u4"), ("n_locals", "<u4"), ("n_terms", "<u4"),
-                      ("reserved", "<u8", (2,))])
+                      ("n_dense", "<u4"), ("reserved32", "<u4"), ("reserved", "<u8")])
+DENSE_DT = np.dtype([("N", "<i8"), ("P", "<i8"), ("theta_base", "<i8"), ("theta_stride", "<i8"),
+                     ("x_slot", "<i4"), ("y_slot", "<i4"), ("n_slot", "<i4"),
+                     ("family", "<u4"), ("link", "<u4"), ("pad", "<u4")])
 assert ARG_DT.itemsize == 16 and GLOBAL_DT.itemsize == 80 and GOP_DT.itemsize == 40
 assert DATA_DT.itemsize == 24 and LOCAL_DT.itemsize == 104 and TERM_DT.itemsize == 32
-assert PLATE_DT.itemsize == 128 and HEADER_DT.itemsize == 64
+assert PLATE_DT.itemsize == 128 and HEADER_DT.itemsize == 64 and DENSE_DT.itemsize == 56
 
 
 @dataclass(frozen=True)
@@ -159,6 +162,21 @@ class Plate:
 
 
 @dataclass
+class Dense:
+    """y[i] ~ dbern|dbin(logistic(inprod(X[i, 1:P], beta[1:P])) [, n[i]]) -- evaluated as FP64 GEMMs over all chains."""
+    N: int
+    P: int
+    theta_base: int
+    theta_stride: int
+    x_slot: int
+    y_slot: int
+    n_slot: int = -1
+    family: int = FAM_BERNOULLI
+    link: int = OP_LOGISTIC
+    name: str = ""
+
+
+@dataclass
 class Plan:
     D: int
     transformed: bool
@@ -166,6 +184,7 @@ class Plan:
     gtape: List[GOp] = field(default_factory=list)
     data: List[DataSlot] = field(default_factory=list)
     plates: List[Plate] = field(default_factory=list)
+    dense: List[Dense] = field(default_factory=list)
     param_names: Optional[List[str]] = None  # theta slot -> variable label (chain naming)
 
     @property
@@ -173,7 +192,7 @@ class Plan:
         return len(self.globals) + len(self.gtape)
 
     def n_obs(self):
-        return sum(p.N * p.T for p in self.plates if p.has_obs)
+        return sum(p.N * p.T for p in self.plates if p.has_obs) + sum(d.N for d in self.dense)
 
     # ------------------------------------------------------------------ serialisation
     def to_bytes(self) -> bytes:
@@ -211,8 +230,12 @@ class Plan:
                 it += 1
         h = np.zeros(1, HEADER_DT)
         h[0] = (MAGIC, VERSION, FLAG_TRANSFORMED if self.transformed else 0, self.D,
-                len(self.globals), len(self.gtape), len(self.data), len(self.plates), nl, nt, (0, 0))
-        return b"".join(x.tobytes() for x in (h, g, t, d, pl, loc, trm))
+                len(self.globals), len(self.gtape), len(self.data), len(self.plates), nl, nt,
+                len(self.dense), 0, 0)
+        dn = np.zeros(len(self.dense), DENSE_DT)
+        for k, x in enumerate(self.dense):
+            dn[k] = (x.N, x.P, x.theta_base, x.theta_stride, x.x_slot, x.y_slot, x.n_slot, x.family, x.link, 0)
+        return b"".join(x.tobytes() for x in (h, g, t, d, pl, loc, trm, dn))
 
     def describe(self) -> str:
         out = [f"plan D={self.D} transformed={self.transformed} globals={len(self.globals)} "

@@ -45,6 +45,7 @@ typedef struct jbo_plan {
     jbugs_plate* plates;
     jbugs_local* locals;
     jbugs_term* terms;
+    jbugs_dense* dense;
     const void** slots; /* borrowed pointers */
     int64_t* shard_i0;  /* per plate */
     int64_t* shard_i1;
@@ -226,7 +227,8 @@ jbo_plan* jbo_plan_create(const void* blob, size_t nbytes) {
     if (memcmp(p->h.magic, JBUGS_PLAN_MAGIC, 8) != 0 || p->h.version != JBUGS_PLAN_VERSION) { free(p); return NULL; }
     size_t need = sizeof(jbugs_plan_header) + p->h.n_globals * sizeof(jbugs_global) + p->h.n_gtape * sizeof(jbugs_gop) +
                   p->h.n_data * sizeof(jbugs_data_desc) + p->h.n_plates * sizeof(jbugs_plate) +
-                  p->h.n_locals * sizeof(jbugs_local) + p->h.n_terms * sizeof(jbugs_term);
+                  p->h.n_locals * sizeof(jbugs_local) + p->h.n_terms * sizeof(jbugs_term) +
+                  p->h.n_dense * sizeof(jbugs_dense);
     if (need != nbytes) { free(p); return NULL; }
     const char* c = (const char*)blob + sizeof(jbugs_plan_header);
 #define TAKE(field, type, n) \
@@ -237,6 +239,7 @@ jbo_plan* jbo_plan_create(const void* blob, size_t nbytes) {
     TAKE(plates, jbugs_plate, p->h.n_plates);
     TAKE(locals, jbugs_local, p->h.n_locals);
     TAKE(terms, jbugs_term, p->h.n_terms);
+    TAKE(dense, jbugs_dense, p->h.n_dense);
 #undef TAKE
     p->slots = (const void**)calloc(p->h.n_data + 1, sizeof(void*));
     p->shard_i0 = (int64_t*)calloc(p->h.n_plates + 1, sizeof(int64_t));
@@ -248,7 +251,7 @@ jbo_plan* jbo_plan_create(const void* blob, size_t nbytes) {
 
 void jbo_plan_destroy(jbo_plan* p) {
     if (!p) return;
-    free(p->globals); free(p->gtape); free(p->data); free(p->plates); free(p->locals); free(p->terms);
+    free(p->globals); free(p->gtape); free(p->data); free(p->plates); free(p->locals); free(p->terms); free(p->dense);
     free(p->slots); free(p->shard_i0); free(p->shard_i1); free(p);
 }
 
@@ -427,6 +430,29 @@ static int eval_chain(const jbo_plan* p, chain_io io, int want_grad, double* log
             if (want_grad)
                 for (int l = 0; l < nl; ++l)
                     if (L[l].level == JBUGS_LEVEL_GROUP) io.g[lslot[l] * io.sg] = ladj[l] * ldx[l] + ldlj[l];
+        }
+    }
+    /* dense predictors: eta_i = inprod(X[i, :], beta) (functions.jl:33-35), one logpdf node per observation */
+    for (uint32_t di = 0; di < p->h.n_dense; ++di) {
+        const jbugs_dense* dn = &p->dense[di];
+        const double* X = (const double*)p->slots[dn->x_slot];
+        const double* Y = (const double*)p->slots[dn->y_slot];
+        const double* Nn = dn->n_slot >= 0 ? (const double*)p->slots[dn->n_slot] : NULL;
+        for (int64_t i = 0; i < dn->N; ++i) {
+            double eta = 0.0;
+            for (int64_t j = 0; j < dn->P; ++j)
+                eta += X[i + dn->N * j] * io.th[(dn->theta_base + dn->theta_stride * j) * io.sth];
+            double v, dv, a[3] = {0, 0, 0}, da[3], lp, dx;
+            if (unary(dn->link, eta, &v, &dv)) return 1;
+            a[0] = v;
+            a[1] = Nn ? Nn[i] : 0.0;
+            if (fam_logpdf(dn->family, Y[i], a, &lp, &dx, da)) return 1;
+            logp += lp;
+            if (want_grad) {
+                const double deta = da[0] * dv;
+                for (int64_t j = 0; j < dn->P; ++j)
+                    io.g[(dn->theta_base + dn->theta_stride * j) * io.sg] += deta * X[i + dn->N * j];
+            }
         }
     }
     /* reverse sweep over the gtape, then through the bijectors of the globals */

@@ -175,3 +175,27 @@ def test_full_size_plate_properties():
     assert grad_err(gK[:5], g0 + k * (g1[:5] - g0)) < 1e-9
     lpo, go_, _ = _oracle(mK.plan).eval_batch(thK[:, :2])
     assert rel_err(lpK[:2], lpo) < TOL and grad_err(gK[:, :2], go_) < TOL
+
+
+@pytest.mark.parametrize("N,P,C,binomial", [(300, 7, 5, False), (3000, 70, 150, False), (1000, 33, 257, True)])
+def test_dense_logistic_gemm_path(N, P, C, binomial):
+    """BASELINE.json config 4 shape: inprod(X[i,1:P], beta[1:P]) as FP64 tensor-core GEMMs fused with dbern / dbin."""
+    rng = np.random.default_rng(N + P)
+    X = np.asfortranarray(rng.standard_normal((N, P)))
+    bt = rng.normal(0.0, 0.3, P)
+    pr = 1.0 / (1.0 + np.exp(-X @ bt))
+    data = {"N": N, "P": P, "X": X}
+    text = jbugs.examples.DENSE_LOGISTIC
+    if binomial:
+        n = rng.integers(1, 30, N).astype(float)
+        data.update(n=n, y=rng.binomial(n.astype(int), pr).astype(float))
+        text = text.replace("y[i] ~ dbern(p[i])", "y[i] ~ dbin(p[i], n[i])")
+    else:
+        data["y"] = (rng.random(N) < pr).astype(float)
+    m = jbugs.compile(text, data)
+    assert len(m.plan.dense) == 1 and m.plan.dense[0].P == P
+    th0 = np.concatenate([[0.5, 0.1], bt])
+    theta = random_thetas(th0, C, seed=3, scale=0.1)
+    co = _oracle(m.plan)
+    _check(m.cuda, co, theta)
+    _check(m.cuda, co, theta, layout="param_fast")
