@@ -671,7 +671,18 @@ static int ensure_workspace(jbugs_plan* p, long long C) {
         const long long m_tiles = std::max<long long>(1, (dn.N + DG_BM - 1) / DG_BM);
         p->dense_row_groups = (int)std::max<long long>(1, std::min<long long>(m_tiles, (2LL * p->num_sms + col_blocks - 1) / col_blocks));
         const long long out_tiles = col_blocks * ((dn.P + DG_BM - 1) / DG_BM);
-        p->dense_splits = (int)std::max<long long>(1, std::min<long long>((dn.N + 4 * DG_BK - 1) / (4 * DG_BK), (2LL * p->num_sms + out_tiles - 1) / out_tiles));
+        // split-K factor of the reverse GEMM: fill whole waves of one CTA per SM (wave quantisation costs up to 2x)
+        {
+            int best = 1;
+            double best_eff = 0.0;
+            for (int s = 1; s <= 96; ++s) {
+                if (s > 1 && dn.N / s < 8 * DG_BK) break;
+                const long long ctas = out_tiles * s, waves = (ctas + p->num_sms - 1) / p->num_sms;
+                const double eff = (double)ctas / (double)(waves * p->num_sms);
+                if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+            }
+            p->dense_splits = best;
+        }
         p->dense_partial_offset = rows;
         rows += p->dense_row_groups;
         if ((rc = grow((void**)&p->d_R, &p->R_bytes, (size_t)std::max<long long>(dn.N, 1) * ldg * 8))) return rc;
@@ -741,6 +752,8 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         fw.op.A = X; fw.op.lda = dn.N;
         fw.op.B = theta + dn.theta_base * ld; fw.op.ldb = dn.theta_stride * ld;
         fw.op.M = dn.N; fw.op.N = C; fw.op.K = dn.P;
+        const bool x_vec = ((uintptr_t)X % 16 == 0) && (dn.N % 2 == 0);
+        fw.op.vec_ok = x_vec && ((uintptr_t)theta % 16 == 0) && (ld % 2 == 0);
         fw.y = (const double*)p->d_slots[dn.y_slot];
         fw.n = dn.n_slot >= 0 ? (const double*)p->d_slots[dn.n_slot] : nullptr;
         fw.R = p->d_R; fw.ldr = ldg;
@@ -771,6 +784,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
             bw.op.A = X; bw.op.lda = dn.N;
             bw.op.B = p->d_R; bw.op.ldb = ldg;
             bw.op.M = dn.P; bw.op.N = C; bw.op.K = dn.N;
+            bw.op.vec_ok = x_vec;
             bw.Gp = p->d_Gp; bw.ldg = ldg;
             bw.k_per_split = ((dn.N + p->dense_splits - 1) / p->dense_splits + DG_BK - 1) / DG_BK * DG_BK;
             dense_bwd_kernel<<<dim3(col_blocks, (unsigned)((dn.P + DG_BM - 1) / DG_BM), (unsigned)p->dense_splits), DG_THREADS, DG_SMEM_BYTES, st>>>(bw);

@@ -11,22 +11,25 @@
 //   reverse  : G[P x C]  = X^T[P x N] * R[N x C]         split-K over the observations, partials added in a fixed order
 //
 // Both products run on the FP64 tensor cores with `mma.sync.aligned.m8n8k4.row.col.f64` (the sm_100a DMMA path;
-// tcgen05 has no FP64 kind).  CTA tile 128 x 128 x 16, 8 warps (2 x 4), warp tile 64 x 32 = 8 x 4 MMA tiles, three
-// cp.async stages.  Shared-memory rows are padded to a stride == 4 (mod 16) doubles so that the 64-bit fragment
-// loads of a half-warp hit 16 distinct bank pairs.
+// tcgen05 has no FP64 kind).  CTA tile 128 x 128 x 16, 16 warps (4 x 4), warp tile 32 x 32 = 4 x 4 MMA tiles (four
+// warps per scheduler hide the DMMA issue cadence), three cp.async stages.  Shared-memory rows are padded to a stride
+// == 4 (mod 16) doubles so that the 64-bit fragment loads of a half-warp hit 16 distinct bank pairs.  Interior tiles
+// use unpredicated 16-byte cp.async with per-thread pointers that are only incremented in the k loop; edge tiles and
+// unaligned operands take a predicated 8-byte zero-filling path.
 #pragma once
 
 #include "jbugs_kernels.cuh"
 
 namespace jbugs {
 
-constexpr int DG_BM = 128, DG_BN = 128, DG_BK = 16, DG_STAGES = 3, DG_THREADS = 256;
+constexpr int DG_BM = 128, DG_BN = 128, DG_BK = 16, DG_STAGES = 3, DG_THREADS = 512;
 constexpr int DG_LDB = DG_BN + 4;   // Bs[k][n]
 constexpr int DG_LDA_M = DG_BM + 4; // As[k][m]   (A is M-major in memory: forward GEMM)
 constexpr int DG_LDA_K = DG_BK + 4; // As[m][k]   (A is K-major in memory: reverse GEMM)
 constexpr int DG_A_DOUBLES = (DG_BK * DG_LDA_M > DG_BM * DG_LDA_K) ? DG_BK * DG_LDA_M : DG_BM * DG_LDA_K;
 constexpr int DG_STAGE_DOUBLES = DG_A_DOUBLES + DG_BK * DG_LDB;
 constexpr size_t DG_SMEM_BYTES = (size_t)DG_STAGES * DG_STAGE_DOUBLES * sizeof(double);
+constexpr int DG_TM = 4, DG_TN = 4;  // MMA tiles per warp
 
 __device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -34,86 +37,129 @@ __device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
-// 8-byte cp.async with zero fill when `ok` is false
-__device__ __forceinline__ void cp_async8_zfill(double* smem_dst, const double* gmem_src, bool ok) {
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int bytes = ok ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gmem_src), "r"(bytes) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
 struct DenseOperands {
     const double* A;  // X
     long long lda;    // number of observations (leading dimension of the column-major X)
-    const double* B;  // forward: theta + beta_base*ld (row j at j*ldb_rows); reverse: R
+    const double* B;  // forward: theta + beta_base*ld (row j at j*ldb); reverse: R
     long long ldb;    // elements between consecutive k rows of B
     long long M, N, K;
+    int vec_ok;       // operands are 16-byte aligned with even leading dimensions
 };
 
-// load one BK-slab of A and B into a stage.  A_MMAJOR: A(m,k) = A[m + lda*k]; else A(m,k) = A[k + lda*m]
+// ---- edge path: one BK-slab, 8-byte elements, bounds-checked, zero fill ---------------------------------------------
+// A_MMAJOR: A(m,k) = A[m + lda*k]; else A(m,k) = A[k + lda*m]
 template <bool A_MMAJOR>
-__device__ __forceinline__ void dg_load_stage(const DenseOperands& op, double* stage, long long m0, long long n0,
-                                              long long k0, int tid) {
+__device__ __forceinline__ void dg_load_stage_edge(const DenseOperands& op, double* stage, long long m0, long long n0,
+                                                   long long k0, long long k_end, int tid) {
     double* As = stage;
     double* Bs = stage + DG_A_DOUBLES;
-    if (A_MMAJOR) {
-        // As[kk][m]: consecutive threads walk m (contiguous in memory)
-        for (int q = tid; q < DG_BK * DG_BM; q += DG_THREADS) {
-            const int kk = q / DG_BM, m = q % DG_BM;
-            const bool ok = (m0 + m < op.M) && (k0 + kk < op.K);
-            cp_async8_zfill(As + kk * DG_LDA_M + m, op.A + (ok ? (m0 + m) + op.lda * (k0 + kk) : 0), ok);
-        }
-    } else {
-        // As[m][kk]: consecutive threads walk kk (contiguous in memory)
-        for (int q = tid; q < DG_BK * DG_BM; q += DG_THREADS) {
-            const int m = q / DG_BK, kk = q % DG_BK;
-            const bool ok = (m0 + m < op.M) && (k0 + kk < op.K);
-            cp_async8_zfill(As + m * DG_LDA_K + kk, op.A + (ok ? (k0 + kk) + op.lda * (m0 + m) : 0), ok);
-        }
+    for (int q = tid; q < DG_BK * DG_BM; q += DG_THREADS) {
+        const int kk = A_MMAJOR ? q / DG_BM : q % DG_BK;
+        const int m = A_MMAJOR ? q % DG_BM : q / DG_BK;
+        double* dst = A_MMAJOR ? As + kk * DG_LDA_M + m : As + m * DG_LDA_K + kk;
+        const bool ok = (m0 + m < op.M) && (k0 + kk < k_end);
+        if (ok) cp_async8(dst, A_MMAJOR ? op.A + (m0 + m) + op.lda * (k0 + kk) : op.A + (k0 + kk) + op.lda * (m0 + m));
+        else *dst = 0.0;
     }
     for (int q = tid; q < DG_BK * DG_BN; q += DG_THREADS) {
         const int kk = q / DG_BN, n = q % DG_BN;
-        const bool ok = (n0 + n < op.N) && (k0 + kk < op.K);
-        cp_async8_zfill(Bs + kk * DG_LDB + n, op.B + (ok ? (k0 + kk) * op.ldb + (n0 + n) : 0), ok);
+        const bool ok = (n0 + n < op.N) && (k0 + kk < k_end);
+        if (ok) cp_async8(Bs + kk * DG_LDB + n, op.B + (k0 + kk) * op.ldb + (n0 + n));
+        else Bs[kk * DG_LDB + n] = 0.0;
+    }
+}
+
+// ---- interior path: per-thread source pointers / shared offsets, two 16-byte chunks of A and two of B per slab ----------
+struct DgFastPtrs {
+    const double* a[2];
+    const double* b[2];
+    int sa[2], sb[2];  // offsets (doubles) inside a stage
+    long long a_step, b_step;
+};
+
+template <bool A_MMAJOR>
+__device__ __forceinline__ DgFastPtrs dg_fast_init(const DenseOperands& op, long long m0, long long n0, long long k0, int tid) {
+    DgFastPtrs f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int q = tid + h * DG_THREADS;  // 1024 chunks of 2 doubles per operand
+        if (A_MMAJOR) {
+            const int kk = q / (DG_BM / 2), m = (q % (DG_BM / 2)) * 2;
+            f.a[h] = op.A + (m0 + m) + op.lda * (k0 + kk);
+            f.sa[h] = kk * DG_LDA_M + m;
+        } else {
+            const int m = q / (DG_BK / 2), kk = (q % (DG_BK / 2)) * 2;
+            f.a[h] = op.A + (k0 + kk) + op.lda * (m0 + m);
+            f.sa[h] = m * DG_LDA_K + kk;
+        }
+        const int kb = q / (DG_BN / 2), n = (q % (DG_BN / 2)) * 2;
+        f.b[h] = op.B + (k0 + kb) * op.ldb + (n0 + n);
+        f.sb[h] = DG_A_DOUBLES + kb * DG_LDB + n;
+    }
+    f.a_step = A_MMAJOR ? op.lda * DG_BK : DG_BK;
+    f.b_step = op.ldb * DG_BK;
+    return f;
+}
+
+__device__ __forceinline__ void dg_fast_load(DgFastPtrs& f, double* stage) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        cp_async16(stage + f.sa[h], f.a[h]);
+        cp_async16(stage + f.sb[h], f.b[h]);
+        f.a[h] += f.a_step;
+        f.b[h] += f.b_step;
     }
 }
 
 // acc[tm][tn][2] += A_tile * B_tile over k in [k_begin, k_end)
 template <bool A_MMAJOR>
 __device__ __forceinline__ void dg_mainloop(const DenseOperands& op, double* smem, long long m0, long long n0,
-                                            long long k_begin, long long k_end, double (&acc)[8][4][2]) {
+                                            long long k_begin, long long k_end, double (&acc)[DG_TM][DG_TN][2]) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+    const int wm = warp >> 2, wn = warp & 3;  // 4 x 4 warps
     const int fr = lane >> 2, fk = lane & 3;  // fragment row / k index
     const long long nk = (k_end - k_begin + DG_BK - 1) / DG_BK;
-    // prologue: stages 0 .. STAGES-2
+    // interior tile with aligned operands: every slab but a ragged last one goes through the fast loader
+    const bool interior = op.vec_ok && (m0 + DG_BM <= op.M) && (n0 + DG_BN <= op.N) && (((k_begin & 1) == 0) || A_MMAJOR);
+    const long long nk_fast = interior ? (k_end - k_begin) / DG_BK : 0;
+    DgFastPtrs fp = dg_fast_init<A_MMAJOR>(op, m0, n0, k_begin, tid);
+    auto load = [&](long long slab) {
+        double* stage = smem + (slab % DG_STAGES) * DG_STAGE_DOUBLES;
+        if (slab < nk_fast) dg_fast_load(fp, stage);
+        else dg_load_stage_edge<A_MMAJOR>(op, stage, m0, n0, k_begin + slab * DG_BK, k_end, tid);
+    };
     for (int s = 0; s < DG_STAGES - 1; ++s) {
-        if (s < nk) dg_load_stage<A_MMAJOR>(op, smem + s * DG_STAGE_DOUBLES, m0, n0, k_begin + (long long)s * DG_BK, tid);
+        if (s < nk) load(s);
         cp_async_commit();
     }
     for (long long kt = 0; kt < nk; ++kt) {
         cp_async_wait_1();
         __syncthreads();
-        // prefetch slab kt + STAGES - 1 into the stage consumed at iteration kt - 1
-        const long long pf = kt + DG_STAGES - 1;
-        if (pf < nk) dg_load_stage<A_MMAJOR>(op, smem + (pf % DG_STAGES) * DG_STAGE_DOUBLES, m0, n0, k_begin + pf * DG_BK, tid);
+        const long long pf = kt + DG_STAGES - 1;  // refill the stage consumed at iteration kt - 1
+        if (pf < nk) load(pf);
         cp_async_commit();
         const double* As = smem + (kt % DG_STAGES) * DG_STAGE_DOUBLES;
         const double* Bs = As + DG_A_DOUBLES;
 #pragma unroll
         for (int ks = 0; ks < DG_BK / 4; ++ks) {
-            double a[8], b[4];
+            double a[DG_TM], b[DG_TN];
 #pragma unroll
-            for (int tm = 0; tm < 8; ++tm) {
-                const int m = wm * 64 + tm * 8 + fr, k = ks * 4 + fk;
+            for (int tm = 0; tm < DG_TM; ++tm) {
+                const int m = wm * 32 + tm * 8 + fr, k = ks * 4 + fk;
                 a[tm] = A_MMAJOR ? As[k * DG_LDA_M + m] : As[m * DG_LDA_K + k];
             }
 #pragma unroll
-            for (int tn = 0; tn < 4; ++tn) b[tn] = Bs[(ks * 4 + fk) * DG_LDB + wn * 32 + tn * 8 + fr];
+            for (int tn = 0; tn < DG_TN; ++tn) b[tn] = Bs[(ks * 4 + fk) * DG_LDB + wn * 32 + tn * 8 + fr];
 #pragma unroll
-            for (int tm = 0; tm < 8; ++tm)
+            for (int tm = 0; tm < DG_TM; ++tm)
 #pragma unroll
-                for (int tn = 0; tn < 4; ++tn) dmma(acc[tm][tn], a[tm], b[tn]);
+                for (int tn = 0; tn < DG_TN; ++tn) dmma(acc[tm][tn], a[tm], b[tn]);
         }
     }
     cp_async_wait_all();
@@ -137,32 +183,32 @@ struct DenseFwdParams {
 __global__ void __launch_bounds__(DG_THREADS, 1)
 dense_fwd_kernel(const __grid_constant__ DenseFwdParams P) {
     extern __shared__ double smem[];
-    __shared__ double red[2][DG_BN];
+    __shared__ double red[4][DG_BN];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3, fr = lane >> 2, fk = lane & 3;
     const long long n0 = (long long)blockIdx.x * DG_BN;
     const long long m_tiles = (P.op.M + DG_BM - 1) / DG_BM;
-    double lp[4][2];  // per-thread log-density sums for its 4 x 2 chain columns
+    double lp[DG_TN][2];  // per-thread log-density sums for its 4 x 2 chain columns
 #pragma unroll
-    for (int tn = 0; tn < 4; ++tn) lp[tn][0] = lp[tn][1] = 0.0;
+    for (int tn = 0; tn < DG_TN; ++tn) lp[tn][0] = lp[tn][1] = 0.0;
     for (long long mt = blockIdx.y; mt < m_tiles; mt += gridDim.y) {
         const long long m0 = mt * DG_BM;
-        double acc[8][4][2];
+        double acc[DG_TM][DG_TN][2];
 #pragma unroll
-        for (int tm = 0; tm < 8; ++tm)
+        for (int tm = 0; tm < DG_TM; ++tm)
 #pragma unroll
-            for (int tn = 0; tn < 4; ++tn) acc[tm][tn][0] = acc[tm][tn][1] = 0.0;
+            for (int tn = 0; tn < DG_TN; ++tn) acc[tm][tn][0] = acc[tm][tn][1] = 0.0;
         dg_mainloop<true>(P.op, smem, m0, n0, 0, P.op.K, acc);
         // epilogue: C fragment element (row = fr, col = 2*fk + {0,1}) of MMA tile (tm, tn)
 #pragma unroll
-        for (int tm = 0; tm < 8; ++tm) {
-            const long long i = m0 + wm * 64 + tm * 8 + fr;
+        for (int tm = 0; tm < DG_TM; ++tm) {
+            const long long i = m0 + wm * 32 + tm * 8 + fr;
             const bool row_ok = i < P.op.M;
             const double yv = row_ok ? __ldg(P.y + i) : 0.0;
             const double nv = row_ok ? (P.n ? __ldg(P.n + i) : 1.0) : 0.0;
             const double mv = nv - yv;
 #pragma unroll
-            for (int tn = 0; tn < 4; ++tn) {
+            for (int tn = 0; tn < DG_TN; ++tn) {
                 double r2[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -188,9 +234,9 @@ dense_fwd_kernel(const __grid_constant__ DenseFwdParams P) {
             }
         }
     }
-    // fixed-order reduction of lp over the 8 fragment rows (shuffles), then over the two M-warps (shared memory)
+    // fixed-order reduction of lp over the 8 fragment rows (shuffles), then over the four M-warps (shared memory)
 #pragma unroll
-    for (int tn = 0; tn < 4; ++tn)
+    for (int tn = 0; tn < DG_TN; ++tn)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             double v = lp[tn][e];
@@ -202,7 +248,7 @@ dense_fwd_kernel(const __grid_constant__ DenseFwdParams P) {
     __syncthreads();
     if (tid < DG_BN) {
         const long long c = n0 + tid;
-        if (c < P.op.N) P.partial[(long long)blockIdx.y * P.ldg + c] = red[0][tid] + red[1][tid];
+        if (c < P.op.N) P.partial[(long long)blockIdx.y * P.ldg + c] = ((red[0][tid] + red[1][tid]) + red[2][tid]) + red[3][tid];
     }
 }
 
@@ -223,19 +269,19 @@ dense_bwd_kernel(const __grid_constant__ DenseBwdParams P) {
     const long long n0 = (long long)blockIdx.x * DG_BN, m0 = (long long)blockIdx.y * DG_BM;
     const long long kb = (long long)blockIdx.z * P.k_per_split;
     const long long ke = kb + P.k_per_split < P.op.K ? kb + P.k_per_split : P.op.K;
-    double acc[8][4][2];
+    double acc[DG_TM][DG_TN][2];
 #pragma unroll
-    for (int tm = 0; tm < 8; ++tm)
+    for (int tm = 0; tm < DG_TM; ++tm)
 #pragma unroll
-        for (int tn = 0; tn < 4; ++tn) acc[tm][tn][0] = acc[tm][tn][1] = 0.0;
+        for (int tn = 0; tn < DG_TN; ++tn) acc[tm][tn][0] = acc[tm][tn][1] = 0.0;
     if (kb < ke) dg_mainloop<false>(P.op, smem, m0, n0, kb, ke, acc);
     double* out = P.Gp + (long long)blockIdx.z * P.op.M * P.ldg;
 #pragma unroll
-    for (int tm = 0; tm < 8; ++tm) {
-        const long long p = m0 + wm * 64 + tm * 8 + fr;
+    for (int tm = 0; tm < DG_TM; ++tm) {
+        const long long p = m0 + wm * 32 + tm * 8 + fr;
         if (p >= P.op.M) continue;
 #pragma unroll
-        for (int tn = 0; tn < 4; ++tn) {
+        for (int tn = 0; tn < DG_TN; ++tn) {
             const long long c = n0 + wn * 32 + tn * 8 + 2 * fk;
             if (c + 1 < P.op.N) *reinterpret_cast<double2*>(out + p * P.ldg + c) = make_double2(acc[tm][tn][0], acc[tm][tn][1]);
             else if (c < P.op.N) out[p * P.ldg + c] = acc[tm][tn][0];
