@@ -214,9 +214,8 @@ dense_fwd_kernel(const __grid_constant__ DenseFwdParams P) {
                 for (int e = 0; e < 2; ++e) {
                     const double eta = acc[tm][tn][e];
                     const double ax = fabs(eta);
-                    const double ex = exp(-ax);
-                    const double l1p = log1p(ex);
-                    const double inv = 1.0 / (1.0 + ex);
+                    const SoftplusParts sp3 = softplus_parts(ax);
+                    const double ex = sp3.e, l1p = sp3.l1p, inv = sp3.inv;
                     const double p = eta >= 0.0 ? inv : ex * inv;
                     const double lsp = -((eta >= 0.0 ? 0.0 : ax) + l1p);
                     const double lsq = -((eta >= 0.0 ? ax : 0.0) + l1p);

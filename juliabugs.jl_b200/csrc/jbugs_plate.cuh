@@ -129,9 +129,8 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
         // The data-only constant -logbeta(k+1, n-k+1) - log(n+1) is added once per plate (obs_const).
         const double n = S::FUSED == FUSED_BERNOULLI_LOGIT ? 1.0 : arg_value(sp.aux(1), V.aux[1], st, sv, g, j);
         const double ax = fabs(eta);
-        const double e = exp(-ax);
-        const double l1p = log1p(e);
-        const double inv = 1.0 / (1.0 + e);
+        const SoftplusParts sp3 = softplus_parts(ax);
+        const double e = sp3.e, l1p = sp3.l1p, inv = sp3.inv;
         const double p = eta >= 0.0 ? inv : e * inv;                 // logistic(eta)
         const double lsp = -((eta >= 0.0 ? 0.0 : ax) + l1p);          // log p
         const double lsq = -((eta >= 0.0 ? ax : 0.0) + l1p);          // log(1 - p)
