@@ -105,6 +105,7 @@ struct DynSpec {
     static constexpr int UNROLL = 1;
     static constexpr int MIN_BLOCKS = 2;
     static constexpr int T_STATIC = 0;  // inner extent read at run time
+    static constexpr bool PREFETCH = false;
     __device__ __forceinline__ bool prior_fused(int) const { return false; }
     const PlateShape& s;
     __device__ __forceinline__ explicit DynSpec(const PlateShape& sh) : s(sh) {}
@@ -139,6 +140,7 @@ struct StaticSpec {
     static constexpr int UNROLL = Desc::UNROLL;
     static constexpr int MIN_BLOCKS = Desc::MIN_BLOCKS;
     static constexpr int T_STATIC = Desc::T_STATIC;  // > 0: inner loop fully unrolled
+    static constexpr bool PREFETCH = Desc::PREFETCH; // theta loads of the next U-block issued before this one is evaluated
     // a dnorm prior whose arguments do not vary over the plate keeps sufficient statistics
     __device__ __forceinline__ constexpr bool prior_fused(int l) const {
         return Desc::sh().loc[l].family == JBUGS_FAM_NORMAL &&

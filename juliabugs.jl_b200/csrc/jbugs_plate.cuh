@@ -177,29 +177,42 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
     return bad;
 }
 
-// UU consecutive groups starting at chunk-local index g (global group index i): loads first, then math
-template <class S, int UU>
-__device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, const StageView& sv, int g, long long i,
-                                            int T, const double* __restrict__ th, double* __restrict__ gr,
-                                            long long ld, bool store, double obs_tau, long long (&pos)[MAX_LOC],
-                                            ChainState& st, FusedAcc& fa, double& lp) {
-    bool bad = false;
+// raw theta values (and row offsets) of the group-level locals of UU consecutive groups
+template <int UU>
+struct GroupLoads {
     double raw[UU][MAX_LOC];
     long long off[UU][MAX_LOC];  // element offset of the slot's row: slot * ld
-    // `pos[l]` walks the affine slot map incrementally (row0 + step_i * i [+ step_j * j], in elements)
+};
+
+// issue the theta loads of groups i .. i+UU-1.  `pos[l]` walks the affine slot map incrementally
+// (row0 + step_i * i, in elements), so calls must come in ascending group order.
+template <class S, int UU>
+__device__ __forceinline__ void load_groups(const S& sp, const PlateVals& V, long long i, const double* __restrict__ th,
+                                            long long ld, long long (&pos)[MAX_LOC], GroupLoads<UU>& gl) {
 #pragma unroll
     for (int u = 0; u < UU; ++u)
 #pragma unroll
         for (int l = 0; l < MAX_LOC; ++l)
             if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) {
                 if (sp.loc_has_idx(l)) {
-                    off[u][l] = local_slot(sp, V, l, i + u, 0) * ld;
+                    gl.off[u][l] = local_slot(sp, V, l, i + u, 0) * ld;
                 } else {
-                    off[u][l] = pos[l];
+                    gl.off[u][l] = pos[l];
                     pos[l] += V.loc[l].step_i;
                 }
-                raw[u][l] = th[off[u][l]];
+                gl.raw[u][l] = th[gl.off[u][l]];
             }
+}
+
+// UU consecutive groups starting at chunk-local index g (global group index i), theta already loaded
+template <class S, int UU>
+__device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, const StageView& sv, int g, long long i,
+                                            int T, const double* __restrict__ th, double* __restrict__ gr,
+                                            long long ld, bool store, double obs_tau, long long (&pos)[MAX_LOC],
+                                            const GroupLoads<UU>& gl, ChainState& st, FusedAcc& fa, double& lp) {
+    bool bad = false;
+    const double (&raw)[UU][MAX_LOC] = gl.raw;
+    const long long (&off)[UU][MAX_LOC] = gl.off;
 #pragma unroll
     for (int u = 0; u < UU; ++u) {
         double ldx[MAX_LOC], ldlj[MAX_LOC], sl[MAX_LOC];
@@ -320,6 +333,8 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
     __syncthreads();
 
     int cur = 0;
+    GroupLoads<U> gl_cur;
+    bool have_cur = false;
     for (long long i0 = ib; i0 < ie; i0 += STAGE_G) {
         const long long rem = ie - i0;
         const int cnt = rem < STAGE_G ? (int)rem : STAGE_G;
@@ -332,11 +347,29 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
         sv.chunk = stage0 + cur * stage_doubles;
         sv.jreg = jreg;
         int g = 0;
-        for (; g + U <= cnt; g += U)
-            bad |= eval_groups<S, U>(sp, V, sv, g, i0 + g, T, th, gr, ld, store, obs_tau, pos, st, fa, lp);
+        for (; g + U <= cnt; g += U) {
+            const long long i = i0 + g;
+            if (S::PREFETCH) {
+                // software pipeline over U-blocks (also across staged chunks: the theta rows do not depend on the
+                // staged data): the loads of block i+U are in flight while block i is evaluated
+                if (!have_cur) load_groups<S, U>(sp, V, i, th, ld, pos, gl_cur);
+                GroupLoads<U> gl_nxt;
+                const bool more = i + 2 * U <= ie;
+                if (more) load_groups<S, U>(sp, V, i + U, th, ld, pos, gl_nxt);
+                bad |= eval_groups<S, U>(sp, V, sv, g, i, T, th, gr, ld, store, obs_tau, pos, gl_cur, st, fa, lp);
+                if (more) gl_cur = gl_nxt;
+                have_cur = more;
+            } else {
+                load_groups<S, U>(sp, V, i, th, ld, pos, gl_cur);
+                bad |= eval_groups<S, U>(sp, V, sv, g, i, T, th, gr, ld, store, obs_tau, pos, gl_cur, st, fa, lp);
+            }
+        }
         if (U > 1)
-            for (; g < cnt; ++g)
-                bad |= eval_groups<S, 1>(sp, V, sv, g, i0 + g, T, th, gr, ld, store, obs_tau, pos, st, fa, lp);
+            for (; g < cnt; ++g) {
+                GroupLoads<1> one;
+                load_groups<S, 1>(sp, V, i0 + g, th, ld, pos, one);
+                bad |= eval_groups<S, 1>(sp, V, sv, g, i0 + g, T, th, gr, ld, store, obs_tau, pos, one, st, fa, lp);
+            }
         cp_async_wait_all();
         __syncthreads();
         cur ^= 1;
