@@ -136,6 +136,11 @@ struct jbugs_plan_s {
     int force_dynamic = 0;
     long long tile_override = 0;
     long long host_chunk = 0;  // chains per pipelined chunk of the host path (0 = automatic)
+    // stage plate data with cp.async.bulk + mbarrier (TMA) instead of cp.async.  Off by default: measured on B200
+    // (rats 10^6 x 5 x 4096) the two-stage TMA ring is 27.8 ms against 20.3 ms for cp.async -- the ~1.5 us
+    // issue-to-complete latency of a tiny bulk copy is longer than one 32-group chunk of compute, and the data
+    // streams are < 1 % of the traffic anyway.  `jbugs_plan_set_option(plan, "tma", 1)` selects the TMA kernels.
+    int use_tma = 0;
     long long launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_plate_ms = 0.f, last_total_ms = 0.f;
@@ -311,6 +316,11 @@ static int build_plate(jbugs_plan* p, int k) {
     V.i0 = p->shard_i0[k]; V.i1 = p->shard_i1[k];
     V.per_group = sb.chunk_acc;
     V.j_doubles = (sb.j_acc + 1) / 2 * 2;
+    // TMA staging needs 16-byte aligned sources: slot bases are cudaMalloc'ed, so element offsets must be even --
+    // the kernel checks the chunk start and length, here: the column stride N of rank-2 streams
+    V.bulk_ok = p->use_tma ? 1 : 0;
+    for (int q = 0; q < V.n_streams; ++q)
+        if (V.streams[q].kind == JBUGS_ARG_DATA_IJ && (pl.N % 2) != 0) V.bulk_ok = 0;
     r.smem_bytes = (size_t)(V.j_doubles + 2 * V.per_group * STAGE_G) * sizeof(double);
     if (r.smem_bytes > 200 * 1024)
         return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: %zu bytes of staged data per chunk exceed shared memory (inner extent too large)", k, r.smem_bytes);
@@ -578,6 +588,10 @@ extern "C" int jbugs_plan_set_option(jbugs_plan* p, const char* key, int64_t val
         p->tile_override = value;
         p->cap_C = 0;
         return JBUGS_OK;
+    }
+    if (!strcmp(key, "tma")) {
+        p->use_tma = value != 0;
+        return rebuild_plates(p);
     }
     if (!strcmp(key, "host_chunk")) {
         if (value < 0) return fail(JBUGS_ERR_INVALID, "host_chunk must be >= 0");

@@ -88,7 +88,7 @@ struct PlateVals {
     int n_streams;     // staged data streams
     int per_group;     // doubles per group in a staged chunk (I streams: 1, IJ streams: T)
     int j_doubles;     // size of the J region (J streams: T each), rounded up to even
-    int pad;
+    int bulk_ok;       // streams are 16-byte aligned for every even group index: chunks may use the TMA path
     Stream streams[MAX_STREAMS];
 };
 

@@ -1,4 +1,4 @@
-// jbugs_launch.cuh -- launcher template for plate_kernel<S, BLK>; included only by the spec_*.cu translation
+// jbugs_launch.cuh -- launcher template for plate_kernel<S, BLK, TMA>; included only by the spec_*.cu translation
 // units, each of which instantiates it for its own specs (so the kernels compile in parallel).
 #pragma once
 
@@ -6,26 +6,17 @@
 
 namespace jbugs {
 
-template <class S, int BLK>
+template <class S, int BLK, bool TMA>
 static cudaError_t launch_plate_blk(JBUGS_LAUNCH_PARAMS) {
     static size_t opted_in = 48 * 1024;  // dynamic shared memory above 48 KB needs an opt-in per kernel
     if (smem > opted_in) {
-        cudaError_t e = cudaFuncSetAttribute(plate_kernel<S, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(plate_kernel<S, BLK, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         opted_in = smem;
     }
     dim3 grid((unsigned)((C + BLK - 1) / BLK), (unsigned)n_tiles);
-    plate_kernel<S, BLK><<<grid, BLK, smem, st>>>(pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
+    plate_kernel<S, BLK, TMA><<<grid, BLK, smem, st>>>(pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
     return cudaGetLastError();
-}
-
-template <class S>
-static cudaError_t launch_plate_t(JBUGS_LAUNCH_PARAMS) {
-    switch (plate_block(C)) {
-    case 32: return launch_plate_blk<S, 32>(JBUGS_LAUNCH_ARGS);
-    case 64: return launch_plate_blk<S, 64>(JBUGS_LAUNCH_ARGS);
-    default: return launch_plate_blk<S, 128>(JBUGS_LAUNCH_ARGS);
-    }
 }
 
 }  // namespace jbugs

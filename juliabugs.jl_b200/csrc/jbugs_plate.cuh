@@ -29,9 +29,57 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_s
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// copy the streams of groups [i, i + cnt) into one stage
-template <int BLK>
-__device__ __forceinline__ void stage_chunk(const PlateVals& V, double* dst, long long i, int cnt, int T, int tid) {
+// ---- TMA (bulk async copy) + mbarrier: the staging path for 16-byte aligned chunks -------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+// global -> shared bulk copy (the 1-D TMA path, SASS UBLKCP); completion is signalled on the mbarrier as transaction bytes
+__device__ __forceinline__ void bulk_g2s(double* smem_dst, const double* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+// copy the streams of groups [i, i + cnt) into one stage.  Returns true when the chunk went through the TMA path
+// (then `bar` completes when the bytes have landed); otherwise every thread issued its share with cp.async.
+template <int BLK, bool TMA>
+__device__ __forceinline__ bool stage_chunk(const PlateVals& V, double* dst, long long i, int cnt, int T, int tid,
+                                            unsigned long long* bar) {
+    // warp 0 drives the copy engine when source, destination and size are 16-byte multiples
+    if (TMA && V.bulk_ok && V.per_group > 0 && ((i & 1) == 0) && ((cnt & 1) == 0)) {
+        if (tid < 32) {
+            // warp 0 issues the copies lane-parallel (copy q = one row of `cnt` doubles: a DATA_I stream has one row,
+            // a DATA_IJ stream T rows), so that no single thread is held up by the whole list
+            const unsigned row_bytes = (unsigned)cnt * 8u;
+            if (tid == 0) mbar_expect_tx(bar, row_bytes * (unsigned)V.per_group);
+            __syncwarp();
+            for (int q = tid; q < V.per_group; q += 32) {
+                int s = 0, base = 0;
+                for (; s < V.n_streams; ++s) {
+                    const int rows = V.streams[s].kind == JBUGS_ARG_DATA_IJ ? T : (V.streams[s].kind == JBUGS_ARG_DATA_I ? 1 : 0);
+                    if (q < base + rows) break;
+                    base += rows;
+                }
+                const Stream sm = V.streams[s];
+                const int j = q - base;
+                bulk_g2s(dst + sm.soff + j * STAGE_G, sm.ptr + i + V.N * (long long)j, row_bytes, bar);
+            }
+        }
+        return true;
+    }
     for (int s = 0; s < V.n_streams; ++s) {
         const Stream sm = V.streams[s];
         if (sm.kind == JBUGS_ARG_DATA_I) {
@@ -43,6 +91,23 @@ __device__ __forceinline__ void stage_chunk(const PlateVals& V, double* dst, lon
             }
         }
     }
+    return false;
+}
+
+// wait until the staged chunk is visible: TMA chunks complete on the mbarrier (bounded spin: a protocol error must
+// surface as a flagged chain, never as a hung GPU), cp.async chunks on the group counter; then the CTA barrier.
+template <bool TMA>
+__device__ __forceinline__ bool stage_wait(bool was_bulk, unsigned long long* bar, unsigned parity) {
+    bool ok = true;
+    if (TMA && was_bulk) {
+        ok = false;
+#pragma unroll 1  // keep the kernel inside the 32 KB instruction cache: the unrolled spin added 600 instructions
+        for (int it = 0; it < (1 << 22); ++it)
+            if (mbar_try_wait(bar, parity)) { ok = true; break; }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    return ok;
 }
 
 template <class S>
@@ -268,8 +333,9 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
     return bad;
 }
 
-// BLK = chains per CTA (128, or 64 / 32 for small batches so that no lane idles)
-template <class S, int BLK>
+// BLK = chains per CTA (128, or 64 / 32 for small batches so that no lane idles); TMA = stage the data streams with
+// cp.async.bulk + mbarrier where aligned (a separate instantiation: the cp.async-only kernel carries none of it)
+template <class S, int BLK, bool TMA>
 __global__ void __launch_bounds__(BLK, (S::MIN_BLOCKS * (128 / BLK) > 24 ? 24 : S::MIN_BLOCKS * (128 / BLK)))
 plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ theta, double* __restrict__ grad,
              long long ld, long long C, const double* __restrict__ gvals, long long ldg,
@@ -296,9 +362,22 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
         if (sm.kind == JBUGS_ARG_DATA_J)
             for (int q = tid; q < T; q += BLK) jreg[sm.soff + q] = __ldg(sm.ptr + q);
     }
+    // one mbarrier per stage for the TMA path (transaction-count completion)
+    __shared__ unsigned long long mbar[2];
+    if (TMA) {
+        if (tid == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
+    bool next_bulk = false;     // the chunk in flight went through the TMA path
+    unsigned parity_bits = 0u;  // bit s: phase parity of mbar[s]
+    bool stage_ok = true;
     {
         const long long rem = ie - ib;
-        stage_chunk<BLK>(V, stage0, ib, rem < STAGE_G ? (int)rem : STAGE_G, T, tid);
+        next_bulk = stage_chunk<BLK, TMA>(V, stage0, ib, rem < STAGE_G ? (int)rem : STAGE_G, T, tid, &mbar[0]);
         cp_async_commit();
     }
 
@@ -329,8 +408,9 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
 #pragma unroll
     for (int l = 0; l < MAX_LOC; ++l) pos[l] = V.loc[l].row0 + V.loc[l].step_i * ib;
 
-    cp_async_wait_all();
-    __syncthreads();
+    stage_ok &= stage_wait<TMA>(next_bulk, &mbar[0], parity_bits & 1u);
+    if (next_bulk) parity_bits ^= 1u;
+    next_bulk = false;
 
     int cur = 0;
     GroupLoads<U> gl_cur;
@@ -340,7 +420,8 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
         const int cnt = rem < STAGE_G ? (int)rem : STAGE_G;
         if (i0 + STAGE_G < ie) {  // prefetch the next chunk into the other stage
             const long long rem2 = ie - (i0 + STAGE_G);
-            stage_chunk<BLK>(V, stage0 + (cur ^ 1) * stage_doubles, i0 + STAGE_G, rem2 < STAGE_G ? (int)rem2 : STAGE_G, T, tid);
+            next_bulk = stage_chunk<BLK, TMA>(V, stage0 + (cur ^ 1) * stage_doubles, i0 + STAGE_G,
+                                                   rem2 < STAGE_G ? (int)rem2 : STAGE_G, T, tid, &mbar[cur ^ 1]);
         }
         cp_async_commit();
         StageView sv;
@@ -370,10 +451,14 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
                 load_groups<S, 1>(sp, V, i0 + g, th, ld, pos, one);
                 bad |= eval_groups<S, 1>(sp, V, sv, g, i0 + g, T, th, gr, ld, store, obs_tau, pos, one, st, fa, lp);
             }
-        cp_async_wait_all();
-        __syncthreads();
+        // the next chunk (issued at the top of this iteration) must have landed before it is read; the barrier also
+        // protects the stage just consumed from the refill issued at the top of the next iteration
+        stage_ok &= stage_wait<TMA>(next_bulk, &mbar[cur ^ 1], (parity_bits >> (cur ^ 1)) & 1u);
+        if (next_bulk) parity_bits ^= 1u << (cur ^ 1);
+        next_bulk = false;
         cur ^= 1;
     }
+    bad |= !stage_ok;
 
     // expand the sufficient statistics of the fused paths
     const double n_obs = (double)((ie - ib) * V.T);

@@ -5,11 +5,13 @@ namespace jbugs {
     cudaError_t name##_32(JBUGS_LAUNCH_PARAMS);                  \
     cudaError_t name##_64(JBUGS_LAUNCH_PARAMS);                  \
     cudaError_t name##_128(JBUGS_LAUNCH_PARAMS);                 \
+    cudaError_t name##_128t(JBUGS_LAUNCH_PARAMS);                \
     cudaError_t name(JBUGS_LAUNCH_PARAMS) {                      \
         switch (plate_block(C)) {                                \
         case 32: return name##_32(JBUGS_LAUNCH_ARGS);            \
         case 64: return name##_64(JBUGS_LAUNCH_ARGS);            \
-        default: return name##_128(JBUGS_LAUNCH_ARGS);           \
+        default: /* TMA-staged instantiation on request */       \
+            return pp.v.bulk_ok ? name##_128t(JBUGS_LAUNCH_ARGS) : name##_128(JBUGS_LAUNCH_ARGS); \
         }                                                        \
     }
 JB_DISPATCH(launch_dyn)

@@ -1,7 +1,7 @@
 // spec_one.cu -- ONE instantiation of the plate kernel per object file, selected on the compile line:
-//   -DJB_SPEC='StaticSpec<RatsDesc<5>>' -DJB_BLK=128 -DJB_NAME=launch_rats_t5_128
-// (24 small translation units compile in parallel instead of one big one.)
+//   -DJB_SPEC='StaticSpec<RatsDesc<5>>' -DJB_BLK=128 -DJB_TMA=false -DJB_NAME=launch_rats_t5_128
+// (small translation units compile in parallel instead of one big one.)
 #include "jbugs_launch.cuh"
 namespace jbugs {
-cudaError_t JB_NAME(JBUGS_LAUNCH_PARAMS) { return launch_plate_blk<JB_SPEC, JB_BLK>(JBUGS_LAUNCH_ARGS); }
+cudaError_t JB_NAME(JBUGS_LAUNCH_PARAMS) { return launch_plate_blk<JB_SPEC, JB_BLK, JB_TMA>(JBUGS_LAUNCH_ARGS); }
 }  // namespace jbugs

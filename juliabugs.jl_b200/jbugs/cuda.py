@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libjbugs_cuda.so")
+LIB_PATH = os.environ.get("JBUGS_CUDA_LIB") or os.path.join(os.path.dirname(_HERE), "csrc", "libjbugs_cuda.so")
 
 LAYOUT_CHAIN_FAST, LAYOUT_PARAM_FAST = 0, 1
 EVAL_ASYNC = 1

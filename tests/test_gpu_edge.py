@@ -143,6 +143,21 @@ def test_ragged_sizes(N, C):
     _check(m.cuda, co, theta)
 
 
+@pytest.mark.parametrize("N", [4096, 4098, 1001])
+def test_tma_and_cp_async_staging_agree(N):
+    """the data streams are staged either by the TMA bulk-copy path (aligned chunks) or by cp.async (unaligned
+    chunks / odd N): both must give bit-identical results."""
+    data, alpha, beta = synth_rats(N, seed=2)
+    m = jbugs.compile(jbugs.examples.RATS, data)
+    theta = random_thetas(np.concatenate([[1.0, 6, -5, 240, -3.5], np.column_stack([beta, alpha]).ravel()]), 70, seed=4, scale=0.05)
+    m.cuda.set_option("tma", 1)
+    a = m.cuda.eval_host(theta)
+    _check(m.cuda, _oracle(m.plan), theta)
+    m.cuda.set_option("tma", 0)
+    b = m.cuda.eval_host(theta)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
 def test_bitwise_repeatability():
     data, alpha, beta = synth_rats(5000, seed=9)
     m = jbugs.compile(jbugs.examples.RATS, data)
