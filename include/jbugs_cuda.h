@@ -130,6 +130,23 @@ int jbugs_plan_set_option(jbugs_plan* plan, const char* key, int64_t value);
  * kernels and in total between the first and last enqueue (CUDA events on the call's stream). */
 int jbugs_last_timing(const jbugs_plan* plan, float* plate_ms, float* total_ms);
 
+/* ---- on-device batched HMC (the caller of the hot path) ---------------------------------------
+ * Replaces: the AdvancedHMC loop behind `AbstractMCMC.sample(model, HMC/NUTS, n)`
+ * (ext/JuliaBUGSAdvancedHMCExt.jl:40-66), which calls logdensity_and_gradient once per leapfrog step with theta on the
+ * host.  C chains advance in lock step; theta, momentum and gradient stay in HBM (5 x D x C doubles).
+ *   jbugs_hmc_init : every chain starts at theta0 + jitter * N(0,1) (unconstrained space)
+ *   jbugs_hmc_run  : n_iter transitions of n_leapfrog steps.  adapt != 0: warm-up (dual-averaging step size pooled over
+ *                    chains, windowed diagonal metric from moments pooled over chains).  The monitored theta rows of
+ *                    every iteration are written to out_host[n_iter][n_monitor][C]. */
+typedef struct jbugs_hmc_s jbugs_hmc;
+int jbugs_hmc_create(jbugs_plan* plan, int64_t C, uint64_t seed, jbugs_hmc** out);
+int jbugs_hmc_destroy(jbugs_hmc* hmc);
+int jbugs_hmc_init(jbugs_hmc* hmc, const double* theta0_host, double jitter, double step_size);
+int jbugs_hmc_run(jbugs_hmc* hmc, int n_iter, int n_leapfrog, int adapt, const int64_t* monitor_rows, int n_monitor,
+                  double* out_host, double* mean_accept);
+int jbugs_hmc_get_state(jbugs_hmc* hmc, double* theta_host /* [D][C] */, double* logp_host /* [C] */, double* step_size,
+                        double* var_host /* [D] diagonal of the inverse metric */);
+
 #ifdef __cplusplus
 }
 #endif

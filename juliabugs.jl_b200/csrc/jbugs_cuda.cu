@@ -15,6 +15,7 @@
 #include "jbugs_kernels.cuh"
 #include "jbugs_obsconst.cuh"
 #include "jbugs_dense.cuh"
+#include "jbugs_hmc.cuh"
 #define JBUGS_SPEC_TABLE
 #include "jbugs_specs.cuh"
 
@@ -967,6 +968,8 @@ extern "C" int jbugs_eval_batch(jbugs_plan* p, const double* theta, int64_t ld, 
     return JBUGS_OK;
 #endif
 }
+
+#include "jbugs_hmc.inc"
 
 extern "C" int jbugs_batch_alloc(jbugs_plan* p, int64_t C, double** theta_dev, double** grad_dev, double** logp_dev,
                                  int32_t** status_dev, int64_t* ld) {

@@ -1,0 +1,190 @@
+// jbugs_hmc.cuh -- on-device batched Hamiltonian Monte Carlo around the batched evaluator.
+//
+// The reference samples with AdvancedHMC through `AbstractMCMC.sample(model, NUTS/HMC, n)`
+// (JuliaBUGS/ext/JuliaBUGSAdvancedHMCExt.jl:40-66): every leapfrog step calls `logdensity_and_gradient` once, one
+// chain per call, with theta on the host.  Here C chains advance in lock step, theta / momentum / gradient never
+// leave HBM, and one iteration is  L x (leapfrog kernel + jbugs evaluator)  + a handful of per-chain kernels.
+//
+// All arrays are chain-fast [D][ld]; a thread owns one chain (column), exactly like the evaluator's kernels.
+// Random numbers: Philox4x32-10 (counter = element / iteration / stream, key = seed): reproducible and independent
+// of the launch geometry.
+#pragma once
+
+#include "jbugs_kernels.cuh"
+
+namespace jbugs {
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ double u01(unsigned hi, unsigned lo) {  // (0, 1)
+    const unsigned long long b = (((unsigned long long)hi << 32) | lo) >> 11;
+    return ((double)b + 0.5) * (1.0 / 9007199254740992.0);
+}
+// two independent standard normals for (element e, iteration it, stream s)
+__device__ __forceinline__ double2 normal2(unsigned long long seed, unsigned long long e, unsigned it, unsigned s) {
+    const uint4 r = philox4x32_10(make_uint4((unsigned)e, (unsigned)(e >> 32), it, s),
+                                  make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const double u = u01(r.x, r.y), v = u01(r.z, r.w);
+    const double rad = sqrt(-2.0 * log(u));
+    double sn, cs;
+    sincospi(2.0 * v, &sn, &cs);
+    return make_double2(rad * cs, rad * sn);
+}
+
+
+// q[d][c] = theta0[d] + jitter * z
+__global__ void __launch_bounds__(BLOCK)
+hmc_init_kernel(double* __restrict__ q, long long ld, long long D, long long C, const double* __restrict__ theta0,
+                double jitter, unsigned long long seed, long long HMC_ROWS) {
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    const long long d0 = (long long)blockIdx.y * HMC_ROWS, d1 = d0 + HMC_ROWS < D ? d0 + HMC_ROWS : D;
+    for (long long d = d0; d < d1; ++d) q[d * ld + c] = theta0[d] + jitter * normal2(seed, d * C + c, 0u, 1u).x;
+}
+
+// fresh momentum p ~ N(0, M), M = diag(1 / var);  kinetic partial sums 0.5 * sum p^2 var
+__global__ void __launch_bounds__(BLOCK)
+hmc_refresh_kernel(double* __restrict__ p, long long ld, long long D, long long C, const double* __restrict__ var,
+                   unsigned long long seed, unsigned it, double* __restrict__ kin_partial, long long ldg, long long HMC_ROWS) {
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    const long long d0 = (long long)blockIdx.y * HMC_ROWS, d1 = d0 + HMC_ROWS < D ? d0 + HMC_ROWS : D;
+    double k = 0.0;
+    for (long long d = d0; d < d1; d += 2) {
+        const double2 z = normal2(seed, (d >> 1) * C + c, it, 2u);
+        const double v0 = var[d];
+        p[d * ld + c] = z.x * rsqrt(v0);
+        k = fma(z.x, z.x, k);  // p^2 var = z^2
+        if (d + 1 < d1) {
+            p[(d + 1) * ld + c] = z.y * rsqrt(var[d + 1]);
+            k = fma(z.y, z.y, k);
+        }
+    }
+    kin_partial[(long long)blockIdx.y * ldg + c] = 0.5 * k;
+}
+
+// one leapfrog update:  p += wp * eps * g;  q_out = q_in + wq * eps * var * p     (wq = 0: momentum only)
+// with `kin_partial` != null the kinetic energy of the updated momentum is accumulated per (row tile, chain)
+__global__ void __launch_bounds__(BLOCK)
+hmc_leap_kernel(const double* q_in, double* q_out /* may alias q_in */, double* __restrict__ p,
+                const double* __restrict__ g, long long ld, long long D, long long C, const double* __restrict__ var,
+                double eps, double wp, double wq, double* __restrict__ kin_partial, long long ldg, long long HMC_ROWS) {
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    const long long d0 = (long long)blockIdx.y * HMC_ROWS, d1 = d0 + HMC_ROWS < D ? d0 + HMC_ROWS : D;
+    double k = 0.0;
+    for (long long d = d0; d < d1; ++d) {
+        const long long e = d * ld + c;
+        const double v = var[d];
+        const double pn = fma(wp * eps, g[e], p[e]);
+        p[e] = pn;
+        if (wq != 0.0) q_out[e] = fma(wq * eps * v, pn, q_in[e]);
+        k = fma(pn * pn, v, k);
+    }
+    if (kin_partial) kin_partial[(long long)blockIdx.y * ldg + c] = 0.5 * k;
+}
+
+// per chain: sum the kinetic partials (ascending tiles); dst[c] = that sum
+__global__ void __launch_bounds__(BLOCK)
+hmc_colsum_kernel(const double* __restrict__ partial, int n_tiles, long long ldg, long long C, double* __restrict__ dst) {
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int t = 0; t < n_tiles; ++t) s += partial[(long long)t * ldg + c];
+    dst[c] = s;
+}
+
+// Metropolis test per chain.  H = -logp + K.  Non-finite proposals (divergences, DomainError) are rejected.
+__global__ void __launch_bounds__(BLOCK)
+hmc_accept_kernel(const double* lp0 /* == lp_cur */, const double* __restrict__ k0, const double* __restrict__ lp1,
+                  const double* __restrict__ k1, const int* __restrict__ status1, long long C, unsigned long long seed,
+                  unsigned it, int* __restrict__ accept, double* __restrict__ accept_prob, double* lp_cur) {
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    const double h0 = -lp0[c] + k0[c], h1 = -lp1[c] + k1[c];
+    double a = exp(fmin(0.0, h0 - h1));
+    if (!(h1 == h1) || !(a == a) || status1[c] != 0 || fabs(h1) == dev_inf()) a = 0.0;
+    const uint4 r = philox4x32_10(make_uint4((unsigned)c, (unsigned)(c >> 32), it, 3u), make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const int acc = u01(r.x, r.y) < a;
+    accept[c] = acc;
+    accept_prob[c] = a;
+    if (acc) lp_cur[c] = lp1[c];
+}
+
+// accepted chains take the proposal:  q_cur, g_cur <- q_prop, g_prop
+__global__ void __launch_bounds__(BLOCK)
+hmc_select_kernel(double* __restrict__ q_cur, double* __restrict__ g_cur, const double* __restrict__ q_prop,
+                  const double* __restrict__ g_prop, long long ld, long long D, long long C, const int* __restrict__ accept,
+                  long long HMC_ROWS) {
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C || !accept[c]) return;
+    const long long d0 = (long long)blockIdx.y * HMC_ROWS, d1 = d0 + HMC_ROWS < D ? d0 + HMC_ROWS : D;
+    for (long long d = d0; d < d1; ++d) {
+        const long long e = d * ld + c;
+        q_cur[e] = q_prop[e];
+        g_cur[e] = g_prop[e];
+    }
+}
+
+// monitored rows of the current state -> out[m][c]
+__global__ void __launch_bounds__(BLOCK)
+hmc_monitor_kernel(const double* __restrict__ q, long long ld, long long C, const long long* __restrict__ rows, int n_rows,
+                   double* __restrict__ out, long long ldo) {
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    for (int m = blockIdx.y; m < n_rows; m += gridDim.y) out[(long long)m * ldo + c] = q[rows[m] * ld + c];
+}
+
+// running first and second moments of every parameter, pooled over chains (one warp per row; fixed-order butterfly)
+__global__ void __launch_bounds__(256)
+hmc_moments_kernel(const double* __restrict__ q, long long ld, long long D, long long C, double* __restrict__ s1,
+                   double* __restrict__ s2) {
+    const long long d = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (d >= D) return;
+    const int lane = threadIdx.x & 31;
+    double a = 0.0, b = 0.0;
+    for (long long c = lane; c < C; c += 32) {
+        const double v = q[d * ld + c];
+        a += v;
+        b = fma(v, v, b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+        s1[d] += a;
+        s2[d] += b;
+    }
+}
+
+// var[d] from the pooled moments (regularised towards 1 like Stan's windowed adaptation), then reset the moments
+__global__ void __launch_bounds__(BLOCK)
+hmc_update_metric_kernel(double* __restrict__ var, double* __restrict__ s1, double* __restrict__ s2, long long D, double n) {
+    const long long d = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (d >= D) return;
+    const double mean = s1[d] / n;
+    double v = (s2[d] - n * mean * mean) / (n - 1.0);
+    v = (n / (n + 5.0)) * v + 1e-3 * (5.0 / (n + 5.0));
+    var[d] = (v > 0.0 && v == v && fabs(v) != dev_inf()) ? v : 1.0;
+    s1[d] = 0.0;
+    s2[d] = 0.0;
+}
+
+__global__ void __launch_bounds__(BLOCK)
+hmc_fill_kernel(double* __restrict__ x, long long n, double v) {
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+
+}  // namespace jbugs

@@ -1,0 +1,93 @@
+"""On-device batched HMC around the CUDA evaluator (the caller of the hot path).
+
+Reference counterpart: `AbstractMCMC.sample(model, NUTS(0.8), n; n_adapts, ...)` through
+`JuliaBUGS/ext/JuliaBUGSAdvancedHMCExt.jl:40-66`, where AdvancedHMC calls `logdensity_and_gradient` once per
+leapfrog step for one chain.  Here every chain of the batch advances in lock step on the GPU; only the monitored
+parameters of each draw come back to the host.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import plan as P
+from .cuda import _check, load
+from .model import BUGSModel, getparams
+
+
+@dataclass
+class HMC:
+    """static-trajectory HMC: `n_leapfrog` steps per transition, step size and diagonal metric adapted in warm-up."""
+    n_leapfrog: int = 16
+    step_size: float = 0.01
+    jitter: float = 0.1
+
+
+@dataclass
+class Chains:
+    names: List[str]
+    samples: np.ndarray          # [n_samples, n_monitored, n_chains], constrained space
+    accept_rate: float
+    step_size: float
+
+    def __getitem__(self, name: str) -> np.ndarray:
+        return self.samples[:, self.names.index(name), :]
+
+    def mean(self, name):
+        return float(self[name].mean())
+
+    def std(self, name):
+        return float(self[name].std())
+
+
+def _bind(L):
+    c = ctypes
+    L.jbugs_hmc_create.argtypes = [c.c_void_p, c.c_int64, c.c_uint64, c.POINTER(c.c_void_p)]
+    L.jbugs_hmc_destroy.argtypes = [c.c_void_p]
+    L.jbugs_hmc_init.argtypes = [c.c_void_p, c.c_void_p, c.c_double, c.c_double]
+    L.jbugs_hmc_run.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_int, c.c_void_p, c.POINTER(c.c_double)]
+    L.jbugs_hmc_get_state.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.POINTER(c.c_double), c.c_void_p]
+
+
+def _constrain(tr, lb, ub, y):
+    if tr == P.TR_LOG:
+        return lb + np.exp(y)
+    if tr == P.TR_UPPER:
+        return ub - np.exp(y)
+    if tr == P.TR_LOGIT:
+        return lb + (ub - lb) / (1.0 + np.exp(-y))
+    return y
+
+
+def sample(model: BUGSModel, sampler: HMC, n_samples: int, n_adapts: int = 500, n_chains: int = 256, seed: int = 1234,
+           monitor: Optional[Sequence[str]] = None, init: Optional[np.ndarray] = None) -> Chains:
+    """`AbstractMCMC.sample(model, sampler, n_samples; n_adapts, ...)` for `n_chains` lock-step chains.
+    `monitor`: names of scalar (global) parameters to record; default: all of them."""
+    L = load()
+    _bind(L)
+    cp = model.cuda
+    names = [g.name for g in model.plan.globals] if monitor is None else list(monitor)
+    by_name = {g.name: g for g in model.plan.globals}
+    rows = np.array([by_name[n].theta_idx for n in names], dtype=np.int64)
+    th0 = np.ascontiguousarray(getparams(model) if init is None else init, dtype=np.float64)
+    th0 = np.where(np.isfinite(th0), th0, 0.0)
+    h = ctypes.c_void_p()
+    _check(L.jbugs_hmc_create(cp.h, n_chains, seed, ctypes.byref(h)))
+    try:
+        _check(L.jbugs_hmc_init(h, th0.ctypes.data, sampler.jitter, sampler.step_size))
+        acc = ctypes.c_double()
+        if n_adapts > 0:
+            _check(L.jbugs_hmc_run(h, n_adapts, sampler.n_leapfrog, 1, None, 0, None, ctypes.byref(acc)))
+        out = np.empty((n_samples, len(names), n_chains))
+        _check(L.jbugs_hmc_run(h, n_samples, sampler.n_leapfrog, 0, rows.ctypes.data, len(names), out.ctypes.data, ctypes.byref(acc)))
+        eps = ctypes.c_double()
+        _check(L.jbugs_hmc_get_state(h, None, None, ctypes.byref(eps), None))
+    finally:
+        L.jbugs_hmc_destroy(h)
+    for k, n in enumerate(names):
+        g = by_name[n]
+        out[:, k, :] = _constrain(g.transform, g.lb, g.ub, out[:, k, :])
+    return Chains(names, out, float(acc.value), float(eps.value))

@@ -1,0 +1,54 @@
+"""On-device batched HMC.  Statistical checks in the style of the reference's sampler tests
+(J/test/ext/JuliaBUGSAdvancedHMCExt.jl:30-63: posterior mean and std vs the WinBUGS `reference_results` at rtol 0.3)."""
+import numpy as np
+import pytest
+
+import jbugs
+from jbugs import hmc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_conjugate_normal_mean():
+    """y_i ~ N(mu, 1), flat-ish prior: posterior N(ybar, 1/n) -- exact answer."""
+    rng = np.random.default_rng(0)
+    y = rng.normal(1.7, 1.0, 400)
+    text = "model { for (i in 1:N) { y[i] ~ dnorm(mu, 1.0) }\n mu ~ dnorm(0.0, 1.0E-6) }"
+    m = jbugs.compile(text, {"N": 400, "y": y}, {"mu": 0.0})
+    ch = hmc.sample(m, hmc.HMC(n_leapfrog=8, step_size=0.05), n_samples=300, n_adapts=200, n_chains=512, seed=3)
+    mu = ch["mu"]
+    assert abs(mu.mean() - y.mean()) < 5e-3
+    assert abs(mu.std() - 1.0 / np.sqrt(400)) < 0.1 / np.sqrt(400)
+    assert 0.5 < ch.accept_rate <= 1.0
+
+
+def test_seeds_posterior_matches_winbugs_reference(fixtures):
+    """Seeds (src/BUGSExamples/Volume_1/04_Seeds.jl:51-57), the second model of the reference's NUTS test."""
+    fx = fixtures["seeds"]
+    m = jbugs.compile(jbugs.examples.SEEDS, fx["data"], fx["inits"])
+    ch = hmc.sample(m, hmc.HMC(n_leapfrog=32, step_size=0.01, jitter=0.05), n_samples=1000, n_adapts=1500, n_chains=256, seed=7)
+    ref = {"alpha0": (-0.5499, 0.1965), "alpha1": (0.08902, 0.3124), "alpha12": (-0.841, 0.4372), "alpha2": (1.356, 0.2772)}
+    for k, (mean, std) in ref.items():
+        assert abs(ch.mean(k) - mean) < 0.15 * std, k     # the reference accepts rtol = 0.3 on the mean itself
+        assert ch.std(k) == pytest.approx(std, rel=0.1), k
+    sigma = 1.0 / np.sqrt(ch["tau"])
+    assert sigma.mean() == pytest.approx(0.2922, rel=0.1) and sigma.std() == pytest.approx(0.1467, rel=0.15)
+
+
+def test_rats_posterior_matches_winbugs_reference(fixtures):
+    """Rats: alpha0 = alpha.c - xbar * beta.c, beta.c, sigma = 1/sqrt(tau.c) against the WinBUGS reference results the
+    reference ships (src/BUGSExamples/Volume_1/01_Rats.jl:97-101), same tolerance as the reference's NUTS test."""
+    fx = fixtures["rats"]
+    m = jbugs.compile(jbugs.examples.RATS, fx["data"], fx["inits"])
+    ch = hmc.sample(m, hmc.HMC(n_leapfrog=32, step_size=0.005, jitter=0.05), n_samples=1000, n_adapts=1500, n_chains=256, seed=1234)
+    alpha0 = ch["alpha.c"] - 22.0 * ch["beta.c"]
+    sigma = 1.0 / np.sqrt(ch["tau.c"])
+    ref = {"alpha0": (106.6, 3.66), "beta.c": (6.186, 0.1086), "sigma": (6.093, 0.4643)}
+    got = {"alpha0": alpha0, "beta.c": ch["beta.c"], "sigma": sigma}
+    for k, (mean, std) in ref.items():
+        # the reference's own NUTS test accepts rtol = 0.3; 256 chains x 1000 draws land within a few per cent
+        assert got[k].mean() == pytest.approx(mean, rel=0.02), k
+        assert got[k].std() == pytest.approx(std, rel=0.1), k
+    # between-chain spread of the per-chain means: all chains found the same posterior
+    assert alpha0.mean(axis=0).std() < 0.6
+    assert 0.6 < ch.accept_rate < 0.95
