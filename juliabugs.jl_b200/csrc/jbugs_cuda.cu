@@ -117,10 +117,6 @@ struct jbugs_plan_s {
     double* d_red = nullptr;   // [1 + NG][ldg] reduced partials (multi-GPU path)
     int* d_flags = nullptr;
     int* d_any_bad = nullptr;
-    // staging for host pointers / PARAM_FAST
-    double *s_theta = nullptr, *s_grad = nullptr, *s_theta_t = nullptr, *s_grad_t = nullptr, *s_logp = nullptr;
-    int* s_status = nullptr;
-    long long s_C = 0;
     // pipelined host path: two staging slots, copy-in / copy-out streams, per-slot events
     struct Slot {
         double *theta = nullptr, *grad = nullptr, *theta_t = nullptr, *grad_t = nullptr, *logp = nullptr;
@@ -495,13 +491,6 @@ static void free_workspace(jbugs_plan* p) {
     p->cap_C = 0;
 }
 
-static void free_staging(jbugs_plan* p) {
-    cudaFree(p->s_theta); cudaFree(p->s_grad); cudaFree(p->s_theta_t); cudaFree(p->s_grad_t); cudaFree(p->s_logp); cudaFree(p->s_status);
-    p->s_theta = p->s_grad = p->s_theta_t = p->s_grad_t = p->s_logp = nullptr;
-    p->s_status = nullptr;
-    p->s_C = 0;
-}
-
 extern "C" int jbugs_batch_free(jbugs_plan* p) {
     if (!p) return fail(JBUGS_ERR_INVALID, "null plan");
     cudaSetDevice(p->device);
@@ -526,7 +515,6 @@ extern "C" int jbugs_plan_destroy(jbugs_plan* p) {
     jbugs_comm_destroy(p);
     for (void* d : p->d_slots) cudaFree(d);
     free_workspace(p);
-    free_staging(p);
     free_slots(p);
     for (auto& s : p->slot) {
         if (s.in_done) cudaEventDestroy(s.in_done);
@@ -866,24 +854,6 @@ static bool is_device_ptr(const void* ptr) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-static int ensure_staging(jbugs_plan* p, long long Cc, bool need_t) {
-    const long long D = std::max<long long>(p->h.D, 1);
-    if (Cc > p->s_C) {
-        free_staging(p);
-        const long long ldc = round_up(Cc, 16);
-        CU(cudaMalloc(&p->s_theta, (size_t)D * ldc * 8));
-        CU(cudaMalloc(&p->s_grad, (size_t)D * ldc * 8));
-        CU(cudaMalloc(&p->s_logp, (size_t)ldc * 8));
-        CU(cudaMalloc(&p->s_status, (size_t)ldc * 4));
-        p->s_C = Cc;
-    }
-    if (need_t && !p->s_theta_t) {
-        CU(cudaMalloc(&p->s_theta_t, (size_t)D * p->s_C * 8));
-        CU(cudaMalloc(&p->s_grad_t, (size_t)D * p->s_C * 8));
-    }
-    return 0;
-}
-
 #include "jbugs_staged.inc"
 
 extern "C" int jbugs_eval_batch(jbugs_plan* p, const double* theta, int64_t ld, int64_t C, int layout, double* logp,
@@ -913,60 +883,6 @@ extern "C" int jbugs_eval_batch(jbugs_plan* p, const double* theta, int64_t ld, 
     }
     // host buffers and/or PARAM_FAST: pipelined through library staging in chunks of chains
     return eval_staged(p, theta, ld, C, layout, logp, grad, status, want_grad, st);
-#if 0  // superseded serial staging path
-    const bool theta_dev = is_device_ptr(theta), logp_dev = is_device_ptr(logp), grad_dev = is_device_ptr(grad), status_dev = is_device_ptr(status);
-    const long long budget = 1LL << 31;  // bytes per staging buffer
-    long long Cc = std::max<long long>(1, std::min<long long>(C, budget / (8 * std::max<long long>(D, 1))));
-    if (Cc >= 16) Cc = Cc / 16 * 16;
-    const bool pf = layout == JBUGS_LAYOUT_PARAM_FAST;
-    rc = ensure_staging(p, Cc, pf);
-    if (rc) return rc;
-    const long long ldc = round_up(p->s_C, 16);
-    float plate_ms = 0.f, total_ms = 0.f;
-    for (long long c0 = 0; c0 < C; c0 += Cc) {
-        const long long n = std::min<long long>(Cc, C - c0);
-        if (pf) {
-            // chains [c0, c0+n) are n contiguous columns of length D (stride ld)
-            const double* src = theta + c0 * ld;
-            if (ld == D) CU(cudaMemcpyAsync(p->s_theta_t, src, (size_t)n * D * 8, cudaMemcpyDefault, st));
-            else CU(cudaMemcpy2DAsync(p->s_theta_t, (size_t)D * 8, src, (size_t)ld * 8, (size_t)D * 8, (size_t)n, cudaMemcpyDefault, st));
-            dim3 g((unsigned)((D + 31) / 32), (unsigned)((n + 31) / 32));
-            transpose_kernel<<<g, 256, 0, st>>>(p->s_theta_t, D, p->s_theta, ldc, n, D);
-            p->launches++;
-        } else {
-            CU(cudaMemcpy2DAsync(p->s_theta, (size_t)ldc * 8, theta + c0, (size_t)ld * 8, (size_t)n * 8, (size_t)D, cudaMemcpyDefault, st));
-        }
-        (void)theta_dev;
-        rc = eval_device(p, p->s_theta, ldc, n, p->s_logp, want_grad ? p->s_grad : nullptr, p->s_status, want_grad, st);
-        if (rc) return rc;
-        if (want_grad) {
-            if (pf) {
-                dim3 g((unsigned)((n + 31) / 32), (unsigned)((D + 31) / 32));
-                transpose_kernel<<<g, 256, 0, st>>>(p->s_grad, ldc, p->s_grad_t, D, D, n);
-                p->launches++;
-                double* dst = grad + c0 * ld;
-                if (ld == D) CU(cudaMemcpyAsync(dst, p->s_grad_t, (size_t)n * D * 8, cudaMemcpyDefault, st));
-                else CU(cudaMemcpy2DAsync(dst, (size_t)ld * 8, p->s_grad_t, (size_t)D * 8, (size_t)D * 8, (size_t)n, cudaMemcpyDefault, st));
-            } else {
-                CU(cudaMemcpy2DAsync(grad + c0, (size_t)ld * 8, p->s_grad, (size_t)ldc * 8, (size_t)n * 8, (size_t)D, cudaMemcpyDefault, st));
-            }
-        }
-        (void)grad_dev; (void)logp_dev; (void)status_dev;
-        CU(cudaMemcpyAsync(logp + c0, p->s_logp, (size_t)n * 8, cudaMemcpyDefault, st));
-        if (status) CU(cudaMemcpyAsync(status + c0, p->s_status, (size_t)n * 4, cudaMemcpyDefault, st));
-        CU(cudaStreamSynchronize(st));
-        if (p->timing) {
-            float a = 0.f, b = 0.f;
-            cudaEventElapsedTime(&a, p->ev[1], p->ev[2]);
-            cudaEventElapsedTime(&b, p->ev[0], p->ev[3]);
-            plate_ms += a;
-            total_ms += b;
-        }
-    }
-    p->last_plate_ms = plate_ms;
-    p->last_total_ms = total_ms;
-    return JBUGS_OK;
-#endif
 }
 
 #include "jbugs_hmc.inc"

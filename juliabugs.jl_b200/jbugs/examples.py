@@ -189,7 +189,117 @@ model {
 }
 """
 
+# Salm: extra-Poisson variation in a dose-response study (BUGS examples vol. 1)
+SALM = """
+model {
+    for (i in 1:doses) {
+        for (j in 1:plates) {
+            y[i, j] ~ dpois(mu[i, j])
+            log(mu[i, j]) <- alpha + beta * log(x[i] + 10) + gamma * x[i] + lambda[i, j]
+            lambda[i, j] ~ dnorm(0.0, tau)
+        }
+    }
+    alpha ~ dnorm(0.0, 1.0E-6)
+    beta ~ dnorm(0.0, 1.0E-6)
+    gamma ~ dnorm(0.0, 1.0E-6)
+    tau ~ dgamma(0.001, 0.001)
+    sigma <- 1 / sqrt(tau)
+}
+"""
+
+# Equiv: bioequivalence in a cross-over trial; the subject effect is indexed by the INNER loop variable
+EQUIV = """
+model {
+    for (k in 1:P) {
+        for (i in 1:N) {
+            Y[i, k] ~ dnorm(m[i, k], tau1)
+            m[i, k] <- mu + sign[T[i, k]] * phi / 2 + sign[k] * pi / 2 + delta[i]
+            T[i, k] <- group[i] * (k - 1.5) + 1.5
+        }
+    }
+    for (i in 1:N) {
+        delta[i] ~ dnorm(0.0, tau2)
+    }
+    tau1 ~ dgamma(0.001, 0.001)
+    sigma1 <- 1 / sqrt(tau1)
+    tau2 ~ dgamma(0.001, 0.001)
+    sigma2 <- 1 / sqrt(tau2)
+    mu ~ dnorm(0.0, 1.0E-6)
+    phi ~ dnorm(0.0, 1.0E-6)
+    pi ~ dnorm(0.0, 1.0E-6)
+    theta <- exp(phi)
+    equiv <- step(theta - 0.8) - step(theta - 1.2)
+}
+"""
+
+# Dyes: variance components
+DYES = """
+model {
+    for (i in 1:batches) {
+        mu[i] ~ dnorm(theta, tau.btw)
+        for (j in 1:samples) {
+            y[i, j] ~ dnorm(mu[i], tau.with)
+        }
+    }
+    sigma2.with <- 1 / tau.with
+    sigma2.btw <- 1 / tau.btw
+    tau.with ~ dgamma(0.001, 0.001)
+    tau.btw ~ dgamma(0.001, 0.001)
+    theta ~ dnorm(0.0, 1.0E-10)
+}
+"""
+
+# Oxford: smooth fit to log-odds ratios; two binomial statements sharing mu[i]
+OXFORD = """
+model {
+    for (i in 1:K) {
+        r0[i] ~ dbin(p0[i], n0[i])
+        r1[i] ~ dbin(p1[i], n1[i])
+        logit(p0[i]) <- mu[i]
+        logit(p1[i]) <- mu[i] + logPsi[i]
+        logPsi[i] <- alpha + beta1 * year[i] + beta2 * (year[i] * year[i] - 22) + b[i]
+        b[i] ~ dnorm(0, tau)
+        mu[i] ~ dnorm(0.0, 1.0E-6)
+    }
+    alpha ~ dnorm(0.0, 1.0E-6)
+    beta1 ~ dnorm(0.0, 1.0E-6)
+    beta2 ~ dnorm(0.0, 1.0E-6)
+    tau ~ dgamma(0.001, 0.001)
+    sigma <- 1 / sqrt(tau)
+}
+"""
+
+# Stacks: regression on standardised covariates; the coefficient vector is referenced element by element
+STACKS = """
+model {
+    for (j in 1:p) {
+        b[j] <- beta[j] / sd(x[, j])
+        for (i in 1:N) {
+            z[i, j] <- (x[i, j] - mean(x[, j])) / sd(x[, j])
+        }
+    }
+    b0 <- beta0 - b[1] * mean(x[, 1]) - b[2] * mean(x[, 2]) - b[3] * mean(x[, 3])
+    for (i in 1:N) {
+        Y[i] ~ dnorm(mu[i], tau)
+        mu[i] <- beta0 + beta[1] * z[i, 1] + beta[2] * z[i, 2] + beta[3] * z[i, 3]
+        stres[i] <- (Y[i] - mu[i]) / sigma
+        outlier[i] <- step(stres[i] - 2.5) + step(-(stres[i] + 2.5))
+    }
+    beta0 ~ dnorm(0, 0.00001)
+    for (j in 1:p) {
+        beta[j] ~ dnorm(0, 0.00001)
+    }
+    tau ~ dgamma(1.0E-3, 1.0E-3)
+    sigma <- sqrt(1 / tau)
+}
+"""
+
 MODELS = {
+    "stacks": STACKS,
+    "salm": SALM,
+    "equiv": EQUIV,
+    "dyes": DYES,
+    "oxford": OXFORD,
     "rats": RATS,
     "pumps": PUMPS,
     "dogs": DOGS,

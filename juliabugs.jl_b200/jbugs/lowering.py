@@ -25,7 +25,7 @@ Models outside the supported class raise `LoweringError` -- there is no CPU fall
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass
+from dataclasses import dataclass, replace
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -143,6 +143,19 @@ class DataEval:
                     idx.append(iv.astype(np.int64) - 1 if iv.ndim else int(iv) - 1)
             return arr[tuple(idx)]
         if isinstance(e, Call):
+            if e.fn in ("mean", "sum", "sd", "inprod"):
+                # reductions over slices: evaluate once per distinct value of the loop variables they depend on
+                # (mean(x[, j]) inside `for j { for i {` is p evaluations, not N * p)
+                used = [v for v in free_vars(e) if v in lv and np.ndim(lv[v]) > 0 and np.size(lv[v]) > 1]
+                if used:
+                    grids = np.broadcast_arrays(*[lv[v] for v in used])
+                    out = np.empty(grids[0].shape, dtype=np.float64)
+                    for pos in np.ndindex(out.shape):
+                        point = dict(lv)
+                        for v, gr in zip(used, grids):
+                            point[v] = int(gr[pos])
+                        out[pos] = self.ev(e, point)
+                    return out
             args = [self.ev(a, lv) for a in e.args]
             if e.fn in _NP_FUNCS:
                 return _NP_FUNCS[e.fn](*args)
@@ -515,6 +528,8 @@ class Lowering:
             return e
         if isinstance(e, Index):
             idx = tuple(self._inline(i, depth + 1) for i in e.idx)
+            if self._elem_label(Index(e.name, idx)) in self._gval_ids:
+                return Index(e.name, idx)  # element of a parameter vector / indexed scalar node held as a global
             defs = [s for s in self._defs(e.name) if s.kind == "logical"]
             if defs:
                 if len(defs) != 1:
@@ -547,6 +562,9 @@ class Lowering:
         if isinstance(e, Var):
             return _Lin(terms={("g", e.name): ONE})
         if isinstance(e, Index):
+            lab = self._elem_label(e)
+            if lab in self._gval_ids:
+                return _Lin(terms={("g", lab): ONE})
             return _Lin(terms={("l", e.name, e.idx): ONE})
         if isinstance(e, Neg):
             z = self._linearize(e.a, loop_vars)
@@ -579,7 +597,55 @@ class Lowering:
             return self._data_arg(e, loop_vars, shape, lv_names)
         if isinstance(e, Var) and e.name in self._gval_ids:
             return P.Arg.gval(self._gval_ids[e.name])
+        if isinstance(e, Index) and self._elem_label(e) in self._gval_ids:
+            return P.Arg.gval(self._gval_ids[self._elem_label(e)])
         raise LoweringError(f"distribution argument {e!r} must be a constant, data, or a scalar parameter")
+
+    def _elem_label(self, e) -> Optional[str]:
+        """'name[3]' for a reference with constant (data-only, loop-free) subscripts, else None."""
+        if not isinstance(e, Index) or any(isinstance(i, (Range, Colon)) for i in e.idx):
+            return None
+        if not all(self._is_data(i, ()) for i in e.idx):
+            return None
+        return f"{e.name}[{','.join(str(int(self.de.ev(i, {}))) for i in e.idx)}]"
+
+    def _vector_globals(self):
+        """sids of looped parameter statements whose elements are referenced with constant subscripts by an
+        observation statement or by a scalar logical node: their elements become globals."""
+        found = set()
+
+        def walk(e):
+            if isinstance(e, Index):
+                if self._elem_label(e) is not None:
+                    for d in self._defs(e.name):
+                        if d.kind == "param" and d.loops and not d.is_gq:
+                            if d.size > 48:
+                                raise LoweringError(
+                                    f"'{e.name}' has {d.size} elements, too many to expand into scalar globals; "
+                                    "write the predictor as inprod(X[i, 1:P], beta[1:P]) for the dense path")
+                            found.add(d.sid)
+                for i in e.idx:
+                    walk(i)
+            elif isinstance(e, Call):
+                for a in e.args:
+                    walk(a)
+            elif isinstance(e, BinOp):
+                walk(e.a)
+                walk(e.b)
+            elif isinstance(e, Neg):
+                walk(e.a)
+
+        for s in self.stmts:
+            if s.is_gq:
+                continue
+            if s.kind == "obs" or (s.kind == "logical" and not s.loops):
+                try:
+                    exprs = [self._inline(a) for a in s.node.dist.args] if s.kind == "obs" else [self._inline(s.node.rhs)]
+                except LoweringError:
+                    continue
+                for e in exprs:
+                    walk(e)
+        return found
 
     def _inline_scalar_logical(self, e):
         return e
@@ -641,27 +707,51 @@ class Lowering:
         self._cur_extents = ()
         by_sid = {s.sid: s for s in self.stmts}
         # ---- globals, in statement order (parents first thanks to the topological order)
-        scalar_params = [s for s in self.stmt_order if s.kind == "param" and not s.is_gq and not s.loops]
+        # (label, statement, loop-variable substitution): scalar parameters, plus the elements of small parameter
+        # vectors that observation statements reference with constant subscripts (beta[1] * z[i, 1] + ...)
+        vec = self._vector_globals()
+        gitems = []
+        for s in self.stmt_order:
+            if s.kind != "param" or s.is_gq:
+                continue
+            if not s.loops:
+                gitems.append((self._labels_for(s)[0], s, {}, 0))
+            elif s.sid in vec:
+                lv = _grids(s.extents, s.loop_vars)
+                vals = [np.broadcast_to(lv[v], s.shape).ravel() for v in s.loop_vars]
+                for k, lab in enumerate(self._labels_for(s)):
+                    gitems.append((lab, s, {v: Num(float(vals[d][k]), True) for d, v in enumerate(s.loop_vars)}, k))
         scalar_logicals = [s for s in self.stmt_order if s.kind == "logical" and not s.is_gq and not s.loops]
-        for s in scalar_params:
-            self._gval_ids[s.name] = len(self._gval_ids)
+        for lab, s, sub, k in gitems:
+            if lab in self._gval_ids:
+                raise LoweringError(f"'{lab}' is defined twice")
+            self._gval_ids[lab] = len(self._gval_ids)
         # scalar logical nodes of globals -> gtape (appended after the globals)
         self._gtape_pending = scalar_logicals
-        for s in scalar_params:
+        for lab, s, sub, k in gitems:
             fam = self._family(s.node.dist)
-            tr, lb, ub = self._transform_of(fam, s.node.dist.args)
-            self.plan.globals.append(P.Global(s.name, int(self.theta_index(s)), tr, fam, [], lb, ub))
+            dargs = [_subst(a, sub) for a in s.node.dist.args]
+            tr, lb, ub = self._transform_of(fam, dargs)
+            self.plan.globals.append(P.Global(lab, int(self.theta_index(s).ravel()[k]), tr, fam, [], lb, ub))
         for s in scalar_logicals:
-            self._emit_gtape(s.name, s.node.rhs)
-        for g, s in zip(self.plan.globals, scalar_params):
-            g.args = [self._scalar_arg(a, (), (), ()) for a in s.node.dist.args]
+            self._emit_gtape(self._labels_for(s)[0], s.node.rhs)
+        for g, (lab, s, sub, k) in zip(self.plan.globals, gitems):
+            g.args = [self._scalar_arg(_subst(a, sub), (), (), ()) for a in s.node.dist.args]
         # ---- plates: one per observed stochastic statement
-        used_locals = set()
-        for s in self.stmt_order:
-            if s.kind == "obs":
+        used_locals = set(vec)
+        merged = set()
+        obs_stmts = [s for s in self.stmt_order if s.kind == "obs"]
+        for s in obs_stmts:
+            if s.sid in merged:
+                continue
+            sibs = self._siblings(s, [t for t in obs_stmts if t.sid not in merged and t.sid != s.sid])
+            if sibs:
+                merged.update(t.sid for t in sibs)
+                pl = self._build_merged_plate([s] + sibs, used_locals)
+            else:
                 pl = self._build_plate(s, used_locals)
-                if pl is not None:
-                    self.plan.plates.append(pl)
+            if pl is not None:
+                self.plan.plates.append(pl)
         # parameter statements in loops that no observation plate consumed -> prior-only plates
         for s in self.stmt_order:
             if s.kind == "param" and not s.is_gq and s.loops and s.sid not in used_locals:
@@ -688,6 +778,8 @@ class Lowering:
             return P.Arg.const(float(self.de.ev(e, {})))
         if isinstance(e, Var):
             return P.Arg.gval(self._gval_of(e.name))
+        if isinstance(e, Index) and self._elem_label(e) is not None:
+            return P.Arg.gval(self._gval_of(self._elem_label(e)))
         if isinstance(e, Neg):
             return self._gpush(P.OP_NEG, self._gexpr(e.a))
         if isinstance(e, BinOp):
@@ -704,6 +796,18 @@ class Lowering:
     def _build_plate(self, s: Stmt, used_locals) -> P.Plate:
         if len(s.loops) > 2:
             raise LoweringError("observation plates deeper than two loops are outside the plate class")
+        if len(s.loops) == 2:
+            # random effects indexed by the INNER loop variable only (Equiv: for k { for i { ... delta[i] } }):
+            # the sum over the plate does not depend on the loop order, so the plate is built with the loops
+            # swapped; the theta layout comes from the parameters' own statements and is not affected
+            try:
+                _, _, _, _, eta = self._peel(s)
+                firsts = {ref[2][0].name for ref in self._linearize(eta, s.loop_vars).terms
+                          if ref[0] == "l" and ref[2] and isinstance(ref[2][0], Var)}
+            except LoweringError:
+                firsts = set()
+            if firsts == {s.loop_vars[1]}:
+                s = replace(s, loops=s.loops[::-1], extents=s.extents[::-1])
         lv_names = s.loop_vars
         shape = s.shape
         self._cur_extents = s.extents
@@ -754,6 +858,140 @@ class Lowering:
             plate.terms.append(P.Term(P.Arg.local(li), self._data_arg(cov, lv_names, shape, lv_names)))
         if lin.const is not None:
             c = self._data_arg(lin.const, lv_names, shape, lv_names)
+            if not (c.kind == P.ARG_CONST and c.value == 0.0):
+                plate.terms.append(P.Term(P.Arg.const(1.0), c))
+        return plate
+
+    # ---- several observation statements of one loop sharing their random effects (Blockers: rc[i], rt[i]) ----------
+    def _peel(self, s: Stmt):
+        """(family, eta_arg, inlined args, link ops innermost-first, predictor expression) of an observation."""
+        fam = self._family(s.node.dist)
+        eta_arg = {P.FAM_GAMMA: 1}.get(fam, 0)
+        args = [self._inline(a) for a in s.node.dist.args]
+        eta = args[eta_arg]
+        link = []
+        while isinstance(eta, Call) and eta.fn in P.LINK_OF and len(eta.args) == 1 \
+                and not self._is_data(eta, s.loop_vars):
+            link.append(P.LINK_OF[eta.fn])
+            eta = eta.args[0]
+        return fam, eta_arg, args, link[::-1], eta
+
+    def _local_refs(self, s: Stmt):
+        try:
+            _, _, _, _, eta = self._peel(s)
+            if isinstance(eta, Call) and eta.fn == "inprod":
+                return set()
+            return {ref[1] for ref in self._linearize(eta, s.loop_vars).terms if ref[0] == "l"}
+        except LoweringError:
+            return set()
+
+    def _siblings(self, s: Stmt, others):
+        """observation statements of the same single loop, family and link as `s` that share a local with it
+        (transitively): they become the columns of one N x K plate, so that each shared local is read once."""
+        if len(s.loops) != 1:
+            return []
+        mine = self._local_refs(s)
+        if not mine:
+            return []
+        fam, _, _, link, _ = self._peel(s)
+        sibs = []
+        grew = True
+        while grew:
+            grew = False
+            for t in others:
+                if t in sibs or t.loops != s.loops:
+                    continue
+                refs = self._local_refs(t)
+                if not (refs & mine):
+                    continue
+                tf, _, _, tl, _ = self._peel(t)
+                if tf != fam or tl != link:
+                    raise LoweringError(f"'{s.name}' and '{t.name}' share a random effect but differ in family or link")
+                sibs.append(t)
+                mine |= refs
+                grew = True
+        return sibs
+
+    def _columns_arg(self, key, cols, N) -> P.Arg:
+        """an argument that takes the value cols[k][i] in column k: CONST, DATA_J (constant in i), DATA_I
+        (identical columns) or DATA_IJ."""
+        K = len(cols)
+        M = np.empty((N, K), dtype=np.float64)
+        for k, c in enumerate(cols):
+            M[:, k] = np.broadcast_to(np.asarray(c, dtype=np.float64), (N,))
+        if N and np.all(M == M[0:1, :]):
+            row = M[0]
+            if np.all(row == row[0]):
+                return P.Arg.one() if row[0] == 1.0 else P.Arg.const(float(row[0]))
+            return P.Arg(P.ARG_DATA_J, self._slot(key + "|J", row.copy()))
+        if np.all(M == M[:, 0:1]):
+            return P.Arg(P.ARG_DATA_I, self._slot(key + "|I", M[:, 0].copy()))
+        return P.Arg(P.ARG_DATA_IJ, self._slot(key + "|IJ", M.ravel(order="F"), rank=2, dim0=N))
+
+    def _build_merged_plate(self, stmts, used_locals) -> P.Plate:
+        s0 = stmts[0]
+        lv_names = s0.loop_vars
+        self._cur_extents = s0.extents
+        N, K = s0.shape[0], len(stmts)
+        lv = _grids(s0.extents, lv_names)
+        fam, eta_arg, _, link, _ = self._peel(s0)
+        if fam in (P.FAM_UNIFORM, P.FAM_BETA, P.FAM_FLAT):
+            raise LoweringError(f"{s0.node.dist.fn} as an observation family is outside the plate class")
+        names = "+".join(t.name for t in stmts)
+        plate = P.Plate(N=N, T=K, family=fam, eta_arg=eta_arg, name=f"{names}~{s0.node.dist.fn}")
+        plate.link = link
+        peeled = [self._peel(t) for t in stmts]
+
+        def ev(e):
+            return np.broadcast_to(np.asarray(self.de.ev(e, lv), dtype=np.float64), (N,))
+
+        ycols = []
+        for t in stmts:
+            lhs = t.node.lhs
+            ycols.append(ev(lhs if isinstance(lhs, Index) else Var(lhs.name)))
+        plate.y = self._columns_arg(f"merged|y|{names}", ycols, N)
+        if plate.y.kind in (P.ARG_CONST, P.ARG_ONE, P.ARG_DATA_J):
+            # keep the general addressing: observations always vary over the plate
+            plate.y = P.Arg(P.ARG_DATA_IJ, self._slot(f"merged|y|{names}|IJ", np.stack(ycols, 1).ravel(order="F"),
+                                                      rank=2, dim0=N))
+        aux = []
+        for q in range(P.FAMILY_NARGS[fam]):
+            if q == eta_arg:
+                aux.append(P.ZERO_ARG)
+                continue
+            exprs = [p[2][q] for p in peeled]
+            if all(self._is_data(e, lv_names) for e in exprs):
+                aux.append(self._columns_arg(f"merged|aux{q}|{names}", [ev(e) for e in exprs], N))
+            else:
+                a0 = self._scalar_arg(exprs[0], lv_names, s0.shape, lv_names)
+                for e in exprs[1:]:
+                    a = self._scalar_arg(e, lv_names, s0.shape, lv_names)
+                    if (a.kind, a.id, a.value) != (a0.kind, a0.id, a0.value):
+                        raise LoweringError("merged observation statements must share their non-data arguments")
+                aux.append(a0)
+        plate.aux = aux
+        lins = [self._linearize(p[4], lv_names) for p in peeled]
+        refs = []
+        for lin in lins:
+            for ref in lin.terms:
+                if ref not in refs:
+                    refs.append(ref)
+        zero = np.zeros(N)
+
+        def cov_cols(ref):
+            return [ev(lin.terms[ref]) if ref in lin.terms else zero for lin in lins]
+
+        for ref in [r for r in refs if r[0] == "g"]:
+            plate.terms.append(P.Term(P.Arg.gval(self._gval_of(ref[1])),
+                                      self._columns_arg(f"merged|cov|{names}|{ref[1]}", cov_cols(ref), N)))
+        for ref in [r for r in refs if r[0] != "g"]:
+            owner = next(t for t, lin in zip(stmts, lins) if ref in lin.terms)
+            li = self._local_index(plate, owner, ref, used_locals)
+            plate.terms.append(P.Term(P.Arg.local(li),
+                                      self._columns_arg(f"merged|cov|{names}|{ref[1]}", cov_cols(ref), N)))
+        if any(lin.const is not None for lin in lins):
+            c = self._columns_arg(f"merged|offset|{names}",
+                                  [ev(lin.const) if lin.const is not None else zero for lin in lins], N)
             if not (c.kind == P.ARG_CONST and c.value == 0.0):
                 plate.terms.append(P.Term(P.Arg.const(1.0), c))
         return plate

@@ -123,8 +123,6 @@ def set_evaluation_mode(model: BUGSModel, mode: EvaluationMode) -> BUGSModel:
     if not isinstance(mode, UseCUDABatch):
         raise NotImplementedError(
             f"{type(mode).__name__}: only UseCUDABatch is provided (the CPU modes are the reference's own)")
-    if not model.transformed and False:
-        pass
     m = copy.copy(model)
     m.evaluation_mode = mode
     m._cuda = None

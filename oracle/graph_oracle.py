@@ -168,6 +168,10 @@ class Evaluator:
         if fn == "mean":
             xs = list(np.asarray(a[0], dtype=object).ravel())
             return _sum(xs) / len(xs)
+        if fn == "sd":  # BUGSPrimitives/functions.jl:132-134: Statistics.std (corrected, n - 1)
+            xs = list(np.asarray(a[0], dtype=object).ravel())
+            m = _sum(xs) / len(xs)
+            return M.sqrt(_sum([(x - m) * (x - m) for x in xs]) / (len(xs) - 1))
         if fn == "inprod":  # functions.jl:33-35: dot product
             xs = list(np.asarray(a[0], dtype=object).ravel())
             ys = list(np.asarray(a[1], dtype=object).ravel())

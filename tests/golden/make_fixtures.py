@@ -117,6 +117,9 @@ def value(src):
     m = re.fullmatch(r"fill\(\s*([^,]+),\s*(\d+)\s*\)", src)
     if m:
         return [number(m.group(1))] * int(m.group(2))
+    m = re.fullmatch(r"zeros\(\s*(?:\w+\s*,\s*)?(\d+)\s*\)", src)
+    if m:
+        return [0] * int(m.group(1))
     if src.startswith("["):
         body = src[1:-1]
         if "," in body and not re.search(r"\d\s+[-\d.m]", body.replace(",", " , ").replace(" , ", ",")):

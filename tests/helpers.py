@@ -11,6 +11,12 @@ ZOO = [
     ("pumps", ex.PUMPS, "pumps", "inits"),
     ("epil", ex.EPIL, "epil", "inits"),
     ("dogs", ex.DOGS, "dogs", "inits"),
+    ("blockers", ex.BLOCKERS, "blockers", "inits"),   # two observation statements sharing mu[i] -> one N x 2 plate
+    ("oxford", ex.OXFORD, "oxford", "inits"),         # same, with per-statement global covariates
+    ("salm", ex.SALM, "salm", "inits"),
+    ("equiv", ex.EQUIV, "equiv", "inits"),            # random effect indexed by the inner loop variable
+    ("dyes", ex.DYES, "dyes", "inits"),
+    ("stacks", ex.STACKS, "stacks", "inits"),         # beta[1], beta[2], beta[3] referenced element by element
 ]
 
 

@@ -94,6 +94,16 @@ def test_scalar_logical_nodes_gtape():
     _check(m.cuda, _oracle(m.plan), theta)
 
 
+@pytest.mark.parametrize("N,C", [(17, 5), (3001, 70)])
+def test_sibling_observation_statements(N, C):
+    """several observation statements sharing their random effects -> one N x K plate (Blockers pattern)."""
+    from test_lowering import SIBLINGS, siblings_data
+    m = jbugs.compile(SIBLINGS, siblings_data(N))
+    assert len(m.plan.plates) == 1 and m.plan.plates[0].T == 3
+    theta = random_thetas(np.zeros(m.plan.D), C, seed=3, scale=0.4)
+    _check(m.cuda, _oracle(m.plan), theta)
+
+
 def test_empty_plate_and_priors_only():
     data = {"x": np.array([8.0, 15, 22, 29, 36]), "xbar": 22.0, "N": 0, "T": 5, "Y": np.zeros((0, 5))}
     m = jbugs.compile(jbugs.examples.RATS, data)

@@ -52,12 +52,19 @@ def test_examples_match_oracle(fixtures, name, text, fx, ini, dynamic):
     assert np.max(np.abs(g[:, 0] - g_g) / np.maximum(np.abs(g_g), 1e-6 * np.abs(g_g).max())) < 1e-9
 
 
-def test_rats_golden_logjoint(fixtures):
-    """the reference's own known answer (test/model/evaluation.jl:356-360, rtol 1e-6 there)."""
-    m = jbugs.compile(jbugs.examples.RATS, fixtures["rats"]["data"], fixtures["rats"]["inits"])
+@pytest.mark.parametrize("name,text,tol", [("rats", jbugs.examples.RATS, 1e-10), ("dogs", jbugs.examples.DOGS, 1e-10),
+                                           ("blockers", jbugs.examples.BLOCKERS, 1e-6)])
+@pytest.mark.parametrize("transformed", [True, False])
+def test_golden_logjoint(fixtures, name, text, tol, transformed):
+    """the reference's own known answers at the example inits (test/model/evaluation.jl:14-33,355-379, rtol 1e-6
+    there; the Blockers constant is only good to 1.5e-8, see tests/test_oracle_goldens.py)."""
+    fx = fixtures[name]
+    m = jbugs.compile(text, fx["data"], fx["inits"])
+    if not transformed:
+        m = jbugs.settrans(m, False)
     lp = jbugs.LogDensityProblems.logdensity(m, jbugs.getparams(m))
-    gold = fixtures["rats"]["golden_logjoint"]["transformed"]
-    assert abs(lp - gold) < 1e-10 * abs(gold)
+    gold = fx["golden_logjoint"]["transformed" if transformed else "untransformed"]
+    assert abs(lp - gold) <= tol * abs(gold), (lp, gold)
 
 
 @pytest.mark.parametrize("N,C", [(1000, 64), (10000, 33)])
