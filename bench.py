@@ -311,9 +311,11 @@ def main():
         dist.barrier()
     tw1 = time.time()
     # per-kernel time of the dominant (plate) kernel: the library's own CUDA events on the launch stream
+    cp.set_option("timing", 1)
     for _ in range(min(K, 5)):
         step(0)
         plate_ms.append(cp.last_timing()[0])
+    cp.set_option("timing", 0)
     clocks = sampler.stop(tw0, tw1)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)

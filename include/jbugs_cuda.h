@@ -126,8 +126,10 @@ int jbugs_plan_describe(const jbugs_plan* plan, char* buf, size_t nbuf);
 /* Tuning knobs (tests force the generic interpreter path with "dynamic=1"). Unknown keys fail. */
 int jbugs_plan_set_option(jbugs_plan* plan, const char* key, int64_t value);
 
-/* Device-side timing of the last jbugs_eval_batch on this plan: milliseconds spent in the plate
- * kernels and in total between the first and last enqueue (CUDA events on the call's stream). */
+/* Device-side timing of the last synchronous jbugs_eval_batch on this plan: milliseconds spent in the
+ * plate kernels and in total between the first and last enqueue (CUDA events on the call's stream).
+ * Recorded only after jbugs_plan_set_option(plan, "timing", 1); off by default because the four
+ * event records are a measurable share of a small model's evaluation. */
 int jbugs_last_timing(const jbugs_plan* plan, float* plate_ms, float* total_ms);
 
 /* ---- on-device batched HMC (the caller of the hot path) ---------------------------------------

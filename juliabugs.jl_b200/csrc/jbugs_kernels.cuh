@@ -106,6 +106,7 @@ struct DynSpec {
     static constexpr int MIN_BLOCKS = 2;
     static constexpr int T_STATIC = 0;  // inner extent read at run time
     static constexpr bool PREFETCH = false;
+    static constexpr bool OBS_LOCALS = true;  // unknown at compile time
     __device__ __forceinline__ bool prior_fused(int) const { return false; }
     const PlateShape& s;
     __device__ __forceinline__ explicit DynSpec(const PlateShape& sh) : s(sh) {}
@@ -141,6 +142,12 @@ struct StaticSpec {
     static constexpr int MIN_BLOCKS = Desc::MIN_BLOCKS;
     static constexpr int T_STATIC = Desc::T_STATIC;  // > 0: inner loop fully unrolled
     static constexpr bool PREFETCH = Desc::PREFETCH; // theta loads of the next U-block issued before this one is evaluated
+    static constexpr bool obs_locals_() {
+        for (int l = 0; l < Desc::sh().nl; ++l)
+            if (Desc::sh().loc[l].level == JBUGS_LEVEL_OBS) return true;
+        return false;
+    }
+    static constexpr bool OBS_LOCALS = obs_locals_();  // the plate has observation-level (i, j) locals
     // a dnorm prior whose arguments do not vary over the plate keeps sufficient statistics
     __device__ __forceinline__ constexpr bool prior_fused(int l) const {
         return Desc::sh().loc[l].family == JBUGS_FAM_NORMAL &&
@@ -188,7 +195,14 @@ struct ChainState {
     double ga[MAX_GREF];  // their adjoints
     double lx[MAX_LOC];   // constrained local values
     double la[MAX_LOC];   // their adjoints
+    // dgamma(a, b) priors of locals whose arguments do not vary over the plate: lgamma(a), digamma(a), log(b) are
+    // computed once per chain instead of once per group
+    double pre_lg[MAX_LOC], pre_dg[MAX_LOC], pre_lb[MAX_LOC];
 };
+
+__device__ __forceinline__ bool arg_invariant(ArgS s) {
+    return s.kind == JBUGS_ARG_GVAL || s.kind == JBUGS_ARG_CONST || s.kind == JBUGS_ARG_ONE;
+}
 
 // where the staged data of the current chunk lives (shared memory)
 struct StageView {
@@ -220,6 +234,10 @@ __device__ __forceinline__ void arg_adjoint(ArgS s, ChainState& st, double d) {
 struct GlobalsParams {
     int n_globals, n_gtape, transformed;
     jbugs_global g[MAX_GVALS];
+    // priors whose arguments are literal constants: the argument-only part of the log-density is computed once on
+    // the host (cst); fast = family code + 1 when that shortcut applies, else 0
+    double cst[MAX_GVALS];
+    unsigned char fast[MAX_GVALS];
 };
 struct GTapeParams {
     jbugs_gop op[MAX_GVALS];
@@ -246,19 +264,34 @@ __device__ __forceinline__ bool gtape_forward(const jbugs_gop& o, const double* 
 }
 
 #ifdef JBUGS_HOST_TU  // the non-template kernels are compiled once, in the host translation unit
+// Thread-per-chain helper kernels run with very few warps per SM, so a load whose result is consumed right away
+// costs a full memory round trip each time (the warp issues in order).  `batched_load` issues eight independent
+// loads before the first use; the index is clamped instead of predicated so that the loads stay unconditional.
+template <typename AddrFn>
+__device__ __forceinline__ void batched_load(double* __restrict__ dst, int n, AddrFn addr) {
+#pragma unroll 1
+    for (int k0 = 0; k0 < n; k0 += 8) {
+        double t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = *addr(min(k0 + u, n - 1));
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (k0 + u < n) dst[k0 + u] = t[u];
+    }
+}
+
 __global__ void __launch_bounds__(BLOCK)
 prologue_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__ GTapeParams TP,
                 const double* __restrict__ theta, long long ld, long long C, double* __restrict__ gvals,
                 long long ldg, int* __restrict__ flags, int* __restrict__ any_bad) {
-    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     if (c == 0) *any_bad = 0;
     double gv[MAX_GVALS];
     bool bad = false;
-    for (int h = 0; h < G.n_globals; ++h) {
-        const TrOut t = transform_eval((int)G.g[h].transform, G.g[h].lb, G.g[h].ub, theta[G.g[h].theta_idx * ld + c]);
-        gv[h] = t.x;
-    }
+    batched_load(gv, G.n_globals, [&](int h) { return theta + G.g[h].theta_idx * ld + c; });
+    for (int h = 0; h < G.n_globals; ++h)
+        gv[h] = transform_eval((int)G.g[h].transform, G.g[h].lb, G.g[h].ub, gv[h]).x;
     for (int k = 0; k < G.n_gtape; ++k) {
         double v, d1, d2;
         bad |= gtape_forward(TP.op[k], gv, v, d1, d2);
@@ -301,32 +334,42 @@ finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
     // mode 1: observation-sharded, first half: write this rank's reduced partials red[0] = logp part,
     //         red[1 + k] = adjoint of global value k, red[1 + NG] = DomainError flag; the host all-reduces `red`.
     // mode 2: second half: read the all-reduced `red`, add the priors of the globals ONCE, finish.
-    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const int H = G.n_globals, NG = G.n_globals + G.n_gtape;
-    double gv[MAX_GVALS], ga[MAX_GVALS];
-    for (int k = 0; k < NG; ++k) {
-        gv[k] = gvals[k * ldg + c];
-        ga[k] = 0.0;
-    }
+    double gv[MAX_GVALS], ga[MAX_GVALS], th[MAX_GVALS];
+    batched_load(gv, NG, [&](int k) { return gvals + k * ldg + c; });
+    if (mode != 1) batched_load(th, H, [&](int h) { return theta + G.g[h].theta_idx * ld + c; });
+    for (int k = 0; k < NG; ++k) ga[k] = 0.0;
     double lp = 0.0;
     bool bad = flags[c] != 0;
     if (mode == 2) {
         lp = red[c];
-        for (int k = 0; k < NG; ++k) ga[k] = red[(long long)(1 + k) * ldg + c];
+        batched_load(ga, NG, [&](int k) { return red + (long long)(1 + k) * ldg + c; });
         bad = red[(long long)(1 + NG) * ldg + c] != 0.0;
     }
     for (int p = 0; p < (mode == 2 ? 0 : F.n_plates); ++p) {
         const PlateFinal& pf = F.p[p];
         const long long stride = (long long)(1 + pf.n_gref) * ldg;
         const double* base = partial + pf.offset * ldg + c;
-        double s = 0.0;
-        for (int t = 0; t < pf.n_tiles; ++t) s += base[t * stride];
-        lp += s + pf.obs_const;
-        for (int k = 0; k < pf.n_gref; ++k) {
-            double a = 0.0;
-            for (int t = 0; t < pf.n_tiles; ++t) a += base[t * stride + (long long)(1 + k) * ldg];
-            ga[pf.gref[k]] += a;
+        const int nt = pf.n_tiles;
+        // row 0 = log-density partials, row 1 + k = adjoint of the k-th referenced global value; tiles are added
+        // in ascending order, sixteen loads in flight at a time
+#pragma unroll 1
+        for (int row = 0; row <= pf.n_gref; ++row) {
+            const double* src = base + (long long)row * ldg;
+            double s = 0.0;
+#pragma unroll 1
+            for (int t0 = 0; t0 < nt; t0 += 16) {
+                double v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = src[min(t0 + u, nt - 1) * stride];
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                    if (t0 + u < nt) s += v[u];
+            }
+            if (row == 0) lp += s + pf.obs_const;
+            else ga[pf.gref[row - 1]] += s;
         }
     }
     if (mode == 1) {
@@ -338,6 +381,18 @@ finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
     flags[c] = bad ? 1 : 0;  // (mode 2: the flag now reflects every rank's shard)
     for (int h = 0; h < H; ++h) {
         const jbugs_global& g = G.g[h];
+        if (G.fast[h] == JBUGS_FAM_NORMAL + 1) {  // dnorm(m, t), literals: cst = (log t - log 2 pi) / 2
+            const double r = gv[h] - g.args[0].value;
+            lp += fma(-0.5 * g.args[1].value * r, r, G.cst[h]);
+            ga[h] -= g.args[1].value * r;
+            continue;
+        }
+        if (G.fast[h] == JBUGS_FAM_GAMMA + 1) {  // dgamma(a, b), literals: cst = a log b - lgamma(a)
+            const double x = gv[h], a = g.args[0].value, b = g.args[1].value;
+            lp += x < 0.0 ? -dev_inf() : (G.cst[h] + xlogy(a - 1.0, x) - b * x);
+            ga[h] += (a - 1.0) / x - b;
+            continue;
+        }
         FamOut o;
         bad |= fam_eval((int)g.family, gv[h], garg(g.args[0], gv), garg(g.args[1], gv), o);
         lp += o.lp;
@@ -355,7 +410,7 @@ finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
     }
     for (int h = 0; h < H; ++h) {
         const jbugs_global& g = G.g[h];
-        const TrOut t = transform_eval((int)g.transform, g.lb, g.ub, theta[g.theta_idx * ld + c]);
+        const TrOut t = transform_eval((int)g.transform, g.lb, g.ub, th[h]);
         lp += t.lj;
         if (want_grad) grad[g.theta_idx * ld + c] = ga[h] * t.dxdy + t.dljdy;
     }

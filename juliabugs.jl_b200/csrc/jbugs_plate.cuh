@@ -144,6 +144,15 @@ __device__ __forceinline__ bool local_prior(const S& sp, const PlateVals& V, int
         st.la[l] -= a1 * d;
         return false;
     }
+    if (sp.loc_family(l) == JBUGS_FAM_GAMMA && arg_invariant(sp.loc_arg(l, 0)) && arg_invariant(sp.loc_arg(l, 1))) {
+        // dgamma(a, b), chain-invariant arguments: the argument-only terms were hoisted (plate_kernel prologue)
+        const double x = st.lx[l], lx = log(x);
+        lp += x < 0.0 ? -dev_inf() : (fma(a0, st.pre_lb[l], -st.pre_lg[l]) + (a0 == 1.0 ? 0.0 : (a0 - 1.0) * lx) - a1 * x);
+        st.la[l] += (a0 - 1.0) / x - a1;
+        arg_adjoint(sp.loc_arg(l, 0), st, st.pre_lb[l] - st.pre_dg[l] + lx);
+        arg_adjoint(sp.loc_arg(l, 1), st, a0 / a1 - x);
+        return !(a0 > 0.0) || !(a1 > 0.0);
+    }
     FamOut o;
     const bool bad = fam_eval(sp.loc_family(l), st.lx[l], a0, a1, o);
     lp += o.lp;
@@ -242,22 +251,34 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
     return bad;
 }
 
-// raw theta values (and row offsets) of the group-level locals of UU consecutive groups
-template <int UU>
+// raw theta values (and row offsets) of the group-level locals of UU consecutive groups; when the inner extent is
+// a small compile-time constant (TS > 0) the observation-level locals of those groups as well, so that no theta
+// load sits right in front of its first use
+template <int UU, int TS = 0>
 struct GroupLoads {
     double raw[UU][MAX_LOC];
     long long off[UU][MAX_LOC];  // element offset of the slot's row: slot * ld
+    double oraw[UU][MAX_LOC][TS > 0 ? TS : 1];
+    long long obase[UU][MAX_LOC];  // offset of (i, j = 0); j advances by step_j
+};
+
+// observation-level locals are preloaded with their group when the inner extent is static and small
+template <class S>
+struct PreObs {
+    static constexpr int TS = (S::OBS_LOCALS && S::T_STATIC > 0 && S::T_STATIC <= 8) ? S::T_STATIC : 0;
 };
 
 // issue the theta loads of groups i .. i+UU-1.  `pos[l]` walks the affine slot map incrementally
 // (row0 + step_i * i, in elements), so calls must come in ascending group order.
 template <class S, int UU>
 __device__ __forceinline__ void load_groups(const S& sp, const PlateVals& V, long long i, const double* __restrict__ th,
-                                            long long ld, long long (&pos)[MAX_LOC], GroupLoads<UU>& gl) {
+                                            long long ld, long long (&pos)[MAX_LOC],
+                                            GroupLoads<UU, PreObs<S>::TS>& gl) {
+    constexpr int TS = PreObs<S>::TS;
 #pragma unroll
     for (int u = 0; u < UU; ++u)
 #pragma unroll
-        for (int l = 0; l < MAX_LOC; ++l)
+        for (int l = 0; l < MAX_LOC; ++l) {
             if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) {
                 if (sp.loc_has_idx(l)) {
                     gl.off[u][l] = local_slot(sp, V, l, i + u, 0) * ld;
@@ -267,6 +288,13 @@ __device__ __forceinline__ void load_groups(const S& sp, const PlateVals& V, lon
                 }
                 gl.raw[u][l] = th[gl.off[u][l]];
             }
+            if (TS > 0 && l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS && !sp.loc_has_idx(l)) {
+                gl.obase[u][l] = pos[l];
+                pos[l] += V.loc[l].step_i;
+#pragma unroll
+                for (int j = 0; j < TS; ++j) gl.oraw[u][l][j] = th[gl.obase[u][l] + j * V.loc[l].step_j];
+            }
+        }
 }
 
 // UU consecutive groups starting at chunk-local index g (global group index i), theta already loaded
@@ -274,7 +302,9 @@ template <class S, int UU>
 __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, const StageView& sv, int g, long long i,
                                             int T, const double* __restrict__ th, double* __restrict__ gr,
                                             long long ld, bool store, double obs_tau, long long (&pos)[MAX_LOC],
-                                            const GroupLoads<UU>& gl, ChainState& st, FusedAcc& fa, double& lp) {
+                                            const GroupLoads<UU, PreObs<S>::TS>& gl, ChainState& st, FusedAcc& fa,
+                                            double& lp) {
+    constexpr int TS = PreObs<S>::TS;
     bool bad = false;
     const double (&raw)[UU][MAX_LOC] = gl.raw;
     const long long (&off)[UU][MAX_LOC] = gl.off;
@@ -292,7 +322,7 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
 
         long long opos[MAX_LOC];
 #pragma unroll
-        for (int l = 0; l < MAX_LOC; ++l) opos[l] = pos[l];
+        for (int l = 0; l < MAX_LOC; ++l) opos[l] = (TS > 0 && !sp.loc_has_idx(l)) ? gl.obase[u][l] : pos[l];
 #pragma unroll(S::T_STATIC > 0 ? S::T_STATIC : 1)
         for (int j = 0; j < T; ++j) {
             long long ooff[MAX_LOC];
@@ -305,7 +335,8 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
                         ooff[l] = opos[l];
                         opos[l] += V.loc[l].step_j;
                     }
-                    local_enter(sp, V, l, th[ooff[l]], st, ldx, ldlj, lp);
+                    const double rawv = (TS > 0 && !sp.loc_has_idx(l)) ? gl.oraw[u][l][j < TS ? j : 0] : th[ooff[l]];
+                    local_enter(sp, V, l, rawv, st, ldx, ldlj, lp);
                 }
 #pragma unroll
             for (int l = 0; l < MAX_LOC; ++l)
@@ -323,7 +354,8 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
         }
 #pragma unroll
         for (int l = 0; l < MAX_LOC; ++l) {
-            if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) pos[l] += V.loc[l].step_i;
+            if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS && !(TS > 0 && !sp.loc_has_idx(l)))
+                pos[l] += V.loc[l].step_i;
             if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) {
                 if (S::FUSED == FUSED_NORMAL_IDENTITY) st.la[l] = fma(obs_tau, sl[l], st.la[l]);
                 if (store) gr[off[u][l]] = fma(st.la[l], ldx[l], ldlj[l]);
@@ -387,6 +419,17 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
         st.gv[k] = (k < sp.n_gref()) ? gvals[(long long)V.gref[k] * ldg + c] : 0.0;
         st.ga[k] = 0.0;
     }
+#pragma unroll
+    for (int l = 0; l < MAX_LOC; ++l)
+        if (l < sp.nl() && sp.loc_family(l) == JBUGS_FAM_GAMMA && arg_invariant(sp.loc_arg(l, 0)) &&
+            arg_invariant(sp.loc_arg(l, 1))) {
+            const ArgS s0 = sp.loc_arg(l, 0), s1 = sp.loc_arg(l, 1);
+            const double a0 = s0.kind == JBUGS_ARG_GVAL ? pick(st.gv, s0.id) : (s0.kind == JBUGS_ARG_ONE ? 1.0 : V.loc[l].args[0].value);
+            const double a1 = s1.kind == JBUGS_ARG_GVAL ? pick(st.gv, s1.id) : (s1.kind == JBUGS_ARG_ONE ? 1.0 : V.loc[l].args[1].value);
+            st.pre_lg[l] = lgamma(a0);
+            st.pre_dg[l] = digamma(a0);
+            st.pre_lb[l] = log(a1);
+        }
     FusedAcc fa;
     fa.ss = 0.0;
 #pragma unroll
@@ -413,7 +456,7 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
     next_bulk = false;
 
     int cur = 0;
-    GroupLoads<U> gl_cur;
+    GroupLoads<U, PreObs<S>::TS> gl_cur;
     bool have_cur = false;
     for (long long i0 = ib; i0 < ie; i0 += STAGE_G) {
         const long long rem = ie - i0;
@@ -434,7 +477,7 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
                 // software pipeline over U-blocks (also across staged chunks: the theta rows do not depend on the
                 // staged data): the loads of block i+U are in flight while block i is evaluated
                 if (!have_cur) load_groups<S, U>(sp, V, i, th, ld, pos, gl_cur);
-                GroupLoads<U> gl_nxt;
+                GroupLoads<U, PreObs<S>::TS> gl_nxt;
                 const bool more = i + 2 * U <= ie;
                 if (more) load_groups<S, U>(sp, V, i + U, th, ld, pos, gl_nxt);
                 bad |= eval_groups<S, U>(sp, V, sv, g, i, T, th, gr, ld, store, obs_tau, pos, gl_cur, st, fa, lp);
@@ -447,7 +490,7 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
         }
         if (U > 1)
             for (; g < cnt; ++g) {
-                GroupLoads<1> one;
+                GroupLoads<1, PreObs<S>::TS> one;
                 load_groups<S, 1>(sp, V, i0 + g, th, ld, pos, one);
                 bad |= eval_groups<S, 1>(sp, V, sv, g, i0 + g, T, th, gr, ld, store, obs_tau, pos, one, st, fa, lp);
             }

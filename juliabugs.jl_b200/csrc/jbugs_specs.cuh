@@ -32,6 +32,7 @@ cudaError_t launch_seeds(JBUGS_LAUNCH_PARAMS);
 cudaError_t launch_surgical(JBUGS_LAUNCH_PARAMS);
 cudaError_t launch_pumps(JBUGS_LAUNCH_PARAMS);
 cudaError_t launch_epil(JBUGS_LAUNCH_PARAMS);
+cudaError_t launch_epil_t4(JBUGS_LAUNCH_PARAMS);
 
 struct SpecEntry {
     const char* name;
@@ -51,6 +52,7 @@ static const SpecEntry g_specs[] = {
     {"rats_normal_identity", &launch_rats, &RatsDesc<0>::matches, RatsDesc<0>::FUSED},
     {"seeds_binomial_logit", &launch_seeds, &SeedsDesc::matches, SeedsDesc::FUSED},
     {"surgical_binomial_logit", &launch_surgical, &SurgicalDesc::matches, SurgicalDesc::FUSED},
+    {"epil_poisson_log_T4", &launch_epil_t4, &EpilDesc<4>::matches, EpilDesc<4>::FUSED},
     {"epil_poisson_log", &launch_epil, &EpilDesc<0>::matches, EpilDesc<0>::FUSED},
     {"pumps_poisson_gamma", &launch_pumps, &PumpsDesc::matches, PumpsDesc::FUSED},
 };

@@ -21,4 +21,5 @@ JB_DISPATCH(launch_seeds)
 JB_DISPATCH(launch_surgical)
 JB_DISPATCH(launch_pumps)
 JB_DISPATCH(launch_epil)
+JB_DISPATCH(launch_epil_t4)
 }  // namespace jbugs
