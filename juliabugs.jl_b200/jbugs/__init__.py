@@ -9,4 +9,4 @@ from .model import (  # noqa: F401
     UseGeneratedLogDensityFunction, UseGraph, compile, getparams, set_evaluation_mode, settrans,
 )
 from .cuda import CudaPlan, JBugsCudaError  # noqa: F401
-from . import dist, hmc  # noqa: F401,E402
+from . import dist, gq, hmc  # noqa: F401,E402

@@ -32,9 +32,31 @@ class Chains:
     samples: np.ndarray          # [n_samples, n_monitored, n_chains], constrained space
     accept_rate: float
     step_size: float
+    model: Optional[BUGSModel] = None
+    _gq: Optional[Dict[str, np.ndarray]] = None
 
     def __getitem__(self, name: str) -> np.ndarray:
-        return self.samples[:, self.names.index(name), :]
+        """draws of a monitored parameter ('tau', 'beta[2]') or of a generated quantity ('sigma', 'b0', 'outlier[21]'),
+        shape [n_samples, n_chains]."""
+        if name in self.names:
+            return self.samples[:, self.names.index(name), :]
+        gq = self.generated_quantities()
+        base, _, rest = name.partition("[")
+        if base in gq:
+            arr = gq[base]
+            if rest:
+                arr = arr[tuple(int(t) - 1 for t in rest.rstrip("]").split(","))]
+            return arr.reshape(self.samples.shape[0], self.samples.shape[2])
+        raise KeyError(name)
+
+    def generated_quantities(self, seed: int = 0) -> Dict[str, np.ndarray]:
+        """logical nodes outside the target and forward draws of unobserved stochastic leaves, computed from the
+        monitored parameters for every draw at once (reference: J/src/model/abstractmcmc.jl:92-110)."""
+        if self._gq is None:
+            from .gq import generated_quantities
+            draws = {n: self.samples[:, k, :].ravel() for k, n in enumerate(self.names)}
+            self._gq = generated_quantities(self.model.lowering, draws, seed=seed)
+        return self._gq
 
     def mean(self, name):
         return float(self[name].mean())
@@ -65,13 +87,24 @@ def _constrain(tr, lb, ub, y):
 def sample(model: BUGSModel, sampler: HMC, n_samples: int, n_adapts: int = 500, n_chains: int = 256, seed: int = 1234,
            monitor: Optional[Sequence[str]] = None, init: Optional[np.ndarray] = None) -> Chains:
     """`AbstractMCMC.sample(model, sampler, n_samples; n_adapts, ...)` for `n_chains` lock-step chains.
-    `monitor`: names of scalar (global) parameters to record; default: all of them."""
+    `monitor`: parameter labels to record ('tau', 'beta[2]', 'alpha[17]'); default: every scalar parameter."""
     L = load()
     _bind(L)
     cp = model.cuda
     names = [g.name for g in model.plan.globals] if monitor is None else list(monitor)
-    by_name = {g.name: g for g in model.plan.globals}
-    rows = np.array([by_name[n].theta_idx for n in names], dtype=np.int64)
+    by_name = {g.name: (g.theta_idx, g.transform, g.lb, g.ub) for g in model.plan.globals}
+    if any(n not in by_name for n in names):
+        # elements of plate-level parameters: slot from the theta map, bijector from the plate's local record
+        lw = model.lowering
+        slot = {lab: k for k, lab in enumerate(lw.param_names())}
+        tr = {l.name: (l.transform, l.lb, l.ub) for pl in model.plan.plates for l in pl.locals}
+        for n in names:
+            if n not in by_name:
+                base = n.partition("[")[0]
+                if n not in slot or base not in tr:
+                    raise KeyError(f"'{n}' is not a parameter of the model")
+                by_name[n] = (slot[n],) + tr[base]
+    rows = np.array([by_name[n][0] for n in names], dtype=np.int64)
     th0 = np.ascontiguousarray(getparams(model) if init is None else init, dtype=np.float64)
     th0 = np.where(np.isfinite(th0), th0, 0.0)
     h = ctypes.c_void_p()
@@ -88,6 +121,6 @@ def sample(model: BUGSModel, sampler: HMC, n_samples: int, n_adapts: int = 500, 
     finally:
         L.jbugs_hmc_destroy(h)
     for k, n in enumerate(names):
-        g = by_name[n]
-        out[:, k, :] = _constrain(g.transform, g.lb, g.ub, out[:, k, :])
-    return Chains(names, out, float(acc.value), float(eps.value))
+        _, tr_k, lb, ub = by_name[n]
+        out[:, k, :] = _constrain(tr_k, lb, ub, out[:, k, :])
+    return Chains(names, out, float(acc.value), float(eps.value), model)

@@ -52,3 +52,34 @@ def test_rats_posterior_matches_winbugs_reference(fixtures):
     # between-chain spread of the per-chain means: all chains found the same posterior
     assert alpha0.mean(axis=0).std() < 0.6
     assert 0.6 < ch.accept_rate < 0.95
+
+
+def test_stacks_posterior_matches_winbugs_reference(fixtures):
+    """Stacks, the third model of the reference's NUTS test (src/BUGSExamples/Volume_1/10_Stacks.jl:107-109):
+    b0 and outlier[21] are generated quantities, filled in for every draw by jbugs.gq."""
+    fx = fixtures["stacks"]
+    m = jbugs.compile(jbugs.examples.STACKS, fx["data"], fx["inits"])
+    ch = hmc.sample(m, hmc.HMC(n_leapfrog=16, step_size=0.05, jitter=0.05), n_samples=1000, n_adapts=1000, n_chains=256, seed=11)
+    b0, outlier = ch["b0"], ch["outlier[21]"]
+    assert b0.shape == (1000, 256)
+    assert b0.mean() == pytest.approx(-39.64, rel=0.05) and b0.std() == pytest.approx(12.63, rel=0.1)
+    assert outlier.mean() == pytest.approx(0.3324, rel=0.15) and outlier.std() == pytest.approx(0.4711, rel=0.1)
+    # the same quantity recomputed by hand from the monitored parameters
+    x = np.asarray(fx["data"]["x"], dtype=float)
+    sd, mean = x.std(axis=0, ddof=1), x.mean(axis=0)
+    by_hand = ch["beta0"] - sum(ch[f"beta[{j + 1}]"] / sd[j] * mean[j] for j in range(3))
+    assert np.allclose(b0, by_hand, rtol=1e-12)
+
+
+def test_monitoring_plate_level_parameters(fixtures):
+    """labels of plate-level parameters are monitored through the theta map and the local's bijector."""
+    fx = fixtures["pumps"]
+    m = jbugs.compile(jbugs.examples.PUMPS, fx["data"], fx["inits"])
+    ch = hmc.sample(m, hmc.HMC(n_leapfrog=16, step_size=0.05), n_samples=500, n_adapts=500, n_chains=128, seed=5,
+                    monitor=["alpha", "beta", "theta[1]", "theta[10]"])
+    # posterior means of the classic BUGS manual for Pumps (the reference ships no reference_results for it):
+    # theta[1] 0.0598 +- 0.0253, theta[10] 1.99 +- 0.43, alpha 0.70 +- 0.27, beta 0.93 +- 0.54
+    assert ch["theta[1]"].min() > 0.0
+    assert ch.mean("theta[1]") == pytest.approx(0.0598, rel=0.1)
+    assert ch.mean("theta[10]") == pytest.approx(1.99, rel=0.1)
+    assert ch.mean("alpha") == pytest.approx(0.70, rel=0.15) and ch.mean("beta") == pytest.approx(0.93, rel=0.2)

@@ -1,0 +1,95 @@
+"""Generated quantities computed for all draws at once (jbugs/gq.py) against the per-node oracle's environment and
+against the defining formulas (reference: J/src/model/abstractmcmc.jl:92-110, evaluation.jl:354-378)."""
+import numpy as np
+import pytest
+
+import graph_oracle as go
+import jbugs
+from jbugs import examples as ex
+from jbugs.gq import generated_quantities
+
+
+def _draws_from_thetas(gm, thetas):
+    """constrained parameter values per label for S points theta (columns), through the oracle's own env."""
+    names = gm.param_names()
+    vals = {n: [] for n in names}
+    envs = []
+    for c in range(thetas.shape[1]):
+        env, _ = gm.evaluate_with_values(thetas[:, c])
+        envs.append(env)
+        for n in names:
+            base, _, rest = n.partition("[")
+            v = env[base]
+            if rest:
+                v = v[tuple(int(t) - 1 for t in rest.rstrip("]").split(","))]
+            vals[n].append(float(v))
+    return {n: np.asarray(v) for n, v in vals.items()}, envs
+
+
+@pytest.mark.parametrize("name,text,nodes", [
+    ("rats", ex.RATS, ["mu"]),
+    ("seeds", ex.SEEDS, ["p"]),
+    ("epil", ex.EPIL, ["mu"]),
+    ("stacks", ex.STACKS, ["mu"]),
+])
+def test_logical_nodes_match_the_node_loop(fixtures, name, text, nodes):
+    fx = fixtures[name]
+    gm = go.compile(text, fx["data"], fx["inits"]).use_generated_order()
+    lw = jbugs.Lowering(text, fx["data"])
+    th0 = gm.getparams()
+    th0 = np.where(np.isfinite(th0), th0, 0.0)
+    rng = np.random.default_rng(0)
+    thetas = th0[:, None] + 0.05 * rng.standard_normal((gm.D, 3))
+    draws, envs = _draws_from_thetas(gm, thetas)
+    out = generated_quantities(lw, draws, only_gq=False)
+    for nd in nodes:
+        for c, env in enumerate(envs):
+            ref = np.asarray(env[nd], dtype=np.float64)
+            got = out[nd][..., c]
+            mask = ~np.isnan(ref)
+            assert np.allclose(got[mask], ref[mask], rtol=1e-13, atol=0), (name, nd)
+
+
+def test_rats_generated_quantities_follow_their_definitions(fixtures):
+    fx = fixtures["rats"]
+    lw = jbugs.Lowering(ex.RATS, fx["data"])
+    rng = np.random.default_rng(1)
+    S = 50
+    draws = {"tau.c": rng.gamma(2.0, 0.02, S), "alpha.c": rng.normal(240, 3, S), "beta.c": rng.normal(6, 0.1, S)}
+    out = generated_quantities(lw, draws)
+    assert set(out) == {"sigma", "alpha0"}          # exactly the nodes the reference excludes from the target
+    assert np.allclose(out["sigma"], 1.0 / np.sqrt(draws["tau.c"]), rtol=1e-15)
+    assert np.allclose(out["alpha0"], draws["alpha.c"] - fx["data"]["xbar"] * draws["beta.c"], rtol=1e-15)
+
+
+def test_blockers_forward_samples_the_unobserved_leaf(fixtures):
+    """delta.new ~ dnorm(d, tau) has no observed descendant: it is drawn forward, once per posterior draw."""
+    fx = fixtures["blockers"]
+    lw = jbugs.Lowering(ex.BLOCKERS, fx["data"])
+    S = 200_000
+    draws = {"d": np.full(S, -0.25), "tau": np.full(S, 16.0)}
+    out = generated_quantities(lw, draws, seed=3)
+    assert np.allclose(out["sigma"], 0.25)
+    assert out["delta.new"].mean() == pytest.approx(-0.25, abs=3e-3)
+    assert out["delta.new"].std() == pytest.approx(0.25, rel=1e-2)
+
+
+def test_stacks_indexed_generated_quantities(fixtures):
+    fx = fixtures["stacks"]
+    lw = jbugs.Lowering(ex.STACKS, fx["data"])
+    rng = np.random.default_rng(2)
+    S = 20
+    draws = {"beta0": rng.normal(17, 1, S), "tau": rng.gamma(5, 0.02, S),
+             "beta[1]": rng.normal(6, 1, S), "beta[2]": rng.normal(3, 1, S), "beta[3]": rng.normal(0, 1, S)}
+    out = generated_quantities(lw, draws)
+    x = np.asarray(fx["data"]["x"], dtype=float)
+    Y = np.asarray(fx["data"]["Y"], dtype=float)
+    sd, mean = x.std(axis=0, ddof=1), x.mean(axis=0)
+    b = np.stack([draws[f"beta[{j + 1}]"] / sd[j] for j in range(3)])
+    assert np.allclose(out["b"], b, rtol=1e-14)
+    assert np.allclose(out["b0"], draws["beta0"] - (b * mean[:, None]).sum(axis=0), rtol=1e-13)
+    z = (x - mean) / sd
+    mu = draws["beta0"][None, :] + z @ np.stack([draws[f"beta[{j + 1}]"] for j in range(3)])
+    stres = (Y[:, None] - mu) * np.sqrt(draws["tau"])[None, :]
+    assert np.allclose(out["stres"], stres, rtol=1e-12)
+    assert np.array_equal(out["outlier"], (stres - 2.5 >= 0).astype(float) + (-(stres + 2.5) >= 0).astype(float))
