@@ -85,6 +85,13 @@ int jbugs_plan_upload_data(jbugs_plan* plan, int slot, const void* src, size_t n
  * over ranks in a fixed order.  Default: the whole plate. */
 int jbugs_plan_set_shard(jbugs_plan* plan, int plate, int64_t i0, int64_t i1);
 
+/* Same for the dense predictor `inprod(X[i, 1:P], beta[1:P])`: this rank
+ * owns rows [i0, i1) of X, y (and n); i0 even keeps the 16-byte loads.  The coefficient vector and
+ * its prior plate stay replicated; the P x C block X^T R travels in the same all-reduce as the
+ * per-chain logp and the global adjoints.  A plate (or the dense predictor) for which no shard
+ * was set is treated as replicated: evaluated on every rank, counted once. */
+int jbugs_plan_set_dense_shard(jbugs_plan* plan, int64_t i0, int64_t i1);
+
 /* Replaces: LogDensityProblems.logdensity (src/model/logdensityproblems.jl:19-27) and
  * logdensity_and_gradient (:219-232) -> evaluate_with_values!! (src/model/evaluation.jl:217-275)
  * plus the AD backend, for C chains at once.

@@ -103,10 +103,12 @@ struct jbugs_plan_s {
     int dense_row_groups = 0, dense_splits = 0;
     double dense_const = 0.0;
     bool dense_const_dirty = true;
+    long long dense_i0 = 0, dense_i1 = -1;  // this rank's row range of X (jbugs_plan_set_dense_shard); -1 = all rows
     std::vector<void*> d_slots;
     std::vector<char> uploaded;
     std::vector<PlateRt> rt;
     std::vector<long long> shard_i0, shard_i1;
+    std::vector<char> shard_set;  // jbugs_plan_set_shard was called for the plate (else it is replicated on every rank)
     GlobalsParams gp{};
     GTapeParams tp{};
     // workspaces sized for cap_C chains
@@ -452,6 +454,7 @@ extern "C" int jbugs_plan_create(const void* blob, size_t nbytes, int device, jb
     }
     p->rt.resize(h.n_plates);
     p->shard_i0.assign(h.n_plates, 0);
+    p->shard_set.assign(h.n_plates, 0);
     p->shard_i1.resize(h.n_plates);
     for (uint32_t k = 0; k < h.n_plates; ++k) p->shard_i1[k] = p->plates[k].N;
     p->gp.n_globals = (int)h.n_globals;
@@ -578,11 +581,24 @@ extern "C" int jbugs_plan_set_shard(jbugs_plan* p, int plate, int64_t i0, int64_
     if (plate < 0 || plate >= (int)p->h.n_plates) return fail(JBUGS_ERR_INVALID, "plate %d out of range", plate);
     if (i0 < 0 || i1 > p->plates[plate].N || i0 > i1) return fail(JBUGS_ERR_INVALID, "shard [%lld, %lld) outside [0, %lld)", (long long)i0, (long long)i1, (long long)p->plates[plate].N);
     p->shard_i0[plate] = i0;
+    p->shard_set[plate] = 1;
     p->shard_i1[plate] = i1;
     p->rt[plate].pp.v.i0 = i0;
     p->rt[plate].pp.v.i1 = i1;
     p->rt[plate].const_dirty = true;
     p->cap_C = 0;  // force re-tiling
+    return JBUGS_OK;
+}
+
+extern "C" int jbugs_plan_set_dense_shard(jbugs_plan* p, int64_t i0, int64_t i1) {
+    if (!p) return fail(JBUGS_ERR_INVALID, "null plan");
+    if (p->dense.empty()) return fail(JBUGS_ERR_INVALID, "the plan has no dense predictor");
+    const long long N = p->dense[0].N;
+    if (i0 < 0 || i1 > N || i0 > i1) return fail(JBUGS_ERR_INVALID, "shard [%lld, %lld) outside [0, %lld)", (long long)i0, (long long)i1, N);
+    p->dense_i0 = i0;
+    p->dense_i1 = i1;
+    p->dense_const_dirty = true;
+    p->cap_C = 0;  // row groups / split-K factor depend on the local row count
     return JBUGS_OK;
 }
 
@@ -694,8 +710,9 @@ static int ensure_workspace(jbugs_plan* p, long long C) {
     if (!p->dense.empty()) {
         // dense predictor: one logp partial row per forward-GEMM row group; R and the split-K partials of X^T R
         const jbugs_dense& dn = p->dense[0];
+        const long long Nloc = (p->dense_i1 >= 0 ? p->dense_i1 : dn.N) - p->dense_i0;  // rows of X on this rank
         const long long col_blocks = (C + DG_BN - 1) / DG_BN;
-        const long long m_tiles = std::max<long long>(1, (dn.N + DG_BM - 1) / DG_BM);
+        const long long m_tiles = std::max<long long>(1, (Nloc + DG_BM - 1) / DG_BM);
         p->dense_row_groups = (int)std::max<long long>(1, std::min<long long>(m_tiles, (2LL * p->num_sms + col_blocks - 1) / col_blocks));
         const long long out_tiles = col_blocks * ((dn.P + DG_BM - 1) / DG_BM);
         // split-K factor of the reverse GEMM: fill whole waves of one CTA per SM (wave quantisation costs up to 2x)
@@ -703,7 +720,7 @@ static int ensure_workspace(jbugs_plan* p, long long C) {
             int best = 1;
             double best_eff = 0.0;
             for (int s = 1; s <= 96; ++s) {
-                if (s > 1 && dn.N / s < 8 * DG_BK) break;
+                if (s > 1 && Nloc / s < 8 * DG_BK) break;
                 const long long ctas = out_tiles * s, waves = (ctas + p->num_sms - 1) / p->num_sms;
                 const double eff = (double)ctas / (double)(waves * p->num_sms);
                 if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
@@ -712,13 +729,15 @@ static int ensure_workspace(jbugs_plan* p, long long C) {
         }
         p->dense_partial_offset = rows;
         rows += p->dense_row_groups;
-        if ((rc = grow((void**)&p->d_R, &p->R_bytes, (size_t)std::max<long long>(dn.N, 1) * ldg * 8))) return rc;
+        if ((rc = grow((void**)&p->d_R, &p->R_bytes, (size_t)std::max<long long>(Nloc, 1) * ldg * 8))) return rc;
         if ((rc = grow((void**)&p->d_Gp, &p->Gp_bytes, (size_t)p->dense_splits * dn.P * ldg * 8))) return rc;
     }
     if ((rc = grow((void**)&p->d_gvals, &p->gvals_bytes, (size_t)std::max(NG, 1) * ldg * 8))) return rc;
     if ((rc = grow((void**)&p->d_partial, &p->partial_bytes, (size_t)std::max<long long>(rows, 1) * ldg * 8))) return rc;
     if ((rc = grow((void**)&p->d_partial2, &p->partial2_bytes, (size_t)std::max<long long>(rows2, 1) * ldg * 8))) return rc;
-    if ((rc = grow((void**)&p->d_red, &p->red_bytes, (size_t)(2 + std::max(NG, 1)) * ldg * 8))) return rc;
+    // all-reduce buffer of the observation-sharded path: [logp | NG global adjoints | flag | P rows of X^T R]
+    const long long red_rows = 2 + std::max(NG, 1) + (p->dense.empty() ? 0 : p->dense[0].P);
+    if ((rc = grow((void**)&p->d_red, &p->red_bytes, (size_t)red_rows * ldg * 8))) return rc;
     if ((rc = grow((void**)&p->d_flags, &p->flags_bytes, (size_t)ldg * sizeof(int)))) return rc;
     p->cap_C = C;
     p->ldg = ldg;
@@ -753,6 +772,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         fp.p[k].n_gref = r.pp.sh.n_gref;
         fp.p[k].offset = r.partial_offset;
         fp.p[k].obs_const = r.obs_const;
+        fp.p[k].replicated = (p->comm && p->nranks > 1 && !p->shard_set[k]) ? 1 : 0;
         for (int q = 0; q < MAX_GREF; ++q) fp.p[k].gref[q] = r.pp.v.gref[q];
         if (r.pp.v.i1 <= r.pp.v.i0) { fp.p[k].n_tiles = 0; continue; }
         PlateParams pp = r.pp;  // per-launch copy: slot maps in element offsets of this batch's leading dimension
@@ -768,8 +788,9 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         reduce_plates.push_back((int)k);
     }
     if (!p->dense.empty()) {
-        if (p->comm && p->nranks > 1) return fail(JBUGS_ERR_UNSUPPORTED, "dense predictors are not observation-sharded yet");
         const jbugs_dense& dn = p->dense[0];
+        const bool sharded = p->comm && p->nranks > 1 && p->dense_i1 >= 0;  // rows of X split over the ranks
+        const long long r0 = p->dense_i0, Nloc = (p->dense_i1 >= 0 ? p->dense_i1 : dn.N) - r0;
         const unsigned col_blocks = (unsigned)((C + DG_BN - 1) / DG_BN);
         static bool opted = false;
         if (!opted) {
@@ -777,15 +798,15 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
             CU(cudaFuncSetAttribute(dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM_BYTES));
             opted = true;
         }
-        const double* X = (const double*)p->d_slots[dn.x_slot];
+        const double* X = (const double*)p->d_slots[dn.x_slot] + r0;  // column-major N x P: a row range is an offset
         DenseFwdParams fw{};
         fw.op.A = X; fw.op.lda = dn.N;
         fw.op.B = theta + dn.theta_base * ld; fw.op.ldb = dn.theta_stride * ld;
-        fw.op.M = dn.N; fw.op.N = C; fw.op.K = dn.P;
+        fw.op.M = Nloc; fw.op.N = C; fw.op.K = dn.P;
         const bool x_vec = ((uintptr_t)X % 16 == 0) && (dn.N % 2 == 0);
         fw.op.vec_ok = x_vec && ((uintptr_t)theta % 16 == 0) && (ld % 2 == 0);
-        fw.y = (const double*)p->d_slots[dn.y_slot];
-        fw.n = dn.n_slot >= 0 ? (const double*)p->d_slots[dn.n_slot] : nullptr;
+        fw.y = (const double*)p->d_slots[dn.y_slot] + r0;
+        fw.n = dn.n_slot >= 0 ? (const double*)p->d_slots[dn.n_slot] + r0 : nullptr;
         fw.R = p->d_R; fw.ldr = ldg;
         fw.partial = p->d_partial + p->dense_partial_offset * ldg; fw.ldg = ldg;
         fw.flags = p->d_flags;
@@ -795,11 +816,12 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         fp.p[k_fp].n_tiles = p->dense_row_groups;
         fp.p[k_fp].n_gref = 0;
         fp.p[k_fp].offset = p->dense_partial_offset;
+        fp.p[k_fp].replicated = (p->comm && p->nranks > 1 && !sharded) ? 1 : 0;
         if (p->dense_const_dirty) {
             // data-only normaliser of the binomial (0 for Bernoulli) + validation of the counts, once per upload
             double h2[2] = {0.0, 0.0};
             obs_const_kernel<<<1, 1024, 0, st>>>(dn.n_slot >= 0 ? FUSED_BINOMIAL_LOGIT : FUSED_BERNOULLI_LOGIT, fw.y, fw.n, 0,
-                                                 JBUGS_ARG_DATA_I, 1.0, dn.N, 1, 0, dn.N, p->d_red);
+                                                 JBUGS_ARG_DATA_I, 1.0, Nloc, 1, 0, Nloc, p->d_red);
             p->launches++;
             CU(cudaMemcpyAsync(h2, p->d_red, sizeof h2, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
@@ -813,14 +835,21 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
             DenseBwdParams bw{};
             bw.op.A = X; bw.op.lda = dn.N;
             bw.op.B = p->d_R; bw.op.ldb = ldg;
-            bw.op.M = dn.P; bw.op.N = C; bw.op.K = dn.N;
+            bw.op.M = dn.P; bw.op.N = C; bw.op.K = Nloc;
             bw.op.vec_ok = x_vec;
             bw.Gp = p->d_Gp; bw.ldg = ldg;
-            bw.k_per_split = ((dn.N + p->dense_splits - 1) / p->dense_splits + DG_BK - 1) / DG_BK * DG_BK;
+            bw.k_per_split = ((Nloc + p->dense_splits - 1) / p->dense_splits + DG_BK - 1) / DG_BK * DG_BK;
             dense_bwd_kernel<<<dim3(col_blocks, (unsigned)((dn.P + DG_BM - 1) / DG_BM), (unsigned)p->dense_splits), DG_THREADS, DG_SMEM_BYTES, st>>>(bw);
             p->launches++;
-            dense_grad_reduce_kernel<<<dim3(chain_tiles, (unsigned)dn.P), BLOCK, 0, st>>>(p->d_Gp, p->dense_splits, dn.P, ldg, grad, ld,
-                                                                                       dn.theta_base, dn.theta_stride, C, 1);
+            if (sharded) {
+                // this rank's rows of X^T R go into the all-reduce buffer (rows 2 + NG ...); added to grad afterwards
+                const long long NGr = std::max<long long>(p->h.n_globals + p->h.n_gtape, 1);
+                dense_grad_reduce_kernel<<<dim3(chain_tiles, (unsigned)dn.P), BLOCK, 0, st>>>(p->d_Gp, p->dense_splits, dn.P, ldg, p->d_red, ldg,
+                                                                                           2 + NGr, 1, C, 0);
+            } else {
+                dense_grad_reduce_kernel<<<dim3(chain_tiles, (unsigned)dn.P), BLOCK, 0, st>>>(p->d_Gp, p->dense_splits, dn.P, ldg, grad, ld,
+                                                                                           dn.theta_base, dn.theta_stride, C, 1);
+            }
             p->launches++;
         }
     }
@@ -851,8 +880,16 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         finalize_kernel<<<helper_tiles, hblk, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, partial_in,
                                                        p->d_flags, logp, status, p->d_any_bad, want_grad && grad, 1, p->d_red);
         p->launches++;
-        const int e = g_nccl.AllReduce(p->d_red, p->d_red, (size_t)(2 + NG) * ldg, /*ncclDouble*/ 8, /*ncclSum*/ 0, p->comm, st);
+        const bool dense_grad = !p->dense.empty() && p->dense_i1 >= 0 && want_grad && grad;
+        const long long red_rows = dense_grad ? 2 + std::max(NG, 1) + p->dense[0].P : 2 + NG;
+        const int e = g_nccl.AllReduce(p->d_red, p->d_red, (size_t)red_rows * ldg, /*ncclDouble*/ 8, /*ncclSum*/ 0, p->comm, st);
         if (e) return fail(JBUGS_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+        if (dense_grad) {
+            const jbugs_dense& dn = p->dense[0];
+            dense_grad_reduce_kernel<<<dim3(chain_tiles, (unsigned)dn.P), BLOCK, 0, st>>>(p->d_red + (2 + std::max(NG, 1)) * ldg, 1, dn.P, ldg, grad, ld,
+                                                                                       dn.theta_base, dn.theta_stride, C, 1);
+            p->launches++;
+        }
         finalize_kernel<<<helper_tiles, hblk, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, partial_in,
                                                        p->d_flags, logp, status, p->d_any_bad, want_grad && grad, 2, p->d_red);
         p->launches++;

@@ -317,6 +317,7 @@ struct PlateFinal {
     long long offset;  // into the partial buffer (in units of ldg rows)
     int gref[MAX_GREF];
     double obs_const;
+    int replicated;  // observation-sharded runs: the plate is evaluated identically on every rank -> counted once
 };
 struct FinalParams {
     int n_plates;
@@ -348,8 +349,10 @@ finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
         batched_load(ga, NG, [&](int k) { return red + (long long)(1 + k) * ldg + c; });
         bad = red[(long long)(1 + NG) * ldg + c] != 0.0;
     }
-    for (int p = 0; p < (mode == 2 ? 0 : F.n_plates); ++p) {
+    for (int p = 0; p < F.n_plates; ++p) {
         const PlateFinal& pf = F.p[p];
+        // sharded plates enter the all-reduce (mode 1); replicated ones are added once, after it (mode 2)
+        if ((mode == 1 && pf.replicated) || (mode == 2 && !pf.replicated)) continue;
         const long long stride = (long long)(1 + pf.n_gref) * ldg;
         const double* base = partial + pf.offset * ldg + c;
         const int nt = pf.n_tiles;

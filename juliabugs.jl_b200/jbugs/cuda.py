@@ -20,7 +20,8 @@ EVAL_ASYNC = 1
 
 SYMBOLS = [
     "jbugs_last_error", "jbugs_version", "jbugs_device_count", "jbugs_plan_create", "jbugs_plan_destroy",
-    "jbugs_dim", "jbugs_plan_upload_data", "jbugs_plan_set_shard", "jbugs_eval_batch", "jbugs_batch_alloc",
+    "jbugs_dim", "jbugs_plan_upload_data", "jbugs_plan_set_shard", "jbugs_plan_set_dense_shard", "jbugs_eval_batch",
+    "jbugs_batch_alloc",
     "jbugs_batch_free", "jbugs_host_alloc", "jbugs_host_free", "jbugs_comm_unique_id", "jbugs_comm_init",
     "jbugs_comm_destroy", "jbugs_launch_count", "jbugs_plan_describe", "jbugs_plan_set_option",
     "jbugs_last_timing", "jbugs_hmc_create", "jbugs_hmc_destroy", "jbugs_hmc_init", "jbugs_hmc_run",
@@ -55,6 +56,7 @@ def load():
     L.jbugs_dim.argtypes = [c.c_void_p]
     L.jbugs_plan_upload_data.argtypes = [c.c_void_p, c.c_int, c.c_void_p, c.c_size_t, c.c_int]
     L.jbugs_plan_set_shard.argtypes = [c.c_void_p, c.c_int, c.c_int64, c.c_int64]
+    L.jbugs_plan_set_dense_shard.argtypes = [c.c_void_p, c.c_int64, c.c_int64]
     L.jbugs_eval_batch.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_void_p, c.c_void_p,
                                    c.c_void_p, c.c_int, c.c_int, c.c_void_p]
     L.jbugs_batch_alloc.argtypes = [c.c_void_p, c.c_int64, c.POINTER(c.c_void_p), c.POINTER(c.c_void_p),
@@ -133,6 +135,9 @@ class CudaPlan:
 
     def set_shard(self, plate: int, i0: int, i1: int):
         _check(self.L.jbugs_plan_set_shard(self.h, plate, i0, i1))
+
+    def set_dense_shard(self, i0: int, i1: int):
+        _check(self.L.jbugs_plan_set_dense_shard(self.h, i0, i1))
 
     def set_option(self, key: str, value: int):
         _check(self.L.jbugs_plan_set_option(self.h, key.encode(), int(value)))

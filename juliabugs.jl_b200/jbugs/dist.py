@@ -56,8 +56,12 @@ def shard_observations(model, rank: int, world: int, group=None):
 
     cp = model.cuda
     for k, pl in enumerate(model.plan.plates):
+        if not pl.has_obs:
+            continue  # prior-only plate (coefficients of a dense predictor): replicated, counted once
         i0, i1 = shard_bounds(pl.N, world, rank)
         cp.set_shard(k, i0, i1)
+    for dn in model.plan.dense:
+        cp.set_dense_shard(*shard_bounds(dn.N, world, rank))  # rows of X, y; X^T R joins the all-reduce
     if world > 1:
         uid = broadcast_unique_id(CudaPlan.comm_unique_id, rank, world, group)
         cp.comm_init(world, rank, uid)

@@ -49,6 +49,22 @@ def main():
     lp2, g2, _ = m2.cuda.eval_host(theta[:, c0:c1], layout="chain_fast")
     assert np.max(np.abs(lp2 - ref_lp[c0:c1]) / np.abs(ref_lp[c0:c1])) < 1e-10
     assert np.max(np.abs(g2 - ref_g[:, c0:c1]) / gs[:, c0:c1]) < 1e-10
+    # --- dense predictor: rows of X sharded, P x C block of X^T R in the same all-reduce, prior plate replicated
+    rng = np.random.default_rng(77)
+    Nd, Pd, Cd = 4096, 40, 130
+    X = np.asfortranarray(rng.standard_normal((Nd, Pd)))
+    bt = rng.normal(0.0, 0.3, Pd)
+    y = (rng.random(Nd) < 1.0 / (1.0 + np.exp(-X @ bt))).astype(float)
+    ddata = {"N": Nd, "P": Pd, "X": X, "y": y}
+    thd = random_thetas(np.concatenate([[0.5, 0.1], bt]), Cd, seed=4, scale=0.1)
+    md = jbugs.set_evaluation_mode(jbugs.compile(jbugs.examples.DENSE_LOGISTIC, ddata), jbugs.UseCUDABatch(device=local))
+    ref_lp, ref_g, _ = COracle(md.plan).eval_batch(thd)
+    cpd = shard_observations(md, rank, world)
+    lp3, g3, st3 = cpd.eval_host(thd, layout="chain_fast")
+    assert np.all(st3 == 0)
+    assert np.max(np.abs(lp3 - ref_lp) / np.abs(ref_lp)) < 1e-10, "dense: logp after all-reduce"
+    gs3 = np.maximum(np.abs(ref_g), 1e-4 * np.abs(ref_g).max(axis=0, keepdims=True))
+    assert np.max(np.abs(g3 - ref_g) / gs3) < 1e-10, "dense: every gradient row is complete on every rank"
     dist.barrier()
     if rank == 0:
         print("MGPU_OK", world)
