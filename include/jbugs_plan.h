@@ -70,7 +70,12 @@ enum jbugs_family {
     JBUGS_FAM_BINOMIAL = 7,    /* dbin(p, n)       :458-460 */
     JBUGS_FAM_POISSON = 8,     /* dpois(lambda)    :486-488 */
     JBUGS_FAM_FLAT = 9,        /* dflat()                   */
-    JBUGS_FAM_COUNT = 10
+    JBUGS_FAM_LOGISTIC = 10,   /* dlogis(mu, tau)  :30-33   Logistic(mu, 1/sqrt(tau)) */
+    JBUGS_FAM_LAPLACE = 11,    /* ddexp(mu, tau)   :92-95   Laplace(mu, 1/sqrt(tau))  */
+    JBUGS_FAM_WEIBULL = 12,    /* dweib(a, b)      :233-235 Weibull(a, 1/b)           */
+    JBUGS_FAM_NEGBIN = 13,     /* dnegbin(p, r)    :516-518 NegativeBinomial(r, p)    */
+    JBUGS_FAM_CHISQ = 14,      /* dchisqr(k)       :215-217 Chisq(k)                  */
+    JBUGS_FAM_COUNT = 15
 };
 
 /* ---- constrained <-> unconstrained maps (Bijectors, call site evaluation.jl:243-257) ------- */

@@ -150,6 +150,44 @@ __device__ __forceinline__ bool fam_eval(int fam, double x, double a0, double a1
         o.da0 = (x == 0.0 ? 0.0 : x / a0) - 1.0;
         return !(a0 >= 0.0);
     }
+    case JBUGS_FAM_LOGISTIC: {  // Logistic(mu, 1/sqrt(tau)): u - 2 log1pexp(u) - log(s), u = -|z|
+        const double rt = sqrt(a1), s = 1.0 / rt;
+        const double z = (x - a0) * rt, u = -fabs(z);
+        o.lp = u - 2.0 * log1p(exp(u)) - log(s);
+        const double w = 1.0 - 2.0 * logistic(z);  // -tanh(z / 2)
+        o.dx = w * rt; o.da0 = -w * rt; o.da1 = w * (x - a0) / (2.0 * rt) + 0.5 / a1;
+        return a1 < 0.0 || !(s > 0.0);
+    }
+    case JBUGS_FAM_LAPLACE: {  // Laplace(mu, 1/sqrt(tau)): -(|x - mu| / b + log(2 b))
+        const double rt = sqrt(a1), b = 1.0 / rt;
+        const double r = x - a0, sg = r >= 0.0 ? 1.0 : -1.0;
+        o.lp = -(fabs(r) / b + log(2.0 * b));
+        o.dx = -sg * rt; o.da0 = sg * rt; o.da1 = -fabs(r) / (2.0 * rt) + 0.5 / a1;
+        return a1 < 0.0 || !(b > 0.0);
+    }
+    case JBUGS_FAM_WEIBULL: {  // Weibull(a, 1/b): log(a / theta) + xlogy(a - 1, z) - z^a, z = x / theta
+        const double theta = 1.0 / a1;
+        const double z = x / theta, lz = log(z), za = exp(a0 * lz);
+        o.lp = x < 0.0 ? -dev_inf() : (log(a0 / theta) + xlogy(a0 - 1.0, z) - za);
+        o.dx = ((a0 - 1.0) - a0 * za) / x;
+        o.da0 = 1.0 / a0 + lz - za * lz;
+        o.da1 = a0 * (1.0 - za) / a1;
+        return !(a0 > 0.0) || !(theta > 0.0);
+    }
+    case JBUGS_FAM_NEGBIN: {  // NegativeBinomial(r = a1, p = a0)
+        const bool out = (x < 0.0 || x != floor(x));
+        o.lp = out ? -dev_inf() : (xlogy(a1, a0) + xlog1py(x, -a0) - log(x + a1) - logbeta(a1, x + 1.0));
+        o.da0 = a1 / a0 - (x == 0.0 ? 0.0 : x / (1.0 - a0));
+        o.da1 = log(a0) - 1.0 / (x + a1) - digamma(a1) + digamma(a1 + x + 1.0);
+        return !(a1 > 0.0) || !(a0 > 0.0 && a0 <= 1.0);
+    }
+    case JBUGS_FAM_CHISQ: {  // Chisq(k) = Gamma(k / 2, 2)
+        const double h = 0.5 * a0;
+        o.lp = x < 0.0 ? -dev_inf() : (-lgamma(h) - h * 0.69314718055994530942 + xlogy(h - 1.0, x) - 0.5 * x);
+        o.dx = (h - 1.0) / x - 0.5;
+        o.da0 = 0.5 * (-digamma(h) - 0.69314718055994530942 + log(x));
+        return !(a0 > 0.0);
+    }
     default: return false;  // FLAT
     }
 }

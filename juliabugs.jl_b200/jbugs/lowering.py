@@ -675,7 +675,7 @@ class Lowering:
     def _transform_of(self, fam, args_expr):
         """Bijectors.bijector(dist): support-based (identity when the model is untransformed)."""
         lb, ub = -np.inf, np.inf
-        if fam in (P.FAM_GAMMA, P.FAM_EXPONENTIAL, P.FAM_LOGNORMAL):
+        if fam in (P.FAM_GAMMA, P.FAM_EXPONENTIAL, P.FAM_LOGNORMAL, P.FAM_WEIBULL, P.FAM_CHISQ):
             lb = 0.0
         elif fam == P.FAM_BETA:
             lb, ub = 0.0, 1.0
@@ -814,7 +814,7 @@ class Lowering:
         N = shape[0] if shape else 1
         T = shape[1] if len(shape) == 2 else 1
         fam = self._family(s.node.dist)
-        eta_arg = {P.FAM_GAMMA: 1}.get(fam, 0)
+        eta_arg = {P.FAM_GAMMA: 1, P.FAM_WEIBULL: 1}.get(fam, 0)
         if fam in (P.FAM_UNIFORM, P.FAM_BETA, P.FAM_FLAT):
             raise LoweringError(f"{s.node.dist.fn} as an observation family is outside the plate class")
         plate = P.Plate(N=N, T=T, family=fam, eta_arg=eta_arg, name=f"{s.name}~{s.node.dist.fn}")
@@ -866,7 +866,7 @@ class Lowering:
     def _peel(self, s: Stmt):
         """(family, eta_arg, inlined args, link ops innermost-first, predictor expression) of an observation."""
         fam = self._family(s.node.dist)
-        eta_arg = {P.FAM_GAMMA: 1}.get(fam, 0)
+        eta_arg = {P.FAM_GAMMA: 1, P.FAM_WEIBULL: 1}.get(fam, 0)
         args = [self._inline(a) for a in s.node.dist.args]
         eta = args[eta_arg]
         link = []

@@ -211,6 +211,83 @@ class Categorical(Dist):
         return M.log(self.p[kv - 1])
 
 
+class Logistic(Dist):
+    def __init__(self, M, mu, tau):
+        # distributions.jl:30-33: Logistic(mu, 1/sqrt(tau)); sqrt throws for tau < 0, Distributions checks scale > 0
+        self.mu = mu
+        self.s = 1.0 / M.sqrt(tau)
+        _check(_val(self.s) > 0, "Logistic requires scale > 0")
+
+    def logpdf(self, M, x):
+        # Distributions: u = -abs(z); u - 2 * log1pexp(u) - log(s)
+        z = (x - self.mu) / self.s
+        u = -M.abs(z)
+        return u - 2.0 * M.log1p(M.exp(u)) - M.log(self.s)
+
+
+class Laplace(Dist):
+    def __init__(self, M, mu, tau):
+        # distributions.jl:92-95: Laplace(mu, 1/sqrt(tau))
+        self.mu = mu
+        self.b = 1.0 / M.sqrt(tau)
+        _check(_val(self.b) > 0, "Laplace requires scale > 0")
+
+    def logpdf(self, M, x):
+        # Distributions: -(abs(x - mu) / b + log(2 b))
+        return -(M.abs(x - self.mu) / self.b + M.log(2.0 * self.b))
+
+
+class Weibull(Dist):
+    def __init__(self, M, a, b):
+        # distributions.jl:233-235: Weibull(a, 1/b) (shape a, scale 1/b)
+        self.a = a
+        self.theta = 1.0 / b
+        _check(_val(a) > 0 and _val(self.theta) > 0, "Weibull requires shape > 0 and scale > 0")
+
+    def support(self):
+        return (0.0, math.inf)
+
+    def logpdf(self, M, x):
+        if _val(x) < 0:
+            return -M.inf
+        # Distributions: z = x / theta; log(a / theta) + xlogy(a - 1, z) - z^a
+        z = x / self.theta
+        return M.log(self.a / self.theta) + _xlogy(M, self.a - 1, z) - M.exp(self.a * M.log(z))
+
+
+class NegativeBinomial(Dist):
+    discrete = True
+
+    def __init__(self, M, p, r):
+        # distributions.jl:516-518 swaps the arguments: dnegbin(p, r) = NegativeBinomial(r, p)
+        _check(_val(r) > 0, "NegativeBinomial requires r > 0")
+        _check(0 < _val(p) <= 1, "NegativeBinomial requires 0 < p <= 1")
+        self.p, self.r = p, r
+
+    def logpdf(self, M, k):
+        if _val(k) < 0 or not M.isint(k):
+            return -M.inf
+        # Distributions: xlogy(r, p) + xlog1py(k, -p) - log(k + r) - logbeta(r, k + 1)
+        return (_xlogy(M, self.r, self.p) + _xlog1py(M, k, -self.p) - M.log(k + self.r)
+                - _logbeta(M, self.r, k + 1))
+
+
+class Chisq(Dist):
+    def __init__(self, M, k):
+        # distributions.jl:215-217: Chisq(k) = Gamma(k/2, 2)
+        _check(_val(k) > 0, "Chisq requires k > 0")
+        self.k = k
+
+    def support(self):
+        return (0.0, math.inf)
+
+    def logpdf(self, M, x):
+        if _val(x) < 0:
+            return -M.inf
+        h = self.k / 2.0
+        return -M.lgamma(h) - h * math.log(2.0) + _xlogy(M, h - 1, x) - x / 2.0
+
+
 class Flat(Dist):
     def logpdf(self, M, x):
         return 0.0 * x
@@ -238,6 +315,16 @@ def make_dist(M, name, args):
         return Poisson(M, *args)
     if name == "dcat":
         return Categorical(M, *args)
+    if name == "dlogis":
+        return Logistic(M, *args)
+    if name == "ddexp":
+        return Laplace(M, *args)
+    if name == "dweib":
+        return Weibull(M, *args)
+    if name == "dnegbin":
+        return NegativeBinomial(M, *args)
+    if name == "dchisqr":
+        return Chisq(M, *args)
     if name == "dflat":
         return Flat()
     raise NotImplementedError(f"distribution {name} is outside the restated subset")

@@ -196,6 +196,60 @@ static int fam_logpdf(uint32_t fam, double x, const double* a, double* lp, doubl
         return 0;
     }
     case JBUGS_FAM_FLAT: *lp = 0.0; return 0;
+    case JBUGS_FAM_LOGISTIC: { /* :30-33 -> Logistic(mu, 1/sqrt(tau)); logpdf = u - 2 log1pexp(u) - log(s), u = -|z| */
+        double mu = a[0], tau = a[1];
+        if (tau < 0.0) return 1;
+        double s = 1.0 / sqrt(tau);
+        if (!(s > 0.0)) return 1;
+        double z = (x - mu) / s, u = -fabs(z);
+        *lp = u - 2.0 * log1p(exp(u)) - log(s);
+        double w = 1.0 - 2.0 * logistic(z); /* d/dz = -tanh(z/2) */
+        *dx = w / s;
+        da[0] = -w / s;
+        da[1] = w * (x - mu) / (2.0 * sqrt(tau)) + 0.5 / tau;
+        return 0;
+    }
+    case JBUGS_FAM_LAPLACE: { /* :92-95 -> Laplace(mu, 1/sqrt(tau)); logpdf = -(|x - mu| / b + log(2 b)) */
+        double mu = a[0], tau = a[1];
+        if (tau < 0.0) return 1;
+        double b = 1.0 / sqrt(tau);
+        if (!(b > 0.0)) return 1;
+        double r = x - mu, sg = r >= 0.0 ? 1.0 : -1.0;
+        *lp = -(fabs(r) / b + log(2.0 * b));
+        *dx = -sg / b;
+        da[0] = sg / b;
+        da[1] = -fabs(r) / (2.0 * sqrt(tau)) + 0.5 / tau;
+        return 0;
+    }
+    case JBUGS_FAM_WEIBULL: { /* :233-235 -> Weibull(a, 1/b); logpdf = log(a/theta) + xlogy(a-1, z) - z^a, z = x/theta */
+        double al = a[0], b = a[1], theta = 1.0 / b;
+        if (!(al > 0.0) || !(theta > 0.0)) return 1;
+        if (x < 0.0) { *lp = -INFINITY; return 0; }
+        double z = x / theta, lz = log(z), za = exp(al * lz);
+        *lp = log(al / theta) + xlogy(al - 1.0, z) - za;
+        *dx = ((al - 1.0) - al * za) / x;
+        da[0] = 1.0 / al + lz - za * lz;
+        da[1] = al * (1.0 - za) / b;
+        return 0;
+    }
+    case JBUGS_FAM_NEGBIN: { /* :516-518 -> NegativeBinomial(r, p) */
+        double p = a[0], r = a[1];
+        if (!(r > 0.0) || !(p > 0.0 && p <= 1.0)) return 1;
+        if (x < 0.0 || x != floor(x)) { *lp = -INFINITY; return 0; }
+        *lp = xlogy(r, p) + xlog1py(x, -p) - log(x + r) - logbeta(r, x + 1.0);
+        da[0] = r / p - (x == 0.0 ? 0.0 : x / (1.0 - p));
+        da[1] = log(p) - 1.0 / (x + r) - digamma(r) + digamma(r + x + 1.0);
+        return 0;
+    }
+    case JBUGS_FAM_CHISQ: { /* :215-217 -> Chisq(k) = Gamma(k/2, 2) */
+        double h = 0.5 * a[0];
+        if (!(a[0] > 0.0)) return 1;
+        if (x < 0.0) { *lp = -INFINITY; return 0; }
+        *lp = -lgamma(h) - h * M_LN2 + xlogy(h - 1.0, x) - 0.5 * x;
+        *dx = (h - 1.0) / x - 0.5;
+        da[0] = 0.5 * (-digamma(h) - M_LN2 + log(x));
+        return 0;
+    }
     default: return 2;
     }
 }

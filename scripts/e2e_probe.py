@@ -25,7 +25,7 @@ for hc in (16,32,64,128,256):
 # param-fast host layout (Julia D x C): contiguous chain columns
 thp=torch.empty((Ce,D),dtype=torch.float64).pin_memory(); gp=torch.empty((Ce,D),dtype=torch.float64).pin_memory()
 thp.copy_(th.t())
-for hc in (16,32,64):
+for hc in (8,16,32,64):
     cp.set_option('host_chunk',hc)
     for _ in range(2): cp.eval_raw(thp.data_ptr(),D,Ce,1,lp.data_ptr(),gp.data_ptr(),st.data_ptr(),True,0,None)
     t=time.perf_counter()
