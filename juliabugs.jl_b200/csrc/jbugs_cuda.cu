@@ -142,6 +142,9 @@ struct jbugs_plan_s {
     // streams are < 1 % of the traffic anyway.  `jbugs_plan_set_option(plan, "tma", 1)` selects the TMA kernels.
     int use_tma = 0;
     long long launches = 0;
+    // bumped whenever anything a captured launch sequence bakes in may have changed (tiling, workspace pointers,
+    // data-only constants): the HMC trajectory graph is rebuilt when it sees a new epoch
+    unsigned long long epoch = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_plate_ms = 0.f, last_total_ms = 0.f;
     bool timing = false;  // record per-phase CUDA events (jbugs_last_timing); off by default: four extra stream ops per call
@@ -336,6 +339,7 @@ static int refresh_obs_const(jbugs_plan* p, int k, cudaStream_t st) {
     if (!r.const_dirty) return 0;
     r.obs_const = 0.0;
     r.const_dirty = false;
+    p->epoch++;
     const int fused = g_specs[r.variant].fused;
     if (fused != FUSED_BINOMIAL_LOGIT && fused != FUSED_POISSON_LOG && fused != FUSED_BERNOULLI_LOGIT) return 0;
     const PlateParams& pp = r.pp;
@@ -679,6 +683,7 @@ static int grow(void** ptr, size_t* cap, size_t need) {
 // (re)tile the plates for a batch of C chains and make sure the workspaces are large enough (grow only)
 static int ensure_workspace(jbugs_plan* p, long long C) {
     if (C == p->cap_C) return 0;
+    p->epoch++;
     const long long ldg = round_up(C, 16);
     const int NG = (int)(p->h.n_globals + p->h.n_gtape);
     const int blk = plate_block(C);
@@ -828,6 +833,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
             if (h2[1] != 0.0) return fail(JBUGS_ERR_UNSUPPORTED, "dense predictor: observations outside the support of the family");
             p->dense_const = h2[0];
             p->dense_const_dirty = false;
+            p->epoch++;
         }
         fp.p[k_fp].obs_const = p->dense_const;
         fp.n_plates = k_fp + 1;

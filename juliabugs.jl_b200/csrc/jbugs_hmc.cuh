@@ -41,6 +41,22 @@ __device__ __forceinline__ double2 normal2(unsigned long long seed, unsigned lon
 }
 
 
+// per-transition scalars live in device memory so that a captured CUDA graph of the trajectory can be replayed with a
+// new step size / iteration counter (set by hmc_ctl_kernel just before the graph launch)
+struct HmcCtl {
+    double eps;
+    unsigned it;
+    unsigned pad;
+    double mean_accept;   // mean acceptance probability of the last transition
+    double accept_total;  // running sum of those means since the last reset
+};
+
+__global__ void hmc_ctl_kernel(HmcCtl* ctl, double eps, unsigned it, int reset_total) {
+    ctl->eps = eps;
+    ctl->it = it;
+    if (reset_total) ctl->accept_total = 0.0;
+}
+
 // q[d][c] = theta0[d] + jitter * z
 __global__ void __launch_bounds__(BLOCK)
 hmc_init_kernel(double* __restrict__ q, long long ld, long long D, long long C, const double* __restrict__ theta0,
@@ -54,9 +70,11 @@ hmc_init_kernel(double* __restrict__ q, long long ld, long long D, long long C, 
 // fresh momentum p ~ N(0, M), M = diag(1 / var);  kinetic partial sums 0.5 * sum p^2 var
 __global__ void __launch_bounds__(BLOCK)
 hmc_refresh_kernel(double* __restrict__ p, long long ld, long long D, long long C, const double* __restrict__ var,
-                   unsigned long long seed, unsigned it, double* __restrict__ kin_partial, long long ldg, long long HMC_ROWS) {
+                   unsigned long long seed, const HmcCtl* __restrict__ ctl, double* __restrict__ kin_partial, long long ldg,
+                   long long HMC_ROWS) {
     const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (c >= C) return;
+    const unsigned it = ctl->it;
     const long long d0 = (long long)blockIdx.y * HMC_ROWS, d1 = d0 + HMC_ROWS < D ? d0 + HMC_ROWS : D;
     double k = 0.0;
     for (long long d = d0; d < d1; d += 2) {
@@ -77,18 +95,33 @@ hmc_refresh_kernel(double* __restrict__ p, long long ld, long long D, long long 
 __global__ void __launch_bounds__(BLOCK)
 hmc_leap_kernel(const double* q_in, double* q_out /* may alias q_in */, double* __restrict__ p,
                 const double* __restrict__ g, long long ld, long long D, long long C, const double* __restrict__ var,
-                double eps, double wp, double wq, double* __restrict__ kin_partial, long long ldg, long long HMC_ROWS) {
+                const HmcCtl* __restrict__ ctl, double wp, double wq, double* __restrict__ kin_partial, long long ldg,
+                long long HMC_ROWS) {
     const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (c >= C) return;
+    const double eps = ctl->eps;
     const long long d0 = (long long)blockIdx.y * HMC_ROWS, d1 = d0 + HMC_ROWS < D ? d0 + HMC_ROWS : D;
     double k = 0.0;
-    for (long long d = d0; d < d1; ++d) {
-        const long long e = d * ld + c;
-        const double v = var[d];
-        const double pn = fma(wp * eps, g[e], p[e]);
-        p[e] = pn;
-        if (wq != 0.0) q_out[e] = fma(wq * eps * v, pn, q_in[e]);
-        k = fma(pn * pn, v, k);
+    // four rows at a time, every load issued before the first use (the index is clamped, not predicated)
+    for (long long d = d0; d < d1; d += 4) {
+        double gv[4], pv[4], qv[4], vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long dd = d + u < d1 ? d + u : d1 - 1, e = dd * ld + c;
+            gv[u] = g[e];
+            pv[u] = p[e];
+            vv[u] = var[dd];
+            qv[u] = wq != 0.0 ? q_in[e] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (d + u < d1) {
+                const long long e = (d + u) * ld + c;
+                const double pn = fma(wp * eps, gv[u], pv[u]);
+                p[e] = pn;
+                if (wq != 0.0) q_out[e] = fma(wq * eps * vv[u], pn, qv[u]);
+                k = fma(pn * pn, vv[u], k);
+            }
     }
     if (kin_partial) kin_partial[(long long)blockIdx.y * ldg + c] = 0.5 * k;
 }
@@ -99,7 +132,14 @@ hmc_colsum_kernel(const double* __restrict__ partial, int n_tiles, long long ldg
     const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (c >= C) return;
     double s = 0.0;
-    for (int t = 0; t < n_tiles; ++t) s += partial[(long long)t * ldg + c];
+    for (int t0 = 0; t0 < n_tiles; t0 += 8) {  // ascending order, eight loads in flight
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = partial[(long long)(t0 + u < n_tiles ? t0 + u : n_tiles - 1) * ldg + c];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (t0 + u < n_tiles) s += v[u];
+    }
     dst[c] = s;
 }
 
@@ -107,9 +147,10 @@ hmc_colsum_kernel(const double* __restrict__ partial, int n_tiles, long long ldg
 __global__ void __launch_bounds__(BLOCK)
 hmc_accept_kernel(const double* lp0 /* == lp_cur */, const double* __restrict__ k0, const double* __restrict__ lp1,
                   const double* __restrict__ k1, const int* __restrict__ status1, long long C, unsigned long long seed,
-                  unsigned it, int* __restrict__ accept, double* __restrict__ accept_prob, double* lp_cur) {
+                  const HmcCtl* __restrict__ ctl, int* __restrict__ accept, double* __restrict__ accept_prob, double* lp_cur) {
     const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (c >= C) return;
+    const unsigned it = ctl->it;
     const double h0 = -lp0[c] + k0[c], h1 = -lp1[c] + k1[c];
     double a = exp(fmin(0.0, h0 - h1));
     if (!(h1 == h1) || !(a == a) || status1[c] != 0 || fabs(h1) == dev_inf()) a = 0.0;
@@ -118,6 +159,25 @@ hmc_accept_kernel(const double* lp0 /* == lp_cur */, const double* __restrict__ 
     accept[c] = acc;
     accept_prob[c] = a;
     if (acc) lp_cur[c] = lp1[c];
+}
+
+// mean acceptance probability over the chains (one CTA; fixed-order strided sums + shared-memory tree)
+__global__ void __launch_bounds__(256)
+hmc_mean_accept_kernel(const double* __restrict__ accept_prob, long long C, HmcCtl* __restrict__ ctl) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (long long c = threadIdx.x; c < C; c += 256) s += accept_prob[c];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double m = sh[0] / (double)C;
+        ctl->mean_accept = m;
+        ctl->accept_total += m;
+    }
 }
 
 // accepted chains take the proposal:  q_cur, g_cur <- q_prop, g_prop
