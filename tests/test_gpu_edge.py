@@ -224,3 +224,32 @@ def test_dense_logistic_gemm_path(N, P, C, binomial):
     co = _oracle(m.plan)
     _check(m.cuda, co, theta)
     _check(m.cuda, co, theta, layout="param_fast")
+
+
+def test_abi_error_codes(fixtures):
+    """nothing throws across the ABI: bad arguments come back as negative codes with a message, and the plan
+    stays usable afterwards."""
+    from jbugs.cuda import JBugsCudaError
+    fx = fixtures["rats"]
+    m = jbugs.compile(jbugs.examples.RATS, fx["data"], fx["inits"])
+    cp = m.cuda
+    D, C = m.plan.D, 8
+    th = np.ascontiguousarray(random_thetas(jbugs.getparams(m), C, seed=1, scale=0.01))
+    lp, g, st = np.empty(C), np.empty((D, C)), np.empty(C, dtype=np.int32)
+    with pytest.raises(JBugsCudaError, match="unknown layout"):
+        cp.eval_raw(th, C, C, 7, lp, g, st)
+    with pytest.raises(JBugsCudaError, match="leading dimension"):
+        cp.eval_raw(th, C - 1, C, 0, lp, g, st)
+    with pytest.raises(JBugsCudaError, match="grad is null"):
+        cp.eval_raw(th, C, C, 0, lp, None, st, want_grad=True)
+    with pytest.raises(JBugsCudaError, match="outside"):
+        cp.set_shard(0, 0, 31)
+    with pytest.raises(JBugsCudaError, match="out of range"):
+        cp.set_shard(3, 0, 1)
+    with pytest.raises(JBugsCudaError, match="no dense predictor"):
+        cp.set_dense_shard(0, 1)
+    with pytest.raises(JBugsCudaError, match="unknown option"):
+        cp.set_option("no_such_knob", 1)
+    cp.eval_raw(th, C, 0, 0, lp, g, st)          # C = 0 is a no-op, not an error
+    lp2, g2, st2 = cp.eval_host(th)              # and the handle still works
+    assert np.all(st2 == 0) and np.all(np.isfinite(lp2))
