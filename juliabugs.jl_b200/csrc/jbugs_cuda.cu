@@ -771,6 +771,8 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
     FinalParams fp{};
     std::vector<int> reduce_plates;
     fp.n_plates = (int)p->rt.size();
+    // small models: the NaN gradient of a flagged chain is written by finalize itself (one launch fewer)
+    fp.poison_rows = (want_grad && grad && p->h.D <= 4096) ? p->h.D : 0;
     for (size_t k = 0; k < p->rt.size(); ++k) {
         PlateRt& r = p->rt[k];
         fp.p[k].n_tiles = (int)r.n_tiles;
@@ -904,7 +906,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
                                                        p->d_flags, logp, status, p->d_any_bad, want_grad && grad, 0, p->d_red);
         p->launches++;
     }
-    if (want_grad && grad) {
+    if (want_grad && grad && fp.poison_rows == 0) {
         // almost always a no-op (no chain was flagged): keep the grid near one wave, rows are strided over it
         const long long rows = std::max<long long>(2LL * p->num_sms / chain_tiles, 1);
         dim3 grid(chain_tiles, (unsigned)std::min<long long>(std::max<long long>(p->h.D, 1), rows));

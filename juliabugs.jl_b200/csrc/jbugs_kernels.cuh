@@ -321,6 +321,7 @@ struct PlateFinal {
 };
 struct FinalParams {
     int n_plates;
+    long long poison_rows;  // > 0: this kernel also writes the NaN gradient of a flagged chain (small models); 0: poison_kernel does
     PlateFinal p[8];
 };
 
@@ -421,6 +422,8 @@ finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
     logp_out[c] = bad ? -dev_inf() : lp;
     if (status_out) status_out[c] = bad ? JBUGS_CHAIN_DOMAIN : JBUGS_CHAIN_OK;
     if (bad) atomicOr(any_bad, 1);
+    if (bad && want_grad)  // DomainError -> NaN gradient (logdensityproblems.jl:226-229); every plate kernel has finished
+        for (long long d = 0; d < F.poison_rows; ++d) grad[d * ld + c] = dev_nan();
 }
 
 // First level of the fixed-order tile reduction, used when a plate has many tiles: super-tile r adds the tiles
