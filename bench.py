@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--dynamic", type=int, default=0, help="1 = force the interpreter kernel")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--tma", type=int, default=-1, help="0 = stage plate data with cp.async only (A/B against the TMA path)")
+    ap.add_argument("--opt", default="", help="comma-separated key=value options passed to jbugs_plan_set_option (A/B runs)")
     ap.add_argument("--shard", default="", choices=["", "chains", "obs"],
                     help="N>1: 'chains' = every GPU its own chains (weak, no collective; default for rats); "
                          "'obs' = the data plate is split by observation + NCCL all-reduce (strong; default for seeds)")
@@ -245,6 +246,9 @@ def main():
         cp.set_option("tile", args.tile)
     if args.tma >= 0:
         cp.set_option("tma", args.tma)
+    for kv in filter(None, args.opt.split(",")):
+        k, v = kv.split("=")
+        cp.set_option(k, int(v))
     local_groups = [pl.N for pl in plan.plates]
     if obs_sharded:
         from jbugs.dist import shard_bounds, shard_observations

@@ -717,7 +717,7 @@ static int ensure_workspace(jbugs_plan* p, long long C) {
         const jbugs_dense& dn = p->dense[0];
         const long long Nloc = (p->dense_i1 >= 0 ? p->dense_i1 : dn.N) - p->dense_i0;  // rows of X on this rank
         const long long col_blocks = (C + DG_BN - 1) / DG_BN;
-        const long long m_tiles = std::max<long long>(1, (Nloc + DG_BM - 1) / DG_BM);
+        const long long m_tiles = std::max<long long>(1, (Nloc + DG_FWD_BM - 1) / DG_FWD_BM);
         p->dense_row_groups = (int)std::max<long long>(1, std::min<long long>(m_tiles, (2LL * p->num_sms + col_blocks - 1) / col_blocks));
         const long long out_tiles = col_blocks * ((dn.P + DG_BM - 1) / DG_BM);
         // split-K factor of the reverse GEMM: fill whole waves of one CTA per SM (wave quantisation costs up to 2x)
@@ -801,8 +801,8 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         const unsigned col_blocks = (unsigned)((C + DG_BN - 1) / DG_BN);
         static bool opted = false;
         if (!opted) {
-            CU(cudaFuncSetAttribute(dense_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM_BYTES));
-            CU(cudaFuncSetAttribute(dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM_BYTES));
+            CU(cudaFuncSetAttribute(dense_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DgFwd::SMEM_BYTES));
+            CU(cudaFuncSetAttribute(dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DgBwd::SMEM_BYTES));
             opted = true;
         }
         const double* X = (const double*)p->d_slots[dn.x_slot] + r0;  // column-major N x P: a row range is an offset
@@ -817,7 +817,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         fw.R = p->d_R; fw.ldr = ldg;
         fw.partial = p->d_partial + p->dense_partial_offset * ldg; fw.ldg = ldg;
         fw.flags = p->d_flags;
-        dense_fwd_kernel<<<dim3(col_blocks, (unsigned)p->dense_row_groups), DG_THREADS, DG_SMEM_BYTES, st>>>(fw);
+        dense_fwd_kernel<<<dim3(col_blocks, (unsigned)p->dense_row_groups), DgFwd::THREADS, DgFwd::SMEM_BYTES, st>>>(fw);
         p->launches++;
         const int k_fp = (int)p->rt.size();
         fp.p[k_fp].n_tiles = p->dense_row_groups;
@@ -847,7 +847,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
             bw.op.vec_ok = x_vec;
             bw.Gp = p->d_Gp; bw.ldg = ldg;
             bw.k_per_split = ((Nloc + p->dense_splits - 1) / p->dense_splits + DG_BK - 1) / DG_BK * DG_BK;
-            dense_bwd_kernel<<<dim3(col_blocks, (unsigned)((dn.P + DG_BM - 1) / DG_BM), (unsigned)p->dense_splits), DG_THREADS, DG_SMEM_BYTES, st>>>(bw);
+            dense_bwd_kernel<<<dim3(col_blocks, (unsigned)((dn.P + DG_BM - 1) / DG_BM), (unsigned)p->dense_splits), DgBwd::THREADS, DgBwd::SMEM_BYTES, st>>>(bw);
             p->launches++;
             if (sharded) {
                 // this rank's rows of X^T R go into the all-reduce buffer (rows 2 + NG ...); added to grad afterwards

@@ -22,14 +22,30 @@
 
 namespace jbugs {
 
-constexpr int DG_BM = 128, DG_BN = 128, DG_BK = 16, DG_STAGES = 3, DG_THREADS = 512;
+constexpr int DG_BN = 128, DG_BK = 16, DG_STAGES = 3;
 constexpr int DG_LDB = DG_BN + 4;   // Bs[k][n]
-constexpr int DG_LDA_M = DG_BM + 4; // As[k][m]   (A is M-major in memory: forward GEMM)
-constexpr int DG_LDA_K = DG_BK + 4; // As[m][k]   (A is K-major in memory: reverse GEMM)
-constexpr int DG_A_DOUBLES = (DG_BK * DG_LDA_M > DG_BM * DG_LDA_K) ? DG_BK * DG_LDA_M : DG_BM * DG_LDA_K;
-constexpr int DG_STAGE_DOUBLES = DG_A_DOUBLES + DG_BK * DG_LDB;
-constexpr size_t DG_SMEM_BYTES = (size_t)DG_STAGES * DG_STAGE_DOUBLES * sizeof(double);
-constexpr int DG_TM = 4, DG_TN = 4;  // MMA tiles per warp
+constexpr int DG_TM = 4, DG_TN = 4;  // MMA tiles per warp (32 x 32 warp tile)
+
+// CTA shape: BM x 128 x 16 with BM / 32 x 4 warps.  The reverse GEMM uses 128 x 128 (16 warps, one CTA per SM: 86 % of
+// the DMMA pipe); the forward GEMM uses 64 x 128 (8 warps, TWO CTAs per SM) so that the FP64 epilogue of one CTA --
+// ~15 % of a tile's time, K = P is short -- runs under the DMMA main loop of the other.
+template <int BM_>
+struct DgCfg {
+    static constexpr int BM = BM_;
+    static constexpr int THREADS = (BM_ / 32) * 4 * 32;
+    static constexpr int WM = BM_ / 32;
+    static constexpr int LDA_M = BM_ + 4;   // As[k][m]   (A is M-major in memory: forward GEMM)
+    static constexpr int LDA_K = DG_BK + 4; // As[m][k]   (A is K-major in memory: reverse GEMM)
+    static constexpr int A_DOUBLES = (DG_BK * LDA_M > BM_ * LDA_K) ? DG_BK * LDA_M : BM_ * LDA_K;
+    static constexpr int STAGE_DOUBLES = A_DOUBLES + DG_BK * DG_LDB;
+    static constexpr size_t SMEM_BYTES = (size_t)DG_STAGES * STAGE_DOUBLES * sizeof(double);
+    static constexpr int A_CH = BM_ * DG_BK / 2 / THREADS;    // 16-byte chunks of A per thread and slab
+    static constexpr int B_CH = DG_BK * DG_BN / 2 / THREADS;  // 16-byte chunks of B per thread and slab
+};
+using DgFwd = DgCfg<64>;
+using DgBwd = DgCfg<128>;
+constexpr int DG_BM = DgBwd::BM;          // row tile of the reverse GEMM (over P)
+constexpr int DG_FWD_BM = DgFwd::BM;      // row tile of the forward GEMM (over observations)
 
 __device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -54,20 +70,20 @@ struct DenseOperands {
 
 // ---- edge path: one BK-slab, 8-byte elements, bounds-checked, zero fill ---------------------------------------------
 // A_MMAJOR: A(m,k) = A[m + lda*k]; else A(m,k) = A[k + lda*m]
-template <bool A_MMAJOR>
+template <bool A_MMAJOR, class Cfg>
 __device__ __forceinline__ void dg_load_stage_edge(const DenseOperands& op, double* stage, long long m0, long long n0,
                                                    long long k0, long long k_end, int tid) {
     double* As = stage;
-    double* Bs = stage + DG_A_DOUBLES;
-    for (int q = tid; q < DG_BK * DG_BM; q += DG_THREADS) {
-        const int kk = A_MMAJOR ? q / DG_BM : q % DG_BK;
-        const int m = A_MMAJOR ? q % DG_BM : q / DG_BK;
-        double* dst = A_MMAJOR ? As + kk * DG_LDA_M + m : As + m * DG_LDA_K + kk;
+    double* Bs = stage + Cfg::A_DOUBLES;
+    for (int q = tid; q < DG_BK * Cfg::BM; q += Cfg::THREADS) {
+        const int kk = A_MMAJOR ? q / Cfg::BM : q % DG_BK;
+        const int m = A_MMAJOR ? q % Cfg::BM : q / DG_BK;
+        double* dst = A_MMAJOR ? As + kk * Cfg::LDA_M + m : As + m * Cfg::LDA_K + kk;
         const bool ok = (m0 + m < op.M) && (k0 + kk < k_end);
         if (ok) cp_async8(dst, A_MMAJOR ? op.A + (m0 + m) + op.lda * (k0 + kk) : op.A + (k0 + kk) + op.lda * (m0 + m));
         else *dst = 0.0;
     }
-    for (int q = tid; q < DG_BK * DG_BN; q += DG_THREADS) {
+    for (int q = tid; q < DG_BK * DG_BN; q += Cfg::THREADS) {
         const int kk = q / DG_BN, n = q % DG_BN;
         const bool ok = (n0 + n < op.N) && (k0 + kk < k_end);
         if (ok) cp_async8(Bs + kk * DG_LDB + n, op.B + (k0 + kk) * op.ldb + (n0 + n));
@@ -76,63 +92,72 @@ __device__ __forceinline__ void dg_load_stage_edge(const DenseOperands& op, doub
 }
 
 // ---- interior path: per-thread source pointers / shared offsets, two 16-byte chunks of A and two of B per slab ----------
+template <class Cfg>
 struct DgFastPtrs {
-    const double* a[2];
-    const double* b[2];
-    int sa[2], sb[2];  // offsets (doubles) inside a stage
+    const double* a[Cfg::A_CH];
+    const double* b[Cfg::B_CH];
+    int sa[Cfg::A_CH], sb[Cfg::B_CH];  // offsets (doubles) inside a stage
     long long a_step, b_step;
 };
 
-template <bool A_MMAJOR>
-__device__ __forceinline__ DgFastPtrs dg_fast_init(const DenseOperands& op, long long m0, long long n0, long long k0, int tid) {
-    DgFastPtrs f;
+template <bool A_MMAJOR, class Cfg>
+__device__ __forceinline__ DgFastPtrs<Cfg> dg_fast_init(const DenseOperands& op, long long m0, long long n0, long long k0, int tid) {
+    DgFastPtrs<Cfg> f;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int q = tid + h * DG_THREADS;  // 1024 chunks of 2 doubles per operand
+    for (int h = 0; h < Cfg::A_CH; ++h) {
+        const int q = tid + h * Cfg::THREADS;  // chunks of 2 doubles
         if (A_MMAJOR) {
-            const int kk = q / (DG_BM / 2), m = (q % (DG_BM / 2)) * 2;
+            const int kk = q / (Cfg::BM / 2), m = (q % (Cfg::BM / 2)) * 2;
             f.a[h] = op.A + (m0 + m) + op.lda * (k0 + kk);
-            f.sa[h] = kk * DG_LDA_M + m;
+            f.sa[h] = kk * Cfg::LDA_M + m;
         } else {
             const int m = q / (DG_BK / 2), kk = (q % (DG_BK / 2)) * 2;
             f.a[h] = op.A + (k0 + kk) + op.lda * (m0 + m);
-            f.sa[h] = m * DG_LDA_K + kk;
+            f.sa[h] = m * Cfg::LDA_K + kk;
         }
+    }
+#pragma unroll
+    for (int h = 0; h < Cfg::B_CH; ++h) {
+        const int q = tid + h * Cfg::THREADS;
         const int kb = q / (DG_BN / 2), n = (q % (DG_BN / 2)) * 2;
         f.b[h] = op.B + (k0 + kb) * op.ldb + (n0 + n);
-        f.sb[h] = DG_A_DOUBLES + kb * DG_LDB + n;
+        f.sb[h] = Cfg::A_DOUBLES + kb * DG_LDB + n;
     }
     f.a_step = A_MMAJOR ? op.lda * DG_BK : DG_BK;
     f.b_step = op.ldb * DG_BK;
     return f;
 }
 
-__device__ __forceinline__ void dg_fast_load(DgFastPtrs& f, double* stage) {
+template <class Cfg>
+__device__ __forceinline__ void dg_fast_load(DgFastPtrs<Cfg>& f, double* stage) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < Cfg::A_CH; ++h) {
         cp_async16(stage + f.sa[h], f.a[h]);
-        cp_async16(stage + f.sb[h], f.b[h]);
         f.a[h] += f.a_step;
+    }
+#pragma unroll
+    for (int h = 0; h < Cfg::B_CH; ++h) {
+        cp_async16(stage + f.sb[h], f.b[h]);
         f.b[h] += f.b_step;
     }
 }
 
 // acc[tm][tn][2] += A_tile * B_tile over k in [k_begin, k_end)
-template <bool A_MMAJOR>
+template <bool A_MMAJOR, class Cfg>
 __device__ __forceinline__ void dg_mainloop(const DenseOperands& op, double* smem, long long m0, long long n0,
                                             long long k_begin, long long k_end, double (&acc)[DG_TM][DG_TN][2]) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;  // 4 x 4 warps
+    const int wm = warp >> 2, wn = warp & 3;  // (BM / 32) x 4 warps
     const int fr = lane >> 2, fk = lane & 3;  // fragment row / k index
     const long long nk = (k_end - k_begin + DG_BK - 1) / DG_BK;
     // interior tile with aligned operands: every slab but a ragged last one goes through the fast loader
-    const bool interior = op.vec_ok && (m0 + DG_BM <= op.M) && (n0 + DG_BN <= op.N) && (((k_begin & 1) == 0) || A_MMAJOR);
+    const bool interior = op.vec_ok && (m0 + Cfg::BM <= op.M) && (n0 + DG_BN <= op.N) && (((k_begin & 1) == 0) || A_MMAJOR);
     const long long nk_fast = interior ? (k_end - k_begin) / DG_BK : 0;
-    DgFastPtrs fp = dg_fast_init<A_MMAJOR>(op, m0, n0, k_begin, tid);
+    DgFastPtrs<Cfg> fp = dg_fast_init<A_MMAJOR, Cfg>(op, m0, n0, k_begin, tid);
     auto load = [&](long long slab) {
-        double* stage = smem + (slab % DG_STAGES) * DG_STAGE_DOUBLES;
-        if (slab < nk_fast) dg_fast_load(fp, stage);
-        else dg_load_stage_edge<A_MMAJOR>(op, stage, m0, n0, k_begin + slab * DG_BK, k_end, tid);
+        double* stage = smem + (slab % DG_STAGES) * Cfg::STAGE_DOUBLES;
+        if (slab < nk_fast) dg_fast_load<Cfg>(fp, stage);
+        else dg_load_stage_edge<A_MMAJOR, Cfg>(op, stage, m0, n0, k_begin + slab * DG_BK, k_end, tid);
     };
     for (int s = 0; s < DG_STAGES - 1; ++s) {
         if (s < nk) load(s);
@@ -144,15 +169,15 @@ __device__ __forceinline__ void dg_mainloop(const DenseOperands& op, double* sme
         const long long pf = kt + DG_STAGES - 1;  // refill the stage consumed at iteration kt - 1
         if (pf < nk) load(pf);
         cp_async_commit();
-        const double* As = smem + (kt % DG_STAGES) * DG_STAGE_DOUBLES;
-        const double* Bs = As + DG_A_DOUBLES;
+        const double* As = smem + (kt % DG_STAGES) * Cfg::STAGE_DOUBLES;
+        const double* Bs = As + Cfg::A_DOUBLES;
 #pragma unroll
         for (int ks = 0; ks < DG_BK / 4; ++ks) {
             double a[DG_TM], b[DG_TN];
 #pragma unroll
             for (int tm = 0; tm < DG_TM; ++tm) {
                 const int m = wm * 32 + tm * 8 + fr, k = ks * 4 + fk;
-                a[tm] = A_MMAJOR ? As[k * DG_LDA_M + m] : As[m * DG_LDA_K + k];
+                a[tm] = A_MMAJOR ? As[k * Cfg::LDA_M + m] : As[m * Cfg::LDA_K + k];
             }
 #pragma unroll
             for (int tn = 0; tn < DG_TN; ++tn) b[tn] = Bs[(ks * 4 + fk) * DG_LDB + wn * 32 + tn * 8 + fr];
@@ -180,25 +205,26 @@ struct DenseFwdParams {
     int* flags;
 };
 
-__global__ void __launch_bounds__(DG_THREADS, 1)
+__global__ void __launch_bounds__(DgFwd::THREADS, 2)
 dense_fwd_kernel(const __grid_constant__ DenseFwdParams P) {
+    using Cfg = DgFwd;
     extern __shared__ double smem[];
-    __shared__ double red[4][DG_BN];
+    __shared__ double red[Cfg::WM][DG_BN];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3, fr = lane >> 2, fk = lane & 3;
     const long long n0 = (long long)blockIdx.x * DG_BN;
-    const long long m_tiles = (P.op.M + DG_BM - 1) / DG_BM;
+    const long long m_tiles = (P.op.M + Cfg::BM - 1) / Cfg::BM;
     double lp[DG_TN][2];  // per-thread log-density sums for its 4 x 2 chain columns
 #pragma unroll
     for (int tn = 0; tn < DG_TN; ++tn) lp[tn][0] = lp[tn][1] = 0.0;
     for (long long mt = blockIdx.y; mt < m_tiles; mt += gridDim.y) {
-        const long long m0 = mt * DG_BM;
+        const long long m0 = mt * Cfg::BM;
         double acc[DG_TM][DG_TN][2];
 #pragma unroll
         for (int tm = 0; tm < DG_TM; ++tm)
 #pragma unroll
             for (int tn = 0; tn < DG_TN; ++tn) acc[tm][tn][0] = acc[tm][tn][1] = 0.0;
-        dg_mainloop<true>(P.op, smem, m0, n0, 0, P.op.K, acc);
+        dg_mainloop<true, Cfg>(P.op, smem, m0, n0, 0, P.op.K, acc);
         // epilogue: C fragment element (row = fr, col = 2*fk + {0,1}) of MMA tile (tm, tn)
 #pragma unroll
         for (int tm = 0; tm < DG_TM; ++tm) {
@@ -247,7 +273,12 @@ dense_fwd_kernel(const __grid_constant__ DenseFwdParams P) {
     __syncthreads();
     if (tid < DG_BN) {
         const long long c = n0 + tid;
-        if (c < P.op.N) P.partial[(long long)blockIdx.y * P.ldg + c] = ((red[0][tid] + red[1][tid]) + red[2][tid]) + red[3][tid];
+        if (c < P.op.N) {
+            double v = red[0][tid];
+#pragma unroll
+            for (int w = 1; w < Cfg::WM; ++w) v += red[w][tid];  // fixed order over the M-warps
+            P.partial[(long long)blockIdx.y * P.ldg + c] = v;
+        }
     }
 }
 
@@ -260,8 +291,9 @@ struct DenseBwdParams {
     long long k_per_split;
 };
 
-__global__ void __launch_bounds__(DG_THREADS, 1)
+__global__ void __launch_bounds__(DgBwd::THREADS, 1)
 dense_bwd_kernel(const __grid_constant__ DenseBwdParams P) {
+    using Cfg = DgBwd;
     extern __shared__ double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3, fr = lane >> 2, fk = lane & 3;
@@ -273,7 +305,7 @@ dense_bwd_kernel(const __grid_constant__ DenseBwdParams P) {
     for (int tm = 0; tm < DG_TM; ++tm)
 #pragma unroll
         for (int tn = 0; tn < DG_TN; ++tn) acc[tm][tn][0] = acc[tm][tn][1] = 0.0;
-    if (kb < ke) dg_mainloop<false>(P.op, smem, m0, n0, kb, ke, acc);
+    if (kb < ke) dg_mainloop<false, Cfg>(P.op, smem, m0, n0, kb, ke, acc);
     double* out = P.Gp + (long long)blockIdx.z * P.op.M * P.ldg;
 #pragma unroll
     for (int tm = 0; tm < DG_TM; ++tm) {
