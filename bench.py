@@ -271,8 +271,10 @@ def main():
         theta[r0:r1] = th0_d[r0:r1, None] + 0.05 * torch.randn((r1 - r0, ld), dtype=torch.float64, device=dev, generator=g)
     grad.zero_()
     torch.cuda.synchronize()
-    stream = torch.cuda.current_stream().cuda_stream
-
+    # a real (non-default) stream: the kernels are launched on it and the events of the timed region recorded on it
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(side)
+    stream = side.cuda_stream
     def step(flags=1):
         cp.eval_raw(theta.data_ptr(), ld, C, 0, logp.data_ptr(), grad.data_ptr(), status.data_ptr(), True, flags, stream)
 

@@ -100,7 +100,10 @@ int jbugs_plan_set_dense_shard(jbugs_plan* plan, int64_t i0, int64_t i1);
  *   grad   : same layout/ld as theta, out (ignored when want_grad == 0; may be NULL then)
  *   status : C int32 out (jbugs_chain_status), may be NULL
  *   stream : cudaStream_t (NULL = default stream).  The call returns after the stream has been
- *            synchronized unless flags & JBUGS_EVAL_ASYNC and every buffer is a device pointer. */
+ *            synchronized unless flags & JBUGS_EVAL_ASYNC and every buffer is a device pointer.
+ *            The launch sequence contains no host synchronisation once the plan is warm, so an
+ *            ASYNC call on a non-default stream can be captured into a CUDA graph by the caller
+ *            (the on-device sampler does exactly that, jbugs_hmc_run). */
 #define JBUGS_EVAL_ASYNC 1
 int jbugs_eval_batch(jbugs_plan* plan, const double* theta, int64_t ld, int64_t C, int layout,
                      double* logp, double* grad, int32_t* status, int want_grad, int flags,

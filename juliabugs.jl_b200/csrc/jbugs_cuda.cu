@@ -569,6 +569,7 @@ extern "C" int jbugs_plan_upload_data(jbugs_plan* p, int slot, const void* src, 
     int rc = set_device(p);
     if (rc) return rc;
     CU(cudaMemcpy(p->d_slots[slot], src, nbytes, cudaMemcpyDefault));
+    p->epoch++;  // data-only constants baked into captured launch sequences are stale now
     p->uploaded[slot] = 1;
     // new observations: constants of the fused paths (and their validity check) must be redone
     p->dense_const_dirty = true;

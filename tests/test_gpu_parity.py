@@ -81,3 +81,4 @@ def test_rats_scaled(N, C):
     th0[6::2] = alpha
     theta = random_thetas(th0, C, seed=3, scale=0.05)
     _check(m.cuda, co, theta)
+
