@@ -158,6 +158,14 @@ int jbugs_hmc_run(jbugs_hmc* hmc, int n_iter, int n_leapfrog, int adapt, const i
                   double* out_host, double* mean_accept);
 int jbugs_hmc_get_state(jbugs_hmc* hmc, double* theta_host /* [D][C] */, double* logp_host /* [C] */, double* step_size,
                         double* var_host /* [D] diagonal of the inverse metric */);
+/*   jbugs_hmc_run_nuts : same, with the No-U-Turn transition the reference uses (`NUTS(0.8)`): multinomial sampling
+ *                    along the trajectory, generalised U-turn criterion, at most max_depth (<= 12) doublings.  All chains
+ *                    build their trees in lock step; a chain that has finished waits for the deepest tree of the batch.
+ *                    Tree state: (12 + 2 x 12) x D x C doubles, so this is for small and medium models.
+ *   jbugs_hmc_nuts_stats : divergent transitions so far, mean tree depth of the last transition. */
+int jbugs_hmc_run_nuts(jbugs_hmc* hmc, int n_iter, int max_depth, int adapt, const int64_t* monitor_rows, int n_monitor,
+                       double* out_host, double* mean_accept);
+int jbugs_hmc_nuts_stats(jbugs_hmc* hmc, int64_t* n_divergent, double* mean_depth);
 
 #ifdef __cplusplus
 }

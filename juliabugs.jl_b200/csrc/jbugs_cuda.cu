@@ -17,6 +17,7 @@
 #include "jbugs_obsconst.cuh"
 #include "jbugs_dense.cuh"
 #include "jbugs_hmc.cuh"
+#include "jbugs_nuts.cuh"
 #define JBUGS_SPEC_TABLE
 #include "jbugs_specs.cuh"
 
@@ -961,6 +962,7 @@ extern "C" int jbugs_eval_batch(jbugs_plan* p, const double* theta, int64_t ld, 
 }
 
 #include "jbugs_hmc.inc"
+#include "jbugs_nuts.inc"
 
 extern "C" int jbugs_batch_alloc(jbugs_plan* p, int64_t C, double** theta_dev, double** grad_dev, double** logp_dev,
                                  int32_t** status_dev, int64_t* ld) {

@@ -25,7 +25,7 @@ SYMBOLS = [
     "jbugs_batch_free", "jbugs_host_alloc", "jbugs_host_free", "jbugs_comm_unique_id", "jbugs_comm_init",
     "jbugs_comm_destroy", "jbugs_launch_count", "jbugs_plan_describe", "jbugs_plan_set_option",
     "jbugs_last_timing", "jbugs_hmc_create", "jbugs_hmc_destroy", "jbugs_hmc_init", "jbugs_hmc_run",
-    "jbugs_hmc_get_state",
+    "jbugs_hmc_get_state", "jbugs_hmc_run_nuts", "jbugs_hmc_nuts_stats",
 ]
 
 

@@ -27,12 +27,24 @@ class HMC:
 
 
 @dataclass
+class NUTS:
+    """No-U-Turn sampler, the reference's default (`NUTS(0.8)`): dynamic trajectory length by tree doubling up to
+    `max_depth`, multinomial sampling, generalised U-turn criterion; step size adapted to the target acceptance
+    statistic 0.8 and a diagonal metric, as for `HMC`."""
+    max_depth: int = 10
+    step_size: float = 0.01
+    jitter: float = 0.1
+
+
+@dataclass
 class Chains:
     names: List[str]
     samples: np.ndarray          # [n_samples, n_monitored, n_chains], constrained space
     accept_rate: float
     step_size: float
     model: Optional[BUGSModel] = None
+    n_divergent: int = 0
+    tree_depth: float = 0.0     # NUTS: mean tree depth of the last transition
     _gq: Optional[Dict[str, np.ndarray]] = None
 
     def __getitem__(self, name: str) -> np.ndarray:
@@ -72,6 +84,8 @@ def _bind(L):
     L.jbugs_hmc_init.argtypes = [c.c_void_p, c.c_void_p, c.c_double, c.c_double]
     L.jbugs_hmc_run.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_int, c.c_void_p, c.POINTER(c.c_double)]
     L.jbugs_hmc_get_state.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.POINTER(c.c_double), c.c_void_p]
+    L.jbugs_hmc_run_nuts.argtypes = L.jbugs_hmc_run.argtypes
+    L.jbugs_hmc_nuts_stats.argtypes = [c.c_void_p, c.POINTER(c.c_int64), c.POINTER(c.c_double)]
 
 
 def _constrain(tr, lb, ub, y):
@@ -84,7 +98,7 @@ def _constrain(tr, lb, ub, y):
     return y
 
 
-def sample(model: BUGSModel, sampler: HMC, n_samples: int, n_adapts: int = 500, n_chains: int = 256, seed: int = 1234,
+def sample(model: BUGSModel, sampler, n_samples: int, n_adapts: int = 500, n_chains: int = 256, seed: int = 1234,
            monitor: Optional[Sequence[str]] = None, init: Optional[np.ndarray] = None) -> Chains:
     """`AbstractMCMC.sample(model, sampler, n_samples; n_adapts, ...)` for `n_chains` lock-step chains.
     `monitor`: parameter labels to record ('tau', 'beta[2]', 'alpha[17]'); default: every scalar parameter."""
@@ -112,15 +126,21 @@ def sample(model: BUGSModel, sampler: HMC, n_samples: int, n_adapts: int = 500, 
     try:
         _check(L.jbugs_hmc_init(h, th0.ctypes.data, sampler.jitter, sampler.step_size))
         acc = ctypes.c_double()
+        nuts = isinstance(sampler, NUTS)
+        run = L.jbugs_hmc_run_nuts if nuts else L.jbugs_hmc_run
+        length = sampler.max_depth if nuts else sampler.n_leapfrog
         if n_adapts > 0:
-            _check(L.jbugs_hmc_run(h, n_adapts, sampler.n_leapfrog, 1, None, 0, None, ctypes.byref(acc)))
+            _check(run(h, n_adapts, length, 1, None, 0, None, ctypes.byref(acc)))
         out = np.empty((n_samples, len(names), n_chains))
-        _check(L.jbugs_hmc_run(h, n_samples, sampler.n_leapfrog, 0, rows.ctypes.data, len(names), out.ctypes.data, ctypes.byref(acc)))
+        _check(run(h, n_samples, length, 0, rows.ctypes.data, len(names), out.ctypes.data, ctypes.byref(acc)))
         eps = ctypes.c_double()
         _check(L.jbugs_hmc_get_state(h, None, None, ctypes.byref(eps), None))
+        n_div, depth = ctypes.c_int64(), ctypes.c_double()
+        _check(L.jbugs_hmc_nuts_stats(h, ctypes.byref(n_div), ctypes.byref(depth)))
     finally:
         L.jbugs_hmc_destroy(h)
     for k, n in enumerate(names):
         _, tr_k, lb, ub = by_name[n]
         out[:, k, :] = _constrain(tr_k, lb, ub, out[:, k, :])
-    return Chains(names, out, float(acc.value), float(eps.value), model)
+    return Chains(names, out, float(acc.value), float(eps.value), model, n_divergent=int(n_div.value),
+                  tree_depth=float(depth.value))

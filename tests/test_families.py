@@ -98,3 +98,70 @@ def test_cuda_matches_c_oracle(name):
     _check(m.cuda, COracle(m.plan), theta)
     theta[0, 3] = 6.0   # one chain far out in the tail: finite on both sides, or flagged identically
     _check(m.cuda, COracle(m.plan), theta)
+
+
+# ---- single-node models against an independent implementation (scipy.stats), in both spaces: the shape of the
+# reference's own per-distribution tests (J/test/model/evaluation.jl:167-352: logpdf + logabsdetjac of the bijector)
+def _scipy_cases():
+    from scipy import stats as S
+    return [
+        # (BUGS call, scipy distribution, support (lb, ub) or None for the real line / discrete, test value)
+        ("dnorm(1.5, 4.0)", S.norm(1.5, 0.5), None, 0.7),
+        ("dgamma(0.001, 0.001)", S.gamma(0.001, scale=1000.0), (0.0, np.inf), np.exp(10.0)),
+        ("dgamma(3.0, 2.0)", S.gamma(3.0, scale=0.5), (0.0, np.inf), 1.3),
+        ("dexp(2.5)", S.expon(scale=0.4), (0.0, np.inf), 0.9),
+        ("dunif(-1.0, 3.0)", S.uniform(-1.0, 4.0), (-1.0, 3.0), 0.25),
+        ("dbeta(2.0, 5.0)", S.beta(2.0, 5.0), (0.0, 1.0), 0.3),
+        ("dlnorm(0.5, 4.0)", S.lognorm(s=0.5, scale=np.exp(0.5)), (0.0, np.inf), 2.2),
+        ("dlogis(0.5, 4.0)", S.logistic(0.5, 0.5), None, -0.4),
+        ("ddexp(0.5, 4.0)", S.laplace(0.5, 0.5), None, 1.9),
+        ("dweib(1.7, 0.8)", S.weibull_min(1.7, scale=1.25), (0.0, np.inf), 0.6),
+        ("dchisqr(5)", S.chi2(5), (0.0, np.inf), 3.3),
+        ("dbern(0.3)", S.bernoulli(0.3), "discrete", 1.0),
+        ("dbin(0.1, 10)", S.binom(10, 0.1), "discrete", 2.0),
+        ("dpois(3.5)", S.poisson(3.5), "discrete", 4.0),
+        ("dnegbin(0.4, 3)", S.nbinom(3, 0.4), "discrete", 5.0),
+    ]
+
+
+def _reference_logp(dist, support, x):
+    """(untransformed logp, transformed logp, theta in the transformed space)"""
+    if support == "discrete":
+        return dist.logpmf(x), dist.logpmf(x), x
+    lp = dist.logpdf(x)
+    if support is None:
+        return lp, lp, x
+    lb, ub = support
+    if np.isfinite(ub):
+        u = (x - lb) / (ub - lb)
+        return lp, lp + np.log((x - lb) * (ub - x) / (ub - lb)), np.log(u) - np.log1p(-u)
+    return lp, lp + np.log(x - lb), np.log(x - lb)
+
+
+@pytest.mark.parametrize("k", range(15))
+def test_single_node_models_against_scipy(k):
+    call, dist, support, x = _scipy_cases()[k]
+    text = "model { a ~ %s }" % call
+    lp_u, lp_t, y = _reference_logp(dist, support, x)
+    gm = go.compile(text, {}, {"a": x})
+    assert gm.getparams()[0] == pytest.approx(y, rel=1e-13, abs=1e-13)
+    assert gm.logdensity(gm.getparams()) == pytest.approx(lp_t, rel=1e-11)
+    gu = go.compile(text, {}, {"a": x}, transformed=False)
+    assert gu.logdensity(gu.getparams()) == pytest.approx(lp_u, rel=1e-11)
+    for transformed, th, ref in ((True, y, lp_t), (False, x, lp_u)):
+        plan, _ = jbugs.lower(text, {}, transformed=transformed)
+        lp, _, st = COracle(plan).eval_batch(np.array([[th]]))
+        assert st[0] == 0 and lp[0] == pytest.approx(ref, rel=1e-11)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", range(15))
+def test_single_node_models_against_scipy_cuda(k):
+    call, dist, support, x = _scipy_cases()[k]
+    text = "model { a ~ %s }" % call
+    lp_u, lp_t, y = _reference_logp(dist, support, x)
+    m = jbugs.compile(text, {}, {"a": x})
+    assert jbugs.getparams(m)[0] == pytest.approx(y, rel=1e-13, abs=1e-13)
+    assert jbugs.LogDensityProblems.logdensity(m, jbugs.getparams(m)) == pytest.approx(lp_t, rel=1e-11)
+    mu = jbugs.settrans(m, False)
+    assert jbugs.LogDensityProblems.logdensity(mu, jbugs.getparams(mu)) == pytest.approx(lp_u, rel=1e-11)

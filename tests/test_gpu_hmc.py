@@ -83,3 +83,38 @@ def test_monitoring_plate_level_parameters(fixtures):
     assert ch.mean("theta[1]") == pytest.approx(0.0598, rel=0.1)
     assert ch.mean("theta[10]") == pytest.approx(1.99, rel=0.1)
     assert ch.mean("alpha") == pytest.approx(0.70, rel=0.15) and ch.mean("beta") == pytest.approx(0.93, rel=0.2)
+
+
+def test_nuts_conjugate_normal():
+    """NUTS on an exactly known posterior: y_i ~ N(mu, 1) -> N(ybar, 1/n)."""
+    rng = np.random.default_rng(0)
+    y = rng.normal(1.7, 1.0, 400)
+    text = "model { for (i in 1:N) { y[i] ~ dnorm(mu, 1.0) }\n mu ~ dnorm(0.0, 1.0E-6) }"
+    m = jbugs.compile(text, {"N": 400, "y": y}, {"mu": 0.0})
+    ch = hmc.sample(m, hmc.NUTS(max_depth=8, step_size=0.05), n_samples=400, n_adapts=300, n_chains=512, seed=3)
+    mu = ch["mu"]
+    assert abs(mu.mean() - y.mean()) < 5e-3
+    assert abs(mu.std() - 1.0 / np.sqrt(400)) < 0.08 / np.sqrt(400)
+    assert 0.6 < ch.accept_rate <= 1.0 and ch.n_divergent == 0 and 1.0 <= ch.tree_depth <= 4.0
+
+
+def test_nuts_rats_and_seeds_match_winbugs_reference(fixtures):
+    """the reference's own sampler test (NUTS(0.8), 1000 + 1000, rtol 0.3 on mean and std) for Rats and Seeds."""
+    fx = fixtures["rats"]
+    m = jbugs.compile(jbugs.examples.RATS, fx["data"], fx["inits"])
+    ch = hmc.sample(m, hmc.NUTS(max_depth=8, step_size=0.005, jitter=0.05), n_samples=500, n_adapts=1000, n_chains=128, seed=21)
+    alpha0 = ch["alpha0"]        # generated quantity: alpha.c - xbar * beta.c
+    sigma = ch["sigma"]
+    ref = {"alpha0": (106.6, 3.66), "beta.c": (6.186, 0.1086), "sigma": (6.093, 0.4643)}
+    got = {"alpha0": alpha0, "beta.c": ch["beta.c"], "sigma": sigma}
+    for k, (mean, std) in ref.items():
+        assert got[k].mean() == pytest.approx(mean, rel=0.02), k
+        assert got[k].std() == pytest.approx(std, rel=0.12), k
+    assert 0.6 < ch.accept_rate < 0.95
+    fx = fixtures["seeds"]
+    m = jbugs.compile(jbugs.examples.SEEDS, fx["data"], fx["inits"])
+    ch = hmc.sample(m, hmc.NUTS(max_depth=8, step_size=0.01, jitter=0.05), n_samples=500, n_adapts=1000, n_chains=128, seed=22)
+    ref = {"alpha0": (-0.5499, 0.1965), "alpha1": (0.08902, 0.3124), "alpha12": (-0.841, 0.4372), "alpha2": (1.356, 0.2772)}
+    for k, (mean, std) in ref.items():
+        assert abs(ch.mean(k) - mean) < 0.2 * std, k
+        assert ch.std(k) == pytest.approx(std, rel=0.12), k
