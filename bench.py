@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--dynamic", type=int, default=0, help="1 = force the interpreter kernel")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--tma", type=int, default=-1, help="0 = stage plate data with cp.async only (A/B against the TMA path)")
+    ap.add_argument("--logdensity-only", action="store_true", help="time logdensity without the gradient (the reference benchmark's first column)")
     ap.add_argument("--opt", default="", help="comma-separated key=value options passed to jbugs_plan_set_option (A/B runs)")
     ap.add_argument("--shard", default="", choices=["", "chains", "obs"],
                     help="N>1: 'chains' = every GPU its own chains (weak, no collective; default for rats); "
@@ -275,8 +276,12 @@ def main():
     side = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(side)
     stream = side.cuda_stream
+    want_grad = not args.logdensity_only
+    if not want_grad:
+        config["evaluation"] = "logdensity only (no gradient): theta is read, nothing but logp is written"
+
     def step(flags=1):
-        cp.eval_raw(theta.data_ptr(), ld, C, 0, logp.data_ptr(), grad.data_ptr(), status.data_ptr(), True, flags, stream)
+        cp.eval_raw(theta.data_ptr(), ld, C, 0, logp.data_ptr(), grad.data_ptr(), status.data_ptr(), want_grad, flags, stream)
 
     step(0)  # first call also builds the one-off data constants
     log("[bench] " + cp.describe().replace("\n", " | "))
@@ -340,7 +345,7 @@ def main():
         peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, which = 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
-    alg_bytes = 2.0 * 8.0 * C * D_local
+    alg_bytes = (2.0 if want_grad else 1.0) * 8.0 * C * D_local
     pk_ms = float(np.mean(plate_ms))
     achieved = alg_bytes / (pk_ms * 1e-3) / 1e9
     traffic, traffic_note = None, None
@@ -384,7 +389,7 @@ def main():
                     "traffic": None, "kernel": "dense_fwd_kernel + dense_bwd_kernel (DMMA m8n8k4 f64)", "kernel_ms": pk_ms,
                     "algorithmic_flops": flops, "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul f64) measured in this run, best of 3"}
 
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+    out = {"metric": METRIC if want_grad else "logdensity obs-evals/s", "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "roofline": roofline,
            "gpu_launches": launches_per_step * K}
