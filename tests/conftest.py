@@ -37,4 +37,9 @@ def fixtures():
 def rel_err(a, b, floor=1e-300):
     a = np.asarray(a, dtype=float)
     b = np.asarray(b, dtype=float)
-    return float(np.max(np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor))) if a.size else 0.0
+    if not a.size:
+        return 0.0
+    same = (a == b) | (np.isnan(a) & np.isnan(b))  # identical values, including equal infinities (-Inf log densities)
+    with np.errstate(invalid="ignore"):
+        err = np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)
+    return float(np.max(np.where(same, 0.0, err)))

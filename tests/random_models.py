@@ -1,0 +1,120 @@
+"""Seeded generator of random BUGS models inside the plate class (used by tests/test_random_models.py).
+
+Every model is one observation plate (one or two loops) with a random observation family and link, a linear predictor
+made of global coefficients x data covariates, group-level and observation-level random effects and a data offset,
+random priors for the random effects (constant, data or global arguments) and for the globals (real-line, positive
+and bounded supports, scalar logical nodes).  The point is coverage of combinations nobody wrote a fixture for."""
+import numpy as np
+
+OBS = [
+    # (name, statement template, link options, aux globals [(name, prior)], y generator)
+    ("normal", "y[{ix}] ~ dnorm(mu[{ix}], tau.y)", ["identity"], [("tau.y", "dgamma(2, 2)")],
+     lambda rng, shp: rng.normal(0.3, 1.0, shp)),
+    ("logistic", "y[{ix}] ~ dlogis(mu[{ix}], tau.y)", ["identity"], [("tau.y", "dgamma(2, 2)")],
+     lambda rng, shp: rng.logistic(0.3, 1.0, shp)),
+    ("laplace", "y[{ix}] ~ ddexp(mu[{ix}], tau.y)", ["identity"], [("tau.y", "dexp(1.0)")],
+     lambda rng, shp: rng.laplace(0.3, 1.0, shp)),
+    ("lognormal", "y[{ix}] ~ dlnorm(mu[{ix}], tau.y)", ["identity"], [("tau.y", "dgamma(2, 2)")],
+     lambda rng, shp: rng.lognormal(0.1, 0.7, shp)),
+    ("bernoulli", "y[{ix}] ~ dbern(mu[{ix}])", ["logit", "probit", "cloglog"], [],
+     lambda rng, shp: (rng.random(shp) < 0.4).astype(float)),
+    ("binomial", "y[{ix}] ~ dbin(mu[{ix}], n[{ix}])", ["logit", "probit", "cloglog"], [],
+     lambda rng, shp: rng.integers(0, 6, shp).astype(float)),
+    ("poisson", "y[{ix}] ~ dpois(mu[{ix}])", ["log"], [],
+     lambda rng, shp: rng.poisson(2.0, shp).astype(float)),
+    ("negbin", "y[{ix}] ~ dnegbin(mu[{ix}], r.y)", ["logit"], [("r.y", "dgamma(3, 1)")],
+     lambda rng, shp: rng.negative_binomial(3, 0.5, shp).astype(float)),
+    ("gamma", "y[{ix}] ~ dgamma(a.y, mu[{ix}])", ["log"], [("a.y", "dgamma(3, 1)")],
+     lambda rng, shp: rng.gamma(2.0, 0.8, shp) + 0.01),
+    ("weibull", "y[{ix}] ~ dweib(a.y, mu[{ix}])", ["log"], [("a.y", "dgamma(3, 2)")],
+     lambda rng, shp: rng.weibull(1.4, shp) + 0.02),
+    ("exponential", "y[{ix}] ~ dexp(mu[{ix}])", ["log"], [],
+     lambda rng, shp: rng.exponential(0.8, shp) + 0.01),
+]
+LINK_LHS = {"identity": "mu[{ix}]", "logit": "logit(mu[{ix}])", "probit": "probit(mu[{ix}])",
+            "cloglog": "cloglog(mu[{ix}])", "log": "log(mu[{ix}])"}
+GLOBAL_PRIORS = ["dnorm(0.0, 0.5)", "dnorm(0.2, 2.0)", "dlogis(0.0, 1.0)", "ddexp(0.0, 1.0)", "dunif(-3.0, 3.0)"]
+POS_PRIORS = ["dgamma(2, 2)", "dexp(1.0)", "dlnorm(0.0, 1.0)", "dweib(1.5, 1.0)", "dchisqr(3)", "dunif(0.1, 4.0)"]
+
+
+def make(seed, n_max=12):
+    """-> (model text, data dict, description)"""
+    rng = np.random.default_rng(1000 + seed)
+    two = bool(rng.integers(0, 2))
+    N = int(rng.integers(1, n_max))
+    T = int(rng.integers(1, 4)) if two else 1
+    shp = (N, T) if two else (N,)
+    ix = "i, j" if two else "i"
+    name, obs_stmt, links, aux, ygen = OBS[int(rng.integers(0, len(OBS)))]
+    link = links[int(rng.integers(0, len(links)))]
+    data = {"N": N, "y": ygen(rng, shp)}
+    if two:
+        data["T"] = T
+    if name == "binomial":
+        data["n"] = data["y"] + rng.integers(0, 5, shp).astype(float)
+    globals_, body, tail, terms = [], [], [], []
+    # global coefficients
+    ng = int(rng.integers(1, 4))
+    for k in range(ng):
+        g = f"b{k}"
+        globals_.append((g, GLOBAL_PRIORS[int(rng.integers(0, len(GLOBAL_PRIORS)))]))
+        kind = int(rng.integers(0, 4)) if k else 0
+        if kind == 0:
+            terms.append(g)
+        elif kind == 1:
+            data[f"x{k}"] = rng.standard_normal(N)
+            terms.append(f"{g} * x{k}[i]")
+        elif kind == 2 and two:
+            data[f"z{k}"] = rng.standard_normal(T)
+            terms.append(f"{g} * (z{k}[j] - zbar{k})")
+            data[f"zbar{k}"] = float(rng.standard_normal())
+        else:
+            data[f"w{k}"] = rng.standard_normal(shp)
+            terms.append(f"{g} * w{k}[{ix}] / 2")
+    # group-level random effects
+    for k in range(int(rng.integers(0, 3))):
+        l = f"u{k}"
+        choice = int(rng.integers(0, 4))
+        if choice == 0:
+            prior = "dnorm(0.0, 1.0)"
+        elif choice == 1:
+            globals_.append((f"m.{l}", "dnorm(0.0, 1.0)"))
+            globals_.append((f"t.{l}", POS_PRIORS[int(rng.integers(0, len(POS_PRIORS)))]))
+            prior = f"dnorm(m.{l}, t.{l})"
+        elif choice == 2:
+            data[f"pm.{l}"] = 0.3 * rng.standard_normal(N)
+            prior = f"dlogis(pm.{l}[i], 2.0)"
+        else:
+            globals_.append((f"s.{l}", "dunif(0.2, 3.0)"))
+            tail.append(f"t.{l} <- 1 / (s.{l} * s.{l})")
+            prior = f"ddexp(0.0, t.{l})"
+        body.append(f"{l}[i] ~ {prior}")
+        if two and rng.integers(0, 2):
+            data[f"c.{l}"] = rng.standard_normal(T)
+            terms.append(f"{l}[i] * c.{l}[j]")
+        else:
+            terms.append(f"{l}[i]")
+    # observation-level random effect
+    inner = []
+    if two and rng.integers(0, 2):
+        globals_.append(("t.e", "dgamma(2, 2)"))
+        inner.append("e[i, j] ~ dnorm(0.0, t.e)")
+        terms.append("e[i, j]")
+    if rng.integers(0, 2):
+        data["off"] = 0.2 * rng.standard_normal(shp)
+        terms.append(f"off[{ix}]")
+    globals_ += aux
+    pred = " + ".join(terms)
+    stmts = [obs_stmt.format(ix=ix), f"{LINK_LHS[link].format(ix=ix)} <- {pred}"] + inner
+    lines = ["model {", "  for (i in 1:N) {"]
+    if two:
+        lines.append("    for (j in 1:T) {")
+        lines += ["      " + s for s in stmts]
+        lines.append("    }")
+    else:
+        lines += ["    " + s for s in stmts]
+    lines += ["    " + s for s in body]
+    lines.append("  }")
+    lines += [f"  {g} ~ {p}" for g, p in globals_] + ["  " + t for t in tail]
+    lines.append("}")
+    return "\n".join(lines), data, f"{name}/{link} N={N} T={T}"

@@ -26,7 +26,9 @@ def _check(cp, co, theta, layout="chain_fast", tol=TOL):
     lp0, g0, st0 = co.eval_batch(theta, layout=layout)
     assert np.array_equal(st, st0)
     assert rel_err(lp, lp0) < tol, (lp[:4], lp0[:4])
-    assert grad_err(g, g0) < tol
+    ok = np.isfinite(lp0)  # a chain at -Inf (outside the support, not a DomainError) has no meaningful gradient
+    if ok.any():
+        assert grad_err(g[:, ok], g0[:, ok]) < tol
     return lp, g
 
 

@@ -1,0 +1,55 @@
+"""Randomly generated models of the plate class: per-node oracle == lowered plan through the C restatement (CPU), and
+CUDA kernels (interpreter and, when one matches, static spec) == C restatement (GPU).  Combinations of families, links,
+loop nests, random-effect levels and prior argument kinds that no fixture covers."""
+import numpy as np
+import pytest
+
+import graph_oracle as go
+import jbugs
+from c_oracle import COracle
+from conftest import rel_err
+from helpers import random_thetas
+from random_models import make
+
+SEEDS = list(range(96))
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_random_model_plan_matches_node_loop(seed):
+    text, data, desc = make(seed)
+    gm = go.compile(text, data).use_generated_order()
+    plan, lw = jbugs.lower(text, data)
+    assert plan.D == gm.D and lw.param_names() == gm.param_names(), desc
+    theta = random_thetas(np.zeros(plan.D), 3, seed=seed, scale=0.3)
+    lp, g, st = COracle(plan).eval_batch(theta)
+    for c in range(3):
+        lp_g, g_g = gm.logdensity_and_gradient(theta[:, c])
+        if not np.isfinite(lp_g):
+            assert lp[c] == lp_g, desc
+            continue
+        assert st[c] == 0 and abs(lp[c] - lp_g) <= 1e-11 * max(1.0, abs(lp_g)), (desc, text)
+        assert rel_err(g[:, c], g_g) < 1e-8, (desc, text)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", SEEDS)
+def test_random_model_cuda_matches_c_oracle(seed):
+    from test_gpu_parity import _check
+    text, data, desc = make(seed)
+    m = jbugs.compile(text, data)
+    co = COracle(m.plan)
+    theta = random_thetas(np.zeros(m.plan.D), 37, seed=seed, scale=0.3)
+    _check(m.cuda, co, theta)
+    _check(m.cuda, co, theta, layout="param_fast")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", list(range(100, 124)))
+def test_random_model_cuda_many_groups(seed):
+    """the same generator with up to 700 groups: several tiles, staged chunks with ragged ends, 300 chains (three CTA
+    columns, the last one partly idle)."""
+    from test_gpu_parity import _check
+    text, data, desc = make(seed, n_max=700)
+    m = jbugs.compile(text, data)
+    theta = random_thetas(np.zeros(m.plan.D), 300, seed=seed, scale=0.2)
+    _check(m.cuda, COracle(m.plan), theta)
