@@ -156,4 +156,39 @@ function logdensity_and_gradient_batch(m::CUDABatchModel, θ::AbstractMatrix)
     return logp, grad
 end
 
+# --- observation sharding (one process per GPU; the unique id travels over MPI / Distributed, not shown) -------------
+set_shard!(h::PlanHandle, plate::Integer, i0::Integer, i1::Integer) =
+    _check(ccall((:jbugs_plan_set_shard, libjbugs), Cint, (Ptr{Cvoid}, Cint, Int64, Int64), h.ptr, plate, i0, i1))
+set_dense_shard!(h::PlanHandle, i0::Integer, i1::Integer) =
+    _check(ccall((:jbugs_plan_set_dense_shard, libjbugs), Cint, (Ptr{Cvoid}, Int64, Int64), h.ptr, i0, i1))
+function comm_init!(h::PlanHandle, nranks::Integer, rank::Integer, unique_id::Vector{UInt8})
+    @assert length(unique_id) == 128
+    _check(ccall((:jbugs_comm_init, libjbugs), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), h.ptr, nranks, rank, unique_id))
+end
+
+# --- the sampler on the device: what `AbstractMCMC.sample(model, NUTS(0.8), n)` does through AdvancedHMC
+# (ext/JuliaBUGSAdvancedHMCExt.jl:40-66), for `n_chains` lock-step chains; draws come back as (chains, monitored, draws)
+function sample_nuts(model::BUGSModel, n_samples::Integer; n_adapts::Integer=1000, n_chains::Integer=128,
+                     max_depth::Integer=10, seed::Integer=1234, monitor::Vector{Int64}=collect(Int64, 0:LogDensityProblems.dimension(model) - 1),
+                     step_size::Real=0.01, jitter::Real=0.1)
+    h = plan_handle(model)
+    hmc = Ref{Ptr{Cvoid}}(C_NULL)
+    _check(ccall((:jbugs_hmc_create, libjbugs), Cint, (Ptr{Cvoid}, Int64, UInt64, Ref{Ptr{Cvoid}}), h.ptr, n_chains, seed, hmc))
+    try
+        θ0 = Vector{Float64}(JuliaBUGS.getparams(model))
+        _check(ccall((:jbugs_hmc_init, libjbugs), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cdouble, Cdouble), hmc[], θ0, jitter, step_size))
+        acc = Ref{Cdouble}(0.0)
+        _check(ccall((:jbugs_hmc_run_nuts, libjbugs), Cint,
+                     (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Cint, Ptr{Float64}, Ref{Cdouble}),
+                     hmc[], n_adapts, max_depth, 1, C_NULL, 0, C_NULL, acc))
+        draws = Array{Float64}(undef, n_chains, length(monitor), n_samples)   # unconstrained theta rows
+        _check(ccall((:jbugs_hmc_run_nuts, libjbugs), Cint,
+                     (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Cint, Ptr{Float64}, Ref{Cdouble}),
+                     hmc[], n_samples, max_depth, 0, monitor, length(monitor), draws, acc))
+        return draws, acc[]
+    finally
+        ccall((:jbugs_hmc_destroy, libjbugs), Cint, (Ptr{Cvoid},), hmc[])
+    end
+end
+
 end # module
