@@ -66,3 +66,29 @@ def shard_observations(model, rank: int, world: int, group=None):
         uid = broadcast_unique_id(CudaPlan.comm_unique_id, rank, world, group)
         cp.comm_init(world, rank, uid)
     return cp
+
+
+def sample_chains_sharded(model, sampler, n_samples: int, n_adapts: int, n_chains: int, seed: int = 1234, monitor=None,
+                          group=None):
+    """`AbstractMCMC.sample(model, sampler, MCMCDistributed(), n, nchains)` of the reference
+    (`JuliaBUGS/docs/src/inference/parallel.md:36-63`): the chains are split over the ranks (one GPU each), every rank
+    runs the on-device sampler on its own chains with its own seed, no data-path collective; the draws are gathered
+    on every rank with `all_gather_object`.  Returns a `Chains` holding all `n_chains` chains."""
+    import numpy as np
+    import torch.distributed as dist
+
+    from . import hmc
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    c0, c1 = chain_bounds(n_chains, world, rank)
+    local = hmc.sample(model, sampler, n_samples, n_adapts=n_adapts, n_chains=c1 - c0, seed=seed + 7919 * rank, monitor=monitor)
+    if world == 1:
+        return local
+    parts = [None] * world
+    dist.all_gather_object(parts, (local.samples, local.accept_rate, local.step_size, local.n_divergent), group=group)
+    samples = np.concatenate([p[0] for p in parts], axis=2)
+    w = np.array([p[0].shape[2] for p in parts], dtype=float)
+    return hmc.Chains(local.names, samples, float(np.average([p[1] for p in parts], weights=w)),
+                      float(np.mean([p[2] for p in parts])), model, n_divergent=int(sum(p[3] for p in parts)),
+                      tree_depth=local.tree_depth)

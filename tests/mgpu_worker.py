@@ -65,6 +65,17 @@ def main():
     assert np.max(np.abs(lp3 - ref_lp) / np.abs(ref_lp)) < 1e-10, "dense: logp after all-reduce"
     gs3 = np.maximum(np.abs(ref_g), 1e-4 * np.abs(ref_g).max(axis=0, keepdims=True))
     assert np.max(np.abs(g3 - ref_g) / gs3) < 1e-10, "dense: every gradient row is complete on every rank"
+    # --- the sampler with chains sharded over the ranks: every rank ends up with all chains, no collective on the path
+    from jbugs import hmc
+    from jbugs.dist import sample_chains_sharded
+    rng = np.random.default_rng(5)
+    yy = rng.normal(1.7, 1.0, 400)
+    mm = jbugs.set_evaluation_mode(
+        jbugs.compile("model { for (i in 1:N) { y[i] ~ dnorm(mu, 1.0) }\n mu ~ dnorm(0.0, 1.0E-6) }", {"N": 400, "y": yy}, {"mu": 0.0}),
+        jbugs.UseCUDABatch(device=local))
+    ch = sample_chains_sharded(mm, hmc.NUTS(max_depth=6, step_size=0.05), n_samples=200, n_adapts=200, n_chains=96 * world + 1)
+    assert ch["mu"].shape == (200, 96 * world + 1)
+    assert abs(ch["mu"].mean() - yy.mean()) < 8e-3 and abs(ch["mu"].std() - 0.05) < 5e-3
     dist.barrier()
     if rank == 0:
         print("MGPU_OK", world)
