@@ -284,6 +284,11 @@ static int build_plate(jbugs_plan* p, int k) {
             if ((rc = resolve_arg(p, pl.aux[q], sh.aux[q], V.aux[q], gref, (int)pl.n_locals, sb))) return rc;
             if ((rc = check_len(p, pl.aux[q], pl.N, pl.T, "aux"))) return rc;
         }
+        // aux[2]: optional 0/1 observation weight of a gathered (padded) plate
+        if (pl.aux[2].kind == JBUGS_ARG_DATA_I || pl.aux[2].kind == JBUGS_ARG_DATA_IJ) {
+            if ((rc = resolve_arg(p, pl.aux[2], sh.aux[2], V.aux[2], gref, (int)pl.n_locals, sb))) return rc;
+            if ((rc = check_len(p, pl.aux[2], pl.N, pl.T, "weight"))) return rc;
+        }
     }
     for (int l = 0; l < (int)pl.n_locals; ++l) {
         LocalS& ls = sh.loc[l];

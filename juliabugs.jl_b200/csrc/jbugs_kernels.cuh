@@ -122,6 +122,8 @@ struct DynSpec {
     __device__ __forceinline__ ArgS cov(int t) const { return s.cov[t]; }
     __device__ __forceinline__ ArgS y() const { return s.y; }
     __device__ __forceinline__ ArgS aux(int q) const { return s.aux[q]; }
+    // aux[2] holds an optional 0/1 observation weight (padded cells of a plate gathered by a data index)
+    __device__ __forceinline__ bool has_w() const { return s.aux[2].kind == JBUGS_ARG_DATA_I || s.aux[2].kind == JBUGS_ARG_DATA_IJ; }
     __device__ __forceinline__ int loc_level(int l) const { return s.loc[l].level; }
     __device__ __forceinline__ int loc_transform(int l) const { return s.loc[l].transform; }
     __device__ __forceinline__ int loc_family(int l) const { return s.loc[l].family; }
@@ -167,6 +169,7 @@ struct StaticSpec {
     __device__ __forceinline__ constexpr ArgS cov(int t) const { return Desc::sh().cov[t]; }
     __device__ __forceinline__ constexpr ArgS y() const { return Desc::sh().y; }
     __device__ __forceinline__ constexpr ArgS aux(int q) const { return Desc::sh().aux[q]; }
+    __device__ __forceinline__ constexpr bool has_w() const { return false; }  // static specs are rectangular plates
     __device__ __forceinline__ constexpr int loc_level(int l) const { return Desc::sh().loc[l].level; }
     __device__ __forceinline__ constexpr int loc_transform(int l) const { return Desc::sh().loc[l].transform; }
     __device__ __forceinline__ constexpr int loc_family(int l) const { return Desc::sh().loc[l].family; }

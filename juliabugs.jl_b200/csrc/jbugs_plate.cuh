@@ -169,6 +169,7 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
     double cv[MAX_TERMS];
     double eta = 0.0;
     bool bad = false;
+    if (sp.has_w() && arg_value(sp.aux(2), V.aux[2], st, sv, g, j) == 0.0) return false;  // padded cell: no observation
 #pragma unroll
     for (int t = 0; t < MAX_GT; ++t)
         if (t < sp.kg()) {

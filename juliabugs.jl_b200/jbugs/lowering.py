@@ -838,6 +838,9 @@ class Lowering:
             self._build_dense(s, fam, plate, eta, args, used_locals)
             return None
         lin = self._linearize(eta, lv_names)
+        gidx = self._gather_index(s, lin)
+        if gidx is not None:
+            return self._build_gathered_plate(s, fam, eta_arg, plate.link, args, lin, gidx, used_locals)
         # aux args
         aux = []
         for k, a in enumerate(args):
@@ -858,6 +861,117 @@ class Lowering:
             plate.terms.append(P.Term(P.Arg.local(li), self._data_arg(cov, lv_names, shape, lv_names)))
         if lin.const is not None:
             c = self._data_arg(lin.const, lv_names, shape, lv_names)
+            if not (c.kind == P.ARG_CONST and c.value == 0.0):
+                plate.terms.append(P.Term(P.Arg.const(1.0), c))
+        return plate
+
+    # ---- random effects picked by a data index: y[i] ~ f(... + b[group[i]] ...) -------------------------------------
+    def _gather_index(self, s: Stmt, lin: _Lin):
+        """the common index expression `group[i]` of the local references of a single-loop observation statement, or
+        None when they are indexed by the loop variable itself (the ordinary plate)."""
+        refs = [r for r in lin.terms if r[0] == "l"]
+        if not refs or len(s.loops) != 1:
+            return None
+        i_name = s.loop_vars[0]
+        plain = [len(r[2]) == 1 and isinstance(r[2][0], Var) and r[2][0].name == i_name for r in refs]
+        if all(plain) or any(len(r[2]) != 1 for r in refs):
+            return None
+        if any(plain):
+            raise LoweringError("random effects indexed both by the loop variable and by a data index in one predictor")
+        exprs = {_show(r[2][0]) for r in refs}
+        if len(exprs) != 1 or not self._is_data(refs[0][2][0], s.loop_vars):
+            raise LoweringError("random effects of one predictor must share one data index expression (b[group[i]])")
+        return refs[0][2][0]
+
+    def _build_gathered_plate(self, s: Stmt, fam, eta_arg, link, args, lin: _Lin, gidx_expr, used_locals) -> P.Plate:
+        """`for i: y[i] ~ f(g^-1(a + b[group[i]] + ...))`: the observations are regrouped by the value of the data
+        index into a G x Tmax plate (group = one element of b), short groups are padded and carry weight 0."""
+        n = s.shape[0]
+        lv = _grids(s.extents, s.loop_vars)
+        grp = np.broadcast_to(np.asarray(self.de.ev(gidx_expr, lv)), (n,)).astype(np.int64)
+        # the random effects: every local of the predictor is defined over the same 1..G loop
+        defs = {}
+        for ref in lin.terms:
+            if ref[0] != "l":
+                continue
+            ds = [d for d in self._defs(ref[1]) if d.kind == "param"]
+            if len(ds) != 1 or len(ds[0].loops) != 1 or ds[0].is_gq:
+                raise LoweringError(f"'{ref[1]}' must be defined by one stochastic statement in a single loop")
+            if ds[0].sid in used_locals:
+                raise LoweringError(f"'{ref[1]}' is a parent of more than one observation plate")
+            defs[ref[1]] = ds[0]
+        ext = {d.extents for d in defs.values()}
+        if len(ext) != 1:
+            raise LoweringError("random effects picked by one data index must share their loop range")
+        (lo, hi), = ext.pop()
+        if grp.min() < lo or grp.max() > hi:
+            raise LoweringError("data index outside the range of the random effect")
+        G = hi - lo + 1
+        g0 = grp - lo
+        counts = np.bincount(g0, minlength=G)
+        if n == 0 or counts.min() == 0:
+            # an element without observed descendants is a generated quantity in the reference (graphs.jl:27-71) and
+            # leaves the target; a statement-level plan cannot drop single elements of a statement
+            raise LoweringError("every element of a random effect picked by a data index needs at least one observation")
+        Tmax = int(counts.max())
+        if G * Tmax > 8 * n + 1024:
+            raise LoweringError("group sizes too unbalanced to pad into a rectangular plate")
+        order = np.argsort(g0, kind="stable")
+        start = np.concatenate([[0], np.cumsum(counts)[:-1]])
+        pos = np.arange(n) - start[g0[order]]           # position of each (sorted) observation inside its group
+        cell = np.zeros((G, Tmax), dtype=np.int64)      # observation shown in each cell (padding: the group's first)
+        first = np.where(counts > 0, order[np.minimum(start, n - 1)], order[0] if n else 0)
+        cell[:] = first[:, None]
+        cell[g0[order], pos] = order
+        w = np.zeros((G, Tmax))
+        w[g0[order], pos] = 1.0
+        self._cur_extents = s.extents
+
+        def cols(e):  # a data expression of the observation loop -> the Tmax columns of the padded plate
+            v = np.broadcast_to(np.asarray(self.de.ev(e, lv), dtype=np.float64), (n,))
+            return [v[cell[:, j]] for j in range(Tmax)]
+
+        key = f"gather|{s.name}|{_show(gidx_expr)}"
+        plate = P.Plate(N=G, T=Tmax, family=fam, eta_arg=eta_arg, name=f"{s.name}~{s.node.dist.fn} by {_show(gidx_expr)}")
+        plate.link = link
+        plate.n_real = n
+        lhs = s.node.lhs
+        ycols = cols(lhs if isinstance(lhs, Index) else Var(lhs.name))
+        plate.y = P.Arg(P.ARG_DATA_IJ, self._slot(key + "|y", np.stack(ycols, 1).ravel(order="F"), rank=2, dim0=G))
+        aux = []
+        for q, a in enumerate(args):
+            if q == eta_arg:
+                aux.append(P.ZERO_ARG)
+            elif self._is_data(a, s.loop_vars):
+                aux.append(self._columns_arg(f"{key}|aux{q}", cols(a), G))
+            else:
+                aux.append(self._scalar_arg(a, s.loop_vars, s.shape, s.loop_vars))
+        plate.aux = aux
+        if not np.all(w == 1.0):
+            plate.weight = P.Arg(P.ARG_DATA_IJ, self._slot(key + "|w", w.ravel(order="F"), rank=2, dim0=G))
+        for ref, cov in lin.terms.items():
+            if ref[0] == "g":
+                plate.terms.append(P.Term(P.Arg.gval(self._gval_of(ref[1])), self._columns_arg(f"{key}|cov|{ref[1]}", cols(cov), G)))
+        for ref, cov in lin.terms.items():
+            if ref[0] != "l":
+                continue
+            d = defs[ref[1]]
+            pfam = self._family(d.node.dist)
+            tr, lb, ub = self._transform_of(pfam, d.node.dist.args)
+            base, si, sj, idx_slot = _affine_or_index(self.theta_index(d))
+            if idx_slot is not None:
+                tidx = self.theta_index(d)
+                idx_slot = self._slot(f"theta_index|{ref[1]}", np.asfortranarray(tidx).ravel(order="F").astype(np.int64),
+                                      rank=tidx.ndim, dim0=tidx.shape[0])
+            self._cur_extents = d.extents
+            pargs = [self._scalar_arg(a, d.loop_vars, d.shape, d.loop_vars) for a in d.node.dist.args]
+            self._cur_extents = s.extents
+            plate.locals.append(P.Local(ref[1], P.LEVEL_GROUP, tr, base, si, sj, pfam, pargs, lb, ub,
+                                        -1 if idx_slot is None else idx_slot))
+            used_locals.add(d.sid)
+            plate.terms.append(P.Term(P.Arg.local(len(plate.locals) - 1), self._columns_arg(f"{key}|cov|{ref[1]}", cols(cov), G)))
+        if lin.const is not None:
+            c = self._columns_arg(f"{key}|offset", cols(lin.const), G)
             if not (c.kind == P.ARG_CONST and c.value == 0.0):
                 plate.terms.append(P.Term(P.Arg.const(1.0), c))
         return plate

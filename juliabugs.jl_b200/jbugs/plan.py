@@ -161,6 +161,8 @@ class Plate:
     y: Arg = ZERO_ARG
     aux: List[Arg] = field(default_factory=list)
     name: str = ""
+    n_real: int = -1               # observed cells when the plate is padded (weight given), else N * T
+    weight: Optional[Arg] = None   # 0/1 per cell (DATA_I | DATA_IJ): padded cells of a plate gathered by a data index
 
 
 @dataclass
@@ -194,7 +196,8 @@ class Plan:
         return len(self.globals) + len(self.gtape)
 
     def n_obs(self):
-        return sum(p.N * p.T for p in self.plates if p.has_obs) + sum(d.N for d in self.dense)
+        return (sum((p.n_real if p.n_real >= 0 else p.N * p.T) for p in self.plates if p.has_obs)
+                + sum(d.N for d in self.dense))
 
     # ------------------------------------------------------------------ serialisation
     def to_bytes(self) -> bytes:
@@ -222,7 +225,8 @@ class Plan:
                 raise ValueError("link tape longer than JBUGS_MAX_LINK")
             link = list(p.link) + [OP_IDENTITY] * (MAX_LINK - len(p.link))
             pl[k] = (p.N, p.T, il, len(p.locals), it, len(p.terms), len(p.link), link, p.family,
-                     p.eta_arg, 1 if p.has_obs else 0, p.y.rec(), args3(p.aux))
+                     p.eta_arg, 1 if p.has_obs else 0, p.y.rec(),
+                     args3(p.aux if p.weight is None else (list(p.aux) + [ZERO_ARG, ZERO_ARG])[:2] + [p.weight]))
             for x in p.locals:
                 loc[il] = (x.level, x.transform, x.theta_base, x.stride_i, x.stride_j, x.idx_slot,
                            x.family, x.lb, x.ub, args3(x.args))

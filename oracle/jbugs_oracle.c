@@ -454,8 +454,10 @@ static int eval_chain(const jbo_plan* p, chain_io io, int want_grad, double* log
                     ladj[l] += dx;
                     for (int q = 0; q < 3; ++q) argadj(&L[l].args[q], da[q], gadj, ladj);
                 }
-                if (pl->has_obs) {
-                    /* linear predictor, link tape, observation (source_gen.jl:738-741) */
+                const int has_w = pl->aux[2].kind == JBUGS_ARG_DATA_I || pl->aux[2].kind == JBUGS_ARG_DATA_IJ;
+                if (pl->has_obs && !(has_w && argval(p, &pl->aux[2], gval, lx, i, j, N) == 0.0)) {
+                    /* linear predictor, link tape, observation (source_gen.jl:738-741); cells with weight 0 are the
+                       padding of a plate whose observations were gathered by a data index */
                     double eta = 0.0;
                     for (int t = 0; t < nt; ++t)
                         eta += argval(p, &Tm[t].coef, gval, lx, i, j, N) * argval(p, &Tm[t].cov, gval, lx, i, j, N);

@@ -165,3 +165,71 @@ def test_single_node_models_against_scipy_cuda(k):
     assert jbugs.LogDensityProblems.logdensity(m, jbugs.getparams(m)) == pytest.approx(lp_t, rel=1e-11)
     mu = jbugs.settrans(m, False)
     assert jbugs.LogDensityProblems.logdensity(mu, jbugs.getparams(mu)) == pytest.approx(lp_u, rel=1e-11)
+
+
+# ---- random effects picked by a data index (b[school[i]]): observations regrouped into a padded G x Tmax plate ----
+NESTED = """model {
+  for (i in 1:n) {
+    y[i] ~ %s
+    %s <- a + b[school[i]] + s[school[i]] * x[i] + c * x[i]
+  }
+  for (g in 1:G) {
+    b[g] ~ dnorm(0, tau.b)
+    s[g] ~ dnorm(m.s, 4)
+  }
+  a ~ dnorm(0, 0.01)
+  c ~ dnorm(0, 0.01)
+  m.s ~ dnorm(0, 1)
+  tau ~ dgamma(2, 2)
+  tau.b ~ dgamma(2, 2)
+}"""
+NESTED_KINDS = {"normal": ("dnorm(mu[i], tau)", "mu[i]"), "poisson": ("dpois(mu[i])", "log(mu[i])"),
+                "binomial": ("dbin(mu[i], m[i])", "logit(mu[i])")}
+
+
+def nested_data(kind, n, G, seed=0):
+    r = np.random.default_rng(seed)
+    school = np.concatenate([np.arange(1, G + 1), r.integers(1, G + 1, n - G)]).astype(float)
+    r.shuffle(school)
+    data = {"n": n, "G": G, "school": school, "x": r.standard_normal(n)}
+    if kind == "normal":
+        data["y"] = r.standard_normal(n)
+    elif kind == "poisson":
+        data["y"] = r.poisson(2.0, n).astype(float)
+    else:
+        data["m"] = r.integers(1, 9, n).astype(float)
+        data["y"] = r.binomial(data["m"].astype(int), 0.4).astype(float)
+    return data
+
+
+@pytest.mark.parametrize("kind", list(NESTED_KINDS))
+def test_nested_index_plate_matches_node_loop(kind):
+    text = NESTED % NESTED_KINDS[kind]
+    data = nested_data(kind, 41, 6)
+    gm = go.compile(text, data).use_generated_order()
+    plan, lw = jbugs.lower(text, data)
+    pl = plan.plates[0]
+    assert (pl.N, pl.n_real) == (6, 41) and pl.weight is not None and plan.n_obs() == 41
+    assert lw.param_names() == gm.param_names()
+    theta = random_thetas(np.zeros(plan.D), 3, seed=1, scale=0.3)
+    lp, g, st = COracle(plan).eval_batch(theta)
+    for c in range(3):
+        lp_g, g_g = gm.logdensity_and_gradient(theta[:, c])
+        assert abs(lp[c] - lp_g) <= 1e-12 * abs(lp_g)
+        assert rel_err(g[:, c], g_g) < 1e-9
+
+
+def test_nested_index_with_an_empty_group_is_refused():
+    data = nested_data("normal", 30, 5)
+    data["school"][data["school"] == 3] = 2.0
+    with pytest.raises(jbugs.LoweringError, match="at least one observation"):
+        jbugs.lower(NESTED % NESTED_KINDS["normal"], data)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,n,G", [("normal", 41, 6), ("poisson", 5000, 300), ("binomial", 977, 40)])
+def test_nested_index_plate_cuda(kind, n, G):
+    from test_gpu_parity import _check
+    m = jbugs.compile(NESTED % NESTED_KINDS[kind], nested_data(kind, n, G, seed=n))
+    theta = random_thetas(np.zeros(m.plan.D), 70, seed=2, scale=0.2)
+    _check(m.cuda, COracle(m.plan), theta)
