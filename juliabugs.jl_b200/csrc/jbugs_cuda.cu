@@ -148,6 +148,7 @@ struct jbugs_plan_s {
     unsigned long long epoch = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_plate_ms = 0.f, last_total_ms = 0.f;
+    bool events_recorded = false;
     bool timing = false;  // record per-phase CUDA events (jbugs_last_timing); off by default: four extra stream ops per call
     // comm
     ncclComm_t comm = nullptr;
@@ -659,6 +660,14 @@ extern "C" int jbugs_plan_describe(const jbugs_plan* p, char* buf, size_t nbuf) 
 
 extern "C" int jbugs_last_timing(const jbugs_plan* p, float* plate_ms, float* total_ms) {
     if (!p) return fail(JBUGS_ERR_INVALID, "null plan");
+    if (p->timing && p->ev[3] && p->events_recorded) {
+        // events of the most recent evaluation (also an asynchronous one): wait for its last event, then read them
+        jbugs_plan* q = const_cast<jbugs_plan*>(p);
+        CU(cudaSetDevice(p->device));
+        CU(cudaEventSynchronize(p->ev[3]));
+        CU(cudaEventElapsedTime(&q->last_plate_ms, p->ev[1], p->ev[2]));
+        CU(cudaEventElapsedTime(&q->last_total_ms, p->ev[0], p->ev[3]));
+    }
     if (plate_ms) *plate_ms = p->last_plate_ms;
     if (total_ms) *total_ms = p->last_total_ms;
     return JBUGS_OK;
@@ -920,7 +929,10 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         poison_kernel<<<grid, BLOCK, 0, st>>>(grad, ld, C, p->h.D, p->d_flags, p->d_any_bad);
         p->launches++;
     }
-    if (p->timing) CU(cudaEventRecord(p->ev[3], st));
+    if (p->timing) {
+        CU(cudaEventRecord(p->ev[3], st));
+        p->events_recorded = true;
+    }
     CU(cudaGetLastError());
     return 0;
 }
