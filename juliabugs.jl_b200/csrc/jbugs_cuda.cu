@@ -815,7 +815,8 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         const bool sharded = p->comm && p->nranks > 1 && p->dense_i1 >= 0;  // rows of X split over the ranks
         const long long r0 = p->dense_i0, Nloc = (p->dense_i1 >= 0 ? p->dense_i1 : dn.N) - r0;
         const unsigned col_blocks = (unsigned)((C + DG_BN - 1) / DG_BN);
-        static bool opted = false;
+        static bool opted_dev[64] = {false};  // per device: a process may hold plans on several GPUs
+        bool& opted = opted_dev[p->device & 63];
         if (!opted) {
             CU(cudaFuncSetAttribute(dense_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DgFwd::SMEM_BYTES));
             CU(cudaFuncSetAttribute(dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DgBwd::SMEM_BYTES));

@@ -8,11 +8,15 @@ namespace jbugs {
 
 template <class S, int BLK, bool TMA>
 static cudaError_t launch_plate_blk(JBUGS_LAUNCH_PARAMS) {
-    static size_t opted_in = 48 * 1024;  // dynamic shared memory above 48 KB needs an opt-in per kernel
-    if (smem > opted_in) {
+    // dynamic shared memory above 48 KB needs an opt-in per kernel AND per device (a process may hold plans on several)
+    static size_t opted_in[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& have = opted_in[dev & 63];
+    if (smem > 48 * 1024 && smem > have) {
         cudaError_t e = cudaFuncSetAttribute(plate_kernel<S, BLK, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        opted_in = smem;
+        have = smem;
     }
     dim3 grid((unsigned)((C + BLK - 1) / BLK), (unsigned)n_tiles);
     plate_kernel<S, BLK, TMA><<<grid, BLK, smem, st>>>(pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
