@@ -7,6 +7,8 @@ Same names and argument meaning as the reference (paths relative to /root/refere
     getparams(model)                         src/model/bugsmodel.jl:619-665
     settrans(model, flag)                    src/model/bugsmodel.jl:697-707
     set_evaluation_mode(model, mode)         src/model/bugsmodel.jl:736-801
+    condition / decondition                  src/model/abstractppl.jl:700-799 (new plan, as the reference drops its
+                                             generated function); set_observed_values = data re-upload (:872-888)
     UseGraph / UseGeneratedLogDensityFunction / UseCUDABatch   (bugsmodel.jl:248-252 + the new mode)
     LogDensityProblems.logdensity / logdensity_and_gradient / dimension / capabilities
                                              src/model/logdensityproblems.jl:19-55,168-174,219-232
@@ -107,6 +109,42 @@ class BUGSModel:
 
 def compile(model_def, data, inits=None, theta_order=None) -> BUGSModel:  # noqa: A001 - reference name
     return BUGSModel(model_def, data, inits, transformed=True, theta_order=theta_order)
+
+
+def condition(model: BUGSModel, values=None, **kw) -> BUGSModel:
+    """`AbstractPPL.condition(model, (; var = value))` (src/model/abstractppl.jl:700-799): the named variables become
+    observations at the given values.  A new model with a new plan -- the reference likewise drops its generated
+    function (`log_density_computation_function => nothing`, :796-797) and rebuilds it on demand."""
+    vals = dict(values or {}, **kw)
+    data = dict(model.data)
+    for k, v in vals.items():
+        if k in data and isinstance(data[k], np.ndarray) and np.ndim(v) == 0:
+            raise ValueError(f"'{k}' is an array: pass the whole array (NaN = still unobserved)")
+        data[k] = v
+    m = BUGSModel(model.model_def, data, {k: v for k, v in model.inits.items() if k not in vals},
+                  transformed=model.transformed, theta_order=None)
+    m.evaluation_mode = model.evaluation_mode
+    m._conditioned = dict(getattr(model, "_conditioned", {}), **{k: model.data.get(k) for k in vals})
+    return m
+
+
+def decondition(model: BUGSModel, *names) -> BUGSModel:
+    """undo `condition` for the named variables (all of them when none is named): they are parameters again."""
+    was = dict(getattr(model, "_conditioned", {}))
+    names = list(names) or list(was)
+    data = dict(model.data)
+    for k in names:
+        if k not in was:
+            raise KeyError(f"'{k}' was not conditioned on")
+        prev = was.pop(k)
+        if prev is None:
+            data.pop(k, None)
+        else:
+            data[k] = prev
+    m = BUGSModel(model.model_def, data, model.inits, transformed=model.transformed, theta_order=None)
+    m.evaluation_mode = model.evaluation_mode
+    m._conditioned = was
+    return m
 
 
 def settrans(model: BUGSModel, flag: bool = True) -> BUGSModel:

@@ -93,3 +93,27 @@ def test_stacks_indexed_generated_quantities(fixtures):
     stres = (Y[:, None] - mu) * np.sqrt(draws["tau"])[None, :]
     assert np.allclose(out["stres"], stres, rtol=1e-12)
     assert np.array_equal(out["outlier"], (stres - 2.5 >= 0).astype(float) + (-(stres + 2.5) >= 0).astype(float))
+
+
+def test_condition_and_decondition(fixtures):
+    """AbstractPPL.condition / decondition (J/src/model/abstractppl.jl:700-799; contract pinned by
+    J/test/model/abstractppl.jl): conditioned variables leave theta and are scored as observations; deconditioning
+    restores the original plan byte for byte."""
+    from c_oracle import COracle
+    fx = fixtures["rats"]
+    m = jbugs.compile(ex.RATS, fx["data"], fx["inits"])
+    mc = jbugs.condition(m, {"tau.c": 0.03, "alpha.c": 240.0})
+    assert m.plan.D == 65 and mc.plan.D == 63
+    assert "tau.c" not in mc.lowering.param_names() and "alpha.c" not in mc.lowering.param_names()
+    gm = go.compile(ex.RATS, dict(fx["data"], **{"tau.c": 0.03, "alpha.c": 240.0}), fx["inits"]).use_generated_order()
+    assert mc.lowering.param_names() == gm.param_names()
+    th = np.where(np.isfinite(gm.getparams()), gm.getparams(), 0.0) + 0.01
+    lp, g, _ = COracle(mc.plan).eval_batch(th.reshape(-1, 1))
+    lp_g, g_g = gm.logdensity_and_gradient(th)
+    assert abs(lp[0] - lp_g) <= 1e-12 * abs(lp_g)
+    assert np.max(np.abs(g[:, 0] - g_g) / np.maximum(np.abs(g_g), 1e-6 * np.abs(g_g).max())) < 1e-10
+    md = jbugs.decondition(mc, "tau.c")
+    assert md.plan.D == 64 and "tau.c" in md.lowering.param_names()
+    assert jbugs.decondition(md).plan.to_bytes() == m.plan.to_bytes()
+    with pytest.raises(KeyError):
+        jbugs.decondition(m, "tau.c")
