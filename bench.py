@@ -140,13 +140,17 @@ def cpu_baseline(plan, th0, n_obs, budget_s=15.0, seed=7):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from c_oracle import COracle
     co = COracle(plan)
-    cores = co.max_threads()
+    # every host core this process may run on; not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or co.max_threads()
     rng = np.random.default_rng(seed)
 
     def run(C):
         theta = np.ascontiguousarray(th0[:, None] + 0.05 * rng.standard_normal((th0.size, C)))
         t = time.perf_counter()
-        co.eval_batch(theta, layout="param_fast", want_grad=True)
+        co.eval_batch(theta, layout="param_fast", want_grad=True, nthreads=cores)
         return time.perf_counter() - t
 
     t1 = run(cores)  # one chain per thread
