@@ -22,7 +22,10 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle", "smsp__pcsamp_warps_issue_stalled_not_selected",
         "smsp__pcsamp_warps_issue_stalled_wait", "smsp__pcsamp_warps_issue_stalled_short_scoreboard",
         "smsp__pcsamp_warps_issue_stalled_selected", "smsp__pcsamp_warps_issue_stalled_dispatch_stall",
-        "launch__shared_mem_per_block_dynamic", "sm__inst_executed_pipe_lsu.sum", "smsp__inst_executed_op_ldgsts.sum"]
+        "launch__shared_mem_per_block_dynamic", "sm__inst_executed_pipe_lsu.sum", "smsp__inst_executed_op_ldgsts.sum",
+        "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 
 
 def page(rep, name):
