@@ -142,6 +142,7 @@ struct jbugs_plan_s {
     // issue-to-complete latency of a tiny bulk copy is longer than one 32-group chunk of compute, and the data
     // streams are < 1 % of the traffic anyway.  `jbugs_plan_set_option(plan, "tma", 1)` selects the TMA kernels.
     int use_tma = 0;
+    int use_pdl = 1;  // programmatic dependent launch of the plate kernels and finalize (option "pdl")
     long long launches = 0;
     // bumped whenever anything a captured launch sequence bakes in may have changed (tiling, workspace pointers,
     // data-only constants): the HMC trajectory graph is rebuilt when it sees a new epoch
@@ -635,6 +636,11 @@ extern "C" int jbugs_plan_set_option(jbugs_plan* p, const char* key, int64_t val
         p->host_chunk = value;
         return JBUGS_OK;
     }
+    if (!strcmp(key, "pdl")) {
+        p->use_pdl = value != 0;
+        p->epoch++;
+        return JBUGS_OK;
+    }
     if (!strcmp(key, "timing")) {
         p->timing = value != 0;
         return JBUGS_OK;
@@ -765,6 +771,26 @@ static int ensure_workspace(jbugs_plan* p, long long C) {
     return 0;
 }
 
+// a thread-per-chain helper kernel, optionally as a programmatic dependent launch (the kernel starts with
+// griddepcontrol.wait, so it is safe after any predecessor)
+template <typename K, typename... Args>
+static void launch_helper(K kernel, int pdl, unsigned grid, unsigned block, cudaStream_t st, Args&&... args) {
+    if (!pdl) {
+        kernel<<<grid, block, 0, st>>>(args...);
+        return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // ------------------------------------------------------------------------------------------------ evaluation on device-resident CHAIN_FAST buffers
 static int eval_device(jbugs_plan* p, const double* theta, long long ld, long long C, double* logp, double* grad,
                        int* status, int want_grad, cudaStream_t st) {
@@ -781,7 +807,9 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
     for (size_t k = 0; k < p->rt.size(); ++k)
         if ((rc = refresh_obs_const(p, (int)k, st))) return rc;
     if (p->timing) CU(cudaEventRecord(p->ev[0], st));
-    prologue_kernel<<<helper_tiles, hblk, 0, st>>>(p->gp, p->tp, theta, ld, C, p->d_gvals, ldg, p->d_flags, p->d_any_bad);
+    // (launched the ordinary way: as a dependent launch behind the sampler's leapfrog kernel it slowed the captured
+    //  trajectory graph down, 1.4 s -> 2.2 s on the Rats probe, for 1.5 us per stand-alone evaluation)
+    launch_helper(prologue_kernel, 0, helper_tiles, hblk, st, p->gp, p->tp, theta, ld, C, p->d_gvals, ldg, p->d_flags, p->d_any_bad);
     p->launches++;
     if (p->timing) CU(cudaEventRecord(p->ev[1], st));
     FinalParams fp{};
@@ -805,7 +833,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
             pp.v.loc[l].step_j = pp.v.loc[l].sj * ld;
         }
         cudaError_t le = g_specs[r.variant].launch(r.n_tiles, r.smem_bytes, st, pp, theta, grad, ld, C, p->d_gvals, ldg,
-                                                   p->d_partial + r.partial_offset * ldg, p->d_flags, want_grad && grad);
+                                                   p->d_partial + r.partial_offset * ldg, p->d_flags, want_grad && grad, p->use_pdl);
         if (le != cudaSuccess) return fail(JBUGS_ERR_CUDA, "plate kernel launch failed: %s", cudaGetErrorString(le));
         p->launches++;
         reduce_plates.push_back((int)k);
@@ -902,7 +930,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         // observation-sharded: reduce this rank's tiles, all-reduce [logp part, global adjoints, flag] over NVLink,
         // then add the priors of the globals once and finish
         const int NG = (int)(p->h.n_globals + p->h.n_gtape);
-        finalize_kernel<<<helper_tiles, hblk, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, partial_in,
+        launch_helper(finalize_kernel, p->use_pdl, helper_tiles, hblk, st, p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, partial_in,
                                                        p->d_flags, logp, status, p->d_any_bad, want_grad && grad, 1, p->d_red);
         p->launches++;
         const bool dense_grad = !p->dense.empty() && p->dense_i1 >= 0 && want_grad && grad;
@@ -915,11 +943,11 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
                                                                                        dn.theta_base, dn.theta_stride, C, 1);
             p->launches++;
         }
-        finalize_kernel<<<helper_tiles, hblk, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, partial_in,
+        launch_helper(finalize_kernel, p->use_pdl, helper_tiles, hblk, st, p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, partial_in,
                                                        p->d_flags, logp, status, p->d_any_bad, want_grad && grad, 2, p->d_red);
         p->launches++;
     } else {
-        finalize_kernel<<<helper_tiles, hblk, 0, st>>>(p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, partial_in,
+        launch_helper(finalize_kernel, p->use_pdl, helper_tiles, hblk, st, p->gp, p->tp, fp, theta, grad, ld, C, p->d_gvals, ldg, partial_in,
                                                        p->d_flags, logp, status, p->d_any_bad, want_grad && grad, 0, p->d_red);
         p->launches++;
     }

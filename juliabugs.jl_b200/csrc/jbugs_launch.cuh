@@ -19,6 +19,19 @@ static cudaError_t launch_plate_blk(JBUGS_LAUNCH_PARAMS) {
         have = smem;
     }
     dim3 grid((unsigned)((C + BLK - 1) / BLK), (unsigned)n_tiles);
+    if (pdl) {  // programmatic dependent launch: overlap this kernel's start with the tail of its predecessor
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(BLK);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, plate_kernel<S, BLK, TMA>, pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
+    }
     plate_kernel<S, BLK, TMA><<<grid, BLK, smem, st>>>(pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
     return cudaGetLastError();
 }

@@ -374,6 +374,7 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
              long long ld, long long C, const double* __restrict__ gvals, long long ldg,
              double* __restrict__ partial, int* __restrict__ flags, int want_grad) {
     extern __shared__ double smem[];
+    pdl_launch_dependents();  // finalize (or the next plate) may be scheduled; it waits for this grid before reading
     const S sp(P.sh);
     const PlateVals& V = P.v;
     const int tid = threadIdx.x;
@@ -414,6 +415,7 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
         cp_async_commit();
     }
 
+    pdl_wait();  // everything above (parameters, first data chunk in flight) may overlap the prologue kernel
     ChainState st;
 #pragma unroll
     for (int k = 0; k < MAX_GREF; ++k) {

@@ -19,8 +19,8 @@ static inline int plate_block(long long C) { return C <= 32 ? 32 : (C <= 64 ? 64
 
 #define JBUGS_LAUNCH_PARAMS                                                                                     \
     long long n_tiles, size_t smem, cudaStream_t st, const PlateParams &pp, const double *theta, double *grad, \
-        long long ld, long long C, const double *gvals, long long ldg, double *partial, int *flags, int want_grad
-#define JBUGS_LAUNCH_ARGS n_tiles, smem, st, pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad
+        long long ld, long long C, const double *gvals, long long ldg, double *partial, int *flags, int want_grad, int pdl
+#define JBUGS_LAUNCH_ARGS n_tiles, smem, st, pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad, pdl
 
 typedef cudaError_t (*plate_launch_fn)(JBUGS_LAUNCH_PARAMS);
 
