@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -44,3 +46,27 @@ def test_our_arm_needs_a_gpu():
         pytest.skip("a GPU is present")
     r = _run("--groups", "1000", "--chains", "8", "--steps", "1", "--warmup", "1", "--no-cpu", "--no-e2e")
     assert r.returncode != 0 and "CUDA" in (r.stderr + r.stdout)
+
+
+@pytest.mark.gpu
+def test_our_arm_line_on_the_gpu():
+    r = _run("--groups", "50000", "--chains", "128", "--e2e-chains", "64", "--steps", "3", "--warmup", "3")
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "roofline", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert "impl" not in d or d["impl"] != "reference"
+    assert d["steps"] == 3 and d["warmup"] == 3 and d["n_gpus"] == 1 and d["scaling"] == "weak" and d["dtype"] == "f64"
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and 0.0 < rf["frac"] < 1.5
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and rf["algorithmic_bytes"] == 2 * 8 * 128 * d["config"]["D"]
+    assert d["gpu_launches"] >= 3 * 3          # at least prologue + plate + finalize per timed step
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 8 * d["config"]["D"] * 64 and e["matches_resident"] is True
+    assert e["value"] < d["value"]             # host buffers cross PCIe inside the timed region
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["value"] > 0 and cb["cores"] >= 1
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
