@@ -6,7 +6,7 @@
 
 namespace jbugs {
 
-template <class S, int BLK, bool TMA>
+template <class S, int BLK, bool TMA, bool GRAD = true>
 static cudaError_t launch_plate_blk(JBUGS_LAUNCH_PARAMS) {
     // dynamic shared memory above 48 KB needs an opt-in per kernel AND per device (a process may hold plans on several)
     static size_t opted_in[64] = {0};
@@ -14,7 +14,7 @@ static cudaError_t launch_plate_blk(JBUGS_LAUNCH_PARAMS) {
     cudaGetDevice(&dev);
     size_t& have = opted_in[dev & 63];
     if (smem > 48 * 1024 && smem > have) {
-        cudaError_t e = cudaFuncSetAttribute(plate_kernel<S, BLK, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(plate_kernel<S, BLK, TMA, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         have = smem;
     }
@@ -30,9 +30,9 @@ static cudaError_t launch_plate_blk(JBUGS_LAUNCH_PARAMS) {
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, plate_kernel<S, BLK, TMA>, pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
+        return cudaLaunchKernelEx(&cfg, plate_kernel<S, BLK, TMA, GRAD>, pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
     }
-    plate_kernel<S, BLK, TMA><<<grid, BLK, smem, st>>>(pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
+    plate_kernel<S, BLK, TMA, GRAD><<<grid, BLK, smem, st>>>(pp, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad);
     return cudaGetLastError();
 }
 

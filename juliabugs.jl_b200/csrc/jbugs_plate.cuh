@@ -368,7 +368,9 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
 
 // BLK = chains per CTA (128, or 64 / 32 for small batches so that no lane idles); TMA = stage the data streams with
 // cp.async.bulk + mbarrier where aligned (a separate instantiation: the cp.async-only kernel carries none of it)
-template <class S, int BLK, bool TMA>
+// GRAD = false: a forward-only instantiation for `logdensity` without the gradient (the adjoint arithmetic is dead
+// code then and the kernel reads theta only); built for the large-plate specs, selected when want_grad == 0
+template <class S, int BLK, bool TMA, bool GRAD = true>
 __global__ void __launch_bounds__(BLK, (S::MIN_BLOCKS * (128 / BLK) > 24 ? 24 : S::MIN_BLOCKS * (128 / BLK)))
 plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ theta, double* __restrict__ grad,
              long long ld, long long C, const double* __restrict__ gvals, long long ldg,
@@ -448,7 +450,7 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
                                : 0.0;
     const double* __restrict__ th = theta + c;
     double* __restrict__ gr = grad + c;
-    const bool store = want_grad && active;
+    const bool store = GRAD && want_grad && active;
 
     long long pos[MAX_LOC];
 #pragma unroll
@@ -476,7 +478,7 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
         int g = 0;
         for (; g + U <= cnt; g += U) {
             const long long i = i0 + g;
-            if (S::PREFETCH) {
+            if (S::PREFETCH || !GRAD) {  // forward-only: no store traffic to fill the memory pipe, so keep twice the loads in flight
                 // software pipeline over U-blocks (also across staged chunks: the theta rows do not depend on the
                 // staged data): the loads of block i+U are in flight while block i is evaluated
                 if (!have_cur) load_groups<S, U>(sp, V, i, th, ld, pos, gl_cur);
@@ -533,9 +535,10 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
     // per (tile, chain) partials: [logp, adjoints of the referenced global values]
     double* out = partial + tile * (long long)(1 + sp.n_gref()) * ldg + c;
     out[0] = lp;
+    if (GRAD)
 #pragma unroll
-    for (int k = 0; k < MAX_GREF; ++k)
-        if (k < sp.n_gref()) out[(long long)(1 + k) * ldg] = st.ga[k];
+        for (int k = 0; k < MAX_GREF; ++k)
+            if (k < sp.n_gref()) out[(long long)(1 + k) * ldg] = st.ga[k];
     if (bad) atomicOr(flags + c, 1);
 }
 

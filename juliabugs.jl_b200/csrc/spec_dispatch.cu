@@ -14,10 +14,26 @@ namespace jbugs {
             return pp.v.bulk_ok ? name##_128t(JBUGS_LAUNCH_ARGS) : name##_128(JBUGS_LAUNCH_ARGS); \
         }                                                        \
     }
+// the same, with a forward-only kernel for logdensity without the gradient (128-chain CTAs)
+#define JB_DISPATCH_NG(name)                                     \
+    cudaError_t name##_32(JBUGS_LAUNCH_PARAMS);                  \
+    cudaError_t name##_64(JBUGS_LAUNCH_PARAMS);                  \
+    cudaError_t name##_128(JBUGS_LAUNCH_PARAMS);                 \
+    cudaError_t name##_128t(JBUGS_LAUNCH_PARAMS);                \
+    cudaError_t name##_128ng(JBUGS_LAUNCH_PARAMS);               \
+    cudaError_t name(JBUGS_LAUNCH_PARAMS) {                      \
+        switch (plate_block(C)) {                                \
+        case 32: return name##_32(JBUGS_LAUNCH_ARGS);            \
+        case 64: return name##_64(JBUGS_LAUNCH_ARGS);            \
+        default:                                                 \
+            if (!want_grad) return name##_128ng(JBUGS_LAUNCH_ARGS); \
+            return pp.v.bulk_ok ? name##_128t(JBUGS_LAUNCH_ARGS) : name##_128(JBUGS_LAUNCH_ARGS); \
+        }                                                        \
+    }
 JB_DISPATCH(launch_dyn)
-JB_DISPATCH(launch_rats_t5)
+JB_DISPATCH_NG(launch_rats_t5)
 JB_DISPATCH(launch_rats)
-JB_DISPATCH(launch_seeds)
+JB_DISPATCH_NG(launch_seeds)
 JB_DISPATCH(launch_surgical)
 JB_DISPATCH(launch_pumps)
 JB_DISPATCH(launch_epil)

@@ -3,5 +3,8 @@
 // (small translation units compile in parallel instead of one big one.)
 #include "jbugs_launch.cuh"
 namespace jbugs {
-cudaError_t JB_NAME(JBUGS_LAUNCH_PARAMS) { return launch_plate_blk<JB_SPEC, JB_BLK, JB_TMA>(JBUGS_LAUNCH_ARGS); }
+#ifndef JB_GRAD
+#define JB_GRAD true
+#endif
+cudaError_t JB_NAME(JBUGS_LAUNCH_PARAMS) { return launch_plate_blk<JB_SPEC, JB_BLK, JB_TMA, JB_GRAD>(JBUGS_LAUNCH_ARGS); }
 }  // namespace jbugs

@@ -233,3 +233,25 @@ def test_nested_index_plate_cuda(kind, n, G):
     m = jbugs.compile(NESTED % NESTED_KINDS[kind], nested_data(kind, n, G, seed=n))
     theta = random_thetas(np.zeros(m.plan.D), 70, seed=2, scale=0.2)
     _check(m.cuda, COracle(m.plan), theta)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["rats", "seeds"])
+def test_forward_only_kernels_give_the_same_logp(which):
+    """logdensity without the gradient runs forward-only instantiations of the large-plate kernels (128-chain CTAs):
+    same log densities as the forward+reverse kernels, and as the C restatement."""
+    from helpers import synth_rats, synth_seeds
+    if which == "rats":
+        data, alpha, beta = synth_rats(5000, seed=9)
+        m = jbugs.compile(jbugs.examples.RATS, data)
+        th0 = np.concatenate([[np.log(4.0), 6.2, np.log(1 / 196.0), 242.0, np.log(1 / 36.0)], np.column_stack([beta, alpha]).ravel()])
+    else:
+        data, b = synth_seeds(20000, seed=9)
+        m = jbugs.compile(jbugs.examples.SEEDS, data)
+        th0 = np.concatenate([[np.log(1 / 0.09), -0.84, 1.36, 0.09, -0.55], b])
+    theta = random_thetas(th0, 200, seed=4, scale=0.05)
+    lp_g, g, st = m.cuda.eval_host(theta, want_grad=True)
+    lp_f, _, st_f = m.cuda.eval_host(theta, want_grad=False)
+    assert np.array_equal(st, st_f) and rel_err(lp_f, lp_g) < 1e-13
+    lp0, _, _ = COracle(m.plan).eval_batch(theta, want_grad=False)
+    assert rel_err(lp_f, lp0) < 1e-10
