@@ -241,13 +241,14 @@ dense_fwd_kernel(const __grid_constant__ DenseFwdParams P) {
                     const double eta = acc[tm][tn][e];
                     const double ax = fabs(eta);
                     const SoftplusParts sp3 = softplus_parts(ax);
-                    const double ex = sp3.e, l1p = sp3.l1p, inv = sp3.inv;
-                    const double p = eta >= 0.0 ? inv : ex * inv;
-                    const double lsp = -((eta >= 0.0 ? 0.0 : ax) + l1p);
-                    const double lsq = -((eta >= 0.0 ? ax : 0.0) + l1p);
-                    double term = (yv == 0.0 ? 0.0 : yv * lsp) + (mv == 0.0 ? 0.0 : mv * lsq);
-                    if (eta > kLogisticUpper && mv != 0.0) term = -dev_inf();
-                    if (eta < kLogisticLower && yv != 0.0) term = -dev_inf();
+                    const bool up = eta >= 0.0;
+                    const double p = up ? sp3.inv : sp3.e * sp3.inv;
+                    // y log p + (n - y) log(1 - p) = -(eta >= 0 ? n - y : y) |eta| - n log1p(exp(-|eta|))
+                    double term = -fma(up ? mv : yv, ax, nv * sp3.l1p);
+                    if (ax > kLogisticUpper) {  // saturated tails (rare): the reference's logistic is exactly 0 / 1 there
+                        if (eta > kLogisticUpper && mv != 0.0) term = -dev_inf();
+                        if (eta < kLogisticLower && yv != 0.0) term = -dev_inf();
+                    }
                     lp[tn][e] += row_ok ? term : 0.0;
                     r2[e] = yv - nv * p;
                 }

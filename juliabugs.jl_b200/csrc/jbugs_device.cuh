@@ -248,10 +248,11 @@ __device__ __forceinline__ SoftplusParts softplus_parts(double ax /* |eta| */) {
     o.e = p * __hiloint2double((k + 1023) << 20, 0);
     // one reciprocal serves both 1/(1+e) and e/(2+e): d = (1+e)(2+e) in (2, 6]
     const double u1 = 1.0 + o.e, u2 = 2.0 + o.e, d = u1 * u2;
+    // 24-bit seed, then one cubic step rc (1 + h + h^2), h = 1 - d rc ~ 1e-7: error h^3 ~ 1e-21 (three DFMA; three
+    // Newton steps would be six FP64 instructions)
     double rc = (double)__frcp_rn((float)d);
-    rc = rc * fma(-d, rc, 2.0);
-    rc = rc * fma(-d, rc, 2.0);
-    rc = rc * fma(-d, rc, 2.0);
+    const double h = fma(-d, rc, 1.0);
+    rc = fma(rc, fma(h, h, h), rc);
     o.inv = rc * u2;
     // log1p(e) = 2 atanh(s), s = e / (2 + e) in (0, 1/3]
     const double s = o.e * (rc * u1), z = s * s;

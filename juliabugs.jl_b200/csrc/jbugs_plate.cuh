@@ -205,16 +205,16 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
         const double n = S::FUSED == FUSED_BERNOULLI_LOGIT ? 1.0 : arg_value(sp.aux(1), V.aux[1], st, sv, g, j);
         const double ax = fabs(eta);
         const SoftplusParts sp3 = softplus_parts(ax);
-        const double e = sp3.e, l1p = sp3.l1p, inv = sp3.inv;
-        const double p = eta >= 0.0 ? inv : e * inv;                 // logistic(eta)
-        const double lsp = -((eta >= 0.0 ? 0.0 : ax) + l1p);          // log p
-        const double lsq = -((eta >= 0.0 ? ax : 0.0) + l1p);          // log(1 - p)
+        const bool up = eta >= 0.0;
+        const double p = up ? sp3.inv : sp3.e * sp3.inv;             // logistic(eta)
         const double m = n - yv;
-        // reference semantics in the saturated tails (LogExpFunctions.logistic returns exactly 0 / 1)
-        const bool sat_hi = eta > kLogisticUpper, sat_lo = eta < kLogisticLower;
-        double term = (yv == 0.0 ? 0.0 : yv * lsp) + (m == 0.0 ? 0.0 : m * lsq);
-        if (sat_hi && m != 0.0) term = -dev_inf();
-        if (sat_lo && yv != 0.0) term = -dev_inf();
+        // k log p + m log(1 - p), with log p = -(max(-eta, 0) + l1p) and log(1 - p) = -(max(eta, 0) + l1p):
+        //   = -(eta >= 0 ? m : k) |eta| - n l1p          (one select, one multiply, one fma)
+        double term = -fma(up ? m : yv, ax, n * sp3.l1p);
+        if (ax > kLogisticUpper) {  // saturated tails (rare): LogExpFunctions.logistic returns exactly 0 / 1 there
+            if (eta > kLogisticUpper && m != 0.0) term = -dev_inf();
+            if (eta < kLogisticLower && yv != 0.0) term = -dev_inf();
+        }
         lp += term;
         deta = yv - n * p;
     } else if (S::FUSED == FUSED_POISSON_LOG) {
