@@ -244,12 +244,12 @@ dense_fwd_kernel(const __grid_constant__ DenseFwdParams P) {
                     const bool up = eta >= 0.0;
                     const double p = up ? sp3.inv : sp3.e * sp3.inv;
                     // y log p + (n - y) log(1 - p) = -(eta >= 0 ? n - y : y) |eta| - n log1p(exp(-|eta|))
-                    double term = -fma(up ? mv : yv, ax, nv * sp3.l1p);
+                    double nll = fma(up ? mv : yv, ax, nv * sp3.l1p);  // minus the log-likelihood term
                     if (ax > kLogisticUpper) {  // saturated tails (rare): the reference's logistic is exactly 0 / 1 there
-                        if (eta > kLogisticUpper && mv != 0.0) term = -dev_inf();
-                        if (eta < kLogisticLower && yv != 0.0) term = -dev_inf();
+                        if (eta > kLogisticUpper && mv != 0.0) nll = dev_inf();
+                        if (eta < kLogisticLower && yv != 0.0) nll = dev_inf();
                     }
-                    lp[tn][e] += row_ok ? term : 0.0;
+                    lp[tn][e] -= row_ok ? nll : 0.0;
                     r2[e] = yv - nv * p;
                 }
                 const long long c = n0 + wn * 32 + tn * 8 + 2 * fk;

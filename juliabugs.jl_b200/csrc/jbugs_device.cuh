@@ -233,14 +233,14 @@ struct SoftplusParts {
 
 __device__ __forceinline__ SoftplusParts softplus_parts(double ax /* |eta| */) {
     SoftplusParts o;
-    double x = -ax;
-    x = x < -700.0 ? -700.0 : x;  // e < 1e-304 below: irrelevant next to |eta|; NaN falls through and propagates
-    // exp(x), x in [-700, 0]: x = k ln2 + r, |r| <= ln2/2, degree-10 polynomial, exact scaling by 2^k
+    const double a = ax > 700.0 ? 700.0 : ax;  // e < 1e-304 beyond: irrelevant next to |eta|; NaN falls through and propagates
+    // exp(-a), a in [0, 700]: -a = k ln2 + r, |r| <= ln2/2, degree-10 polynomial, exact scaling by 2^k
+    // (the sign of a lives in the operand modifiers of the fma's: no separate negation on the FP64 pipe)
     const double magic = 6755399441055744.0;  // 1.5 * 2^52: the low word of (t + magic) is rint(t)
-    const double t = fma(x, 1.4426950408889634074, magic);
+    const double t = fma(a, -1.4426950408889634074, magic);
     const int k = __double2loint(t);
     const double kf = t - magic;
-    double r = fma(kf, -6.93147180369123816490e-01, x);
+    double r = fma(kf, -6.93147180369123816490e-01, -a);
     r = fma(kf, -1.90821492927058770002e-10, r);
     double p = kExpPoly[0];
 #pragma unroll

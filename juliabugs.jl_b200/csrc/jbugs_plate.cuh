@@ -210,12 +210,12 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
         const double m = n - yv;
         // k log p + m log(1 - p), with log p = -(max(-eta, 0) + l1p) and log(1 - p) = -(max(eta, 0) + l1p):
         //   = -(eta >= 0 ? m : k) |eta| - n l1p          (one select, one multiply, one fma)
-        double term = -fma(up ? m : yv, ax, n * sp3.l1p);
+        double nll = fma(up ? m : yv, ax, n * sp3.l1p);  // minus the log-likelihood term
         if (ax > kLogisticUpper) {  // saturated tails (rare): LogExpFunctions.logistic returns exactly 0 / 1 there
-            if (eta > kLogisticUpper && m != 0.0) term = -dev_inf();
-            if (eta < kLogisticLower && yv != 0.0) term = -dev_inf();
+            if (eta > kLogisticUpper && m != 0.0) nll = dev_inf();
+            if (eta < kLogisticLower && yv != 0.0) nll = dev_inf();
         }
-        lp += term;
+        lp -= nll;
         deta = yv - n * p;
     } else if (S::FUSED == FUSED_POISSON_LOG) {
         // k ~ dpois(exp(eta)): k * eta - exp(eta); -lgamma(k+1) goes to obs_const
