@@ -255,3 +255,56 @@ def test_forward_only_kernels_give_the_same_logp(which):
     assert np.array_equal(st, st_f) and rel_err(lp_f, lp_g) < 1e-13
     lp0, _, _ = COracle(m.plan).eval_batch(theta, want_grad=False)
     assert rel_err(lp_f, lp0) < 1e-10
+
+
+# ---- several plates in one model (two data sets sharing hyper-parameters; different loop extents and families) ----
+TWO_PLATES = """model {
+  for (i in 1:N1) {
+    for (j in 1:T) { Y[i, j] ~ dnorm(mu[i, j], tau.c)
+                     mu[i, j] <- alpha[i] + beta.c * (x[j] - xbar) }
+    alpha[i] ~ dnorm(alpha.c, alpha.tau)
+  }
+  for (k in 1:N2) {
+    r[k] ~ dbin(p[k], n[k])
+    logit(p[k]) <- g0 + beta.c * z[k] + b[k]
+    b[k] ~ dnorm(0, alpha.tau)
+  }
+  for (k in 1:N3) { c[k] ~ dpois(lam[k])
+                    log(lam[k]) <- g0 + w[k] }
+  alpha.c ~ dnorm(0, 1.0E-4)
+  beta.c ~ dnorm(0, 1.0E-2)
+  g0 ~ dnorm(0, 1.0E-2)
+  tau.c ~ dgamma(1.0E-3, 1.0E-3)
+  alpha.tau ~ dgamma(1.0E-1, 1.0E-1)
+}"""
+
+
+def two_plates_data(N1, N2, N3, seed=0):
+    r = np.random.default_rng(seed)
+    n = r.integers(1, 20, N2).astype(float)
+    return {"N1": N1, "T": 4, "N2": N2, "N3": N3, "x": np.array([1.0, 2.0, 4.0, 7.0]), "xbar": 3.5,
+            "Y": r.normal(3.0, 1.0, (N1, 4)), "z": r.standard_normal(N2), "n": n,
+            "r": r.binomial(n.astype(int), 0.4).astype(float), "w": 0.3 * r.standard_normal(N3),
+            "c": r.poisson(1.5, N3).astype(float)}
+
+
+def test_three_plates_plan_matches_node_loop():
+    data = two_plates_data(7, 9, 5)
+    gm = go.compile(TWO_PLATES, data).use_generated_order()
+    plan, lw = jbugs.lower(TWO_PLATES, data)
+    assert len(plan.plates) == 3 and lw.param_names() == gm.param_names()
+    theta = random_thetas(np.zeros(plan.D), 3, seed=1, scale=0.3)
+    lp, g, st = COracle(plan).eval_batch(theta)
+    for c in range(3):
+        lp_g, g_g = gm.logdensity_and_gradient(theta[:, c])
+        assert abs(lp[c] - lp_g) <= 1e-12 * abs(lp_g) and rel_err(g[:, c], g_g) < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sizes,C", [((7, 9, 5), 5), ((700, 1300, 90), 150)])
+def test_three_plates_cuda(sizes, C):
+    from test_gpu_parity import _check
+    m = jbugs.compile(TWO_PLATES, two_plates_data(*sizes, seed=3))
+    theta = random_thetas(np.zeros(m.plan.D), C, seed=2, scale=0.2)
+    _check(m.cuda, COracle(m.plan), theta)
+    _check(m.cuda, COracle(m.plan), theta, layout="param_fast")
