@@ -61,6 +61,12 @@ class Chains:
             return arr.reshape(self.samples.shape[0], self.samples.shape[2])
         raise KeyError(name)
 
+    def summary(self, names: Optional[Sequence[str]] = None) -> Dict[str, Dict[str, float]]:
+        """mean, sd, split-R-hat and effective sample size per quantity (what `summarize(chains)` of MCMCChains shows
+        for the reference's runs; `J/test/ext/JuliaBUGSAdvancedHMCExt.jl:56-62` reads mean and std from it)."""
+        return {n: dict(mean=float(self[n].mean()), std=float(self[n].std(ddof=1)), rhat=split_rhat(self[n]),
+                        ess=effective_sample_size(self[n])) for n in (names or self.names)}
+
     def generated_quantities(self, seed: int = 0) -> Dict[str, np.ndarray]:
         """logical nodes outside the target and forward draws of unobserved stochastic leaves, computed from the
         monitored parameters for every draw at once (reference: J/src/model/abstractmcmc.jl:92-110)."""
@@ -75,6 +81,42 @@ class Chains:
 
     def std(self, name):
         return float(self[name].std())
+
+
+def split_rhat(x: np.ndarray) -> float:
+    """split-R-hat (Gelman et al., BDA3) of draws x[n_samples, n_chains]: every chain is cut in two halves."""
+    n = x.shape[0] // 2
+    if n < 2:
+        return float("nan")
+    h = np.concatenate([x[:n], x[n:2 * n]], axis=1)           # [n, 2 * chains]
+    w = h.var(axis=0, ddof=1).mean()
+    b = n * h.mean(axis=0).var(ddof=1)
+    return float(np.sqrt(((n - 1) / n * w + b / n) / w)) if w > 0 else float("nan")
+
+
+def effective_sample_size(x: np.ndarray) -> float:
+    """ESS of draws x[n_samples, n_chains] from the chain-averaged autocorrelation with Geyer's initial positive
+    sequence truncation (the estimator Stan and MCMCChains use, without rank normalisation)."""
+    n, m = x.shape
+    if n < 4:
+        return float("nan")
+    xc = x - x.mean(axis=0, keepdims=True)
+    nfft = 1 << int(np.ceil(np.log2(2 * n)))
+    f = np.fft.rfft(xc, nfft, axis=0)
+    acov = np.fft.irfft(f * np.conj(f), nfft, axis=0)[:n] / n   # biased autocovariance per chain
+    w = acov[0].mean() * n / (n - 1)
+    var_plus = w * (n - 1) / n + (x.mean(axis=0).var(ddof=1) if m > 1 else 0.0)
+    if not var_plus > 0:
+        return float("nan")
+    rho = 1.0 - (w - acov.mean(axis=1)) / var_plus
+    tau, t = -1.0, 0
+    while t + 1 < n:
+        pair = rho[t] + rho[t + 1]
+        if pair < 0:
+            break
+        tau += 2.0 * pair
+        t += 2
+    return float(n * m / max(tau, 1.0 / np.log10(max(n * m, 10))))
 
 
 def _bind(L):

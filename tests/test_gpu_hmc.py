@@ -111,6 +111,8 @@ def test_nuts_rats_and_seeds_match_winbugs_reference(fixtures):
         assert got[k].mean() == pytest.approx(mean, rel=0.02), k
         assert got[k].std() == pytest.approx(std, rel=0.12), k
     assert 0.6 < ch.accept_rate < 0.95
+    diag = ch.summary(["beta.c", "alpha.c", "tau.c"])
+    assert all(d["rhat"] < 1.05 and d["ess"] > 2000 for d in diag.values()), diag   # 128 chains x 500 draws
     fx = fixtures["seeds"]
     m = jbugs.compile(jbugs.examples.SEEDS, fx["data"], fx["inits"])
     ch = hmc.sample(m, hmc.NUTS(max_depth=8, step_size=0.01, jitter=0.05), n_samples=500, n_adapts=1000, n_chains=128, seed=22)

@@ -117,3 +117,22 @@ def test_condition_and_decondition(fixtures):
     assert jbugs.decondition(md).plan.to_bytes() == m.plan.to_bytes()
     with pytest.raises(KeyError):
         jbugs.decondition(m, "tau.c")
+
+
+def test_chain_diagnostics_on_known_processes():
+    """split-R-hat ~ 1 and ESS ~ N (1 - rho) / (1 + rho) for stationary AR(1) chains; R-hat >> 1 when chains disagree."""
+    from jbugs.hmc import Chains, effective_sample_size, split_rhat
+    rng = np.random.default_rng(0)
+    n, m, rho = 4000, 8, 0.6
+    x = np.empty((n, m))
+    x[0] = rng.standard_normal(m)
+    for t in range(1, n):
+        x[t] = rho * x[t - 1] + np.sqrt(1 - rho * rho) * rng.standard_normal(m)
+    assert abs(split_rhat(x) - 1.0) < 0.01
+    assert effective_sample_size(x) == pytest.approx(n * m * (1 - rho) / (1 + rho), rel=0.12)
+    iid = rng.standard_normal((n, m))
+    assert effective_sample_size(iid) == pytest.approx(n * m, rel=0.1)
+    assert split_rhat(iid + np.arange(m)[None, :]) > 1.5
+    ch = Chains(["a"], iid[:, None, :], 0.8, 0.1)
+    s = ch.summary()["a"]
+    assert abs(s["mean"]) < 0.03 and abs(s["std"] - 1.0) < 0.03 and abs(s["rhat"] - 1.0) < 0.01
