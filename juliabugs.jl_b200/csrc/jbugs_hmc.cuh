@@ -67,6 +67,21 @@ hmc_init_kernel(double* __restrict__ q, long long ld, long long D, long long C, 
     for (long long d = d0; d < d1; ++d) q[d * ld + c] = theta0[d] + jitter * normal2(seed, d * C + c, 0u, 1u).x;
 }
 
+// chains whose start has no finite log density (or a DomainError) are drawn again closer to theta0: jitter / 2^attempt.
+// `n_bad` counts them (set to 0 by the host before the launch; every row tile of a bad chain adds 1).
+__global__ void __launch_bounds__(BLOCK)
+hmc_reinit_kernel(double* __restrict__ q, long long ld, long long D, long long C, const double* __restrict__ theta0,
+                  double jitter, unsigned long long seed, unsigned attempt, const double* __restrict__ lp,
+                  const int* __restrict__ status, int* __restrict__ n_bad, long long HMC_ROWS) {
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    const double l = lp[c];
+    if (l == l && fabs(l) != dev_inf() && status[c] == 0) return;
+    if (blockIdx.y == 0) atomicAdd(n_bad, 1);
+    const long long d0 = (long long)blockIdx.y * HMC_ROWS, d1 = d0 + HMC_ROWS < D ? d0 + HMC_ROWS : D;
+    for (long long d = d0; d < d1; ++d) q[d * ld + c] = theta0[d] + jitter * normal2(seed, d * C + c, attempt, 5u).x;
+}
+
 // fresh momentum p ~ N(0, M), M = diag(1 / var);  kinetic partial sums 0.5 * sum p^2 var
 __global__ void __launch_bounds__(BLOCK)
 hmc_refresh_kernel(double* __restrict__ p, long long ld, long long D, long long C, const double* __restrict__ var,
