@@ -147,8 +147,8 @@ int jbugs_last_timing(const jbugs_plan* plan, float* plate_ms, float* total_ms);
  * (ext/JuliaBUGSAdvancedHMCExt.jl:40-66), which calls logdensity_and_gradient once per leapfrog step with theta on the
  * host.  C chains advance in lock step; theta, momentum and gradient stay in HBM (5 x D x C doubles).
  *   jbugs_hmc_init : every chain starts at theta0 + jitter * N(0,1) (unconstrained space)
- *   jbugs_hmc_run  : n_iter transitions of n_leapfrog steps.  adapt != 0: warm-up (dual-averaging step size pooled over
- *                    chains, windowed diagonal metric from moments pooled over chains).  The monitored theta rows of
+ *   jbugs_hmc_run  : n_iter transitions of n_leapfrog steps.  adapt != 0: warm-up (dual averaging of a per-chain step
+ *                    size on the device, windowed diagonal metric from moments pooled over chains).  The monitored theta rows of
  *                    every iteration are written to out_host[n_iter][n_monitor][C]. */
 typedef struct jbugs_hmc_s jbugs_hmc;
 int jbugs_hmc_create(jbugs_plan* plan, int64_t C, uint64_t seed, jbugs_hmc** out);

@@ -43,13 +43,55 @@ __device__ __forceinline__ double2 normal2(unsigned long long seed, unsigned lon
 
 // per-transition scalars live in device memory so that a captured CUDA graph of the trajectory can be replayed with a
 // new step size / iteration counter (set by hmc_ctl_kernel just before the graph launch)
+// per-chain step size and its dual-averaging state (Hoffman & Gelman 2014): every chain adapts to its own acceptance
+// statistic, as the reference's independent chains do; the metric is pooled over chains
+struct HmcDa {
+    double *eps, *hbar, *logeps_bar, *mu;  // [ld] each
+};
+
 struct HmcCtl {
-    double eps;
+    double eps;           // multiplier of every chain's step size in this transition (the +-10 % jitter)
     unsigned it;
     unsigned pad;
     double mean_accept;   // mean acceptance probability of the last transition
     double accept_total;  // running sum of those means since the last reset
 };
+
+__global__ void __launch_bounds__(BLOCK) hmc_da_init_kernel(HmcDa da, long long C, double eps0) {
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    da.eps[c] = eps0;
+    da.mu[c] = log(10.0 * eps0);
+    da.hbar[c] = 0.0;
+    da.logeps_bar[c] = log(eps0);
+}
+// m = number of updates since the last restart (1, 2, ...); final_ != 0: leave the averaged step size in place
+__global__ void __launch_bounds__(BLOCK)
+hmc_da_update_kernel(HmcDa da, const double* __restrict__ accept_prob, long long C, double m, int final_) {
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    const double delta = 0.8, gamma = 0.05, t0 = 10.0, kappa = 0.75;
+    double a = accept_prob[c];
+    if (!(a == a)) a = 0.0;
+    const double hbar = (1.0 - 1.0 / (m + t0)) * da.hbar[c] + (delta - a) / (m + t0);
+    const double logeps = da.mu[c] - sqrt(m) / gamma * hbar;
+    const double eta = pow(m, -kappa);
+    const double lb = eta * logeps + (1.0 - eta) * da.logeps_bar[c];
+    da.hbar[c] = hbar;
+    da.logeps_bar[c] = lb;
+    const double e = exp(final_ ? lb : logeps);
+    da.eps[c] = fmin(fmax(e, 1e-10), 1e4);
+}
+// new metric window: continue from the averaged step size
+__global__ void __launch_bounds__(BLOCK) hmc_da_restart_kernel(HmcDa da, long long C) {
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    const double e = fmin(fmax(exp(da.logeps_bar[c]), 1e-10), 1e4);
+    da.eps[c] = e;
+    da.mu[c] = log(10.0 * e);
+    da.hbar[c] = 0.0;
+    da.logeps_bar[c] = log(e);
+}
 
 __global__ void hmc_ctl_kernel(HmcCtl* ctl, double eps, unsigned it, int reset_total) {
     ctl->eps = eps;
@@ -110,11 +152,11 @@ hmc_refresh_kernel(double* __restrict__ p, long long ld, long long D, long long 
 __global__ void __launch_bounds__(BLOCK)
 hmc_leap_kernel(const double* q_in, double* q_out /* may alias q_in */, double* __restrict__ p,
                 const double* __restrict__ g, long long ld, long long D, long long C, const double* __restrict__ var,
-                const HmcCtl* __restrict__ ctl, double wp, double wq, double* __restrict__ kin_partial, long long ldg,
-                long long HMC_ROWS) {
+                const HmcCtl* __restrict__ ctl, const double* __restrict__ eps_c, double wp, double wq,
+                double* __restrict__ kin_partial, long long ldg, long long HMC_ROWS) {
     const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (c >= C) return;
-    const double eps = ctl->eps;
+    const double eps = ctl->eps * eps_c[c];
     const long long d0 = (long long)blockIdx.y * HMC_ROWS, d1 = d0 + HMC_ROWS < D ? d0 + HMC_ROWS : D;
     double k = 0.0;
     // four rows at a time, every load issued before the first use (the index is clamped, not predicated)

@@ -109,12 +109,13 @@ nuts_load_end_kernel(NutsState S, double* __restrict__ qw, double* __restrict__ 
 // first half of a leapfrog step in the chain's own direction:  p += dir eps/2 g ;  q += dir eps var p
 __global__ void __launch_bounds__(BLOCK)
 nuts_leap_a_kernel(NutsState S, double* __restrict__ q, double* __restrict__ p, const double* __restrict__ g, long long ld,
-                   long long D, long long C, const double* __restrict__ var, const HmcCtl* __restrict__ ctl, long long ROWS) {
+                   long long D, long long C, const double* __restrict__ var, const HmcCtl* __restrict__ ctl,
+                   const double* __restrict__ eps_c, long long ROWS) {
     const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (c >= C) return;
     const int dir = S.valid[c] ? S.dir[c] : 0;
     if (dir == 0) return;
-    const double eps = ctl->eps * (double)dir;
+    const double eps = ctl->eps * eps_c[c] * (double)dir;
     const long long d0 = (long long)blockIdx.y * ROWS, d1 = d0 + ROWS < D ? d0 + ROWS : D;
     for (long long d = d0; d < d1; d += 4) {
         double gv[4], pv[4], qv[4], vv[4];
@@ -138,7 +139,8 @@ nuts_leap_a_kernel(NutsState S, double* __restrict__ q, double* __restrict__ p, 
 // kinetic energy, rhoS += p, checkpoint (even leaves) or sub-tree U-turn dot products (odd leaves)
 __global__ void __launch_bounds__(BLOCK)
 nuts_leaf_rows_kernel(NutsState S, double* __restrict__ p, const double* __restrict__ g, long long ld, long long D, long long C,
-                      const double* __restrict__ var, const HmcCtl* __restrict__ ctl, long long ROWS, int n_rows_partial) {
+                      const double* __restrict__ var, const HmcCtl* __restrict__ ctl, const double* __restrict__ eps_c,
+                      long long ROWS, int n_rows_partial) {
     const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (c >= C) return;
     const int dir = S.valid[c] ? S.dir[c] : 0;
@@ -151,7 +153,7 @@ nuts_leaf_rows_kernel(NutsState S, double* __restrict__ p, const double* __restr
         part[0] = 0.0;
         return;
     }
-    const double eps = ctl->eps * (double)dir;
+    const double eps = ctl->eps * eps_c[c] * (double)dir;
     const long long d0 = (long long)blockIdx.y * ROWS, d1 = d0 + ROWS < D ? d0 + ROWS : D;
     const long long plane = D * ld;
     double k = 0.0;
