@@ -127,12 +127,11 @@ def test_chains_starting_outside_the_support_are_redrawn():
     log density -Inf).  The sampler redraws those chains closer to the initial value instead of leaving them frozen at
     a point where every proposal is compared with -Inf."""
     y = np.array([3.0, 5.0, 4.0, 6.0, 2.0])
-    m = jbugs.compile("model { for (i in 1:N) { y[i] ~ dpois(alpha) }\n alpha ~ dnorm(4.0, 0.01) }", {"N": 5, "y": y}, {"alpha": 3.0})
-    ch = hmc.sample(m, hmc.HMC(n_leapfrog=8, step_size=0.05, jitter=2.0), n_samples=300, n_adapts=300, n_chains=256, seed=2)
+    m = jbugs.compile("model { for (i in 1:N) { y[i] ~ dpois(alpha) }\n alpha ~ dnorm(4.0, 0.01) }", {"N": 5, "y": y}, {"alpha": 0.5})
+    ch = hmc.sample(m, hmc.HMC(n_leapfrog=8, step_size=0.05, jitter=3.0), n_samples=300, n_adapts=300, n_chains=256, seed=2)
     a = ch["alpha"]
-    assert np.all(np.isfinite(a)) and np.all(a > 0.0)          # ~7 % of the starts were negative
-    moving = a.std(axis=0) > 0.3
-    assert moving.mean() > 0.98                                 # (a start within 0.05 of the boundary can still stick:
-    #                                                              the step size is pooled over the chains)
+    assert np.all(np.isfinite(a)) and np.all(a > 0.0)          # ~43 % of the starts were negative
+    assert a.std(axis=0).min() > 0.3                            # every chain moves: a start right at the boundary gets
+    #                                                              its own small step size from the per-chain adaptation
     # the likelihood dominates the vague prior: posterior close to Gamma(sum y + 1, n)
-    assert a[:, moving].mean() == pytest.approx((y.sum() + 1) / 5.0, rel=0.05)
+    assert a.mean() == pytest.approx((y.sum() + 1) / 5.0, rel=0.05)
