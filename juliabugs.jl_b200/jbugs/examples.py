@@ -294,6 +294,22 @@ model {
 }
 """
 
+# Beetles (BUGS examples vol. 2): dose-response with a choice of link function; BEETLES % "logit" | "probit" | "cloglog"
+BEETLES = """
+model {
+    for (i in 1:N) {
+        r[i] ~ dbin(p[i], n[i])
+        %s(p[i]) <- alpha.star + beta * (x[i] - mean(x[]))
+        rhat[i] <- n[i] * p[i]
+    }
+    alpha <- alpha.star - beta * mean(x[])
+    beta ~ dnorm(0.0, 0.001)
+    alpha.star ~ dnorm(0.0, 0.001)
+}
+"""
+BEETLES_DATA = {"x": [1.6907, 1.7242, 1.7552, 1.7842, 1.8113, 1.8369, 1.8610, 1.8839],
+                "n": [59, 60, 62, 56, 63, 59, 62, 60], "r": [6, 13, 18, 28, 52, 53, 61, 60], "N": 8}
+
 MODELS = {
     "stacks": STACKS,
     "salm": SALM,

@@ -135,3 +135,20 @@ def test_chains_starting_outside_the_support_are_redrawn():
     #                                                              its own small step size from the per-chain adaptation
     # the likelihood dominates the vague prior: posterior close to Gamma(sum y + 1, n)
     assert a.mean() == pytest.approx((y.sum() + 1) / 5.0, rel=0.05)
+
+
+@pytest.mark.parametrize("link,ref", [
+    # WinBUGS reference results shipped with the example (J/src/BUGSExamples/Volume_2/13_Beetles.jl:42-76)
+    ("logit", {"alpha": (-60.78, 5.168), "beta": (34.3, 2.904), "rhat[1]": (3.571, 0.957), "rhat[4]": (33.9, 1.768), "rhat[8]": (58.68, 0.4284)}),
+    ("probit", {"alpha": (-35.08, 2.64), "beta": (19.81, 1.485), "rhat[1]": (3.429, 1.015), "rhat[6]": (53.28, 1.153)}),
+    ("cloglog", {"alpha": (-39.7, 3.197), "beta": (22.11, 1.775), "rhat[1]": (5.646, 1.113), "rhat[5]": (47.74, 1.712)}),
+])
+def test_beetles_three_links_match_winbugs_reference(link, ref):
+    """Beetles with the logit, probit and complementary log-log links: NUTS posterior of the parameters and of the
+    generated quantities alpha and rhat[i] = n[i] p[i] against the WinBUGS values, well inside the reference's rtol 0.3."""
+    m = jbugs.compile(jbugs.examples.BEETLES % link, jbugs.examples.BEETLES_DATA, {"alpha.star": 0.0, "beta": 0.0})
+    ch = hmc.sample(m, hmc.NUTS(max_depth=8, step_size=0.05, jitter=0.1), n_samples=500, n_adapts=700, n_chains=128, seed=31)
+    for k, (mean, std) in ref.items():
+        assert ch[k].mean() == pytest.approx(mean, rel=0.03), (link, k)
+        assert ch[k].std() == pytest.approx(std, rel=0.12), (link, k)
+    assert ch.summary(["beta"])["beta"]["rhat"] < 1.05
