@@ -133,6 +133,14 @@ int jbugs_comm_destroy(jbugs_plan* plan);
 int64_t jbugs_launch_count(const jbugs_plan* plan);
 int jbugs_plan_describe(const jbugs_plan* plan, char* buf, size_t nbuf);
 
+/* Run-time specialisation (optional).  Plates whose shape has no in-tree specialised kernel run the
+ * interpreter instantiation; this call writes the constexpr description of each such plate as C++
+ * source, compiles the SAME kernel body for it with nvcc (sm_100a) into a small shared object next
+ * to `cache_dir` (NULL: $JBUGS_JIT_CACHE or /tmp/jbugs_jit; cached by a hash of the shape) and uses
+ * it from then on.  Needs nvcc ($JBUGS_NVCC or /usr/local/cuda/bin/nvcc) and the in-tree kernel
+ * headers next to the library; returns JBUGS_ERR_UNSUPPORTED otherwise and nothing changes. */
+int jbugs_plan_specialize(jbugs_plan* plan, const char* cache_dir);
+
 /* Tuning knobs (tests force the generic interpreter path with "dynamic=1"). Unknown keys fail. */
 int jbugs_plan_set_option(jbugs_plan* plan, const char* key, int64_t value);
 

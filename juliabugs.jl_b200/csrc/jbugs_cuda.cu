@@ -83,6 +83,10 @@ struct PlateRt {
     double obs_const = 0.0;
     bool const_dirty = true;  // obs_const must be recomputed (new data / shard / kernel variant)
     size_t smem_bytes = 0;    // dynamic shared memory of the plate kernel (J region + two stages)
+    // run-time specialisation (jbugs_plan_specialize): a kernel compiled for exactly this plate's shape
+    plate_launch_fn jit_launch = nullptr;
+    int jit_fused = FUSED_NONE;
+    bool jit_valid = true;    // false: the data are outside the fused formulas' domain -> interpreter
 };
 
 struct jbugs_plan_s {
@@ -348,7 +352,8 @@ static int refresh_obs_const(jbugs_plan* p, int k, cudaStream_t st) {
     r.obs_const = 0.0;
     r.const_dirty = false;
     p->epoch++;
-    const int fused = g_specs[r.variant].fused;
+    const int fused = (r.variant == 0 && r.jit_launch && !p->force_dynamic) ? r.jit_fused : g_specs[r.variant].fused;
+    r.jit_valid = true;
     if (fused != FUSED_BINOMIAL_LOGIT && fused != FUSED_POISSON_LOG && fused != FUSED_BERNOULLI_LOGIT) return 0;
     const PlateParams& pp = r.pp;
     if (pp.v.i1 <= pp.v.i0) return 0;
@@ -362,6 +367,7 @@ static int refresh_obs_const(jbugs_plan* p, int k, cudaStream_t st) {
     CU(cudaStreamSynchronize(st));
     if (h[1] != 0.0) {
         r.variant = 0;  // data outside the fused formulas' domain: the interpreter reproduces the -Inf semantics
+        r.jit_valid = false;
         r.obs_const = 0.0;
     } else {
         r.obs_const = h[0];
@@ -657,7 +663,8 @@ extern "C" int jbugs_plan_describe(const jbugs_plan* p, char* buf, size_t nbuf) 
     for (size_t k = 0; k < p->rt.size(); ++k) {
         const auto& r = p->rt[k];
         snprintf(line, sizeof line, "plate %zu: N=%lld T=%lld kernel=%s tiles=%lld tile=%lld gref=%d\n", k, r.pp.v.N, r.pp.v.T,
-                 spec_name(r.variant), r.n_tiles, r.pp.v.tile, r.pp.sh.n_gref);
+                 (r.variant == 0 && r.jit_launch && r.jit_valid && !p->force_dynamic) ? "specialised_at_run_time" : spec_name(r.variant),
+                 r.n_tiles, r.pp.v.tile, r.pp.sh.n_gref);
         s += line;
     }
     snprintf(buf, nbuf, "%s", s.c_str());
@@ -832,7 +839,9 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
             pp.v.loc[l].step_i = pp.v.loc[l].si * ld;
             pp.v.loc[l].step_j = pp.v.loc[l].sj * ld;
         }
-        cudaError_t le = g_specs[r.variant].launch(r.n_tiles, r.smem_bytes, st, pp, theta, grad, ld, C, p->d_gvals, ldg,
+        const bool jit = r.variant == 0 && r.jit_launch && r.jit_valid && !p->force_dynamic;
+        if (!jit && r.variant == 0) fp.p[k].obs_const = 0.0;  // the interpreter evaluates the full log-density itself
+        cudaError_t le = (jit ? r.jit_launch : g_specs[r.variant].launch)(r.n_tiles, r.smem_bytes, st, pp, theta, grad, ld, C, p->d_gvals, ldg,
                                                    p->d_partial + r.partial_offset * ldg, p->d_flags, want_grad && grad, p->use_pdl);
         if (le != cudaSuccess) return fail(JBUGS_ERR_CUDA, "plate kernel launch failed: %s", cudaGetErrorString(le));
         p->launches++;
@@ -1009,6 +1018,7 @@ extern "C" int jbugs_eval_batch(jbugs_plan* p, const double* theta, int64_t ld, 
 
 #include "jbugs_hmc.inc"
 #include "jbugs_nuts.inc"
+#include "jbugs_jit.inc"
 
 extern "C" int jbugs_batch_alloc(jbugs_plan* p, int64_t C, double** theta_dev, double** grad_dev, double** logp_dev,
                                  int32_t** status_dev, int64_t* ld) {

@@ -178,7 +178,9 @@ struct StaticSpec {
     __device__ __forceinline__ constexpr ArgS cov(int t) const { return Desc::sh().cov[t]; }
     __device__ __forceinline__ constexpr ArgS y() const { return Desc::sh().y; }
     __device__ __forceinline__ constexpr ArgS aux(int q) const { return Desc::sh().aux[q]; }
-    __device__ __forceinline__ constexpr bool has_w() const { return false; }  // static specs are rectangular plates
+    __device__ __forceinline__ constexpr bool has_w() const {  // (only a run-time generated description has a weight)
+        return Desc::sh().aux[2].kind == JBUGS_ARG_DATA_I || Desc::sh().aux[2].kind == JBUGS_ARG_DATA_IJ;
+    }
     __device__ __forceinline__ constexpr int loc_level(int l) const { return Desc::sh().loc[l].level; }
     __device__ __forceinline__ constexpr int loc_transform(int l) const { return Desc::sh().loc[l].transform; }
     __device__ __forceinline__ constexpr int loc_family(int l) const { return Desc::sh().loc[l].family; }

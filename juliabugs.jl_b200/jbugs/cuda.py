@@ -25,7 +25,7 @@ SYMBOLS = [
     "jbugs_batch_free", "jbugs_host_alloc", "jbugs_host_free", "jbugs_comm_unique_id", "jbugs_comm_init",
     "jbugs_comm_destroy", "jbugs_launch_count", "jbugs_plan_describe", "jbugs_plan_set_option",
     "jbugs_last_timing", "jbugs_hmc_create", "jbugs_hmc_destroy", "jbugs_hmc_init", "jbugs_hmc_run",
-    "jbugs_hmc_get_state", "jbugs_hmc_run_nuts", "jbugs_hmc_nuts_stats",
+    "jbugs_hmc_get_state", "jbugs_hmc_run_nuts", "jbugs_hmc_nuts_stats", "jbugs_plan_specialize",
 ]
 
 
@@ -57,6 +57,7 @@ def load():
     L.jbugs_plan_upload_data.argtypes = [c.c_void_p, c.c_int, c.c_void_p, c.c_size_t, c.c_int]
     L.jbugs_plan_set_shard.argtypes = [c.c_void_p, c.c_int, c.c_int64, c.c_int64]
     L.jbugs_plan_set_dense_shard.argtypes = [c.c_void_p, c.c_int64, c.c_int64]
+    L.jbugs_plan_specialize.argtypes = [c.c_void_p, c.c_char_p]
     L.jbugs_eval_batch.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_void_p, c.c_void_p,
                                    c.c_void_p, c.c_int, c.c_int, c.c_void_p]
     L.jbugs_batch_alloc.argtypes = [c.c_void_p, c.c_int64, c.POINTER(c.c_void_p), c.POINTER(c.c_void_p),
@@ -135,6 +136,11 @@ class CudaPlan:
 
     def set_shard(self, plate: int, i0: int, i1: int):
         _check(self.L.jbugs_plan_set_shard(self.h, plate, i0, i1))
+
+    def specialize(self, cache_dir: Optional[str] = None):
+        """compile the plate kernel for the exact shape of every plate that has no in-tree specialisation (nvcc at run
+        time, cached on disk); without it those plates run the interpreter instantiation."""
+        _check(self.L.jbugs_plan_specialize(self.h, cache_dir.encode() if cache_dir else None))
 
     def set_dense_shard(self, i0: int, i1: int):
         _check(self.L.jbugs_plan_set_dense_shard(self.h, i0, i1))
