@@ -354,7 +354,7 @@ static int refresh_obs_const(jbugs_plan* p, int k, cudaStream_t st) {
     p->epoch++;
     const int fused = (r.variant == 0 && r.jit_launch && !p->force_dynamic) ? r.jit_fused : g_specs[r.variant].fused;
     r.jit_valid = true;
-    if (fused != FUSED_BINOMIAL_LOGIT && fused != FUSED_POISSON_LOG && fused != FUSED_BERNOULLI_LOGIT) return 0;
+    if (fused == FUSED_NONE || fused == FUSED_NORMAL_IDENTITY) return 0;  // the other paths drop a data-only normaliser
     const PlateParams& pp = r.pp;
     if (pp.v.i1 <= pp.v.i0) return 0;
     double* d_out = p->d_gvals ? p->d_red : nullptr;  // d_red has room for >= 2 doubles once a workspace exists

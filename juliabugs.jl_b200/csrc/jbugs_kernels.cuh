@@ -142,7 +142,10 @@ struct DynSpec {
 
 // fused observation paths (family x link pairs with a hand-derived forward+reverse)
 enum { FUSED_NONE = 0, FUSED_NORMAL_IDENTITY = 1, FUSED_BINOMIAL_LOGIT = 2, FUSED_POISSON_LOG = 3,
-       FUSED_BERNOULLI_LOGIT = 4 };
+       FUSED_BERNOULLI_LOGIT = 4,
+       // any inverse-link tape (probit, cloglog, identity, ...): the kernel keeps the theta-dependent part of the
+       // log-density, the data-only normaliser goes to obs_const exactly as for the logit / log versions
+       FUSED_BINOMIAL_LINK = 5, FUSED_BERNOULLI_LINK = 6, FUSED_POISSON_LINK = 7 };
 
 // A static spec is a struct with `static constexpr PlateShape SH` ; see specs in jbugs_cuda.cu.
 template <class Desc>

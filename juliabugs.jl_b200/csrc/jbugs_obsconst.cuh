@@ -24,14 +24,14 @@ obs_const_kernel(int fused, const double* __restrict__ y, const double* __restri
     for (long long q = threadIdx.x; q < count; q += 1024) {
         const long long i = i0 + q / T, j = q % T;
         const double k = y_ij ? y[i + N * j] : y[i];
-        if (fused == FUSED_POISSON_LOG) {
+        if (fused == FUSED_POISSON_LOG || fused == FUSED_POISSON_LINK) {
             bad |= !(k >= 0.0) || k != floor(k);
             acc -= lgamma(k + 1.0);
-        } else if (fused == FUSED_BINOMIAL_LOGIT) {
+        } else if (fused == FUSED_BINOMIAL_LOGIT || fused == FUSED_BINOMIAL_LINK) {
             const double nn = n_kind == JBUGS_ARG_DATA_IJ ? n[i + N * j] : (n_kind == JBUGS_ARG_DATA_I ? n[i] : n_const);
             bad |= !(nn >= 0.0) || !(k >= 0.0) || k > nn || k != floor(k);
             acc -= logbeta(k + 1.0, nn - k + 1.0) + log(nn + 1.0);
-        } else if (fused == FUSED_BERNOULLI_LOGIT) {
+        } else if (fused == FUSED_BERNOULLI_LOGIT || fused == FUSED_BERNOULLI_LINK) {
             bad |= !(k == 0.0 || k == 1.0);
         }
     }

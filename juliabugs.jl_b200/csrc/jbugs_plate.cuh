@@ -223,6 +223,28 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
         // xlogy(k, lambda) saturates to -Inf once exp underflows to 0 (reference semantics)
         lp += (yv == 0.0 ? 0.0 : (lam == 0.0 ? -dev_inf() : yv * eta)) - lam;
         deta = yv - lam;
+    } else if (S::FUSED == FUSED_BINOMIAL_LINK || S::FUSED == FUSED_BERNOULLI_LINK || S::FUSED == FUSED_POISSON_LINK) {
+        // any inverse-link tape; only the theta-dependent part of the log-density (the rest is in obs_const)
+        double v = eta, dv = 1.0;
+#pragma unroll
+        for (int q = 0; q < JBUGS_MAX_LINK; ++q)
+            if (q < sp.n_link()) {
+                double nv, d;
+                bad |= unary_op(sp.link(q), v, nv, d);
+                v = nv;
+                dv *= d;
+            }
+        if (S::FUSED == FUSED_POISSON_LINK) {
+            bad |= !(v >= 0.0);
+            lp += xlogy(yv, v) - v;
+            deta = ((yv == 0.0 ? 0.0 : yv / v) - 1.0) * dv;
+        } else {
+            const double n = S::FUSED == FUSED_BERNOULLI_LINK ? 1.0 : arg_value(sp.aux(1), V.aux[1], st, sv, g, j);
+            const double m = n - yv;
+            bad |= !(v >= 0.0 && v <= 1.0);
+            lp += xlogy(yv, v) + xlog1py(m, -v);
+            deta = ((yv == 0.0 ? 0.0 : yv / v) - (m == 0.0 ? 0.0 : m / (1.0 - v))) * dv;
+        }
     } else {
         double v = eta, dv = 1.0;
 #pragma unroll
