@@ -46,8 +46,11 @@ class UseGeneratedLogDensityFunction(EvaluationMode):
 
 @dataclass
 class UseCUDABatch(EvaluationMode):
-    """The new evaluation mode: plate plan + libjbugs_cuda on one B200."""
+    """The new evaluation mode: plate plan + libjbugs_cuda on one B200.  `specialize=True` compiles a kernel for the
+    exact shape of every plate that has no in-tree specialisation when the device plan is built (nvcc at run time,
+    cached on disk; the reference generates and compiles Julia code per model at the same point, bugsmodel.jl:736-801)."""
     device: int = 0
+    specialize: bool = False
 
 
 class LogDensityOrder:
@@ -84,6 +87,8 @@ class BUGSModel:
                                  "use set_evaluation_mode(model, UseCUDABatch())")
         if self._cuda is None:
             self._cuda = CudaPlan(self.plan, device=self.evaluation_mode.device)
+            if self.evaluation_mode.specialize:
+                self._cuda.specialize()
         return self._cuda
 
     def invalidate(self):
