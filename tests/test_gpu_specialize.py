@@ -19,7 +19,7 @@ def _nvcc():
 
 
 @pytest.mark.skipif(not os.access(_nvcc(), os.X_OK), reason="nvcc is not installed on this box")
-@pytest.mark.parametrize("which", ["random-3", "random-17", "nested-poisson"])
+@pytest.mark.parametrize("which", ["random-3", "nested-poisson"])   # ~25 s of nvcc each
 def test_specialised_kernel_matches_interpreter(which, tmp_path_factory):
     cache = str(tmp_path_factory.getbasetemp().parent / "jbugs_jit_cache")   # shared by the cases of one session
     if which.startswith("random"):
