@@ -141,12 +141,14 @@ def _constrain(tr, lb, ub, y):
 
 
 def sample(model: BUGSModel, sampler, n_samples: int, n_adapts: int = 500, n_chains: int = 256, seed: int = 1234,
-           monitor: Optional[Sequence[str]] = None, init: Optional[np.ndarray] = None) -> Chains:
+           monitor: Optional[Sequence[str]] = None, init: Optional[np.ndarray] = None, specialize: bool = False) -> Chains:
     """`AbstractMCMC.sample(model, sampler, n_samples; n_adapts, ...)` for `n_chains` lock-step chains.
     `monitor`: parameter labels to record ('tau', 'beta[2]', 'alpha[17]'); default: every scalar parameter."""
     L = load()
     _bind(L)
     cp = model.cuda
+    if specialize:
+        cp.specialize()   # a kernel for this model's plate shapes (nvcc at run time, cached): worth it for long runs
     names = [g.name for g in model.plan.globals] if monitor is None else list(monitor)
     by_name = {g.name: (g.theta_idx, g.transform, g.lb, g.ub) for g in model.plan.globals}
     if any(n not in by_name for n in names):
