@@ -118,3 +118,50 @@ def make(seed, n_max=12):
     lines += [f"  {g} ~ {p}" for g, p in globals_] + ["  " + t for t in tail]
     lines.append("}")
     return "\n".join(lines), data, f"{name}/{link} N={N} T={T}"
+
+
+def make_structured(seed):
+    """random models exercising the structural lowering paths: random effects picked by a data index (regrouped, padded,
+    weighted plate) or sibling observation statements sharing a random effect (merged N x K plate).
+    -> (model text, data dict, description)"""
+    rng = np.random.default_rng(5000 + seed)
+    name, obs_stmt, links, aux, ygen = OBS[int(rng.integers(0, len(OBS)))]
+    link = links[int(rng.integers(0, len(links)))]
+    globals_ = [("b0", GLOBAL_PRIORS[int(rng.integers(0, len(GLOBAL_PRIORS)))]), ("b1", "dnorm(0.0, 1.0)")] + list(aux)
+    if rng.integers(0, 2):
+        # --- gathered: y[i] ~ f(b0 + b1 x[i] + u[g[i]] (+ v[g[i]] z[i]))
+        n, G = int(rng.integers(8, 60)), int(rng.integers(2, 7))
+        grp = np.concatenate([np.arange(1, G + 1), rng.integers(1, G + 1, n - G)]).astype(float)
+        rng.shuffle(grp)
+        data = {"n": n, "G": G, "g": grp, "x": rng.standard_normal(n), "y": ygen(rng, (n,))}
+        if name == "binomial":
+            data["n.tr"] = data["y"] + rng.integers(0, 5, n).astype(float)
+        terms = ["b0", "b1 * x[i]", "u[g[i]]"]
+        body = ["u[k] ~ dnorm(0.0, t.u)"]
+        globals_.append(("t.u", POS_PRIORS[int(rng.integers(0, len(POS_PRIORS)))]))
+        if rng.integers(0, 2):
+            data["z"] = rng.standard_normal(n)
+            terms.append("v[g[i]] * z[i]")
+            body.append("v[k] ~ dlogis(0.0, 2.0)")
+        stmt = obs_stmt.format(ix="i").replace("n[i]", "n.tr[i]")
+        lines = ["model {", "  for (i in 1:n) {", "    " + stmt, f"    {LINK_LHS[link].format(ix='i')} <- " + " + ".join(terms), "  }",
+                 "  for (k in 1:G) {"] + ["    " + b for b in body] + ["  }"]
+        desc = f"gathered {name}/{link} n={n} G={G}"
+    else:
+        # --- siblings: K statements of one loop sharing u[i], each with its own covariate and offset
+        N, K = int(rng.integers(2, 25)), int(rng.integers(2, 4))
+        data = {"N": N}
+        lines = ["model {", "  for (i in 1:N) {"]
+        for k in range(K):
+            data[f"y{k}"] = ygen(rng, (N,))
+            data[f"x{k}"] = rng.standard_normal(N)
+            if name == "binomial":
+                data[f"n{k}"] = data[f"y{k}"] + rng.integers(0, 5, N).astype(float)
+            stmt = obs_stmt.format(ix="i").replace("y[i]", f"y{k}[i]").replace("mu[i]", f"mu{k}[i]").replace("n[i]", f"n{k}[i]")
+            lhs = LINK_LHS[link].format(ix="i").replace("mu[i]", f"mu{k}[i]")
+            lines += ["    " + stmt, f"    {lhs} <- b0 + b1 * x{k}[i] + u[i]" + (f" - {0.1 * k}" if k else "")]
+        lines += ["    u[i] ~ dnorm(0.0, t.u)", "  }"]
+        globals_.append(("t.u", POS_PRIORS[int(rng.integers(0, len(POS_PRIORS)))]))
+        desc = f"siblings {name}/{link} N={N} K={K}"
+    lines += [f"  {g} ~ {p}" for g, p in globals_] + ["}"]
+    return "\n".join(lines), data, desc

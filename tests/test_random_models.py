@@ -9,7 +9,7 @@ import jbugs
 from c_oracle import COracle
 from conftest import rel_err
 from helpers import random_thetas
-from random_models import make
+from random_models import make, make_structured
 
 SEEDS = list(range(96))
 
@@ -52,4 +52,32 @@ def test_random_model_cuda_many_groups(seed):
     text, data, desc = make(seed, n_max=700)
     m = jbugs.compile(text, data)
     theta = random_thetas(np.zeros(m.plan.D), 300, seed=seed, scale=0.2)
+    _check(m.cuda, COracle(m.plan), theta)
+
+
+@pytest.mark.parametrize("seed", list(range(40)))
+def test_structured_random_model_plan_matches_node_loop(seed):
+    """data-indexed random effects (regrouped, padded, weighted plate) and sibling observation statements (merged plate)."""
+    text, data, desc = make_structured(seed)
+    gm = go.compile(text, data).use_generated_order()
+    plan, lw = jbugs.lower(text, data)
+    assert len(plan.plates) == 1 and plan.D == gm.D and lw.param_names() == gm.param_names(), desc
+    theta = random_thetas(np.zeros(plan.D), 3, seed=seed, scale=0.3)
+    lp, g, st = COracle(plan).eval_batch(theta)
+    for c in range(3):
+        lp_g, g_g = gm.logdensity_and_gradient(theta[:, c])
+        if not np.isfinite(lp_g):
+            assert lp[c] == lp_g, desc
+            continue
+        assert st[c] == 0 and abs(lp[c] - lp_g) <= 1e-11 * max(1.0, abs(lp_g)), (desc, text)
+        assert rel_err(g[:, c], g_g) < 1e-8, (desc, text)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", list(range(40)))
+def test_structured_random_model_cuda_matches_c_oracle(seed):
+    from test_gpu_parity import _check
+    text, data, desc = make_structured(seed)
+    m = jbugs.compile(text, data)
+    theta = random_thetas(np.zeros(m.plan.D), 37, seed=seed, scale=0.3)
     _check(m.cuda, COracle(m.plan), theta)
