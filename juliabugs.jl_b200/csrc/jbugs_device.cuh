@@ -79,7 +79,8 @@ struct FamOut {
     double lp, dx, da0, da1;
 };
 
-__device__ __forceinline__ bool fam_eval(int fam, double x, double a0, double a1, FamOut& o) {
+// a2: third argument of the three-argument families (dt's degrees of freedom), a constant: it has no adjoint
+__device__ __forceinline__ bool fam_eval(int fam, double x, double a0, double a1, FamOut& o, double a2 = 0.0) {
     o.dx = 0.0; o.da0 = 0.0; o.da1 = 0.0; o.lp = 0.0;
     switch (fam) {
     case JBUGS_FAM_NORMAL: {
@@ -187,6 +188,14 @@ __device__ __forceinline__ bool fam_eval(int fam, double x, double a0, double a1
         o.dx = (h - 1.0) / x - 0.5;
         o.da0 = 0.5 * (-digamma(h) - 0.69314718055994530942 + log(x));
         return !(a0 > 0.0);
+    }
+    case JBUGS_FAM_T: {  // TDistShiftedScaled(nu = a2, mu = a0, sigma = 1/sqrt(tau)): tdistlogpdf(nu, z) - log(sigma)
+        const double nu = a2, rt = sqrt(a1), z = (x - a0) * rt, w = z * z / nu;
+        o.lp = lgamma(0.5 * (nu + 1.0)) - 0.5 * log(nu * 3.14159265358979323846) - lgamma(0.5 * nu) - 0.5 * (nu + 1.0) * log1p(w) + 0.5 * log(a1);
+        const double s = (nu + 1.0) * z / (nu + z * z);  // -d/dz of the log-density
+        o.dx = -s * rt; o.da0 = s * rt;
+        o.da1 = (0.5 / a1) * (1.0 - s * z);
+        return a1 < 0.0 || !(nu > 0.0) || !(rt > 0.0);
     }
     default: return false;  // FLAT
     }

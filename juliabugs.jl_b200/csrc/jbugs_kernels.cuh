@@ -418,7 +418,7 @@ finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
             continue;
         }
         FamOut o;
-        bad |= fam_eval((int)g.family, gv[h], garg(g.args[0], gv), garg(g.args[1], gv), o);
+        bad |= fam_eval((int)g.family, gv[h], garg(g.args[0], gv), garg(g.args[1], gv), o, garg(g.args[2], gv));
         lp += o.lp;
         ga[h] += o.dx;
         if (g.args[0].kind == JBUGS_ARG_GVAL) ga[g.args[0].id] += o.da0;

@@ -154,7 +154,7 @@ __device__ __forceinline__ bool local_prior(const S& sp, const PlateVals& V, int
         return !(a0 > 0.0) || !(a1 > 0.0);
     }
     FamOut o;
-    const bool bad = fam_eval(sp.loc_family(l), st.lx[l], a0, a1, o);
+    const bool bad = fam_eval(sp.loc_family(l), st.lx[l], a0, a1, o, L.args[2].value);
     lp += o.lp;
     st.la[l] += o.dx;
     arg_adjoint(sp.loc_arg(l, 0), st, o.da0);
@@ -259,7 +259,7 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
         const double a0 = ea == 0 ? v : arg_value(sp.aux(0), V.aux[0], st, sv, g, j);
         const double a1 = ea == 1 ? v : arg_value(sp.aux(1), V.aux[1], st, sv, g, j);
         FamOut o;
-        bad |= fam_eval(sp.family(), yv, a0, a1, o);
+        bad |= fam_eval(sp.family(), yv, a0, a1, o, V.aux[2].value);
         lp += o.lp;
         deta = (ea == 0 ? o.da0 : o.da1) * dv;
         if (ea != 0) arg_adjoint(sp.aux(0), st, o.da0);

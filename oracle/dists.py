@@ -288,6 +288,23 @@ class Chisq(Dist):
         return -M.lgamma(h) - h * math.log(2.0) + _xlogy(M, h - 1, x) - x / 2.0
 
 
+class TDistShiftedScaled(Dist):
+    def __init__(self, M, mu, tau, nu):
+        # distributions.jl:73-80: dt(mu, tau, nu) = TDistShiftedScaled(nu, mu, sqrt(1/tau)) (TDist(nu) when mu = 0, sigma = 1:
+        # the same density); logpdf = tdistlogpdf(nu, (x - mu) / sigma) - log(sigma)   (:58-60)
+        _check(not (_val(tau) < 0), "dt requires tau > 0")
+        self.mu, self.nu = mu, nu
+        self.sigma = M.sqrt(1.0 / tau)
+        _check(_val(nu) > 0 and _val(self.sigma) > 0, "dt requires nu > 0 and sigma > 0")
+
+    def logpdf(self, M, x):
+        # StatsFuns.tdistlogpdf: loggamma((nu+1)/2) - log(nu pi)/2 - loggamma(nu/2) - (nu+1)/2 log1p(z^2/nu)
+        z = (x - self.mu) / self.sigma
+        nu = self.nu
+        return (M.lgamma((nu + 1.0) / 2.0) - M.log(nu * math.pi) / 2.0 - M.lgamma(nu / 2.0)
+                - (nu + 1.0) / 2.0 * M.log1p(z * z / nu) - M.log(self.sigma))
+
+
 class Flat(Dist):
     def logpdf(self, M, x):
         return 0.0 * x
@@ -325,6 +342,8 @@ def make_dist(M, name, args):
         return NegativeBinomial(M, *args)
     if name == "dchisqr":
         return Chisq(M, *args)
+    if name == "dt":
+        return TDistShiftedScaled(M, *args)
     if name == "dflat":
         return Flat()
     raise NotImplementedError(f"distribution {name} is outside the restated subset")

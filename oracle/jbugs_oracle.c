@@ -250,6 +250,21 @@ static int fam_logpdf(uint32_t fam, double x, const double* a, double* lp, doubl
         da[0] = 0.5 * (-digamma(h) - M_LN2 + log(x));
         return 0;
     }
+    case JBUGS_FAM_T: { /* :73-80 -> TDistShiftedScaled(nu, mu, 1/sqrt(tau)): StatsFuns.tdistlogpdf(nu, z) - log(sigma) */
+        double mu = a[0], tau = a[1], nu = a[2];
+        if (tau < 0.0) return 1;
+        double sigma = sqrt(1.0 / tau);
+        if (!(nu > 0.0) || !(sigma > 0.0)) return 1;
+        double z = (x - mu) / sigma;
+        *lp = lgamma((nu + 1.0) / 2.0) - log(nu * M_PI) / 2.0 - lgamma(nu / 2.0) - (nu + 1.0) / 2.0 * log1p(z * z / nu) - log(sigma);
+        double s = (nu + 1.0) * z / (nu + z * z);
+        *dx = -s / sigma;
+        da[0] = s / sigma;
+        da[1] = (0.5 / tau) * (1.0 - s * z);
+        da[2] = 0.5 * digamma((nu + 1.0) / 2.0) - 0.5 / nu - 0.5 * digamma(nu / 2.0) - 0.5 * log1p(z * z / nu)
+                + (nu + 1.0) / 2.0 * (z * z / (nu * nu)) / (1.0 + z * z / nu);
+        return 0;
+    }
     default: return 2;
     }
 }

@@ -14,6 +14,8 @@ OBS = [
      lambda rng, shp: rng.logistic(0.3, 1.0, shp)),
     ("laplace", "y[{ix}] ~ ddexp(mu[{ix}], tau.y)", ["identity"], [("tau.y", "dexp(1.0)")],
      lambda rng, shp: rng.laplace(0.3, 1.0, shp)),
+    ("student", "y[{ix}] ~ dt(mu[{ix}], tau.y, 4)", ["identity"], [("tau.y", "dgamma(2, 2)")],
+     lambda rng, shp: rng.standard_t(4, shp)),
     ("lognormal", "y[{ix}] ~ dlnorm(mu[{ix}], tau.y)", ["identity"], [("tau.y", "dgamma(2, 2)")],
      lambda rng, shp: rng.lognormal(0.1, 0.7, shp)),
     ("bernoulli", "y[{ix}] ~ dbern(mu[{ix}])", ["logit", "probit", "cloglog"], [],
@@ -128,7 +130,7 @@ def make_structured(seed):
     name, obs_stmt, links, aux, ygen = OBS[int(rng.integers(0, len(OBS)))]
     link = links[int(rng.integers(0, len(links)))]
     globals_ = [("b0", GLOBAL_PRIORS[int(rng.integers(0, len(GLOBAL_PRIORS)))]), ("b1", "dnorm(0.0, 1.0)")] + list(aux)
-    if rng.integers(0, 2):
+    if rng.integers(0, 2) and name != "student":   # (dt's third argument and the padding weight share a slot)
         # --- gathered: y[i] ~ f(b0 + b1 x[i] + u[g[i]] (+ v[g[i]] z[i]))
         n, G = int(rng.integers(8, 60)), int(rng.integers(2, 7))
         grp = np.concatenate([np.arange(1, G + 1), rng.integers(1, G + 1, n - G)]).astype(float)

@@ -43,6 +43,13 @@ MODELS = {
         v ~ dgamma(2, 2)
         a ~ dnorm(0, 0.1)
         b ~ dnorm(0, 0.1) }""", {"N": N, "x": x, "w": rng.weibull(1.5, N) + 0.05}),
+    "obs_t": ("""model {
+        for (i in 1:N) { y[i] ~ dt(mu[i], tau, 4)
+                         mu[i] <- a + b * x[i] + u[i]
+                         u[i] ~ dt(0, 2.0, 7) }
+        tau ~ dgamma(2, 2)
+        a ~ dt(0.5, 0.25, 3)
+        b ~ dnorm(0, 0.1) }""", {"N": N, "x": x, "y": 0.5 + x + rng.standard_t(4, N)}),
     "obs_chisq": ("""model {
         for (i in 1:N) { z[i] ~ dchisqr(k) }
         k ~ dunif(1, 10) }""", {"N": N, "z": rng.chisquare(4, N)}),
@@ -121,6 +128,7 @@ def _scipy_cases():
         ("dbin(0.1, 10)", S.binom(10, 0.1), "discrete", 2.0),
         ("dpois(3.5)", S.poisson(3.5), "discrete", 4.0),
         ("dnegbin(0.4, 3)", S.nbinom(3, 0.4), "discrete", 5.0),
+        ("dt(1.5, 4.0, 5)", S.t(5, 1.5, 0.5), None, 0.7),
     ]
 
 
@@ -138,7 +146,7 @@ def _reference_logp(dist, support, x):
     return lp, lp + np.log(x - lb), np.log(x - lb)
 
 
-@pytest.mark.parametrize("k", range(15))
+@pytest.mark.parametrize("k", range(16))
 def test_single_node_models_against_scipy(k):
     call, dist, support, x = _scipy_cases()[k]
     text = "model { a ~ %s }" % call
@@ -155,7 +163,7 @@ def test_single_node_models_against_scipy(k):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k", range(15))
+@pytest.mark.parametrize("k", range(16))
 def test_single_node_models_against_scipy_cuda(k):
     call, dist, support, x = _scipy_cases()[k]
     text = "model { a ~ %s }" % call
