@@ -156,6 +156,11 @@ function logdensity_and_gradient_batch(m::CUDABatchModel, θ::AbstractMatrix)
     return logp, grad
 end
 
+# --- run-time specialisation: a kernel compiled for this model's plate shapes (nvcc, cached by shape); the reference
+# generates and compiles Julia code per model at the same point (set_evaluation_mode, bugsmodel.jl:736-801)
+specialize!(h::PlanHandle; cache_dir::Union{Nothing,String}=nothing) =
+    _check(ccall((:jbugs_plan_specialize, libjbugs), Cint, (Ptr{Cvoid}, Cstring), h.ptr, cache_dir === nothing ? C_NULL : cache_dir))
+
 # --- observation sharding (one process per GPU; the unique id travels over MPI / Distributed, not shown) -------------
 set_shard!(h::PlanHandle, plate::Integer, i0::Integer, i1::Integer) =
     _check(ccall((:jbugs_plan_set_shard, libjbugs), Cint, (Ptr{Cvoid}, Cint, Int64, Int64), h.ptr, plate, i0, i1))
