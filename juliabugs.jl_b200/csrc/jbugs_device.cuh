@@ -197,6 +197,12 @@ __device__ __forceinline__ bool fam_eval(int fam, double x, double a0, double a1
         o.da1 = (0.5 / a1) * (1.0 - s * z);
         return a1 < 0.0 || !(nu > 0.0) || !(rt > 0.0);
     }
+    case JBUGS_FAM_GEOMETRIC: {  // Geometric(p = a0): log(p) + xlog1py(x, -p)
+        const bool out = (x < 0.0 || x != floor(x));
+        o.lp = out ? -dev_inf() : (log(a0) + xlog1py(x, -a0));
+        o.da0 = 1.0 / a0 - (x == 0.0 ? 0.0 : x / (1.0 - a0));
+        return !(a0 > 0.0 && a0 <= 1.0);
+    }
     default: return false;  // FLAT
     }
 }

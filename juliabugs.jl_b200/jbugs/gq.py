@@ -91,6 +91,20 @@ def _sample(rng, fn, args, shape):
         return rng.binomial(a[1].astype(np.int64), a[0]).astype(np.float64)
     if fn == "dpois":
         return rng.poisson(a[0]).astype(np.float64)
+    if fn == "dlogis":
+        return rng.logistic(a[0], 1.0 / np.sqrt(a[1]))
+    if fn == "ddexp":
+        return rng.laplace(a[0], 1.0 / np.sqrt(a[1]))
+    if fn == "dweib":
+        return rng.weibull(a[0]) / a[1]
+    if fn == "dchisqr":
+        return rng.chisquare(a[0])
+    if fn == "dt":
+        return a[0] + rng.standard_t(a[2]) / np.sqrt(a[1])
+    if fn == "dnegbin":
+        return rng.negative_binomial(a[1], a[0]).astype(np.float64)
+    if fn == "dgeom":
+        return (rng.geometric(a[0]) - 1).astype(np.float64)   # failures before the first success
     raise LoweringError(f"forward sampling of {fn} is not provided")
 
 

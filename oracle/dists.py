@@ -272,6 +272,21 @@ class NegativeBinomial(Dist):
                 - _logbeta(M, self.r, k + 1))
 
 
+class Geometric(Dist):
+    discrete = True
+
+    def __init__(self, M, p):
+        # distributions.jl:500-502: dgeom(p) = Geometric(p), the number of failures before the first success
+        _check(0 < _val(p) <= 1, "Geometric requires 0 < p <= 1")
+        self.p = p
+
+    def logpdf(self, M, k):
+        if _val(k) < 0 or not M.isint(k):
+            return -M.inf
+        # Distributions: xlog1py(k, -p) + log(p)
+        return _xlog1py(M, k, -self.p) + M.log(self.p)
+
+
 class Chisq(Dist):
     def __init__(self, M, k):
         # distributions.jl:215-217: Chisq(k) = Gamma(k/2, 2)
@@ -340,6 +355,8 @@ def make_dist(M, name, args):
         return Weibull(M, *args)
     if name == "dnegbin":
         return NegativeBinomial(M, *args)
+    if name == "dgeom":
+        return Geometric(M, *args)
     if name == "dchisqr":
         return Chisq(M, *args)
     if name == "dt":

@@ -265,6 +265,14 @@ static int fam_logpdf(uint32_t fam, double x, const double* a, double* lp, doubl
                 + (nu + 1.0) / 2.0 * (z * z / (nu * nu)) / (1.0 + z * z / nu);
         return 0;
     }
+    case JBUGS_FAM_GEOMETRIC: { /* :500-502 -> Geometric(p): log(p) + xlog1py(x, -p), x = 0, 1, 2, ... */
+        double p = a[0];
+        if (!(p > 0.0 && p <= 1.0)) return 1;
+        if (x < 0.0 || x != floor(x)) { *lp = -INFINITY; return 0; }
+        *lp = log(p) + xlog1py(x, -p);
+        da[0] = 1.0 / p - (x == 0.0 ? 0.0 : x / (1.0 - p));
+        return 0;
+    }
     default: return 2;
     }
 }

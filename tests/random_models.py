@@ -26,6 +26,8 @@ OBS = [
      lambda rng, shp: rng.poisson(2.0, shp).astype(float)),
     ("negbin", "y[{ix}] ~ dnegbin(mu[{ix}], r.y)", ["logit"], [("r.y", "dgamma(3, 1)")],
      lambda rng, shp: rng.negative_binomial(3, 0.5, shp).astype(float)),
+    ("geometric", "y[{ix}] ~ dgeom(mu[{ix}])", ["logit", "probit", "cloglog"], [],
+     lambda rng, shp: (rng.geometric(0.4, shp) - 1).astype(float)),
     ("gamma", "y[{ix}] ~ dgamma(a.y, mu[{ix}])", ["log"], [("a.y", "dgamma(3, 1)")],
      lambda rng, shp: rng.gamma(2.0, 0.8, shp) + 0.01),
     ("weibull", "y[{ix}] ~ dweib(a.y, mu[{ix}])", ["log"], [("a.y", "dgamma(3, 2)")],

@@ -37,6 +37,13 @@ MODELS = {
         r ~ dgamma(2, 1)
         a ~ dnorm(0, 0.1)
         b ~ dnorm(0, 0.1) }""", {"N": N, "x": x, "k": rng.negative_binomial(3, 0.4, N).astype(float)}),
+    "obs_geom": ("""model {
+        for (i in 1:N) { k[i] ~ dgeom(p[i])
+                         logit(p[i]) <- a + b * x[i] + u[i]
+                         u[i] ~ dnorm(0, tau) }
+        tau ~ dgamma(2, 2)
+        a ~ dnorm(0, 0.1)
+        b ~ dnorm(0, 0.1) }""", {"N": N, "x": x, "k": (rng.geometric(0.4, N) - 1).astype(float)}),
     "obs_weibull": ("""model {
         for (i in 1:N) { w[i] ~ dweib(v, lam[i])
                          log(lam[i]) <- a + b * x[i] }
@@ -73,7 +80,7 @@ def test_plan_matches_node_loop(name):
 
 def test_new_families_against_mpmath():
     """50-digit evaluation of the same node loop: the float64 formulas carry no hidden cancellation."""
-    for name in ("priors", "obs_negbin", "obs_weibull"):
+    for name in ("priors", "obs_negbin", "obs_geom", "obs_weibull"):
         text, data = MODELS[name]
         gm = go.compile(text, data)
         th = 0.3 * np.ones(gm.D)
@@ -84,6 +91,8 @@ def test_new_families_against_mpmath():
     ("model { t ~ dnorm(1, 1)\n y ~ dlogis(0, t) }", {"y": 0.3}, -1.0),
     ("model { t ~ dnorm(1, 1)\n y ~ ddexp(0, t) }", {"y": 0.3}, -1.0),
     ("model { p ~ dnorm(0.5, 1)\n k ~ dnegbin(p, 3) }", {"k": 2}, 1.5),
+    ("model { p ~ dnorm(0.5, 1)\n k ~ dgeom(p) }", {"k": 2}, 1.5),
+    ("model { p ~ dnorm(0.5, 1)\n k ~ dgeom(p) }", {"k": 2}, 0.0),
     ("model { v ~ dnorm(1, 1)\n w ~ dweib(v, 1) }", {"w": 0.7}, -0.5),
     ("model { k ~ dnorm(1, 1)\n z ~ dchisqr(k) }", {"z": 0.7}, -0.5),
 ])
@@ -129,6 +138,7 @@ def _scipy_cases():
         ("dpois(3.5)", S.poisson(3.5), "discrete", 4.0),
         ("dnegbin(0.4, 3)", S.nbinom(3, 0.4), "discrete", 5.0),
         ("dt(1.5, 4.0, 5)", S.t(5, 1.5, 0.5), None, 0.7),
+        ("dgeom(0.3)", S.geom(0.3, loc=-1), "discrete", 4.0),
     ]
 
 
@@ -146,7 +156,7 @@ def _reference_logp(dist, support, x):
     return lp, lp + np.log(x - lb), np.log(x - lb)
 
 
-@pytest.mark.parametrize("k", range(16))
+@pytest.mark.parametrize("k", range(17))
 def test_single_node_models_against_scipy(k):
     call, dist, support, x = _scipy_cases()[k]
     text = "model { a ~ %s }" % call
@@ -163,7 +173,7 @@ def test_single_node_models_against_scipy(k):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k", range(16))
+@pytest.mark.parametrize("k", range(17))
 def test_single_node_models_against_scipy_cuda(k):
     call, dist, support, x = _scipy_cases()[k]
     text = "model { a ~ %s }" % call

@@ -136,3 +136,24 @@ def test_chain_diagnostics_on_known_processes():
     ch = Chains(["a"], iid[:, None, :], 0.8, 0.1)
     s = ch.summary()["a"]
     assert abs(s["mean"]) < 0.03 and abs(s["std"] - 1.0) < 0.03 and abs(s["rhat"] - 1.0) < 0.01
+
+
+@pytest.mark.parametrize("fn,args,dist", [
+    ("dlogis", (0.5, 4.0), lambda S: S.logistic(0.5, 0.5)),
+    ("ddexp", (0.5, 4.0), lambda S: S.laplace(0.5, 0.5)),
+    ("dweib", (1.7, 0.8), lambda S: S.weibull_min(1.7, scale=1.25)),
+    ("dchisqr", (5.0,), lambda S: S.chi2(5)),
+    ("dt", (1.5, 4.0, 7.0), lambda S: S.t(7, 1.5, 0.5)),
+    ("dnegbin", (0.4, 3.0), lambda S: S.nbinom(3, 0.4)),
+    ("dgeom", (0.3,), lambda S: S.geom(0.3, loc=-1)),
+])
+def test_forward_sampler_parameterisations(fn, args, dist):
+    """The BUGS -> numpy parameterisation of each forward sampler (precision -> scale, rate -> scale, dgeom counting
+    failures: J/src/BUGSPrimitives/distributions.jl) against the moments of the scipy distribution the density tests use."""
+    from scipy import stats
+    from jbugs.gq import _sample
+    d = dist(stats)
+    x = _sample(np.random.default_rng(7), fn, args, (400_000,))
+    assert x.shape == (400_000,)
+    assert x.mean() == pytest.approx(d.mean(), abs=6 * d.std() / np.sqrt(x.size))
+    assert x.std() == pytest.approx(d.std(), rel=2e-2)
