@@ -77,8 +77,7 @@ enum jbugs_family {
     JBUGS_FAM_CHISQ = 14,      /* dchisqr(k)       :215-217 Chisq(k)                  */
     JBUGS_FAM_T = 15,          /* dt(mu, tau, nu)  :73-80   TDistShiftedScaled(nu, mu, 1/sqrt(tau)); nu a constant */
     JBUGS_FAM_GEOMETRIC = 16,  /* dgeom(p)         :500-502 Geometric(p): failures before the first success */
-    JBUGS_FAM_BETABIN = 17,    /* dbetabin(a, b, n) :530-532 BetaBinomial(n, a, b); n a constant */
-    JBUGS_FAM_COUNT = 18
+    JBUGS_FAM_COUNT = 17
 };
 
 /* ---- constrained <-> unconstrained maps (Bijectors, call site evaluation.jl:243-257) ------- */

@@ -293,8 +293,8 @@ static int build_plate(jbugs_plan* p, int k) {
         // aux[2]: the constant third argument of a three-argument family (dt), or the optional 0/1 observation weight of
         // a gathered (padded) plate
         V.aux[2].value = pl.aux[2].kind == JBUGS_ARG_ONE ? 1.0 : pl.aux[2].value;
-        if ((pl.family == JBUGS_FAM_T || pl.family == JBUGS_FAM_BETABIN) && pl.aux[2].kind != JBUGS_ARG_CONST && pl.aux[2].kind != JBUGS_ARG_ONE)
-            return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: the third argument of dt / dbetabin must be a constant", k);
+        if (pl.family == JBUGS_FAM_T && pl.aux[2].kind != JBUGS_ARG_CONST && pl.aux[2].kind != JBUGS_ARG_ONE)
+            return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: the degrees of freedom of dt must be a constant", k);
         if (pl.aux[2].kind == JBUGS_ARG_DATA_I || pl.aux[2].kind == JBUGS_ARG_DATA_IJ) {
             if ((rc = resolve_arg(p, pl.aux[2], sh.aux[2], V.aux[2], gref, (int)pl.n_locals, sb))) return rc;
             if ((rc = check_len(p, pl.aux[2], pl.N, pl.T, "weight"))) return rc;
@@ -329,7 +329,7 @@ static int build_plate(jbugs_plan* p, int k) {
             if ((rc = check_len(p, L[l].args[q], pl.N, pl.T, "prior argument"))) return rc;
         }
         lv.args[2].value = L[l].args[2].kind == JBUGS_ARG_ONE ? 1.0 : L[l].args[2].value;  // dt's constant degrees of freedom
-        if ((L[l].family == JBUGS_FAM_T || L[l].family == JBUGS_FAM_BETABIN) && L[l].args[2].kind != JBUGS_ARG_CONST && L[l].args[2].kind != JBUGS_ARG_ONE)
+        if (L[l].family == JBUGS_FAM_T && L[l].args[2].kind != JBUGS_ARG_CONST && L[l].args[2].kind != JBUGS_ARG_ONE)
             return fail(JBUGS_ERR_UNSUPPORTED, "plate %d local %d: the degrees of freedom of dt must be a constant", k, l);
     }
     if ((int)gref.size() > MAX_GREF) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d references more than %d global values", k, MAX_GREF);
