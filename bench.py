@@ -1,23 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- logdensity+gradient obs-evals/s of the batched B200 evaluator (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload rats|seeds|epil|pumps]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload rats|seeds|dense|pumps|epil] [--no-secondary] ...
 
 A "step" is one batched `logdensity_and_gradient` (jbugs_eval_batch) over the whole synthetic data
 plate for every chain of the batch.  Default workload = BASELINE.json configs[1]: Rats scaled to
 10^6 rats x 5 timepoints, 4096 chains, fp64, one B200.  With N > 1 (torchrun) chains shard across
 GPUs with no data-path collective (weak scaling: 4096 chains per GPU).
 
-  value     obs-evals/s with theta/grad resident in HBM (CUDA events around exactly K steps)
-  e2e       same metric through the C ABI with pinned HOST buffers (H2D of theta, D2H of grad/logp
-            inside the timed region) on a bounded chain sample
-  roofline  algorithmic bytes (2*8*C*D) / measured plate-kernel time vs MEASURED_PEAKS.json hbm_gbs
+  value      obs-evals/s with theta/grad resident in HBM (CUDA events around exactly K steps)
+  e2e        same metric through the C ABI with pinned HOST buffers (H2D of theta, D2H of grad/logp
+             inside the timed region), every chain of the batch, in slabs; both host layouts
+  roofline   algorithmic bytes (2*8*C*D) / MEAN plate-kernel time over the K timed steps (the
+             library's own CUDA events, one set per step) vs MEASURED_PEAKS.json hbm_gbs
+  sustained  the same step repeated for >= 3 s right after the timed region (per-step p50 / p95)
+  secondary  the other BASELINE configurations (3: Seeds 10^7 obs, observation-sharded + NCCL
+             all-reduce when N > 1; 4: dense logistic 2^22 x 512 x 1024 on the FP64 tensor cores,
+             rows sharded when N > 1; 5: Pumps / Epil ensembles, 8192 chains per GPU), each with its
+             own roofline, measured in the same process after the primary workload
   cpu_baseline  the C restatement of the reference evaluator (oracle/) on the host cores, bounded sample
 
 `--impl reference` times that CPU restatement alone (Julia is not installed here or on the GPU box,
 so the reference itself cannot run; kind = "port").
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -29,9 +37,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "juliabugs.jl_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "logdensity+gradient obs-evals/s"
 UNIT = "obs-evals/s"
+DEFAULT_CHAINS = {"rats": 4096, "seeds": 256, "pumps": 8192, "epil": 8192, "dense": 1024}
 
 
 def log(*a):
@@ -39,10 +49,11 @@ def log(*a):
 
 
 # ----------------------------------------------------------------------------------- workloads
-def make_workload(name, groups):
-    """returns (model_text, data, theta0 (D,), description)"""
+def make_workload(name, groups, dev=None):
+    """returns (model_text, data, theta0 (D,), description, device_slots).  `device_slots` maps a data-slot name
+    prefix to a device tensor that is uploaded straight from HBM (the 17 GB design matrix of the dense workload is
+    generated on the GPU; its host entry is an untouched placeholder of the right shape)."""
     from jbugs import examples as ex
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import synth_rats, synth_seeds
     if name == "rats":
         N = groups or 1_000_000
@@ -52,25 +63,36 @@ def make_workload(name, groups):
         th0[:5] = [np.log(4.0), 6.2, np.log(1 / 196.0), 242.0, np.log(1 / 36.0)]  # beta.tau, beta.c, alpha.tau, alpha.c, tau.c
         th0[5::2] = beta
         th0[6::2] = alpha
-        return ex.RATS, data, th0, f"rats N={N} T=5"
+        return ex.RATS, data, th0, f"rats N={N} T=5", {}
     if name == "seeds":
         N = groups or 10_000_000
         data, b = synth_seeds(N)
         th0 = np.empty(N + 5)
         th0[:5] = [np.log(1 / 0.09), -0.84, 1.36, 0.09, -0.55]  # tau, alpha12, alpha2, alpha1, alpha0
         th0[5:] = b
-        return ex.SEEDS, data, th0, f"seeds N={N}"
+        return ex.SEEDS, data, th0, f"seeds N={N}", {}
     if name == "dense":
-        # BASELINE.json config 4: dense hierarchical logistic regression, X (N x P) fp64, beta over chains
+        # BASELINE.json config 4: dense hierarchical logistic regression, X (N x P) fp64 column-major, beta over chains
         import torch
         N, Pn = groups or (1 << 22), 512
-        gen = torch.Generator().manual_seed(1234)
-        X = torch.randn(Pn * N, dtype=torch.float64, generator=gen).numpy().reshape((Pn, N)).T  # F-contiguous N x P
         rng = np.random.default_rng(1234)
         bt = rng.normal(0.0, 0.1, Pn)
-        y = (rng.random(N) < 1.0 / (1.0 + np.exp(-(X @ bt)))).astype(np.float64)
         th0 = np.concatenate([[np.log(100.0), 0.0], bt])  # tau.b, mu.b, beta[1..P]
-        return ex.DENSE_LOGISTIC, {"N": N, "P": Pn, "X": X, "y": y}, th0, f"dense logistic N={N} P={Pn}"
+        desc = f"dense logistic N={N} P={Pn}"
+        if dev is None:  # CPU arm: host arrays
+            gen = torch.Generator().manual_seed(1234)
+            X = torch.randn(Pn * N, dtype=torch.float64, generator=gen).numpy().reshape((Pn, N)).T  # F-contiguous N x P
+            y = (rng.random(N) < 1.0 / (1.0 + np.exp(-(X @ bt)))).astype(np.float64)
+            return ex.DENSE_LOGISTIC, {"N": N, "P": Pn, "X": X, "y": y}, th0, desc, {}
+        gen = torch.Generator(device=dev).manual_seed(1234)
+        Xd = torch.empty((Pn, N), dtype=torch.float64, device=dev)  # [P][N] row-major == N x P column-major
+        for j0 in range(0, Pn, 64):
+            Xd[j0:j0 + 64] = torch.randn((min(64, Pn - j0), N), dtype=torch.float64, device=dev, generator=gen)
+        eta = torch.from_numpy(bt).to(dev) @ Xd
+        yd = (torch.rand(N, dtype=torch.float64, device=dev, generator=gen) < torch.sigmoid(eta)).to(torch.float64)
+        y = yd.cpu().numpy()
+        X = np.empty((Pn, N), dtype=np.float64).T  # placeholder (never touched): shape and layout only
+        return ex.DENSE_LOGISTIC, {"N": N, "P": Pn, "X": X, "y": y}, th0, desc, {"dense|X": Xd}
     if name in ("pumps", "epil"):
         # BASELINE.json config 5: the shipped fixtures, a large ensemble of independent chains (chain-sharded)
         fx = json.load(open(os.path.join(ROOT, "tests", "golden", "examples_vol1.json")))[name]
@@ -81,7 +103,7 @@ def make_workload(name, groups):
         th0 = jbugs.getparams(m)
         if name == "pumps":
             th0[2:] = np.log(np.maximum(data["x"], 0.5) / data["t"])  # theta_i near x_i / t_i
-        return (ex.PUMPS if name == "pumps" else ex.EPIL), data, th0, f"{name} (shipped fixture)"
+        return (ex.PUMPS if name == "pumps" else ex.EPIL), data, th0, f"{name} (shipped fixture)", {}
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -110,13 +132,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append((time.time(), line.strip()))
 
-    def stop(self, t0, t1):
+    def window(self, t0, t1):
+        """clocks / throttle reasons sampled between the wall-clock instants t0 and t1"""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
-        self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for t, line in self.samples:
+        for t, line in list(self.samples):
             if not (t0 - 0.05 <= t <= t1 + 0.15):
                 continue
             f = [x.strip() for x in line.split(",")]
@@ -130,21 +152,26 @@ class ClockSampler:
                     reasons.add(nm)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sample in the timed region"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(np.min(sm)), "sm_max_mhz": float(np.max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
 
 
 # ----------------------------------------------------------------------------------- CPU baseline (oracle port)
-def cpu_baseline(plan, th0, n_obs, budget_s=15.0, seed=7):
+def cpu_baseline(plan, th0, n_obs, budget_s=15.0, seed=7, cores=None):
     """the C restatement of the reference evaluator on the host cores, one chain per thread."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from c_oracle import COracle
     co = COracle(plan)
     # every host core this process may run on; not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        cores = os.cpu_count() or co.max_threads()
+    if cores is None:
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or co.max_threads()
     rng = np.random.default_rng(seed)
 
     def run(C):
@@ -161,43 +188,43 @@ def cpu_baseline(plan, th0, n_obs, budget_s=15.0, seed=7):
     else:
         C = cores
     return {"value": n_obs * C / t1, "unit": UNIT, "cores": cores, "kind": "port", "seconds": t1,
-            "sample": f"{C} chains x {n_obs} obs, one chain per thread, {t1:.2f} s"}
+            "sample": f"{C} chains x {n_obs} obs, one chain per thread, {t1:.2f} s",
+            "note": "C restatement of the reference's generated evaluator (oracle/jbugs_oracle.c, gcc -O2 "
+                    "-ffp-contract=off, analytic gradient) -- NOT JuliaBUGS + Mooncake itself (Julia is not installed)"}
 
 
-# ----------------------------------------------------------------------------------- main
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="rats")
-    ap.add_argument("--groups", type=int, default=0, help="plate size override (default: the BASELINE config)")
-    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default 4096 for rats, 256 for seeds)")
-    ap.add_argument("--e2e-chains", type=int, default=256)
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--dynamic", type=int, default=0, help="1 = force the interpreter kernel")
-    ap.add_argument("--tile", type=int, default=0)
-    ap.add_argument("--tma", type=int, default=-1, help="0 = stage plate data with cp.async only (A/B against the TMA path)")
-    ap.add_argument("--logdensity-only", action="store_true", help="time logdensity without the gradient (the reference benchmark's first column)")
-    ap.add_argument("--opt", default="", help="comma-separated key=value options passed to jbugs_plan_set_option (A/B runs)")
-    ap.add_argument("--shard", default="", choices=["", "chains", "obs"],
-                    help="N>1: 'chains' = every GPU its own chains (weak, no collective; default for rats); "
-                         "'obs' = the data plate is split by observation + NCCL all-reduce (strong; default for seeds)")
-    args = ap.parse_args()
-    shard = args.shard or ("obs" if args.workload == "seeds" else "chains")
+# ----------------------------------------------------------------------------------- one workload on the GPU(s)
+class Ctx:
+    pass
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    n_gpus = max(args.gpus, world)
-    W = max(args.warmup, 3)
-    K = max(args.steps, 1)
-    C = args.chains or {"rats": 4096, "seeds": 256, "pumps": 8192, "epil": 8192, "dense": 1024}.get(args.workload, 1024)
 
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def pinned(nbytes, write_combined=False):
+    """(torch tensor view, raw address) of library-allocated pinned host memory (cudaHostAlloc on the NUMA node this
+    process was bound to)."""
+    import torch
+    from jbugs import cuda
+    ptr = cuda.host_alloc(nbytes, write_combined=write_combined)
+    arr = np.ctypeslib.as_array((ctypes.c_double * (nbytes // 8)).from_address(ptr))
+    return torch.from_numpy(arr), ptr
+
+
+def measure(name, ctx, args, K, W, C, primary):
+    """build the workload, time exactly K steps (CUDA events on the launch stream, max over ranks), return the
+    fields of a bench line for it"""
+    import torch
     import jbugs
-    model_text, data, th0, desc = make_workload(args.workload, args.groups)
+    from jbugs import cuda as jcuda
+    dist = ctx.dist
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    shard = (args.shard if primary and args.shard else {"seeds": "obs", "dense": "obs"}.get(name, "chains"))
+    model_text, data, th0, desc, dev_slots = make_workload(name, args.groups if primary else 0, dev)
     t0 = time.time()
     model = jbugs.compile(model_text, data)
     plan = model.plan
@@ -205,60 +232,40 @@ def main():
     D = plan.D
     log(f"[bench] lowered {desc}: D={D} obs={n_obs} in {time.time() - t0:.1f}s")
     obs_sharded = shard == "obs" and world > 1
-    par = (f"data plate sharded by observation x{n_gpus} + ncclAllReduce of C x (1+G) doubles" if shard == "obs"
-           else f"chains sharded x{n_gpus}, no collective")
-    config = {"workload": f"{desc} x {C} chains{'' if shard == 'obs' else '/GPU'}, fp64, theta+grad resident in HBM (chain-fast layout)",
-              "chains_per_gpu": C, "D": D, "n_obs": n_obs, "parallelism": par,
-              "l2": "inputs (theta+grad = %.1f GB/GPU) exceed the 126 MB L2; no flush needed"
-                    % (2 * 8 * C * D / 1e9 / (world if obs_sharded else 1))}
-    scaling = "strong" if shard == "obs" else "weak"
-
-    # ---------------- reference arm: CPU restatement only (rank 0)
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        vals = []
-        for _ in range(W):
-            cpu_baseline(plan, th0, n_obs, budget_s=2.0)
-        for _ in range(K):
-            vals.append(cpu_baseline(plan, th0, n_obs, budget_s=max(5.0, 60.0 / K)))
-        v = float(np.mean([x["value"] for x in vals]))
-        cb = dict(vals[-1], value=v)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": n_gpus,
-                          "steps": K, "warmup": W, "ms_per_step": float(np.mean([x["seconds"] for x in vals])) * 1e3,
-                          "higher_is_better": True, "scaling": scaling,
-                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                          "cpu_baseline": cb,
-                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "note": "Julia is not installed: the reference arm is the C restatement of the reference's "
-                                  "generated evaluator (oracle/jbugs_oracle.c), OpenMP one chain per thread"}))
-        return
-
-    # ---------------- our arm
-    import torch
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    model = jbugs.set_evaluation_mode(model, jbugs.UseCUDABatch(device=local_rank))
-    cp = model.cuda
-    if args.dynamic:
-        cp.set_option("dynamic", 1)
-    if args.tile:
-        cp.set_option("tile", args.tile)
-    if args.tma >= 0:
-        cp.set_option("tma", args.tma)
-    for kv in filter(None, args.opt.split(",")):
-        k, v = kv.split("=")
-        cp.set_option(k, int(v))
+    model = jbugs.set_evaluation_mode(model, jbugs.UseCUDABatch(device=ctx.local_rank))
+    cp = jcuda.CudaPlan(plan, device=ctx.local_rank, upload=False)
+    model._cuda = cp
+    for k, slot in enumerate(plan.data):
+        src = next((t for pre, t in dev_slots.items() if slot.name.startswith(pre)), None)
+        if src is None:
+            cp.upload(k, slot.values)
+        else:  # device-resident source: device-to-device copy inside the library
+            jcuda._check(cp.L.jbugs_plan_upload_data(cp.h, k, src.data_ptr(), src.numel() * 8, 0))
+    dev_slots.clear()
+    del data
+    if primary:
+        if args.dynamic:
+            cp.set_option("dynamic", 1)
+        if args.tile:
+            cp.set_option("tile", args.tile)
+        if args.tma >= 0:
+            cp.set_option("tma", args.tma)
+        for kv in filter(None, args.opt.split(",")):
+            k, v = kv.split("=")
+            cp.set_option(k, int(v))
     local_groups = [pl.N for pl in plan.plates]
+    dense_rows = plan.dense[0].N if plan.dense else 0
     if obs_sharded:
         from jbugs.dist import shard_bounds, shard_observations
         shard_observations(model, rank, world)
-        local_groups = [b - a for a, b in (shard_bounds(pl.N, world, rank) for pl in plan.plates)]
+        local_groups = [(b - a) if pl.has_obs else pl.N
+                        for (a, b), pl in ((shard_bounds(pl.N, world, rank), pl) for pl in plan.plates)]
+        if plan.dense:
+            a, b = shard_bounds(plan.dense[0].N, world, rank)
+            dense_rows = b - a
+    par = ((f"data plate sharded by observation x{world} + one ncclAllReduce of C x (2+G"
+            f"{'+P' if plan.dense else ''}) doubles per evaluation") if shard == "obs"
+           else f"chains sharded x{world}, no collective")
     # theta rows this rank really reads / writes: the globals + the locals of its groups
     D_local = len(plan.globals) + sum(
         ng * sum(pl.T if l.level == 1 else 1 for l in pl.locals) for ng, pl in zip(local_groups, plan.plates))
@@ -276,11 +283,12 @@ def main():
         theta[r0:r1] = th0_d[r0:r1, None] + 0.05 * torch.randn((r1 - r0, ld), dtype=torch.float64, device=dev, generator=g)
     grad.zero_()
     torch.cuda.synchronize()
-    # a real (non-default) stream: the kernels are launched on it and the events of the timed region recorded on it
-    side = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(side)
-    stream = side.cuda_stream
-    want_grad = not args.logdensity_only
+    stream = ctx.stream.cuda_stream
+    want_grad = not (primary and args.logdensity_only)
+    work_gb = 2 * 8 * C * D_local / 1e9
+    config = {"workload": f"{desc} x {C} chains{'' if shard == 'obs' else '/GPU'}, fp64, theta+grad resident in HBM (chain-fast layout)",
+              "chains_per_gpu": C, "D": D, "n_obs": n_obs, "parallelism": par,
+              "l2": "inputs (theta+grad = %.1f GB/GPU) exceed the 126 MB L2; no flush needed" % work_gb}
     if not want_grad:
         config["evaluation"] = "logdensity only (no gradient): theta is read, nothing but logp is written"
 
@@ -294,90 +302,131 @@ def main():
     launches0 = cp.launch_count()
     step(0)
     launches_per_step = cp.launch_count() - launches0
-    plate_ms = []
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
+    small = 2 * 8 * C * D_local < (1 << 28)  # working set could sit in the 126 MB L2: flush between timed steps
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    small = 2 * 8 * C * D_local < (1 << 28)  # working set could sit in the 126 MB L2: flush between timed steps
     tw0 = time.time()
+    Ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     if small:
+        # event pair per step, a 256 MB write (> L2) between steps and outside the pair.  The library's own phase events
+        # are NOT recorded here: four event records are a visible share of a 30 us step (timed separately below)
         flush = torch.empty(1 << 28, dtype=torch.uint8, device=dev)
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        evs = [(Ev(), Ev()) for _ in range(K)]
         for a, b in evs:
-            flush.zero_()  # 256 MB write > L2, outside the timed event pair
+            flush.zero_()
             a.record()
             step(1)
             b.record()
         torch.cuda.synchronize()
-        ms_total = float(sum(a.elapsed_time(b) for a, b in evs))
+        step_ms = [a.elapsed_time(b) for a, b in evs]
+        ms_total = float(sum(step_ms))
+        del flush
         config["l2"] = "working set fits in L2: a 256 MB buffer is rewritten before every timed step (outside the event pair)"
+        cp.set_option("timing", 2)
+        for _ in range(min(K, 20)):
+            step(0)
+        plate_ms, total_ms = cp.timing_history()
+        cp.set_option("timing", 0)
     else:
-        # the library's own events around the plate kernel are recorded inside the timed region (four event records
-        # per call: nothing against a 20 ms step); the last step's are read after the region
-        cp.set_option("timing", 1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(K):
+        # one boundary event per step (K + 1 events) -> per-step times; the library records its own four events per step
+        # into a ring ("timing" = 2), so the plate-kernel time of EVERY timed step is known (mean and max reported)
+        cp.set_option("timing", 2)
+        evs = [Ev() for _ in range(K + 1)]
+        evs[0].record()
+        for k in range(K):
             step(1)
-        e1.record()
+            evs[k + 1].record()
         torch.cuda.synchronize()
-        ms_total = e0.elapsed_time(e1)
-        plate_ms.append(cp.last_timing()[0])
+        ms_total = evs[0].elapsed_time(evs[K])
+        step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(K)]
+        plate_ms, total_ms = cp.timing_history()
+        plate_ms, total_ms = plate_ms[-K:], total_ms[-K:]
         cp.set_option("timing", 0)
     if world > 1:
         dist.barrier()
     tw1 = time.time()
-    # per-kernel time of the dominant (plate) kernel: the library's own CUDA events on the launch stream
-    if not plate_ms:  # small workloads: timed separately, the event records would be a visible share of a 30 us step
-        cp.set_option("timing", 1)
-        for _ in range(min(K, 5)):
-            step(0)
-            plate_ms.append(cp.last_timing()[0])
-        cp.set_option("timing", 0)
-    clocks = sampler.stop(tw0, tw1)
+    clocks = ctx.sampler.window(tw0, tw1)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_per_step = ms_total / K
-    value = n_obs * C * (1 if obs_sharded else world) / (ms_per_step * 1e-3)
+    value = n_obs * C * (1 if shard == "obs" else world) / (ms_per_step * 1e-3)
     lp_host = logp[:C].cpu().numpy()
     st_host = status[:C].cpu().numpy()
     if not (np.all(np.isfinite(lp_host)) and np.all(st_host == 0)):
-        raise SystemExit("bench produced non-finite log densities: invalid run")
+        raise SystemExit(f"bench ({name}) produced non-finite log densities: invalid run")
 
-    # roofline of the plate kernel
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, which = 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
+    # ---- sustained region (primary workload): the same step for >= 3 s, per-step boundary events
+    sustained = None
+    if primary and args.sustain_s > 0 and not small:
+        n_s = int(min(1000, max(K, np.ceil(args.sustain_s * 1e3 / ms_per_step))))
+        cp.set_option("timing", 2)
+        evs = [Ev() for _ in range(n_s + 1)]
+        ts0 = time.time()
+        evs[0].record()
+        for k in range(n_s):
+            step(1)
+            evs[k + 1].record()
+        torch.cuda.synchronize()
+        ts1 = time.time()
+        sm = np.array([evs[k].elapsed_time(evs[k + 1]) for k in range(n_s)])
+        pk, _ = cp.timing_history()
+        pk = pk[-n_s:]
+        cp.set_option("timing", 0)
+        sustained = {"steps": n_s, "seconds": float(sm.sum() * 1e-3), "ms_per_step_mean": float(sm.mean()),
+                     "ms_per_step_p50": float(np.percentile(sm, 50)), "ms_per_step_p95": float(np.percentile(sm, 95)),
+                     "kernel_ms_mean": float(pk.mean()), "kernel_ms_max": float(pk.max()),
+                     "value": n_obs * C * (1 if shard == "obs" else world) / (float(sm.mean()) * 1e-3),
+                     "clocks": ctx.sampler.window(ts0, ts1)}
+
+    # ---- roofline of the dominant kernel: mean over the K timed steps of the library's per-step events
+    peak, which = hbm_peak()
     alg_bytes = (2.0 if want_grad else 1.0) * 8.0 * C * D_local
     pk_ms = float(np.mean(plate_ms))
     achieved = alg_bytes / (pk_ms * 1e-3) / 1e9
     traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath) and not args.groups:
+    if os.path.exists(tpath) and not (primary and args.groups):
         try:
-            t = json.load(open(tpath)).get(args.workload)
+            t = json.load(open(tpath)).get(name)
             # the ncu --set full capture replays the kernel ~40x and must save/restore what it writes, so it was
             # taken at fewer chains than fit beside a 131 GB working set; DRAM bytes are linear in the chain count
-            traffic = t["dram_bytes_per_launch"] * C / t["chains"]
+            traffic = t["dram_bytes_per_launch"] * C / t["chains"] * (D_local / D)
             traffic_note = f"dram__bytes_read+write from {t['source']} (captured at {t['chains']} chains, scaled to {C})"
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_note": traffic_note, "kernel": "plate_kernel", "kernel_ms": pk_ms,
-                "algorithmic_bytes": alg_bytes, "peak_source": which}
-
+                "traffic": traffic, "traffic_note": traffic_note, "kernel": "plate_kernel",
+                "kernel_ms": pk_ms, "kernel_ms_max": float(np.max(plate_ms)), "kernel_ms_samples": int(len(plate_ms)),
+                "eval_ms": float(np.mean(total_ms)), "algorithmic_bytes": alg_bytes, "peak_source": which}
+    fpath = os.path.join(ROOT, "profiles", "fp64_counts.json")
+    if name in ("seeds",) and os.path.exists(fpath):
+        # the logit plate kernel is FP64-pipe bound, not HBM bound: report both.  FP64 instructions per
+        # observation-evaluation are counted in the SASS of the timed kernel (scripts/count_fp64_sass.py)
+        try:
+            fc = json.load(open(fpath))[name]
+            fpeak = jcuda.fp64_peak(ctx.local_rank)  # DFMA / s, measured now
+            n_local_obs = sum(ng * pl.T for ng, pl in zip(local_groups, plan.plates) if pl.has_obs)
+            instr = fc["fp64_per_obs"] * n_local_obs * C
+            ach = instr / (pk_ms * 1e-3)
+            roofline = {"bound": "fp64", "achieved": ach / 1e12, "peak": fpeak / 1e12, "unit": "T FP64-instr/s",
+                        "frac": ach / fpeak, "traffic": traffic, "traffic_note": traffic_note, "kernel": "plate_kernel",
+                        "kernel_ms": pk_ms, "kernel_ms_max": float(np.max(plate_ms)), "kernel_ms_samples": int(len(plate_ms)),
+                        "eval_ms": float(np.mean(total_ms)),
+                        "fp64_instr_per_obs_eval": fc["fp64_per_obs"], "fp64_count_source": fc.get("source"),
+                        "peak_source": "independent DFMA chains measured in this run (jbugs_fp64_peak): one FP64 "
+                                       "instruction per lane-slot, so a DADD/DMUL costs the same slot as a DFMA",
+                        "hbm": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                "algorithmic_bytes": alg_bytes, "peak_source": which}}
+        except Exception as e:  # noqa: BLE001
+            roofline["fp64_note"] = f"fp64 bound not reported: {e}"
     if plan.dense:
         # dense linear predictor: the two X products dominate -> FP64 tensor pipe.  Denominator: cuBLAS DGEMM measured
-        # here, in the same process (MEASURED_PEAKS.json has no FP64 entry).
+        # here, in the same process (MEASURED_PEAKS.json has no FP64 entry).  Rows of X local to this rank.
         dn = plan.dense[0]
-        flops = 4.0 * dn.N * dn.P * C
+        flops = 4.0 * dense_rows * dn.P * C
         n = 8192
         a = torch.randn((n, n), dtype=torch.float64, device=dev)
         b = torch.randn((n, n), dtype=torch.float64, device=dev)
@@ -386,7 +435,7 @@ def main():
         torch.cuda.synchronize()
         best = 1e9
         for _ in range(3):
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0, s1 = Ev(), Ev()
             s0.record()
             torch.matmul(a, b)
             s1.record()
@@ -397,56 +446,225 @@ def main():
         ach = flops / (pk_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": ach / dgemm_tf,
                     "traffic": None, "kernel": "dense_fwd_kernel + dense_bwd_kernel (DMMA m8n8k4 f64)", "kernel_ms": pk_ms,
-                    "algorithmic_flops": flops, "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul f64) measured in this run, best of 3"}
+                    "kernel_ms_max": float(np.max(plate_ms)), "kernel_ms_samples": int(len(plate_ms)),
+                    "eval_ms": float(np.mean(total_ms)), "algorithmic_flops": flops, "local_rows": dense_rows,
+                    "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul f64) measured in this run, best of 3"}
 
-    out = {"metric": METRIC if want_grad else "logdensity obs-evals/s", "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
-           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+    out = {"metric": METRIC if want_grad else "logdensity obs-evals/s", "value": value, "unit": UNIT, "n_gpus": ctx.n_gpus,
+           "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+           "ms_per_step_p50": float(np.percentile(step_ms, 50)), "ms_per_step_p95": float(np.percentile(step_ms, 95)),
+           "higher_is_better": True, "scaling": "strong" if shard == "obs" else "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "roofline": roofline,
            "gpu_launches": launches_per_step * K}
+    if sustained:
+        out["sustained"] = sustained
 
-    # e2e: host pinned theta -> C ABI -> host grad, bounded chain sample
-    if rank == 0 or world > 1:
-        if not args.no_e2e and not obs_sharded:
-            Ce = min(args.e2e_chains, C)
-            th_h = torch.empty((D, Ce), dtype=torch.float64).pin_memory()
-            g_h = torch.empty((D, Ce), dtype=torch.float64).pin_memory()
-            lp_h = torch.empty(Ce, dtype=torch.float64).pin_memory()
-            st_h = torch.empty(Ce, dtype=torch.int32).pin_memory()
-            th_h.copy_(theta[:, :Ce])
-            torch.cuda.synchronize()
+    # ---- e2e: host pinned theta -> C ABI -> host grad; every chain of the batch, slab by slab, both host layouts
+    if primary and not args.no_e2e and not obs_sharded:
+        out["e2e"] = e2e(ctx, args, cp, theta, grad, lp_host, n_obs, D, C, K)
+    res = (out, plan, th0, n_obs)
+    del theta, grad
+    cp.close()
+    model._cuda = None
+    torch.cuda.empty_cache()
+    return res
 
-            def e2e_step():
-                cp.eval_raw(th_h.data_ptr(), Ce, Ce, 0, lp_h.data_ptr(), g_h.data_ptr(), st_h.data_ptr(), True, 0, stream)
 
-            for _ in range(2):
-                e2e_step()
-            reps = max(2, min(K, 5))
-            if world > 1:
-                dist.barrier()
-            t = time.perf_counter()
-            for _ in range(reps):
-                e2e_step()
-            torch.cuda.synchronize()
-            dt = (time.perf_counter() - t) / reps
-            if world > 1:
-                tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                dt = float(tt.item())
-            ok = bool(np.allclose(lp_h.numpy(), lp_host[:Ce], rtol=1e-12, atol=0))
-            out["e2e"] = {"value": n_obs * Ce * world / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * D * Ce,
-                          "d2h_bytes_per_step": 8 * D * Ce + 12 * Ce, "chains": Ce, "ms_per_step": dt * 1e3,
-                          "matches_resident": ok,
-                          "sample": f"{Ce} of {C} chains per GPU through jbugs_eval_batch with pinned host buffers"}
-            del th_h, g_h
+def e2e(ctx, args, cp, theta, grad, lp_host, n_obs, D, C, K):
+    """the metric through jbugs_eval_batch with HOST buffers: one step = every chain of the batch, in slabs of
+    `Ce` chains that are staged through ONE pair of pinned host buffers (pinning 2 x 65.5 GB for all 4096 chains at
+    once is not reasonable on a shared host; each slab's bytes cross PCIe in both directions inside the timed region)."""
+    import torch
+    from jbugs import cuda as jcuda
+    dist, world, dev = ctx.dist, ctx.world, ctx.dev
+    stream = ctx.stream.cuda_stream
+    Ce = min(args.e2e_chains or (1024 if world == 1 else 512), C)
+    while Ce > 64 and 2 * 8 * D * Ce > (40 << 30):
+        Ce //= 2
+    n_slabs = (C + Ce - 1) // Ce
+    res = {}
+    th_h, th_p = pinned(8 * D * Ce, write_combined=True)  # written by the host, read by the copy engine only
+    g_h, g_p = pinned(8 * D * Ce)
+    lp_h, lp_p = pinned(8 * Ce)
+    st_p = jcuda.host_alloc(4 * Ce)
+    th_h = th_h.view(D, Ce)
+    th_h.copy_(theta[:, :Ce])  # slab 0's values (the other slabs re-send the same bytes: the copies are what is timed)
+    torch.cuda.synchronize()
+    # free the resident batch: the staging slots of the host path get the device memory (chunks of 256 chains)
+    theta.untyped_storage().resize_(0)
+    grad.untyped_storage().resize_(0)
+    torch.cuda.empty_cache()
+    for lay_name, lay in (("chain_fast", 0), ("param_fast", 1)):
+        if lay == 1:
+            # a Julia Matrix{Float64}(D, Ce): one contiguous column per chain -- what eval_batch! of the Julia glue sends
+            tmp = th_h.clone()
+            th_h.view(Ce, D).copy_(tmp.t())
+            del tmp
+        ld = Ce if lay == 0 else D
+
+        def e2e_step():
+            for _ in range(n_slabs):
+                cp.eval_raw(th_p, ld, Ce, lay, lp_p, g_p, st_p, True, 0, stream)
+
+        e2e_step()
+        reps = max(2, min(K, 3))
+        if world > 1:
+            dist.barrier()
+        t = time.perf_counter()
+        for _ in range(reps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t) / reps
+        dt_local = dt
+        if world > 1:
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        ok = bool(np.allclose(lp_h.numpy()[:Ce], lp_host[:Ce], rtol=1e-12, atol=0))
+        h2d = 8 * D * Ce * n_slabs
+        d2h = (8 * D * Ce + 12 * Ce) * n_slabs
+        res[lay_name] = {"value": n_obs * Ce * n_slabs * world / dt, "ms_per_step": dt * 1e3, "matches_resident": ok,
+                         "h2d_gbs_this_rank": h2d / dt_local / 1e9, "d2h_gbs_this_rank": d2h / dt_local / 1e9}
+    best = max(res, key=lambda k: res[k]["value"])
+    out = {"value": res["chain_fast"]["value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "chains": Ce * n_slabs, "slab_chains": Ce, "slabs_per_step": n_slabs,
+           "ms_per_step": res["chain_fast"]["ms_per_step"], "layout": "chain_fast",
+           "matches_resident": res["chain_fast"]["matches_resident"] and res["param_fast"]["matches_resident"],
+           "h2d_gbs_per_rank": res["chain_fast"]["h2d_gbs_this_rank"], "d2h_gbs_per_rank": res["chain_fast"]["d2h_gbs_this_rank"],
+           "param_fast": res["param_fast"], "best_layout": best,
+           "numa": ctx.numa,
+           "sample": f"all {Ce * n_slabs} chains per GPU in {n_slabs} slabs of {Ce} through jbugs_eval_batch with pinned "
+                     "host buffers (theta write-combined), H2D and D2H inside the timed region; `value` is the "
+                     "chain_fast host layout, `param_fast` = a Julia Matrix(D, C) incl. the two on-device transposes"}
+    for p in (th_p, g_p, lp_p, st_p):
+        jcuda.host_free(p)
+    return out
+
+
+# ----------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (default: enough for a >= 3 s timed region)")
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rats")
+    ap.add_argument("--groups", type=int, default=0, help="plate size override (default: the BASELINE config)")
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default 4096 for rats, 256 for seeds)")
+    ap.add_argument("--e2e-chains", type=int, default=0, help="chains per host slab of the e2e measurement")
+    ap.add_argument("--sustain-s", type=float, default=3.0, help="length of the sustained region after the K timed steps")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configurations")
+    ap.add_argument("--secondary", default="seeds,dense,pumps,epil")
+    ap.add_argument("--dynamic", type=int, default=0, help="1 = force the interpreter kernel")
+    ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--tma", type=int, default=-1, help="0 = stage plate data with cp.async only (A/B against the TMA path)")
+    ap.add_argument("--logdensity-only", action="store_true", help="time logdensity without the gradient (the reference benchmark's first column)")
+    ap.add_argument("--opt", default="", help="comma-separated key=value options passed to jbugs_plan_set_option (A/B runs)")
+    ap.add_argument("--shard", default="", choices=["", "chains", "obs"],
+                    help="N>1: 'chains' = every GPU its own chains (weak, no collective; default for rats); "
+                         "'obs' = the data plate is split by observation + NCCL all-reduce (strong; default for seeds)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, world)
+    W = max(args.warmup, 3)
+    C = args.chains or DEFAULT_CHAINS.get(args.workload, 1024)
+    # default K: a timed region of >= 3 s at the step times measured on B200 (rats 21 ms, seeds 15 ms, dense 300 ms)
+    K = args.steps if args.steps > 0 else {"rats": 150, "seeds": 220, "dense": 12, "pumps": 200, "epil": 200}.get(args.workload, 100)
+
+    # ---------------- reference arm: CPU restatement only (rank 0)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import jbugs
+        model_text, data, th0, desc, _ = make_workload(args.workload, args.groups)
+        plan = jbugs.compile(model_text, data).plan
+        n_obs, D = plan.n_obs(), plan.D
+        shard = args.shard or ("obs" if args.workload in ("seeds", "dense") else "chains")
+        config = {"workload": f"{desc} x {C} chains{'' if shard == 'obs' else '/GPU'}, fp64, theta+grad resident in HBM (chain-fast layout)",
+                  "chains_per_gpu": C, "D": D, "n_obs": n_obs,
+                  "parallelism": "host cores, OpenMP, one chain per thread"}
+        vals = []
+        for _ in range(min(W, 3)):
+            cpu_baseline(plan, th0, n_obs, budget_s=2.0)
+        for _ in range(K):
+            vals.append(cpu_baseline(plan, th0, n_obs, budget_s=max(5.0, 60.0 / K)))
+        v = float(np.mean([x["value"] for x in vals]))
+        cb = dict(vals[-1], value=v)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": n_gpus,
+                          "steps": K, "warmup": W, "ms_per_step": float(np.mean([x["seconds"] for x in vals])) * 1e3,
+                          "higher_is_better": True, "scaling": "strong" if shard == "obs" else "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "note": "Julia is not installed: the reference arm is the C restatement of the reference's "
+                                  "generated evaluator (oracle/jbugs_oracle.c), OpenMP one chain per thread"}))
+        return
+
+    # ---------------- our arm
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
+    from jbugs import cuda as jcuda
+    try:
+        all_cores = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        all_cores = list(range(os.cpu_count() or 1))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = Ctx()
+    ctx.rank, ctx.world, ctx.local_rank, ctx.dev, ctx.n_gpus = rank, world, local_rank, dev, n_gpus
+    ctx.dist = None
+    # pinned staging of the host path must sit on the GPU's own NUMA node (8 ranks on one node share its memory system)
+    node, ncpu = jcuda.bind_host_to_device(local_rank)
+    ctx.numa = {"node": node, "cpus_bound": ncpu, "cpus_before": len(all_cores),
+                "how": "jbugs_bind_host_to_device: sched_setaffinity to the node's CPUs + set_mempolicy(MPOL_PREFERRED) "
+                       "before any pinned allocation" if node >= 0 else "platform reports no NUMA node for the GPU: not bound"}
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        ctx.dist = dist
+    ctx.sampler = ClockSampler(local_rank)
+    ctx.sampler.start()
+    # a real (non-default) stream: the kernels are launched on it and the events of the timed region recorded on it
+    ctx.stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(ctx.stream)
+    time.sleep(0.3)
+
+    out, plan, th0, n_obs = measure(args.workload, ctx, args, K, W, C, primary=True)
+
+    if not args.no_secondary and not args.groups and not args.chains:
+        sec = []
+        for nm in [s for s in args.secondary.split(",") if s and s != args.workload]:
+            Ks = {"seeds": 20, "dense": 3, "pumps": 50, "epil": 50}.get(nm, 10)
+            try:
+                o, _, _, _ = measure(nm, ctx, args, Ks, 3, DEFAULT_CHAINS[nm], primary=False)
+                sec.append({k: o[k] for k in ("value", "unit", "ms_per_step", "ms_per_step_p50", "ms_per_step_p95", "steps",
+                                              "warmup", "scaling", "config", "clocks", "roofline", "gpu_launches")})
+                sec[-1]["name"] = nm
+            except BaseException as e:  # noqa: BLE001 - a secondary workload must never void the primary line
+                sec.append({"name": nm, "failed": f"{type(e).__name__}: {e}"})
+                if world > 1:
+                    break  # the ranks may be out of step after a failure: stop here
+        out["secondary"] = sec
+    ctx.sampler.stop()
     if rank == 0 and not args.no_cpu and world == 1:
         try:
-            out["cpu_baseline"] = cpu_baseline(plan, th0, n_obs)
+            os.sched_setaffinity(0, all_cores)  # the CPU baseline gets every core, not just the GPU's node
+        except Exception:
+            pass
+        try:
+            out["cpu_baseline"] = cpu_baseline(plan, th0, n_obs, cores=len(all_cores))
         except Exception as e:  # the oracle is a checker; never let it break the bench line
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e}"}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

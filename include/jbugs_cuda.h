@@ -116,9 +116,17 @@ int jbugs_batch_alloc(jbugs_plan* plan, int64_t C, double** theta_dev, double** 
                       double** logp_dev, int32_t** status_dev, int64_t* ld);
 int jbugs_batch_free(jbugs_plan* plan);
 
-/* Pinned host memory for callers that stage from the host (bench e2e path). */
+/* Pinned host memory for callers that stage from the host (bench e2e path).  _ex: flags = JBUGS_HOST_WRITE_COMBINED
+ * for buffers the host only writes and the device only reads (theta): no cache snooping on the PCIe read path. */
+#define JBUGS_HOST_WRITE_COMBINED 1
 int jbugs_host_alloc(void** ptr, size_t nbytes);
+int jbugs_host_alloc_ex(void** ptr, size_t nbytes, int flags);
 int jbugs_host_free(void* ptr);
+
+/* Bind the calling process to the CPUs and (preferred) memory of the NUMA node of `device` (sysfs topology), so that
+ * pinned staging buffers allocated afterwards sit next to the GPU's PCIe root.  *node_out = -1 when the platform
+ * reports no node.  One process per GPU: call once, before allocating host buffers. */
+int jbugs_bind_host_to_device(int device, int* node_out, int* n_cpus_out);
 
 /* Multi-GPU (one process per GPU).  Replaces: AbstractMCMC MCMCThreads/MCMCDistributed chain
  * parallelism (docs/src/inference/parallel.md) -- which needs nothing here, chains shard with no
@@ -149,6 +157,14 @@ int jbugs_plan_set_option(jbugs_plan* plan, const char* key, int64_t value);
  * Recorded only after jbugs_plan_set_option(plan, "timing", 1); off by default because the four
  * event records are a measurable share of a small model's evaluation. */
 int jbugs_last_timing(const jbugs_plan* plan, float* plate_ms, float* total_ms);
+/* After jbugs_plan_set_option(plan, "timing", 2) every evaluation records into its own events (a ring of 1024):
+ * plate_ms[k] / total_ms[k] of the (up to `cap`) most recent evaluations since the option was set, oldest first.
+ * Waits for the last of them. */
+int jbugs_timing_history(const jbugs_plan* plan, float* plate_ms, float* total_ms, int cap, int* n_out);
+
+/* FP64-pipe peak of `device` in fused multiply-adds per second, measured with independent DFMA chains (the bound of the
+ * logit / log-link plate kernels; bench.py reports them against it). */
+int jbugs_fp64_peak(int device, double* fma_per_s);
 
 /* ---- on-device batched HMC (the caller of the hot path) ---------------------------------------
  * Replaces: the AdvancedHMC loop behind `AbstractMCMC.sample(model, HMC/NUTS, n)`
@@ -166,6 +182,9 @@ int jbugs_hmc_run(jbugs_hmc* hmc, int n_iter, int n_leapfrog, int adapt, const i
                   double* out_host, double* mean_accept);
 int jbugs_hmc_get_state(jbugs_hmc* hmc, double* theta_host /* [D][C] */, double* logp_host /* [C] */, double* step_size,
                         double* var_host /* [D] diagonal of the inverse metric */);
+/*   jbugs_hmc_draw_momentum : one momentum refresh p ~ N(0, M) exactly as a transition draws it (Philox counter =
+ *                    iteration `it`), copied to p_host[D][C]. */
+int jbugs_hmc_draw_momentum(jbugs_hmc* hmc, uint32_t it, double* p_host);
 /*   jbugs_hmc_run_nuts : same, with the No-U-Turn transition the reference uses (`NUTS(0.8)`): multinomial sampling
  *                    along the trajectory, generalised U-turn criterion, at most max_depth (<= 12) doublings.  All chains
  *                    build their trees in lock step; a chain that has finished waits for the deepest tree of the batch.

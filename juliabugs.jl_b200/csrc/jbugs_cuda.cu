@@ -2,8 +2,12 @@
 // C ABI declared in include/jbugs_cuda.h.  No torch types, no CPU fallback.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -152,9 +156,16 @@ struct jbugs_plan_s {
     // data-only constants): the HMC trajectory graph is rebuilt when it sees a new epoch
     unsigned long long epoch = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_last[4] = {nullptr, nullptr, nullptr, nullptr};  // the events the most recent evaluation recorded
     float last_plate_ms = 0.f, last_total_ms = 0.f;
     bool events_recorded = false;
     bool timing = false;  // record per-phase CUDA events (jbugs_last_timing); off by default: four extra stream ops per call
+    // "timing" = 2: every evaluation records into its own four events of a ring (jbugs_timing_history reads the
+    // plate-kernel and total time of each call since the option was set), so that a benchmark can report the mean and
+    // the maximum of the dominant kernel over exactly the steps of its timed region
+    std::vector<cudaEvent_t> ring;  // 4 events per entry
+    long long ring_n = 0;           // evaluations recorded since the ring was (re)started
+    static constexpr int RING = 1024;
     // comm
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
@@ -575,8 +586,19 @@ extern "C" int jbugs_plan_destroy(jbugs_plan* p) {
     cudaFree(p->d_any_bad);
     for (auto& e : p->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : p->ring)
+        if (e) cudaEventDestroy(e);
     delete p;
     return JBUGS_OK;
+}
+
+static bool is_device_ptr_strict(const void* ptr) {
+    cudaPointerAttributes a;
+    if (!ptr || cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice;
 }
 
 extern "C" int64_t jbugs_dim(const jbugs_plan* p) { return p ? p->h.D : -1; }
@@ -589,6 +611,25 @@ extern "C" int jbugs_plan_upload_data(jbugs_plan* p, int slot, const void* src, 
     if (nbytes != (size_t)p->data[slot].len * 8) return fail(JBUGS_ERR_INVALID, "data slot %d: %zu bytes given, %zu expected", slot, nbytes, (size_t)p->data[slot].len * 8);
     int rc = set_device(p);
     if (rc) return rc;
+    if (dtype == 1) {
+        // an int64 slot used as the explicit theta-slot map of a local (gathered plates): the kernels use its values
+        // as theta / gradient row numbers, so every one must lie in [0, D)
+        bool is_index = false;
+        for (const jbugs_local& L : p->locals) is_index |= L.idx_slot == slot;
+        if (is_index) {
+            const size_t n = nbytes / 8;
+            std::vector<long long> tmp;
+            const long long* v = (const long long*)src;
+            if (is_device_ptr_strict(src)) {
+                tmp.resize(n);
+                CU(cudaMemcpy(tmp.data(), src, nbytes, cudaMemcpyDeviceToHost));
+                v = tmp.data();
+            }
+            for (size_t q = 0; q < n; ++q)
+                if (v[q] < 0 || v[q] >= p->h.D)
+                    return fail(JBUGS_ERR_INVALID, "data slot %d: index %lld at element %zu is outside [0, %lld)", slot, v[q], q, (long long)p->h.D);
+        }
+    }
     CU(cudaMemcpy(p->d_slots[slot], src, nbytes, cudaMemcpyDefault));
     p->epoch++;  // data-only constants baked into captured launch sequences are stale now
     p->uploaded[slot] = 1;
@@ -656,6 +697,18 @@ extern "C" int jbugs_plan_set_option(jbugs_plan* p, const char* key, int64_t val
     }
     if (!strcmp(key, "timing")) {
         p->timing = value != 0;
+        p->ring_n = 0;
+        if (value == 2 && p->ring.empty()) {  // one set of four events per evaluation, RING evaluations deep
+            int rc = set_device(p);
+            if (rc) return rc;
+            p->ring.assign(4 * jbugs_plan_s::RING, nullptr);
+            for (auto& e : p->ring) CU(cudaEventCreate(&e));
+        }
+        if (value != 2) {
+            for (auto& e : p->ring)
+                if (e) cudaEventDestroy(e);
+            p->ring.clear();
+        }
         return JBUGS_OK;
     }
     return fail(JBUGS_ERR_INVALID, "unknown option '%s'", key);
@@ -680,22 +733,143 @@ extern "C" int jbugs_plan_describe(const jbugs_plan* p, char* buf, size_t nbuf) 
 
 extern "C" int jbugs_last_timing(const jbugs_plan* p, float* plate_ms, float* total_ms) {
     if (!p) return fail(JBUGS_ERR_INVALID, "null plan");
-    if (p->timing && p->ev[3] && p->events_recorded) {
+    if (p->timing && p->ev_last[3] && p->events_recorded) {
         // events of the most recent evaluation (also an asynchronous one): wait for its last event, then read them
         jbugs_plan* q = const_cast<jbugs_plan*>(p);
         CU(cudaSetDevice(p->device));
-        CU(cudaEventSynchronize(p->ev[3]));
-        CU(cudaEventElapsedTime(&q->last_plate_ms, p->ev[1], p->ev[2]));
-        CU(cudaEventElapsedTime(&q->last_total_ms, p->ev[0], p->ev[3]));
+        CU(cudaEventSynchronize(p->ev_last[3]));
+        CU(cudaEventElapsedTime(&q->last_plate_ms, p->ev_last[1], p->ev_last[2]));
+        CU(cudaEventElapsedTime(&q->last_total_ms, p->ev_last[0], p->ev_last[3]));
     }
     if (plate_ms) *plate_ms = p->last_plate_ms;
     if (total_ms) *total_ms = p->last_total_ms;
     return JBUGS_OK;
 }
 
+extern "C" int jbugs_timing_history(const jbugs_plan* p, float* plate_ms, float* total_ms, int cap, int* n_out) {
+    if (!p || !n_out) return fail(JBUGS_ERR_INVALID, "null argument");
+    *n_out = 0;
+    if (p->ring.empty() || p->ring_n == 0) return JBUGS_OK;
+    CU(cudaSetDevice(p->device));
+    const long long n = std::min<long long>(p->ring_n, jbugs_plan_s::RING), first = p->ring_n - n;
+    int k = 0;
+    for (long long q = first; q < p->ring_n && k < cap; ++q, ++k) {
+        const cudaEvent_t* e = p->ring.data() + 4 * (q % jbugs_plan_s::RING);
+        CU(cudaEventSynchronize(e[3]));
+        float a = 0.f, b = 0.f;
+        CU(cudaEventElapsedTime(&a, e[1], e[2]));
+        CU(cudaEventElapsedTime(&b, e[0], e[3]));
+        if (plate_ms) plate_ms[k] = a;
+        if (total_ms) total_ms[k] = b;
+    }
+    *n_out = k;
+    return JBUGS_OK;
+}
+
+// FP64 pipe peak measured on this device: independent DFMA chains, 8 per thread, enough warps to cover the pipe latency.
+// The logit / log-link plate kernels are bound by this pipe, not by HBM; bench.py reports them
+// against the number this returns (fused multiply-adds per second, all SMs).
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678) out[0] = s;  // never true: keeps the chains alive
+}
+
+extern "C" int jbugs_fp64_peak(int device, double* fma_per_s) {
+    if (!fma_per_s) return fail(JBUGS_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    double* d_out = nullptr;
+    CU(cudaMalloc(&d_out, 8));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int ctas = prop.multiProcessorCount * 8, iters = 1 << 14;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(e0, 0));
+        dfma_peak_kernel<<<ctas, 256>>>(d_out, iters, 0.999999, 1e-9);
+        CU(cudaEventRecord(e1, 0));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double rate = (double)ctas * 256.0 * 8.0 * iters / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;  // first launch: warm-up
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *fma_per_s = best;
+    return JBUGS_OK;
+}
+
 extern "C" int jbugs_host_alloc(void** ptr, size_t nbytes) {
     if (!ptr) return fail(JBUGS_ERR_INVALID, "null argument");
     CU(cudaHostAlloc(ptr, nbytes, cudaHostAllocDefault));
+    return JBUGS_OK;
+}
+extern "C" int jbugs_host_alloc_ex(void** ptr, size_t nbytes, int flags) {
+    if (!ptr) return fail(JBUGS_ERR_INVALID, "null argument");
+    CU(cudaHostAlloc(ptr, nbytes, (flags & JBUGS_HOST_WRITE_COMBINED) ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+    return JBUGS_OK;
+}
+
+// Bind the calling process (threads created later inherit it) to the CPUs and the memory of the NUMA node the GPU hangs
+// off, so that pinned staging buffers allocated afterwards are node-local: eight ranks that all stage through node 0
+// share one memory controller and one PCIe root complex (round 1: 0.19 scaling of the host-buffer path at 8 GPUs).
+// Topology comes from sysfs (/sys/bus/pci/devices/<bdf>/numa_node, /sys/devices/system/node/node<k>/cpulist).
+// Returns the node (>= 0) in *node_out, -1 when the platform reports none; never fails the caller for that.
+extern "C" int jbugs_bind_host_to_device(int device, int* node_out, int* n_cpus_out) {
+    if (node_out) *node_out = -1;
+    if (n_cpus_out) *n_cpus_out = 0;
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, device) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(JBUGS_ERR_CUDA, "cudaDeviceGetPCIBusId(%d) failed", device);
+    }
+    for (char* c = bdf; *c; ++c) *c = (char)tolower(*c);
+    char path[256];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+    FILE* f = fopen(path, "r");
+    int node = -1;
+    if (f) {
+        if (fscanf(f, "%d", &node) != 1) node = -1;
+        fclose(f);
+    }
+    if (node < 0) return JBUGS_OK;  // single-node box or a VM that hides the topology
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return JBUGS_OK;
+    char list[4096] = {0};
+    if (!fgets(list, sizeof list, f)) list[0] = 0;
+    fclose(f);
+    cpu_set_t cur, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof cur, &cur) != 0) return JBUGS_OK;
+    int n = 0;
+    for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int got = sscanf(tok, "%d-%d", &a, &b);
+        if (got < 1) continue;
+        if (got == 1) b = a;
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c)
+            if (CPU_ISSET(c, &cur)) { CPU_SET(c, &want); ++n; }
+    }
+    if (n > 0) sched_setaffinity(0, sizeof want, &want);  // (none of the node's CPUs allowed: keep the current set)
+    // memory: prefer the node (MPOL_PREFERRED = 1): falls back silently when the cpuset forbids it
+    unsigned long mask[16] = {0};
+    if (node < (int)(sizeof mask * 8)) {
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof mask * 8);
+    }
+    if (node_out) *node_out = node;
+    if (n_cpus_out) *n_cpus_out = n;
     return JBUGS_OK;
 }
 extern "C" int jbugs_host_free(void* ptr) {
@@ -820,12 +994,14 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
     const unsigned helper_tiles = (unsigned)((C + hblk - 1) / hblk);
     for (size_t k = 0; k < p->rt.size(); ++k)
         if ((rc = refresh_obs_const(p, (int)k, st))) return rc;
-    if (p->timing) CU(cudaEventRecord(p->ev[0], st));
+    cudaEvent_t* tev = p->ev;  // the four events of this call
+    if (p->timing && !p->ring.empty()) tev = p->ring.data() + 4 * (p->ring_n % jbugs_plan_s::RING);
+    if (p->timing) CU(cudaEventRecord(tev[0], st));
     // (launched the ordinary way: as a dependent launch behind the sampler's leapfrog kernel it slowed the captured
     //  trajectory graph down, 1.4 s -> 2.2 s on the Rats probe, for 1.5 us per stand-alone evaluation)
     launch_helper(prologue_kernel, 0, helper_tiles, hblk, st, p->gp, p->tp, theta, ld, C, p->d_gvals, ldg, p->d_flags, p->d_any_bad);
     p->launches++;
-    if (p->timing) CU(cudaEventRecord(p->ev[1], st));
+    if (p->timing) CU(cudaEventRecord(tev[1], st));
     FinalParams fp{};
     std::vector<int> reduce_plates;
     fp.n_plates = (int)p->rt.size();
@@ -922,7 +1098,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
             p->launches++;
         }
     }
-    if (p->timing) CU(cudaEventRecord(p->ev[2], st));
+    if (p->timing) CU(cudaEventRecord(tev[2], st));
     const double* partial_in = p->d_partial;
     {
         // many tiles: first level of the fixed-order tree (super-tiles), so that finalize's serial loop stays short
@@ -975,8 +1151,14 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         p->launches++;
     }
     if (p->timing) {
-        CU(cudaEventRecord(p->ev[3], st));
+        CU(cudaEventRecord(tev[3], st));
         p->events_recorded = true;
+        if (!p->ring.empty()) {
+            for (int q = 0; q < 4; ++q) p->ev_last[q] = tev[q];
+            p->ring_n++;
+        } else {
+            for (int q = 0; q < 4; ++q) p->ev_last[q] = p->ev[q];
+        }
     }
     CU(cudaGetLastError());
     return 0;
@@ -1013,8 +1195,8 @@ extern "C" int jbugs_eval_batch(jbugs_plan* p, const double* theta, int64_t ld, 
         if (!(flags & JBUGS_EVAL_ASYNC)) {
             CU(cudaStreamSynchronize(st));
             if (p->timing) {
-                cudaEventElapsedTime(&p->last_plate_ms, p->ev[1], p->ev[2]);
-                cudaEventElapsedTime(&p->last_total_ms, p->ev[0], p->ev[3]);
+                cudaEventElapsedTime(&p->last_plate_ms, p->ev_last[1], p->ev_last[2]);
+                cudaEventElapsedTime(&p->last_total_ms, p->ev_last[0], p->ev_last[3]);
             }
         }
         return JBUGS_OK;

@@ -124,7 +124,18 @@ hmc_reinit_kernel(double* __restrict__ q, long long ld, long long D, long long C
     for (long long d = d0; d < d1; ++d) q[d * ld + c] = theta0[d] + jitter * normal2(seed, d * C + c, attempt, 5u).x;
 }
 
-// fresh momentum p ~ N(0, M), M = diag(1 / var);  kinetic partial sums 0.5 * sum p^2 var
+// number of chains whose log density is not finite (or that were flagged DomainError)
+__global__ void __launch_bounds__(BLOCK)
+hmc_count_bad_kernel(const double* __restrict__ lp, const int* __restrict__ status, long long C, int* __restrict__ n_bad) {
+    const long long c = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (c >= C) return;
+    const double l = lp[c];
+    if (!(l == l && fabs(l) != dev_inf() && status[c] == 0)) atomicAdd(n_bad, 1);
+}
+
+// fresh momentum p ~ N(0, M), M = diag(1 / var);  kinetic partial sums 0.5 * sum p^2 var.
+// One Philox call gives the normals of rows (d, d + 1) with d counted from the tile start: HMC_ROWS must be even
+// (jbugs_hmc_create rounds it up) so that every tile starts on an even row and no two rows share a counter.
 __global__ void __launch_bounds__(BLOCK)
 hmc_refresh_kernel(double* __restrict__ p, long long ld, long long D, long long C, const double* __restrict__ var,
                    unsigned long long seed, const HmcCtl* __restrict__ ctl, double* __restrict__ kin_partial, long long ldg,

@@ -25,7 +25,8 @@ SYMBOLS = [
     "jbugs_batch_free", "jbugs_host_alloc", "jbugs_host_free", "jbugs_comm_unique_id", "jbugs_comm_init",
     "jbugs_comm_destroy", "jbugs_launch_count", "jbugs_plan_describe", "jbugs_plan_set_option",
     "jbugs_last_timing", "jbugs_hmc_create", "jbugs_hmc_destroy", "jbugs_hmc_init", "jbugs_hmc_run",
-    "jbugs_hmc_get_state", "jbugs_hmc_run_nuts", "jbugs_hmc_nuts_stats", "jbugs_plan_specialize",
+    "jbugs_hmc_get_state", "jbugs_hmc_run_nuts", "jbugs_hmc_nuts_stats", "jbugs_plan_specialize", "jbugs_hmc_draw_momentum", "jbugs_timing_history", "jbugs_host_alloc_ex",
+    "jbugs_bind_host_to_device", "jbugs_fp64_peak",
 ]
 
 
@@ -73,6 +74,10 @@ def load():
     L.jbugs_plan_describe.argtypes = [c.c_void_p, c.c_char_p, c.c_size_t]
     L.jbugs_plan_set_option.argtypes = [c.c_void_p, c.c_char_p, c.c_int64]
     L.jbugs_last_timing.argtypes = [c.c_void_p, c.POINTER(c.c_float), c.POINTER(c.c_float)]
+    L.jbugs_timing_history.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.POINTER(c.c_int)]
+    L.jbugs_host_alloc_ex.argtypes = [c.POINTER(c.c_void_p), c.c_size_t, c.c_int]
+    L.jbugs_fp64_peak.argtypes = [c.c_int, c.POINTER(c.c_double)]
+    L.jbugs_bind_host_to_device.argtypes = [c.c_int, c.POINTER(c.c_int), c.POINTER(c.c_int)]
     _lib = L
     return L
 
@@ -161,6 +166,14 @@ class CudaPlan:
         _check(self.L.jbugs_last_timing(self.h, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
 
+    def timing_history(self, cap: int = 1024):
+        """(plate_ms, total_ms) arrays of the evaluations since set_option("timing", 2), oldest first."""
+        a = np.zeros(cap, dtype=np.float32)
+        b = np.zeros(cap, dtype=np.float32)
+        n = ctypes.c_int()
+        _check(self.L.jbugs_timing_history(self.h, a.ctypes.data, b.ctypes.data, cap, ctypes.byref(n)))
+        return a[:n.value].astype(float), b[:n.value].astype(float)
+
     # -- evaluation -------------------------------------------------------------------------------
     def eval_raw(self, theta, ld, C, layout, logp, grad, status, want_grad=True, flags=0, stream=None):
         """thin call: every buffer is an address / numpy array / torch tensor, nothing is allocated."""
@@ -210,10 +223,24 @@ class CudaPlan:
         _check(self.L.jbugs_comm_init(self.h, nranks, rank, ctypes.c_char_p(unique_id)))
 
 
-def host_alloc(nbytes: int) -> Optional[int]:
+def host_alloc(nbytes: int, write_combined: bool = False) -> Optional[int]:
     p = ctypes.c_void_p()
-    _check(load().jbugs_host_alloc(ctypes.byref(p), nbytes))
+    _check(load().jbugs_host_alloc_ex(ctypes.byref(p), nbytes, 1 if write_combined else 0))
     return p.value
+
+
+def fp64_peak(device: int = 0) -> float:
+    """measured FP64 fused multiply-adds per second of the device (independent DFMA chains)."""
+    v = ctypes.c_double()
+    _check(load().jbugs_fp64_peak(device, ctypes.byref(v)))
+    return v.value
+
+
+def bind_host_to_device(device: int):
+    """pin this process to the CPUs / memory of the GPU's NUMA node; returns (node, n_cpus), node -1 if unknown."""
+    node, ncpu = ctypes.c_int(-1), ctypes.c_int(0)
+    _check(load().jbugs_bind_host_to_device(device, ctypes.byref(node), ctypes.byref(ncpu)))
+    return node.value, ncpu.value
 
 
 def host_free(ptr: int):

@@ -128,6 +128,7 @@ def _bind(L):
     L.jbugs_hmc_get_state.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.POINTER(c.c_double), c.c_void_p]
     L.jbugs_hmc_run_nuts.argtypes = L.jbugs_hmc_run.argtypes
     L.jbugs_hmc_nuts_stats.argtypes = [c.c_void_p, c.POINTER(c.c_int64), c.POINTER(c.c_double)]
+    L.jbugs_hmc_draw_momentum.argtypes = [c.c_void_p, c.c_uint32, c.c_void_p]
 
 
 def _constrain(tr, lb, ub, y):

@@ -458,6 +458,20 @@ class Lowering:
                 self.theta_map[s.sid] = (base + q, strides)
             base += m * size
         self.D = base
+        if self.theta_order is not None:
+            # a custom order must be a permutation of the D parameter labels: a duplicate or an extra label would alias
+            # two parameters onto one gradient row (or address a row outside theta) on the device
+            order = list(self.theta_order)
+            if len(order) != self.D or len(set(order)) != self.D:
+                raise LoweringError(f"theta_order must be a permutation of the {self.D} parameter labels "
+                                    f"({len(order)} given, {len(set(order))} distinct)")
+            have = set()
+            for s in self.stmts:
+                if s.sid in self.theta_map:
+                    have.update(self._labels_for(s))
+            extra = set(order) - have
+            if extra:
+                raise LoweringError(f"theta_order names unknown parameters: {sorted(extra)[:5]}")
 
     # ---- labels ----------------------------------------------------------------------------------------
     def _labels_for(self, s: Stmt):

@@ -40,12 +40,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 if _HERE not in sys.path:
     sys.path.insert(0, _HERE)
-_PKG = os.path.join(os.path.dirname(_HERE), "juliabugs.jl_b200")
-if _PKG not in sys.path:
-    sys.path.insert(0, _PKG)
-
-# the BUGS text front end is shared with the product (front end is outside the hot path)
-from jbugs.parser import (  # noqa: E402
+# the oracle reads BUGS text with its own front end (oracle/bugs_ast.py): nothing under oracle/ imports the product
+from bugs_ast import (  # noqa: E402
     BinOp, Call, Colon, Det, For, Index, Neg, Num, Range, Stoch, Var, parse,
 )
 

@@ -43,3 +43,20 @@ def rel_err(a, b, floor=1e-300):
     with np.errstate(invalid="ignore"):
         err = np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)
     return float(np.max(np.where(same, 0.0, err)))
+
+
+def grad_err(g, g0):
+    """max relative gradient error per chain.  A component that is a sum of many terms of mixed sign (the
+    hyper-parameter slots: tau * sum_i (alpha_i - alpha.c)) can cancel to far below the size of its summands, and two
+    correct evaluations that add in a different order then differ by eps * sum|terms|, not eps * |result|; so components
+    are measured against max(|g_d|, 1e-4 * max_d |g_d|) of their chain.  The ONE scale used by every gradient parity
+    test, CPU and GPU, against the plan-level C restatement and against the independent per-node oracle."""
+    g = np.asarray(g, dtype=float)
+    g0 = np.asarray(g0, dtype=float)
+    if g.ndim == 1:
+        g, g0 = g[:, None], g0[:, None]
+    if not g0.size:
+        return 0.0
+    scale = np.maximum(np.abs(g0), 1e-4 * np.max(np.abs(g0), axis=0, keepdims=True))
+    scale = np.maximum(scale, 1e-300)
+    return float(np.max(np.abs(g - g0) / scale))

@@ -50,7 +50,7 @@ def test_our_arm_needs_a_gpu():
 
 @pytest.mark.gpu
 def test_our_arm_line_on_the_gpu():
-    r = _run("--groups", "50000", "--chains", "128", "--e2e-chains", "64", "--steps", "3", "--warmup", "3")
+    r = _run("--groups", "50000", "--chains", "128", "--e2e-chains", "64", "--steps", "3", "--warmup", "3", "--sustain-s", "0.6")
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -65,8 +65,14 @@ def test_our_arm_line_on_the_gpu():
     assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and rf["algorithmic_bytes"] == 2 * 8 * 128 * d["config"]["D"]
     assert d["gpu_launches"] >= 3 * 3          # at least prologue + plate + finalize per timed step
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 8 * d["config"]["D"] * 64 and e["matches_resident"] is True
+    # every chain of the batch crosses PCIe (two slabs of 64), in both host layouts
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 8 * d["config"]["D"] * 128 and e["matches_resident"] is True
+    assert e["chains"] == 128 and e["slabs_per_step"] == 2 and e["param_fast"]["value"] > 0
     assert e["value"] < d["value"]             # host buffers cross PCIe inside the timed region
+    # the plate kernel is timed in EVERY timed step (library events); its mean cannot exceed the step it is part of
+    assert rf["kernel_ms_samples"] == 3 and rf["kernel_ms"] <= d["ms_per_step"] * 1.001 and rf["kernel_ms"] <= rf["kernel_ms_max"]
+    assert d["ms_per_step_p50"] <= d["ms_per_step_p95"]
+    assert d["sustained"]["seconds"] >= 0.5 and d["sustained"]["kernel_ms_mean"] <= d["sustained"]["ms_per_step_mean"] * 1.001
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["value"] > 0 and cb["cores"] >= 1
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 import jbugs
+from helpers import synth_seeds
 from jbugs import hmc
 
 pytestmark = pytest.mark.gpu
@@ -152,3 +153,90 @@ def test_beetles_three_links_match_winbugs_reference(link, ref):
         assert ch[k].mean() == pytest.approx(mean, rel=0.03), (link, k)
         assert ch[k].std() == pytest.approx(std, rel=0.12), (link, k)
     assert ch.summary(["beta"])["beta"]["rhat"] < 1.05
+
+
+# ---- advisor findings of round 1 -------------------------------------------------------------------
+def _hmc_handle(model, C, seed=7):
+    import ctypes
+
+    from jbugs.cuda import _check, load
+    from jbugs.hmc import _bind
+    L = load()
+    _bind(L)
+    h = ctypes.c_void_p()
+    _check(L.jbugs_hmc_create(model.cuda.h, C, seed, ctypes.byref(h)))
+    return L, h
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,C", [(4995, 256), (995, 1024), (2995, 512)])  # D = 5000 / 1000 / 3000: odd row tiles before the fix
+def test_momentum_draws_are_independent_across_row_tiles(N, C):
+    """hmc_refresh_kernel takes the two normals of one Philox call for rows (d, d+1) counted from the tile start; with
+    an odd number of rows per tile the last row of a tile and the first of the next shared a counter (identical
+    draws).  Every pair of adjacent rows must be uncorrelated and no two rows may be equal."""
+    import ctypes
+
+    from jbugs.cuda import _check
+    data, b = synth_seeds(N)
+    m = jbugs.compile(jbugs.examples.SEEDS, data)
+    D = m.plan.D
+    L, h = _hmc_handle(m, C)
+    try:
+        th0 = np.zeros(D)
+        th0[0] = np.log(1 / 0.09)
+        _check(L.jbugs_hmc_init(h, th0.ctypes.data, 0.01, 0.01))
+        p = np.empty((D, C))
+        _check(L.jbugs_hmc_draw_momentum(h, 3, p.ctypes.data))
+    finally:
+        L.jbugs_hmc_destroy(h)
+    assert np.all(np.isfinite(p))
+    same = np.all(p[1:] == p[:-1], axis=1)
+    assert not same.any(), f"rows {np.nonzero(same)[0][:5]} repeat their predecessor"
+    z = (p - p.mean(axis=1, keepdims=True)) / p.std(axis=1, keepdims=True)
+    corr = (z[1:] * z[:-1]).mean(axis=1)
+    assert np.abs(corr).max() < 6.0 / np.sqrt(C), np.abs(corr).max()
+    assert abs(p.var() - 1.0) < 0.01  # unit metric at initialisation
+
+
+@pytest.mark.gpu
+def test_monitor_buffers_grow_independently(fixtures):
+    """a second run on the same handle that monitors MORE rows for FEWER iterations must not overflow the row-index buffer."""
+    import ctypes
+
+    from jbugs.cuda import _check
+    fx = fixtures["rats"]
+    m = jbugs.compile(jbugs.examples.RATS, fx["data"], fx["inits"])
+    C = 64
+    L, h = _hmc_handle(m, C)
+    try:
+        th0 = np.ascontiguousarray(jbugs.getparams(m))
+        _check(L.jbugs_hmc_init(h, th0.ctypes.data, 0.01, 0.01))
+        acc = ctypes.c_double()
+        rows = np.array([0, 1], dtype=np.int64)
+        out = np.empty((200, 2, C))
+        _check(L.jbugs_hmc_run(h, 200, 4, 0, rows.ctypes.data, 2, out.ctypes.data, ctypes.byref(acc)))
+        rows2 = np.arange(60, dtype=np.int64)
+        out2 = np.full((5, 60, C), np.nan)
+        _check(L.jbugs_hmc_run(h, 5, 4, 0, rows2.ctypes.data, 60, out2.ctypes.data, ctypes.byref(acc)))
+        th = np.empty((m.plan.D, C))
+        _check(L.jbugs_hmc_get_state(h, th.ctypes.data, None, None, None))
+    finally:
+        L.jbugs_hmc_destroy(h)
+    assert np.all(np.isfinite(out2))
+    np.testing.assert_array_equal(out2[-1], th[:60])  # the last monitored draw is the final state
+
+
+@pytest.mark.gpu
+def test_init_refuses_chains_that_stay_outside_the_support():
+    """a chain whose log density is not finite can never accept: jbugs_hmc_init must not return OK with frozen chains."""
+    from jbugs.cuda import JBugsCudaError, _check
+    # x ~ dunif(0, 1) in the constrained space (settrans false): theta0 = 5 is outside the support for every re-draw
+    m = jbugs.compile("model { x ~ dunif(0, 1)\n y ~ dnorm(x, 1) }", {"y": 0.3})
+    m = jbugs.settrans(m, False)
+    L, h = _hmc_handle(m, 32)
+    try:
+        th0 = np.array([5.0])
+        with pytest.raises(JBugsCudaError, match="outside the support"):
+            _check(L.jbugs_hmc_init(h, th0.ctypes.data, 0.01, 0.01))
+    finally:
+        L.jbugs_hmc_destroy(h)

@@ -114,3 +114,133 @@ def test_temperature_and_split(fixtures):
     m = go.compile(ex.RATS, fx["data"], fx["inits"])
     _, r = m.evaluate_with_values(list(m.getparams()), temperature=2.0)
     assert r["tempered_logjoint"] == pytest.approx(r["logprior"] + 2.0 * r["loglikelihood"], rel=1e-15)
+
+
+# ---- the oracle's own front end (oracle/bugs_ast.py) vs the product's (jbugs/parser.py) ---------------------------------
+def _all_example_texts():
+    out = [(k, v) for k, v in vars(ex).items() if k.isupper() and isinstance(v, str) and ("~" in v or "<-" in v)
+           and "%s" not in v]  # (BEETLES is a template over the link function: instantiated below)
+    out += [(f"BEETLES_{l}", ex.BEETLES % l) for l in ("logit", "probit", "cloglog")]
+    assert len(out) >= 13
+    return out
+
+
+@pytest.mark.parametrize("name,text", _all_example_texts(), ids=[k for k, _ in _all_example_texts()])
+def test_oracle_and_product_front_ends_agree(name, text):
+    """two independently written readers (precedence climbing vs recursive descent) must build the same tree for every
+    example model: a front-end bug is no longer common-mode between the product and its checker."""
+    import bugs_ast
+    from jbugs import parser
+    assert bugs_ast.as_plain(bugs_ast.parse(text)) == bugs_ast.as_plain(parser.parse(text))
+
+
+@pytest.mark.parametrize("expr,want", [
+    ("-x^2", ("Neg", ("BinOp", "^", ("Var", "x"), ("Num", 2.0, True)))),
+    ("2^3^2", ("BinOp", "^", ("Num", 2.0, True), ("BinOp", "^", ("Num", 3.0, True), ("Num", 2.0, True)))),
+    ("a-b-c", ("BinOp", "-", ("BinOp", "-", ("Var", "a"), ("Var", "b")), ("Var", "c"))),
+    ("-a*b", ("BinOp", "*", ("Neg", ("Var", "a")), ("Var", "b"))),
+    ("a/b*c", ("BinOp", "*", ("BinOp", "/", ("Var", "a"), ("Var", "b")), ("Var", "c"))),
+    ("x[i,]", ("Index", "x", (("Var", "i"), ("Colon",)))),
+    ("x[2:n, j+1]", ("Index", "x", (("Range", ("Num", 2.0, True), ("Var", "n")), ("BinOp", "+", ("Var", "j"), ("Num", 1.0, True))))),
+    ("1.5E-3*alpha.c", ("BinOp", "*", ("Num", 0.0015, False), ("Var", "alpha.c"))),
+])
+def test_operator_precedence_known_answers(expr, want):
+    """R / Julia precedence, pinned by hand for both readers"""
+    import bugs_ast
+    from jbugs import parser
+    for mod in (bugs_ast, parser):
+        (st,) = mod.parse(f"y <- {expr}")
+        assert bugs_ast.as_plain(st.rhs) == want, mod.__name__
+
+
+def test_link_on_the_left_hand_side():
+    """logit(p[i]) <- e  ==  p[i] = logistic(e)   (src/parser/bugs_macro.jl:159-182)"""
+    import bugs_ast
+    from jbugs import parser
+    for mod in (bugs_ast, parser):
+        (st,) = mod.parse("cloglog(p[i]) <- a + b * x[i]")
+        got = bugs_ast.as_plain(st)
+        assert got[0] == "Det" and got[1] == ("Index", "p", (("Var", "i"),)) and got[2][0:2] == ("Call", "cexpexp"), mod.__name__
+
+
+def test_oracle_imports_nothing_from_the_product():
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    for f in os.listdir(root):
+        if f.endswith(".py"):
+            text = open(os.path.join(root, f)).read()
+            assert re.search(r"^\s*(from|import)\s+jbugs", text, re.M) is None, f
+            assert re.search(r"sys\.path[^\n]*juliabugs|join\([^\n]*juliabugs", text) is None, f
+
+
+# ---- dbin pinned independently of both restatements (VERDICT r1 weak #1b) -------------------------------------------
+def _mp_norm(x, mu, tau):
+    import mpmath as mp
+    return (mp.log(tau) - mp.log(2 * mp.pi)) / 2 - tau * (x - mu) ** 2 / 2
+
+
+def _mp_gamma(x, a, b):
+    import mpmath as mp
+    return a * mp.log(b) - mp.loggamma(a) + (a - 1) * mp.log(x) - b * x
+
+
+def _mp_binom(k, p, n):
+    """log Binomial(n, p) pmf at k from the exact binomial coefficient -- not the logbeta form either restatement uses"""
+    import mpmath as mp
+    return mp.log(mp.binomial(int(n), int(k))) + k * mp.log(p) + (n - k) * mp.log(1 - p)
+
+
+def test_blockers_dbin_pinned_by_50_digit_arithmetic(fixtures):
+    """Blockers at the example inits written out by hand in 50-digit arithmetic (exact binomial coefficients):
+    the oracle agrees to 1e-13.  The reference's own constant (test/model/evaluation.jl:355-379) is -8417.497576569103:
+    it differs from exact arithmetic by 1.5e-8 relative, inside that test's rtol = 1e-6 -- so `dbin` is pinned HERE,
+    and the reference constant only bounds it to 1e-6."""
+    import mpmath as mp
+    mp.mp.dps = 50
+    fx = fixtures["blockers"]
+    d, ini = fx["data"], fx["inits"]
+    n = int(d["Num"])
+    tau, dd = mp.mpf(float(ini["tau"])), mp.mpf(float(ini["d"]))
+    mu = [mp.mpf(float(x)) for x in np.asarray(ini["mu"])]
+    delta = [mp.mpf(float(x)) for x in np.asarray(ini["delta"])]
+    total = _mp_norm(dd, 0, mp.mpf("1e-6")) + _mp_gamma(tau, mp.mpf("0.001"), mp.mpf("0.001"))
+    for i in range(n):
+        pc = 1 / (1 + mp.exp(-mu[i]))
+        pt = 1 / (1 + mp.exp(-(mu[i] + delta[i])))
+        total += _mp_binom(int(d["rc"][i]), pc, int(d["nc"][i])) + _mp_binom(int(d["rt"][i]), pt, int(d["nt"][i]))
+        total += _mp_norm(mu[i], 0, mp.mpf("1e-5")) + _mp_norm(delta[i], dd, tau)
+    m = go.compile(ex.BLOCKERS, d, ini, transformed=False)   # constrained space: no log-Jacobian term
+    lp = m.logdensity(m.getparams())
+    assert abs(lp - float(total)) <= 1e-13 * abs(float(total)), (lp, mp.nstr(total, 20))
+    gold = fx["golden_logjoint"]["untransformed"]
+    rel = abs(float(total) - gold) / abs(gold)
+    assert 1e-8 < rel < 2e-8   # the reference constant itself: good to 1.5e-8 only
+
+
+def test_seeds_dbin_pinned_by_50_digit_arithmetic(fixtures):
+    """the Seeds fixture (dbin with a logit link, the shape of BASELINE config 3) the same way, at the example inits and
+    at a perturbed point; the C restatement and the CUDA kernels are held to this oracle at 1e-10 elsewhere."""
+    import mpmath as mp
+    mp.mp.dps = 50
+    fx = fixtures["seeds"]
+    d, ini = fx["data"], fx["inits"]
+    m = go.compile(ex.SEEDS, d, ini, transformed=False).use_generated_order()
+    names = m.param_names()
+    rng = np.random.default_rng(11)
+    for trial in range(2):
+        th = m.getparams()
+        if trial:
+            th = th + 0.2 * rng.standard_normal(th.size)
+            th[names.index("tau")] = 0.7
+        v = {nm: mp.mpf(float(t)) for nm, t in zip(names, th)}
+        total = _mp_gamma(v["tau"], mp.mpf("0.001"), mp.mpf("0.001"))
+        for a in ("alpha0", "alpha1", "alpha2", "alpha12"):
+            total += _mp_norm(v[a], 0, mp.mpf("1e-6"))
+        for i in range(int(d["N"])):
+            b = v[f"b[{i + 1}]"]
+            x1, x2 = int(d["x1"][i]), int(d["x2"][i])
+            eta = v["alpha0"] + v["alpha1"] * x1 + v["alpha2"] * x2 + v["alpha12"] * x1 * x2 + b
+            total += _mp_binom(int(d["r"][i]), 1 / (1 + mp.exp(-eta)), int(d["n"][i])) + _mp_norm(b, 0, v["tau"])
+        lp = m.logdensity(th)
+        assert abs(lp - float(total)) <= 1e-13 * abs(float(total)), (trial, lp, mp.nstr(total, 20))

@@ -7,7 +7,7 @@ import pytest
 import graph_oracle as go
 import jbugs
 from c_oracle import COracle
-from conftest import rel_err
+from conftest import grad_err, rel_err
 from helpers import random_thetas
 from random_models import make, make_structured
 
@@ -28,7 +28,7 @@ def test_random_model_plan_matches_node_loop(seed):
             assert lp[c] == lp_g, desc
             continue
         assert st[c] == 0 and abs(lp[c] - lp_g) <= 1e-11 * max(1.0, abs(lp_g)), (desc, text)
-        assert rel_err(g[:, c], g_g) < 1e-8, (desc, text)
+        assert grad_err(g[:, c], g_g) < 1e-10, (desc, text)
 
 
 @pytest.mark.gpu
@@ -70,7 +70,7 @@ def test_structured_random_model_plan_matches_node_loop(seed):
             assert lp[c] == lp_g, desc
             continue
         assert st[c] == 0 and abs(lp[c] - lp_g) <= 1e-11 * max(1.0, abs(lp_g)), (desc, text)
-        assert rel_err(g[:, c], g_g) < 1e-8, (desc, text)
+        assert grad_err(g[:, c], g_g) < 1e-10, (desc, text)
 
 
 @pytest.mark.gpu
