@@ -470,6 +470,40 @@ def measure(name, ctx, args, K, W, C, primary):
     return res
 
 
+def pcie_ceiling(dev):
+    """what this box's host link gives plain cudaMemcpyAsync on pinned 1 GiB buffers: each direction alone and both at
+    once (two streams).  The e2e step moves 16 bytes per parameter per chain, so this is its bound."""
+    import torch
+    n = (1 << 30) // 8
+    h_in, p1 = pinned(8 * n)
+    h_out, p2 = pinned(8 * n)
+    d_in = torch.empty(n, dtype=torch.float64, device=dev)
+    d_out = torch.empty(n, dtype=torch.float64, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def run(h2d, d2h, reps=3):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        return 8 * n / ((time.perf_counter() - t) / reps) / 1e9
+
+    run(True, True, 1)
+    out = {"h2d_alone_gbs": run(True, False), "d2h_alone_gbs": run(False, True), "both_each_way_gbs": run(True, True),
+           "how": "cudaMemcpyAsync of pinned 1 GiB buffers on two streams, measured in this run"}
+    del h_in, h_out, d_in, d_out
+    from jbugs import cuda as jcuda
+    jcuda.host_free(p1)
+    jcuda.host_free(p2)
+    return out
+
+
 def e2e(ctx, args, cp, theta, grad, lp_host, n_obs, D, C, K):
     """the metric through jbugs_eval_batch with HOST buffers: one step = every chain of the batch, in slabs of
     `Ce` chains that are staged through ONE pair of pinned host buffers (pinning 2 x 65.5 GB for all 4096 chains at
@@ -494,6 +528,7 @@ def e2e(ctx, args, cp, theta, grad, lp_host, n_obs, D, C, K):
     theta.untyped_storage().resize_(0)
     grad.untyped_storage().resize_(0)
     torch.cuda.empty_cache()
+    res["pcie_ceiling"] = pcie_ceiling(dev)
     for lay_name, lay in (("chain_fast", 0), ("param_fast", 1)):
         if lay == 1:
             # a Julia Matrix{Float64}(D, Ce): one contiguous column per chain -- what eval_batch! of the Julia glue sends
@@ -525,6 +560,7 @@ def e2e(ctx, args, cp, theta, grad, lp_host, n_obs, D, C, K):
         d2h = (8 * D * Ce + 12 * Ce) * n_slabs
         res[lay_name] = {"value": n_obs * Ce * n_slabs * world / dt, "ms_per_step": dt * 1e3, "matches_resident": ok,
                          "h2d_gbs_this_rank": h2d / dt_local / 1e9, "d2h_gbs_this_rank": d2h / dt_local / 1e9}
+    ceiling = res.pop("pcie_ceiling")
     best = max(res, key=lambda k: res[k]["value"])
     out = {"value": res["chain_fast"]["value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "chains": Ce * n_slabs, "slab_chains": Ce, "slabs_per_step": n_slabs,
@@ -532,7 +568,7 @@ def e2e(ctx, args, cp, theta, grad, lp_host, n_obs, D, C, K):
            "matches_resident": res["chain_fast"]["matches_resident"] and res["param_fast"]["matches_resident"],
            "h2d_gbs_per_rank": res["chain_fast"]["h2d_gbs_this_rank"], "d2h_gbs_per_rank": res["chain_fast"]["d2h_gbs_this_rank"],
            "param_fast": res["param_fast"], "best_layout": best,
-           "numa": ctx.numa,
+           "numa": ctx.numa, "pcie_ceiling": ceiling,
            "sample": f"all {Ce * n_slabs} chains per GPU in {n_slabs} slabs of {Ce} through jbugs_eval_batch with pinned "
                      "host buffers (theta write-combined), H2D and D2H inside the timed region; `value` is the "
                      "chain_fast host layout, `param_fast` = a Julia Matrix(D, C) incl. the two on-device transposes"}

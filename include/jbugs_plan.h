@@ -16,7 +16,7 @@
  *
  * The blob is a header followed by packed arrays of the records below, in this order:
  *   header | globals[n_globals] | gtape[n_gtape] | data[n_data] | plates[n_plates]
- *          | locals[n_locals] | terms[n_terms] | dense[n_dense]
+ *          | locals[n_locals] | terms[n_terms] | dense[n_dense] | xops[n_xops]
  * All integers little-endian, all reals IEEE-754 binary64 (the reference computes in Float64,
  * indices in Int64).  Arrays of observations/covariates are NOT in the blob: they are uploaded
  * per data slot (jbugs_plan_upload_data) so that `set_observed_values!`
@@ -49,7 +49,10 @@ enum jbugs_arg_kind {
     JBUGS_ARG_DATA_I = 3,  /* id = data slot, indexed by the group index i            */
     JBUGS_ARG_DATA_J = 4,  /* id = data slot, indexed by the inner index j            */
     JBUGS_ARG_DATA_IJ = 5, /* id = data slot (N x T column-major), indexed by (i, j)  */
-    JBUGS_ARG_ONE = 6      /* the constant 1 (covariate of an intercept-like term)    */
+    JBUGS_ARG_ONE = 6,     /* the constant 1 (covariate of an intercept-like term)    */
+    JBUGS_ARG_XVAL = 7,    /* id = value slot of the plate's expression tape          */
+    JBUGS_ARG_GVEC_J = 8   /* id = global value slot of element 0 of a (short) parameter
+                              vector indexed by the inner index: gval[id + j]         */
 };
 
 typedef struct jbugs_arg {
@@ -77,7 +80,9 @@ enum jbugs_family {
     JBUGS_FAM_CHISQ = 14,      /* dchisqr(k)       :215-217 Chisq(k)                  */
     JBUGS_FAM_T = 15,          /* dt(mu, tau, nu)  :73-80   TDistShiftedScaled(nu, mu, 1/sqrt(tau)); nu a constant */
     JBUGS_FAM_GEOMETRIC = 16,  /* dgeom(p)         :500-502 Geometric(p): failures before the first success */
-    JBUGS_FAM_COUNT = 17
+    JBUGS_FAM_CATEGORICAL = 17,/* dcat(p[1:K])     :472-474 Categorical(p): the plate's argument is p[y], the
+                                  probability of the observed category (log density = log p[y]) */
+    JBUGS_FAM_COUNT = 18
 };
 
 /* ---- constrained <-> unconstrained maps (Bijectors, call site evaluation.jl:243-257) ------- */
@@ -103,8 +108,25 @@ enum jbugs_op {
     JBUGS_OP_SUB = 17,
     JBUGS_OP_MUL = 18,
     JBUGS_OP_DIV = 19,
-    JBUGS_OP_POW = 20
+    JBUGS_OP_POW = 20,
+    /* expression tapes only */
+    JBUGS_OP_LEAF = 32,  /* value of `leaf`: CONST | ONE | GVAL | GVEC_J | LOCAL | DATA_I | DATA_J | DATA_IJ */
+    JBUGS_OP_SELECT = 33 /* v[a] != 0 ? v[b] : v[c]  (a: a 0/1 data leaf; no adjoint flows into a)          */
 };
+
+/* ---- expression tape of a plate whose predictor is not linear in the parameters -----------------------------
+ * (dugongs `alpha - beta * pow(gamma, x[i])`, lsat `logistic(beta * theta[j] - alpha[k])`, the cumulative-logit
+ * probabilities behind Bones' `dcat`).  The node functions of the reference (compiler_pass.jl:751-814) composed along
+ * the chain of logical parents of ONE observation, in static single assignment form: op k produces value slot k from
+ * slots a, b, c < k.  The forward sweep fills the slots, the reverse sweep carries adjoints back to the leaves. */
+#define JBUGS_MAX_XOPS 64
+typedef struct jbugs_xop {
+    uint32_t op;       /* jbugs_op */
+    uint16_t a, b, c;  /* operand slots */
+    uint16_t pad;
+    uint32_t pad2;
+    jbugs_arg leaf;    /* JBUGS_OP_LEAF */
+} jbugs_xop;           /* 32 bytes */
 
 typedef struct jbugs_global {
     int64_t theta_idx;  /* slot in theta                                             */
@@ -158,9 +180,12 @@ typedef struct jbugs_plate {
     uint32_t link[JBUGS_MAX_LINK]; /* applied to eta in order */
     uint32_t family;               /* observation family */
     uint32_t eta_arg;              /* which family argument receives link(eta) */
-    uint32_t has_obs;              /* 0: prior-only plate (locals without a likelihood) */
+    uint32_t has_obs;              /* 0: prior-only plate (locals without a likelihood); 1: linear predictor (terms +
+                                      link); 2: expression plate -- first_term / n_terms address xops[] instead of
+                                      terms[], n_link = 0, and the family arguments that depend on parameters are
+                                      XVAL references into the tape */
     jbugs_arg y;                   /* DATA_I | DATA_IJ */
-    jbugs_arg aux[3];              /* the family's arguments; aux[eta_arg] is ignored */
+    jbugs_arg aux[3];              /* the family's arguments; aux[eta_arg] is ignored (has_obs == 1) */
 } jbugs_plate;                     /* 128 bytes */
 
 /* Dense linear predictor:  y[i] ~ dbern|dbin(logistic(inprod(X[i, 1:P], beta[1:P])) [, n[i]])
@@ -186,7 +211,7 @@ typedef struct jbugs_plan_header {
     uint32_t n_locals;
     uint32_t n_terms;
     uint32_t n_dense; /* jbugs_dense records appended after terms[] */
-    uint32_t reserved32;
+    uint32_t n_xops;  /* jbugs_xop records appended after dense[] */
     uint64_t reserved;
 } jbugs_plan_header; /* 64 bytes */
 

@@ -91,6 +91,7 @@ struct PlateRt {
     plate_launch_fn jit_launch = nullptr;
     int jit_fused = FUSED_NONE;
     bool jit_valid = true;    // false: the data are outside the fused formulas' domain -> interpreter
+    XOpDev* d_xtape = nullptr;  // expression plates: the resolved tape in device memory
 };
 
 struct jbugs_plan_s {
@@ -104,6 +105,7 @@ struct jbugs_plan_s {
     std::vector<jbugs_local> locals;
     std::vector<jbugs_term> terms;
     std::vector<jbugs_dense> dense;
+    std::vector<jbugs_xop> xops;
     // dense predictors: residual matrix R [N x ldr], split-K partials of X^T R, per-chain logp partial rows
     double* d_R = nullptr;
     double* d_Gp = nullptr;
@@ -206,6 +208,7 @@ static int resolve_arg(const jbugs_plan* p, const jbugs_arg& a, ArgS& s, ArgV& v
                        StreamBuilder& sb) {
     s.kind = (int)a.kind;
     s.id = 0;
+    s.soff = 0;
     v.ptr = nullptr;
     v.value = a.value;
     v.soff = 0;
@@ -236,6 +239,7 @@ static int resolve_arg(const jbugs_plan* p, const jbugs_arg& a, ArgS& s, ArgV& v
         v.ptr = (const double*)p->d_slots[a.id];
         v.soff = sb.add(v.ptr, (int)a.kind);
         if (v.soff < 0) return fail(JBUGS_ERR_UNSUPPORTED, "a plate uses more than %d distinct data streams", MAX_STREAMS);
+        s.soff = v.soff;  // also part of the shape (static specs with a static inner extent bake the layout in)
         return 0;
     default: return fail(JBUGS_ERR_INVALID, "unknown argument kind %u", a.kind);
     }
@@ -251,6 +255,157 @@ static int check_len(const jbugs_plan* p, const jbugs_arg& a, long long N, long 
     return 0;
 }
 
+// the part of a plate's device description shared by linear-predictor plates and expression plates: the locals with
+// their priors and theta-slot maps, the gref table, staging sizes, the kernel variant
+static int pick_variant(const jbugs_plan* p, const PlateRt& r, long long T);
+static int build_locals_and_finish(jbugs_plan* p, int k, std::vector<int>& gref, StreamBuilder& sb) {
+    const jbugs_plate& pl = p->plates[k];
+    PlateRt& r = p->rt[k];
+    PlateParams& pp = r.pp;
+    PlateShape& sh = pp.sh;
+    PlateVals& V = pp.v;
+    const jbugs_local* L = p->locals.data() + pl.first_local;
+    int rc;
+    for (int l = 0; l < (int)pl.n_locals; ++l) {
+        LocalS& ls = sh.loc[l];
+        LocalV& lv = V.loc[l];
+        if (L[l].family >= JBUGS_FAM_COUNT) return fail(JBUGS_ERR_INVALID, "plate %d local %d: unknown family", k, l);
+        ls.level = (int)L[l].level; ls.transform = (int)L[l].transform; ls.family = (int)L[l].family;
+        ls.has_idx = L[l].idx_slot >= 0;
+        lv.base = L[l].theta_base; lv.si = L[l].stride_i; lv.sj = L[l].stride_j;
+        lv.lb = L[l].lb; lv.ub = L[l].ub; lv.idx = nullptr;
+        if (ls.has_idx) {
+            if (L[l].idx_slot >= (int)p->h.n_data || p->data[L[l].idx_slot].dtype != 1)
+                return fail(JBUGS_ERR_INVALID, "plate %d local %d: index slot must be int64", k, l);
+            const long long need = ls.level == JBUGS_LEVEL_OBS ? pl.N * pl.T : pl.N;
+            if (p->data[L[l].idx_slot].len < need) return fail(JBUGS_ERR_INVALID, "plate %d local %d: index array too short", k, l);
+            lv.idx = (const long long*)p->d_slots[L[l].idx_slot];
+        } else {
+            // every addressed slot must lie inside [0, D)
+            const long long jmax = ls.level == JBUGS_LEVEL_OBS ? pl.T - 1 : 0;
+            const long long c[4] = {lv.base, lv.base + lv.si * (pl.N - 1), lv.base + lv.sj * jmax,
+                                    lv.base + lv.si * (pl.N - 1) + lv.sj * jmax};
+            for (long long x : c)
+                if (pl.N > 0 && (x < 0 || x >= p->h.D)) return fail(JBUGS_ERR_INVALID, "plate %d local %d: theta slot out of range", k, l);
+        }
+        for (int q = 0; q < 2; ++q) {
+            if ((rc = resolve_arg(p, L[l].args[q], ls.args[q], lv.args[q], gref, (int)pl.n_locals, sb))) return rc;
+            if (ls.level == JBUGS_LEVEL_GROUP && (L[l].args[q].kind == JBUGS_ARG_DATA_J || L[l].args[q].kind == JBUGS_ARG_DATA_IJ))
+                return fail(JBUGS_ERR_INVALID, "plate %d local %d: group-level prior indexed by j", k, l);
+            if ((rc = check_len(p, L[l].args[q], pl.N, pl.T, "prior argument"))) return rc;
+        }
+        ls.mu_zero = (L[l].args[0].kind == JBUGS_ARG_CONST && L[l].args[0].value == 0.0) ? 1 : 0;
+        lv.args[2].value = L[l].args[2].kind == JBUGS_ARG_ONE ? 1.0 : L[l].args[2].value;  // dt's constant degrees of freedom
+        if (L[l].family == JBUGS_FAM_T && L[l].args[2].kind != JBUGS_ARG_CONST && L[l].args[2].kind != JBUGS_ARG_ONE)
+            return fail(JBUGS_ERR_UNSUPPORTED, "plate %d local %d: the degrees of freedom of dt must be a constant", k, l);
+    }
+    if ((int)gref.size() > MAX_GREF) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d references more than %d global values", k, MAX_GREF);
+    sh.n_gref = (int)gref.size();
+    for (int q = 0; q < MAX_GREF; ++q) V.gref[q] = q < (int)gref.size() ? gref[q] : 0;
+    V.i0 = p->shard_i0[k]; V.i1 = p->shard_i1[k];
+    V.per_group = sb.chunk_acc;
+    V.j_doubles = (sb.j_acc + 1) / 2 * 2;
+    // TMA staging needs 16-byte aligned sources: slot bases are cudaMalloc'ed, so element offsets must be even --
+    // the kernel checks the chunk start and length, here: the column stride N of rank-2 streams
+    V.bulk_ok = p->use_tma ? 1 : 0;
+    for (int q = 0; q < V.n_streams; ++q)
+        if (V.streams[q].kind == JBUGS_ARG_DATA_IJ && (pl.N % 2) != 0) V.bulk_ok = 0;
+    r.smem_bytes = (size_t)(V.j_doubles + 2 * V.per_group * STAGE_G) * sizeof(double);
+    if (r.smem_bytes > 200 * 1024)
+        return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: %zu bytes of staged data per chunk exceed shared memory (inner extent too large)", k, r.smem_bytes);
+    r.variant = pick_variant(p, r, pl.T);
+    r.const_dirty = true;
+    r.obs_const = 0.0;
+    return 0;
+}
+
+// expression plate (has_obs == 2): the predictor is an SSA tape of the composed node functions; leaves are resolved
+// like any other argument (data leaves become staged streams, global leaves plate-local gref indices)
+static int build_xplate(jbugs_plan* p, int k) {
+    const jbugs_plate& pl = p->plates[k];
+    PlateRt& r = p->rt[k];
+    PlateParams& pp = r.pp;
+    PlateShape& sh = pp.sh;
+    PlateVals& V = pp.v;
+    const jbugs_xop* X = p->xops.data() + pl.first_term;
+    const int nx = (int)pl.n_terms;
+    if (nx < 1 || nx > JBUGS_MAX_XOPS) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: expression tape of %d ops (1..%d supported)", k, nx, JBUGS_MAX_XOPS);
+    if (pl.n_link != 0) return fail(JBUGS_ERR_INVALID, "plate %d: an expression plate has no link tape", k);
+    sh.kg = 0; sh.nl = (int)pl.n_locals; sh.has_off = 0;
+    sh.family = (int)pl.family; sh.eta_arg = 0; sh.has_obs = 1; sh.n_link = 0; sh.n_x = nx;
+    V.N = pl.N; V.T = pl.T;
+    StreamBuilder sb;
+    sb.V = &V;
+    sb.T = pl.T;
+    std::vector<int> gref;
+    const int n_gv = (int)(p->h.n_globals + p->h.n_gtape);
+    // parameter vectors indexed by the inner index first: their T elements must sit in consecutive gref positions
+    for (int q = 0; q < nx; ++q)
+        if (X[q].op == JBUGS_OP_LEAF && X[q].leaf.kind == JBUGS_ARG_GVEC_J) {
+            const int base = X[q].leaf.id;
+            if (base < 0 || base + pl.T > n_gv) return fail(JBUGS_ERR_INVALID, "plate %d: parameter vector out of range", k);
+            if (std::find(gref.begin(), gref.end(), base) == gref.end()) {
+                for (long long e = 0; e < pl.T; ++e)
+                    if (std::find(gref.begin(), gref.end(), base + (int)e) != gref.end())
+                        return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: overlapping parameter vectors in one tape", k);
+                for (long long e = 0; e < pl.T; ++e) gref.push_back(base + (int)e);
+            }
+        }
+    std::vector<XOpDev> tape((size_t)nx);
+    int rc;
+    for (int q = 0; q < nx; ++q) {
+        XOpDev& o = tape[q];
+        memset(&o, 0, sizeof o);
+        o.op = (int)X[q].op;
+        o.a = X[q].a; o.b = X[q].b; o.c = X[q].c;
+        const bool unary = X[q].op < 16, binary = X[q].op >= 16 && X[q].op <= JBUGS_OP_POW;
+        if (X[q].op == JBUGS_OP_LEAF) {
+            const jbugs_arg& a = X[q].leaf;
+            if (a.kind == JBUGS_ARG_GVEC_J) {
+                o.kind = JBUGS_ARG_GVEC_J;
+                o.id = (int)(std::find(gref.begin(), gref.end(), a.id) - gref.begin());
+                continue;
+            }
+            if (a.kind == JBUGS_ARG_XVAL) return fail(JBUGS_ERR_INVALID, "plate %d: a tape leaf cannot be a tape value", k);
+            ArgS s2; ArgV v2;
+            if ((rc = resolve_arg(p, a, s2, v2, gref, (int)pl.n_locals, sb))) return rc;
+            if ((rc = check_len(p, a, pl.N, pl.T, "tape leaf"))) return rc;
+            o.kind = s2.kind; o.id = s2.id; o.soff = v2.soff; o.value = a.kind == JBUGS_ARG_ONE ? 1.0 : a.value;
+        } else if (X[q].op == JBUGS_OP_SELECT) {
+            if (o.a >= q || o.b >= q || o.c >= q) return fail(JBUGS_ERR_INVALID, "plate %d: tape op %d looks forward", k, q);
+        } else if (unary || binary) {
+            if (o.a >= q || (binary && o.b >= q)) return fail(JBUGS_ERR_INVALID, "plate %d: tape op %d looks forward", k, q);
+            if (unary && X[q].op > JBUGS_OP_NEG) return fail(JBUGS_ERR_INVALID, "plate %d: unknown tape op %u", k, X[q].op);
+        } else {
+            return fail(JBUGS_ERR_INVALID, "plate %d: unknown tape op %u", k, X[q].op);
+        }
+    }
+    if ((rc = resolve_arg(p, pl.y, sh.y, V.y, gref, 0, sb))) return rc;
+    if ((rc = check_len(p, pl.y, pl.N, pl.T, "y"))) return rc;
+    for (int q = 0; q < 2; ++q) {
+        if (pl.aux[q].kind == JBUGS_ARG_XVAL) {
+            if (pl.aux[q].id < 0 || pl.aux[q].id >= nx) return fail(JBUGS_ERR_INVALID, "plate %d: family argument outside the tape", k);
+            sh.aux[q] = ArgS{JBUGS_ARG_XVAL, pl.aux[q].id, 0};
+            continue;
+        }
+        if ((rc = resolve_arg(p, pl.aux[q], sh.aux[q], V.aux[q], gref, (int)pl.n_locals, sb))) return rc;
+        if ((rc = check_len(p, pl.aux[q], pl.N, pl.T, "aux"))) return rc;
+    }
+    V.aux[2].value = pl.aux[2].kind == JBUGS_ARG_ONE ? 1.0 : pl.aux[2].value;
+    if (pl.aux[2].kind == JBUGS_ARG_DATA_I || pl.aux[2].kind == JBUGS_ARG_DATA_IJ) {
+        if (pl.family == JBUGS_FAM_T) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: dt observations cannot carry a weight", k);
+        if ((rc = resolve_arg(p, pl.aux[2], sh.aux[2], V.aux[2], gref, (int)pl.n_locals, sb))) return rc;
+        if ((rc = check_len(p, pl.aux[2], pl.N, pl.T, "weight"))) return rc;
+    }
+    cudaFree(r.d_xtape);
+    r.d_xtape = nullptr;
+    CU(cudaMalloc(&r.d_xtape, tape.size() * sizeof(XOpDev)));
+    CU(cudaMemcpy(r.d_xtape, tape.data(), tape.size() * sizeof(XOpDev), cudaMemcpyHostToDevice));
+    V.xtape = r.d_xtape;
+    return build_locals_and_finish(p, k, gref, sb);
+}
+
+static int build_xplate(jbugs_plan* p, int k);
 static int build_plate(jbugs_plan* p, int k) {
     const jbugs_plate& pl = p->plates[k];
     PlateRt& r = p->rt[k];
@@ -262,6 +417,7 @@ static int build_plate(jbugs_plan* p, int k) {
     if (pl.family >= JBUGS_FAM_COUNT) return fail(JBUGS_ERR_INVALID, "plate %d: unknown family", k);
     if (pl.eta_arg > 1) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: eta_arg > 1", k);
     const jbugs_local* L = p->locals.data() + pl.first_local;
+    if (pl.has_obs == 2) return build_xplate(p, k);
     const jbugs_term* T = p->terms.data() + pl.first_term;
     std::vector<int> gref;
     // canonical term order: GVAL-coef terms, then one term per local (in local order), then an offset
@@ -311,55 +467,7 @@ static int build_plate(jbugs_plan* p, int k) {
             if ((rc = check_len(p, pl.aux[2], pl.N, pl.T, "weight"))) return rc;
         }
     }
-    for (int l = 0; l < (int)pl.n_locals; ++l) {
-        LocalS& ls = sh.loc[l];
-        LocalV& lv = V.loc[l];
-        if (L[l].family >= JBUGS_FAM_COUNT) return fail(JBUGS_ERR_INVALID, "plate %d local %d: unknown family", k, l);
-        ls.level = (int)L[l].level; ls.transform = (int)L[l].transform; ls.family = (int)L[l].family;
-        ls.has_idx = L[l].idx_slot >= 0;
-        lv.base = L[l].theta_base; lv.si = L[l].stride_i; lv.sj = L[l].stride_j;
-        lv.lb = L[l].lb; lv.ub = L[l].ub; lv.idx = nullptr;
-        if (ls.has_idx) {
-            if (L[l].idx_slot >= (int)p->h.n_data || p->data[L[l].idx_slot].dtype != 1)
-                return fail(JBUGS_ERR_INVALID, "plate %d local %d: index slot must be int64", k, l);
-            const long long need = ls.level == JBUGS_LEVEL_OBS ? pl.N * pl.T : pl.N;
-            if (p->data[L[l].idx_slot].len < need) return fail(JBUGS_ERR_INVALID, "plate %d local %d: index array too short", k, l);
-            lv.idx = (const long long*)p->d_slots[L[l].idx_slot];
-        } else {
-            // every addressed slot must lie inside [0, D)
-            const long long jmax = ls.level == JBUGS_LEVEL_OBS ? pl.T - 1 : 0;
-            const long long c[4] = {lv.base, lv.base + lv.si * (pl.N - 1), lv.base + lv.sj * jmax,
-                                    lv.base + lv.si * (pl.N - 1) + lv.sj * jmax};
-            for (long long x : c)
-                if (pl.N > 0 && (x < 0 || x >= p->h.D)) return fail(JBUGS_ERR_INVALID, "plate %d local %d: theta slot out of range", k, l);
-        }
-        for (int q = 0; q < 2; ++q) {
-            if ((rc = resolve_arg(p, L[l].args[q], ls.args[q], lv.args[q], gref, (int)pl.n_locals, sb))) return rc;
-            if (ls.level == JBUGS_LEVEL_GROUP && (L[l].args[q].kind == JBUGS_ARG_DATA_J || L[l].args[q].kind == JBUGS_ARG_DATA_IJ))
-                return fail(JBUGS_ERR_INVALID, "plate %d local %d: group-level prior indexed by j", k, l);
-            if ((rc = check_len(p, L[l].args[q], pl.N, pl.T, "prior argument"))) return rc;
-        }
-        lv.args[2].value = L[l].args[2].kind == JBUGS_ARG_ONE ? 1.0 : L[l].args[2].value;  // dt's constant degrees of freedom
-        if (L[l].family == JBUGS_FAM_T && L[l].args[2].kind != JBUGS_ARG_CONST && L[l].args[2].kind != JBUGS_ARG_ONE)
-            return fail(JBUGS_ERR_UNSUPPORTED, "plate %d local %d: the degrees of freedom of dt must be a constant", k, l);
-    }
-    if ((int)gref.size() > MAX_GREF) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d references more than %d global values", k, MAX_GREF);
-    sh.n_gref = (int)gref.size();
-    for (int q = 0; q < MAX_GREF; ++q) V.gref[q] = q < (int)gref.size() ? gref[q] : 0;
-    V.i0 = p->shard_i0[k]; V.i1 = p->shard_i1[k];
-    V.per_group = sb.chunk_acc;
-    V.j_doubles = (sb.j_acc + 1) / 2 * 2;
-    // TMA staging needs 16-byte aligned sources: slot bases are cudaMalloc'ed, so element offsets must be even --
-    // the kernel checks the chunk start and length, here: the column stride N of rank-2 streams
-    V.bulk_ok = p->use_tma ? 1 : 0;
-    for (int q = 0; q < V.n_streams; ++q)
-        if (V.streams[q].kind == JBUGS_ARG_DATA_IJ && (pl.N % 2) != 0) V.bulk_ok = 0;
-    r.smem_bytes = (size_t)(V.j_doubles + 2 * V.per_group * STAGE_G) * sizeof(double);
-    if (r.smem_bytes > 200 * 1024)
-        return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: %zu bytes of staged data per chunk exceed shared memory (inner extent too large)", k, r.smem_bytes);
-    r.variant = p->force_dynamic ? 0 : select_spec(sh, pl.T);
-    r.const_dirty = true;
-    r.obs_const = 0.0;
+    if ((rc = build_locals_and_finish(p, k, gref, sb))) return rc;
     return 0;
 }
 
@@ -391,6 +499,13 @@ static int refresh_obs_const(jbugs_plan* p, int k, cudaStream_t st) {
         r.obs_const = h[0];
     }
     return 0;
+}
+
+// kernel variant of a plate: expression plates run the tape interpreter; everything else a static spec whose shape is
+// identical, else the generic interpreter (variant 0; also when the caller forces it)
+static int pick_variant(const jbugs_plan* p, const PlateRt& r, long long T) {
+    if (r.pp.sh.n_x > 0) return g_xspec;
+    return p->force_dynamic ? 0 : select_spec(r.pp.sh, T);
 }
 
 static int rebuild_plates(jbugs_plan* p) {
@@ -425,7 +540,7 @@ extern "C" int jbugs_plan_create(const void* blob, size_t nbytes, int device, jb
     const size_t need = sizeof h + h.n_globals * sizeof(jbugs_global) + h.n_gtape * sizeof(jbugs_gop) +
                         h.n_data * sizeof(jbugs_data_desc) + h.n_plates * sizeof(jbugs_plate) +
                         h.n_locals * sizeof(jbugs_local) + h.n_terms * sizeof(jbugs_term) +
-                        h.n_dense * sizeof(jbugs_dense);
+                        h.n_dense * sizeof(jbugs_dense) + h.n_xops * sizeof(jbugs_xop);
     if (need != nbytes) return fail(JBUGS_ERR_INVALID, "plan blob is %zu bytes, records need %zu", nbytes, need);
     if (h.D < 0) return fail(JBUGS_ERR_INVALID, "negative dimension");
     if (h.n_globals + h.n_gtape > (uint32_t)MAX_GVALS) return fail(JBUGS_ERR_UNSUPPORTED, "more than %d global values", MAX_GVALS);
@@ -451,13 +566,15 @@ extern "C" int jbugs_plan_create(const void* blob, size_t nbytes, int device, jb
     take(p->locals, h.n_locals);
     take(p->terms, h.n_terms);
     take(p->dense, h.n_dense);
+    take(p->xops, h.n_xops);
     auto destroy = [&](int rc) {
         jbugs_plan_destroy(p);
         return rc;
     };
     // validation of record ranges
     for (auto& pl : p->plates) {
-        if ((size_t)pl.first_local + pl.n_locals > p->locals.size() || (size_t)pl.first_term + pl.n_terms > p->terms.size())
+        const size_t tape_len = pl.has_obs == 2 ? p->xops.size() : p->terms.size();
+        if ((size_t)pl.first_local + pl.n_locals > p->locals.size() || (size_t)pl.first_term + pl.n_terms > tape_len)
             return destroy(fail(JBUGS_ERR_INVALID, "plate record ranges exceed the blob"));
     }
     for (size_t k = 0; k < p->globals.size(); ++k) {
@@ -573,6 +690,7 @@ extern "C" int jbugs_plan_destroy(jbugs_plan* p) {
     cudaSetDevice(p->device);
     jbugs_comm_destroy(p);
     for (void* d : p->d_slots) cudaFree(d);
+    for (auto& r : p->rt) cudaFree(r.d_xtape);
     free_workspace(p);
     free_slots(p);
     for (auto& s : p->slot) {
@@ -637,7 +755,7 @@ extern "C" int jbugs_plan_upload_data(jbugs_plan* p, int slot, const void* src, 
     p->dense_const_dirty = true;
     if (!p->force_dynamic)
         for (size_t k = 0; k < p->rt.size(); ++k) {
-            p->rt[k].variant = select_spec(p->rt[k].pp.sh, p->rt[k].pp.v.T);
+            p->rt[k].variant = pick_variant(p, p->rt[k], p->rt[k].pp.v.T);
             p->rt[k].const_dirty = true;
         }
     return JBUGS_OK;

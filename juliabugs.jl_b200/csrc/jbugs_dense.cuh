@@ -232,25 +232,19 @@ dense_fwd_kernel(const __grid_constant__ DenseFwdParams P) {
             const bool row_ok = i < P.op.M;
             const double yv = row_ok ? __ldg(P.y + i) : 0.0;
             const double nv = row_ok ? (P.n ? __ldg(P.n + i) : 1.0) : 0.0;
-            const double mv = nv - yv;
 #pragma unroll
             for (int tn = 0; tn < DG_TN; ++tn) {
                 double r2[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const double eta = acc[tm][tn][e];
-                    const double ax = fabs(eta);
-                    const SoftplusParts sp3 = softplus_parts(ax);
-                    const bool up = eta >= 0.0;
-                    const double p = up ? sp3.inv : sp3.e * sp3.inv;
-                    // y log p + (n - y) log(1 - p) = -(eta >= 0 ? n - y : y) |eta| - n log1p(exp(-|eta|))
-                    double nll = fma(up ? mv : yv, ax, nv * sp3.l1p);  // minus the log-likelihood term
-                    if (ax > kLogisticUpper) {  // saturated tails (rare): the reference's logistic is exactly 0 / 1 there
-                        if (eta > kLogisticUpper && mv != 0.0) nll = dev_inf();
-                        if (eta < kLogisticLower && yv != 0.0) nll = dev_inf();
-                    }
-                    lp[tn][e] -= row_ok ? nll : 0.0;
-                    r2[e] = yv - nv * p;
+                    // y log p + (n - y) log(1 - p) and y - n p, branch-free (jbugs_device.cuh: binomial_logit)
+                    double l = 0.0, dl;
+                    int sat = 0;
+                    binomial_logit(eta, yv, nv, l, dl, sat);
+                    if (sat && logit_tail_is_inf(eta, yv, nv)) l = -dev_inf();  // saturated tails (rare)
+                    lp[tn][e] += row_ok ? l : 0.0;
+                    r2[e] = dl;
                 }
                 const long long c = n0 + wn * 32 + tn * 8 + 2 * fk;
                 if (row_ok && c < P.op.N) {

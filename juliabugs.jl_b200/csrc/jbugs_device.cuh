@@ -203,6 +203,11 @@ __device__ __forceinline__ bool fam_eval(int fam, double x, double a0, double a1
         o.da0 = 1.0 / a0 - (x == 0.0 ? 0.0 : x / (1.0 - a0));
         return !(a0 > 0.0 && a0 <= 1.0);
     }
+    case JBUGS_FAM_CATEGORICAL: {  // Categorical(p): a0 = p[x], the probability of the observed category
+        o.lp = log(a0);
+        o.da0 = 1.0 / a0;
+        return !(a0 >= 0.0 && a0 <= 1.0 + 1e-8);
+    }
     default: return false;  // FLAT
     }
 }
@@ -246,36 +251,127 @@ struct SoftplusParts {
     double l1p;  // log(1 + e)
 };
 
-__device__ __forceinline__ SoftplusParts softplus_parts(double ax /* |eta| */) {
-    SoftplusParts o;
-    const double a = ax > 700.0 ? 700.0 : ax;  // e < 1e-304 beyond: irrelevant next to |eta|; NaN falls through and propagates
-    // exp(-a), a in [0, 700]: -a = k ln2 + r, |r| <= ln2/2, degree-10 polynomial, exact scaling by 2^k
-    // (the sign of a lives in the operand modifiers of the fma's: no separate negation on the FP64 pipe)
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52: the low word of (t + magic) is rint(t)
-    const double t = fma(a, -1.4426950408889634074, magic);
-    const int k = __double2loint(t);
-    const double kf = t - magic;
-    double r = fma(kf, -6.93147180369123816490e-01, -a);
-    r = fma(kf, -1.90821492927058770002e-10, r);
+// 2 * (atanh(s) / s) coefficients: l1p = s * poly(s^2) with the factor 2 folded in (exact: a power of two)
+static __constant__ double kAtanhPoly2[10] = {
+    2 * 0.08890381913056651,
+    2 * 0.04940394524382393,
+    2 * 0.06795652742789947,
+    2 * 0.07681838124445817,
+    2 * 0.09091429900236955,
+    2 * 0.11111095430673142,
+    2 * 0.1428571455582858,
+    2 * 0.199999999976438,
+    2 * 0.33333333333341286,
+    2.0};
+
+// approximate reciprocal of a double from its upper word only (SASS MUFU.RCP64H, ~20 significant bits): the seed of the
+// cubic correction below.  One instruction, against eleven for the float round trip with its IEEE slow-path call.
+__device__ __forceinline__ double rcp_seed(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    return r;
+}
+
+// Branch-free and free of FP64 compares / selects: everything that is not arithmetic runs on the integer pipe
+// (the plate kernels that call this are bound by the FP64 pipe: 16 lanes per SM sub-partition, a warp-wide FP64
+// instruction holds it for two cycles, so every FP64 instruction saved is two cycles per observation-warp).
+//   hi_abs : upper word of |eta|, clamped by the caller's integer min to the upper word of 700.0 (e < 1e-304 beyond:
+//            irrelevant next to |eta|; the exponent field below must not wrap).  NaN is clamped as well: the caller's
+//            own use of eta keeps it alive.
+// polynomial evaluation order: Horner (fewest instructions, one dependent chain of `degree` fused multiply-adds) or
+// Estrin (three more multiplies, depth 4): the plate kernels interleave several observations per thread, which hides a
+// Horner chain; the build picks with -DJB_ESTRIN=1 (measured: see DESIGN section 3)
+#ifndef JB_ESTRIN
+#define JB_ESTRIN 0
+#endif
+__device__ __forceinline__ double exp_poly(double r) {  // degree 10, kExpPoly highest degree first
+#if JB_ESTRIN
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a0 = fma(kExpPoly[9], r, kExpPoly[10]), a1 = fma(kExpPoly[7], r, kExpPoly[8]),
+                 a2 = fma(kExpPoly[5], r, kExpPoly[6]), a3 = fma(kExpPoly[3], r, kExpPoly[4]),
+                 a4 = fma(kExpPoly[1], r, kExpPoly[2]);
+    const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(kExpPoly[0], r2, a4);
+    return fma(b2, r8, fma(b1, r4, b0));
+#else
     double p = kExpPoly[0];
 #pragma unroll
     for (int n = 1; n < 11; ++n) p = fma(p, r, kExpPoly[n]);
-    o.e = p * __hiloint2double((k + 1023) << 20, 0);
+    return p;
+#endif
+}
+__device__ __forceinline__ double atanh_poly2(double z) {  // degree 9 in z = s^2, kAtanhPoly2 highest degree first
+#if JB_ESTRIN
+    const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+    const double e0 = fma(kAtanhPoly2[8], z, kAtanhPoly2[9]), e1 = fma(kAtanhPoly2[6], z, kAtanhPoly2[7]),
+                 e2 = fma(kAtanhPoly2[4], z, kAtanhPoly2[5]), e3 = fma(kAtanhPoly2[2], z, kAtanhPoly2[3]),
+                 e4 = fma(kAtanhPoly2[0], z, kAtanhPoly2[1]);
+    const double f0 = fma(e1, z2, e0), f1 = fma(e3, z2, e2);
+    return fma(e4, z8, fma(f1, z4, f0));
+#else
+    double q = kAtanhPoly2[0];
+#pragma unroll
+    for (int n = 1; n < 10; ++n) q = fma(q, z, kAtanhPoly2[n]);
+    return q;
+#endif
+}
+
+__device__ __forceinline__ SoftplusParts softplus_parts(double ax /* |eta| (<= ~700, see above) */) {
+    SoftplusParts o;
+    // exp(-a), a in [0, 700]: -a = k ln2 + r, |r| <= ln2/2, degree-10 polynomial, scaling by 2^k on the integer pipe
+    // (the sign of a lives in the operand modifiers of the fma's: no separate negation on the FP64 pipe)
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52: the low word of (t + magic) is rint(t)
+    const double t = fma(ax, -1.4426950408889634074, magic);
+    const int k = __double2loint(t);
+    const double kf = t - magic;
+    double r = fma(kf, -6.93147180369123816490e-01, -ax);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    const double p = exp_poly(r);
+    // p in [0.70, 1.42], k >= -1010: adding k to the exponent field keeps the number normal -- no FP64 multiply
+    o.e = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
     // one reciprocal serves both 1/(1+e) and e/(2+e): d = (1+e)(2+e) in (2, 6]
     const double u1 = 1.0 + o.e, u2 = 2.0 + o.e, d = u1 * u2;
-    // 24-bit seed, then one cubic step rc (1 + h + h^2), h = 1 - d rc ~ 1e-7: error h^3 ~ 1e-21 (three DFMA; three
-    // Newton steps would be six FP64 instructions)
-    double rc = (double)__frcp_rn((float)d);
+    // ~20-bit seed, then one cubic step rc (1 + h + h^2), h = 1 - d rc < 2^-19: error h^3 < 1e-17 (three DFMA)
+    double rc = rcp_seed(d);
     const double h = fma(-d, rc, 1.0);
     rc = fma(rc, fma(h, h, h), rc);
     o.inv = rc * u2;
     // log1p(e) = 2 atanh(s), s = e / (2 + e) in (0, 1/3]
-    const double s = o.e * (rc * u1), z = s * s;
-    double q = kAtanhPoly[0];
-#pragma unroll
-    for (int n = 1; n < 10; ++n) q = fma(q, z, kAtanhPoly[n]);
-    o.l1p = 2.0 * s * q;
+    const double s = o.e * (rc * u1);
+    o.l1p = s * atanh_poly2(s * s);
     return o;
+}
+
+// |eta| with its upper word clamped to that of 700.0 (integer min: for non-negative doubles the bit patterns order like
+// the values), and the upper word itself for range tests on the integer pipe
+constexpr int kHi700 = 0x4085E000;        // 700.0 = 0x4085E00000000000
+constexpr int kHiLogisticUpper = 0x40425E4F;  // upper word of kLogisticUpper = 36.7368005696771
+__device__ __forceinline__ double abs_clamped(double eta, int& hi_abs) {
+    hi_abs = __double2hiint(eta) & 0x7fffffff;
+    return __hiloint2double(min(hi_abs, kHi700), __double2loint(eta));
+}
+
+// k ~ dbin(logistic(eta), n)  (dbern: n = 1), the theta-dependent part of the log-density and d/d eta:
+//   k log p + m log(1 - p),  m = n - k,  log p = -(max(-eta, 0) + l1p),  log(1 - p) = -(max(eta, 0) + l1p),
+//   max(x, 0) = (|x| + x) / 2   =>   = -[ n (|eta| / 2 + l1p) + (n / 2 - k) eta ]          (no select)
+//   p = 1/2 + copysign(1 / (1 + e) - 1/2, eta)   =>   d/d eta = k - n p = -[(n / 2 - k) + n copysign(...)]
+// The data-only constant -logbeta(k+1, m+1) - log(n+1) is added once per plate (obs_const).  `sat` collects (integer
+// pipe) whether |eta| reached the range where the reference's logistic saturates to exactly 0 / 1; the caller then runs
+// logit_tail_is_inf on the block -- rarely -- to reproduce the reference's -Inf there.
+__device__ __forceinline__ void binomial_logit(double eta, double k, double n, double& lp, double& deta, int& sat) {
+    int hi_abs;
+    const double ax = abs_clamped(eta, hi_abs);
+    const SoftplusParts sp = softplus_parts(ax);
+    const double hd = fma(0.5, n, -k);
+    lp = fma(-n, fma(0.5, fabs(eta), sp.l1p), lp);
+    lp = fma(-hd, eta, lp);
+    const double cq = copysign(sp.inv - 0.5, eta);
+    deta = -fma(n, cq, hd);
+    sat |= (hi_abs >= kHiLogisticUpper) ? 1 : 0;
+}
+// LogExpFunctions.logistic returns exactly 1 above kLogisticUpper and exactly 0 below kLogisticLower: the binomial
+// log-density is then -Inf unless the corresponding count is zero
+__device__ __forceinline__ bool logit_tail_is_inf(double eta, double k, double n) {
+    return (eta > kLogisticUpper && n - k != 0.0) || (eta < kLogisticLower && k != 0.0);
 }
 
 // ---- bijectors: slot y -> value x, logjac lj, dx/dy, d(lj)/dy

@@ -37,6 +37,9 @@ constexpr int BLOCK = 128;                       // chains per CTA
 struct ArgS {  // structural half of an argument
     int kind;  // jbugs_arg_kind
     int id;    // GVAL: plate-local gref index; LOCAL: local index
+    int soff;  // DATA_*: offset (in doubles) of the stream inside the staged chunk / J region.  Part of the SHAPE: a static
+               // spec with a static inner extent knows its stream layout at compile time, so shared-memory addresses of
+               // the data become immediates (one base register + constants instead of one address computation per stream)
 };
 struct ArgV {  // value half
     const double* ptr;  // DATA_*: device array (host-side bookkeeping / obs_const kernel)
@@ -60,6 +63,7 @@ struct Stream {
 struct LocalS {
     int level, transform, family, has_idx;
     ArgS args[3];
+    int mu_zero;  // args[0] is the literal constant 0.0 (part of the shape: static specs may assume it)
 };
 struct LocalV {
     long long base, si, sj;
@@ -69,6 +73,14 @@ struct LocalV {
     ArgV args[3];
 };
 
+// one op of an expression tape on the device (jbugs_xop with its leaf resolved: plate-local gref index, stream offset)
+struct XOpDev {
+    int op;
+    unsigned short a, b, c, pad;
+    int kind, id, soff, pad2;  // leaf
+    double value;
+};
+
 struct PlateShape {
     int kg, nl, has_off, n_gref;
     int family, eta_arg, has_obs, n_link;
@@ -76,6 +88,7 @@ struct PlateShape {
     ArgS cov[MAX_TERMS];
     ArgS y, aux[3];
     LocalS loc[MAX_LOC];
+    int n_x;  // > 0: expression plate (has_obs == 2): the predictor is the tape PlateVals::xtape, aux[q] may be XVAL
 };
 
 struct PlateVals {
@@ -90,6 +103,7 @@ struct PlateVals {
     int j_doubles;     // size of the J region (J streams: T each), rounded up to even
     int bulk_ok;       // streams are 16-byte aligned for every even group index: chunks may use the TMA path
     Stream streams[MAX_STREAMS];
+    const XOpDev* xtape;  // expression plates: sh.n_x ops in device memory (read-only, identical for every thread)
 };
 
 struct PlateParams {
@@ -116,7 +130,10 @@ struct DynSpec {
     static constexpr int T_STATIC = 0;  // inner extent read at run time
     static constexpr bool PREFETCH = false;
     static constexpr bool OBS_LOCALS = true;  // unknown at compile time
+    static constexpr bool SOFF = false;       // stream offsets come from the kernel parameters
+    static constexpr bool XTAPE = false;      // (XSpec: the instantiation that interprets expression tapes)
     __device__ __forceinline__ bool prior_fused(int) const { return false; }
+    __device__ __forceinline__ bool prior_mu_zero(int) const { return false; }
     const PlateShape& s;
     __device__ __forceinline__ explicit DynSpec(const PlateShape& sh) : s(sh) {}
     __device__ __forceinline__ int kg() const { return s.kg; }
@@ -138,6 +155,14 @@ struct DynSpec {
     __device__ __forceinline__ int loc_family(int l) const { return s.loc[l].family; }
     __device__ __forceinline__ int loc_has_idx(int l) const { return s.loc[l].has_idx; }
     __device__ __forceinline__ ArgS loc_arg(int l, int q) const { return s.loc[l].args[q]; }
+};
+
+// The interpreter for expression plates: DynSpec plus the tape sweep in observe() (its own instantiation, so that the
+// per-thread value / adjoint arrays of the tape -- 2 KB of local memory -- are not part of every interpreter launch)
+struct XSpec : DynSpec {
+    static constexpr bool XTAPE = true;
+    __device__ __forceinline__ explicit XSpec(const PlateShape& sh) : DynSpec(sh) {}
+    __device__ __forceinline__ int n_x() const { return s.n_x; }
 };
 
 // fused observation paths (family x link pairs with a hand-derived forward+reverse)
@@ -162,12 +187,18 @@ struct StaticSpec {
         return false;
     }
     static constexpr bool OBS_LOCALS = obs_locals_();  // the plate has observation-level (i, j) locals
+    // static inner extent: the layout of the staged streams follows from the shape alone (canon_soffs, mirrored by
+    // build_plate and checked by shape_equal), so stream offsets are compile-time constants
+    static constexpr bool SOFF = Desc::T_STATIC > 0;
+    static constexpr bool XTAPE = false;
     // a dnorm prior whose arguments do not vary over the plate keeps sufficient statistics
     __device__ __forceinline__ constexpr bool prior_fused(int l) const {
         return Desc::sh().loc[l].family == JBUGS_FAM_NORMAL &&
                (Desc::sh().loc[l].args[0].kind == JBUGS_ARG_GVAL || Desc::sh().loc[l].args[0].kind == JBUGS_ARG_CONST) &&
                (Desc::sh().loc[l].args[1].kind == JBUGS_ARG_GVAL || Desc::sh().loc[l].args[1].kind == JBUGS_ARG_CONST);
     }
+    // ... and its mean is the literal 0 (the shape records it: LocalS::mu_zero, set by build_plate from the plan)
+    __device__ __forceinline__ constexpr bool prior_mu_zero(int l) const { return Desc::sh().loc[l].mu_zero != 0; }
     __device__ __forceinline__ explicit StaticSpec(const PlateShape&) {}
     __device__ __forceinline__ constexpr int kg() const { return Desc::sh().kg; }
     __device__ __forceinline__ constexpr int nl() const { return Desc::sh().nl; }
@@ -215,6 +246,7 @@ struct ChainState {
     // dgamma(a, b) priors of locals whose arguments do not vary over the plate: lgamma(a), digamma(a), log(b) are
     // computed once per chain instead of once per group
     double pre_lg[MAX_LOC], pre_dg[MAX_LOC], pre_lb[MAX_LOC];
+    int sat;  // logit paths: an |eta| of the current block reached the range where the reference's logistic saturates
 };
 
 __device__ __forceinline__ bool arg_invariant(ArgS s) {
@@ -227,16 +259,18 @@ struct StageView {
     const double* jreg;   // J region
 };
 
-// g = group index inside the staged chunk, j = inner index
+// g = group index inside the staged chunk, j = inner index.  SS: take the stream offset from the (compile-time) shape
+template <bool SS = false>
 __device__ __forceinline__ double arg_value(ArgS s, const ArgV& v, const ChainState& st, const StageView& sv, int g, int j) {
+    const int soff = SS ? s.soff : v.soff;
     switch (s.kind) {
     case JBUGS_ARG_CONST: return v.value;
     case JBUGS_ARG_ONE: return 1.0;
     case JBUGS_ARG_GVAL: return pick(st.gv, s.id);
     case JBUGS_ARG_LOCAL: return pick(st.lx, s.id);
-    case JBUGS_ARG_DATA_I: return sv.chunk[v.soff + g];
-    case JBUGS_ARG_DATA_J: return sv.jreg[v.soff + j];
-    case JBUGS_ARG_DATA_IJ: return sv.chunk[v.soff + j * STAGE_G + g];
+    case JBUGS_ARG_DATA_I: return sv.chunk[soff + g];
+    case JBUGS_ARG_DATA_J: return sv.jreg[soff + j];
+    case JBUGS_ARG_DATA_IJ: return sv.chunk[soff + j * STAGE_G + g];
     default: return 0.0;
     }
 }

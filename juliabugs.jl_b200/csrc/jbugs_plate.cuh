@@ -10,6 +10,10 @@
 //     gradient rows are stored.
 #pragma once
 
+#ifndef JB_L2PF
+#define JB_L2PF 0
+#endif
+
 namespace jbugs {
 
 // Per-thread accumulators of the fused (sufficient-statistic) paths.  Unused members are dead code
@@ -19,7 +23,7 @@ struct FusedAcc {
     double sg[MAX_GT];    // sum r * cov_t for the global terms               (normal / identity)
     double pss[MAX_LOC];  // sum (x_l - mu_l)^2 over the tile                 (normal prior, invariant args)
     double ps[MAX_LOC];   // sum (x_l - mu_l)
-    double cnt[MAX_LOC];  // number of instances of local l in the tile
+    double pd[MAX_LOC];   // x_l - mu_l of the instance being evaluated (its prior adjoint is applied at the store)
 };
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
@@ -121,27 +125,48 @@ __device__ __forceinline__ long long local_slot(const S& sp, const PlateVals& V,
 template <class S>
 __device__ __forceinline__ void local_enter(const S& sp, const PlateVals& V, int l, double raw, ChainState& st,
                                             double (&ldx)[MAX_LOC], double (&ldlj)[MAX_LOC], double& lp) {
+    // -0.0, the additive identity for EVERY double (x + 0.0 turns -0.0 into +0.0, so the compiler must keep that add;
+    // x + -0.0 is x, and it folds): the first contribution to an accumulator then costs no FP64 instruction
+    st.la[l] = -0.0;
+    if (sp.loc_transform(l) == JBUGS_TR_IDENTITY) {
+        // (written out: `lp += 0.0`, `la * 1.0 + 0.0` are not foldable under IEEE rules and would each cost an FP64 slot)
+        st.lx[l] = raw;
+        ldx[l] = 1.0;
+        ldlj[l] = 0.0;
+        return;
+    }
     const TrOut t = transform_eval(sp.loc_transform(l), V.loc[l].lb, V.loc[l].ub, raw);
     st.lx[l] = t.x;
-    st.la[l] = 0.0;
     ldx[l] = t.dxdy;
     ldlj[l] = t.dljdy;
     lp += t.lj;
+}
+
+// gradient of the slot of local l: (d logp / d x) * dx/dy + d logjac / dy
+template <class S>
+__device__ __forceinline__ double local_grad(const S& sp, int l, const ChainState& st, const double (&ldx)[MAX_LOC],
+                                             const double (&ldlj)[MAX_LOC]) {
+    return sp.loc_transform(l) == JBUGS_TR_IDENTITY ? st.la[l] : fma(st.la[l], ldx[l], ldlj[l]);
 }
 
 template <class S>
 __device__ __forceinline__ bool local_prior(const S& sp, const PlateVals& V, int l, const StageView& sv, int g, int j,
                                             ChainState& st, FusedAcc& fa, double& lp) {
     const LocalV& L = V.loc[l];
-    const double a0 = arg_value(sp.loc_arg(l, 0), L.args[0], st, sv, g, j);
-    const double a1 = arg_value(sp.loc_arg(l, 1), L.args[1], st, sv, g, j);
+    const double a0 = arg_value<S::SOFF>(sp.loc_arg(l, 0), L.args[0], st, sv, g, j);
+    const double a1 = arg_value<S::SOFF>(sp.loc_arg(l, 1), L.args[1], st, sv, g, j);
     if (sp.prior_fused(l)) {
-        // dnorm(mu, tau) with chain-invariant arguments: keep sufficient statistics, expand at tile end
+        // dnorm(mu, tau) with chain-invariant arguments: keep sufficient statistics, expand at tile end.  The adjoint
+        // -tau (x - mu) is applied where the gradient is stored (eval_groups: one fma with the likelihood's part).
+        if (sp.prior_mu_zero(l)) {  // mu is the literal 0 (random effects): sum x^2 is all that is needed
+            fa.pss[l] = fma(st.lx[l], st.lx[l], fa.pss[l]);
+            fa.pd[l] = st.lx[l];
+            return false;
+        }
         const double d = st.lx[l] - a0;
         fa.pss[l] = fma(d, d, fa.pss[l]);
-        fa.ps[l] += d;
-        fa.cnt[l] += 1.0;
-        st.la[l] -= a1 * d;
+        if (sp.loc_arg(l, 0).kind == JBUGS_ARG_GVAL) fa.ps[l] += d;  // only the adjoint of a parameter mean needs it
+        fa.pd[l] = d;
         return false;
     }
     if (sp.loc_family(l) == JBUGS_FAM_GAMMA && arg_invariant(sp.loc_arg(l, 0)) && arg_invariant(sp.loc_arg(l, 1))) {
@@ -162,28 +187,113 @@ __device__ __forceinline__ bool local_prior(const S& sp, const PlateVals& V, int
     return bad;
 }
 
-// one observation: linear predictor, inverse link, family; accumulates adjoints
+// linear predictor of observation (g, j): eta = sum_t coef_t * cov_t (+ offset); cv receives the covariate values
 template <class S>
-__device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const StageView& sv, int g, int j,
-                                        ChainState& st, FusedAcc& fa, double (&sl)[MAX_LOC], double& lp) {
-    double cv[MAX_TERMS];
-    double eta = 0.0;
-    bool bad = false;
-    if (sp.has_w() && arg_value(sp.aux(2), V.aux[2], st, sv, g, j) == 0.0) return false;  // padded cell: no observation
+__device__ __forceinline__ double predictor(const S& sp, const PlateVals& V, const StageView& sv, int g, int j,
+                                            const ChainState& st, double (&cv)[MAX_TERMS]) {
+    double eta = -0.0;  // (additive identity that folds, see local_enter)
 #pragma unroll
     for (int t = 0; t < MAX_GT; ++t)
         if (t < sp.kg()) {
-            cv[t] = arg_value(sp.cov(t), V.cov[t], st, sv, g, j);
+            cv[t] = arg_value<S::SOFF>(sp.cov(t), V.cov[t], st, sv, g, j);
             eta = fma(st.gv[t], cv[t], eta);
         }
 #pragma unroll
     for (int l = 0; l < MAX_LOC; ++l)
         if (l < sp.nl()) {
-            cv[MAX_GT + l] = arg_value(sp.cov(sp.kg() + l), V.cov[sp.kg() + l], st, sv, g, j);
+            cv[MAX_GT + l] = arg_value<S::SOFF>(sp.cov(sp.kg() + l), V.cov[sp.kg() + l], st, sv, g, j);
             eta = fma(st.lx[l], cv[MAX_GT + l], eta);
         }
-    if (sp.has_off()) eta += arg_value(sp.cov(sp.kg() + sp.nl()), V.cov[sp.kg() + sp.nl()], st, sv, g, j);
+    if (sp.has_off()) eta += arg_value<S::SOFF>(sp.cov(sp.kg() + sp.nl()), V.cov[sp.kg() + sp.nl()], st, sv, g, j);
+    return eta;
+}
+
+// one observation of an expression plate: forward sweep over the tape, the family, reverse sweep back to the leaves
+// (the composed node functions of the observation's logical parents, compiler_pass.jl:751-814, in SSA form)
+template <class S>
+__device__ __noinline__ bool observe_tape(const S& sp, const PlateVals& V, const StageView& sv, int g, int j,
+                                          ChainState& st, double& lp) {
+    double v[JBUGS_MAX_XOPS], w[JBUGS_MAX_XOPS], d1[JBUGS_MAX_XOPS], d2[JBUGS_MAX_XOPS];
+    const int nx = sp.n_x();
+    bool bad = false;
+    for (int k = 0; k < nx; ++k) {
+        const XOpDev o = V.xtape[k];
+        w[k] = 0.0; d1[k] = 0.0; d2[k] = 0.0;
+        if (o.op == JBUGS_OP_LEAF) {
+            switch (o.kind) {
+            case JBUGS_ARG_CONST: v[k] = o.value; break;
+            case JBUGS_ARG_ONE: v[k] = 1.0; break;
+            case JBUGS_ARG_GVAL: v[k] = pick(st.gv, o.id); break;
+            case JBUGS_ARG_GVEC_J: v[k] = pick(st.gv, o.id + j); break;
+            case JBUGS_ARG_LOCAL: v[k] = pick(st.lx, o.id); break;
+            case JBUGS_ARG_DATA_I: v[k] = sv.chunk[o.soff + g]; break;
+            case JBUGS_ARG_DATA_J: v[k] = sv.jreg[o.soff + j]; break;
+            case JBUGS_ARG_DATA_IJ: v[k] = sv.chunk[o.soff + j * STAGE_G + g]; break;
+            default: v[k] = dev_nan(); break;
+            }
+        } else if (o.op == JBUGS_OP_SELECT) {
+            v[k] = v[o.a] != 0.0 ? v[o.b] : v[o.c];
+        } else if (o.op < 16) {
+            bad |= unary_op(o.op, v[o.a], v[k], d1[k]);
+        } else {
+            const double a = v[o.a], b = v[o.b];
+            switch (o.op) {
+            case JBUGS_OP_ADD: v[k] = a + b; d1[k] = 1.0; d2[k] = 1.0; break;
+            case JBUGS_OP_SUB: v[k] = a - b; d1[k] = 1.0; d2[k] = -1.0; break;
+            case JBUGS_OP_MUL: v[k] = a * b; d1[k] = b; d2[k] = a; break;
+            case JBUGS_OP_DIV: v[k] = a / b; d1[k] = 1.0 / b; d2[k] = -a / (b * b); break;
+            default:  // POW
+                v[k] = pow(a, b); d1[k] = b * pow(a, b - 1.0); d2[k] = a > 0.0 ? v[k] * log(a) : 0.0;
+                bad |= a < 0.0 && b != floor(b);
+                break;
+            }
+        }
+    }
+    double a[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const ArgS s = sp.aux(q);
+        a[q] = s.kind == JBUGS_ARG_XVAL ? v[s.id] : arg_value(s, V.aux[q], st, sv, g, j);
+    }
     const double yv = arg_value(sp.y(), V.y, st, sv, g, j);
+    FamOut o;
+    bad |= fam_eval(sp.family(), yv, a[0], a[1], o, V.aux[2].value);
+    lp += o.lp;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const ArgS s = sp.aux(q);
+        const double da = q == 0 ? o.da0 : o.da1;
+        if (s.kind == JBUGS_ARG_XVAL) w[s.id] += da;
+        else arg_adjoint(s, st, da);
+    }
+    for (int k = nx - 1; k >= 0; --k) {
+        const double wk = w[k];
+        if (wk == 0.0) continue;
+        const XOpDev o = V.xtape[k];
+        if (o.op == JBUGS_OP_LEAF) {
+            if (o.kind == JBUGS_ARG_GVAL) bump(st.ga, o.id, wk);
+            else if (o.kind == JBUGS_ARG_GVEC_J) bump(st.ga, o.id + j, wk);
+            else if (o.kind == JBUGS_ARG_LOCAL) bump(st.la, o.id, wk);
+        } else if (o.op == JBUGS_OP_SELECT) {
+            w[v[o.a] != 0.0 ? o.b : o.c] += wk;
+        } else {
+            w[o.a] += wk * d1[k];
+            if (o.op >= 16) w[o.b] += wk * d2[k];
+        }
+    }
+    return bad;
+}
+
+// one observation: linear predictor, inverse link, family; accumulates adjoints
+template <class S>
+__device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const StageView& sv, int g, int j,
+                                        ChainState& st, FusedAcc& fa, double (&sl)[MAX_LOC], double& lp) {
+    double cv[MAX_TERMS];
+    bool bad = false;
+    if (sp.has_w() && arg_value<S::SOFF>(sp.aux(2), V.aux[2], st, sv, g, j) == 0.0) return false;  // padded cell: no observation
+    if constexpr (S::XTAPE) return observe_tape(sp, V, sv, g, j, st, lp);
+    const double eta = predictor(sp, V, sv, g, j, st, cv);
+    const double yv = arg_value<S::SOFF>(sp.y(), V.y, st, sv, g, j);
 
     if (S::FUSED == FUSED_NORMAL_IDENTITY) {
         // y ~ dnorm(eta, tau), tau chain-invariant: d/d eta = tau * r; tau is factored out of every sum
@@ -200,23 +310,10 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
 
     double deta;
     if (S::FUSED == FUSED_BINOMIAL_LOGIT || S::FUSED == FUSED_BERNOULLI_LOGIT) {
-        // k ~ dbin(logistic(eta), n): log p = -softplus(-eta), log(1-p) = -softplus(eta); one exp, one log1p.
-        // The data-only constant -logbeta(k+1, n-k+1) - log(n+1) is added once per plate (obs_const).
-        const double n = S::FUSED == FUSED_BERNOULLI_LOGIT ? 1.0 : arg_value(sp.aux(1), V.aux[1], st, sv, g, j);
-        const double ax = fabs(eta);
-        const SoftplusParts sp3 = softplus_parts(ax);
-        const bool up = eta >= 0.0;
-        const double p = up ? sp3.inv : sp3.e * sp3.inv;             // logistic(eta)
-        const double m = n - yv;
-        // k log p + m log(1 - p), with log p = -(max(-eta, 0) + l1p) and log(1 - p) = -(max(eta, 0) + l1p):
-        //   = -(eta >= 0 ? m : k) |eta| - n l1p          (one select, one multiply, one fma)
-        double nll = fma(up ? m : yv, ax, n * sp3.l1p);  // minus the log-likelihood term
-        if (ax > kLogisticUpper) {  // saturated tails (rare): LogExpFunctions.logistic returns exactly 0 / 1 there
-            if (eta > kLogisticUpper && m != 0.0) nll = dev_inf();
-            if (eta < kLogisticLower && yv != 0.0) nll = dev_inf();
-        }
-        lp -= nll;
-        deta = yv - n * p;
+        // k ~ dbin(logistic(eta), n): branch-free, selects and range tests on the integer pipe (binomial_logit);
+        // the saturated tails are fixed up once per unrolled block of groups (eval_groups), not per observation
+        const double n = S::FUSED == FUSED_BERNOULLI_LOGIT ? 1.0 : arg_value<S::SOFF>(sp.aux(1), V.aux[1], st, sv, g, j);
+        binomial_logit(eta, yv, n, lp, deta, st.sat);
     } else if (S::FUSED == FUSED_POISSON_LOG) {
         // k ~ dpois(exp(eta)): k * eta - exp(eta); -lgamma(k+1) goes to obs_const
         const double lam = exp(eta);
@@ -239,7 +336,7 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
             lp += xlogy(yv, v) - v;
             deta = ((yv == 0.0 ? 0.0 : yv / v) - 1.0) * dv;
         } else {
-            const double n = S::FUSED == FUSED_BERNOULLI_LINK ? 1.0 : arg_value(sp.aux(1), V.aux[1], st, sv, g, j);
+            const double n = S::FUSED == FUSED_BERNOULLI_LINK ? 1.0 : arg_value<S::SOFF>(sp.aux(1), V.aux[1], st, sv, g, j);
             const double m = n - yv;
             bad |= !(v >= 0.0 && v <= 1.0);
             lp += xlogy(yv, v) + xlog1py(m, -v);
@@ -256,8 +353,8 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
                 dv *= d;
             }
         const int ea = sp.eta_arg();
-        const double a0 = ea == 0 ? v : arg_value(sp.aux(0), V.aux[0], st, sv, g, j);
-        const double a1 = ea == 1 ? v : arg_value(sp.aux(1), V.aux[1], st, sv, g, j);
+        const double a0 = ea == 0 ? v : arg_value<S::SOFF>(sp.aux(0), V.aux[0], st, sv, g, j);
+        const double a1 = ea == 1 ? v : arg_value<S::SOFF>(sp.aux(1), V.aux[1], st, sv, g, j);
         FamOut o;
         bad |= fam_eval(sp.family(), yv, a0, a1, o, V.aux[2].value);
         lp += o.lp;
@@ -272,6 +369,13 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
     for (int l = 0; l < MAX_LOC; ++l)
         if (l < sp.nl()) st.la[l] = fma(deta, cv[MAX_GT + l], st.la[l]);
     return bad;
+}
+
+// precision of a fused dnorm prior (chain-invariant: a referenced global value or a literal)
+template <class S>
+__device__ __forceinline__ double prior_tau(const S& sp, const PlateVals& V, int l, const ChainState& st) {
+    const ArgS a1 = sp.loc_arg(l, 1);
+    return a1.kind == JBUGS_ARG_GVAL ? pick(st.gv, a1.id) : (a1.kind == JBUGS_ARG_ONE ? 1.0 : V.loc[l].args[1].value);
 }
 
 // raw theta values (and row offsets) of the group-level locals of UU consecutive groups; when the inner extent is
@@ -310,6 +414,11 @@ __device__ __forceinline__ void load_groups(const S& sp, const PlateVals& V, lon
                     pos[l] += V.loc[l].step_i;
                 }
                 gl.raw[u][l] = th[gl.off[u][l]];
+#if JB_L2PF > 0
+                // (A/B) pull the row JB_L2PF groups ahead into L2: no register cost, the later load is an L2 hit
+                if (!sp.loc_has_idx(l))
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(th + gl.off[u][l] + (long long)JB_L2PF * V.loc[l].step_i));
+#endif
             }
             if (TS > 0 && l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS && !sp.loc_has_idx(l)) {
                 gl.obase[u][l] = pos[l];
@@ -336,7 +445,7 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
         double ldx[MAX_LOC], ldlj[MAX_LOC], sl[MAX_LOC];
 #pragma unroll
         for (int l = 0; l < MAX_LOC; ++l) {
-            sl[l] = 0.0;
+            sl[l] = -0.0;
             if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) local_enter(sp, V, l, raw[u][l], st, ldx, ldlj, lp);
         }
 #pragma unroll
@@ -370,9 +479,10 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
                 if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) {
                     if (S::FUSED == FUSED_NORMAL_IDENTITY) {
                         st.la[l] = fma(obs_tau, sl[l], st.la[l]);
-                        sl[l] = 0.0;
+                        sl[l] = -0.0;
                     }
-                    if (store) gr[ooff[l]] = fma(st.la[l], ldx[l], ldlj[l]);
+                    if (sp.prior_fused(l)) st.la[l] = fma(-prior_tau(sp, V, l, st), fa.pd[l], st.la[l]);
+                    if (store) gr[ooff[l]] = local_grad(sp, l, st, ldx, ldlj);
                 }
         }
 #pragma unroll
@@ -381,7 +491,40 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
                 pos[l] += V.loc[l].step_i;
             if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) {
                 if (S::FUSED == FUSED_NORMAL_IDENTITY) st.la[l] = fma(obs_tau, sl[l], st.la[l]);
-                if (store) gr[off[u][l]] = fma(st.la[l], ldx[l], ldlj[l]);
+                if (sp.prior_fused(l)) st.la[l] = fma(-prior_tau(sp, V, l, st), fa.pd[l], st.la[l]);
+                if (store) gr[off[u][l]] = local_grad(sp, l, st, ldx, ldlj);
+            }
+        }
+    }
+    if ((S::FUSED == FUSED_BINOMIAL_LOGIT || S::FUSED == FUSED_BERNOULLI_LOGIT) && __builtin_expect(st.sat != 0, 0)) {
+        // rare: some |eta| of this block lies where the reference's logistic is exactly 0 or 1.  Walk the block again,
+        // recompute each linear predictor (same arithmetic, same bits) and give the observation the reference's -Inf
+        // where it applies; the finite value the hot path added is swallowed by it.
+        st.sat = 0;
+#pragma unroll
+        for (int u = 0; u < UU; ++u) {
+            double d0[MAX_LOC], d1[MAX_LOC], dummy = 0.0;
+#pragma unroll
+            for (int l = 0; l < MAX_LOC; ++l)
+                if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) local_enter(sp, V, l, raw[u][l], st, d0, d1, dummy);
+            long long opos[MAX_LOC];
+#pragma unroll
+            for (int l = 0; l < MAX_LOC; ++l)  // pos[] has moved past the block: group u sits (UU - u) steps back
+                opos[l] = (TS > 0 && !sp.loc_has_idx(l)) ? gl.obase[u][l] : pos[l] - (long long)(UU - u) * V.loc[l].step_i;
+#pragma unroll 1
+            for (int j = 0; j < T; ++j) {
+#pragma unroll
+                for (int l = 0; l < MAX_LOC; ++l)
+                    if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) {
+                        const long long o = sp.loc_has_idx(l) ? local_slot(sp, V, l, i + u, j) * ld : opos[l] + j * V.loc[l].step_j;
+                        local_enter(sp, V, l, th[o], st, d0, d1, dummy);
+                    }
+                if (sp.has_w() && arg_value<S::SOFF>(sp.aux(2), V.aux[2], st, sv, g + u, j) == 0.0) continue;
+                double cv[MAX_TERMS];
+                const double eta = predictor(sp, V, sv, g + u, j, st, cv);
+                const double yv = arg_value<S::SOFF>(sp.y(), V.y, st, sv, g + u, j);
+                const double n = S::FUSED == FUSED_BERNOULLI_LOGIT ? 1.0 : arg_value<S::SOFF>(sp.aux(1), V.aux[1], st, sv, g + u, j);
+                if (logit_tail_is_inf(eta, yv, n)) lp = -dev_inf();
             }
         }
     }
@@ -462,7 +605,8 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
 #pragma unroll
     for (int t = 0; t < MAX_GT; ++t) fa.sg[t] = 0.0;
 #pragma unroll
-    for (int l = 0; l < MAX_LOC; ++l) fa.pss[l] = fa.ps[l] = fa.cnt[l] = 0.0;
+    for (int l = 0; l < MAX_LOC; ++l) fa.pss[l] = fa.ps[l] = fa.pd[l] = 0.0;
+    st.sat = 0;
 
     double lp = 0.0;
     bool bad = false;
@@ -546,11 +690,13 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
     for (int l = 0; l < MAX_LOC; ++l)
         if (l < sp.nl() && sp.prior_fused(l)) {
             const ArgS a0 = sp.loc_arg(l, 0), a1 = sp.loc_arg(l, 1);
-            const double tau = a1.kind == JBUGS_ARG_GVAL ? pick(st.gv, a1.id) : V.loc[l].args[1].value;
+            const double tau = prior_tau(sp, V, l, st);
+            // instances of local l in this tile (a padded cell of a gathered plate still holds a parameter)
+            const double cnt = (double)((ie - ib) * (sp.loc_level(l) == JBUGS_LEVEL_OBS ? V.T : 1));
             bad |= tau < 0.0;
-            lp += fa.cnt[l] * (0.5 * log(tau) - 0.5 * kLog2Pi) - 0.5 * tau * fa.pss[l];
+            lp += cnt * (0.5 * log(tau) - 0.5 * kLog2Pi) - 0.5 * tau * fa.pss[l];
             if (a0.kind == JBUGS_ARG_GVAL) bump(st.ga, a0.id, tau * fa.ps[l]);
-            if (a1.kind == JBUGS_ARG_GVAL) bump(st.ga, a1.id, fa.cnt[l] * 0.5 / tau - 0.5 * fa.pss[l]);
+            if (a1.kind == JBUGS_ARG_GVAL) bump(st.ga, a1.id, cnt * 0.5 / tau - 0.5 * fa.pss[l]);
         }
 
     if (!active) return;

@@ -26,6 +26,7 @@ typedef cudaError_t (*plate_launch_fn)(JBUGS_LAUNCH_PARAMS);
 
 // defined in spec_dyn.cu / spec_rats.cu / spec_glm.cu / spec_epil.cu
 cudaError_t launch_dyn(JBUGS_LAUNCH_PARAMS);
+cudaError_t launch_x(JBUGS_LAUNCH_PARAMS);  // expression-tape interpreter (XSpec)
 cudaError_t launch_rats_t5(JBUGS_LAUNCH_PARAMS);
 cudaError_t launch_rats(JBUGS_LAUNCH_PARAMS);
 cudaError_t launch_seeds(JBUGS_LAUNCH_PARAMS);
@@ -55,8 +56,10 @@ static const SpecEntry g_specs[] = {
     {"epil_poisson_log_T4", &launch_epil_t4, &EpilDesc<4>::matches, EpilDesc<4>::FUSED},
     {"epil_poisson_log", &launch_epil, &EpilDesc<0>::matches, EpilDesc<0>::FUSED},
     {"pumps_poisson_gamma", &launch_pumps, &PumpsDesc::matches, PumpsDesc::FUSED},
+    {"expression_tape", &launch_x, &match_never, FUSED_NONE},
 };
 static const int g_num_specs = (int)(sizeof(g_specs) / sizeof(g_specs[0]));
+static const int g_xspec = g_num_specs - 1;  // the tape interpreter: selected by the plate kind, never by shape
 
 static int select_spec(const PlateShape& sh, long long T) {
     for (int k = 1; k < g_num_specs; ++k)

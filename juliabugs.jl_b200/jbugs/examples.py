@@ -310,7 +310,101 @@ model {
 BEETLES_DATA = {"x": [1.6907, 1.7242, 1.7552, 1.7842, 1.8113, 1.8369, 1.8610, 1.8839],
                 "n": [59, 60, 62, 56, 63, 59, 62, 60], "r": [6, 13, 18, 28, 52, 53, 61, 60], "N": 8}
 
+# ---- models whose predictor is not linear in the parameters: lowered to expression plates ---------------------------
+# Dugongs (BUGS examples vol. 2): non-linear growth curve, no random effects
+DUGONGS = """
+model {
+    for (i in 1:N) {
+        Y[i] ~ dnorm(mu[i], tau)
+        mu[i] <- alpha - beta * pow(gamma, x[i])
+    }
+    alpha ~ dunif(0, 100)
+    beta ~ dunif(0, 100)
+    gamma ~ dunif(0.5, 1.0)
+    tau ~ dgamma(0.001, 0.001)
+    sigma <- 1 / sqrt(tau)
+    U3 <- logit(gamma)
+}
+"""
+
+# LSAT (vol. 1): Rasch model; the response patterns are expanded by a ragged data transformation
+LSAT = """
+model {
+    for (j in 1:culm[1]) {
+        for (k in 1:T) {
+            r[j, k] <- response[1, k]
+        }
+    }
+    for (i in 2:R) {
+        for (j in culm[i - 1] + 1:culm[i]) {
+            for (k in 1:T) {
+                r[j, k] <- response[i, k]
+            }
+        }
+    }
+    for (j in 1:N) {
+        for (k in 1:T) {
+            logit(p[j, k]) <- beta * theta[j] - alpha[k]
+            r[j, k] ~ dbern(p[j, k])
+        }
+        theta[j] ~ dnorm(0, 1)
+    }
+    for (k in 1:T) {
+        alpha[k] ~ dnorm(0, 0.0001)
+        a[k] <- alpha[k] - mean(alpha[])
+    }
+    beta ~ dunif(0, 1000)
+}
+"""
+
+# Air (vol. 2): measurement error in the covariate of a logistic regression -- a latent covariate X[j] multiplies a
+# coefficient
+AIR = """
+model {
+    for (j in 1:J) {
+        y[j] ~ dbin(p[j], n[j])
+        logit(p[j]) <- theta[1] + theta[2] * X[j]
+        X[j] ~ dnorm(mu[j], tau)
+        mu[j] <- alpha + beta * Z[j]
+    }
+    theta[1] ~ dnorm(0.0, 0.001)
+    theta[2] ~ dnorm(0.0, 0.001)
+}
+"""
+
+# Leuk (vol. 1): Cox regression as a Poisson counting process with independent-increment gamma hazards
+LEUK = """
+model {
+    for (i in 1:N) {
+        for (j in 1:T) {
+            Y[i, j] <- step(obs.t[i] - t[j] + eps)
+            dN[i, j] <- Y[i, j] * step(t[j + 1] - obs.t[i] - eps) * fail[i]
+        }
+    }
+    for (j in 1:T) {
+        for (i in 1:N) {
+            dN[i, j] ~ dpois(Idt[i, j])
+            Idt[i, j] <- Y[i, j] * exp(beta * Z[i]) * dL0[j]
+        }
+        dL0[j] ~ dgamma(mu[j], c)
+        mu[j] <- dL0.star[j] * c
+        S.treat[j] <- pow(exp(-sum(dL0[1:j])), exp(beta * -0.5))
+        S.placebo[j] <- pow(exp(-sum(dL0[1:j])), exp(beta * 0.5))
+    }
+    c <- 0.001
+    r <- 0.1
+    for (j in 1:T) {
+        dL0.star[j] <- r * (t[j + 1] - t[j])
+    }
+    beta ~ dnorm(0.0, 0.000001)
+}
+"""
+
 MODELS = {
+    "dugongs": DUGONGS,
+    "lsat": LSAT,
+    "air": AIR,
+    "leuk": LEUK,
     "stacks": STACKS,
     "salm": SALM,
     "equiv": EQUIV,

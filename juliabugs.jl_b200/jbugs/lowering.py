@@ -49,6 +49,9 @@ class Stmt:
     extents: Tuple[Tuple[int, int], ...] = ()      # evaluated (lo, hi)
     kind: str = ""                 # 'tdata' | 'obs' | 'param' | 'logical'
     is_gq: bool = False
+    ragged: bool = False           # a loop bound depends on an enclosing loop variable (`for k in 1:ncat[j]-1`): the
+                                   # statement has no rectangular domain; it can be folded pointwise (data) or inlined
+    obs_mask: object = None        # partially observed statement: boolean array over the loop domain (True = observed)
 
     @property
     def name(self):
@@ -99,6 +102,7 @@ class DataEval:
 
     def __init__(self, data: Dict[str, object]):
         self.data = data
+        self.lenient = False   # clamp out-of-range / missing subscripts (set while evaluating case-split leaves)
 
     def known(self, e, loop_vars=()) -> bool:
         return all((v in self.data) or (v in loop_vars) for v in free_vars(e))
@@ -137,7 +141,11 @@ class DataEval:
                     idx.append(slice(int(lo) - 1, int(hi)))
                 else:
                     v = self.ev(ie, lv)
-                    iv = np.asarray(v)
+                    iv = np.asarray(v, dtype=np.float64)
+                    if self.lenient:
+                        # a subscript computed from data of cells the value is not used for (the other branch of a
+                        # case split, a missing observation): keep it inside the array, the result is discarded
+                        iv = np.clip(np.nan_to_num(np.floor(iv), nan=1.0), 1, arr.shape[len(idx)])
                     if not np.all(iv == np.floor(iv)):
                         raise LoweringError("non-integer array index")
                     idx.append(iv.astype(np.int64) - 1 if iv.ndim else int(iv) - 1)
@@ -173,8 +181,12 @@ class DataEval:
                 return np.maximum(args[0], args[1])
             if e.fn == "min":
                 return np.minimum(args[0], args[1])
-            if e.fn == "equals":
+            if e.fn == "equals" or e.fn == "__eq__":
                 return (np.asarray(args[0]) == np.asarray(args[1])).astype(float)
+            if e.fn == "__le__":
+                return (np.asarray(args[0]) <= np.asarray(args[1])).astype(float)
+            if e.fn == "__and__":
+                return ((np.asarray(args[0]) != 0) & (np.asarray(args[1]) != 0)).astype(float)
             if e.fn == "phi":
                 from math import erfc, sqrt
                 return np.vectorize(lambda v: 0.5 * erfc(-v / sqrt(2.0)))(args[0])
@@ -261,13 +273,35 @@ class Lowering:
     def _bounds(self):
         for s in self.stmts:
             ext = []
+            outer = []
             for (var, lo, hi) in s.loops:
                 if not (self.de.known(lo) and self.de.known(hi)):
+                    if self.de.known(lo, outer) and self.de.known(hi, outer) and isinstance(s.node, Det):
+                        s.ragged = True   # bound depends on an enclosing loop variable: no rectangular domain
+                        break
                     raise LoweringError(f"loop bounds of '{var}' must depend on data only (rectangular plates)")
                 ext.append((int(self.de.ev(lo, {})), int(self.de.ev(hi, {}))))
+                outer.append(var)
+            if s.ragged:
+                s.extents = ()
+                continue
             s.extents = tuple(ext)
             if any(hi < lo for lo, hi in ext):
                 s.kind = "tdata"  # BUGS skips a loop whose lower bound exceeds its upper bound (compiler_pass.jl:21-27)
+
+    def _ragged_points(self, s: Stmt):
+        """the iteration points (dicts loop variable -> int) of a statement with ragged loop bounds, in program order"""
+        pts = [{}]
+        for (var, lo, hi) in s.loops:
+            nxt = []
+            for pt in pts:
+                lv = {k: np.int64(v) for k, v in pt.items()}
+                a, b = int(self.de.ev(lo, lv)), int(self.de.ev(hi, lv))
+                nxt.extend(dict(pt, **{var: q}) for q in range(a, b + 1))
+            pts = nxt
+            if len(pts) > 2_000_000:
+                raise LoweringError("ragged transformed-data statement with too many iterations")
+        return pts
 
     # ---- C. transformed data ------------------------------------------------------------------
     def _lhs_loopvars(self, s: Stmt):
@@ -284,6 +318,12 @@ class Lowering:
             changed = False
             for s in self.stmts:
                 if s.kind or not isinstance(s.node, Det):
+                    continue
+                if s.ragged:
+                    if self.de.known(s.node.rhs, s.loop_vars) and isinstance(s.node.lhs, Index):
+                        self._fold_ragged(s)
+                        s.kind = "tdata"
+                        changed = True
                     continue
                 if any(hi < lo for lo, hi in s.extents):
                     s.kind = "tdata"
@@ -315,6 +355,29 @@ class Lowering:
                 s.kind = "tdata"
                 changed = True
 
+    def _fold_ragged(self, s: Stmt):
+        """data-only statement inside loops whose bounds depend on outer loop variables (LSAT: `for j in culm[i-1]+1 :
+        culm[i]`): evaluated point by point over the ragged domain."""
+        lhs = s.node.lhs
+        pts = self._ragged_points(s)
+        if not pts:
+            return
+        rows = []
+        for pt in pts:
+            lv = {k: np.int64(v) for k, v in pt.items()}
+            rows.append(([int(self.de.ev(ie, lv)) for ie in lhs.idx], float(self.de.ev(s.node.rhs, lv))))
+        top = tuple(max(r[0][d] for r in rows) for d in range(len(lhs.idx)))
+        cur = self.data.get(lhs.name)
+        if cur is None or not isinstance(cur, np.ndarray):
+            cur = np.full(top, np.nan)
+        elif any(c < t for c, t in zip(cur.shape, top)):
+            new = np.full(tuple(max(c, t) for c, t in zip(cur.shape, top)), np.nan)
+            new[tuple(slice(0, c) for c in cur.shape)] = cur
+            cur = new
+        for idx, val in rows:
+            cur[tuple(i - 1 for i in idx)] = val
+        self.data[lhs.name] = cur
+
     def _fold_pointwise(self, s: Stmt):
         """slow path for data expressions with loop-dependent slices (e.g. running sums)."""
         if s.size > 200000:
@@ -336,6 +399,8 @@ class Lowering:
             if isinstance(s.node, Det):
                 s.kind = "logical"
                 continue
+            if s.ragged:
+                raise LoweringError(f"stochastic statement '{s.name}' in a loop with ragged bounds")
             nm = s.name
             if nm in self.data:
                 arr = self.data[nm]
@@ -343,13 +408,16 @@ class Lowering:
                     lv = _grids(s.extents, s.loop_vars)
                     lhs = s.node.lhs
                     sub = arr if isinstance(lhs, Var) else self.de.ev(lhs, lv)
-                    miss = np.isnan(sub)
+                    miss = np.isnan(np.broadcast_to(sub, s.shape))
                     if miss.all():
                         s.kind = "param"
                     elif miss.any():
-                        raise LoweringError(
-                            f"'{nm}' is partially observed: mixed observation/parameter statements "
-                            "are outside the plate class")
+                        # the missing cells are unobserved stochastic nodes.  When nothing depends on the variable they
+                        # have no observed descendants: generated quantities, outside the target (graphs.jl:27-71; the
+                        # reference's Bones golden constant confirms it) -- the plate carries a 0/1 weight.  Checked
+                        # below, once the statement graph exists.
+                        s.kind = "obs"
+                        s.obs_mask = ~miss
                     else:
                         s.kind = "obs"
                 else:
@@ -372,6 +440,15 @@ class Lowering:
                         self.children[parent.sid].add(s.sid)
                     elif s.kind in ("param", "logical"):
                         raise LoweringError(f"loop-carried self dependence in statement {s.sid} ({s.name})")
+        referenced = set()
+        for t in self.stmts:
+            if t.kind != "tdata":
+                referenced.update(free_vars(t.node.rhs if isinstance(t.node, Det) else t.node.dist))
+        for s in self.stmts:
+            if s.obs_mask is not None and s.name in referenced:
+                raise LoweringError(
+                    f"'{s.name}' is partially observed and has children: its missing cells would be parameters "
+                    "(mixed observation/parameter statements are outside the plate class)")
         # generated quantities: statements from which no observation is reachable (graphs.jl:27-71)
         memo: Dict[int, bool] = {}
         by_sid = {s.sid: s for s in self.stmts}
@@ -546,16 +623,39 @@ class Lowering:
                 return Index(e.name, idx)  # element of a parameter vector / indexed scalar node held as a global
             defs = [s for s in self._defs(e.name) if s.kind == "logical"]
             if defs:
-                if len(defs) != 1:
-                    raise LoweringError(f"'{e.name}' is defined by several statements")
-                d = defs[0]
-                lhs = d.node.lhs
-                sub = {}
-                for li, ri in zip(lhs.idx, idx):
-                    if not isinstance(li, Var) or li.name not in d.loop_vars:
-                        raise LoweringError(f"lhs index of logical '{e.name}' must be a loop variable")
-                    sub[li.name] = ri
-                return self._inline(_subst(d.node.rhs, sub), depth + 1)
+                plain = (len(defs) == 1 and not defs[0].ragged and isinstance(defs[0].node.lhs, Index)
+                         and all(isinstance(li, Var) and li.name in defs[0].loop_vars for li in defs[0].node.lhs.idx))
+                if plain:
+                    d = defs[0]
+                    sub = {li.name: ri for li, ri in zip(d.node.lhs.idx, idx)}
+                    return self._inline(_subst(d.node.rhs, sub), depth + 1)
+                # several defining statements and / or constant subscripts on their left-hand sides (Bones: p[i,j,1],
+                # p[i,j,k] for k in 2:ncat[j]-1, p[i,j,ncat[j]]): a case split.  Statement d defines the referenced
+                # element where its loop variables, solved from the reference's subscripts, lie inside their (possibly
+                # ragged) ranges and its constant subscripts equal the reference's; the conditions are data expressions
+                # of the observation's loop variables, evaluated per cell when the tape is built.
+                out = Call("__nodef__", ())
+                for d in reversed(defs):
+                    lhs = d.node.lhs
+                    if not isinstance(lhs, Index) or len(lhs.idx) != len(idx):
+                        raise LoweringError(f"cannot match '{e.name}' against its definition in statement {d.sid}")
+                    sub, conds = {}, []
+                    for li, ri in zip(lhs.idx, idx):
+                        if isinstance(li, Var) and li.name in d.loop_vars and li.name not in sub:
+                            sub[li.name] = ri
+                    for li, ri in zip(lhs.idx, idx):
+                        if not (isinstance(li, Var) and li.name in d.loop_vars and sub.get(li.name) is ri):
+                            conds.append(Call("__eq__", (ri, _subst(li, sub))))
+                    if set(sub) != set(d.loop_vars):
+                        raise LoweringError(f"'{e.name}': a loop variable of statement {d.sid} is not a subscript of its lhs")
+                    for (var, lo, hi) in d.loops:
+                        conds.append(Call("__le__", (_subst(lo, sub), sub[var])))
+                        conds.append(Call("__le__", (sub[var], _subst(hi, sub))))
+                    cond = conds[0]
+                    for c in conds[1:]:
+                        cond = Call("__and__", (cond, c))
+                    out = Call("__select__", (cond, self._inline(_subst(d.node.rhs, sub), depth + 1), out))
+                return out
             return Index(e.name, idx)
         if isinstance(e, Neg):
             return Neg(self._inline(e.a, depth))
@@ -649,6 +749,42 @@ class Lowering:
             elif isinstance(e, Neg):
                 walk(e.a)
 
+        # parameter vectors indexed by the INNER loop variable of a two-loop observation whose predictor also holds
+        # parameters indexed by the outer one (LSAT: logistic(beta * theta[j] - alpha[k])): the vector is shared by every
+        # group, i.e. its elements behave like globals -- expanded the same way, read on the tape as gval[base + k]
+        for s in self.stmts:
+            if s.is_gq or s.kind != "obs" or len(s.loops) != 2:
+                continue
+            try:
+                exprs = [self._inline(a) for a in s.node.dist.args]
+            except LoweringError:
+                continue
+            refs = []
+
+            def collect(e):
+                if isinstance(e, Index):
+                    refs.append(e)
+                    for i in e.idx:
+                        collect(i)
+                elif isinstance(e, Call):
+                    for a in e.args:
+                        collect(a)
+                elif isinstance(e, BinOp):
+                    collect(e.a)
+                    collect(e.b)
+                elif isinstance(e, Neg):
+                    collect(e.a)
+
+            for e in exprs:
+                collect(e)
+            prm = [r for r in refs if any(d.kind == "param" and d.loops and not d.is_gq for d in self._defs(r.name))]
+            outer = [r for r in prm if any(isinstance(i, Var) and i.name == s.loop_vars[0] for i in r.idx)]
+            inner = [r for r in prm if len(r.idx) == 1 and isinstance(r.idx[0], Var) and r.idx[0].name == s.loop_vars[1]]
+            if outer and inner:
+                for r in inner:
+                    for d in self._defs(r.name):
+                        if d.kind == "param" and len(d.loops) == 1 and d.extents == s.extents[1:] and d.size <= 10:
+                            found.add(d.sid)
         for s in self.stmts:
             if s.is_gq:
                 continue
@@ -810,6 +946,23 @@ class Lowering:
 
     # ---- one plate ----------------------------------------------------------------------------------------------
     def _build_plate(self, s: Stmt, used_locals) -> P.Plate:
+        """the plate of one observed statement: linear predictor + link tape when the predictor is linear in the parameters
+        and every other family argument is a scalar; otherwise an expression plate"""
+        before, n_slots = set(used_locals), len(self.plan.data)
+        try:
+            return self._build_linear_plate(s, used_locals)
+        except LoweringError as first:
+            used_locals.clear()
+            used_locals.update(before)
+            for sl in self.plan.data[n_slots:]:
+                self._slot_ids.pop(sl.name, None)
+            del self.plan.data[n_slots:]
+            try:
+                return self._build_xplate(s, self._family(s.node.dist), used_locals)
+            except LoweringError as second:
+                raise LoweringError(f"{second} (as a linear-predictor plate: {first})") from None
+
+    def _build_linear_plate(self, s: Stmt, used_locals) -> P.Plate:
         if len(s.loops) > 2:
             raise LoweringError("observation plates deeper than two loops are outside the plate class")
         if len(s.loops) == 2:
@@ -853,7 +1006,13 @@ class Lowering:
         if isinstance(eta, Call) and eta.fn == "inprod":
             self._build_dense(s, fam, plate, eta, args, used_locals)
             return None
+        if fam == P.FAM_CATEGORICAL:
+            raise LoweringError("dcat needs an expression plate")
+        # (a predictor that is not linear in the parameters -- dugongs, lsat, air, leuk ... -- raises here and the
+        # observation's chain of logical parents becomes an expression tape, _build_plate)
         lin = self._linearize(eta, lv_names)
+        if any(ref[0] == "l" and self._is_gvec_ref(s, ref) for ref in lin.terms):
+            raise LoweringError("a parameter vector indexed by the inner loop variable")
         gidx = self._gather_index(s, lin)
         if gidx is not None:
             return self._build_gathered_plate(s, fam, eta_arg, plate.link, args, lin, gidx, used_locals)
@@ -879,7 +1038,146 @@ class Lowering:
             c = self._data_arg(lin.const, lv_names, shape, lv_names)
             if not (c.kind == P.ARG_CONST and c.value == 0.0):
                 plate.terms.append(P.Term(P.Arg.const(1.0), c))
+        self._apply_obs_mask(plate, s)
         return plate
+
+    def _apply_obs_mask(self, plate: P.Plate, s: Stmt):
+        """partially observed statement: missing cells carry weight 0 and a harmless placeholder observation"""
+        if s.obs_mask is None:
+            return
+        if plate.family == P.FAM_T:
+            raise LoweringError("dt observations with missing cells are not supported")
+        m = np.asarray(s.obs_mask, dtype=np.float64)
+        if m.ndim == 1:
+            plate.weight = P.Arg(P.ARG_DATA_I, self._slot(f"obs_mask|{s.name}", m.copy()))
+        else:
+            plate.weight = P.Arg(P.ARG_DATA_IJ, self._slot(f"obs_mask|{s.name}", np.asfortranarray(m).ravel(order="F"),
+                                                           rank=2, dim0=m.shape[0]))
+        plate.n_real = int(m.sum())
+        yslot = self.plan.data[plate.y.id]
+        vals = yslot.values
+        fill = vals[~np.isnan(vals)][0] if np.any(~np.isnan(vals)) else 0.0
+        yslot.values = np.where(np.isnan(vals), fill, vals)
+
+    # ---- predictors that are not linear in the parameters -> expression plate ------------------------------------------
+    def _is_gvec_ref(self, s: Stmt, ref) -> bool:
+        """('l', name, idx) is a reference `name[k]` with k the INNER loop variable of a two-loop observation whose
+        parameter statement was expanded into scalar globals (_vector_globals)"""
+        _, name, idx = ref
+        return (len(s.loops) == 2 and len(idx) == 1 and isinstance(idx[0], Var) and idx[0].name == s.loop_vars[1]
+                and f"{name}[{s.extents[1][0]}]" in self._gval_ids)
+
+    def _build_xplate(self, s: Stmt, fam, used_locals) -> P.Plate:
+        lv_names, shape = s.loop_vars, s.shape
+        self._cur_extents = s.extents
+        N = shape[0] if shape else 1
+        T = shape[1] if len(shape) == 2 else 1
+        plate = P.Plate(N=N, T=T, family=fam, eta_arg=0, name=f"{s.name}~{s.node.dist.fn} (expression tape)")
+        lhs = s.node.lhs
+        lhs_e = lhs if isinstance(lhs, Index) else Var(lhs.name)
+        if not shape:
+            raise LoweringError("a scalar observation with a non-linear predictor is outside the plate class")
+        plate.y = self._data_arg(lhs_e, lv_names, shape, lv_names)
+        if plate.y.kind in (P.ARG_CONST, P.ARG_ONE, P.ARG_DATA_J):
+            raise LoweringError("observation does not vary over its plate")
+        args = list(s.node.dist.args)
+        if fam == P.FAM_CATEGORICAL:
+            # y ~ dcat(p[.., 1:K]): the density is p[.., y] -- the element of p picked by the observed category
+            pa = args[0]
+            if not (isinstance(pa, Index) and isinstance(pa.idx[-1], (Range, Colon))
+                    and not any(isinstance(i, (Range, Colon)) for i in pa.idx[:-1])):
+                raise LoweringError("dcat expects a probability vector p[..., 1:K]")
+            args = [Index(pa.name, pa.idx[:-1] + (lhs_e,))]
+        tape: List[P.XOp] = []
+        memo: Dict[str, int] = {}
+        self.de.lenient = True
+        try:
+            aux = []
+            for a in args:
+                e = self._inline(a)
+                if self._is_data(e, lv_names):
+                    aux.append(self._data_arg(e, lv_names, shape, lv_names))
+                elif isinstance(e, Var) and e.name in self._gval_ids:
+                    aux.append(P.Arg.gval(self._gval_ids[e.name]))
+                else:
+                    aux.append(P.Arg.xval(self._tape(e, s, plate, tape, memo, used_locals)))
+        finally:
+            self.de.lenient = False
+        if fam == P.FAM_T and aux[2].kind != P.ARG_CONST:
+            raise LoweringError("the degrees of freedom of dt must be a constant")
+        if not tape:
+            raise LoweringError("internal: an expression plate without a tape")
+        plate.aux = aux
+        plate.xops = tape
+        self._apply_obs_mask(plate, s)
+        return plate
+
+    def _tape(self, e, s: Stmt, plate: P.Plate, tape, memo, used_locals) -> int:
+        """append the ops computing `e` for one cell of the plate (common subexpressions shared), return its slot"""
+        key = _show(e)
+        if key in memo:
+            return memo[key]
+
+        def push(op):
+            tape.append(op)
+            if len(tape) > P.MAX_XOPS:
+                raise LoweringError(f"the predictor needs more than {P.MAX_XOPS} tape ops")
+            memo[key] = len(tape) - 1
+            return memo[key]
+
+        lv_names, shape = s.loop_vars, s.shape
+        rec = lambda x: self._tape(x, s, plate, tape, memo, used_locals)  # noqa: E731
+        if isinstance(e, Call) and e.fn == "__select__":
+            cond, a, b = e.args
+            lv = _grids(s.extents, lv_names)
+            m = np.broadcast_to(np.asarray(self.de.ev(cond, lv), dtype=np.float64), shape) != 0
+            live = m if s.obs_mask is None else (m | ~np.asarray(s.obs_mask))  # unobserved cells do not care
+            dead = ~m if s.obs_mask is None else (~m | ~np.asarray(s.obs_mask))
+            if live.all():
+                memo[key] = rec(a)
+                return memo[key]
+            if dead.all():
+                memo[key] = rec(b)
+                return memo[key]
+            ia, ib = rec(a), rec(b)
+            ic = rec(Call("__mask__", (cond,)))
+            return push(P.XOp(P.OP_SELECT, ic, ia, ib))
+        if isinstance(e, Call) and e.fn == "__mask__":
+            lv = _grids(s.extents, lv_names)
+            m = (np.broadcast_to(np.asarray(self.de.ev(e.args[0], lv), dtype=np.float64), shape) != 0).astype(np.float64)
+            k = f"mask|{s.name}|{_show(e.args[0])}"
+            if m.ndim == 1:
+                leaf = P.Arg(P.ARG_DATA_I, self._slot(k, m.copy()))
+            else:
+                leaf = P.Arg(P.ARG_DATA_IJ, self._slot(k, np.asfortranarray(m).ravel(order="F"), rank=2, dim0=shape[0]))
+            return push(P.XOp(P.OP_LEAF, leaf=leaf))
+        if isinstance(e, Call) and e.fn == "__nodef__":
+            return push(P.XOp(P.OP_LEAF, leaf=P.Arg.const(float("nan"))))
+        if self._is_data(e, lv_names):
+            return push(P.XOp(P.OP_LEAF, leaf=self._data_arg(e, lv_names, shape, lv_names)))
+        if isinstance(e, Var):
+            return push(P.XOp(P.OP_LEAF, leaf=P.Arg.gval(self._gval_of(e.name))))
+        if isinstance(e, Index):
+            lab = self._elem_label(e)
+            if lab is not None and lab in self._gval_ids:
+                return push(P.XOp(P.OP_LEAF, leaf=P.Arg.gval(self._gval_ids[lab])))
+            ref = ("l", e.name, e.idx)
+            if self._is_gvec_ref(s, ref):
+                return push(P.XOp(P.OP_LEAF, leaf=P.Arg(P.ARG_GVEC_J, self._gval_ids[f"{e.name}[{s.extents[1][0]}]"])))
+            return push(P.XOp(P.OP_LEAF, leaf=P.Arg.local(self._local_index(plate, s, ref, used_locals))))
+        if isinstance(e, Neg):
+            return push(P.XOp(P.OP_NEG, rec(e.a)))
+        if isinstance(e, BinOp):
+            op = {"+": P.OP_ADD, "-": P.OP_SUB, "*": P.OP_MUL, "/": P.OP_DIV, "^": P.OP_POW}[e.op]
+            ia, ib = rec(e.a), rec(e.b)
+            return push(P.XOp(op, ia, ib))
+        if isinstance(e, Call):
+            if e.fn == "pow" and len(e.args) == 2:
+                ia, ib = rec(e.args[0]), rec(e.args[1])
+                return push(P.XOp(P.OP_POW, ia, ib))
+            if e.fn in P.UNARY_OF and len(e.args) == 1:
+                return push(P.XOp(P.UNARY_OF[e.fn], rec(e.args[0])))
+        raise LoweringError(f"unsupported expression in a predictor: {_show(e)}")
 
     # ---- random effects picked by a data index: y[i] ~ f(... + b[group[i]] ...) -------------------------------------
     def _gather_index(self, s: Stmt, lin: _Lin):

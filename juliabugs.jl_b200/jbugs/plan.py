@@ -16,28 +16,30 @@ VERSION = 1
 FLAG_TRANSFORMED = 1
 
 # enum jbugs_arg_kind
-ARG_CONST, ARG_GVAL, ARG_LOCAL, ARG_DATA_I, ARG_DATA_J, ARG_DATA_IJ, ARG_ONE = range(7)
+ARG_CONST, ARG_GVAL, ARG_LOCAL, ARG_DATA_I, ARG_DATA_J, ARG_DATA_IJ, ARG_ONE, ARG_XVAL, ARG_GVEC_J = range(9)
 # enum jbugs_family
 (FAM_NORMAL, FAM_GAMMA, FAM_EXPONENTIAL, FAM_UNIFORM, FAM_BETA, FAM_LOGNORMAL, FAM_BERNOULLI,
  FAM_BINOMIAL, FAM_POISSON, FAM_FLAT, FAM_LOGISTIC, FAM_LAPLACE, FAM_WEIBULL, FAM_NEGBIN, FAM_CHISQ, FAM_T,
- FAM_GEOMETRIC) = range(17)
+ FAM_GEOMETRIC, FAM_CATEGORICAL) = range(18)
 FAMILY_OF = {
     "dnorm": FAM_NORMAL, "dgamma": FAM_GAMMA, "dexp": FAM_EXPONENTIAL, "dunif": FAM_UNIFORM,
     "dbeta": FAM_BETA, "dlnorm": FAM_LOGNORMAL, "dbern": FAM_BERNOULLI, "dbin": FAM_BINOMIAL,
     "dpois": FAM_POISSON, "dflat": FAM_FLAT, "dlogis": FAM_LOGISTIC, "ddexp": FAM_LAPLACE, "dweib": FAM_WEIBULL,
-    "dnegbin": FAM_NEGBIN, "dchisqr": FAM_CHISQ, "dt": FAM_T, "dgeom": FAM_GEOMETRIC,
+    "dnegbin": FAM_NEGBIN, "dchisqr": FAM_CHISQ, "dt": FAM_T, "dgeom": FAM_GEOMETRIC, "dcat": FAM_CATEGORICAL,
 }
 FAMILY_NAME = {v: k for k, v in FAMILY_OF.items()}
 FAMILY_NARGS = {FAM_NORMAL: 2, FAM_GAMMA: 2, FAM_EXPONENTIAL: 1, FAM_UNIFORM: 2, FAM_BETA: 2,
                 FAM_LOGNORMAL: 2, FAM_BERNOULLI: 1, FAM_BINOMIAL: 2, FAM_POISSON: 1, FAM_FLAT: 0,
                 FAM_LOGISTIC: 2, FAM_LAPLACE: 2, FAM_WEIBULL: 2, FAM_NEGBIN: 2, FAM_CHISQ: 1, FAM_T: 3,
-                FAM_GEOMETRIC: 1}
-DISCRETE = {FAM_BERNOULLI, FAM_BINOMIAL, FAM_POISSON, FAM_NEGBIN, FAM_GEOMETRIC}
+                FAM_GEOMETRIC: 1, FAM_CATEGORICAL: 1}
+DISCRETE = {FAM_BERNOULLI, FAM_BINOMIAL, FAM_POISSON, FAM_NEGBIN, FAM_GEOMETRIC, FAM_CATEGORICAL}
 # enum jbugs_transform
 TR_IDENTITY, TR_LOG, TR_LOGIT, TR_UPPER = range(4)
 # enum jbugs_op
 OP_IDENTITY, OP_EXP, OP_LOGISTIC, OP_CEXPEXP, OP_PHI, OP_LOG, OP_SQRT, OP_NEG = range(8)
 OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW = 16, 17, 18, 19, 20
+OP_LEAF, OP_SELECT = 32, 33   # expression tapes only
+MAX_XOPS = 64
 LINK_OF = {"exp": OP_EXP, "logistic": OP_LOGISTIC, "ilogit": OP_LOGISTIC, "cexpexp": OP_CEXPEXP,
            "icloglog": OP_CEXPEXP, "phi": OP_PHI}
 UNARY_OF = dict(LINK_OF, log=OP_LOG, sqrt=OP_SQRT)
@@ -60,10 +62,12 @@ PLATE_DT = np.dtype([("N", "<i8"), ("T", "<i8"), ("first_local", "<u4"), ("n_loc
 HEADER_DT = np.dtype([("magic", "S8"), ("version", "<u4"), ("flags", "<u4"), ("D", "<i8"),
                       ("n_globals", "<u4"), ("n_gtape", "<u4"), ("n_data", "<u4"),
                       ("n_plates", "<u4"), ("n_locals", "<u4"), ("n_terms", "<u4"),
-                      ("n_dense", "<u4"), ("reserved32", "<u4"), ("reserved", "<u8")])
+                      ("n_dense", "<u4"), ("n_xops", "<u4"), ("reserved", "<u8")])
 DENSE_DT = np.dtype([("N", "<i8"), ("P", "<i8"), ("theta_base", "<i8"), ("theta_stride", "<i8"),
                      ("x_slot", "<i4"), ("y_slot", "<i4"), ("n_slot", "<i4"),
                      ("family", "<u4"), ("link", "<u4"), ("pad", "<u4")])
+XOP_DT = np.dtype([("op", "<u4"), ("a", "<u2"), ("b", "<u2"), ("c", "<u2"), ("pad", "<u2"), ("pad2", "<u4"), ("leaf", ARG_DT)])
+assert XOP_DT.itemsize == 32
 assert ARG_DT.itemsize == 16 and GLOBAL_DT.itemsize == 80 and GOP_DT.itemsize == 40
 assert DATA_DT.itemsize == 24 and LOCAL_DT.itemsize == 104 and TERM_DT.itemsize == 32
 assert PLATE_DT.itemsize == 128 and HEADER_DT.itemsize == 64 and DENSE_DT.itemsize == 56
@@ -90,6 +94,10 @@ class Arg:
     @staticmethod
     def one():
         return Arg(ARG_ONE, 0, 1.0)
+
+    @staticmethod
+    def xval(i):
+        return Arg(ARG_XVAL, int(i))
 
     def rec(self):
         return (self.kind, self.id, self.value)
@@ -151,6 +159,16 @@ class Term:
 
 
 @dataclass
+class XOp:
+    """one op of a plate's expression tape (static single assignment: produces value slot = its position)"""
+    op: int
+    a: int = 0
+    b: int = 0
+    c: int = 0
+    leaf: Arg = ZERO_ARG
+
+
+@dataclass
 class Plate:
     N: int
     T: int
@@ -165,6 +183,7 @@ class Plate:
     name: str = ""
     n_real: int = -1               # observed cells when the plate is padded (weight given), else N * T
     weight: Optional[Arg] = None   # 0/1 per cell (DATA_I | DATA_IJ): padded cells of a plate gathered by a data index
+    xops: List[XOp] = field(default_factory=list)   # expression plate (has_obs == 2 in the record): replaces terms/link
 
 
 @dataclass
@@ -218,17 +237,26 @@ class Plan:
             d[k] = (x.values.size, x.dim0 or x.values.size, x.rank, x.dtype_code)
         nl = sum(len(p.locals) for p in self.plates)
         nt = sum(len(p.terms) for p in self.plates)
+        nx = sum(len(p.xops) for p in self.plates)
         loc = np.zeros(nl, LOCAL_DT)
         trm = np.zeros(nt, TERM_DT)
+        xop = np.zeros(nx, XOP_DT)
         pl = np.zeros(len(self.plates), PLATE_DT)
-        il = it = 0
+        il = it = ix = 0
         for k, p in enumerate(self.plates):
             if len(p.link) > MAX_LINK:
                 raise ValueError("link tape longer than JBUGS_MAX_LINK")
+            if len(p.xops) > MAX_XOPS:
+                raise ValueError("expression tape longer than JBUGS_MAX_XOPS")
             link = list(p.link) + [OP_IDENTITY] * (MAX_LINK - len(p.link))
-            pl[k] = (p.N, p.T, il, len(p.locals), it, len(p.terms), len(p.link), link, p.family,
-                     p.eta_arg, 1 if p.has_obs else 0, p.y.rec(),
+            is_x = bool(p.xops)
+            pl[k] = (p.N, p.T, il, len(p.locals), ix if is_x else it, len(p.xops) if is_x else len(p.terms),
+                     len(p.link), link, p.family,
+                     p.eta_arg, (2 if is_x else 1) if p.has_obs else 0, p.y.rec(),
                      args3(p.aux if p.weight is None else (list(p.aux) + [ZERO_ARG, ZERO_ARG])[:2] + [p.weight]))
+            for x in p.xops:
+                xop[ix] = (x.op, x.a, x.b, x.c, 0, 0, x.leaf.rec())
+                ix += 1
             for x in p.locals:
                 loc[il] = (x.level, x.transform, x.theta_base, x.stride_i, x.stride_j, x.idx_slot,
                            x.family, x.lb, x.ub, args3(x.args))
@@ -239,11 +267,11 @@ class Plan:
         h = np.zeros(1, HEADER_DT)
         h[0] = (MAGIC, VERSION, FLAG_TRANSFORMED if self.transformed else 0, self.D,
                 len(self.globals), len(self.gtape), len(self.data), len(self.plates), nl, nt,
-                len(self.dense), 0, 0)
+                len(self.dense), nx, 0)
         dn = np.zeros(len(self.dense), DENSE_DT)
         for k, x in enumerate(self.dense):
             dn[k] = (x.N, x.P, x.theta_base, x.theta_stride, x.x_slot, x.y_slot, x.n_slot, x.family, x.link, 0)
-        return b"".join(x.tobytes() for x in (h, g, t, d, pl, loc, trm, dn))
+        return b"".join(x.tobytes() for x in (h, g, t, d, pl, loc, trm, dn, xop))
 
     def describe(self) -> str:
         out = [f"plan D={self.D} transformed={self.transformed} globals={len(self.globals)} "

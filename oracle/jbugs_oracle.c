@@ -46,6 +46,7 @@ typedef struct jbo_plan {
     jbugs_local* locals;
     jbugs_term* terms;
     jbugs_dense* dense;
+    jbugs_xop* xops;
     const void** slots; /* borrowed pointers */
     int64_t* shard_i0;  /* per plate */
     int64_t* shard_i1;
@@ -273,6 +274,15 @@ static int fam_logpdf(uint32_t fam, double x, const double* a, double* lp, doubl
         da[0] = 1.0 / p - (x == 0.0 ? 0.0 : x / (1.0 - p));
         return 0;
     }
+    case JBUGS_FAM_CATEGORICAL: { /* distributions.jl:472-474 -> Categorical(p): logpdf = log p[x]; a[0] = p[x].
+                                     (the whole-vector check sum(p) == 1 is not part of the plan: the other components
+                                     never enter the density) */
+        double py = a[0];
+        if (!(py >= 0.0 && py <= 1.0 + 1e-8)) return 1;
+        *lp = log(py);
+        da[0] = 1.0 / py;
+        return 0;
+    }
     default: return 2;
     }
 }
@@ -305,7 +315,7 @@ jbo_plan* jbo_plan_create(const void* blob, size_t nbytes) {
     size_t need = sizeof(jbugs_plan_header) + p->h.n_globals * sizeof(jbugs_global) + p->h.n_gtape * sizeof(jbugs_gop) +
                   p->h.n_data * sizeof(jbugs_data_desc) + p->h.n_plates * sizeof(jbugs_plate) +
                   p->h.n_locals * sizeof(jbugs_local) + p->h.n_terms * sizeof(jbugs_term) +
-                  p->h.n_dense * sizeof(jbugs_dense);
+                  p->h.n_dense * sizeof(jbugs_dense) + p->h.n_xops * sizeof(jbugs_xop);
     if (need != nbytes) { free(p); return NULL; }
     const char* c = (const char*)blob + sizeof(jbugs_plan_header);
 #define TAKE(field, type, n) \
@@ -317,6 +327,7 @@ jbo_plan* jbo_plan_create(const void* blob, size_t nbytes) {
     TAKE(locals, jbugs_local, p->h.n_locals);
     TAKE(terms, jbugs_term, p->h.n_terms);
     TAKE(dense, jbugs_dense, p->h.n_dense);
+    TAKE(xops, jbugs_xop, p->h.n_xops);
 #undef TAKE
     p->slots = (const void**)calloc(p->h.n_data + 1, sizeof(void*));
     p->shard_i0 = (int64_t*)calloc(p->h.n_plates + 1, sizeof(int64_t));
@@ -328,7 +339,7 @@ jbo_plan* jbo_plan_create(const void* blob, size_t nbytes) {
 
 void jbo_plan_destroy(jbo_plan* p) {
     if (!p) return;
-    free(p->globals); free(p->gtape); free(p->data); free(p->plates); free(p->locals); free(p->terms); free(p->dense);
+    free(p->globals); free(p->gtape); free(p->data); free(p->plates); free(p->locals); free(p->terms); free(p->dense); free(p->xops);
     free(p->slots); free(p->shard_i0); free(p->shard_i1); free(p);
 }
 
@@ -365,6 +376,7 @@ static inline double argval(const jbo_plan* p, const jbugs_arg* a, const double*
     case JBUGS_ARG_CONST: return a->value;
     case JBUGS_ARG_ONE: return 1.0;
     case JBUGS_ARG_GVAL: return gval[a->id];
+    case JBUGS_ARG_GVEC_J: return gval[a->id + j];
     case JBUGS_ARG_LOCAL: return lx[a->id];
     case JBUGS_ARG_DATA_I: return ((const double*)p->slots[a->id])[i];
     case JBUGS_ARG_DATA_J: return ((const double*)p->slots[a->id])[j];
@@ -478,7 +490,58 @@ static int eval_chain(const jbo_plan* p, chain_io io, int want_grad, double* log
                     for (int q = 0; q < 3; ++q) argadj(&L[l].args[q], da[q], gadj, ladj);
                 }
                 const int has_w = pl->aux[2].kind == JBUGS_ARG_DATA_I || pl->aux[2].kind == JBUGS_ARG_DATA_IJ;
-                if (pl->has_obs && !(has_w && argval(p, &pl->aux[2], gval, lx, i, j, N) == 0.0)) {
+                if (pl->has_obs == 2 && !(has_w && argval(p, &pl->aux[2], gval, lx, i, j, N) == 0.0)) {
+                    /* expression plate: forward sweep over the tape (the composed node functions of the observation's
+                       logical parents), observation, reverse sweep back to the leaves */
+                    const jbugs_xop* X = p->xops + pl->first_term;
+                    const int nx = (int)pl->n_terms;
+                    double v[JBUGS_MAX_XOPS], w[JBUGS_MAX_XOPS], d1[JBUGS_MAX_XOPS], d2[JBUGS_MAX_XOPS];
+                    for (int k = 0; k < nx; ++k) {
+                        const jbugs_xop* o = &X[k];
+                        w[k] = 0.0; d1[k] = 0.0; d2[k] = 0.0;
+                        if (o->op == JBUGS_OP_LEAF) { v[k] = argval(p, &o->leaf, gval, lx, i, j, N); continue; }
+                        if (o->op == JBUGS_OP_SELECT) { v[k] = v[o->a] != 0.0 ? v[o->b] : v[o->c]; continue; }
+                        const double a = v[o->a];
+                        if (o->op < 16) {
+                            if (unary(o->op, a, &v[k], &d1[k])) return 1;
+                            continue;
+                        }
+                        const double b = v[o->b];
+                        switch (o->op) {
+                        case JBUGS_OP_ADD: v[k] = a + b; d1[k] = 1; d2[k] = 1; break;
+                        case JBUGS_OP_SUB: v[k] = a - b; d1[k] = 1; d2[k] = -1; break;
+                        case JBUGS_OP_MUL: v[k] = a * b; d1[k] = b; d2[k] = a; break;
+                        case JBUGS_OP_DIV: v[k] = a / b; d1[k] = 1.0 / b; d2[k] = -a / (b * b); break;
+                        case JBUGS_OP_POW:
+                            if (a < 0 && b != floor(b)) return 1;
+                            v[k] = pow(a, b); d1[k] = b * pow(a, b - 1.0); d2[k] = (a > 0) ? v[k] * log(a) : 0.0; break;
+                        default: return 1;
+                        }
+                    }
+                    double a[3], da[3], lp, dx;
+                    for (int q = 0; q < 3; ++q)
+                        a[q] = pl->aux[q].kind == JBUGS_ARG_XVAL ? v[pl->aux[q].id] : argval(p, &pl->aux[q], gval, lx, i, j, N);
+                    double y = argval(p, &pl->y, gval, lx, i, j, N);
+                    if (fam_logpdf(pl->family, y, a, &lp, &dx, da)) return 1;
+                    logp += lp;
+                    for (int q = 0; q < 3; ++q) {
+                        if (pl->aux[q].kind == JBUGS_ARG_XVAL) w[pl->aux[q].id] += da[q];
+                        else if (q < 2) argadj(&pl->aux[q], da[q], gadj, ladj);
+                    }
+                    for (int k = nx - 1; k >= 0; --k) {
+                        const jbugs_xop* o = &X[k];
+                        if (w[k] == 0.0) continue;
+                        if (o->op == JBUGS_OP_LEAF) {
+                            if (o->leaf.kind == JBUGS_ARG_GVEC_J) gadj[o->leaf.id + j] += w[k];
+                            else argadj(&o->leaf, w[k], gadj, ladj);
+                        } else if (o->op == JBUGS_OP_SELECT) {
+                            w[v[o->a] != 0.0 ? o->b : o->c] += w[k];
+                        } else {
+                            w[o->a] += w[k] * d1[k];
+                            if (o->op >= 16) w[o->b] += w[k] * d2[k];
+                        }
+                    }
+                } else if (pl->has_obs && !(has_w && argval(p, &pl->aux[2], gval, lx, i, j, N) == 0.0)) {
                     /* linear predictor, link tape, observation (source_gen.jl:738-741); cells with weight 0 are the
                        padding of a plate whose observations were gathered by a data index */
                     double eta = 0.0;

@@ -27,6 +27,8 @@ def fixtures():
     """data / inits of the reference's own examples (tests/golden/make_fixtures.py)."""
     with open(os.path.join(ROOT, "tests", "golden", "examples_vol1.json")) as f:
         raw = json.load(f)
+    with open(os.path.join(ROOT, "tests", "golden", "examples_vol2.json")) as f:
+        raw.update(json.load(f))
     out = {}
     for name, entry in raw.items():
         out[name] = {k: ({kk: _arr(vv) for kk, vv in v.items()} if isinstance(v, dict) and k != "golden_logjoint" else v)

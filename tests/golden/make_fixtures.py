@@ -43,6 +43,9 @@ FILES = {
     "leuk": "19_Leuk.jl",
     "leukfr": "20_LeukFr.jl",
 }
+# Volume 2 examples used by the expression-plate tests (written to examples_vol2.json)
+REF2 = "/root/reference/JuliaBUGS/src/BUGSExamples/Volume_2"
+FILES2 = {"dugongs": "01_Dugongs.jl", "air": "07_Air.jl"}
 TUPLES = re.compile(r"^(data|inits\w*|inits_alternative\w*)\s*=\s*\(", re.M)
 
 # golden constants: JuliaBUGS/test/model/evaluation.jl:355-379 (rtol 1e-6 in the reference test)
@@ -150,16 +153,14 @@ def named_tuple(src):
     return out
 
 
-def main():
-    if not os.path.isdir(REF):
-        sys.exit("reference tree not mounted; fixtures can only be regenerated in the build container")
+def extract(ref, files, volume):
     out = {}
-    for name, fn in FILES.items():
-        path = os.path.join(REF, fn)
+    for name, fn in files.items():
+        path = os.path.join(ref, fn)
         if not os.path.exists(path):
             continue
         text = open(path).read()
-        entry = {"source": f"JuliaBUGS/src/BUGSExamples/Volume_1/{fn}"}
+        entry = {"source": f"JuliaBUGS/src/BUGSExamples/{volume}/{fn}"}
         for m in TUPLES.finditer(text):
             end = balanced(text, m.end() - 1)
             try:
@@ -169,10 +170,19 @@ def main():
         if name in GOLDEN_LOGJOINT:
             entry["golden_logjoint"] = GOLDEN_LOGJOINT[name]
         out[name] = entry
-    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "examples_vol1.json")
-    with open(dst, "w") as f:
-        json.dump(out, f, separators=(",", ":"))
-    print("wrote", dst, os.path.getsize(dst), "bytes;", ", ".join(out))
+    return out
+
+
+def main():
+    if not os.path.isdir(REF):
+        sys.exit("reference tree not mounted; fixtures can only be regenerated in the build container")
+    here = os.path.dirname(os.path.abspath(__file__))
+    for ref, files, volume, fn in ((REF, FILES, "Volume_1", "examples_vol1.json"), (REF2, FILES2, "Volume_2", "examples_vol2.json")):
+        out = extract(ref, files, volume)
+        dst = os.path.join(here, fn)
+        with open(dst, "w") as f:
+            json.dump(out, f, separators=(",", ":"))
+        print("wrote", dst, os.path.getsize(dst), "bytes;", ", ".join(out))
 
 
 if __name__ == "__main__":

@@ -17,6 +17,12 @@ ZOO = [
     ("equiv", ex.EQUIV, "equiv", "inits"),            # random effect indexed by the inner loop variable
     ("dyes", ex.DYES, "dyes", "inits"),
     ("stacks", ex.STACKS, "stacks", "inits"),         # beta[1], beta[2], beta[3] referenced element by element
+    # predictors that are not linear in the parameters: expression plates (tape interpreter)
+    ("bones", ex.BONES, "bones", "inits"),            # dcat of cumulative-logit probabilities, 20 missing cells
+    ("dugongs", ex.DUGONGS, "dugongs", "inits"),      # alpha - beta * pow(gamma, x[i])
+    ("lsat", ex.LSAT, "lsat", "inits"),               # logistic(beta * theta[j] - alpha[k]), ragged data transformation
+    ("air", ex.AIR, "air", "inits"),                  # a latent covariate times a coefficient
+    ("leuk", ex.LEUK, "leuk", "inits"),               # Y[i,j] * exp(beta * Z[i]) * dL0[j] as a Poisson mean
 ]
 
 

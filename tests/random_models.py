@@ -169,3 +169,28 @@ def make_structured(seed):
         desc = f"siblings {name}/{link} N={N} K={K}"
     lines += [f"  {g} ~ {p}" for g, p in globals_] + ["}"]
     return "\n".join(lines), data, desc
+
+
+def make_nonlinear(seed, n_max=12):
+    """the same random plates with a predictor that is NOT linear in the parameters (products of parameters, parameters
+    inside exp / pow): they lower to expression plates (tape interpreter).  -> (model text, data dict, description)"""
+    text, data, desc = make(seed, n_max=n_max)
+    rng = np.random.default_rng(9000 + seed)
+    lines = text.split("\n")
+    k = next(q for q, l in enumerate(lines) if "<-" in l and ("mu[" in l.split("<-")[0]))
+    lhs, pred = lines[k].split("<-", 1)
+    pred = pred.strip()
+    kind = int(rng.integers(0, 4))
+    extra = ["  sc ~ dnorm(0.0, 1.0)"]
+    if kind == 0:
+        new = f"({pred}) * exp(0.3 * sc)"
+    elif kind == 1:
+        new = f"{pred} + 0.1 * b0 * sc"
+    elif kind == 2:
+        new = f"pow(1.0 + exp(sc), -0.5) * ({pred})"
+    else:
+        new = f"{pred} + 0.2 * sc * u0[i]" if "u0[i]" in pred else f"{pred} - 0.1 * sc * sc"
+    lines[k] = f"{lhs}<- {new}"
+    end = max(q for q, l in enumerate(lines) if l.strip() == "}")
+    lines[end:end] = extra
+    return "\n".join(lines), data, desc + f" nonlinear#{kind}"

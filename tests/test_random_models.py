@@ -9,7 +9,7 @@ import jbugs
 from c_oracle import COracle
 from conftest import grad_err, rel_err
 from helpers import random_thetas
-from random_models import make, make_structured
+from random_models import make, make_nonlinear, make_structured
 
 SEEDS = list(range(96))
 
@@ -81,3 +81,34 @@ def test_structured_random_model_cuda_matches_c_oracle(seed):
     m = jbugs.compile(text, data)
     theta = random_thetas(np.zeros(m.plan.D), 37, seed=seed, scale=0.3)
     _check(m.cuda, COracle(m.plan), theta)
+
+
+@pytest.mark.parametrize("seed", list(range(48)))
+def test_nonlinear_random_model_plan_matches_node_loop(seed):
+    """expression plates: random predictors that are not linear in the parameters, every observation family"""
+    text, data, desc = make_nonlinear(seed)
+    gm = go.compile(text, data).use_generated_order()
+    plan, lw = jbugs.lower(text, data)
+    assert len(plan.plates) == 1 and plan.plates[0].xops, desc
+    assert plan.D == gm.D and lw.param_names() == gm.param_names(), desc
+    theta = random_thetas(np.zeros(plan.D), 3, seed=seed, scale=0.3)
+    lp, g, st = COracle(plan).eval_batch(theta)
+    for c in range(3):
+        lp_g, g_g = gm.logdensity_and_gradient(theta[:, c])
+        if not np.isfinite(lp_g):
+            assert lp[c] == lp_g, desc
+            continue
+        assert st[c] == 0 and abs(lp[c] - lp_g) <= 1e-11 * max(1.0, abs(lp_g)), (desc, text)
+        assert grad_err(g[:, c], g_g) < 1e-10, (desc, text)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", list(range(48)))
+def test_nonlinear_random_model_cuda_matches_c_oracle(seed):
+    from test_gpu_parity import _check
+    text, data, desc = make_nonlinear(seed, n_max=90)
+    m = jbugs.compile(text, data)
+    assert "expression_tape" in m.cuda.describe()
+    theta = random_thetas(np.zeros(m.plan.D), 70, seed=seed, scale=0.3)
+    _check(m.cuda, COracle(m.plan), theta)
+    _check(m.cuda, COracle(m.plan), theta, layout="param_fast")
