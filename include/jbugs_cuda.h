@@ -109,6 +109,17 @@ int jbugs_eval_batch(jbugs_plan* plan, const double* theta, int64_t ld, int64_t 
                      double* logp, double* grad, int32_t* status, int want_grad, int flags,
                      void* stream);
 
+/* Replaces: the `(logprior, loglikelihood, tempered_logjoint)` triple of `evaluate_with_values!!`
+ * (src/model/evaluation.jl:116, 269-274; `AbstractPPL.evaluate!!`, src/model/abstractppl.jl:989-1005), for C chains:
+ *   logprior : densities of the unobserved stochastic nodes + log-Jacobians of their bijectors
+ *   loglik   : densities of the observed nodes (may be NULL)
+ *   logp     : logprior + temperature * loglik;  grad : its gradient (same layout as theta)
+ * Two evaluations: everything, then the prior part alone (observations switched off); the likelihood part is their
+ * difference.  Buffers are all host pointers or all device pointers.  DomainError chains: logp = -Inf, the parts NaN. */
+int jbugs_eval_batch_tempered(jbugs_plan* plan, const double* theta, int64_t ld, int64_t C, int layout,
+                              double temperature, double* logprior, double* loglik, double* logp, double* grad,
+                              int32_t* status, int want_grad, void* stream);
+
 /* Library-owned theta / gradient batch (north_star: "owns the device buffers for data, the theta
  * batch and the gradients").  Returns device pointers in CHAIN_FAST layout with *ld >= C padded so
  * that every row is 128-byte aligned. */

@@ -153,6 +153,8 @@ struct jbugs_plan_s {
     // streams are < 1 % of the traffic anyway.  `jbugs_plan_set_option(plan, "tma", 1)` selects the TMA kernels.
     int use_tma = 0;
     int use_pdl = 1;  // programmatic dependent launch of the plate kernels and finalize (option "pdl")
+    int parts = 0;    // 1: evaluate the prior part only (parameters' densities + log-Jacobians; observations skipped) --
+                      // the second pass of jbugs_eval_batch_tempered
     long long launches = 0;
     // bumped whenever anything a captured launch sequence bakes in may have changed (tiling, workspace pointers,
     // data-only constants): the HMC trajectory graph is rebuilt when it sees a new epoch
@@ -1140,15 +1142,23 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
             pp.v.loc[l].step_i = pp.v.loc[l].si * ld;
             pp.v.loc[l].step_j = pp.v.loc[l].sj * ld;
         }
-        const bool jit = r.variant == 0 && r.jit_launch && r.jit_valid && !p->force_dynamic;
-        if (!jit && r.variant == 0) fp.p[k].obs_const = 0.0;  // the interpreter evaluates the full log-density itself
-        cudaError_t le = (jit ? r.jit_launch : g_specs[r.variant].launch)(r.n_tiles, r.smem_bytes, st, pp, theta, grad, ld, C, p->d_gvals, ldg,
+        bool jit = r.variant == 0 && r.jit_launch && r.jit_valid && !p->force_dynamic;
+        int variant = r.variant;
+        if (p->parts == 1) {
+            // prior part only: the interpreter with the observation switched off (has_obs = 0 is a run-time shape field)
+            jit = false;
+            variant = pp.sh.n_x > 0 ? g_xspec : 0;
+            pp.sh.has_obs = 0;
+            fp.p[k].obs_const = 0.0;
+        }
+        if (!jit && variant == 0) fp.p[k].obs_const = 0.0;  // the interpreter evaluates the full log-density itself
+        cudaError_t le = (jit ? r.jit_launch : g_specs[variant].launch)(r.n_tiles, r.smem_bytes, st, pp, theta, grad, ld, C, p->d_gvals, ldg,
                                                    p->d_partial + r.partial_offset * ldg, p->d_flags, want_grad && grad, p->use_pdl);
         if (le != cudaSuccess) return fail(JBUGS_ERR_CUDA, "plate kernel launch failed: %s", cudaGetErrorString(le));
         p->launches++;
         reduce_plates.push_back((int)k);
     }
-    if (!p->dense.empty()) {
+    if (!p->dense.empty() && p->parts != 1) {  // (the dense predictor is all likelihood: no part of the prior pass)
         const jbugs_dense& dn = p->dense[0];
         const bool sharded = p->comm && p->nranks > 1 && p->dense_i1 >= 0;  // rows of X split over the ranks
         const long long r0 = p->dense_i0, Nloc = (p->dense_i1 >= 0 ? p->dense_i1 : dn.N) - r0;
@@ -1321,6 +1331,83 @@ extern "C" int jbugs_eval_batch(jbugs_plan* p, const double* theta, int64_t ld, 
     }
     // host buffers and/or PARAM_FAST: pipelined through library staging in chunks of chains
     return eval_staged(p, theta, ld, C, layout, logp, grad, status, want_grad, st);
+}
+
+// ---- logprior / loglikelihood / tempered log joint (evaluation.jl:116, 269-274) -------------------------------------
+__global__ void __launch_bounds__(256)
+temper_kernel(double* __restrict__ a /* total -> tempered */, const double* __restrict__ b /* prior part */, long long rows,
+              long long cols, long long ld, double t) {
+    const long long q = (long long)blockIdx.x * 256 + threadIdx.x, r = blockIdx.y;
+    if (q < cols && r < rows) {
+        const double tot = a[r * ld + q], pr = b[r * ld + q];
+        a[r * ld + q] = fma(t, tot - pr, pr);
+    }
+}
+__global__ void __launch_bounds__(256)
+temper_logp_kernel(double* __restrict__ total, double* __restrict__ prior, double* __restrict__ lik, const int* __restrict__ status,
+                   long long C, double t) {
+    const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (c >= C) return;
+    const double tot = total[c], pr = prior[c];
+    const bool bad = status && status[c] != 0;
+    const double ll = bad ? dev_nan() : tot - pr;
+    if (lik) lik[c] = ll;
+    total[c] = bad ? -dev_inf() : fma(t, ll, pr);
+    if (bad) prior[c] = dev_nan();
+}
+
+extern "C" int jbugs_eval_batch_tempered(jbugs_plan* p, const double* theta, int64_t ld, int64_t C, int layout, double temperature,
+                                         double* logprior, double* loglik, double* logp, double* grad, int32_t* status,
+                                         int want_grad, void* stream) {
+    if (!p || !theta || !logp || !logprior) return fail(JBUGS_ERR_INVALID, "null argument");
+    if (want_grad && !grad) return fail(JBUGS_ERR_INVALID, "want_grad set but grad is null");
+    if (p->comm && p->nranks > 1) return fail(JBUGS_ERR_UNSUPPORTED, "the prior / likelihood split is not available on an observation-sharded plan");
+    const bool dev = is_device_ptr_strict(theta);
+    if (dev != is_device_ptr_strict(logp) || dev != is_device_ptr_strict(logprior) || (grad && dev != is_device_ptr_strict(grad)) ||
+        (loglik && dev != is_device_ptr_strict(loglik)) || (status && dev != is_device_ptr_strict(status)))
+        return fail(JBUGS_ERR_INVALID, "buffers must all be host pointers or all be device pointers");
+    // pass 1: everything -> (logp, grad, status); pass 2: the prior part -> (logprior, scratch gradient)
+    int rc = jbugs_eval_batch(p, theta, ld, C, layout, logp, grad, status, want_grad, 0, stream);
+    if (rc) return rc;
+    if (C == 0) return JBUGS_OK;
+    const long long D = p->h.D;
+    const long long rows = layout == JBUGS_LAYOUT_CHAIN_FAST ? D : C, cols = layout == JBUGS_LAYOUT_CHAIN_FAST ? C : D;
+    const size_t gbytes = (size_t)std::max<long long>(rows, 1) * (size_t)ld * 8;
+    double* g2 = nullptr;
+    if (want_grad) {
+        if (dev) CU(cudaMalloc(&g2, gbytes));
+        else if (!(g2 = (double*)malloc(gbytes))) return fail(JBUGS_ERR_STATE, "out of host memory");
+    }
+    p->parts = 1;
+    rc = jbugs_eval_batch(p, theta, ld, C, layout, logprior, g2, nullptr, want_grad, 0, stream);
+    p->parts = 0;
+    p->epoch++;
+    if (!rc) {
+        if (dev) {
+            cudaStream_t st = (cudaStream_t)stream;
+            if (want_grad) temper_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)rows), 256, 0, st>>>(grad, g2, rows, cols, ld, temperature);
+            temper_logp_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(logp, logprior, loglik, status, C, temperature);
+            p->launches += want_grad ? 2 : 1;
+            if (cudaStreamSynchronize(st) != cudaSuccess) rc = fail(JBUGS_ERR_CUDA, "tempering kernels failed");
+        } else {
+            if (want_grad)
+                for (long long r = 0; r < rows; ++r)
+                    for (long long q = 0; q < cols; ++q) {
+                        const double tot = grad[r * ld + q], pr = g2[r * ld + q];
+                        grad[r * ld + q] = std::fma(temperature, tot - pr, pr);
+                    }
+            for (long long c = 0; c < C; ++c) {
+                const bool bad = status && status[c] != 0;
+                const double ll = bad ? NAN : logp[c] - logprior[c];
+                if (loglik) loglik[c] = ll;
+                logp[c] = bad ? -INFINITY : std::fma(temperature, ll, logprior[c]);
+                if (bad) logprior[c] = NAN;
+            }
+        }
+    }
+    if (dev) cudaFree(g2);
+    else free(g2);
+    return rc;
 }
 
 #include "jbugs_hmc.inc"

@@ -132,6 +132,7 @@ struct DynSpec {
     static constexpr bool OBS_LOCALS = true;  // unknown at compile time
     static constexpr bool SOFF = false;       // stream offsets come from the kernel parameters
     static constexpr bool XTAPE = false;      // (XSpec: the instantiation that interprets expression tapes)
+    static constexpr int L2PF = 0;            // no L2 prefetch of theta rows
     __device__ __forceinline__ bool prior_fused(int) const { return false; }
     __device__ __forceinline__ bool prior_mu_zero(int) const { return false; }
     const PlateShape& s;
@@ -191,6 +192,7 @@ struct StaticSpec {
     // build_plate and checked by shape_equal), so stream offsets are compile-time constants
     static constexpr bool SOFF = Desc::T_STATIC > 0;
     static constexpr bool XTAPE = false;
+    static constexpr int L2PF = Desc::L2PF;           // groups ahead whose theta rows are prefetched into L2 (0 = off)
     // a dnorm prior whose arguments do not vary over the plate keeps sufficient statistics
     __device__ __forceinline__ constexpr bool prior_fused(int l) const {
         return Desc::sh().loc[l].family == JBUGS_FAM_NORMAL &&

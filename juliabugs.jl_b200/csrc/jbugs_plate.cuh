@@ -10,10 +10,6 @@
 //     gradient rows are stored.
 #pragma once
 
-#ifndef JB_L2PF
-#define JB_L2PF 0
-#endif
-
 namespace jbugs {
 
 // Per-thread accumulators of the fused (sufficient-statistic) paths.  Unused members are dead code
@@ -414,11 +410,11 @@ __device__ __forceinline__ void load_groups(const S& sp, const PlateVals& V, lon
                     pos[l] += V.loc[l].step_i;
                 }
                 gl.raw[u][l] = th[gl.off[u][l]];
-#if JB_L2PF > 0
-                // (A/B) pull the row JB_L2PF groups ahead into L2: no register cost, the later load is an L2 hit
-                if (!sp.loc_has_idx(l))
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(th + gl.off[u][l] + (long long)JB_L2PF * V.loc[l].step_i));
-#endif
+                // FP64-bound plates: pull the row S::L2PF groups ahead into L2 (no register cost; the later load finds it
+                // there).  The theta load right in front of its use was the top stall of the logit kernels (long
+                // scoreboard, profiles/r2_seeds_plate_v5_summary.txt); distance 8 measured best (4..32 tried).
+                if (S::L2PF > 0 && !sp.loc_has_idx(l))
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(th + gl.off[u][l] + (long long)S::L2PF * V.loc[l].step_i));
             }
             if (TS > 0 && l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS && !sp.loc_has_idx(l)) {
                 gl.obase[u][l] = pos[l];

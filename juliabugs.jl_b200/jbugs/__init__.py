@@ -6,8 +6,8 @@ from . import examples, plan  # noqa: F401
 from .lowering import Lowering, LoweringError, lower  # noqa: F401
 from .model import (  # noqa: F401
     BUGSModel, EvaluationMode, LogDensityOrder, LogDensityProblems, UseCUDABatch,
-    UseGeneratedLogDensityFunction, UseGraph, compile, condition, decondition, getparams, set_evaluation_mode,
-    settrans,
+    UseGeneratedLogDensityFunction, UseGraph, compile, condition, decondition, evaluate_with_values, getparams,
+    set_evaluation_mode, settrans,
 )
 from .cuda import CudaPlan, JBugsCudaError  # noqa: F401
 from . import dist, gq, hmc  # noqa: F401,E402

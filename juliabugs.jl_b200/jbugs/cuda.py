@@ -26,7 +26,7 @@ SYMBOLS = [
     "jbugs_comm_destroy", "jbugs_launch_count", "jbugs_plan_describe", "jbugs_plan_set_option",
     "jbugs_last_timing", "jbugs_hmc_create", "jbugs_hmc_destroy", "jbugs_hmc_init", "jbugs_hmc_run",
     "jbugs_hmc_get_state", "jbugs_hmc_run_nuts", "jbugs_hmc_nuts_stats", "jbugs_plan_specialize", "jbugs_hmc_draw_momentum", "jbugs_timing_history", "jbugs_host_alloc_ex",
-    "jbugs_bind_host_to_device", "jbugs_fp64_peak",
+    "jbugs_bind_host_to_device", "jbugs_fp64_peak", "jbugs_eval_batch_tempered",
 ]
 
 
@@ -61,6 +61,8 @@ def load():
     L.jbugs_plan_specialize.argtypes = [c.c_void_p, c.c_char_p]
     L.jbugs_eval_batch.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_void_p, c.c_void_p,
                                    c.c_void_p, c.c_int, c.c_int, c.c_void_p]
+    L.jbugs_eval_batch_tempered.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_double, c.c_void_p,
+                                            c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_void_p]
     L.jbugs_batch_alloc.argtypes = [c.c_void_p, c.c_int64, c.POINTER(c.c_void_p), c.POINTER(c.c_void_p),
                                     c.POINTER(c.c_void_p), c.POINTER(c.c_void_p), c.POINTER(c.c_int64)]
     L.jbugs_batch_free.argtypes = [c.c_void_p]
@@ -201,6 +203,23 @@ class CudaPlan:
         status = np.empty(C, dtype=np.int32)
         self.eval_raw(th, ld, C, lay, logp, grad, status, want_grad)
         return logp, grad, status
+
+    def eval_tempered(self, theta: np.ndarray, temperature: float = 1.0, layout="param_fast", want_grad=True):
+        """(logprior, loglikelihood, tempered_logjoint, grad of the tempered log joint, status) for a (D, C) batch"""
+        theta = np.asarray(theta, dtype=np.float64)
+        if theta.ndim == 1:
+            theta = theta.reshape(-1, 1)
+        D, C = theta.shape
+        if layout == "chain_fast":
+            th, grad, ld, lay = np.ascontiguousarray(theta), np.empty((D, C), order="C"), C, LAYOUT_CHAIN_FAST
+        else:
+            th, grad, ld, lay = np.asfortranarray(theta), np.empty((D, C), order="F"), D, LAYOUT_PARAM_FAST
+        lpr, ll, lp = np.empty(C), np.empty(C), np.empty(C)
+        status = np.empty(C, dtype=np.int32)
+        _check(self.L.jbugs_eval_batch_tempered(self.h, th.ctypes.data, ld, C, lay, float(temperature), lpr.ctypes.data,
+                                                ll.ctypes.data, lp.ctypes.data, grad.ctypes.data if want_grad else None,
+                                                status.ctypes.data, 1 if want_grad else 0, None))
+        return lpr, ll, lp, (grad if want_grad else None), status
 
     def batch_alloc(self, C: int):
         th, g, lp, st = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()

@@ -219,6 +219,17 @@ def getparams(model: BUGSModel) -> np.ndarray:
     return theta
 
 
+def evaluate_with_values(model: BUGSModel, theta, temperature: float = 1.0):
+    """`evaluate_with_values!!(model, theta; temperature)` (src/model/evaluation.jl:217-275) for one theta or a (D, C)
+    batch: dict(logprior, loglikelihood, tempered_logjoint) -- floats for one theta, arrays over chains for a batch.
+    (The evaluation environment the reference also returns is host-side state: `Chains.generated_quantities`.)"""
+    th = np.asarray(theta, dtype=np.float64)
+    single = th.ndim == 1
+    lpr, ll, lp, _, _ = model.cuda.eval_tempered(th.reshape(-1, 1) if single else th, temperature, want_grad=False)
+    pick = (lambda a: float(a[0])) if single else (lambda a: a)
+    return {"logprior": pick(lpr), "loglikelihood": pick(ll), "tempered_logjoint": pick(lp)}
+
+
 class LogDensityProblems:
     """Namespace mirroring LogDensityProblems.jl's generic functions for `BUGSModel`."""
 

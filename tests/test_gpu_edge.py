@@ -254,3 +254,38 @@ def test_abi_error_codes(fixtures):
     cp.eval_raw(th, C, 0, 0, lp, g, st)          # C = 0 is a no-op, not an error
     lp2, g2, st2 = cp.eval_host(th)              # and the handle still works
     assert np.all(st2 == 0) and np.all(np.isfinite(lp2))
+
+
+@pytest.mark.parametrize("name", ["rats", "seeds", "epil", "bones", "dugongs", "stacks"])
+def test_logprior_loglikelihood_and_temperature(fixtures, name):
+    """the (logprior, loglikelihood, tempered_logjoint) triple of evaluate_with_values!! (evaluation.jl:116, 269-274;
+    reference test test/model/evaluation.jl:112-165) and the gradient of the tempered log joint, against the per-node
+    oracle's own split and dual-number gradient"""
+    import graph_oracle as go
+    from helpers import ZOO
+    from numeric import Dual
+    _, text, fx, ini = next(z for z in ZOO if z[0] == name)
+    data, inits = fixtures[fx]["data"], fixtures[fx][ini]
+    m = jbugs.compile(text, data, inits)
+    gm = go.compile(text, data, inits).use_generated_order()
+    th0 = gm.getparams()
+    th0 = np.where(np.isfinite(th0), th0, 0.0)
+    theta = random_thetas(th0, 5, seed=11, scale=0.05)
+    T = 2.5
+    lpr, ll, lp, grad, st = m.cuda.eval_tempered(theta, T)
+    assert (st == 0).all()
+    n = theta.shape[0]
+    for c in range(5):
+        _, r = gm.evaluate_with_values([Dual.seed(float(theta[i, c]), i, n) for i in range(n)], temperature=T)
+        val = lambda x: x.v if isinstance(x, Dual) else float(x)  # noqa: E731
+        assert abs(lpr[c] - val(r["logprior"])) <= 1e-10 * max(1.0, abs(val(r["logprior"])))
+        assert abs(ll[c] - val(r["loglikelihood"])) <= 1e-10 * max(1.0, abs(val(r["loglikelihood"])), abs(val(r["logprior"])))
+        tj = r["tempered_logjoint"]
+        assert abs(lp[c] - tj.v) <= 1e-10 * max(1.0, abs(tj.v))
+        assert grad_err(grad[:, c], np.asarray(tj.d, dtype=float)) < 1e-10
+    # temperature 1 is the ordinary log density; a single theta goes through the host mirror of the reference's name
+    lp1, g1, _ = m.cuda.eval_host(theta, layout="param_fast")
+    _, _, lpt, gt, _ = m.cuda.eval_tempered(theta, 1.0)
+    assert rel_err(lpt, lp1) < 1e-13 and grad_err(gt, g1) < 1e-12
+    r1 = jbugs.evaluate_with_values(m, theta[:, 0], temperature=T)
+    assert r1["tempered_logjoint"] == pytest.approx(r1["logprior"] + T * r1["loglikelihood"], rel=1e-14)
