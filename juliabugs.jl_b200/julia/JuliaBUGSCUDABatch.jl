@@ -67,57 +67,115 @@ function eval_batch!(h::PlanHandle, θ::Matrix{Float64}, logp::Vector{Float64}, 
 end
 
 # ---------------------------------------------------------------------------------------------- the evaluation mode
+include("lower_to_plan.jl")
+using .JBugsLowering
+
 """
     UseCUDABatch(; device=0)
 
 New `EvaluationMode`: the model is lowered at statement/plate granularity to a flat kernel plan
 (`include/jbugs_plan.h`) and evaluated by libjbugs_cuda for a whole batch of chains per launch.
+
+The device state lives IN the mode object (a mutable struct): `BUGSModel` is an immutable struct, so it cannot key a
+`WeakKeyDict`, and the reference resets `evaluation_mode` to `UseGraph()` whenever `condition` / `fix` / `decondition`
+change the graph (src/model/abstractppl.jl:789-797, next to `log_density_computation_function => nothing`) -- the old
+mode object, and with it the plan handle, is dropped exactly where the generated function is.
 """
-struct UseCUDABatch <: EvaluationMode
+mutable struct UseCUDABatch <: EvaluationMode
     device::Int
+    handle::Union{Nothing,PlanHandle}
+    plan::Union{Nothing,JBugsLowering.Plan}
 end
-UseCUDABatch(; device=0) = UseCUDABatch(device)
+UseCUDABatch(; device=0) = UseCUDABatch(device, nothing, nothing)
 
-# Per-model device state, keyed like `log_density_computation_function`: dropped whenever the graph changes.
-const _PLANS = WeakKeyDict{Any,PlanHandle}()
+_label(vn) = replace(string(vn), " " => "")          # "Y[1, 2]" -> "Y[1,2]", the label format of the lowering
 
 """
-    lower_to_plan(model::BUGSModel) -> (blob::Vector{UInt8}, slots::Vector{Vector})
+    lower_to_plan(model::BUGSModel) -> (plan::JBugsLowering.Plan, reconstructed_model_def::Expr)
 
-Statement-level lowering.  It starts from exactly what `_generate_lowered_model_def`
-(src/source_gen.jl:459-552) already computes -- statement ids, the coarse statement graph, the fissioned and
-sorted statements with their loop nests, and the per-statement observed / parameter / generated-quantity
-classes (`:615-666`) -- and, instead of emitting Julia `for` loops, emits for every observed statement one
-plate record (term tape of the inlined linear predictor, inverse-link tape, family, local priors with their
-affine theta-slot maps) plus the data slots.  The record layout is `include/jbugs_plan.h`; the reference
-implementation of this pass, byte-for-byte the same plan, is `jbugs/lowering.py`.
+Statement-level lowering on top of `_generate_lowered_model_def` (src/source_gen.jl:459-552): the reference fissions,
+sorts and regroups the statements and removes transformed data; `JBugsLowering.lower_program` (lower_to_plan.jl) turns
+the reconstructed program into plate records.  Observed / parameter / generated-quantity classes come from
+`model.graph_evaluation_data` (src/model/bugsmodel.jl:118-246), data from `model.data` and the transformed data the
+reference folded into `model.evaluation_env` (src/JuliaBUGS.jl:175-187).
 """
-function lower_to_plan end   # provided by the maintainer-side port of jbugs/lowering.py (see INTEGRATION.md)
+function lower_to_plan(model::BUGSModel)
+    gd = model.graph_evaluation_data
+    lowered, reconstructed = JuliaBUGS._generate_lowered_model_def(
+        model.model_def, model.g, model.evaluation_env;
+        generated_quantities=Set(gd.generated_quantities), fixed_parameters=Set(gd.fixed_parameters))
+    lowered === nothing && throw(JBugsLowering.LoweringError("the reference could not order the statements of this model sequentially"))
+    gq = Set(_label(vn) for vn in gd.generated_quantities)
+    node_info = Dict{String,Tuple{Bool,Bool,Bool}}()
+    for (k, vn) in enumerate(gd.sorted_nodes)
+        lab = _label(vn)
+        node_info[lab] = (gd.is_stochastic_vals[k], gd.is_observed_vals[k], lab in gq)
+    end
+    # data = what the user passed (missing -> NaN) + the transformed data the reference computed: every symbol of the
+    # evaluation environment that no statement of the reconstructed program defines
+    defined = Set{Symbol}()
+    function lhs_symbols(block)
+        for st in block.args
+            st isa Expr || continue
+            if st.head == :for
+                lhs_symbols(st.args[2])
+            elseif st.head == :block
+                lhs_symbols(st)
+            elseif st.head == :(=) || (st.head == :call && st.args[1] == :~)
+                l = st.head == :(=) ? st.args[1] : st.args[2]
+                push!(defined, l isa Symbol ? l : l.args[1])
+            end
+        end
+    end
+    lhs_symbols(reconstructed)
+    tofloat(v) = v isa AbstractArray ? map(x -> ismissing(x) ? NaN : Float64(x), v) : (ismissing(v) ? NaN : Float64(v))
+    data = Dict{Symbol,Any}()
+    for (k, v) in pairs(model.evaluation_env)
+        k in defined || (data[k] = tofloat(v))
+    end
+    for (k, v) in pairs(model.data)
+        data[k] = tofloat(v)
+    end
+    plan, _ = JBugsLowering.lower_program(reconstructed, data, node_info; transformed=model.transformed)
+    return plan, reconstructed
+end
 
 function plan_handle(model::BUGSModel)
     mode = model.evaluation_mode::UseCUDABatch
-    get!(_PLANS, model) do
-        blob, slots = lower_to_plan(model)
-        h = PlanHandle(blob, mode.device)
-        foreach(((k, v),) -> upload!(h, k - 1, v), enumerate(slots))
-        h
+    if mode.handle === nothing
+        plan, _ = lower_to_plan(model)
+        h = PlanHandle(JBugsLowering.to_bytes(plan), mode.device)
+        foreach(((k, sl),) -> upload!(h, k - 1, sl.values), enumerate(plan.data))
+        mode.handle, mode.plan = h, plan
     end
+    return mode.handle
 end
 
-# set_evaluation_mode(model, UseCUDABatch()) : same contract as the generated mode (transformed space only,
-# parameter order rebuilt from the reconstructed program, bugsmodel.jl:770-799)
+# set_evaluation_mode(model, UseCUDABatch()): the parameter order is rebuilt from the reconstructed program exactly as the
+# generated mode does (src/model/bugsmodel.jl:770-799) so that getparams / dimension / chain naming follow the plan's
+# theta layout.  Works in both spaces: `settrans(model, false)` gives identity transforms in the plan.
 function JuliaBUGS.set_evaluation_mode(model::BUGSModel, mode::UseCUDABatch)
-    model.transformed || error("UseCUDABatch evaluates in transformed (unconstrained) space; call settrans(model, true)")
-    model = JuliaBUGS.set_evaluation_mode(model, JuliaBUGS.UseGeneratedLogDensityFunction())  # fixes sorted_nodes
-    return JuliaBUGS.BangBang.setproperty!!(model, :evaluation_mode, mode)
+    _, reconstructed = lower_to_plan(model)
+    pass = JuliaBUGS.CollectSortedNodes(model.evaluation_env)
+    JuliaBUGS.analyze_block(pass, reconstructed)
+    gd = model.graph_evaluation_data
+    sorted_nodes = filter(node -> node in gd.sorted_nodes, pass.sorted_nodes)
+    new_gd = JuliaBUGS.Model.GraphEvaluationData(model.g, sorted_nodes;
+                                                 generated_quantities=Set(gd.generated_quantities),
+                                                 fixed_parameters=Set(gd.fixed_parameters))
+    model = JuliaBUGS.BangBang.setproperty!!(model, :graph_evaluation_data, new_gd)
+    # (the same call the reference ends its own set_evaluation_mode with, bugsmodel.jl:876)
+    return JuliaBUGS.BangBang.setproperty!!(model, :evaluation_mode, UseCUDABatch(mode.device, nothing, nothing))
 end
 
-# condition / fix / decondition create a new model object (abstractppl.jl:740-809): the WeakKeyDict entry of the
-# old object dies with it.  set_observed_values! keeps the structure: re-upload, do not re-plan.
+# set_observed_values! keeps the structure (abstractppl.jl:872-888): re-lower for the new values, re-upload, do not re-plan
 function reupload!(model::BUGSModel)
     h = plan_handle(model)
-    _, slots = lower_to_plan(model)
-    foreach(((k, v),) -> upload!(h, k - 1, v), enumerate(slots))
+    plan, _ = lower_to_plan(model)
+    JBugsLowering.to_bytes(plan) == JBugsLowering.to_bytes(model.evaluation_mode.plan) ||
+        error("the new observations change the structure of the plan (e.g. the missingness pattern): set the evaluation mode again")
+    foreach(((k, sl),) -> upload!(h, k - 1, sl.values), enumerate(plan.data))
+    model.evaluation_mode.plan = plan
     return model
 end
 
