@@ -111,7 +111,9 @@ enum jbugs_op {
     JBUGS_OP_POW = 20,
     /* expression tapes only */
     JBUGS_OP_LEAF = 32,  /* value of `leaf`: CONST | ONE | GVAL | GVEC_J | LOCAL | DATA_I | DATA_J | DATA_IJ */
-    JBUGS_OP_SELECT = 33 /* v[a] != 0 ? v[b] : v[c]  (a: a 0/1 data leaf; no adjoint flows into a)          */
+    JBUGS_OP_SELECT = 33,/* v[a] != 0 ? v[b] : v[c]  (a: a 0/1 data leaf; no adjoint flows into a)          */
+    JBUGS_OP_PICK_K = 34 /* v[a + k], k = the state of the plate's marginalised discrete latent (has_obs == 3):
+                            slots a .. a + K - 1 hold the K candidates (`mu[z[i]]` -> mu[1], ..., mu[K])         */
 };
 
 /* ---- expression tape of a plate whose predictor is not linear in the parameters -----------------------------
@@ -120,6 +122,7 @@ enum jbugs_op {
  * the chain of logical parents of ONE observation, in static single assignment form: op k produces value slot k from
  * slots a, b, c < k.  The forward sweep fills the slots, the reverse sweep carries adjoints back to the leaves. */
 #define JBUGS_MAX_XOPS 64
+#define JBUGS_MAX_STATES 16 /* states of a discrete latent that is summed out per observation (has_obs == 3) */
 typedef struct jbugs_xop {
     uint32_t op;       /* jbugs_op */
     uint16_t a, b, c;  /* operand slots */
@@ -183,7 +186,13 @@ typedef struct jbugs_plate {
     uint32_t has_obs;              /* 0: prior-only plate (locals without a likelihood); 1: linear predictor (terms +
                                       link); 2: expression plate -- first_term / n_terms address xops[] instead of
                                       terms[], n_link = 0, and the family arguments that depend on parameters are
-                                      XVAL references into the tape */
+                                      XVAL references into the tape; 3: expression plate with a finite discrete
+                                      latent per observation that is summed out (auto-marginalisation,
+                                      evaluation.jl:739-961): eta_arg holds the number of states K, link[0] the tape
+                                      slot of the latent's log prior log p(z = k), link[1] - 1 the tape slot of a data leaf
+                                      with the observed state of a partially observed latent (0 = missing; link[1] == 0:
+                                      no cell is observed); the cell contributes
+                                      logsumexp_k [ log p(z = k) + log p(y | z = k) ] */
     jbugs_arg y;                   /* DATA_I | DATA_IJ */
     jbugs_arg aux[3];              /* the family's arguments; aux[eta_arg] is ignored (has_obs == 1) */
 } jbugs_plate;                     /* 128 bytes */

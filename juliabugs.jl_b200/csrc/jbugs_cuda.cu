@@ -333,6 +333,16 @@ static int build_xplate(jbugs_plan* p, int k) {
     const int nx = (int)pl.n_terms;
     if (nx < 1 || nx > JBUGS_MAX_XOPS) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: expression tape of %d ops (1..%d supported)", k, nx, JBUGS_MAX_XOPS);
     if (pl.n_link != 0) return fail(JBUGS_ERR_INVALID, "plate %d: an expression plate has no link tape", k);
+    // has_obs == 3: a discrete latent per observation is summed out; eta_arg holds its number of states, link[0] the
+    // tape slot of log p(z = k)
+    const int K = pl.has_obs == 3 ? (int)pl.eta_arg : 0;
+    if (pl.has_obs == 3 && (K < 1 || K > JBUGS_MAX_STATES || (int)pl.link[0] >= nx))
+        return fail(JBUGS_ERR_INVALID, "plate %d: %d latent states (1..%d) / log-prior slot %u outside the tape", k, K, JBUGS_MAX_STATES, pl.link[0]);
+    sh.n_states = K; sh.lp_slot = K > 0 ? (int)pl.link[0] : 0;
+    sh.zobs_slot = K > 0 ? (int)pl.link[1] - 1 : -1;
+    if (sh.zobs_slot >= nx || (sh.zobs_slot >= 0 && (X[sh.zobs_slot].op != JBUGS_OP_LEAF ||
+            (X[sh.zobs_slot].leaf.kind != JBUGS_ARG_DATA_I && X[sh.zobs_slot].leaf.kind != JBUGS_ARG_DATA_IJ))))
+        return fail(JBUGS_ERR_INVALID, "plate %d: the latent's observed-state slot must be a data leaf of the tape", k);
     sh.kg = 0; sh.nl = (int)pl.n_locals; sh.has_off = 0;
     sh.family = (int)pl.family; sh.eta_arg = 0; sh.has_obs = 1; sh.n_link = 0; sh.n_x = nx;
     V.N = pl.N; V.T = pl.T;
@@ -375,6 +385,8 @@ static int build_xplate(jbugs_plan* p, int k) {
             o.kind = s2.kind; o.id = s2.id; o.soff = v2.soff; o.value = a.kind == JBUGS_ARG_ONE ? 1.0 : a.value;
         } else if (X[q].op == JBUGS_OP_SELECT) {
             if (o.a >= q || o.b >= q || o.c >= q) return fail(JBUGS_ERR_INVALID, "plate %d: tape op %d looks forward", k, q);
+        } else if (X[q].op == JBUGS_OP_PICK_K) {
+            if (K < 1 || (int)o.a + K > q) return fail(JBUGS_ERR_INVALID, "plate %d: tape op %d picks outside the tape or without a latent", k, q);
         } else if (unary || binary) {
             if (o.a >= q || (binary && o.b >= q)) return fail(JBUGS_ERR_INVALID, "plate %d: tape op %d looks forward", k, q);
             if (unary && X[q].op > JBUGS_OP_NEG) return fail(JBUGS_ERR_INVALID, "plate %d: unknown tape op %u", k, X[q].op);
@@ -417,9 +429,10 @@ static int build_plate(jbugs_plan* p, int k) {
     if (pl.n_locals > (uint32_t)MAX_LOC) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: more than %d locals", k, MAX_LOC);
     if (pl.n_link > JBUGS_MAX_LINK) return fail(JBUGS_ERR_INVALID, "plate %d: link tape too long", k);
     if (pl.family >= JBUGS_FAM_COUNT) return fail(JBUGS_ERR_INVALID, "plate %d: unknown family", k);
+    if (pl.has_obs > 3) return fail(JBUGS_ERR_INVALID, "plate %d: unknown plate kind", k);
+    if (pl.has_obs >= 2) return build_xplate(p, k);
     if (pl.eta_arg > 1) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: eta_arg > 1", k);
     const jbugs_local* L = p->locals.data() + pl.first_local;
-    if (pl.has_obs == 2) return build_xplate(p, k);
     const jbugs_term* T = p->terms.data() + pl.first_term;
     std::vector<int> gref;
     // canonical term order: GVAL-coef terms, then one term per local (in local order), then an offset
@@ -575,7 +588,7 @@ extern "C" int jbugs_plan_create(const void* blob, size_t nbytes, int device, jb
     };
     // validation of record ranges
     for (auto& pl : p->plates) {
-        const size_t tape_len = pl.has_obs == 2 ? p->xops.size() : p->terms.size();
+        const size_t tape_len = pl.has_obs >= 2 ? p->xops.size() : p->terms.size();
         if ((size_t)pl.first_local + pl.n_locals > p->locals.size() || (size_t)pl.first_term + pl.n_terms > tape_len)
             return destroy(fail(JBUGS_ERR_INVALID, "plate record ranges exceed the blob"));
     }

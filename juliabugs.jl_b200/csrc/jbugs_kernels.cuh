@@ -89,6 +89,9 @@ struct PlateShape {
     ArgS y, aux[3];
     LocalS loc[MAX_LOC];
     int n_x;  // > 0: expression plate (has_obs == 2): the predictor is the tape PlateVals::xtape, aux[q] may be XVAL
+    int n_states, lp_slot, zobs_slot;  // n_states > 0 (has_obs == 3 in the record): one discrete latent per observation is summed out
+                            // over its n_states states; tape slot lp_slot holds log p(z = k), zobs_slot (or -1) the data
+                            // leaf with the observed state of a partially observed latent (0 = missing)
 };
 
 struct PlateVals {
@@ -164,6 +167,9 @@ struct XSpec : DynSpec {
     static constexpr bool XTAPE = true;
     __device__ __forceinline__ explicit XSpec(const PlateShape& sh) : DynSpec(sh) {}
     __device__ __forceinline__ int n_x() const { return s.n_x; }
+    __device__ __forceinline__ int n_states() const { return s.n_states; }
+    __device__ __forceinline__ int lp_slot() const { return s.lp_slot; }
+    __device__ __forceinline__ int zobs_slot() const { return s.zobs_slot; }
 };
 
 // fused observation paths (family x link pairs with a hand-derived forward+reverse)

@@ -204,31 +204,36 @@ __device__ __forceinline__ double predictor(const S& sp, const PlateVals& V, con
     return eta;
 }
 
-// one observation of an expression plate: forward sweep over the tape, the family, reverse sweep back to the leaves
-// (the composed node functions of the observation's logical parents, compiler_pass.jl:751-814, in SSA form)
+__device__ __forceinline__ double tape_leaf(const XOpDev& o, const StageView& sv, int g, int j, const ChainState& st) {
+    switch (o.kind) {
+    case JBUGS_ARG_CONST: return o.value;
+    case JBUGS_ARG_ONE: return 1.0;
+    case JBUGS_ARG_GVAL: return pick(st.gv, o.id);
+    case JBUGS_ARG_GVEC_J: return pick(st.gv, o.id + j);
+    case JBUGS_ARG_LOCAL: return pick(st.lx, o.id);
+    case JBUGS_ARG_DATA_I: return sv.chunk[o.soff + g];
+    case JBUGS_ARG_DATA_J: return sv.jreg[o.soff + j];
+    case JBUGS_ARG_DATA_IJ: return sv.chunk[o.soff + j * STAGE_G + g];
+    default: return dev_nan();
+    }
+}
+
+// forward sweep of an expression tape for one observation; `state` is the state of the discrete latent being summed out
+// (PICK_K ops), 0 when there is none.  d1 / d2 receive the partial derivatives of each op for the reverse sweep.
 template <class S>
-__device__ __noinline__ bool observe_tape(const S& sp, const PlateVals& V, const StageView& sv, int g, int j,
-                                          ChainState& st, double& lp) {
-    double v[JBUGS_MAX_XOPS], w[JBUGS_MAX_XOPS], d1[JBUGS_MAX_XOPS], d2[JBUGS_MAX_XOPS];
+__device__ __noinline__ bool tape_forward(const S& sp, const PlateVals& V, const StageView& sv, int g, int j,
+                                          const ChainState& st, int state, double* v, double* d1, double* d2) {
     const int nx = sp.n_x();
     bool bad = false;
     for (int k = 0; k < nx; ++k) {
         const XOpDev o = V.xtape[k];
-        w[k] = 0.0; d1[k] = 0.0; d2[k] = 0.0;
+        d1[k] = 0.0; d2[k] = 0.0;
         if (o.op == JBUGS_OP_LEAF) {
-            switch (o.kind) {
-            case JBUGS_ARG_CONST: v[k] = o.value; break;
-            case JBUGS_ARG_ONE: v[k] = 1.0; break;
-            case JBUGS_ARG_GVAL: v[k] = pick(st.gv, o.id); break;
-            case JBUGS_ARG_GVEC_J: v[k] = pick(st.gv, o.id + j); break;
-            case JBUGS_ARG_LOCAL: v[k] = pick(st.lx, o.id); break;
-            case JBUGS_ARG_DATA_I: v[k] = sv.chunk[o.soff + g]; break;
-            case JBUGS_ARG_DATA_J: v[k] = sv.jreg[o.soff + j]; break;
-            case JBUGS_ARG_DATA_IJ: v[k] = sv.chunk[o.soff + j * STAGE_G + g]; break;
-            default: v[k] = dev_nan(); break;
-            }
+            v[k] = tape_leaf(o, sv, g, j, st);
         } else if (o.op == JBUGS_OP_SELECT) {
             v[k] = v[o.a] != 0.0 ? v[o.b] : v[o.c];
+        } else if (o.op == JBUGS_OP_PICK_K) {
+            v[k] = v[o.a + state];
         } else if (o.op < 16) {
             bad |= unary_op(o.op, v[o.a], v[k], d1[k]);
         } else {
@@ -245,24 +250,40 @@ __device__ __noinline__ bool observe_tape(const S& sp, const PlateVals& V, const
             }
         }
     }
+    return bad;
+}
+
+// the family of an expression plate at the tape's values; seeds the adjoints w[] of the tape slots its arguments sit in
+// (scaled by r: the posterior weight of the latent's state, 1 without a latent) when `seed` is set
+template <class S>
+__device__ __noinline__ bool tape_family(const S& sp, const PlateVals& V, const StageView& sv, int g, int j, ChainState& st,
+                                         const double* v, double* w, double yv, double r, bool seed, double& lp_out) {
     double a[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const ArgS s = sp.aux(q);
         a[q] = s.kind == JBUGS_ARG_XVAL ? v[s.id] : arg_value(s, V.aux[q], st, sv, g, j);
     }
-    const double yv = arg_value(sp.y(), V.y, st, sv, g, j);
     FamOut o;
-    bad |= fam_eval(sp.family(), yv, a[0], a[1], o, V.aux[2].value);
-    lp += o.lp;
+    const bool bad = fam_eval(sp.family(), yv, a[0], a[1], o, V.aux[2].value);
+    lp_out = o.lp;
+    if (seed) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const ArgS s = sp.aux(q);
-        const double da = q == 0 ? o.da0 : o.da1;
-        if (s.kind == JBUGS_ARG_XVAL) w[s.id] += da;
-        else arg_adjoint(s, st, da);
+        for (int q = 0; q < 2; ++q) {
+            const ArgS s = sp.aux(q);
+            const double da = r * (q == 0 ? o.da0 : o.da1);
+            if (s.kind == JBUGS_ARG_XVAL) w[s.id] += da;
+            else arg_adjoint(s, st, da);
+        }
     }
-    for (int k = nx - 1; k >= 0; --k) {
+    return bad;
+}
+
+// reverse sweep: adjoints w[] back to the leaves (global / local adjoint accumulators of the chain)
+template <class S>
+__device__ __noinline__ void tape_reverse(const S& sp, const PlateVals& V, int j, ChainState& st, int state, const double* v,
+                                          double* w, const double* d1, const double* d2) {
+    for (int k = sp.n_x() - 1; k >= 0; --k) {
         const double wk = w[k];
         if (wk == 0.0) continue;
         const XOpDev o = V.xtape[k];
@@ -272,10 +293,65 @@ __device__ __noinline__ bool observe_tape(const S& sp, const PlateVals& V, const
             else if (o.kind == JBUGS_ARG_LOCAL) bump(st.la, o.id, wk);
         } else if (o.op == JBUGS_OP_SELECT) {
             w[v[o.a] != 0.0 ? o.b : o.c] += wk;
+        } else if (o.op == JBUGS_OP_PICK_K) {
+            w[o.a + state] += wk;
         } else {
             w[o.a] += wk * d1[k];
             if (o.op >= 16) w[o.b] += wk * d2[k];
         }
+    }
+}
+
+// one observation of an expression plate: forward sweep over the tape, the family, reverse sweep back to the leaves
+// (the composed node functions of the observation's logical parents, compiler_pass.jl:751-814, in SSA form).
+// With a discrete latent that is summed out (n_states > 0; evaluation.jl:739-961 for one latent per plate cell): the
+// cell contributes logsumexp_k [log p(z = k) + log p(y | z = k)] -- a first round of forward sweeps for the K branch
+// values, a second one whose reverse sweeps are weighted by the posterior probability of each state.
+template <class S>
+__device__ __noinline__ bool observe_tape(const S& sp, const PlateVals& V, const StageView& sv, int g, int j,
+                                          ChainState& st, double& lp) {
+    double v[JBUGS_MAX_XOPS], w[JBUGS_MAX_XOPS], d1[JBUGS_MAX_XOPS], d2[JBUGS_MAX_XOPS];
+    const int nx = sp.n_x();
+    const int K = sp.n_states();
+    const double yv = arg_value(sp.y(), V.y, st, sv, g, j);
+    bool bad = false;
+    double l1;
+    if (K <= 0) {
+        bad |= tape_forward(sp, V, sv, g, j, st, 0, v, d1, d2);
+        for (int k = 0; k < nx; ++k) w[k] = 0.0;
+        bad |= tape_family(sp, V, sv, g, j, st, v, w, yv, 1.0, true, l1);
+        lp += l1;
+        tape_reverse(sp, V, j, st, 0, v, w, d1, d2);
+        return bad;
+    }
+    double branch[JBUGS_MAX_STATES];
+    const int lps = sp.lp_slot();
+    // a partially observed latent: an observed cell (state > 0 in the data leaf) takes the branch of its value only
+    const int zo = sp.zobs_slot() >= 0 ? (int)tape_leaf(V.xtape[sp.zobs_slot()], sv, g, j, st) : 0;
+    double mx = -dev_inf();
+    for (int k = 0; k < K; ++k) {
+        if (zo > 0 && k != zo - 1) { branch[k] = -dev_inf(); continue; }
+        bad |= tape_forward(sp, V, sv, g, j, st, k, v, d1, d2);
+        bad |= tape_family(sp, V, sv, g, j, st, v, w, yv, 0.0, false, l1);
+        branch[k] = l1 + v[lps];
+        mx = branch[k] > mx ? branch[k] : mx;
+    }
+    if (!(mx > -dev_inf())) {  // no state has support (or NaN): nothing to differentiate
+        lp += mx;
+        return bad;
+    }
+    double sum = 0.0;
+    for (int k = 0; k < K; ++k) sum += exp(branch[k] - mx);
+    const double lse = mx + log(sum);
+    lp += lse;
+    for (int k = 0; k < K; ++k) {
+        const double r = exp(branch[k] - lse);
+        if (r == 0.0) continue;
+        tape_forward(sp, V, sv, g, j, st, k, v, d1, d2);
+        for (int q = 0; q < nx; ++q) w[q] = 0.0;
+        w[lps] = r;
+        tape_family(sp, V, sv, g, j, st, v, w, yv, r, true, l1);
+        tape_reverse(sp, V, j, st, k, v, w, d1, d2);
     }
     return bad;
 }

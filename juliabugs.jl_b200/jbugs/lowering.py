@@ -52,6 +52,7 @@ class Stmt:
     ragged: bool = False           # a loop bound depends on an enclosing loop variable (`for k in 1:ncat[j]-1`): the
                                    # statement has no rectangular domain; it can be folded pointwise (data) or inlined
     obs_mask: object = None        # partially observed statement: boolean array over the loop domain (True = observed)
+    zobs: object = None            # discrete latent being summed out, partially observed: its value per cell, 0 = missing
 
     @property
     def name(self):
@@ -103,9 +104,10 @@ class DataEval:
     def __init__(self, data: Dict[str, object]):
         self.data = data
         self.lenient = False   # clamp out-of-range / missing subscripts (set while evaluating case-split leaves)
+        self.unknown = set()   # data arrays that are not data for the lowering: partially observed latents being summed out
 
     def known(self, e, loop_vars=()) -> bool:
-        return all((v in self.data) or (v in loop_vars) for v in free_vars(e))
+        return all(((v in self.data) and (v not in self.unknown)) or (v in loop_vars) for v in free_vars(e))
 
     def ev(self, e, lv: Dict[str, np.ndarray]):
         if isinstance(e, Num):
@@ -248,9 +250,12 @@ ONE = Num(1.0)
 
 
 class Lowering:
-    def __init__(self, model_text, data, transformed=True, theta_order=None):
+    def __init__(self, model_text, data, transformed=True, theta_order=None, marginalize=False):
         self.stmts_ast = parse(model_text) if isinstance(model_text, str) else tuple(model_text)
         self.transformed = transformed
+        # UseAutoMarginalization (bugsmodel.jl:803-876): unobserved finite discrete nodes are summed out instead of
+        # being parameters; theta holds the continuous parameters only
+        self.marginalize = marginalize
         self.data: Dict[str, object] = {}
         for k, v in data.items():
             if isinstance(v, (list, tuple)):
@@ -411,6 +416,11 @@ class Lowering:
                     miss = np.isnan(np.broadcast_to(sub, s.shape))
                     if miss.all():
                         s.kind = "param"
+                    elif miss.any() and s.node.dist.fn == "dcat" and self.marginalize:
+                        # a partially observed discrete latent (auto_marginalization.jl:391-462): the missing cells are
+                        # summed out, the observed ones take the branch of their value
+                        s.kind = "param"
+                        s.zobs = np.where(miss, 0.0, np.broadcast_to(sub, s.shape)).astype(np.float64)
                     elif miss.any():
                         # the missing cells are unobserved stochastic nodes.  When nothing depends on the variable they
                         # have no observed descendants: generated quantities, outside the target (graphs.jl:27-71; the
@@ -424,11 +434,22 @@ class Lowering:
                     s.kind = "param" if math.isnan(arr) else "obs"
             else:
                 s.kind = "param"
+        for s in self.stmts:
+            if s.kind == "param" and s.node.dist.fn in ("dcat", "dbern", "dbin"):
+                # an unobserved finite discrete node: a parameter with the identity bijector in UseGraph / UseGeneratedLogDensityFunction
+                # (the reference evaluates the pmf at theta's value); summed out under UseAutoMarginalization
+                if not self.marginalize:
+                    continue
+                if s.node.dist.fn != "dcat":
+                    raise LoweringError(f"'{s.name}': only dcat latents are summed out")
+                s.kind = "latent"
+                if s.zobs is not None:
+                    self.de.unknown.add(s.name)
         # statement-level dependence edges: parent statement -> child statement
         self.children: Dict[int, set] = {s.sid: set() for s in self.stmts}
         by_name: Dict[str, List[Stmt]] = {}
         for s in self.stmts:
-            if s.kind in ("param", "logical"):
+            if s.kind in ("param", "logical", "latent"):
                 by_name.setdefault(s.name, []).append(s)
         for s in self.stmts:
             if s.kind == "tdata":
@@ -438,7 +459,7 @@ class Lowering:
                 for parent in by_name.get(v, []):
                     if parent.sid != s.sid:
                         self.children[parent.sid].add(s.sid)
-                    elif s.kind in ("param", "logical"):
+                    elif s.kind in ("param", "logical", "latent"):
                         raise LoweringError(f"loop-carried self dependence in statement {s.sid} ({s.name})")
         referenced = set()
         for t in self.stmts:
@@ -463,7 +484,7 @@ class Lowering:
 
         has_obs = any(s.kind == "obs" for s in self.stmts)
         for s in self.stmts:
-            if s.kind in ("param", "logical"):
+            if s.kind in ("param", "logical", "latent"):
                 s.is_gq = not reach(s.sid)
         if not has_obs:
             # bugsmodel.jl:181-199: without observations stochastic nodes stay parameters
@@ -629,6 +650,10 @@ class Lowering:
                     d = defs[0]
                     sub = {li.name: ri for li, ri in zip(d.node.lhs.idx, idx)}
                     return self._inline(_subst(d.node.rhs, sub), depth + 1)
+                if any(isinstance(i, (Index, Var)) and any(d.kind == "latent" for d in self._defs(i.name)) for i in idx):
+                    # w[z[i]] with w defined element by element and z a discrete latent that is summed out: the tape
+                    # gathers the candidates w[1], ..., w[K] and picks by the state (_tape), no case split on data
+                    return Index(e.name, idx)
                 # several defining statements and / or constant subscripts on their left-hand sides (Bones: p[i,j,1],
                 # p[i,j,k] for k in 2:ncat[j]-1, p[i,j,ncat[j]]): a case split.  Statement d defines the referenced
                 # element where its loop variables, solved from the reference's subscripts, lie inside their (possibly
@@ -785,6 +810,35 @@ class Lowering:
                     for d in self._defs(r.name):
                         if d.kind == "param" and len(d.loops) == 1 and d.extents == s.extents[1:] and d.size <= 10:
                             found.add(d.sid)
+        # parameter vectors subscripted by a discrete latent that is summed out (mixtures: mu[z[i]], sigma[z[i]])
+        latents = {d.name for d in self.stmts if d.kind == "latent"}
+        if latents:
+            def walk_latent(e, via=False):
+                """`via`: e sits inside the definition of a looped logical node that is itself selected by the latent
+                (tau[k] <- 1 / (sigma[k] * sigma[k]) referenced as tau[z[i]]): its looped parameters are selected too"""
+                if isinstance(e, Index):
+                    if via or any(isinstance(i, (Index, Var)) and i.name in latents for i in e.idx):
+                        for d in self._defs(e.name):
+                            if d.kind == "param" and d.loops and not d.is_gq:
+                                if d.size > 48:
+                                    raise LoweringError(f"'{e.name}' has too many elements to expand into scalar globals")
+                                found.add(d.sid)
+                            elif d.kind == "logical" and d.loops:
+                                walk_latent(d.node.rhs, True)
+                    for i in e.idx:
+                        walk_latent(i)
+                elif isinstance(e, Call):
+                    for a in e.args:
+                        walk_latent(a, via)
+                elif isinstance(e, BinOp):
+                    walk_latent(e.a, via)
+                    walk_latent(e.b, via)
+                elif isinstance(e, Neg):
+                    walk_latent(e.a, via)
+            for s in self.stmts:
+                if s.kind == "obs" and not s.is_gq:
+                    for a in s.node.dist.args:
+                        walk_latent(a)
         for s in self.stmts:
             if s.is_gq:
                 continue
@@ -1059,6 +1113,33 @@ class Lowering:
         fill = vals[~np.isnan(vals)][0] if np.any(~np.isnan(vals)) else 0.0
         yslot.values = np.where(np.isnan(vals), fill, vals)
 
+    def _latent_ref(self, ie, s: Stmt):
+        """(latent statement, K) when `ie` is a reference `z[i]` / `z` to a discrete latent of this plate that is being
+        summed out, else None"""
+        if not isinstance(ie, (Index, Var)):
+            return None
+        ds = [d for d in self._defs(ie.name) if d.kind == "latent"]
+        if not ds:
+            return None
+        d = ds[0]
+        if len(ds) != 1 or d.loops != s.loops[:len(d.loops)] or d.is_gq:
+            raise LoweringError(f"'{ie.name}': a discrete latent must share the loop nest of the observation it selects for")
+        idx = ie.idx if isinstance(ie, Index) else ()
+        lhs_idx = d.node.lhs.idx if isinstance(d.node.lhs, Index) else ()
+        if tuple(_show(a) for a in idx) != tuple(_show(a) for a in lhs_idx):
+            raise LoweringError(f"'{ie.name}' must be referenced with the subscripts of its own statement")
+        wa = d.node.dist.args[0]
+        if not (isinstance(wa, Index) and isinstance(wa.idx[-1], Range) and self._is_data(wa.idx[-1].lo, ()) and
+                self._is_data(wa.idx[-1].hi, ()) and int(self.de.ev(wa.idx[-1].lo, {})) == 1):
+            raise LoweringError("the latent's dcat needs a probability vector w[..., 1:K] with constant K")
+        K = int(self.de.ev(wa.idx[-1].hi, {}))
+        if not 1 <= K <= 16:
+            raise LoweringError("between 1 and 16 states can be summed out per observation")
+        if self._latent is not None and self._latent[0].sid != d.sid:
+            raise LoweringError("one discrete latent per observation plate")
+        self._latent = (d, K)
+        return d, K
+
     # ---- predictors that are not linear in the parameters -> expression plate ------------------------------------------
     def _is_gvec_ref(self, s: Stmt, ref) -> bool:
         """('l', name, idx) is a reference `name[k]` with k the INNER loop variable of a two-loop observation whose
@@ -1076,8 +1157,11 @@ class Lowering:
         lhs = s.node.lhs
         lhs_e = lhs if isinstance(lhs, Index) else Var(lhs.name)
         if not shape:
-            raise LoweringError("a scalar observation with a non-linear predictor is outside the plate class")
-        plate.y = self._data_arg(lhs_e, lv_names, shape, lv_names)
+            # a scalar observation (y ~ dnorm(mu + delta[z], tau)): a plate of one cell
+            yv = self.de.ev(lhs_e, {})
+            plate.y = P.Arg(P.ARG_DATA_I, self._slot(f"scalar_obs|{s.name}", np.array([float(yv)])))
+        else:
+            plate.y = self._data_arg(lhs_e, lv_names, shape, lv_names)
         if plate.y.kind in (P.ARG_CONST, P.ARG_ONE, P.ARG_DATA_J):
             raise LoweringError("observation does not vary over its plate")
         args = list(s.node.dist.args)
@@ -1090,6 +1174,7 @@ class Lowering:
             args = [Index(pa.name, pa.idx[:-1] + (lhs_e,))]
         tape: List[P.XOp] = []
         memo: Dict[str, int] = {}
+        self._latent = None   # (statement of the discrete latent summed out in this plate, K), found while taping
         self.de.lenient = True
         try:
             aux = []
@@ -1108,6 +1193,36 @@ class Lowering:
         if not tape:
             raise LoweringError("internal: an expression plate without a tape")
         plate.aux = aux
+        if self._latent is not None:
+            # log p(z = k): the latent's own dcat(w[1:K]) picked at the state
+            z, K = self._latent
+            wa = z.node.dist.args[0]
+            self.de.lenient = True
+            try:
+                zref = z.node.lhs if isinstance(z.node.lhs, Index) else Var(z.name)
+                pk = Index(wa.name, wa.idx[:-1] + (zref,))
+                plate.logprior_slot = self._tape(Call("log", (pk,)), s, plate, tape, memo, used_locals)
+            finally:
+                self.de.lenient = False
+            plate.n_states = K
+            if z.zobs is not None:
+                if len(z.loops) not in (1, 2) or len(z.loops) != len(s.loops):
+                    raise LoweringError(f"'{z.name}': a partially observed latent must be indexed like its observation")
+                zo = z.zobs
+                if np.any((zo != np.floor(zo)) | (zo < 0) | (zo > K)):
+                    raise LoweringError(f"'{z.name}': observed states must be integers in 1..{K}")
+                if zo.ndim == 1:
+                    leaf = P.Arg(P.ARG_DATA_I, self._slot(f"latent_obs|{z.name}", zo.copy()))
+                else:
+                    leaf = P.Arg(P.ARG_DATA_IJ, self._slot(f"latent_obs|{z.name}", np.asfortranarray(zo).ravel(order="F"),
+                                                           rank=2, dim0=zo.shape[0]))
+                if len(tape) + 1 > P.MAX_XOPS:
+                    raise LoweringError(f"the predictor needs more than {P.MAX_XOPS} tape ops")
+                tape.append(P.XOp(P.OP_LEAF, leaf=leaf))
+                plate.zobs_slot = len(tape) - 1
+            plate.name += f", {z.name} summed out over {K} states"
+            used_locals.add(z.sid)
+            self._latent = None
         plate.xops = tape
         self._apply_obs_mask(plate, s)
         return plate
@@ -1158,6 +1273,21 @@ class Lowering:
         if isinstance(e, Var):
             return push(P.XOp(P.OP_LEAF, leaf=P.Arg.gval(self._gval_of(e.name))))
         if isinstance(e, Index):
+            lat = [q for q, ie in enumerate(e.idx) if self._latent_ref(ie, s) is not None]
+            if lat:
+                # name[.., z[i], ..] with z a discrete latent that is summed out: the K candidates name[.., k, ..] in
+                # consecutive slots (identity copies gather them), picked by the state
+                if len(lat) != 1:
+                    raise LoweringError("a reference may use the discrete latent in one subscript only")
+                z, K = self._latent_ref(e.idx[lat[0]], s)
+                slots = [rec(self._inline(Index(e.name, e.idx[:lat[0]] + (Num(float(k), True),) + e.idx[lat[0] + 1:])))
+                         for k in range(1, K + 1)]
+                first = len(tape)
+                for k, sl in enumerate(slots):
+                    tape.append(P.XOp(P.OP_IDENTITY, sl))
+                if len(tape) + 1 > P.MAX_XOPS:
+                    raise LoweringError(f"the predictor needs more than {P.MAX_XOPS} tape ops")
+                return push(P.XOp(P.OP_PICK_K, first))
             lab = self._elem_label(e)
             if lab is not None and lab in self._gval_ids:
                 return push(P.XOp(P.OP_LEAF, leaf=P.Arg.gval(self._gval_ids[lab])))
@@ -1546,6 +1676,21 @@ def _affine_or_index(tidx: np.ndarray):
     return (base, si, sj, None) if np.array_equal(tidx, fit) else (0, 0, 0, True)
 
 
+def _subexprs(e):
+    yield e
+    if isinstance(e, Index):
+        for i in e.idx:
+            yield from _subexprs(i)
+    elif isinstance(e, Call):
+        for a in e.args:
+            yield from _subexprs(a)
+    elif isinstance(e, BinOp):
+        yield from _subexprs(e.a)
+        yield from _subexprs(e.b)
+    elif isinstance(e, Neg):
+        yield from _subexprs(e.a)
+
+
 def _subst(e, sub):
     if isinstance(e, Var):
         return sub.get(e.name, e)
@@ -1582,6 +1727,6 @@ def _show(e) -> str:
     return repr(e)
 
 
-def lower(model_text, data, transformed=True, theta_order=None) -> Tuple[P.Plan, Lowering]:
-    lw = Lowering(model_text, data, transformed=transformed, theta_order=theta_order)
+def lower(model_text, data, transformed=True, theta_order=None, marginalize=False) -> Tuple[P.Plan, Lowering]:
+    lw = Lowering(model_text, data, transformed=transformed, theta_order=theta_order, marginalize=marginalize)
     return lw.plan, lw

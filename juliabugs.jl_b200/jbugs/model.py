@@ -9,7 +9,8 @@ Same names and argument meaning as the reference (paths relative to /root/refere
     set_evaluation_mode(model, mode)         src/model/bugsmodel.jl:736-801
     condition / decondition                  src/model/abstractppl.jl:700-799 (new plan, as the reference drops its
                                              generated function); set_observed_values = data re-upload (:872-888)
-    UseGraph / UseGeneratedLogDensityFunction / UseCUDABatch   (bugsmodel.jl:248-252 + the new mode)
+    UseGraph / UseGeneratedLogDensityFunction / UseAutoMarginalization / UseCUDABatch
+                                             (bugsmodel.jl:248-252 + the new mode)
     LogDensityProblems.logdensity / logdensity_and_gradient / dimension / capabilities
                                              src/model/logdensityproblems.jl:19-55,168-174,219-232
 
@@ -53,6 +54,14 @@ class UseCUDABatch(EvaluationMode):
     specialize: bool = False
 
 
+@dataclass
+class UseAutoMarginalization(UseCUDABatch):
+    """`UseAutoMarginalization()` (bugsmodel.jl:803-876, evaluation.jl:739-961) on the CUDA path: unobserved finite
+    discrete nodes (`z[i] ~ dcat(w[1:K])` selecting the parameters of `y[i]`) are summed out inside the plate kernel,
+    theta holds the continuous parameters only.  The plate class covers one latent per observation cell (mixtures);
+    chained latents (HMMs) raise `LoweringError`."""
+
+
 class LogDensityOrder:
     def __init__(self, k):
         self.k = k
@@ -65,18 +74,20 @@ class LogDensityOrder:
 
 
 class BUGSModel:
-    def __init__(self, model_def, data, inits=None, transformed=True, theta_order=None):
+    def __init__(self, model_def, data, inits=None, transformed=True, theta_order=None, evaluation_mode=None):
         self.model_def = model_def
         self.data = dict(data)
         self.inits = dict(inits or {})
         self.transformed = transformed
         self.theta_order = theta_order
-        self.evaluation_mode: EvaluationMode = UseCUDABatch()
+        self.evaluation_mode: EvaluationMode = evaluation_mode or UseCUDABatch()
+        self.marginalize = isinstance(self.evaluation_mode, UseAutoMarginalization)
         self._lower()
         self._cuda: Optional[CudaPlan] = None
 
     def _lower(self):
-        self.lowering = Lowering(self.model_def, self.data, transformed=self.transformed, theta_order=self.theta_order)
+        self.lowering = Lowering(self.model_def, self.data, transformed=self.transformed, theta_order=self.theta_order,
+                                 marginalize=self.marginalize)
         self.plan: P.Plan = self.lowering.plan
 
     # -- device state ---------------------------------------------------------------------------
@@ -112,8 +123,11 @@ class BUGSModel:
         return self
 
 
-def compile(model_def, data, inits=None, theta_order=None) -> BUGSModel:  # noqa: A001 - reference name
-    return BUGSModel(model_def, data, inits, transformed=True, theta_order=theta_order)
+def compile(model_def, data, inits=None, theta_order=None, evaluation_mode=None) -> BUGSModel:  # noqa: A001 - reference name
+    """`evaluation_mode`: the reference compiles first and switches modes afterwards (`set_evaluation_mode`); a model
+    whose discrete latents select parameters (`mu[z[i]]`) has no plan outside `UseAutoMarginalization()` -- a discrete
+    theta entry cannot steer a gather on the device -- so that mode can be named at compile time."""
+    return BUGSModel(model_def, data, inits, transformed=True, theta_order=theta_order, evaluation_mode=evaluation_mode)
 
 
 def condition(model: BUGSModel, values=None, **kw) -> BUGSModel:
@@ -129,6 +143,9 @@ def condition(model: BUGSModel, values=None, **kw) -> BUGSModel:
     m = BUGSModel(model.model_def, data, {k: v for k, v in model.inits.items() if k not in vals},
                   transformed=model.transformed, theta_order=None)
     m.evaluation_mode = model.evaluation_mode
+    if model.marginalize:
+        m.marginalize = True
+        m._lower()
     m._conditioned = dict(getattr(model, "_conditioned", {}), **{k: model.data.get(k) for k in vals})
     return m
 
@@ -148,6 +165,9 @@ def decondition(model: BUGSModel, *names) -> BUGSModel:
             data[k] = prev
     m = BUGSModel(model.model_def, data, model.inits, transformed=model.transformed, theta_order=None)
     m.evaluation_mode = model.evaluation_mode
+    if model.marginalize:
+        m.marginalize = True
+        m._lower()
     m._conditioned = was
     return m
 
@@ -169,6 +189,9 @@ def set_evaluation_mode(model: BUGSModel, mode: EvaluationMode) -> BUGSModel:
     m = copy.copy(model)
     m.evaluation_mode = mode
     m._cuda = None
+    if isinstance(mode, UseAutoMarginalization) != model.marginalize:
+        m.marginalize = isinstance(mode, UseAutoMarginalization)
+        m._lower()
     return m
 
 

@@ -38,7 +38,7 @@ TR_IDENTITY, TR_LOG, TR_LOGIT, TR_UPPER = range(4)
 # enum jbugs_op
 OP_IDENTITY, OP_EXP, OP_LOGISTIC, OP_CEXPEXP, OP_PHI, OP_LOG, OP_SQRT, OP_NEG = range(8)
 OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW = 16, 17, 18, 19, 20
-OP_LEAF, OP_SELECT = 32, 33   # expression tapes only
+OP_LEAF, OP_SELECT, OP_PICK_K = 32, 33, 34   # expression tapes only
 MAX_XOPS = 64
 LINK_OF = {"exp": OP_EXP, "logistic": OP_LOGISTIC, "ilogit": OP_LOGISTIC, "cexpexp": OP_CEXPEXP,
            "icloglog": OP_CEXPEXP, "phi": OP_PHI}
@@ -184,6 +184,9 @@ class Plate:
     n_real: int = -1               # observed cells when the plate is padded (weight given), else N * T
     weight: Optional[Arg] = None   # 0/1 per cell (DATA_I | DATA_IJ): padded cells of a plate gathered by a data index
     xops: List[XOp] = field(default_factory=list)   # expression plate (has_obs == 2 in the record): replaces terms/link
+    n_states: int = 0              # > 0: one finite discrete latent per observation is summed out (has_obs == 3)
+    logprior_slot: int = -1        # tape slot of log p(z = k)
+    zobs_slot: int = -1            # tape slot of a data leaf holding the latent's observed state per cell (0 = missing)
 
 
 @dataclass
@@ -250,9 +253,13 @@ class Plan:
                 raise ValueError("expression tape longer than JBUGS_MAX_XOPS")
             link = list(p.link) + [OP_IDENTITY] * (MAX_LINK - len(p.link))
             is_x = bool(p.xops)
+            if p.n_states > 0:
+                link[0] = p.logprior_slot
+                link[1] = p.zobs_slot + 1
             pl[k] = (p.N, p.T, il, len(p.locals), ix if is_x else it, len(p.xops) if is_x else len(p.terms),
                      len(p.link), link, p.family,
-                     p.eta_arg, (2 if is_x else 1) if p.has_obs else 0, p.y.rec(),
+                     p.n_states if p.n_states > 0 else p.eta_arg,
+                     ((3 if p.n_states > 0 else 2) if is_x else 1) if p.has_obs else 0, p.y.rec(),
                      args3(p.aux if p.weight is None else (list(p.aux) + [ZERO_ARG, ZERO_ARG])[:2] + [p.weight]))
             for x in p.xops:
                 xop[ix] = (x.op, x.a, x.b, x.c, 0, 0, x.leaf.rec())

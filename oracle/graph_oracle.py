@@ -710,6 +710,82 @@ class GraphModel:
         return env, {"logprior": logprior, "loglikelihood": loglik,
                      "tempered_logjoint": logprior + temperature * loglik}
 
+    # ---- UseAutoMarginalization (evaluation.jl:739-961) ------------------------------------------------------
+    def _is_latent(self, nd):
+        return (nd.is_stochastic and not nd.is_observed and self.var_type[nd.vid] != "GeneratedQuantity"
+                and nd.stmt.dist.fn == "dcat")
+
+    def marginal_param_names(self):
+        """the continuous parameters, in `sorted_nodes` order: theta of the marginalised model"""
+        return [nd.label for nd in self.parameters if not self._is_latent(nd)]
+
+    def evaluate_with_marginalization_values(self, theta, temperature=1.0, M=None):
+        """`evaluate_with_marginalization_values!!` / `_marginalize_recursive` (evaluation.jl:739-961) without the
+        memo table: the node loop, with every unobserved finite discrete node summed over its support --
+        log_prior_marg = logsumexp_z(log p(z) + rest_prior), log_joint_marg = logsumexp_z(that + rest_lik),
+        log_lik = log_joint_marg - log_prior_marg.  Exponential in the number of latents: small test cases only."""
+        ev = self.ev if M is None else Evaluator(M)
+        M = ev.M
+        nodes = [nd for nd in self.sorted_nodes if self.var_type[nd.vid] != "GeneratedQuantity"]
+        slot, cur = {}, 0
+        for nd in nodes:
+            if nd.is_stochastic and not nd.is_observed and not self._is_latent(nd):
+                slot[nd.vid] = cur
+                cur += 1
+        assert cur == len(theta), "theta holds the continuous parameters only"
+
+        def lse(xs):
+            m = max(float(_val(x)) for x in xs)
+            if m == -math.inf:
+                return -math.inf
+            acc = 0.0
+            for x in xs:
+                acc = acc + M.exp(x - m)
+            return m + M.log(acc)
+
+        def rec(k, env):
+            if k == len(nodes):
+                return 0.0, 0.0
+            nd = nodes[k]
+            if not nd.is_stochastic:
+                env = dict(env)
+                env[nd.name] = env[nd.name].copy() if isinstance(env[nd.name], np.ndarray) else env[nd.name]
+                self._set(env, nd.name, nd.idx, ev.ev(nd.stmt.rhs, env, nd.lv))
+                return rec(k + 1, env)
+            d = self._dist_of(nd, env, ev)
+            if nd.is_observed:
+                pr, lk = rec(k + 1, env)
+                return pr, lk + d.logpdf(M, self._get_env(env, nd))
+            if self._is_latent(nd):
+                priors, joints = [], []
+                for val in range(1, len(d.p) + 1):
+                    env2 = dict(env)
+                    env2[nd.name] = env2[nd.name].copy() if isinstance(env2[nd.name], np.ndarray) else env2[nd.name]
+                    self._set(env2, nd.name, nd.idx, float(val))
+                    pr, lk = rec(k + 1, env2)
+                    tot = d.logpdf(M, val) + pr
+                    priors.append(tot)
+                    joints.append(tot + lk)
+                lp, lj = lse(priors), lse(joints)
+                return lp, (lj - lp if math.isfinite(float(_val(lp))) else lj)
+            y = theta[slot[nd.vid]]
+            x, logjac = dists.invlink_with_logjac(M, d, y) if self.transformed else (y, 0.0)
+            env = dict(env)
+            env[nd.name] = env[nd.name].copy() if isinstance(env[nd.name], np.ndarray) else env[nd.name]
+            self._set(env, nd.name, nd.idx, x)
+            pr, lk = rec(k + 1, env)
+            return d.logpdf(M, x) + logjac + pr, lk
+
+        env0 = {k: (v.astype(object) if isinstance(v, np.ndarray) else v) for k, v in self.env.items()}
+        pr, lk = rec(0, env0)
+        return {"logprior": pr, "loglikelihood": lk, "tempered_logjoint": pr + temperature * lk}
+
+    def marginal_logdensity_and_gradient(self, theta):
+        n = len(theta)
+        duals = [Dual.seed(float(theta[i]), i, n) for i in range(n)]
+        lj = self.evaluate_with_marginalization_values(duals)["tempered_logjoint"]
+        return lj.v, np.array(lj.d, dtype=float)
+
     @staticmethod
     def _get_env(env, nd):
         if nd.idx == ():

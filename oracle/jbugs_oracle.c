@@ -490,55 +490,97 @@ static int eval_chain(const jbo_plan* p, chain_io io, int want_grad, double* log
                     for (int q = 0; q < 3; ++q) argadj(&L[l].args[q], da[q], gadj, ladj);
                 }
                 const int has_w = pl->aux[2].kind == JBUGS_ARG_DATA_I || pl->aux[2].kind == JBUGS_ARG_DATA_IJ;
-                if (pl->has_obs == 2 && !(has_w && argval(p, &pl->aux[2], gval, lx, i, j, N) == 0.0)) {
+                if (pl->has_obs >= 2 && !(has_w && argval(p, &pl->aux[2], gval, lx, i, j, N) == 0.0)) {
                     /* expression plate: forward sweep over the tape (the composed node functions of the observation's
-                       logical parents), observation, reverse sweep back to the leaves */
+                       logical parents), observation, reverse sweep back to the leaves.  has_obs == 3: a finite discrete
+                       latent per observation is summed out (evaluation.jl:739-961 restricted to one latent per plate
+                       cell): the cell contributes logsumexp_k [log p(z = k) + log p(y | z = k)], its gradient is the
+                       posterior-weighted sum of the branch gradients */
                     const jbugs_xop* X = p->xops + pl->first_term;
                     const int nx = (int)pl->n_terms;
+                    const int K = pl->has_obs == 3 ? (int)pl->eta_arg : 1;
+                    const int lps = pl->has_obs == 3 ? (int)pl->link[0] : -1;
                     double v[JBUGS_MAX_XOPS], w[JBUGS_MAX_XOPS], d1[JBUGS_MAX_XOPS], d2[JBUGS_MAX_XOPS];
-                    for (int k = 0; k < nx; ++k) {
-                        const jbugs_xop* o = &X[k];
-                        w[k] = 0.0; d1[k] = 0.0; d2[k] = 0.0;
-                        if (o->op == JBUGS_OP_LEAF) { v[k] = argval(p, &o->leaf, gval, lx, i, j, N); continue; }
-                        if (o->op == JBUGS_OP_SELECT) { v[k] = v[o->a] != 0.0 ? v[o->b] : v[o->c]; continue; }
-                        const double a = v[o->a];
-                        if (o->op < 16) {
-                            if (unary(o->op, a, &v[k], &d1[k])) return 1;
-                            continue;
-                        }
-                        const double b = v[o->b];
-                        switch (o->op) {
-                        case JBUGS_OP_ADD: v[k] = a + b; d1[k] = 1; d2[k] = 1; break;
-                        case JBUGS_OP_SUB: v[k] = a - b; d1[k] = 1; d2[k] = -1; break;
-                        case JBUGS_OP_MUL: v[k] = a * b; d1[k] = b; d2[k] = a; break;
-                        case JBUGS_OP_DIV: v[k] = a / b; d1[k] = 1.0 / b; d2[k] = -a / (b * b); break;
-                        case JBUGS_OP_POW:
-                            if (a < 0 && b != floor(b)) return 1;
-                            v[k] = pow(a, b); d1[k] = b * pow(a, b - 1.0); d2[k] = (a > 0) ? v[k] * log(a) : 0.0; break;
-                        default: return 1;
-                        }
-                    }
-                    double a[3], da[3], lp, dx;
-                    for (int q = 0; q < 3; ++q)
-                        a[q] = pl->aux[q].kind == JBUGS_ARG_XVAL ? v[pl->aux[q].id] : argval(p, &pl->aux[q], gval, lx, i, j, N);
+                    double branch[JBUGS_MAX_STATES];
+                    if (K < 1 || K > JBUGS_MAX_STATES) return 1;
                     double y = argval(p, &pl->y, gval, lx, i, j, N);
-                    if (fam_logpdf(pl->family, y, a, &lp, &dx, da)) return 1;
-                    logp += lp;
-                    for (int q = 0; q < 3; ++q) {
-                        if (pl->aux[q].kind == JBUGS_ARG_XVAL) w[pl->aux[q].id] += da[q];
-                        else if (q < 2) argadj(&pl->aux[q], da[q], gadj, ladj);
-                    }
-                    for (int k = nx - 1; k >= 0; --k) {
-                        const jbugs_xop* o = &X[k];
-                        if (w[k] == 0.0) continue;
-                        if (o->op == JBUGS_OP_LEAF) {
-                            if (o->leaf.kind == JBUGS_ARG_GVEC_J) gadj[o->leaf.id + j] += w[k];
-                            else argadj(&o->leaf, w[k], gadj, ladj);
-                        } else if (o->op == JBUGS_OP_SELECT) {
-                            w[v[o->a] != 0.0 ? o->b : o->c] += w[k];
-                        } else {
-                            w[o->a] += w[k] * d1[k];
-                            if (o->op >= 16) w[o->b] += w[k] * d2[k];
+                    double lse = 0.0;
+                    /* a partially observed latent: link[1] - 1 is the tape slot of a data leaf with the observed state
+                       of the cell (0 = missing); an observed cell takes the branch of its value only */
+                    const int zs = pl->has_obs == 3 ? (int)pl->link[1] - 1 : -1;
+                    const int zo = zs >= 0 ? (int)argval(p, &X[zs].leaf, gval, lx, i, j, N) : 0;
+                    for (int pass = 0; pass < 2; ++pass) {
+                        for (int k = 0; k < K; ++k) {
+                            if (zo > 0 && k != zo - 1) {
+                                if (pass == 0) branch[k] = -INFINITY;
+                                continue;
+                            }
+                            for (int q = 0; q < nx; ++q) {
+                                const jbugs_xop* o = &X[q];
+                                w[q] = 0.0; d1[q] = 0.0; d2[q] = 0.0;
+                                if (o->op == JBUGS_OP_LEAF) { v[q] = argval(p, &o->leaf, gval, lx, i, j, N); continue; }
+                                if (o->op == JBUGS_OP_SELECT) { v[q] = v[o->a] != 0.0 ? v[o->b] : v[o->c]; continue; }
+                                if (o->op == JBUGS_OP_PICK_K) { v[q] = v[o->a + k]; continue; }
+                                const double a = v[o->a];
+                                if (o->op < 16) {
+                                    if (unary(o->op, a, &v[q], &d1[q])) return 1;
+                                    continue;
+                                }
+                                const double b = v[o->b];
+                                switch (o->op) {
+                                case JBUGS_OP_ADD: v[q] = a + b; d1[q] = 1; d2[q] = 1; break;
+                                case JBUGS_OP_SUB: v[q] = a - b; d1[q] = 1; d2[q] = -1; break;
+                                case JBUGS_OP_MUL: v[q] = a * b; d1[q] = b; d2[q] = a; break;
+                                case JBUGS_OP_DIV: v[q] = a / b; d1[q] = 1.0 / b; d2[q] = -a / (b * b); break;
+                                case JBUGS_OP_POW:
+                                    if (a < 0 && b != floor(b)) return 1;
+                                    v[q] = pow(a, b); d1[q] = b * pow(a, b - 1.0); d2[q] = (a > 0) ? v[q] * log(a) : 0.0; break;
+                                default: return 1;
+                                }
+                            }
+                            double a[3], da[3], lp, dx;
+                            for (int q = 0; q < 3; ++q)
+                                a[q] = pl->aux[q].kind == JBUGS_ARG_XVAL ? v[pl->aux[q].id] : argval(p, &pl->aux[q], gval, lx, i, j, N);
+                            if (fam_logpdf(pl->family, y, a, &lp, &dx, da)) return 1;
+                            if (pass == 0) {
+                                branch[k] = lp + (lps >= 0 ? v[lps] : 0.0);
+                                continue;
+                            }
+                            /* pass 1: reverse sweep of branch k, scaled by its posterior weight */
+                            const double r = K == 1 ? 1.0 : exp(branch[k] - lse);
+                            if (r == 0.0) continue;
+                            if (lps >= 0) w[lps] += r;
+                            for (int q = 0; q < 3; ++q) {
+                                if (pl->aux[q].kind == JBUGS_ARG_XVAL) w[pl->aux[q].id] += r * da[q];
+                                else if (q < 2) argadj(&pl->aux[q], r * da[q], gadj, ladj);
+                            }
+                            for (int q = nx - 1; q >= 0; --q) {
+                                const jbugs_xop* o = &X[q];
+                                if (w[q] == 0.0) continue;
+                                if (o->op == JBUGS_OP_LEAF) {
+                                    if (o->leaf.kind == JBUGS_ARG_GVEC_J) gadj[o->leaf.id + j] += w[q];
+                                    else argadj(&o->leaf, w[q], gadj, ladj);
+                                } else if (o->op == JBUGS_OP_SELECT) {
+                                    w[v[o->a] != 0.0 ? o->b : o->c] += w[q];
+                                } else if (o->op == JBUGS_OP_PICK_K) {
+                                    w[o->a + k] += w[q];
+                                } else {
+                                    w[o->a] += w[q] * d1[q];
+                                    if (o->op >= 16) w[o->b] += w[q] * d2[q];
+                                }
+                            }
+                        }
+                        if (pass == 0) {
+                            double mx = branch[0];
+                            for (int k = 1; k < K; ++k) mx = branch[k] > mx ? branch[k] : mx;
+                            if (K == 1 || !(mx > -INFINITY)) lse = mx;
+                            else {
+                                double sum = 0.0;
+                                for (int k = 0; k < K; ++k) sum += exp(branch[k] - mx);
+                                lse = mx + log(sum);
+                            }
+                            logp += lse;
+                            if (!(lse > -INFINITY)) break; /* no branch has support: nothing to differentiate */
                         }
                     }
                 } else if (pl->has_obs && !(has_w && argval(p, &pl->aux[2], gval, lx, i, j, N) == 0.0)) {

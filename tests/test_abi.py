@@ -94,7 +94,7 @@ def test_host_api_mirrors_reference(fixtures):
     assert isinstance(jbugs.set_evaluation_mode(m, jbugs.UseCUDABatch(device=0)).evaluation_mode, jbugs.UseCUDABatch)
 
 
-@pytest.mark.parametrize("spec,max_regs", [("spec_rats_t5_128", 80), ("spec_seeds_128", 128), ("spec_surgical_128", 64),
+@pytest.mark.parametrize("spec,max_regs", [("spec_rats_t5_128", 80), ("spec_seeds_128", 128), ("spec_surgical_128", 128),
                                            ("spec_rats_t5_128ng", 80)])
 def test_static_kernels_keep_their_register_budget(spec, max_regs):
     """DESIGN section 9 (round 1): one more case in the shared `fam_eval` switch once pushed the static Rats kernel to a

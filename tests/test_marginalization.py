@@ -1,0 +1,332 @@
+"""UseAutoMarginalization (J/src/model/evaluation.jl:739-961, J/src/model/bugsmodel.jl:803-876):
+finite discrete latents summed out.  The models and the closed-form expectations are the ones of the reference's own
+test file (J/test/model/auto_marginalization.jl:216-461,654-745), written in BUGS vocabulary (dnorm takes a precision,
+so `Normal(mu, sigma)` becomes `dnorm(mu, tau)` with `tau <- 1 / sigma^2`).
+
+Three implementations must agree: the per-node oracle's recursion over the latents' supports (exponential, the
+reference's algorithm without the memo table), the lowered plate plan evaluated by the C restatement, and the CUDA
+tape kernel; all of them against the closed form (log-sum-exp over components per observation) from scipy."""
+import numpy as np
+import pytest
+from scipy import stats as S
+from scipy.special import logsumexp
+
+import graph_oracle as go
+import jbugs
+from c_oracle import COracle
+from conftest import grad_err
+
+GMM2 = """model {
+  w[1] <- %s
+  w[2] <- %s
+  mu[1] ~ dnorm(-2, 0.04)
+  mu[2] ~ dnorm(2, 0.04)
+  sigma[1] ~ dexp(1)
+  sigma[2] ~ dexp(1)
+  for (k in 1:2) { tau[k] <- 1 / (sigma[k] * sigma[k]) }
+  for (i in 1:N) {
+    z[i] ~ dcat(w[1:2])
+    y[i] ~ dnorm(mu[z[i]], tau[z[i]])
+  }
+}"""
+
+GMM3 = """model {
+  w[1] <- 0.2
+  w[2] <- 0.5
+  w[3] <- 0.3
+  mu[1] ~ dnorm(-3, 0.04)
+  mu[2] ~ dnorm(0, 0.04)
+  mu[3] ~ dnorm(3, 0.04)
+  for (k in 1:3) {
+    sigma[k] ~ dexp(1)
+    tau[k] <- 1 / (sigma[k] * sigma[k])
+  }
+  for (i in 1:N) {
+    z[i] ~ dcat(w[1:3])
+    y[i] ~ dnorm(mu[z[i]], tau[z[i]])
+  }
+}"""
+
+GMM_SHARED = """model {
+  w[1] <- 0.3
+  w[2] <- 0.7
+  mu[1] ~ dnorm(-2, 0.04)
+  mu[2] ~ dnorm(2, 0.04)
+  sigma ~ dexp(1)
+  tau <- 1 / (sigma * sigma)
+  for (i in 1:N) {
+    z[i] ~ dcat(w[1:2])
+    y[i] ~ dnorm(mu[z[i]], tau)
+  }
+}"""
+
+SCALAR = """model {
+  mu ~ dnorm(0, 1)
+  z ~ dcat(w[1:K])
+  y ~ dnorm(mu + delta[z], tau)
+}"""
+
+# weights that are themselves a function of a parameter (not in the reference's file: the Dirichlet prior it uses
+# there is multivariate and outside the plate class)
+GMM_W = """model {
+  p ~ dbeta(2, 3)
+  w[1] <- p
+  w[2] <- 1 - p
+  mu[1] ~ dnorm(-2, 0.04)
+  mu[2] ~ dnorm(2, 0.04)
+  for (i in 1:N) {
+    z[i] ~ dcat(w[1:2])
+    y[i] ~ dnorm(mu[z[i]], 1.5)
+  }
+}"""
+
+# a Poisson mixture with a covariate: the latent selects the intercept of a log-linear predictor
+POISMIX = """model {
+  w[1] <- 0.6
+  w[2] <- 0.4
+  a[1] ~ dnorm(0, 1)
+  a[2] ~ dnorm(1, 1)
+  b ~ dnorm(0, 4)
+  for (i in 1:N) {
+    z[i] ~ dcat(w[1:2])
+    log(lam[i]) <- a[z[i]] + b * x[i]
+    y[i] ~ dpois(lam[i])
+  }
+}"""
+
+
+def mixture_loglik(y, w, mus, sigmas):
+    """`mixture_loglikelihood` of the reference's test (auto_marginalization.jl:218-233)"""
+    return float(sum(logsumexp([np.log(w[j]) + S.norm(mus[j], sigmas[j]).logpdf(yi) for j in range(len(w))]) for yi in y))
+
+
+def theta_by_name(names, values):
+    return np.array([values[n] for n in names], dtype=float)
+
+
+def lowered(text, data):
+    plan, lw = jbugs.lower(text, data, marginalize=True)
+    gm = go.compile(text, data, {}).use_generated_order()
+    assert lw.param_names() == gm.marginal_param_names()
+    return plan, gm
+
+
+def check_c_port(plan, gm, theta, tol=1e-12):
+    lp, g, st = COracle(plan).eval_batch(theta)
+    for c in range(theta.shape[1]):
+        lp_g, g_g = gm.marginal_logdensity_and_gradient(theta[:, c])
+        assert st[c] == 0
+        assert abs(lp[c] - lp_g) <= tol * max(1.0, abs(lp_g))
+        assert grad_err(g[:, c], g_g) < 1e-10
+    return lp, g
+
+
+def test_two_component_mixture_fixed_weights():
+    """auto_marginalization.jl:235-288"""
+    y = np.array([-1.5, 2.3, -2.1, 1.8])
+    data = {"N": 4, "y": y}
+    plan, gm = lowered(GMM2 % (0.3, 0.7), data)
+    assert plan.D == 4  # dimension(model) == 4: the latents are not parameters
+    th = theta_by_name(gm.marginal_param_names(), {"sigma[1]": 0.0, "sigma[2]": 0.0, "mu[2]": 2.0, "mu[1]": -2.0})
+    expected = (mixture_loglik(y, [0.3, 0.7], [-2.0, 2.0], [1.0, 1.0]) + S.norm(-2, 5).logpdf(-2.0) + S.norm(2, 5).logpdf(2.0)
+                + 2 * S.expon().logpdf(1.0))
+    assert gm.evaluate_with_marginalization_values(list(th))["tempered_logjoint"] == pytest.approx(expected, abs=1e-10)
+    lp, _ = check_c_port(plan, gm, th.reshape(-1, 1))
+    assert lp[0] == pytest.approx(expected, abs=1e-10)
+
+
+def test_three_component_mixture():
+    """auto_marginalization.jl:290-349"""
+    y = np.array([-2.5, 0.5, 3.2])
+    data = {"N": 3, "y": y}
+    plan, gm = lowered(GMM3, data)
+    assert plan.D == 6
+    vals = {"sigma[1]": 0.0, "sigma[2]": 0.0, "sigma[3]": 0.0, "mu[1]": -3.0, "mu[2]": 0.0, "mu[3]": 3.0}
+    th = theta_by_name(gm.marginal_param_names(), vals)
+    expected = (mixture_loglik(y, [0.2, 0.5, 0.3], [-3.0, 0.0, 3.0], [1.0] * 3)
+                + S.norm(-3, 5).logpdf(-3.0) + S.norm(0, 5).logpdf(0.0) + S.norm(3, 5).logpdf(3.0) + 3 * S.expon().logpdf(1.0))
+    lp, _ = check_c_port(plan, gm, th.reshape(-1, 1))
+    assert lp[0] == pytest.approx(expected, abs=1e-10)
+
+
+def test_label_invariance():
+    """auto_marginalization.jl:351-389: equal weights, swapping the components' parameters leaves logp unchanged"""
+    data = {"N": 4, "y": np.array([1.0, 2.0, -1.0, 3.0])}
+    text = GMM2.replace("dnorm(-2, 0.04)", "dnorm(0, 0.01)").replace("dnorm(2, 0.04)", "dnorm(0, 0.01)") % (0.5, 0.5)
+    plan, gm = lowered(text, data)
+    names = gm.marginal_param_names()
+    a = theta_by_name(names, {"sigma[1]": -0.5, "sigma[2]": 0.0, "mu[2]": 3.0, "mu[1]": 1.0})
+    b = theta_by_name(names, {"sigma[1]": 0.0, "sigma[2]": -0.5, "mu[2]": 1.0, "mu[1]": 3.0})
+    lp, _ = check_c_port(plan, gm, np.stack([a, b], axis=1))
+    assert lp[0] == pytest.approx(lp[1], abs=1e-10)
+
+
+def test_partially_observed_latent():
+    """auto_marginalization.jl:391-462: z = [2, missing, 1, missing]; the observed cells take their own branch"""
+    y = np.array([1.0, 2.0, -1.0, 3.0])
+    data = {"N": 4, "y": y, "z": np.array([2.0, np.nan, 1.0, np.nan])}
+    plan, gm = lowered(GMM_SHARED, data)
+    assert plan.D == 3
+    th = theta_by_name(gm.marginal_param_names(), {"sigma": 0.0, "mu[2]": 2.0, "mu[1]": -2.0})
+    w, mu = [0.3, 0.7], [-2.0, 2.0]
+    obs = np.log(w[1]) + S.norm(mu[1], 1).logpdf(1.0) + np.log(w[0]) + S.norm(mu[0], 1).logpdf(-1.0)
+    marg = sum(logsumexp([np.log(w[k]) + S.norm(mu[k], 1).logpdf(v) for k in range(2)]) for v in (2.0, 3.0))
+    expected = obs + marg + S.norm(-2, 5).logpdf(-2.0) + S.norm(2, 5).logpdf(2.0) + S.expon().logpdf(1.0)
+    lp, _ = check_c_port(plan, gm, th.reshape(-1, 1))
+    assert lp[0] == pytest.approx(expected, abs=1e-10)
+
+
+def test_gradient_gmm():
+    """auto_marginalization.jl:654-703: gradient at the initialised point (dual numbers through the recursion ==
+    analytic posterior-weighted reverse sweep of the plan), and central differences as the reference does"""
+    y = np.array([-1.8, -2.2, 1.9, 2.1, -1.5, 2.4])
+    data = {"N": 6, "y": y}
+    plan, gm = lowered(GMM2 % (0.3, 0.7), data)
+    th = theta_by_name(gm.marginal_param_names(), {"mu[1]": -2.0, "mu[2]": 2.0, "sigma[1]": np.log(1.1), "sigma[2]": np.log(0.9)})
+    lp, g = check_c_port(plan, gm, th.reshape(-1, 1))
+    co = COracle(plan)
+    eps = 1e-6
+    fd = np.zeros_like(th)
+    for i in range(th.size):
+        e = np.zeros_like(th)
+        e[i] = eps
+        fd[i] = (co.eval_batch((th + e).reshape(-1, 1))[0][0] - co.eval_batch((th - e).reshape(-1, 1))[0][0]) / (2 * eps)
+    assert np.max(np.abs(g[:, 0] - fd) / (np.abs(fd) + 1e-8)) < 5e-5
+
+
+def test_prior_likelihood_split_and_tempering():
+    """auto_marginalization.jl:705-745: a scalar latent picking a data offset; logprior / loglikelihood / temperature"""
+    data = {"K": 2, "w": np.array([0.3, 0.7]), "delta": np.array([0.0, 2.0]), "tau": 1.0, "y": 1.5}
+    plan, gm = lowered(SCALAR, data)
+    assert plan.D == 1
+    r = gm.evaluate_with_marginalization_values([0.0], temperature=0.4)
+    e_prior = S.norm(0, 1).logpdf(0.0)
+    e_lik = logsumexp([np.log(data["w"][i]) + S.norm(data["delta"][i], 1.0).logpdf(1.5) for i in range(2)])
+    assert r["logprior"] == pytest.approx(e_prior, abs=1e-10)
+    assert r["loglikelihood"] == pytest.approx(e_lik, abs=1e-10)
+    assert r["tempered_logjoint"] == pytest.approx(e_prior + 0.4 * e_lik, abs=1e-10)
+    co = COracle(plan)
+    lp, _, _ = co.eval_batch(np.zeros((1, 1)))
+    assert lp[0] == pytest.approx(e_prior + e_lik, abs=1e-10)
+
+
+def _random_cases():
+    rng = np.random.default_rng(11)
+    N = 37
+    z = rng.integers(0, 2, N)
+    y = np.where(z == 0, rng.normal(-2, 1.0, N), rng.normal(2, 0.7, N))
+    x = rng.standard_normal(N)
+    yp = rng.poisson(np.exp(np.where(z == 0, 0.2, 1.3) + 0.3 * x)).astype(float)
+    return {
+        "gmm2": (GMM2 % (0.3, 0.7), {"N": N, "y": y}),
+        "gmm3": (GMM3, {"N": N, "y": y}),
+        "gmm_weights_from_a_parameter": (GMM_W, {"N": N, "y": y}),
+        "poisson_mixture": (POISMIX, {"N": N, "y": yp, "x": x}),
+    }
+
+
+@pytest.mark.parametrize("name", ["gmm2", "gmm3", "gmm_weights_from_a_parameter", "poisson_mixture"])
+def test_random_thetas_node_oracle_vs_plan(name):
+    text, data = _random_cases()[name]
+    data = dict(data)
+    data["N"] = 5   # the recursion over the joint support is exponential in N
+    for k in ("y", "x"):
+        if k in data:
+            data[k] = data[k][:5]
+    plan, gm = lowered(text, data)
+    rng = np.random.default_rng(3)
+    theta = 0.4 * rng.standard_normal((plan.D, 4))
+    check_c_port(plan, gm, theta)
+
+
+def test_unsupported_shapes_raise():
+    hmm = """model {
+      z[1] ~ dcat(p0[1:2])
+      for (t in 2:T) { z[t] ~ dcat(A[z[t-1], 1:2]) }
+      for (t in 1:T) { y[t] ~ dnorm(mu[z[t]], 1) }
+      mu[1] ~ dnorm(0, 1)
+      mu[2] ~ dnorm(3, 1)
+    }"""
+    data = {"T": 3, "y": np.array([0.1, 2.9, 3.2]), "p0": np.array([0.5, 0.5]), "A": np.array([[0.9, 0.1], [0.2, 0.8]])}
+    with pytest.raises(jbugs.LoweringError):
+        jbugs.lower(hmm, data, marginalize=True)
+
+
+def test_mode_object():
+    data = {"N": 4, "y": np.array([-1.5, 2.3, -2.1, 1.8])}
+    with pytest.raises(jbugs.LoweringError):
+        jbugs.compile(GMM2 % (0.3, 0.7), data)  # z[i] as a discrete theta entry steering mu[z[i]]: not on the device
+    mm = jbugs.compile(GMM2 % (0.3, 0.7), data, evaluation_mode=jbugs.UseAutoMarginalization())
+    assert jbugs.LogDensityProblems.dimension(mm) == 4
+    assert isinstance(mm.evaluation_mode, jbugs.UseCUDABatch)  # the marginalising mode is a CUDA batch mode
+
+
+# ---- the CUDA tape kernel ------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["gmm2", "gmm3", "gmm_weights_from_a_parameter", "poisson_mixture"])
+@pytest.mark.parametrize("layout", ["chain_fast", "param_fast"])
+def test_cuda_matches_c_port(name, layout):
+    text, data = _random_cases()[name]
+    m = jbugs.compile(text, data, evaluation_mode=jbugs.UseAutoMarginalization())
+    rng = np.random.default_rng(5)
+    theta = 0.4 * rng.standard_normal((m.plan.D, 70))
+    lp, g, st = m.cuda.eval_host(theta, layout="param_fast")
+    lp0, g0, st0 = COracle(m.plan).eval_batch(theta)
+    assert (st == 0).all() and (st0 == 0).all()
+    assert np.max(np.abs(lp - lp0) / np.maximum(1.0, np.abs(lp0))) < 1e-12
+    scale = np.maximum(np.abs(g0), 1e-4 * np.abs(g0).max(axis=0, keepdims=True))
+    assert np.max(np.abs(g - g0) / scale) < 1e-10
+
+
+@pytest.mark.gpu
+def test_cuda_reference_cases():
+    """the reference's closed-form expectations through the C ABI"""
+    y = np.array([-1.5, 2.3, -2.1, 1.8])
+    m = jbugs.compile(GMM2 % (0.3, 0.7), {"N": 4, "y": y}, evaluation_mode=jbugs.UseAutoMarginalization())
+    assert jbugs.LogDensityProblems.dimension(m) == 4
+    th = theta_by_name(m.lowering.param_names(), {"sigma[1]": 0.0, "sigma[2]": 0.0, "mu[2]": 2.0, "mu[1]": -2.0})
+    expected = (mixture_loglik(y, [0.3, 0.7], [-2.0, 2.0], [1.0, 1.0]) + S.norm(-2, 5).logpdf(-2.0) + S.norm(2, 5).logpdf(2.0)
+                + 2 * S.expon().logpdf(1.0))
+    assert jbugs.LogDensityProblems.logdensity(m, th) == pytest.approx(expected, abs=1e-10)
+    data = {"K": 2, "w": np.array([0.3, 0.7]), "delta": np.array([0.0, 2.0]), "tau": 1.0, "y": 1.5}
+    ms = jbugs.compile(SCALAR, data, evaluation_mode=jbugs.UseAutoMarginalization())
+    r = jbugs.evaluate_with_values(ms, np.zeros(1), temperature=0.4)
+    e_prior = S.norm(0, 1).logpdf(0.0)
+    e_lik = logsumexp([np.log(data["w"][i]) + S.norm(data["delta"][i], 1.0).logpdf(1.5) for i in range(2)])
+    assert r["logprior"] == pytest.approx(e_prior, abs=1e-10)
+    assert r["loglikelihood"] == pytest.approx(e_lik, abs=1e-10)
+    assert r["tempered_logjoint"] == pytest.approx(e_prior + 0.4 * e_lik, abs=1e-10)
+    # partially observed latent
+    yp = np.array([1.0, 2.0, -1.0, 3.0])
+    mp = jbugs.compile(GMM_SHARED, {"N": 4, "y": yp, "z": np.array([2.0, np.nan, 1.0, np.nan])},
+                       evaluation_mode=jbugs.UseAutoMarginalization())
+    th = theta_by_name(mp.lowering.param_names(), {"sigma": 0.0, "mu[2]": 2.0, "mu[1]": -2.0})
+    lp0, g0, _ = COracle(mp.plan).eval_batch(th.reshape(-1, 1))
+    lp, g = jbugs.LogDensityProblems.logdensity_and_gradient(mp, th)
+    assert lp == pytest.approx(lp0[0], rel=1e-12)
+    assert grad_err(g, g0[:, 0]) < 1e-10
+
+
+@pytest.mark.gpu
+def test_cuda_large_mixture_against_closed_form():
+    """10^5 observations x 64 chains: the plate's log-sum-exp against numpy's closed form, gradient by the C port on 4 chains"""
+    rng = np.random.default_rng(2)
+    N = 100_000
+    z = rng.random(N) < 0.3
+    y = np.where(z, rng.normal(-2, 1.0, N), rng.normal(2, 0.7, N))
+    m = jbugs.compile(GMM2 % (0.3, 0.7), {"N": N, "y": y}, evaluation_mode=jbugs.UseAutoMarginalization())
+    names = m.lowering.param_names()
+    base = theta_by_name(names, {"sigma[1]": 0.0, "sigma[2]": np.log(0.7), "mu[2]": 2.0, "mu[1]": -2.0})
+    theta = base[:, None] + 0.02 * rng.standard_normal((4, 64))
+    lp, g, st = m.cuda.eval_host(theta, layout="param_fast")
+    assert (st == 0).all()
+    ix = {n: i for i, n in enumerate(names)}
+    for c in (0, 17, 63):
+        mu = [theta[ix["mu[1]"], c], theta[ix["mu[2]"], c]]
+        sg = [np.exp(theta[ix["sigma[1]"], c]), np.exp(theta[ix["sigma[2]"], c])]
+        ll = logsumexp(np.stack([np.log(w) + S.norm(mu[k], sg[k]).logpdf(y) for k, w in enumerate((0.3, 0.7))]), axis=0).sum()
+        pr = (S.norm(-2, 5).logpdf(mu[0]) + S.norm(2, 5).logpdf(mu[1]) + sum(S.expon().logpdf(s) + np.log(s) for s in sg))
+        assert lp[c] == pytest.approx(ll + pr, rel=1e-11)
+    lp0, g0, _ = COracle(m.plan).eval_batch(theta[:, :4])
+    scale = np.maximum(np.abs(g0), 1e-4 * np.abs(g0).max(axis=0, keepdims=True))
+    assert np.max(np.abs(g[:, :4] - g0) / scale) < 1e-10
