@@ -152,13 +152,22 @@ int jbugs_comm_destroy(jbugs_plan* plan);
 int64_t jbugs_launch_count(const jbugs_plan* plan);
 int jbugs_plan_describe(const jbugs_plan* plan, char* buf, size_t nbuf);
 
-/* Run-time specialisation (optional).  Plates whose shape has no in-tree specialised kernel run the
- * interpreter instantiation; this call writes the constexpr description of each such plate as C++
- * source, compiles the SAME kernel body for it with nvcc (sm_100a) into a small shared object next
- * to `cache_dir` (NULL: $JBUGS_JIT_CACHE or /tmp/jbugs_jit; cached by a hash of the shape) and uses
- * it from then on.  Needs nvcc ($JBUGS_NVCC or /usr/local/cuda/bin/nvcc) and the in-tree kernel
- * headers next to the library; returns JBUGS_ERR_UNSUPPORTED otherwise and nothing changes. */
+/* Run-time specialisation (optional; the analogue of the reference generating and compiling a Julia function
+ * per model, J/src/model/bugsmodel.jl:736-801).  Plates whose shape has no in-tree specialised kernel run the
+ * interpreter instantiations; this call writes the constexpr description of each such plate -- and, for an
+ * expression plate, its tape as straight-line code -- as C++ source and compiles the SAME kernel body for it
+ * in-process with NVRTC (libnvrtc is dlopen'ed: $JBUGS_NVRTC, libnvrtc.so.12, /usr/local/cuda/lib64; the
+ * kernel headers are embedded in this library, so neither nvcc nor a source tree is needed).  Cubins are cached
+ * in `cache_dir` (NULL: $JBUGS_JIT_CACHE, $XDG_CACHE_HOME/jbugs_jit or ~/.cache/jbugs_jit; "none": no cache),
+ * created 0700 and used only if owned by the caller and not writable by others.  Returns JBUGS_ERR_UNSUPPORTED
+ * when libnvrtc cannot be loaded; nothing changes then.  jbugs_jit_last_compile_seconds: time NVRTC took in
+ * the last call (0 when every kernel came from the cache). */
 int jbugs_plan_specialize(jbugs_plan* plan, const char* cache_dir);
+double jbugs_jit_last_compile_seconds(void);
+/* The same without blocking: NVRTC runs on a worker thread, evaluations keep using the interpreter instantiations
+ * and switch to the specialised kernels at the first jbugs_eval_batch after they are ready (the two agree to rounding,
+ * not bit for bit).  Cached kernels are adopted at once; jbugs_plan_specialize() afterwards waits for the worker. */
+int jbugs_plan_specialize_async(jbugs_plan* plan, const char* cache_dir);
 
 /* Tuning knobs (tests force the generic interpreter path with "dynamic=1"). Unknown keys fail. */
 int jbugs_plan_set_option(jbugs_plan* plan, const char* key, int64_t value);

@@ -28,7 +28,9 @@
 #ifndef JBUGS_PLAN_H
 #define JBUGS_PLAN_H
 
+#ifndef JBUGS_PLAN_NO_STDINT /* (set by the NVRTC build of the device headers, which defines the integer types itself) */
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {

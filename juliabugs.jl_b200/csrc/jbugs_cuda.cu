@@ -88,11 +88,17 @@ struct PlateRt {
     bool const_dirty = true;  // obs_const must be recomputed (new data / shard / kernel variant)
     size_t smem_bytes = 0;    // dynamic shared memory of the plate kernel (J region + two stages)
     // run-time specialisation (jbugs_plan_specialize): a kernel compiled for exactly this plate's shape
-    plate_launch_fn jit_launch = nullptr;
+    struct JitKernels* jit = nullptr;  // (jbugs_jit.inc; owned by the plan)
     int jit_fused = FUSED_NONE;
     bool jit_valid = true;    // false: the data are outside the fused formulas' domain -> interpreter
     XOpDev* d_xtape = nullptr;  // expression plates: the resolved tape in device memory
+    std::vector<XOpDev> xtape_host;  // ... and on the host (the source the specialiser writes the tape's code from)
 };
+static cudaError_t jit_launch(JitKernels& jk, JBUGS_LAUNCH_PARAMS);
+static void jit_free(JitKernels* jk);
+struct JitJob;
+static void jit_job_free(JitJob* j);
+static int jit_poll(jbugs_plan* p);
 
 struct jbugs_plan_s {
     int device = 0;
@@ -118,6 +124,7 @@ struct jbugs_plan_s {
     std::vector<void*> d_slots;
     std::vector<char> uploaded;
     std::vector<PlateRt> rt;
+    JitJob* jit_job = nullptr;  // asynchronous run-time specialisation under way (jbugs_jit.inc)
     std::vector<long long> shard_i0, shard_i1;
     std::vector<char> shard_set;  // jbugs_plan_set_shard was called for the plate (else it is replicated on every rank)
     GlobalsParams gp{};
@@ -416,6 +423,7 @@ static int build_xplate(jbugs_plan* p, int k) {
     CU(cudaMalloc(&r.d_xtape, tape.size() * sizeof(XOpDev)));
     CU(cudaMemcpy(r.d_xtape, tape.data(), tape.size() * sizeof(XOpDev), cudaMemcpyHostToDevice));
     V.xtape = r.d_xtape;
+    r.xtape_host = tape;
     return build_locals_and_finish(p, k, gref, sb);
 }
 
@@ -493,7 +501,7 @@ static int refresh_obs_const(jbugs_plan* p, int k, cudaStream_t st) {
     r.obs_const = 0.0;
     r.const_dirty = false;
     p->epoch++;
-    const int fused = (r.variant == 0 && r.jit_launch && !p->force_dynamic) ? r.jit_fused : g_specs[r.variant].fused;
+    const int fused = (r.variant == 0 && r.jit && !p->force_dynamic) ? r.jit_fused : g_specs[r.variant].fused;
     r.jit_valid = true;
     if (fused == FUSED_NONE || fused == FUSED_NORMAL_IDENTITY) return 0;  // the other paths drop a data-only normaliser
     const PlateParams& pp = r.pp;
@@ -705,7 +713,11 @@ extern "C" int jbugs_plan_destroy(jbugs_plan* p) {
     cudaSetDevice(p->device);
     jbugs_comm_destroy(p);
     for (void* d : p->d_slots) cudaFree(d);
-    for (auto& r : p->rt) cudaFree(r.d_xtape);
+    jit_job_free(p->jit_job);  // (waits for the worker thread)
+    for (auto& r : p->rt) {
+        cudaFree(r.d_xtape);
+        jit_free(r.jit);
+    }
     free_workspace(p);
     free_slots(p);
     for (auto& s : p->slot) {
@@ -856,7 +868,8 @@ extern "C" int jbugs_plan_describe(const jbugs_plan* p, char* buf, size_t nbuf) 
     for (size_t k = 0; k < p->rt.size(); ++k) {
         const auto& r = p->rt[k];
         snprintf(line, sizeof line, "plate %zu: N=%lld T=%lld kernel=%s tiles=%lld tile=%lld gref=%d\n", k, r.pp.v.N, r.pp.v.T,
-                 (r.variant == 0 && r.jit_launch && r.jit_valid && !p->force_dynamic) ? "specialised_at_run_time" : spec_name(r.variant),
+                 ((r.variant == 0 || r.variant == g_xspec) && r.jit && r.jit_valid && !p->force_dynamic)
+                     ? (r.variant == 0 ? "specialised_at_run_time" : "expression_tape_specialised_at_run_time") : spec_name(r.variant),
                  r.n_tiles, r.pp.v.tile, r.pp.sh.n_gref);
         s += line;
     }
@@ -1155,7 +1168,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
             pp.v.loc[l].step_i = pp.v.loc[l].si * ld;
             pp.v.loc[l].step_j = pp.v.loc[l].sj * ld;
         }
-        bool jit = r.variant == 0 && r.jit_launch && r.jit_valid && !p->force_dynamic;
+        bool jit = (r.variant == 0 || r.variant == g_xspec) && r.jit && r.jit_valid && !p->force_dynamic;
         int variant = r.variant;
         if (p->parts == 1) {
             // prior part only: the interpreter with the observation switched off (has_obs = 0 is a run-time shape field)
@@ -1165,8 +1178,10 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
             fp.p[k].obs_const = 0.0;
         }
         if (!jit && variant == 0) fp.p[k].obs_const = 0.0;  // the interpreter evaluates the full log-density itself
-        cudaError_t le = (jit ? r.jit_launch : g_specs[variant].launch)(r.n_tiles, r.smem_bytes, st, pp, theta, grad, ld, C, p->d_gvals, ldg,
-                                                   p->d_partial + r.partial_offset * ldg, p->d_flags, want_grad && grad, p->use_pdl);
+        cudaError_t le = jit ? jit_launch(*r.jit, r.n_tiles, r.smem_bytes, st, pp, theta, grad, ld, C, p->d_gvals, ldg,
+                                          p->d_partial + r.partial_offset * ldg, p->d_flags, want_grad && grad, p->use_pdl)
+                             : g_specs[variant].launch(r.n_tiles, r.smem_bytes, st, pp, theta, grad, ld, C, p->d_gvals, ldg,
+                                                       p->d_partial + r.partial_offset * ldg, p->d_flags, want_grad && grad, p->use_pdl);
         if (le != cudaSuccess) return fail(JBUGS_ERR_CUDA, "plate kernel launch failed: %s", cudaGetErrorString(le));
         p->launches++;
         reduce_plates.push_back((int)k);
@@ -1327,6 +1342,7 @@ extern "C" int jbugs_eval_batch(jbugs_plan* p, const double* theta, int64_t ld, 
     if (layout == JBUGS_LAYOUT_CHAIN_FAST ? ld < C : ld < D) return fail(JBUGS_ERR_INVALID, "leading dimension %lld too small", (long long)ld);
     int rc = set_device(p);
     if (rc) return rc;
+    if ((rc = jit_poll(p))) return rc;  // an asynchronous specialisation that has finished takes over from here on
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 0) return JBUGS_OK;
     const bool dev_io = is_device_ptr(theta) && is_device_ptr(logp) && is_device_ptr(grad) && is_device_ptr(status);

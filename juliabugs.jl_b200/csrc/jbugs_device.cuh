@@ -12,11 +12,27 @@
 // plate specs) and falls back to a warp-uniform switch otherwise.
 #pragma once
 
+#ifdef __CUDACC_RTC__
+// run-time specialisation (jbugs_jit.inc) compiles this header with NVRTC: no host headers, the device math and the
+// fixed-width integer types are built in or defined here; the headers come embedded in libjbugs_cuda (flat names)
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+#define JBUGS_PLAN_NO_STDINT 1
+#include "jbugs_plan.h"
+#else
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
 
 #include "../../include/jbugs_plan.h"
+#endif
 
 namespace jbugs {
 
@@ -80,7 +96,7 @@ struct FamOut {
 };
 
 // a2: third argument of the three-argument families (dt's degrees of freedom), a constant: it has no adjoint
-__device__ __forceinline__ bool fam_eval(int fam, double x, double a0, double a1, FamOut& o, double a2 = 0.0) {
+__device__ inline bool fam_eval(int fam, double x, double a0, double a1, FamOut& o, double a2 = 0.0) {
     o.dx = 0.0; o.da0 = 0.0; o.da1 = 0.0; o.lp = 0.0;
     switch (fam) {
     case JBUGS_FAM_NORMAL: {

@@ -135,6 +135,11 @@ struct DynSpec {
     static constexpr bool OBS_LOCALS = true;  // unknown at compile time
     static constexpr bool SOFF = false;       // stream offsets come from the kernel parameters
     static constexpr bool XTAPE = false;      // (XSpec: the instantiation that interprets expression tapes)
+    static constexpr bool XGEN = false;       // (a run-time generated description whose tape is compiled code)
+    // bounds of the unrolled loops over locals / global-coefficient terms (the arrays keep their MAX_* sizes: the kernel
+    // parameter layout is one for all instantiations).  A static spec knows its counts: the front end then emits nl / kg
+    // copies of each loop body instead of MAX_LOC / MAX_GT guarded ones for the optimiser to throw away.
+    static constexpr int NL_MAX = MAX_LOC, KG_MAX = MAX_GT;
     static constexpr int L2PF = 0;            // no L2 prefetch of theta rows
     __device__ __forceinline__ bool prior_fused(int) const { return false; }
     __device__ __forceinline__ bool prior_mu_zero(int) const { return false; }
@@ -179,9 +184,25 @@ enum { FUSED_NONE = 0, FUSED_NORMAL_IDENTITY = 1, FUSED_BINOMIAL_LOGIT = 2, FUSE
        // log-density, the data-only normaliser goes to obs_const exactly as for the logit / log versions
        FUSED_BINOMIAL_LINK = 5, FUSED_BERNOULLI_LINK = 6, FUSED_POISSON_LINK = 7 };
 
+// does the description carry generated code for an expression tape (`XGEN`, `observe_gen`)?  Only run-time generated ones do.
+template <class D, class = void>
+struct desc_xgen { static constexpr bool value = false; };
+template <class D>
+struct desc_xgen<D, decltype((void)D::XGEN)> { static constexpr bool value = D::XGEN; };
+
 // A static spec is a struct with `static constexpr PlateShape SH` ; see specs in jbugs_cuda.cu.
+// the shape of a description as ONE constant object in device memory: every accessor of StaticSpec is a load at a
+// constant address that the optimiser folds (calling the constexpr sh() per access instead made NVVM inline and
+// scalarise a 500-byte struct thousands of times: 47 s of optimiser time for one kernel under NVRTC against 0.1 s in
+// the front end)
+template <class Desc>
+__device__ constexpr PlateShape g_shape_of = Desc::sh();
+
 template <class Desc>
 struct StaticSpec {
+    using D = Desc;
+    static constexpr int NL_MAX = Desc::sh().nl, KG_MAX = Desc::sh().kg;
+    static constexpr bool XGEN = desc_xgen<Desc>::value;
     static constexpr bool STATIC = true;
     static constexpr int FUSED = Desc::FUSED;
     static constexpr int UNROLL = Desc::UNROLL;
@@ -201,33 +222,33 @@ struct StaticSpec {
     static constexpr int L2PF = Desc::L2PF;           // groups ahead whose theta rows are prefetched into L2 (0 = off)
     // a dnorm prior whose arguments do not vary over the plate keeps sufficient statistics
     __device__ __forceinline__ constexpr bool prior_fused(int l) const {
-        return Desc::sh().loc[l].family == JBUGS_FAM_NORMAL &&
-               (Desc::sh().loc[l].args[0].kind == JBUGS_ARG_GVAL || Desc::sh().loc[l].args[0].kind == JBUGS_ARG_CONST) &&
-               (Desc::sh().loc[l].args[1].kind == JBUGS_ARG_GVAL || Desc::sh().loc[l].args[1].kind == JBUGS_ARG_CONST);
+        return g_shape_of<Desc>.loc[l].family == JBUGS_FAM_NORMAL &&
+               (g_shape_of<Desc>.loc[l].args[0].kind == JBUGS_ARG_GVAL || g_shape_of<Desc>.loc[l].args[0].kind == JBUGS_ARG_CONST) &&
+               (g_shape_of<Desc>.loc[l].args[1].kind == JBUGS_ARG_GVAL || g_shape_of<Desc>.loc[l].args[1].kind == JBUGS_ARG_CONST);
     }
     // ... and its mean is the literal 0 (the shape records it: LocalS::mu_zero, set by build_plate from the plan)
-    __device__ __forceinline__ constexpr bool prior_mu_zero(int l) const { return Desc::sh().loc[l].mu_zero != 0; }
+    __device__ __forceinline__ constexpr bool prior_mu_zero(int l) const { return g_shape_of<Desc>.loc[l].mu_zero != 0; }
     __device__ __forceinline__ explicit StaticSpec(const PlateShape&) {}
-    __device__ __forceinline__ constexpr int kg() const { return Desc::sh().kg; }
-    __device__ __forceinline__ constexpr int nl() const { return Desc::sh().nl; }
-    __device__ __forceinline__ constexpr int has_off() const { return Desc::sh().has_off; }
-    __device__ __forceinline__ constexpr int n_gref() const { return Desc::sh().n_gref; }
-    __device__ __forceinline__ constexpr int family() const { return Desc::sh().family; }
-    __device__ __forceinline__ constexpr int eta_arg() const { return Desc::sh().eta_arg; }
-    __device__ __forceinline__ constexpr int has_obs() const { return Desc::sh().has_obs; }
-    __device__ __forceinline__ constexpr int n_link() const { return Desc::sh().n_link; }
-    __device__ __forceinline__ constexpr int link(int q) const { return Desc::sh().link[q]; }
-    __device__ __forceinline__ constexpr ArgS cov(int t) const { return Desc::sh().cov[t]; }
-    __device__ __forceinline__ constexpr ArgS y() const { return Desc::sh().y; }
-    __device__ __forceinline__ constexpr ArgS aux(int q) const { return Desc::sh().aux[q]; }
+    __device__ __forceinline__ constexpr int kg() const { return g_shape_of<Desc>.kg; }
+    __device__ __forceinline__ constexpr int nl() const { return g_shape_of<Desc>.nl; }
+    __device__ __forceinline__ constexpr int has_off() const { return g_shape_of<Desc>.has_off; }
+    __device__ __forceinline__ constexpr int n_gref() const { return g_shape_of<Desc>.n_gref; }
+    __device__ __forceinline__ constexpr int family() const { return g_shape_of<Desc>.family; }
+    __device__ __forceinline__ constexpr int eta_arg() const { return g_shape_of<Desc>.eta_arg; }
+    __device__ __forceinline__ constexpr int has_obs() const { return g_shape_of<Desc>.has_obs; }
+    __device__ __forceinline__ constexpr int n_link() const { return g_shape_of<Desc>.n_link; }
+    __device__ __forceinline__ constexpr int link(int q) const { return g_shape_of<Desc>.link[q]; }
+    __device__ __forceinline__ constexpr ArgS cov(int t) const { return g_shape_of<Desc>.cov[t]; }
+    __device__ __forceinline__ constexpr ArgS y() const { return g_shape_of<Desc>.y; }
+    __device__ __forceinline__ constexpr ArgS aux(int q) const { return g_shape_of<Desc>.aux[q]; }
     __device__ __forceinline__ constexpr bool has_w() const {  // (only a run-time generated description has a weight)
-        return Desc::sh().aux[2].kind == JBUGS_ARG_DATA_I || Desc::sh().aux[2].kind == JBUGS_ARG_DATA_IJ;
+        return g_shape_of<Desc>.aux[2].kind == JBUGS_ARG_DATA_I || g_shape_of<Desc>.aux[2].kind == JBUGS_ARG_DATA_IJ;
     }
-    __device__ __forceinline__ constexpr int loc_level(int l) const { return Desc::sh().loc[l].level; }
-    __device__ __forceinline__ constexpr int loc_transform(int l) const { return Desc::sh().loc[l].transform; }
-    __device__ __forceinline__ constexpr int loc_family(int l) const { return Desc::sh().loc[l].family; }
-    __device__ __forceinline__ constexpr int loc_has_idx(int l) const { return Desc::sh().loc[l].has_idx; }
-    __device__ __forceinline__ constexpr ArgS loc_arg(int l, int q) const { return Desc::sh().loc[l].args[q]; }
+    __device__ __forceinline__ constexpr int loc_level(int l) const { return g_shape_of<Desc>.loc[l].level; }
+    __device__ __forceinline__ constexpr int loc_transform(int l) const { return g_shape_of<Desc>.loc[l].transform; }
+    __device__ __forceinline__ constexpr int loc_family(int l) const { return g_shape_of<Desc>.loc[l].family; }
+    __device__ __forceinline__ constexpr int loc_has_idx(int l) const { return g_shape_of<Desc>.loc[l].has_idx; }
+    __device__ __forceinline__ constexpr ArgS loc_arg(int l, int q) const { return g_shape_of<Desc>.loc[l].args[q]; }
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -189,13 +189,13 @@ __device__ __forceinline__ double predictor(const S& sp, const PlateVals& V, con
                                             const ChainState& st, double (&cv)[MAX_TERMS]) {
     double eta = -0.0;  // (additive identity that folds, see local_enter)
 #pragma unroll
-    for (int t = 0; t < MAX_GT; ++t)
+    for (int t = 0; t < S::KG_MAX; ++t)
         if (t < sp.kg()) {
             cv[t] = arg_value<S::SOFF>(sp.cov(t), V.cov[t], st, sv, g, j);
             eta = fma(st.gv[t], cv[t], eta);
         }
 #pragma unroll
-    for (int l = 0; l < MAX_LOC; ++l)
+    for (int l = 0; l < S::NL_MAX; ++l)
         if (l < sp.nl()) {
             cv[MAX_GT + l] = arg_value<S::SOFF>(sp.cov(sp.kg() + l), V.cov[sp.kg() + l], st, sv, g, j);
             eta = fma(st.lx[l], cv[MAX_GT + l], eta);
@@ -364,35 +364,36 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
     bool bad = false;
     if (sp.has_w() && arg_value<S::SOFF>(sp.aux(2), V.aux[2], st, sv, g, j) == 0.0) return false;  // padded cell: no observation
     if constexpr (S::XTAPE) return observe_tape(sp, V, sv, g, j, st, lp);
+    if constexpr (S::XGEN) return S::D::observe_gen(sp, V, sv, g, j, st, lp);
     const double eta = predictor(sp, V, sv, g, j, st, cv);
     const double yv = arg_value<S::SOFF>(sp.y(), V.y, st, sv, g, j);
 
-    if (S::FUSED == FUSED_NORMAL_IDENTITY) {
+    if constexpr (S::FUSED == FUSED_NORMAL_IDENTITY) {
         // y ~ dnorm(eta, tau), tau chain-invariant: d/d eta = tau * r; tau is factored out of every sum
         const double r = yv - eta;
         fa.ss = fma(r, r, fa.ss);
 #pragma unroll
-        for (int t = 0; t < MAX_GT; ++t)
+        for (int t = 0; t < S::KG_MAX; ++t)
             if (t < sp.kg()) fa.sg[t] = fma(r, cv[t], fa.sg[t]);
 #pragma unroll
-        for (int l = 0; l < MAX_LOC; ++l)
+        for (int l = 0; l < S::NL_MAX; ++l)
             if (l < sp.nl()) sl[l] = fma(r, cv[MAX_GT + l], sl[l]);
         return false;
     }
 
     double deta;
-    if (S::FUSED == FUSED_BINOMIAL_LOGIT || S::FUSED == FUSED_BERNOULLI_LOGIT) {
+    if constexpr (S::FUSED == FUSED_BINOMIAL_LOGIT || S::FUSED == FUSED_BERNOULLI_LOGIT) {
         // k ~ dbin(logistic(eta), n): branch-free, selects and range tests on the integer pipe (binomial_logit);
         // the saturated tails are fixed up once per unrolled block of groups (eval_groups), not per observation
         const double n = S::FUSED == FUSED_BERNOULLI_LOGIT ? 1.0 : arg_value<S::SOFF>(sp.aux(1), V.aux[1], st, sv, g, j);
         binomial_logit(eta, yv, n, lp, deta, st.sat);
-    } else if (S::FUSED == FUSED_POISSON_LOG) {
+    } else if constexpr (S::FUSED == FUSED_POISSON_LOG) {
         // k ~ dpois(exp(eta)): k * eta - exp(eta); -lgamma(k+1) goes to obs_const
         const double lam = exp(eta);
         // xlogy(k, lambda) saturates to -Inf once exp underflows to 0 (reference semantics)
         lp += (yv == 0.0 ? 0.0 : (lam == 0.0 ? -dev_inf() : yv * eta)) - lam;
         deta = yv - lam;
-    } else if (S::FUSED == FUSED_BINOMIAL_LINK || S::FUSED == FUSED_BERNOULLI_LINK || S::FUSED == FUSED_POISSON_LINK) {
+    } else if constexpr (S::FUSED == FUSED_BINOMIAL_LINK || S::FUSED == FUSED_BERNOULLI_LINK || S::FUSED == FUSED_POISSON_LINK) {
         // any inverse-link tape; only the theta-dependent part of the log-density (the rest is in obs_const)
         double v = eta, dv = 1.0;
 #pragma unroll
@@ -403,7 +404,7 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
                 v = nv;
                 dv *= d;
             }
-        if (S::FUSED == FUSED_POISSON_LINK) {
+        if constexpr (S::FUSED == FUSED_POISSON_LINK) {
             bad |= !(v >= 0.0);
             lp += xlogy(yv, v) - v;
             deta = ((yv == 0.0 ? 0.0 : yv / v) - 1.0) * dv;
@@ -435,10 +436,10 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
         if (ea != 1) arg_adjoint(sp.aux(1), st, o.da1);
     }
 #pragma unroll
-    for (int t = 0; t < MAX_GT; ++t)
+    for (int t = 0; t < S::KG_MAX; ++t)
         if (t < sp.kg()) st.ga[t] = fma(deta, cv[t], st.ga[t]);
 #pragma unroll
-    for (int l = 0; l < MAX_LOC; ++l)
+    for (int l = 0; l < S::NL_MAX; ++l)
         if (l < sp.nl()) st.la[l] = fma(deta, cv[MAX_GT + l], st.la[l]);
     return bad;
 }
@@ -477,7 +478,7 @@ __device__ __forceinline__ void load_groups(const S& sp, const PlateVals& V, lon
 #pragma unroll
     for (int u = 0; u < UU; ++u)
 #pragma unroll
-        for (int l = 0; l < MAX_LOC; ++l) {
+        for (int l = 0; l < S::NL_MAX; ++l) {
             if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) {
                 if (sp.loc_has_idx(l)) {
                     gl.off[u][l] = local_slot(sp, V, l, i + u, 0) * ld;
@@ -516,22 +517,22 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
     for (int u = 0; u < UU; ++u) {
         double ldx[MAX_LOC], ldlj[MAX_LOC], sl[MAX_LOC];
 #pragma unroll
-        for (int l = 0; l < MAX_LOC; ++l) {
+        for (int l = 0; l < S::NL_MAX; ++l) {
             sl[l] = -0.0;
             if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) local_enter(sp, V, l, raw[u][l], st, ldx, ldlj, lp);
         }
 #pragma unroll
-        for (int l = 0; l < MAX_LOC; ++l)
+        for (int l = 0; l < S::NL_MAX; ++l)
             if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) bad |= local_prior(sp, V, l, sv, g + u, 0, st, fa, lp);
 
         long long opos[MAX_LOC];
 #pragma unroll
-        for (int l = 0; l < MAX_LOC; ++l) opos[l] = (TS > 0 && !sp.loc_has_idx(l)) ? gl.obase[u][l] : pos[l];
+        for (int l = 0; l < S::NL_MAX; ++l) opos[l] = (TS > 0 && !sp.loc_has_idx(l)) ? gl.obase[u][l] : pos[l];
 #pragma unroll(S::T_STATIC > 0 ? S::T_STATIC : 1)
         for (int j = 0; j < T; ++j) {
             long long ooff[MAX_LOC];
 #pragma unroll
-            for (int l = 0; l < MAX_LOC; ++l)
+            for (int l = 0; l < S::NL_MAX; ++l)
                 if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) {
                     if (sp.loc_has_idx(l)) {
                         ooff[l] = local_slot(sp, V, l, i + u, j) * ld;
@@ -543,13 +544,13 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
                     local_enter(sp, V, l, rawv, st, ldx, ldlj, lp);
                 }
 #pragma unroll
-            for (int l = 0; l < MAX_LOC; ++l)
+            for (int l = 0; l < S::NL_MAX; ++l)
                 if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) bad |= local_prior(sp, V, l, sv, g + u, j, st, fa, lp);
             if (sp.has_obs()) bad |= observe(sp, V, sv, g + u, j, st, fa, sl, lp);
 #pragma unroll
-            for (int l = 0; l < MAX_LOC; ++l)
+            for (int l = 0; l < S::NL_MAX; ++l)
                 if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) {
-                    if (S::FUSED == FUSED_NORMAL_IDENTITY) {
+                    if constexpr (S::FUSED == FUSED_NORMAL_IDENTITY) {
                         st.la[l] = fma(obs_tau, sl[l], st.la[l]);
                         sl[l] = -0.0;
                     }
@@ -558,7 +559,7 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
                 }
         }
 #pragma unroll
-        for (int l = 0; l < MAX_LOC; ++l) {
+        for (int l = 0; l < S::NL_MAX; ++l) {
             if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS && !(TS > 0 && !sp.loc_has_idx(l)))
                 pos[l] += V.loc[l].step_i;
             if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) {
@@ -568,7 +569,7 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
             }
         }
     }
-    if ((S::FUSED == FUSED_BINOMIAL_LOGIT || S::FUSED == FUSED_BERNOULLI_LOGIT) && __builtin_expect(st.sat != 0, 0)) {
+    if constexpr (S::FUSED == FUSED_BINOMIAL_LOGIT || S::FUSED == FUSED_BERNOULLI_LOGIT) if (__builtin_expect(st.sat != 0, 0)) {
         // rare: some |eta| of this block lies where the reference's logistic is exactly 0 or 1.  Walk the block again,
         // recompute each linear predictor (same arithmetic, same bits) and give the observation the reference's -Inf
         // where it applies; the finite value the hot path added is swallowed by it.
@@ -577,16 +578,16 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
         for (int u = 0; u < UU; ++u) {
             double d0[MAX_LOC], d1[MAX_LOC], dummy = 0.0;
 #pragma unroll
-            for (int l = 0; l < MAX_LOC; ++l)
+            for (int l = 0; l < S::NL_MAX; ++l)
                 if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_GROUP) local_enter(sp, V, l, raw[u][l], st, d0, d1, dummy);
             long long opos[MAX_LOC];
 #pragma unroll
-            for (int l = 0; l < MAX_LOC; ++l)  // pos[] has moved past the block: group u sits (UU - u) steps back
+            for (int l = 0; l < S::NL_MAX; ++l)  // pos[] has moved past the block: group u sits (UU - u) steps back
                 opos[l] = (TS > 0 && !sp.loc_has_idx(l)) ? gl.obase[u][l] : pos[l] - (long long)(UU - u) * V.loc[l].step_i;
 #pragma unroll 1
             for (int j = 0; j < T; ++j) {
 #pragma unroll
-                for (int l = 0; l < MAX_LOC; ++l)
+                for (int l = 0; l < S::NL_MAX; ++l)
                     if (l < sp.nl() && sp.loc_level(l) == JBUGS_LEVEL_OBS) {
                         const long long o = sp.loc_has_idx(l) ? local_slot(sp, V, l, i + u, j) * ld : opos[l] + j * V.loc[l].step_j;
                         local_enter(sp, V, l, th[o], st, d0, d1, dummy);
@@ -662,7 +663,7 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
         st.ga[k] = 0.0;
     }
 #pragma unroll
-    for (int l = 0; l < MAX_LOC; ++l)
+    for (int l = 0; l < S::NL_MAX; ++l)
         if (l < sp.nl() && sp.loc_family(l) == JBUGS_FAM_GAMMA && arg_invariant(sp.loc_arg(l, 0)) &&
             arg_invariant(sp.loc_arg(l, 1))) {
             const ArgS s0 = sp.loc_arg(l, 0), s1 = sp.loc_arg(l, 1);
@@ -675,9 +676,9 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
     FusedAcc fa;
     fa.ss = 0.0;
 #pragma unroll
-    for (int t = 0; t < MAX_GT; ++t) fa.sg[t] = 0.0;
+    for (int t = 0; t < S::KG_MAX; ++t) fa.sg[t] = 0.0;
 #pragma unroll
-    for (int l = 0; l < MAX_LOC; ++l) fa.pss[l] = fa.ps[l] = fa.pd[l] = 0.0;
+    for (int l = 0; l < S::NL_MAX; ++l) fa.pss[l] = fa.ps[l] = fa.pd[l] = 0.0;
     st.sat = 0;
 
     double lp = 0.0;
@@ -692,7 +693,7 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
 
     long long pos[MAX_LOC];
 #pragma unroll
-    for (int l = 0; l < MAX_LOC; ++l) pos[l] = V.loc[l].row0 + V.loc[l].step_i * ib;
+    for (int l = 0; l < S::NL_MAX; ++l) pos[l] = V.loc[l].row0 + V.loc[l].step_i * ib;
 
     stage_ok &= stage_wait<TMA>(next_bulk, &mbar[0], parity_bits & 1u);
     if (next_bulk) parity_bits ^= 1u;
@@ -716,7 +717,7 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
         int g = 0;
         for (; g + U <= cnt; g += U) {
             const long long i = i0 + g;
-            if (S::PREFETCH || !GRAD) {  // forward-only: no store traffic to fill the memory pipe, so keep twice the loads in flight
+            if constexpr (S::PREFETCH || !GRAD) {  // forward-only: no store traffic to fill the memory pipe, so keep twice the loads in flight
                 // software pipeline over U-blocks (also across staged chunks: the theta rows do not depend on the
                 // staged data): the loads of block i+U are in flight while block i is evaluated
                 if (!have_cur) load_groups<S, U>(sp, V, i, th, ld, pos, gl_cur);
@@ -748,18 +749,18 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
 
     // expand the sufficient statistics of the fused paths
     const double n_obs = (double)((ie - ib) * V.T);
-    if (S::FUSED == FUSED_NORMAL_IDENTITY) {
+    if constexpr (S::FUSED == FUSED_NORMAL_IDENTITY) {
         const bool tg = sp.aux(1).kind == JBUGS_ARG_GVAL;
         const double tau = obs_tau;
         bad |= tau < 0.0;
         lp += n_obs * (0.5 * log(tau) - 0.5 * kLog2Pi) - 0.5 * tau * fa.ss;
         if (tg) bump(st.ga, sp.aux(1).id, n_obs * 0.5 / tau - 0.5 * fa.ss);
 #pragma unroll
-        for (int t = 0; t < MAX_GT; ++t)
+        for (int t = 0; t < S::KG_MAX; ++t)
             if (t < sp.kg()) st.ga[t] = fma(tau, fa.sg[t], st.ga[t]);
     }
 #pragma unroll
-    for (int l = 0; l < MAX_LOC; ++l)
+    for (int l = 0; l < S::NL_MAX; ++l)
         if (l < sp.nl() && sp.prior_fused(l)) {
             const ArgS a0 = sp.loc_arg(l, 0), a1 = sp.loc_arg(l, 1);
             const double tau = prior_tau(sp, V, l, st);

@@ -26,7 +26,7 @@ SYMBOLS = [
     "jbugs_comm_destroy", "jbugs_launch_count", "jbugs_plan_describe", "jbugs_plan_set_option",
     "jbugs_last_timing", "jbugs_hmc_create", "jbugs_hmc_destroy", "jbugs_hmc_init", "jbugs_hmc_run",
     "jbugs_hmc_get_state", "jbugs_hmc_run_nuts", "jbugs_hmc_nuts_stats", "jbugs_plan_specialize", "jbugs_hmc_draw_momentum", "jbugs_timing_history", "jbugs_host_alloc_ex",
-    "jbugs_bind_host_to_device", "jbugs_fp64_peak", "jbugs_eval_batch_tempered",
+    "jbugs_bind_host_to_device", "jbugs_fp64_peak", "jbugs_eval_batch_tempered", "jbugs_jit_last_compile_seconds", "jbugs_plan_specialize_async",
 ]
 
 
@@ -59,6 +59,8 @@ def load():
     L.jbugs_plan_set_shard.argtypes = [c.c_void_p, c.c_int, c.c_int64, c.c_int64]
     L.jbugs_plan_set_dense_shard.argtypes = [c.c_void_p, c.c_int64, c.c_int64]
     L.jbugs_plan_specialize.argtypes = [c.c_void_p, c.c_char_p]
+    L.jbugs_jit_last_compile_seconds.restype = c.c_double
+    L.jbugs_plan_specialize_async.argtypes = [c.c_void_p, c.c_char_p]
     L.jbugs_eval_batch.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_void_p, c.c_void_p,
                                    c.c_void_p, c.c_int, c.c_int, c.c_void_p]
     L.jbugs_eval_batch_tempered.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_double, c.c_void_p,
@@ -145,9 +147,18 @@ class CudaPlan:
         _check(self.L.jbugs_plan_set_shard(self.h, plate, i0, i1))
 
     def specialize(self, cache_dir: Optional[str] = None):
-        """compile the plate kernel for the exact shape of every plate that has no in-tree specialisation (nvcc at run
-        time, cached on disk); without it those plates run the interpreter instantiation."""
+        """compile the plate kernel for the exact shape of every plate that has no in-tree specialisation, expression
+        tapes included (NVRTC in-process, cubins cached in a per-user directory; "none" disables the cache); without it
+        those plates run the interpreter instantiations."""
         _check(self.L.jbugs_plan_specialize(self.h, cache_dir.encode() if cache_dir else None))
+
+    def specialize_async(self, cache_dir: Optional[str] = None):
+        """`specialize` without blocking: the compiler runs on a worker thread, evaluations switch over when it is done"""
+        _check(self.L.jbugs_plan_specialize_async(self.h, cache_dir.encode() if cache_dir else None))
+
+    def last_compile_seconds(self) -> float:
+        """seconds NVRTC spent in the last `specialize` call of this process (0.0: everything came from the cache)"""
+        return float(self.L.jbugs_jit_last_compile_seconds())
 
     def set_dense_shard(self, i0: int, i1: int):
         _check(self.L.jbugs_plan_set_dense_shard(self.h, i0, i1))
