@@ -22,6 +22,7 @@
 #include "jbugs_dense.cuh"
 #include "jbugs_hmc.cuh"
 #include "jbugs_nuts.cuh"
+#include "jbugs_gq.cuh"
 #define JBUGS_SPEC_TABLE
 #include "jbugs_specs.cuh"
 
@@ -1442,6 +1443,7 @@ extern "C" int jbugs_eval_batch_tempered(jbugs_plan* p, const double* theta, int
 #include "jbugs_hmc.inc"
 #include "jbugs_nuts.inc"
 #include "jbugs_jit.inc"
+#include "jbugs_gq.inc"
 
 extern "C" int jbugs_batch_alloc(jbugs_plan* p, int64_t C, double** theta_dev, double** grad_dev, double** logp_dev,
                                  int32_t** status_dev, int64_t* ld) {

@@ -10,4 +10,4 @@ from .model import (  # noqa: F401
     set_evaluation_mode, settrans,
 )
 from .cuda import CudaPlan, JBugsCudaError  # noqa: F401
-from . import dist, gq, hmc  # noqa: F401,E402
+from . import dist, gq, gq_device, hmc  # noqa: F401,E402

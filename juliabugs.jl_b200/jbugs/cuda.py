@@ -27,6 +27,7 @@ SYMBOLS = [
     "jbugs_last_timing", "jbugs_hmc_create", "jbugs_hmc_destroy", "jbugs_hmc_init", "jbugs_hmc_run",
     "jbugs_hmc_get_state", "jbugs_hmc_run_nuts", "jbugs_hmc_nuts_stats", "jbugs_plan_specialize", "jbugs_hmc_draw_momentum", "jbugs_timing_history", "jbugs_host_alloc_ex",
     "jbugs_bind_host_to_device", "jbugs_fp64_peak", "jbugs_eval_batch_tempered", "jbugs_jit_last_compile_seconds", "jbugs_plan_specialize_async",
+    "jbugs_gq_create", "jbugs_gq_destroy", "jbugs_gq_run", "jbugs_gq_launch_count",
 ]
 
 

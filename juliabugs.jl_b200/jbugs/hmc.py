@@ -46,6 +46,8 @@ class Chains:
     n_divergent: int = 0
     tree_depth: float = 0.0     # NUTS: mean tree depth of the last transition
     _gq: Optional[Dict[str, np.ndarray]] = None
+    raw: Optional[np.ndarray] = None      # the same draws in unconstrained space (what the device program reads)
+    rows: Optional[np.ndarray] = None     # theta index of every monitored row
 
     def __getitem__(self, name: str) -> np.ndarray:
         """draws of a monitored parameter ('tau', 'beta[2]') or of a generated quantity ('sigma', 'b0', 'outlier[21]'),
@@ -67,9 +69,20 @@ class Chains:
         return {n: dict(mean=float(self[n].mean()), std=float(self[n].std(ddof=1)), rhat=split_rhat(self[n]),
                         ess=effective_sample_size(self[n])) for n in (names or self.names)}
 
-    def generated_quantities(self, seed: int = 0) -> Dict[str, np.ndarray]:
+    def generated_quantities(self, seed: int = 0, device: bool = False) -> Dict[str, np.ndarray]:
         """logical nodes outside the target and forward draws of unobserved stochastic leaves, computed from the
-        monitored parameters for every draw at once (reference: J/src/model/abstractmcmc.jl:92-110)."""
+        monitored parameters for every draw at once (reference: J/src/model/abstractmcmc.jl:92-110).
+        `device=True`: the lowered program on the GPU (jbugs/gq_device.py, one thread per draw) instead of numpy on
+        the host; the monitored rows must cover the parameters the quantities read."""
+        if self._gq is None and device:
+            from .gq_device import DeviceGQ
+            dq = DeviceGQ(self.model.lowering, device=self.model.evaluation_mode.device, only_gq=True)
+            try:
+                n, k, c = self.raw.shape
+                th = np.ascontiguousarray(self.raw.transpose(1, 0, 2).reshape(k, n * c))
+                self._gq = dq.run(th, rows=self.rows, seed=seed)
+            finally:
+                dq.close()
         if self._gq is None:
             from .gq import generated_quantities
             draws = {n: self.samples[:, k, :].ravel() for k, n in enumerate(self.names)}
@@ -184,8 +197,9 @@ def sample(model: BUGSModel, sampler, n_samples: int, n_adapts: int = 500, n_cha
         _check(L.jbugs_hmc_nuts_stats(h, ctypes.byref(n_div), ctypes.byref(depth)))
     finally:
         L.jbugs_hmc_destroy(h)
+    raw = out.copy()
     for k, n in enumerate(names):
         _, tr_k, lb, ub = by_name[n]
         out[:, k, :] = _constrain(tr_k, lb, ub, out[:, k, :])
     return Chains(names, out, float(acc.value), float(eps.value), model, n_divergent=int(n_div.value),
-                  tree_depth=float(depth.value))
+                  tree_depth=float(depth.value), raw=raw, rows=rows)

@@ -24,7 +24,7 @@ def lib():
 
 
 def test_header_symbols_are_exported(lib):
-    hdr = open(os.path.join(ROOT, "include", "jbugs_cuda.h")).read()
+    hdr = open(os.path.join(ROOT, "include", "jbugs_cuda.h")).read() + open(os.path.join(ROOT, "include", "jbugs_gq.h")).read()
     declared = set(re.findall(r"\b(jbugs_[a-z_0-9]+)\s*\(", hdr))
     assert declared == set(cuda.SYMBOLS), declared ^ set(cuda.SYMBOLS)
     for s in declared:
