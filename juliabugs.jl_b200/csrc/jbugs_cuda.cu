@@ -25,6 +25,7 @@
 #include "jbugs_gq.cuh"
 #define JBUGS_SPEC_TABLE
 #include "jbugs_specs.cuh"
+static_assert(jbugs::CHAIN_OK == JBUGS_CHAIN_OK && jbugs::CHAIN_DOMAIN == JBUGS_CHAIN_DOMAIN, "status codes of the kernels and of the ABI differ");
 
 using namespace jbugs;
 
@@ -139,6 +140,12 @@ struct jbugs_plan_s {
     double* d_red = nullptr;   // [1 + NG][ldg] reduced partials (multi-GPU path)
     int* d_flags = nullptr;
     int* d_any_bad = nullptr;
+    // one-launch evaluation of small single-plate models (fused_small_kernel): its own DomainError flags and one ticket
+    // per chain block, both zero between evaluations (the kernel cleans up after itself)
+    int* d_fflags = nullptr;
+    unsigned* d_tickets = nullptr;
+    size_t fflags_bytes = 0, tickets_bytes = 0;
+    int one_launch = 1;  // option "one_launch"
     // pipelined host path: two staging slots, copy-in / copy-out streams, per-slot events
     struct Slot {
         double *theta = nullptr, *grad = nullptr, *theta_t = nullptr, *grad_t = nullptr, *logp = nullptr;
@@ -730,6 +737,8 @@ extern "C" int jbugs_plan_destroy(jbugs_plan* p) {
     if (p->st_out) cudaStreamDestroy(p->st_out);
     jbugs_batch_free(p);
     cudaFree(p->d_any_bad);
+    cudaFree(p->d_fflags);
+    cudaFree(p->d_tickets);
     for (auto& e : p->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : p->ring)
@@ -834,6 +843,11 @@ extern "C" int jbugs_plan_set_option(jbugs_plan* p, const char* key, int64_t val
     if (!strcmp(key, "host_chunk")) {
         if (value < 0) return fail(JBUGS_ERR_INVALID, "host_chunk must be >= 0");
         p->host_chunk = value;
+        return JBUGS_OK;
+    }
+    if (!strcmp(key, "one_launch")) {  // 0: always the three-kernel sequence (A/B against fused_small_kernel)
+        p->one_launch = value != 0;
+        p->epoch++;
         return JBUGS_OK;
     }
     if (!strcmp(key, "pdl")) {
@@ -1101,6 +1115,12 @@ static int ensure_workspace(jbugs_plan* p, long long C) {
     const long long red_rows = 2 + std::max(NG, 1) + (p->dense.empty() ? 0 : p->dense[0].P);
     if ((rc = grow((void**)&p->d_red, &p->red_bytes, (size_t)red_rows * ldg * 8))) return rc;
     if ((rc = grow((void**)&p->d_flags, &p->flags_bytes, (size_t)ldg * sizeof(int)))) return rc;
+    if ((size_t)ldg * sizeof(int) > p->fflags_bytes) {
+        if ((rc = grow((void**)&p->d_fflags, &p->fflags_bytes, (size_t)ldg * sizeof(int)))) return rc;
+        if ((rc = grow((void**)&p->d_tickets, &p->tickets_bytes, (size_t)(ldg / 32 + 1) * sizeof(unsigned)))) return rc;
+        CU(cudaMemset(p->d_fflags, 0, p->fflags_bytes));
+        CU(cudaMemset(p->d_tickets, 0, p->tickets_bytes));
+    }
     p->cap_C = C;
     p->ldg = ldg;
     return 0;
@@ -1141,6 +1161,37 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
     const unsigned helper_tiles = (unsigned)((C + hblk - 1) / hblk);
     for (size_t k = 0; k < p->rt.size(); ++k)
         if ((rc = refresh_obs_const(p, (int)k, st))) return rc;
+    // small single-plate model: prologue + plate + finalize in ONE kernel (latency-bound: BASELINE config 5)
+    if (p->one_launch && p->rt.size() == 1 && p->dense.empty() && !(p->comm && p->nranks > 1) && !p->timing && p->parts == 0 &&
+        p->h.D <= 4096 && p->rt[0].n_tiles <= 64 && p->rt[0].pp.v.i1 > p->rt[0].pp.v.i0) {
+        PlateRt& r = p->rt[0];
+        const bool jit = (r.variant == 0 || r.variant == g_xspec) && r.jit && r.jit_valid && !p->force_dynamic;
+        const fused_launch_fn fn = jit ? nullptr : g_specs[r.variant].one_launch;
+        if (fn) {
+            FusedParams fq;
+            fq.G = p->gp;
+            fq.TP = p->tp;
+            memset(&fq.F, 0, sizeof fq.F);
+            fq.F.n_plates = 1;
+            fq.F.poison_rows = (want_grad && grad) ? p->h.D : 0;
+            fq.F.p[0].n_tiles = (int)r.n_tiles;
+            fq.F.p[0].n_gref = r.pp.sh.n_gref;
+            fq.F.p[0].offset = 0;  // (the kernel gets the plate's own slice of the partial buffer)
+            fq.F.p[0].obs_const = r.variant == 0 ? 0.0 : r.obs_const;  // the interpreter evaluates the full log-density itself
+            for (int q = 0; q < MAX_GREF; ++q) fq.F.p[0].gref[q] = r.pp.v.gref[q];
+            fq.P = r.pp;
+            for (int l = 0; l < fq.P.sh.nl; ++l) {
+                fq.P.v.loc[l].row0 = fq.P.v.loc[l].base * ld;
+                fq.P.v.loc[l].step_i = fq.P.v.loc[l].si * ld;
+                fq.P.v.loc[l].step_j = fq.P.v.loc[l].sj * ld;
+            }
+            cudaError_t le = fn(r.n_tiles, r.smem_bytes, st, fq, theta, grad, ld, C, p->d_gvals, ldg, p->d_partial + r.partial_offset * ldg,
+                                p->d_fflags, logp, status, p->d_any_bad, want_grad && grad, p->d_tickets, p->use_pdl);
+            if (le != cudaSuccess) return fail(JBUGS_ERR_CUDA, "one-launch kernel failed: %s", cudaGetErrorString(le));
+            p->launches++;
+            return 0;
+        }
+    }
     cudaEvent_t* tev = p->ev;  // the four events of this call
     if (p->timing && !p->ring.empty()) tev = p->ring.data() + 4 * (p->ring_n % jbugs_plan_s::RING);
     if (p->timing) CU(cudaEventRecord(tev[0], st));

@@ -33,6 +33,7 @@ constexpr int MAX_TERMS = MAX_GT + MAX_LOC + 1;  // + optional data offset
 constexpr int MAX_GREF = 12;                     // distinct global values a plate references
 constexpr int MAX_GVALS = 64;                    // globals + gtape results of a plan
 constexpr int BLOCK = 128;                       // chains per CTA
+constexpr int CHAIN_OK = 0, CHAIN_DOMAIN = 1;    // JBUGS_CHAIN_OK / JBUGS_CHAIN_DOMAIN of jbugs_cuda.h (checked in jbugs_cuda.cu)
 
 struct ArgS {  // structural half of an argument
     int kind;  // jbugs_arg_kind
@@ -343,8 +344,7 @@ __device__ __forceinline__ bool gtape_forward(const jbugs_gop& o, const double* 
     }
 }
 
-#ifdef JBUGS_HOST_TU  // the non-template kernels are compiled once, in the host translation unit
-// Thread-per-chain helper kernels run with very few warps per SM, so a load whose result is consumed right away
+// Thread-per-chain helper code runs with very few warps per SM, so a load whose result is consumed right away
 // costs a full memory round trip each time (the warp issues in order).  `batched_load` issues eight independent
 // loads before the first use; the index is clamped instead of predicated so that the loads stay unconditional.
 template <typename AddrFn>
@@ -360,15 +360,13 @@ __device__ __forceinline__ void batched_load(double* __restrict__ dst, int n, Ad
     }
 }
 
-__global__ void __launch_bounds__(BLOCK)
-prologue_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__ GTapeParams TP,
-                const double* __restrict__ theta, long long ld, long long C, double* __restrict__ gvals,
-                long long ldg, int* __restrict__ flags, int* __restrict__ any_bad) {
-    pdl_launch_dependents();  // the plate kernel may get going (it waits before it reads gvals)
-    pdl_wait();               // theta may come from the kernel before (a leapfrog update); gvals / flags are still being read
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    if (c == 0) *any_bad = 0;
+// constrained globals + gtape of chain c -> gvals[k][c].  ONE_LAUNCH: part of fused_small_kernel, where every CTA of a
+// chain block runs it for its own chains (identical values to identical addresses) and a DomainError is OR-ed into
+// the flag instead of stored, because the other CTAs' plate tiles raise the same flag concurrently.
+template <bool ONE_LAUNCH>
+__device__ __forceinline__ void prologue_body(const GlobalsParams& G, const GTapeParams& TP, const double* __restrict__ theta,
+                                              long long ld, long long c, double* __restrict__ gvals, long long ldg,
+                                              int* __restrict__ flags) {
     double gv[MAX_GVALS];
     bool bad = false;
     batched_load(gv, G.n_globals, [&](int h) { return theta + G.g[h].theta_idx * ld + c; });
@@ -380,7 +378,24 @@ prologue_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
         gv[G.n_globals + k] = v;
     }
     for (int k = 0; k < G.n_globals + G.n_gtape; ++k) gvals[k * ldg + c] = gv[k];
-    flags[c] = bad ? 1 : 0;
+    if (ONE_LAUNCH) {
+        if (bad) atomicOr(flags + c, 1);
+    } else {
+        flags[c] = bad ? 1 : 0;
+    }
+}
+
+#ifdef JBUGS_HOST_TU  // the non-template kernels are compiled once, in the host translation unit
+__global__ void __launch_bounds__(BLOCK)
+prologue_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__ GTapeParams TP,
+                const double* __restrict__ theta, long long ld, long long C, double* __restrict__ gvals,
+                long long ldg, int* __restrict__ flags, int* __restrict__ any_bad) {
+    pdl_launch_dependents();  // the plate kernel may get going (it waits before it reads gvals)
+    pdl_wait();               // theta may come from the kernel before (a leapfrog update); gvals / flags are still being read
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    if (c == 0) *any_bad = 0;
+    prologue_body<false>(G, TP, theta, ld, c, gvals, ldg, flags);
 }
 #endif  // JBUGS_HOST_TU
 
@@ -390,7 +405,6 @@ prologue_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
 
 namespace jbugs {
 
-#ifdef JBUGS_HOST_TU
 // ------------------------------------------------------------------------------------------------
 // finalize: add the tiles in ascending order, the priors of the globals, reverse the gtape and the
 // bijectors; write logp, status and the gradient rows of the globals.
@@ -407,27 +421,26 @@ struct FinalParams {
     PlateFinal p[8];
 };
 
-__global__ void __launch_bounds__(BLOCK)
-finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__ GTapeParams TP,
-                const __grid_constant__ FinalParams F, const double* __restrict__ theta, double* __restrict__ grad,
-                long long ld, long long C, const double* __restrict__ gvals, long long ldg,
-                const double* __restrict__ partial, int* __restrict__ flags, double* __restrict__ logp_out,
-                int* __restrict__ status_out, int* __restrict__ any_bad, int want_grad, int mode,
-                double* __restrict__ red) {
-    // mode 0: single GPU, everything in one pass.
-    // mode 1: observation-sharded, first half: write this rank's reduced partials red[0] = logp part,
-    //         red[1 + k] = adjoint of global value k, red[1 + NG] = DomainError flag; the host all-reduces `red`.
-    // mode 2: second half: read the all-reduced `red`, add the priors of the globals ONCE, finish.
-    pdl_wait();  // partials, gvals and flags come from the kernels before this one
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// mode 0: single GPU, everything in one pass.
+// mode 1: observation-sharded, first half: write this rank's reduced partials red[0] = logp part,
+//         red[1 + k] = adjoint of global value k, red[1 + NG] = DomainError flag; the host all-reduces `red`.
+// mode 2: second half: read the all-reduced `red`, add the priors of the globals ONCE, finish.
+// ONE_LAUNCH: the last CTA of a chain block inside fused_small_kernel; partials and flags were written by other CTAs
+// of the same launch, so they are read past L1 (__ldcg).
+template <bool ONE_LAUNCH>
+__device__ __forceinline__ void finalize_body(const GlobalsParams& G, const GTapeParams& TP, const FinalParams& F,
+                                              const double* __restrict__ theta, double* __restrict__ grad, long long ld,
+                                              long long c, const double* __restrict__ gvals, long long ldg,
+                                              const double* partial, int* flags, double* __restrict__ logp_out,
+                                              int* __restrict__ status_out, int* __restrict__ any_bad, int want_grad,
+                                              int mode, double* __restrict__ red) {
     const int H = G.n_globals, NG = G.n_globals + G.n_gtape;
     double gv[MAX_GVALS], ga[MAX_GVALS], th[MAX_GVALS];
     batched_load(gv, NG, [&](int k) { return gvals + k * ldg + c; });
     if (mode != 1) batched_load(th, H, [&](int h) { return theta + G.g[h].theta_idx * ld + c; });
     for (int k = 0; k < NG; ++k) ga[k] = 0.0;
     double lp = 0.0;
-    bool bad = flags[c] != 0;
+    bool bad = (ONE_LAUNCH ? __ldcg(flags + c) : flags[c]) != 0;
     if (mode == 2) {
         lp = red[c];
         batched_load(ga, NG, [&](int k) { return red + (long long)(1 + k) * ldg + c; });
@@ -450,7 +463,7 @@ finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
             for (int t0 = 0; t0 < nt; t0 += 16) {
                 double v[16];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) v[u] = src[min(t0 + u, nt - 1) * stride];
+                for (int u = 0; u < 16; ++u) v[u] = ONE_LAUNCH ? __ldcg(src + min(t0 + u, nt - 1) * stride) : src[min(t0 + u, nt - 1) * stride];
 #pragma unroll
                 for (int u = 0; u < 16; ++u)
                     if (t0 + u < nt) s += v[u];
@@ -465,7 +478,7 @@ finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
         red[(long long)(1 + NG) * ldg + c] = bad ? 1.0 : 0.0;
         return;
     }
-    flags[c] = bad ? 1 : 0;  // (mode 2: the flag now reflects every rank's shard)
+    if (!ONE_LAUNCH) flags[c] = bad ? 1 : 0;  // (mode 2: the flag now reflects every rank's shard)
     for (int h = 0; h < H; ++h) {
         const jbugs_global& g = G.g[h];
         if (G.fast[h] == JBUGS_FAM_NORMAL + 1) {  // dnorm(m, t), literals: cst = (log t - log 2 pi) / 2
@@ -501,12 +514,62 @@ finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__
         lp += t.lj;
         if (want_grad) grad[g.theta_idx * ld + c] = ga[h] * t.dxdy + t.dljdy;
     }
-    if (bad) flags[c] = 1;
+    if (ONE_LAUNCH) flags[c] = 0;  // (the one-launch kernel owns its flag row: clean for the next evaluation)
+    else if (bad) flags[c] = 1;
     logp_out[c] = bad ? -dev_inf() : lp;
-    if (status_out) status_out[c] = bad ? JBUGS_CHAIN_DOMAIN : JBUGS_CHAIN_OK;
+    if (status_out) status_out[c] = bad ? CHAIN_DOMAIN : CHAIN_OK;
     if (bad) atomicOr(any_bad, 1);
     if (bad && want_grad)  // DomainError -> NaN gradient (logdensityproblems.jl:226-229); every plate kernel has finished
         for (long long d = 0; d < F.poison_rows; ++d) grad[d * ld + c] = dev_nan();
+}
+
+// ------------------------------------------------------------------------------------------------
+// One launch per evaluation for small single-plate models (BASELINE config 5: a few hundred nodes x thousands of
+// chains, latency-bound).  Three dependent launches -- prologue, plate, finalize -- cost more in launch latency and
+// drain/fill gaps than the arithmetic itself.  Here every CTA (chain block x group tile) recomputes the prologue for
+// its own chains, evaluates its tile, publishes its partials and takes a ticket per chain block; the CTA that draws the
+// last ticket adds the tiles in ascending order (the same fixed order as finalize_kernel) and finishes the chains.
+struct FusedParams {
+    GlobalsParams G;
+    GTapeParams TP;
+    FinalParams F;
+    PlateParams P;
+};
+
+template <class S, int BLK>
+__global__ void __launch_bounds__(BLK, (S::MIN_BLOCKS * (128 / BLK) > 24 ? 24 : S::MIN_BLOCKS * (128 / BLK)))
+fused_small_kernel(const __grid_constant__ FusedParams Q, const double* __restrict__ theta, double* __restrict__ grad,
+                   long long ld, long long C, double* __restrict__ gvals, long long ldg, double* __restrict__ partial,
+                   int* __restrict__ flags, double* __restrict__ logp_out, int* __restrict__ status_out,
+                   int* __restrict__ any_bad, int want_grad, unsigned* __restrict__ tickets) {
+    pdl_wait();  // theta may come from the kernel before (a leapfrog update)
+    const long long c = (long long)blockIdx.x * BLK + threadIdx.x;
+    if (c < C) prologue_body<true>(Q.G, Q.TP, theta, ld, c, gvals, ldg, flags);   // this thread reads back its own writes only
+    plate_body<S, BLK, false, true>(Q.P, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad, blockIdx.y);
+    __shared__ unsigned last;
+    __threadfence();  // partials (and a raised flag) are visible device-wide before the ticket is taken
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(tickets + blockIdx.x, 1u) == gridDim.y - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;  // ready for the next evaluation
+    if (c < C)
+        finalize_body<true>(Q.G, Q.TP, Q.F, theta, grad, ld, c, gvals, ldg, partial, flags, logp_out, status_out, any_bad, want_grad, 0, nullptr);
+}
+
+#ifdef JBUGS_HOST_TU
+__global__ void __launch_bounds__(BLOCK)
+finalize_kernel(const __grid_constant__ GlobalsParams G, const __grid_constant__ GTapeParams TP,
+                const __grid_constant__ FinalParams F, const double* __restrict__ theta, double* __restrict__ grad,
+                long long ld, long long C, const double* __restrict__ gvals, long long ldg,
+                const double* __restrict__ partial, int* __restrict__ flags, double* __restrict__ logp_out,
+                int* __restrict__ status_out, int* __restrict__ any_bad, int want_grad, int mode,
+                double* __restrict__ red) {
+    pdl_wait();  // partials, gvals and flags come from the kernels before this one
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    finalize_body<false>(G, TP, F, theta, grad, ld, c, gvals, ldg, partial, flags, logp_out, status_out, any_bad, want_grad, mode, red);
 }
 
 // First level of the fixed-order tile reduction, used when a plate has many tiles: super-tile r adds the tiles

@@ -36,4 +36,30 @@ static cudaError_t launch_plate_blk(JBUGS_LAUNCH_PARAMS) {
     return cudaGetLastError();
 }
 
+// one-launch evaluation of a small single-plate model (fused_small_kernel)
+template <class S, int BLK>
+static cudaError_t launch_fused_blk(JBUGS_FUSED_PARAMS) {
+    static size_t opted_in[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& have = opted_in[dev & 63];
+    if (smem > 48 * 1024 && smem > have) {
+        cudaError_t e = cudaFuncSetAttribute(fused_small_kernel<S, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        have = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((C + BLK - 1) / BLK), (unsigned)n_tiles);
+    cfg.blockDim = dim3(BLK);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, fused_small_kernel<S, BLK>, fq, theta, grad, ld, C, gvals, ldg, partial, flags, logp, status, any_bad,
+                              want_grad, tickets);
+}
+
 }  // namespace jbugs

@@ -608,11 +608,13 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
 // cp.async.bulk + mbarrier where aligned (a separate instantiation: the cp.async-only kernel carries none of it)
 // GRAD = false: a forward-only instantiation for `logdensity` without the gradient (the adjoint arithmetic is dead
 // code then and the kernel reads theta only); built for the large-plate specs, selected when want_grad == 0
-template <class S, int BLK, bool TMA, bool GRAD = true>
-__global__ void __launch_bounds__(BLK, (S::MIN_BLOCKS * (128 / BLK) > 24 ? 24 : S::MIN_BLOCKS * (128 / BLK)))
-plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ theta, double* __restrict__ grad,
-             long long ld, long long C, const double* __restrict__ gvals, long long ldg,
-             double* __restrict__ partial, int* __restrict__ flags, int want_grad) {
+// the body of plate_kernel: one CTA = BLK chains x tile `tile` of the plate's groups (also the middle part of
+// fused_small_kernel, jbugs_kernels.cuh)
+template <class S, int BLK, bool TMA, bool GRAD>
+__device__ __forceinline__ void plate_body(const PlateParams& P, const double* __restrict__ theta, double* __restrict__ grad,
+                                           long long ld, long long C, const double* __restrict__ gvals, long long ldg,
+                                           double* __restrict__ partial, int* __restrict__ flags, int want_grad,
+                                           const long long tile) {
     extern __shared__ double smem[];
     pdl_launch_dependents();  // finalize (or the next plate) may be scheduled; it waits for this grid before reading
     const S sp(P.sh);
@@ -621,7 +623,6 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
     const long long c_raw = (long long)blockIdx.x * BLK + tid;
     const bool active = c_raw < C;           // inactive lanes still take part in staging and barriers
     const long long c = active ? c_raw : C - 1;
-    const long long tile = blockIdx.y;
     const long long ib = V.i0 + tile * V.tile;
     const long long ie = (ib + V.tile < V.i1) ? ib + V.tile : V.i1;
     constexpr int U = S::UNROLL;
@@ -781,6 +782,14 @@ plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ t
         for (int k = 0; k < MAX_GREF; ++k)
             if (k < sp.n_gref()) out[(long long)(1 + k) * ldg] = st.ga[k];
     if (bad) atomicOr(flags + c, 1);
+}
+
+template <class S, int BLK, bool TMA, bool GRAD = true>
+__global__ void __launch_bounds__(BLK, (S::MIN_BLOCKS * (128 / BLK) > 24 ? 24 : S::MIN_BLOCKS * (128 / BLK)))
+plate_kernel(const __grid_constant__ PlateParams P, const double* __restrict__ theta, double* __restrict__ grad,
+             long long ld, long long C, const double* __restrict__ gvals, long long ldg,
+             double* __restrict__ partial, int* __restrict__ flags, int want_grad) {
+    plate_body<S, BLK, TMA, GRAD>(P, theta, grad, ld, C, gvals, ldg, partial, flags, want_grad, blockIdx.y);
 }
 
 }  // namespace jbugs

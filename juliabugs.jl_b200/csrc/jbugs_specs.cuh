@@ -24,6 +24,18 @@ static inline int plate_block(long long C) { return C <= 32 ? 32 : (C <= 64 ? 64
 
 typedef cudaError_t (*plate_launch_fn)(JBUGS_LAUNCH_PARAMS);
 
+// one-launch evaluation of a small single-plate model (fused_small_kernel)
+#define JBUGS_FUSED_PARAMS                                                                                             \
+    long long n_tiles, size_t smem, cudaStream_t st, const FusedParams &fq, const double *theta, double *grad, long long ld, \
+        long long C, double *gvals, long long ldg, double *partial, int *flags, double *logp, int *status, int *any_bad,  \
+        int want_grad, unsigned *tickets, int pdl
+#define JBUGS_FUSED_ARGS n_tiles, smem, st, fq, theta, grad, ld, C, gvals, ldg, partial, flags, logp, status, any_bad, want_grad, tickets, pdl
+typedef cudaError_t (*fused_launch_fn)(JBUGS_FUSED_PARAMS);
+cudaError_t launch_fused_dyn(JBUGS_FUSED_PARAMS);
+cudaError_t launch_fused_pumps(JBUGS_FUSED_PARAMS);
+cudaError_t launch_fused_epil(JBUGS_FUSED_PARAMS);
+cudaError_t launch_fused_epil_t4(JBUGS_FUSED_PARAMS);
+
 // defined in spec_dyn.cu / spec_rats.cu / spec_glm.cu / spec_epil.cu
 cudaError_t launch_dyn(JBUGS_LAUNCH_PARAMS);
 cudaError_t launch_x(JBUGS_LAUNCH_PARAMS);  // expression-tape interpreter (XSpec)
@@ -40,6 +52,7 @@ struct SpecEntry {
     plate_launch_fn launch;
     bool (*matches)(const PlateShape&, long long T);
     int fused;  // FUSED_* code: tells the host whether the plate needs obs_const
+    fused_launch_fn one_launch;  // whole evaluation of a small single-plate model in one kernel (nullptr: not built for this spec)
 };
 
 #include "jbugs_static_specs.inc"
@@ -48,15 +61,15 @@ struct SpecEntry {
 static bool match_never(const PlateShape&, long long) { return false; }
 
 static const SpecEntry g_specs[] = {
-    {"dynamic", &launch_dyn, &match_never, FUSED_NONE},
-    {"rats_normal_identity_T5", &launch_rats_t5, &RatsDesc<5>::matches, RatsDesc<5>::FUSED},
-    {"rats_normal_identity", &launch_rats, &RatsDesc<0>::matches, RatsDesc<0>::FUSED},
-    {"seeds_binomial_logit", &launch_seeds, &SeedsDesc::matches, SeedsDesc::FUSED},
-    {"surgical_binomial_logit", &launch_surgical, &SurgicalDesc::matches, SurgicalDesc::FUSED},
-    {"epil_poisson_log_T4", &launch_epil_t4, &EpilDesc<4>::matches, EpilDesc<4>::FUSED},
-    {"epil_poisson_log", &launch_epil, &EpilDesc<0>::matches, EpilDesc<0>::FUSED},
-    {"pumps_poisson_gamma", &launch_pumps, &PumpsDesc::matches, PumpsDesc::FUSED},
-    {"expression_tape", &launch_x, &match_never, FUSED_NONE},
+    {"dynamic", &launch_dyn, &match_never, FUSED_NONE, &launch_fused_dyn},
+    {"rats_normal_identity_T5", &launch_rats_t5, &RatsDesc<5>::matches, RatsDesc<5>::FUSED, nullptr},
+    {"rats_normal_identity", &launch_rats, &RatsDesc<0>::matches, RatsDesc<0>::FUSED, nullptr},
+    {"seeds_binomial_logit", &launch_seeds, &SeedsDesc::matches, SeedsDesc::FUSED, nullptr},
+    {"surgical_binomial_logit", &launch_surgical, &SurgicalDesc::matches, SurgicalDesc::FUSED, nullptr},
+    {"epil_poisson_log_T4", &launch_epil_t4, &EpilDesc<4>::matches, EpilDesc<4>::FUSED, &launch_fused_epil_t4},
+    {"epil_poisson_log", &launch_epil, &EpilDesc<0>::matches, EpilDesc<0>::FUSED, &launch_fused_epil},
+    {"pumps_poisson_gamma", &launch_pumps, &PumpsDesc::matches, PumpsDesc::FUSED, &launch_fused_pumps},
+    {"expression_tape", &launch_x, &match_never, FUSED_NONE, nullptr},
 };
 static const int g_num_specs = (int)(sizeof(g_specs) / sizeof(g_specs[0]));
 static const int g_xspec = g_num_specs - 1;  // the tape interpreter: selected by the plate kind, never by shape

@@ -39,4 +39,20 @@ JB_DISPATCH(launch_surgical)
 JB_DISPATCH(launch_pumps)
 JB_DISPATCH(launch_epil)
 JB_DISPATCH(launch_epil_t4)
+// one-launch kernels for small single-plate models
+#define JB_DISPATCH_FUSED(name)                                  \
+    cudaError_t name##_32(JBUGS_FUSED_PARAMS);                   \
+    cudaError_t name##_64(JBUGS_FUSED_PARAMS);                   \
+    cudaError_t name##_128(JBUGS_FUSED_PARAMS);                  \
+    cudaError_t name(JBUGS_FUSED_PARAMS) {                       \
+        switch (plate_block(C)) {                                \
+        case 32: return name##_32(JBUGS_FUSED_ARGS);             \
+        case 64: return name##_64(JBUGS_FUSED_ARGS);             \
+        default: return name##_128(JBUGS_FUSED_ARGS);            \
+        }                                                        \
+    }
+JB_DISPATCH_FUSED(launch_fused_dyn)
+JB_DISPATCH_FUSED(launch_fused_pumps)
+JB_DISPATCH_FUSED(launch_fused_epil)
+JB_DISPATCH_FUSED(launch_fused_epil_t4)
 }  // namespace jbugs

@@ -6,5 +6,9 @@ namespace jbugs {
 #ifndef JB_GRAD
 #define JB_GRAD true
 #endif
+#ifdef JB_ONE_LAUNCH  // the one-launch kernel for small single-plate models instead of the plate kernel
+cudaError_t JB_NAME(JBUGS_FUSED_PARAMS) { return launch_fused_blk<JB_SPEC, JB_BLK>(JBUGS_FUSED_ARGS); }
+#else
 cudaError_t JB_NAME(JBUGS_LAUNCH_PARAMS) { return launch_plate_blk<JB_SPEC, JB_BLK, JB_TMA, JB_GRAD>(JBUGS_LAUNCH_ARGS); }
+#endif
 }  // namespace jbugs
