@@ -538,8 +538,11 @@ def e2e(ctx, args, cp, theta, grad, lp_host, n_obs, D, C, K):
         ld = Ce if lay == 0 else D
 
         def e2e_step():
+            # asynchronous host calls: the library's copy-in / kernels / copy-out pipeline runs on from one slab into the
+            # next (no fill / drain bubble per call); one synchronisation when the whole batch is back in host memory
             for _ in range(n_slabs):
-                cp.eval_raw(th_p, ld, Ce, lay, lp_p, g_p, st_p, True, 0, stream)
+                cp.eval_raw(th_p, ld, Ce, lay, lp_p, g_p, st_p, True, 1, stream)
+            cp.synchronize(stream)
 
         e2e_step()
         reps = max(2, min(K, 3))
@@ -570,7 +573,7 @@ def e2e(ctx, args, cp, theta, grad, lp_host, n_obs, D, C, K):
            "param_fast": res["param_fast"], "best_layout": best,
            "numa": ctx.numa, "pcie_ceiling": ceiling,
            "sample": f"all {Ce * n_slabs} chains per GPU in {n_slabs} slabs of {Ce} through jbugs_eval_batch with pinned "
-                     "host buffers (theta write-combined), H2D and D2H inside the timed region; `value` is the "
+                     "host buffers (theta write-combined; JBUGS_EVAL_ASYNC calls, one jbugs_plan_synchronize per step), H2D and D2H inside the timed region; `value` is the "
                      "chain_fast host layout, `param_fast` = a Julia Matrix(D, C) incl. the two on-device transposes"}
     for p in (th_p, g_p, lp_p, st_p):
         jcuda.host_free(p)

@@ -100,7 +100,12 @@ int jbugs_plan_set_dense_shard(jbugs_plan* plan, int64_t i0, int64_t i1);
  *   grad   : same layout/ld as theta, out (ignored when want_grad == 0; may be NULL then)
  *   status : C int32 out (jbugs_chain_status), may be NULL
  *   stream : cudaStream_t (NULL = default stream).  The call returns after the stream has been
- *            synchronized unless flags & JBUGS_EVAL_ASYNC and every buffer is a device pointer.
+ *            synchronized unless flags & JBUGS_EVAL_ASYNC.  With device buffers an ASYNC call only enqueues work
+ *            on `stream`.  With host buffers an ASYNC call enqueues the whole staged pipeline (copy-in, kernels,
+ *            copy-out on the library's streams) and returns: consecutive ASYNC calls run as ONE pipeline, the
+ *            copy-in of a call overlapping the kernels and copy-out of the one before; the host buffers must
+ *            be ready when the call is made, stay untouched until jbugs_plan_synchronize, and hold the results
+ *            after it.
  *            The launch sequence contains no host synchronisation once the plan is warm, so an
  *            ASYNC call on a non-default stream can be captured into a CUDA graph by the caller
  *            (the on-device sampler does exactly that, jbugs_hmc_run). */
@@ -108,6 +113,9 @@ int jbugs_plan_set_dense_shard(jbugs_plan* plan, int64_t i0, int64_t i1);
 int jbugs_eval_batch(jbugs_plan* plan, const double* theta, int64_t ld, int64_t C, int layout,
                      double* logp, double* grad, int32_t* status, int want_grad, int flags,
                      void* stream);
+
+/* Waits for everything earlier (ASYNC) evaluations of this plan put on `stream` and on the library's copy streams. */
+int jbugs_plan_synchronize(jbugs_plan* plan, void* stream);
 
 /* Replaces: the `(logprior, loglikelihood, tempered_logjoint)` triple of `evaluate_with_values!!`
  * (src/model/evaluation.jl:116, 269-274; `AbstractPPL.evaluate!!`, src/model/abstractppl.jl:989-1005), for C chains:

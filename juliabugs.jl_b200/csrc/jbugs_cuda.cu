@@ -153,6 +153,7 @@ struct jbugs_plan_s {
         cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
     } slot[2];
     long long slot_C = 0;
+    long long chunk_seq = 0;  // staged chunks issued so far (slots alternate across calls)
     bool slot_t = false;
     cudaStream_t st_in = nullptr, st_out = nullptr;
     // library-owned batch
@@ -1411,7 +1412,19 @@ extern "C" int jbugs_eval_batch(jbugs_plan* p, const double* theta, int64_t ld, 
         return JBUGS_OK;
     }
     // host buffers and/or PARAM_FAST: pipelined through library staging in chunks of chains
-    return eval_staged(p, theta, ld, C, layout, logp, grad, status, want_grad, st);
+    return eval_staged(p, theta, ld, C, layout, logp, grad, status, want_grad, st, (flags & JBUGS_EVAL_ASYNC) != 0);
+}
+
+extern "C" int jbugs_plan_synchronize(jbugs_plan* p, void* stream) {
+    if (!p) return fail(JBUGS_ERR_INVALID, "null plan");
+    int rc = set_device(p);
+    if (rc) return rc;
+    if (p->st_out) {
+        CU(cudaStreamSynchronize(p->st_in));
+        CU(cudaStreamSynchronize(p->st_out));
+    }
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return JBUGS_OK;
 }
 
 // ---- logprior / loglikelihood / tempered log joint (evaluation.jl:116, 269-274) -------------------------------------

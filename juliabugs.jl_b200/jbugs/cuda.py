@@ -27,7 +27,7 @@ SYMBOLS = [
     "jbugs_last_timing", "jbugs_hmc_create", "jbugs_hmc_destroy", "jbugs_hmc_init", "jbugs_hmc_run",
     "jbugs_hmc_get_state", "jbugs_hmc_run_nuts", "jbugs_hmc_nuts_stats", "jbugs_plan_specialize", "jbugs_hmc_draw_momentum", "jbugs_timing_history", "jbugs_host_alloc_ex",
     "jbugs_bind_host_to_device", "jbugs_fp64_peak", "jbugs_eval_batch_tempered", "jbugs_jit_last_compile_seconds", "jbugs_plan_specialize_async",
-    "jbugs_gq_create", "jbugs_gq_destroy", "jbugs_gq_run", "jbugs_gq_launch_count",
+    "jbugs_gq_create", "jbugs_gq_destroy", "jbugs_gq_run", "jbugs_gq_launch_count", "jbugs_plan_synchronize",
 ]
 
 
@@ -62,6 +62,7 @@ def load():
     L.jbugs_plan_specialize.argtypes = [c.c_void_p, c.c_char_p]
     L.jbugs_jit_last_compile_seconds.restype = c.c_double
     L.jbugs_plan_specialize_async.argtypes = [c.c_void_p, c.c_char_p]
+    L.jbugs_plan_synchronize.argtypes = [c.c_void_p, c.c_void_p]
     L.jbugs_eval_batch.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_void_p, c.c_void_p,
                                    c.c_void_p, c.c_int, c.c_int, c.c_void_p]
     L.jbugs_eval_batch_tempered.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_double, c.c_void_p,
@@ -152,6 +153,10 @@ class CudaPlan:
         tapes included (NVRTC in-process, cubins cached in a per-user directory; "none" disables the cache); without it
         those plates run the interpreter instantiations."""
         _check(self.L.jbugs_plan_specialize(self.h, cache_dir.encode() if cache_dir else None))
+
+    def synchronize(self, stream=None):
+        """wait for earlier asynchronous evaluations (flags = JBUGS_EVAL_ASYNC) of this plan"""
+        _check(self.L.jbugs_plan_synchronize(self.h, stream))
 
     def specialize_async(self, cache_dir: Optional[str] = None):
         """`specialize` without blocking: the compiler runs on a worker thread, evaluations switch over when it is done"""
