@@ -84,7 +84,8 @@ enum jbugs_family {
     JBUGS_FAM_GEOMETRIC = 16,  /* dgeom(p)         :500-502 Geometric(p): failures before the first success */
     JBUGS_FAM_CATEGORICAL = 17,/* dcat(p[1:K])     :472-474 Categorical(p): the plate's argument is p[y], the
                                   probability of the observed category (log density = log p[y]) */
-    JBUGS_FAM_COUNT = 18
+    JBUGS_FAM_BETABIN = 18,    /* dbetabin(a, b, n) :530-532 BetaBinomial(n, a, b); n a constant */
+    JBUGS_FAM_COUNT = 19
 };
 
 /* ---- constrained <-> unconstrained maps (Bijectors, call site evaluation.jl:243-257) ------- */

@@ -314,7 +314,7 @@ static int build_locals_and_finish(jbugs_plan* p, int k, std::vector<int>& gref,
         }
         ls.mu_zero = (L[l].args[0].kind == JBUGS_ARG_CONST && L[l].args[0].value == 0.0) ? 1 : 0;
         lv.args[2].value = L[l].args[2].kind == JBUGS_ARG_ONE ? 1.0 : L[l].args[2].value;  // dt's constant degrees of freedom
-        if (L[l].family == JBUGS_FAM_T && L[l].args[2].kind != JBUGS_ARG_CONST && L[l].args[2].kind != JBUGS_ARG_ONE)
+        if ((L[l].family == JBUGS_FAM_T || L[l].family == JBUGS_FAM_BETABIN) && L[l].args[2].kind != JBUGS_ARG_CONST && L[l].args[2].kind != JBUGS_ARG_ONE)
             return fail(JBUGS_ERR_UNSUPPORTED, "plate %d local %d: the degrees of freedom of dt must be a constant", k, l);
     }
     if ((int)gref.size() > MAX_GREF) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d references more than %d global values", k, MAX_GREF);
@@ -423,7 +423,7 @@ static int build_xplate(jbugs_plan* p, int k) {
     }
     V.aux[2].value = pl.aux[2].kind == JBUGS_ARG_ONE ? 1.0 : pl.aux[2].value;
     if (pl.aux[2].kind == JBUGS_ARG_DATA_I || pl.aux[2].kind == JBUGS_ARG_DATA_IJ) {
-        if (pl.family == JBUGS_FAM_T) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: dt observations cannot carry a weight", k);
+        if (pl.family == JBUGS_FAM_T || pl.family == JBUGS_FAM_BETABIN) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: dt / dbetabin observations cannot carry a weight", k);
         if ((rc = resolve_arg(p, pl.aux[2], sh.aux[2], V.aux[2], gref, (int)pl.n_locals, sb))) return rc;
         if ((rc = check_len(p, pl.aux[2], pl.N, pl.T, "weight"))) return rc;
     }
@@ -492,8 +492,8 @@ static int build_plate(jbugs_plan* p, int k) {
         // aux[2]: the constant third argument of a three-argument family (dt), or the optional 0/1 observation weight of
         // a gathered (padded) plate
         V.aux[2].value = pl.aux[2].kind == JBUGS_ARG_ONE ? 1.0 : pl.aux[2].value;
-        if (pl.family == JBUGS_FAM_T && pl.aux[2].kind != JBUGS_ARG_CONST && pl.aux[2].kind != JBUGS_ARG_ONE)
-            return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: the degrees of freedom of dt must be a constant", k);
+        if ((pl.family == JBUGS_FAM_T || pl.family == JBUGS_FAM_BETABIN) && pl.aux[2].kind != JBUGS_ARG_CONST && pl.aux[2].kind != JBUGS_ARG_ONE)
+            return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: the third argument of dt / dbetabin must be a constant", k);
         if (pl.aux[2].kind == JBUGS_ARG_DATA_I || pl.aux[2].kind == JBUGS_ARG_DATA_IJ) {
             if ((rc = resolve_arg(p, pl.aux[2], sh.aux[2], V.aux[2], gref, (int)pl.n_locals, sb))) return rc;
             if ((rc = check_len(p, pl.aux[2], pl.N, pl.T, "weight"))) return rc;

@@ -224,6 +224,16 @@ __device__ inline bool fam_eval(int fam, double x, double a0, double a1, FamOut&
         o.da0 = 1.0 / a0;
         return !(a0 >= 0.0 && a0 <= 1.0 + 1e-8);
     }
+    case JBUGS_FAM_BETABIN: {  // BetaBinomial(n = a2, alpha = a0, beta = a1)
+        const double n = a2, m = n - x;
+        const bool out = (x < 0.0 || x > n || x != floor(x));
+        const double xs = out ? 0.0 : x, ms = out ? n : m;
+        o.lp = out ? -dev_inf() : (-log1p(n) - logbeta(xs + 1.0, ms + 1.0) + logbeta(xs + a0, ms + a1) - logbeta(a0, a1));
+        const double dsum = digamma(a0 + a1) - digamma(n + a0 + a1);
+        o.da0 = digamma(xs + a0) - digamma(a0) + dsum;
+        o.da1 = digamma(ms + a1) - digamma(a1) + dsum;
+        return !(n >= 0.0) || !(a0 >= 0.0) || !(a1 >= 0.0);
+    }
     default: return false;  // FLAT
     }
 }

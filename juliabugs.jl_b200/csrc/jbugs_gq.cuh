@@ -181,6 +181,7 @@ __device__ double gq_sample(unsigned fam, double a0, double a1, double a2, GqRng
     case JBUGS_FAM_NEGBIN: return g.poisson(g.gamma(a1) * (1.0 - a0) / a0);  // gamma-Poisson mixture: NegativeBinomial(r, p)
     case JBUGS_FAM_CHISQ: return 2.0 * g.gamma(0.5 * a0);
     case JBUGS_FAM_T: return a0 + g.normal() / sqrt(2.0 * g.gamma(0.5 * a2) / a2) / sqrt(a1);
+    case JBUGS_FAM_BETABIN: { const double x = g.gamma(a0), y = g.gamma(a1); return g.binomial(a2, x / (x + y)); }
     case JBUGS_FAM_GEOMETRIC: return a0 >= 1.0 ? 0.0 : floor(log(g.uniform()) / log1p(-a0));  // failures before the first success
     default: return dev_nan();
     }

@@ -103,6 +103,8 @@ def _sample(rng, fn, args, shape):
         return a[0] + rng.standard_t(a[2]) / np.sqrt(a[1])
     if fn == "dnegbin":
         return rng.negative_binomial(a[1], a[0]).astype(np.float64)
+    if fn == "dbetabin":
+        return rng.binomial(a[2].astype(np.int64), rng.beta(a[0], a[1])).astype(np.float64)
     if fn == "dgeom":
         return (rng.geometric(a[0]) - 1).astype(np.float64)   # failures before the first success
     raise LoweringError(f"forward sampling of {fn} is not provided")

@@ -902,8 +902,8 @@ class Lowering:
         fam = P.FAMILY_OF[call.fn]
         if len(call.args) != P.FAMILY_NARGS[fam]:
             raise LoweringError(f"{call.fn} expects {P.FAMILY_NARGS[fam]} arguments")
-        if fam == P.FAM_T and not (self._is_data(call.args[2], ()) and np.ndim(self.de.ev(call.args[2], {})) == 0):
-            raise LoweringError("the degrees of freedom of dt must be a constant")
+        if fam in (P.FAM_T, P.FAM_BETABIN) and not (self._is_data(call.args[2], ()) and np.ndim(self.de.ev(call.args[2], {})) == 0):
+            raise LoweringError("the third argument of dt (degrees of freedom) / dbetabin (n) must be a constant")
         return fam
 
     def _build_plan(self):
@@ -1099,7 +1099,7 @@ class Lowering:
         """partially observed statement: missing cells carry weight 0 and a harmless placeholder observation"""
         if s.obs_mask is None:
             return
-        if plate.family == P.FAM_T:
+        if plate.family in (P.FAM_T, P.FAM_BETABIN):
             raise LoweringError("dt observations with missing cells are not supported")
         m = np.asarray(s.obs_mask, dtype=np.float64)
         if m.ndim == 1:
@@ -1188,7 +1188,7 @@ class Lowering:
                     aux.append(P.Arg.xval(self._tape(e, s, plate, tape, memo, used_locals)))
         finally:
             self.de.lenient = False
-        if fam == P.FAM_T and aux[2].kind != P.ARG_CONST:
+        if fam in (P.FAM_T, P.FAM_BETABIN) and aux[2].kind != P.ARG_CONST:
             raise LoweringError("the degrees of freedom of dt must be a constant")
         if not tape:
             raise LoweringError("internal: an expression plate without a tape")
@@ -1391,8 +1391,8 @@ class Lowering:
             else:
                 aux.append(self._scalar_arg(a, s.loop_vars, s.shape, s.loop_vars))
         plate.aux = aux
-        if not np.all(w == 1.0) and fam == P.FAM_T:
-            raise LoweringError("dt observations in a padded (data-indexed) plate are not supported")
+        if not np.all(w == 1.0) and fam in (P.FAM_T, P.FAM_BETABIN):
+            raise LoweringError("dt / dbetabin observations in a padded (data-indexed) plate are not supported")
         if not np.all(w == 1.0):
             plate.weight = P.Arg(P.ARG_DATA_IJ, self._slot(key + "|w", w.ravel(order="F"), rank=2, dim0=G))
         for ref, cov in lin.terms.items():

@@ -20,19 +20,20 @@ ARG_CONST, ARG_GVAL, ARG_LOCAL, ARG_DATA_I, ARG_DATA_J, ARG_DATA_IJ, ARG_ONE, AR
 # enum jbugs_family
 (FAM_NORMAL, FAM_GAMMA, FAM_EXPONENTIAL, FAM_UNIFORM, FAM_BETA, FAM_LOGNORMAL, FAM_BERNOULLI,
  FAM_BINOMIAL, FAM_POISSON, FAM_FLAT, FAM_LOGISTIC, FAM_LAPLACE, FAM_WEIBULL, FAM_NEGBIN, FAM_CHISQ, FAM_T,
- FAM_GEOMETRIC, FAM_CATEGORICAL) = range(18)
+ FAM_GEOMETRIC, FAM_CATEGORICAL, FAM_BETABIN) = range(19)
 FAMILY_OF = {
     "dnorm": FAM_NORMAL, "dgamma": FAM_GAMMA, "dexp": FAM_EXPONENTIAL, "dunif": FAM_UNIFORM,
     "dbeta": FAM_BETA, "dlnorm": FAM_LOGNORMAL, "dbern": FAM_BERNOULLI, "dbin": FAM_BINOMIAL,
     "dpois": FAM_POISSON, "dflat": FAM_FLAT, "dlogis": FAM_LOGISTIC, "ddexp": FAM_LAPLACE, "dweib": FAM_WEIBULL,
     "dnegbin": FAM_NEGBIN, "dchisqr": FAM_CHISQ, "dt": FAM_T, "dgeom": FAM_GEOMETRIC, "dcat": FAM_CATEGORICAL,
+    "dbetabin": FAM_BETABIN,
 }
 FAMILY_NAME = {v: k for k, v in FAMILY_OF.items()}
 FAMILY_NARGS = {FAM_NORMAL: 2, FAM_GAMMA: 2, FAM_EXPONENTIAL: 1, FAM_UNIFORM: 2, FAM_BETA: 2,
                 FAM_LOGNORMAL: 2, FAM_BERNOULLI: 1, FAM_BINOMIAL: 2, FAM_POISSON: 1, FAM_FLAT: 0,
                 FAM_LOGISTIC: 2, FAM_LAPLACE: 2, FAM_WEIBULL: 2, FAM_NEGBIN: 2, FAM_CHISQ: 1, FAM_T: 3,
-                FAM_GEOMETRIC: 1, FAM_CATEGORICAL: 1}
-DISCRETE = {FAM_BERNOULLI, FAM_BINOMIAL, FAM_POISSON, FAM_NEGBIN, FAM_GEOMETRIC, FAM_CATEGORICAL}
+                FAM_GEOMETRIC: 1, FAM_CATEGORICAL: 1, FAM_BETABIN: 3}
+DISCRETE = {FAM_BERNOULLI, FAM_BINOMIAL, FAM_POISSON, FAM_NEGBIN, FAM_GEOMETRIC, FAM_CATEGORICAL, FAM_BETABIN}
 # enum jbugs_transform
 TR_IDENTITY, TR_LOG, TR_LOGIT, TR_UPPER = range(4)
 # enum jbugs_op

@@ -32,12 +32,13 @@ fail(msg) = throw(LoweringError(msg))
 const ARG_CONST, ARG_GVAL, ARG_LOCAL, ARG_DATA_I, ARG_DATA_J, ARG_DATA_IJ, ARG_ONE, ARG_XVAL, ARG_GVEC_J = UInt32.(0:8)
 const FAMILY_OF = Dict(:dnorm => 0, :dgamma => 1, :dexp => 2, :dunif => 3, :dbeta => 4, :dlnorm => 5, :dbern => 6,
                        :dbin => 7, :dpois => 8, :dflat => 9, :dlogis => 10, :ddexp => 11, :dweib => 12, :dnegbin => 13,
-                       :dchisqr => 14, :dt => 15, :dgeom => 16, :dcat => 17)
+                       :dchisqr => 14, :dt => 15, :dgeom => 16, :dcat => 17, :dbetabin => 18)
 const FAMILY_NARGS = Dict(0 => 2, 1 => 2, 2 => 1, 3 => 2, 4 => 2, 5 => 2, 6 => 1, 7 => 2, 8 => 1, 9 => 0, 10 => 2, 11 => 2,
-                          12 => 2, 13 => 2, 14 => 1, 15 => 3, 16 => 1, 17 => 1)
+                          12 => 2, 13 => 2, 14 => 1, 15 => 3, 16 => 1, 17 => 1, 18 => 3)
 const FAM_GAMMA, FAM_EXPONENTIAL, FAM_UNIFORM, FAM_BETA, FAM_LOGNORMAL = 1, 2, 3, 4, 5
 const FAM_BERNOULLI, FAM_BINOMIAL, FAM_FLAT, FAM_WEIBULL, FAM_CHISQ, FAM_T, FAM_CATEGORICAL = 6, 7, 9, 12, 14, 15, 17
-const DISCRETE = Set([6, 7, 8, 13, 16, 17])
+const FAM_BETABIN = 18   # dbetabin(a, b, n): the third argument (n) is a constant, like dt's degrees of freedom
+const DISCRETE = Set([6, 7, 8, 13, 16, 17, 18])
 const TR_IDENTITY, TR_LOG, TR_LOGIT = 0, 1, 2
 const OP_IDENTITY, OP_EXP, OP_LOGISTIC, OP_CEXPEXP, OP_PHI, OP_LOG, OP_SQRT, OP_NEG = 0:7
 const OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_LEAF, OP_SELECT = 16, 17, 18, 19, 20, 32, 33
@@ -809,7 +810,7 @@ end
 
 function apply_obs_mask!(lw::Lowering, plate::Plate, s::Stmt)
     s.obs_mask === nothing && return
-    plate.family == FAM_T && fail("dt observations with missing cells are not supported")
+    (plate.family == FAM_T || plate.family == FAM_BETABIN) && fail("dt observations with missing cells are not supported")
     m = Float64.(s.obs_mask)
     plate.weight = ndims(m) == 1 ? Arg(ARG_DATA_I, slot!(lw, "obs_mask|$(name_of(s))", m)) :
                    Arg(ARG_DATA_IJ, slot!(lw, "obs_mask|$(name_of(s))", m; rank=2, dim0=size(m, 1)))
@@ -940,7 +941,7 @@ function build_xplate!(lw::Lowering, s::Stmt, fam, used::Set{Int})
     finally
         lw.de.lenient = false
     end
-    (fam == FAM_T && plate.aux[3].kind != ARG_CONST) && fail("the degrees of freedom of dt must be a constant")
+    ((fam == FAM_T || fam == FAM_BETABIN) && plate.aux[3].kind != ARG_CONST) && fail("the degrees of freedom of dt must be a constant")
     isempty(tape) && fail("internal: an expression plate without a tape")
     plate.xops = tape
     apply_obs_mask!(lw, plate, s)
@@ -1088,7 +1089,7 @@ function build_gathered_plate!(lw::Lowering, s::Stmt, fam, eta_arg, link, args, 
             push!(plate.aux, scalar_arg(lw, a, lvs, shape_of(s)))
         end
     end
-    (!all(w .== 1.0) && fam == FAM_T) && fail("dt observations in a padded (data-indexed) plate are not supported")
+    (!all(w .== 1.0) && (fam == FAM_T || fam == FAM_BETABIN)) && fail("dt / dbetabin observations in a padded (data-indexed) plate are not supported")
     all(w .== 1.0) || (plate.weight = Arg(ARG_DATA_IJ, slot!(lw, key * "|w", w; rank=2, dim0=G)))
     for (ref, cov) in lin.terms
         ref[1] == :g && push!(plate.terms, Term(Arg(ARG_GVAL, gval_of(lw, ref[2])), columns_arg(lw, "$(key)|cov|$(ref[2])", cols(cov), G)))

@@ -287,6 +287,25 @@ class Geometric(Dist):
         return _xlog1py(M, k, -self.p) + M.log(self.p)
 
 
+class BetaBinomial(Dist):
+    discrete = True
+
+    def __init__(self, M, a, b, n):
+        # distributions.jl:530-532: dbetabin(a, b, n) = BetaBinomial(n, a, b); Distributions checks n >= 0, a >= 0, b >= 0
+        _check(_val(n) >= 0, "BetaBinomial requires n >= 0")
+        _check(_val(a) >= 0 and _val(b) >= 0, "BetaBinomial requires a >= 0 and b >= 0")
+        self.a, self.b, self.n = a, b, n
+
+    def logpdf(self, M, k):
+        kv, nv = _val(k), _val(self.n)
+        if not (0 <= kv <= nv) or not M.isint(k):
+            return -M.inf
+        # Distributions: -log1p(n) - logbeta(k + 1, n - k + 1) + logbeta(k + a, n - k + b) - logbeta(a, b)
+        n = self.n
+        return (-M.log1p(n + 0.0 * self.a) - _logbeta(M, k + 1, n - k + 1) + _logbeta(M, k + self.a, n - k + self.b)
+                - _logbeta(M, self.a, self.b))
+
+
 class Chisq(Dist):
     def __init__(self, M, k):
         # distributions.jl:215-217: Chisq(k) = Gamma(k/2, 2)
@@ -355,6 +374,8 @@ def make_dist(M, name, args):
         return Weibull(M, *args)
     if name == "dnegbin":
         return NegativeBinomial(M, *args)
+    if name == "dbetabin":
+        return BetaBinomial(M, *args)
     if name == "dgeom":
         return Geometric(M, *args)
     if name == "dchisqr":

@@ -283,6 +283,15 @@ static int fam_logpdf(uint32_t fam, double x, const double* a, double* lp, doubl
         da[0] = 1.0 / py;
         return 0;
     }
+    case JBUGS_FAM_BETABIN: { /* :530-532 -> BetaBinomial(n, a, b): -log1p(n) - logbeta(k+1, n-k+1) + logbeta(k+a, n-k+b) - logbeta(a, b) */
+        double al = a[0], be = a[1], n = a[2];
+        if (!(n >= 0.0) || !(al >= 0.0) || !(be >= 0.0)) return 1;
+        if (x < 0.0 || x > n || x != floor(x)) { *lp = -INFINITY; return 0; }
+        *lp = -log1p(n) - logbeta(x + 1.0, n - x + 1.0) + logbeta(x + al, n - x + be) - logbeta(al, be);
+        da[0] = digamma(x + al) - digamma(n + al + be) - digamma(al) + digamma(al + be);
+        da[1] = digamma(n - x + be) - digamma(n + al + be) - digamma(be) + digamma(al + be);
+        return 0;
+    }
     default: return 2;
     }
 }

@@ -26,6 +26,8 @@ OBS = [
      lambda rng, shp: rng.poisson(2.0, shp).astype(float)),
     ("negbin", "y[{ix}] ~ dnegbin(mu[{ix}], r.y)", ["logit"], [("r.y", "dgamma(3, 1)")],
      lambda rng, shp: rng.negative_binomial(3, 0.5, shp).astype(float)),
+    ("betabin", "y[{ix}] ~ dbetabin(mu[{ix}], b.y, 6)", ["log"], [("b.y", "dgamma(3, 1)")],
+     lambda rng, shp: rng.integers(0, 7, shp).astype(float)),
     ("geometric", "y[{ix}] ~ dgeom(mu[{ix}])", ["logit", "probit", "cloglog"], [],
      lambda rng, shp: (rng.geometric(0.4, shp) - 1).astype(float)),
     ("gamma", "y[{ix}] ~ dgamma(a.y, mu[{ix}])", ["log"], [("a.y", "dgamma(3, 1)")],
@@ -132,7 +134,7 @@ def make_structured(seed):
     name, obs_stmt, links, aux, ygen = OBS[int(rng.integers(0, len(OBS)))]
     link = links[int(rng.integers(0, len(links)))]
     globals_ = [("b0", GLOBAL_PRIORS[int(rng.integers(0, len(GLOBAL_PRIORS)))]), ("b1", "dnorm(0.0, 1.0)")] + list(aux)
-    if rng.integers(0, 2) and name != "student":   # (dt's third argument and the padding weight share a slot)
+    if rng.integers(0, 2) and name not in ("student", "betabin"):   # (the third argument and the padding weight share a slot)
         # --- gathered: y[i] ~ f(b0 + b1 x[i] + u[g[i]] (+ v[g[i]] z[i]))
         n, G = int(rng.integers(8, 60)), int(rng.integers(2, 7))
         grp = np.concatenate([np.arange(1, G + 1), rng.integers(1, G + 1, n - G)]).astype(float)

@@ -44,6 +44,12 @@ MODELS = {
         tau ~ dgamma(2, 2)
         a ~ dnorm(0, 0.1)
         b ~ dnorm(0, 0.1) }""", {"N": N, "x": x, "k": (rng.geometric(0.4, N) - 1).astype(float)}),
+    "obs_betabin": ("""model {
+        for (i in 1:N) { r[i] ~ dbetabin(al[i], be, 12)
+                         log(al[i]) <- a + b * x[i] }
+        be ~ dgamma(2, 1)
+        a ~ dnorm(0, 0.1)
+        b ~ dnorm(0, 0.1) }""", {"N": N, "x": x, "r": rng.binomial(12, rng.beta(2.0, 3.0, N)).astype(float)}),
     "obs_weibull": ("""model {
         for (i in 1:N) { w[i] ~ dweib(v, lam[i])
                          log(lam[i]) <- a + b * x[i] }
@@ -80,7 +86,7 @@ def test_plan_matches_node_loop(name):
 
 def test_new_families_against_mpmath():
     """50-digit evaluation of the same node loop: the float64 formulas carry no hidden cancellation."""
-    for name in ("priors", "obs_negbin", "obs_geom", "obs_weibull"):
+    for name in ("priors", "obs_negbin", "obs_geom", "obs_betabin", "obs_weibull"):
         text, data = MODELS[name]
         gm = go.compile(text, data)
         th = 0.3 * np.ones(gm.D)
@@ -93,6 +99,7 @@ def test_new_families_against_mpmath():
     ("model { p ~ dnorm(0.5, 1)\n k ~ dnegbin(p, 3) }", {"k": 2}, 1.5),
     ("model { p ~ dnorm(0.5, 1)\n k ~ dgeom(p) }", {"k": 2}, 1.5),
     ("model { p ~ dnorm(0.5, 1)\n k ~ dgeom(p) }", {"k": 2}, 0.0),
+    ("model { a ~ dnorm(0.5, 1)\n k ~ dbetabin(a, 2, 5) }", {"k": 2}, -0.5),
     ("model { v ~ dnorm(1, 1)\n w ~ dweib(v, 1) }", {"w": 0.7}, -0.5),
     ("model { k ~ dnorm(1, 1)\n z ~ dchisqr(k) }", {"z": 0.7}, -0.5),
 ])
@@ -139,6 +146,7 @@ def _scipy_cases():
         ("dnegbin(0.4, 3)", S.nbinom(3, 0.4), "discrete", 5.0),
         ("dt(1.5, 4.0, 5)", S.t(5, 1.5, 0.5), None, 0.7),
         ("dgeom(0.3)", S.geom(0.3, loc=-1), "discrete", 4.0),
+        ("dbetabin(2.5, 1.5, 9)", S.betabinom(9, 2.5, 1.5), "discrete", 4.0),
     ]
 
 
@@ -156,7 +164,7 @@ def _reference_logp(dist, support, x):
     return lp, lp + np.log(x - lb), np.log(x - lb)
 
 
-@pytest.mark.parametrize("k", range(17))
+@pytest.mark.parametrize("k", range(18))
 def test_single_node_models_against_scipy(k):
     call, dist, support, x = _scipy_cases()[k]
     text = "model { a ~ %s }" % call
@@ -173,7 +181,7 @@ def test_single_node_models_against_scipy(k):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k", range(17))
+@pytest.mark.parametrize("k", range(18))
 def test_single_node_models_against_scipy_cuda(k):
     call, dist, support, x = _scipy_cases()[k]
     text = "model { a ~ %s }" % call

@@ -146,6 +146,7 @@ def test_chain_diagnostics_on_known_processes():
     ("dt", (1.5, 4.0, 7.0), lambda S: S.t(7, 1.5, 0.5)),
     ("dnegbin", (0.4, 3.0), lambda S: S.nbinom(3, 0.4)),
     ("dgeom", (0.3,), lambda S: S.geom(0.3, loc=-1)),
+    ("dbetabin", (2.5, 1.5, 9.0), lambda S: S.betabinom(9, 2.5, 1.5)),
 ])
 def test_forward_sampler_parameterisations(fn, args, dist):
     """The BUGS -> numpy parameterisation of each forward sampler (precision -> scale, rate -> scale, dgeom counting

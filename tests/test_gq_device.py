@@ -175,7 +175,7 @@ def test_forward_samplers_have_the_right_moments():
         ("ddexp(0.5, 4.0)", S.laplace(0.5, 0.5)), ("dweib(1.7, 0.8)", S.weibull_min(1.7, scale=1.25)), ("dchisqr(5)", S.chi2(5)),
         ("dbern(0.3)", S.bernoulli(0.3)), ("dbin(0.1, 10)", S.binom(10, 0.1)), ("dbin(0.7, 500)", S.binom(500, 0.7)),
         ("dpois(3.5)", S.poisson(3.5)), ("dpois(140.0)", S.poisson(140.0)), ("dnegbin(0.4, 3)", S.nbinom(3, 0.4)),
-        ("dt(1.5, 4.0, 7)", S.t(7, 1.5, 0.5)), ("dgeom(0.3)", S.geom(0.3, loc=-1)),
+        ("dt(1.5, 4.0, 7)", S.t(7, 1.5, 0.5)), ("dgeom(0.3)", S.geom(0.3, loc=-1)), ("dbetabin(2.5, 1.5, 9)", S.betabinom(9, 2.5, 1.5)),
     ]
     body = "\n".join(f"  q{k} ~ {call}" for k, (call, _) in enumerate(fams))
     text = "model {\n  a ~ dnorm(0, 1)\n  y ~ dnorm(a, 1)\n" + body + "\n}"
