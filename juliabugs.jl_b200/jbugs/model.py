@@ -33,6 +33,9 @@ from .cuda import CudaPlan, JBugsCudaError
 from .lowering import Lowering, LoweringError
 
 
+AUTO_SPECIALIZE_CELLS = 200_000
+
+
 class EvaluationMode:
     pass
 
@@ -47,11 +50,14 @@ class UseGeneratedLogDensityFunction(EvaluationMode):
 
 @dataclass
 class UseCUDABatch(EvaluationMode):
-    """The new evaluation mode: plate plan + libjbugs_cuda on one B200.  `specialize=True` compiles a kernel for the
-    exact shape of every plate that has no in-tree specialisation when the device plan is built (nvcc at run time,
-    cached on disk; the reference generates and compiles Julia code per model at the same point, bugsmodel.jl:736-801)."""
+    """The new evaluation mode: plate plan + libjbugs_cuda on one B200.  `specialize`: compile a kernel for the exact
+    shape of every plate that has no in-tree specialisation, expression tapes included (NVRTC in-process, cubins cached
+    per user; the reference generates and compiles Julia code per model at the same point, bugsmodel.jl:736-801).
+    True: when the device plan is built, blocking.  "auto" (default): for plates of at least `AUTO_SPECIALIZE_CELLS`
+    observations, on a worker thread -- the interpreter kernels answer until the compiled ones are ready, and a box
+    without libnvrtc simply keeps the interpreter.  False: never."""
     device: int = 0
-    specialize: bool = False
+    specialize: object = "auto"
 
 
 @dataclass
@@ -98,9 +104,23 @@ class BUGSModel:
                                  "use set_evaluation_mode(model, UseCUDABatch())")
         if self._cuda is None:
             self._cuda = CudaPlan(self.plan, device=self.evaluation_mode.device)
-            if self.evaluation_mode.specialize:
+            want = self.evaluation_mode.specialize
+            if want is True:
                 self._cuda.specialize()
+            elif want == "auto" and self._interpreted_cells() >= AUTO_SPECIALIZE_CELLS:
+                try:
+                    self._cuda.specialize_async()
+                except JBugsCudaError:
+                    pass   # no libnvrtc on this box: the interpreter instantiations keep running
         return self._cuda
+
+    def _interpreted_cells(self) -> int:
+        """observation cells of the plates that run an interpreter instantiation (no in-tree specialised kernel)"""
+        cells = 0
+        for k, line in enumerate(self._cuda.describe().splitlines()[1:]):
+            if k < len(self.plan.plates) and ("kernel=dynamic " in line or "kernel=expression_tape " in line):
+                cells += self.plan.plates[k].N * self.plan.plates[k].T
+        return cells
 
     def invalidate(self):
         """drop the device plan (what condition/fix/decondition do to the generated function,
