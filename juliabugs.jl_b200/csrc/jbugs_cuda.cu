@@ -1233,7 +1233,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
         if (!jit && variant == 0) fp.p[k].obs_const = 0.0;  // the interpreter evaluates the full log-density itself
         cudaError_t le = jit ? jit_launch(*r.jit, r.n_tiles, r.smem_bytes, st, pp, theta, grad, ld, C, p->d_gvals, ldg,
                                           p->d_partial + r.partial_offset * ldg, p->d_flags, want_grad && grad, p->use_pdl)
-                             : g_specs[variant].launch(r.n_tiles, r.smem_bytes, st, pp, theta, grad, ld, C, p->d_gvals, ldg,
+                             : g_specs[variant].launch(r.n_tiles, r.smem_bytes + (size_t)g_specs[variant].smpf_doubles * 8, st, pp, theta, grad, ld, C, p->d_gvals, ldg,
                                                        p->d_partial + r.partial_offset * ldg, p->d_flags, want_grad && grad, p->use_pdl);
         if (le != cudaSuccess) return fail(JBUGS_ERR_CUDA, "plate kernel launch failed: %s", cudaGetErrorString(le));
         p->launches++;

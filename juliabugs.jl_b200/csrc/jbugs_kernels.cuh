@@ -137,6 +137,7 @@ struct DynSpec {
     static constexpr bool SOFF = false;       // stream offsets come from the kernel parameters
     static constexpr bool XTAPE = false;      // (XSpec: the instantiation that interprets expression tapes)
     static constexpr bool XGEN = false;       // (a run-time generated description whose tape is compiled code)
+    static constexpr bool SMPF = false;       // (shared-memory theta prefetch: static specs only)
     // bounds of the unrolled loops over locals / global-coefficient terms (the arrays keep their MAX_* sizes: the kernel
     // parameter layout is one for all instantiations).  A static spec knows its counts: the front end then emits nl / kg
     // copies of each loop body instead of MAX_LOC / MAX_GT guarded ones for the optimiser to throw away.
@@ -191,6 +192,12 @@ struct desc_xgen { static constexpr bool value = false; };
 template <class D>
 struct desc_xgen<D, decltype((void)D::XGEN)> { static constexpr bool value = D::XGEN; };
 
+// does the description ask for the shared-memory theta prefetch (`SMPF`)?
+template <class D, class = void>
+struct desc_smpf { static constexpr bool value = false; };
+template <class D>
+struct desc_smpf<D, decltype((void)D::SMPF)> { static constexpr bool value = D::SMPF; };
+
 // A static spec is a struct with `static constexpr PlateShape SH` ; see specs in jbugs_cuda.cu.
 // the shape of a description as ONE constant object in device memory: every accessor of StaticSpec is a load at a
 // constant address that the optimiser folds (calling the constexpr sh() per access instead made NVVM inline and
@@ -204,6 +211,10 @@ struct StaticSpec {
     using D = Desc;
     static constexpr int NL_MAX = Desc::sh().nl, KG_MAX = Desc::sh().kg;
     static constexpr bool XGEN = desc_xgen<Desc>::value;
+    // FP64-bound plates: the theta rows of the NEXT block of UNROLL groups travel global -> shared with cp.async while
+    // this block is evaluated (no registers held across the block, unlike PREFETCH); group-level locals with affine
+    // slot maps only.  The launcher adds smpf_doubles() of dynamic shared memory behind the staging buffers.
+    static constexpr bool SMPF = desc_smpf<Desc>::value;
     static constexpr bool STATIC = true;
     static constexpr int FUSED = Desc::FUSED;
     static constexpr int UNROLL = Desc::UNROLL;

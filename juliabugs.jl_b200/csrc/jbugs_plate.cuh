@@ -502,6 +502,38 @@ __device__ __forceinline__ void load_groups(const S& sp, const PlateVals& V, lon
         }
 }
 
+// SMPF: the same for a block whose theta rows were copied to shared memory while the previous block was evaluated
+// (`src`, this thread's column of a [UU][MAX_LOC] table of BLK-wide rows; null: load from global memory), and the
+// cp.async copies of the block after it (`dst`; null: none).  pos[] ends up at the start of the next block either way.
+template <class S, int UU, int BLK>
+__device__ __forceinline__ void load_groups_sm(const S& sp, const PlateVals& V, const double* __restrict__ th,
+                                               long long (&pos)[MAX_LOC], GroupLoads<UU, PreObs<S>::TS>& gl,
+                                               const double* src, double* dst, bool newer_group) {
+    // this thread's own copies (it is the only reader of its column).  `newer_group`: the staging copies of the next
+    // chunk were committed after them and may stay in flight
+    if (src) {
+        if (newer_group) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        else cp_async_wait_all();
+    }
+#pragma unroll
+    for (int u = 0; u < UU; ++u)
+#pragma unroll
+        for (int l = 0; l < S::NL_MAX; ++l)
+            if (l < sp.nl()) {
+                gl.off[u][l] = pos[l];
+                pos[l] += V.loc[l].step_i;
+                gl.raw[u][l] = src ? src[(u * MAX_LOC + l) * BLK] : th[gl.off[u][l]];
+            }
+    if (dst) {
+#pragma unroll
+        for (int u = 0; u < UU; ++u)
+#pragma unroll
+            for (int l = 0; l < S::NL_MAX; ++l)
+                if (l < sp.nl()) cp_async8(dst + (u * MAX_LOC + l) * BLK, th + pos[l] + u * V.loc[l].step_i);
+        cp_async_commit();
+    }
+}
+
 // UU consecutive groups starting at chunk-local index g (global group index i), theta already loaded
 template <class S, int UU>
 __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, const StageView& sv, int g, long long i,
@@ -703,6 +735,9 @@ __device__ __forceinline__ void plate_body(const PlateParams& P, const double* _
     int cur = 0;
     GroupLoads<U, PreObs<S>::TS> gl_cur;
     bool have_cur = false;
+    // SMPF: two [U][MAX_LOC][BLK] tables behind the staging buffers
+    double* const pf_base = stage0 + 2 * stage_doubles;
+    int pf_cur = 0;
     for (long long i0 = ib; i0 < ie; i0 += STAGE_G) {
         const long long rem = ie - i0;
         const int cnt = rem < STAGE_G ? (int)rem : STAGE_G;
@@ -728,6 +763,15 @@ __device__ __forceinline__ void plate_body(const PlateParams& P, const double* _
                 bad |= eval_groups<S, U>(sp, V, sv, g, i, T, th, gr, ld, store, obs_tau, pos, gl_cur, st, fa, lp);
                 if (more) gl_cur = gl_nxt;
                 have_cur = more;
+            } else if constexpr (S::SMPF) {
+                // theta of block i came through shared memory if the block before it asked for it; ask for block i + U
+                const bool more = i + 2 * U <= ie;
+                double* const mine = pf_base + tid;
+                load_groups_sm<S, U, BLK>(sp, V, th, pos, gl_cur, have_cur ? mine + pf_cur * (U * MAX_LOC * BLK) : nullptr,
+                                          more ? mine + (pf_cur ^ 1) * (U * MAX_LOC * BLK) : nullptr, g == 0 && i0 + STAGE_G < ie);
+                pf_cur ^= 1;
+                have_cur = more;
+                bad |= eval_groups<S, U>(sp, V, sv, g, i, T, th, gr, ld, store, obs_tau, pos, gl_cur, st, fa, lp);
             } else {
                 load_groups<S, U>(sp, V, i, th, ld, pos, gl_cur);
                 bad |= eval_groups<S, U>(sp, V, sv, g, i, T, th, gr, ld, store, obs_tau, pos, gl_cur, st, fa, lp);

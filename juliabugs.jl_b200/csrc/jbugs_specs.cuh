@@ -53,6 +53,7 @@ struct SpecEntry {
     bool (*matches)(const PlateShape&, long long T);
     int fused;  // FUSED_* code: tells the host whether the plate needs obs_const
     fused_launch_fn one_launch;  // whole evaluation of a small single-plate model in one kernel (nullptr: not built for this spec)
+    int smpf_doubles;            // extra dynamic shared memory (doubles) of a spec with the shared-memory theta prefetch
 };
 
 #include "jbugs_static_specs.inc"
@@ -61,15 +62,15 @@ struct SpecEntry {
 static bool match_never(const PlateShape&, long long) { return false; }
 
 static const SpecEntry g_specs[] = {
-    {"dynamic", &launch_dyn, &match_never, FUSED_NONE, &launch_fused_dyn},
-    {"rats_normal_identity_T5", &launch_rats_t5, &RatsDesc<5>::matches, RatsDesc<5>::FUSED, nullptr},
-    {"rats_normal_identity", &launch_rats, &RatsDesc<0>::matches, RatsDesc<0>::FUSED, nullptr},
-    {"seeds_binomial_logit", &launch_seeds, &SeedsDesc::matches, SeedsDesc::FUSED, nullptr},
-    {"surgical_binomial_logit", &launch_surgical, &SurgicalDesc::matches, SurgicalDesc::FUSED, nullptr},
-    {"epil_poisson_log_T4", &launch_epil_t4, &EpilDesc<4>::matches, EpilDesc<4>::FUSED, &launch_fused_epil_t4},
-    {"epil_poisson_log", &launch_epil, &EpilDesc<0>::matches, EpilDesc<0>::FUSED, &launch_fused_epil},
-    {"pumps_poisson_gamma", &launch_pumps, &PumpsDesc::matches, PumpsDesc::FUSED, &launch_fused_pumps},
-    {"expression_tape", &launch_x, &match_never, FUSED_NONE, nullptr},
+    {"dynamic", &launch_dyn, &match_never, FUSED_NONE, &launch_fused_dyn, 0},
+    {"rats_normal_identity_T5", &launch_rats_t5, &RatsDesc<5>::matches, RatsDesc<5>::FUSED, nullptr, 0},
+    {"rats_normal_identity", &launch_rats, &RatsDesc<0>::matches, RatsDesc<0>::FUSED, nullptr, 0},
+    {"seeds_binomial_logit", &launch_seeds, &SeedsDesc::matches, SeedsDesc::FUSED, nullptr, SeedsDesc::SMPF ? 2 * SeedsDesc::UNROLL * MAX_LOC * 128 : 0},
+    {"surgical_binomial_logit", &launch_surgical, &SurgicalDesc::matches, SurgicalDesc::FUSED, nullptr, SurgicalDesc::SMPF ? 2 * SurgicalDesc::UNROLL * MAX_LOC * 128 : 0},
+    {"epil_poisson_log_T4", &launch_epil_t4, &EpilDesc<4>::matches, EpilDesc<4>::FUSED, &launch_fused_epil_t4, 0},
+    {"epil_poisson_log", &launch_epil, &EpilDesc<0>::matches, EpilDesc<0>::FUSED, &launch_fused_epil, 0},
+    {"pumps_poisson_gamma", &launch_pumps, &PumpsDesc::matches, PumpsDesc::FUSED, &launch_fused_pumps, 0},
+    {"expression_tape", &launch_x, &match_never, FUSED_NONE, nullptr, 0},
 };
 static const int g_num_specs = (int)(sizeof(g_specs) / sizeof(g_specs[0]));
 static const int g_xspec = g_num_specs - 1;  // the tape interpreter: selected by the plate kind, never by shape
