@@ -400,7 +400,47 @@ model {
 }
 """
 
+MICE = """
+model {
+    for (i in 1:M) {
+        for (j in 1:N) {
+            t[i, j] ~ dweib(r, mu[i]) C(t.cen[i, j],)
+        }
+        mu[i] <- exp(beta[i])
+        beta[i] ~ dnorm(0.0, 0.001)
+        median[i] <- pow(log(2) * exp(-beta[i]), 1 / r)
+    }
+    r ~ dunif(0.1, 10)
+    veh.control <- beta[2] - beta[1]
+    test.sub <- beta[3] - beta[1]
+    pos.control <- beta[4] - beta[1]
+}
+"""
+
+KIDNEY = """
+model {
+    for (i in 1:N) {
+        for (j in 1:M) {
+            t[i, j] ~ dweib(r, mu[i, j]) C(t.cen[i, j],)
+            log(mu[i, j]) <- alpha + beta.age * age[i, j] + beta.sex * sex[i] + beta.dis[disease[i]] + b[i]
+        }
+        b[i] ~ dnorm(0.0, tau)
+    }
+    alpha ~ dnorm(0.0, 0.0001)
+    beta.age ~ dnorm(0.0, 0.0001)
+    beta.sex ~ dnorm(0.0, 0.0001)
+    for (k in 2:4) {
+        beta.dis[k] ~ dnorm(0.0, 0.0001)
+    }
+    tau ~ dgamma(1.0E-3, 1.0E-3)
+    r ~ dgamma(1.0, 1.0E-3)
+    sigma <- 1 / sqrt(tau)
+}
+"""
+
 MODELS = {
+    "mice": MICE,
+    "kidney": KIDNEY,
     "dugongs": DUGONGS,
     "lsat": LSAT,
     "air": AIR,

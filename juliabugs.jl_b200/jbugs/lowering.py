@@ -53,6 +53,7 @@ class Stmt:
                                    # statement has no rectangular domain; it can be folded pointwise (data) or inlined
     obs_mask: object = None        # partially observed statement: boolean array over the loop domain (True = observed)
     zobs: object = None            # discrete latent being summed out, partially observed: its value per cell, 0 = missing
+    censor: object = None          # (lower, upper) expressions of `dist(...) C(lower, upper)`; Var("nothing") = no bound
 
     @property
     def name(self):
@@ -80,6 +81,12 @@ def _flatten(stmts, loops=(), out=None):
     for s in stmts:
         if isinstance(s, For):
             _flatten(s.body, loops + ((s.var, s.lo, s.hi),), out)
+        elif isinstance(s, Stoch) and s.dist.fn in ("censored", "truncated"):
+            # dist(...) C(lower, upper): the statement keeps the inner distribution; the bounds are checked against the
+            # observed values once the statement is classified (Lowering._check_censoring)
+            if s.dist.fn == "truncated" or len(s.dist.args) != 3 or not isinstance(s.dist.args[0], Call):
+                raise LoweringError("truncated distributions (T(,)) are outside the plate class")
+            out.append(Stmt(len(out) + 1, Stoch(s.lhs, s.dist.args[0]), loops, censor=(s.dist.args[1], s.dist.args[2])))
         else:
             out.append(Stmt(len(out) + 1, s, loops))
     return out
@@ -265,12 +272,29 @@ class Lowering:
             else:
                 v = float(v)
             self.data[k] = v
+        self.theta_order = theta_order
+        try:
+            self._lower_all(expand_picks=False)
+        except LoweringError as first:
+            # second reading: short parameter vectors picked by a data index written out as indicator sums (Kidney-style
+            # factor levels); the gathered plate (b[school[i]]) stays the first choice
+            try:
+                self._lower_all(expand_picks=True)
+            except LoweringError as second:
+                if str(second) == str(first):
+                    raise first from None
+                raise LoweringError(f"{first} (with data-index picks of short parameter vectors written out: {second})") from None
+            except Exception:
+                raise first from None
+
+    def _lower_all(self, expand_picks: bool):
         self.de = DataEval(self.data)
         self.stmts: List[Stmt] = _flatten(self.stmts_ast)
-        self.theta_order = theta_order
         self._bounds()
         self._fold_transformed_data()
         self._classify()
+        if expand_picks:
+            self._expand_data_picks()
         self._order_parameters()
         self._build_plan()
 
@@ -397,6 +421,94 @@ class Lowering:
     def _defs(self, name):
         return [s for s in self.stmts if s.name == name and s.kind != "tdata"]
 
+    def _expand_data_picks(self):
+        """`beta.dis[disease[i]]`: an element of a SHORT parameter vector picked by a data index (the factor-level idiom of
+        regression models; Kidney) is the sum over the vector's elements with 0/1 data coefficients,
+        beta.dis[1] * equals(disease[i], 1) + ... -- from there on the ordinary machinery applies (elements referenced
+        with constant subscripts become globals, the indicators are folded to data covariates).  Elements of the array
+        that are data (a corner-point constraint beta.dis[1] = 0 given as data) enter as constants."""
+        short: Dict[str, tuple] = {}
+        for d in self.stmts:
+            if d.kind == "param" and not d.is_gq and len(d.loops) == 1 and isinstance(d.node.lhs, Index) and len(d.node.lhs.idx) == 1:
+                lo, hi = d.extents[0]
+                idx = np.asarray(self.de.ev(d.node.lhs.idx[0], _grids(d.extents, d.loop_vars))).astype(np.int64).ravel()
+                got = short.get(d.name, ())
+                short[d.name] = tuple(sorted(set(got) | set(int(i) for i in idx)))
+        short = {k: v for k, v in short.items() if len(v) <= 8 and max(v) <= 16}
+        if not short:
+            return
+
+        def rewrite(e, loop_vars):
+            if isinstance(e, Index):
+                idx = tuple(rewrite(i, loop_vars) for i in e.idx)
+                if e.name in short and len(idx) == 1 and not isinstance(idx[0], (Range, Colon)) and \
+                        self.de.known(idx[0], loop_vars) and not self.de.known(idx[0], ()):
+                    arr = self.data.get(e.name)
+                    picked = set(int(v) for v in np.unique(np.asarray(self.de.ev(idx[0], cur_grid[0]))))
+                    if any(k not in picked for k in short[e.name]):
+                        # (an element nobody picks has no observed descendants: a generated quantity in the reference)
+                        raise LoweringError(f"every element of '{e.name}' needs at least one observation that picks it")
+                    top = max(max(short[e.name]), len(arr) if isinstance(arr, np.ndarray) else 0)
+                    out = None
+                    for k in range(1, top + 1):
+                        ind = Call("equals", (idx[0], Num(float(k), True)))
+                        if k in short[e.name]:
+                            term = BinOp("*", Index(e.name, (Num(float(k), True),)), ind)
+                        else:
+                            v = float(arr[k - 1]) if isinstance(arr, np.ndarray) and k <= len(arr) else float("nan")
+                            if math.isnan(v):
+                                raise LoweringError(f"'{e.name}[{k}]' is neither a parameter nor data")
+                            if v == 0.0:
+                                continue
+                            term = BinOp("*", Num(v), ind)
+                        out = term if out is None else BinOp("+", out, term)
+                    return out if out is not None else Num(0.0)
+                return Index(e.name, idx)
+            if isinstance(e, Call):
+                return Call(e.fn, tuple(rewrite(a, loop_vars) for a in e.args))
+            if isinstance(e, BinOp):
+                return BinOp(e.op, rewrite(e.a, loop_vars), rewrite(e.b, loop_vars))
+            if isinstance(e, Neg):
+                return Neg(rewrite(e.a, loop_vars))
+            return e
+
+        cur_grid = [None]
+        for t in self.stmts:
+            if t.ragged or t.kind == "tdata":
+                continue
+            cur_grid[0] = _grids(t.extents, t.loop_vars)
+            if t.kind == "logical":
+                t.node = Det(t.node.lhs, rewrite(t.node.rhs, t.loop_vars))
+            elif t.kind in ("obs", "param", "latent"):
+                t.node = Stoch(t.node.lhs, rewrite(t.node.dist, t.loop_vars))
+
+    def _check_censoring(self):
+        """`y ~ dist(...) C(lower, upper)` (Distributions.censored): strictly between the bounds the density is the inner
+        distribution's -- the only case the plate kernels evaluate.  An observation ON a bound carries the tail mass of
+        the inner distribution (needs its cdf), an unobserved censored node in the target a mixed discrete-continuous
+        prior: both are refused.  Missing cells without descendants are generated quantities and drop out of the
+        target (graphs.jl:27-71), which is how the reference's Mice / Kidney examples evaluate."""
+        for s in self.stmts:
+            if s.censor is None or s.kind == "tdata":
+                continue
+            lv = _grids(s.extents, s.loop_vars)
+            shape = s.shape if s.shape else ()
+            bounds = []
+            for b, none in zip(s.censor, (-np.inf, np.inf)):
+                if isinstance(b, Var) and b.name == "nothing":
+                    bounds.append(np.full(shape, none))
+                elif not self.de.known(b, s.loop_vars):
+                    raise LoweringError(f"'{s.name}': censoring bounds must be data")
+                else:
+                    bounds.append(np.broadcast_to(np.asarray(self.de.ev(b, lv), dtype=np.float64), shape))
+            s.censor = tuple(bounds)
+            if s.kind == "obs":
+                lhs = s.node.lhs
+                y = np.broadcast_to(np.asarray(self.de.ev(lhs if isinstance(lhs, Index) else Var(lhs.name), lv), dtype=np.float64), shape)
+                seen = ~np.isnan(y) if s.obs_mask is None else np.asarray(s.obs_mask)
+                if np.any(seen & ~((y > bounds[0]) & (y < bounds[1]))):
+                    raise LoweringError(f"'{s.name}': an observation on or outside its censoring bounds is outside the plate class")
+
     def _classify(self):
         for s in self.stmts:
             if s.kind:
@@ -434,6 +546,12 @@ class Lowering:
                     s.kind = "param" if math.isnan(arr) else "obs"
             else:
                 s.kind = "param"
+        self._check_censoring()
+        for s in self.stmts:
+            # an array that is partly data and partly parameters (beta.dis = [0, NA, NA, NA]): a reference to it is not a
+            # data expression
+            if s.kind == "param" and isinstance(self.data.get(s.name), np.ndarray):
+                self.de.unknown.add(s.name)
         for s in self.stmts:
             if s.kind == "param" and s.node.dist.fn in ("dcat", "dbern", "dbin"):
                 # an unobserved finite discrete node: a parameter with the identity bijector in UseGraph / UseGeneratedLogDensityFunction
@@ -1102,6 +1220,12 @@ class Lowering:
         if plate.family in (P.FAM_T, P.FAM_BETABIN):
             raise LoweringError("dt observations with missing cells are not supported")
         m = np.asarray(s.obs_mask, dtype=np.float64)
+        # a plate-level parameter all of whose observations are missing has no observed descendants: the reference
+        # takes that ELEMENT out of the target (graphs.jl:27-71; Kidney's b[14], b[19], b[36]) -- per-element holes in
+        # theta are outside the plate class
+        if plate.locals and np.any(m.reshape(m.shape[0], -1).sum(axis=1) == 0):
+            raise LoweringError(f"'{s.name}': a group without any observed cell leaves its parameters without observed "
+                                "descendants (generated quantities element by element) -- outside the plate class")
         if m.ndim == 1:
             plate.weight = P.Arg(P.ARG_DATA_I, self._slot(f"obs_mask|{s.name}", m.copy()))
         else:

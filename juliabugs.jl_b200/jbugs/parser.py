@@ -214,6 +214,17 @@ class _Parser:
             d = self.primary()
             if not isinstance(d, Call):
                 raise BUGSSyntaxError("distribution call expected after '~'")
+            # censoring / truncation suffix: dweib(r, mu) C(lower, upper), T(lower, upper) (I(,) is WinBUGS' spelling of
+            # C); either bound may be empty.  Same tree as the reference builds (bugs_parser.jl:493):
+            # censored(dist, lower, upper) with `nothing` for an empty bound
+            if self.peek()[0] == "name" and self.peek()[1] in ("C", "T", "I") and self.peek(1)[1] == "(":
+                which = self.next()[1]
+                self.next()
+                bounds = []
+                for closer in (",", ")"):
+                    bounds.append(Var("nothing") if self.peek()[1] == closer else self.expr())
+                    self.expect(closer)
+                d = Call("truncated" if which == "T" else "censored", (d, bounds[0], bounds[1]))
             return Stoch(lhs, d)
         if self.accept("<-") or self.accept("="):
             return Det(lhs, self.expr())

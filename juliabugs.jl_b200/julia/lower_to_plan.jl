@@ -213,6 +213,10 @@ function flatten!(out::Vector{Stmt}, block, loops)
         elseif st isa Expr && st.head == :block
             flatten!(out, st, loops)
         elseif st isa Expr && st.head == :call && st.args[1] == :~
+            # (censored(dist, lower, upper) / truncated(...): jbugs/lowering.py checks the observed values against the
+            #  bounds and keeps the inner distribution; not ported to this file yet -- refuse rather than mis-evaluate)
+            (st.args[3] isa Expr && st.args[3].head == :call && st.args[3].args[1] in (:censored, :truncated)) &&
+                fail("censored / truncated statements are lowered by the Python front end only")
             push!(out, Stmt(length(out) + 1, true, st.args[2], binarize(st.args[3]), loops, Tuple{Int,Int}[], :none, false, false, nothing))
         elseif st isa Expr && st.head == :(=)
             push!(out, Stmt(length(out) + 1, false, st.args[1], binarize(st.args[2]), loops, Tuple{Int,Int}[], :none, false, false, nothing))

@@ -162,6 +162,19 @@ class Reader:
             d = self.atom()
             if not isinstance(d, Call):
                 raise ModelTextError("a distribution call must follow '~'")
+            # dist(...) C(lo, hi) / T(lo, hi) / I(lo, hi): censored(dist, lo, hi) / truncated(dist, lo, hi), an empty
+            # bound is `nothing` (J/src/parser/bugs_parser.jl:470-500)
+            if any(self.at_word(w) for w in ("C", "T", "I")) and self.at_sym("(", 1):
+                which = self.take()[1]
+                self.take()
+                bounds = []
+                for closer in (",", ")"):
+                    if self.at_sym(closer):
+                        bounds.append(Var("nothing"))
+                    else:
+                        bounds.append(self.expression())
+                    self.need(closer)
+                d = Call("truncated" if which == "T" else "censored", (d, bounds[0], bounds[1]))
             return Stoch(target, d)
         if self.eat("<-") or self.eat("="):
             return Det(target, self.expression())

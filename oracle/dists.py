@@ -344,8 +344,33 @@ class Flat(Dist):
         return 0.0 * x
 
 
+class Censored(Dist):
+    """`censored(d, lower, upper)` (Distributions.Censored; the BUGS suffix C(lower, upper), bugs_parser.jl:470-500):
+    the density of `d` strictly inside (lower, upper), the tail mass of `d` on a bound, -Inf outside.  The tail masses
+    need the cdf of `d`; only the interior case occurs in the reference's examples once the missing (censored) cells
+    have dropped out of the target as generated quantities, so a value ON a bound raises instead of guessing."""
+
+    def __init__(self, M, inner, lower, upper):
+        self.inner, self.lower, self.upper = inner, lower, upper
+        self.discrete = inner.discrete
+
+    def support(self):
+        lb, ub = self.inner.support()
+        return (max(_val(lb), _val(self.lower)), min(_val(ub), _val(self.upper)))
+
+    def logpdf(self, M, x):
+        xv = _val(x)
+        if xv < _val(self.lower) or xv > _val(self.upper):
+            return -M.inf
+        if xv == _val(self.lower) or xv == _val(self.upper):
+            raise NotImplementedError("an observation on its censoring bound needs the cdf of the inner distribution")
+        return self.inner.logpdf(M, x)
+
+
 def make_dist(M, name, args):
     """BUGS distribution call -> distribution object (BUGSPrimitives/distributions.jl)."""
+    if name.startswith("censored:"):
+        return Censored(M, make_dist(M, name.split(":", 1)[1], args[:-2]), args[-2], args[-1])
     if name == "dnorm":
         return Normal(M, *args)
     if name == "dgamma":

@@ -239,11 +239,30 @@ def _flatten(stmts, loops=(), out=None):
     return out
 
 
+def _flatten_bounds(stmts):
+    """censored(d(args...), lower, upper) -> a plain call `censored:d`(args..., lower, upper) with +-Inf for an empty
+    bound, so that the bounds take part in evaluation and dependency tracking like any other distribution argument"""
+    out = []
+    for s in stmts:
+        if isinstance(s, For):
+            out.append(For(s.var, s.lo, s.hi, _flatten_bounds(s.body)))
+        elif isinstance(s, Stoch) and s.dist.fn in ("censored", "truncated"):
+            if s.dist.fn == "truncated":
+                raise NotImplementedError("truncated distributions (T(,)) are not part of the oracle")
+            inner, lo, hi = s.dist.args
+            lo = Num(-math.inf, False) if lo == Var("nothing") else lo
+            hi = Num(math.inf, False) if hi == Var("nothing") else hi
+            out.append(Stoch(s.lhs, Call("censored:" + inner.fn, tuple(inner.args) + (lo, hi))))
+        else:
+            out.append(s)
+    return tuple(out)
+
+
 class GraphModel:
     """What `compile` hands to the evaluator: environment, graph, node order, theta layout."""
 
     def __init__(self, text_or_stmts, data, inits=None, transformed=True):
-        self.stmts = parse(text_or_stmts) if isinstance(text_or_stmts, str) else tuple(text_or_stmts)
+        self.stmts = _flatten_bounds(parse(text_or_stmts) if isinstance(text_or_stmts, str) else tuple(text_or_stmts))
         self.transformed = transformed
         self.ev = Evaluator(FLOAT_OR_DUAL)
         self._flat = _flatten(self.stmts)

@@ -23,6 +23,7 @@ ZOO = [
     ("lsat", ex.LSAT, "lsat", "inits"),               # logistic(beta * theta[j] - alpha[k]), ragged data transformation
     ("air", ex.AIR, "air", "inits"),                  # a latent covariate times a coefficient
     ("leuk", ex.LEUK, "leuk", "inits"),               # Y[i,j] * exp(beta * Z[i]) * dL0[j] as a Poisson mean
+    ("mice", ex.MICE, "mice", "inits"),               # censored Weibull: the censored cells are missing, hence outside the target
 ]
 
 

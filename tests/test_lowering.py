@@ -220,3 +220,44 @@ def test_partially_observed_with_children_is_refused():
     text = "model { for (i in 1:N) { x[i] ~ dnorm(0, 1)\n y[i] ~ dnorm(x[i], 1) } }"
     with pytest.raises(jbugs.LoweringError, match="partially observed"):
         jbugs.lower(text, {"N": 3, "x": np.array([0.1, np.nan, 0.3]), "y": np.ones(3)})
+
+
+def test_kidney_is_refused_not_mis_evaluated(fixtures):
+    """Kidney: b[14], b[19], b[36] have no observed descendants (both of the patient's times are censored = missing), so
+    the reference takes exactly those ELEMENTS out of theta (43 parameters, the oracle agrees); a plate cannot leave
+    holes in a parameter vector, and lowering all 46 would evaluate a different model"""
+    fx = fixtures["kidney"]
+    gm = go.compile(jbugs.examples.KIDNEY, fx["data"], fx["inits"])
+    assert gm.D == 43 and "b[14]" not in gm.param_names()
+    with pytest.raises(jbugs.LoweringError, match="without any observed cell"):
+        jbugs.lower(jbugs.examples.KIDNEY, fx["data"])
+
+
+def test_factor_levels_picked_by_a_data_index():
+    """the Kidney idiom on complete data: beta.dis[disease[i]] with a corner-point constraint given as data"""
+    rng = np.random.default_rng(4)
+    N, M = 30, 2
+    text = jbugs.examples.KIDNEY
+    dis = rng.integers(1, 5, N).astype(float)
+    dis[:4] = [1, 2, 3, 4]
+    data = {"N": N, "M": M, "t": rng.weibull(1.2, (N, M)) * 50 + 1.0, "t.cen": np.zeros((N, M)), "age": rng.normal(45, 10, (N, M)),
+            "sex": rng.integers(0, 2, N).astype(float), "disease": dis, "beta.dis": np.array([0.0, np.nan, np.nan, np.nan])}
+    data["t"][3, 1] = np.nan
+    data["t.cen"][3, 1] = 60.0
+    gm = go.compile(text, data, {}).use_generated_order()
+    plan, lw = jbugs.lower(text, data)
+    assert plan.D == gm.D == 8 + N and lw.param_names() == gm.param_names()
+    th0 = np.zeros(plan.D)
+    names = lw.param_names()
+    th0[names.index("alpha")] = -4.0
+    th0[names.index("beta.age")] = 0.002
+    theta = random_thetas(th0, 3, seed=2, scale=0.05)
+    lp, g, st = COracle(plan).eval_batch(theta)
+    for c in range(3):
+        lp_g, g_g = gm.logdensity_and_gradient(theta[:, c])
+        assert st[c] == 0 and abs(lp[c] - lp_g) <= 1e-12 * abs(lp_g)
+        assert grad_err(g[:, c], g_g) < 1e-10
+    # an observation ON its censoring bound is refused (it would need the inner distribution's cdf)
+    data["t.cen"][0, 0] = data["t"][0, 0]
+    with pytest.raises(jbugs.LoweringError, match="censoring bounds"):
+        jbugs.lower(text, data)
