@@ -41,6 +41,18 @@ class LoweringError(NotImplementedError):
 # ----------------------------------------------------------------------------- statements
 
 
+class Ext(tuple):
+    """loop extents ((lo, hi), ...) whose OUTER loop runs over a subset of its range: `keep` holds the kept values of
+    the outer loop variable.  Used when rows of an observation plate have no observed cell at all: the reference takes
+    the parameters of such a row out of the target element by element (graphs.jl:27-71), so the plate -- and the
+    parameter statements it owns -- are compacted to the rows that remain (Kidney)."""
+    keep = None
+
+
+def _ext_keep(extents):
+    return getattr(extents, "keep", None)
+
+
 @dataclass
 class Stmt:
     sid: int                       # 1-based statement id in program order (source_gen.jl:5-20)
@@ -65,7 +77,9 @@ class Stmt:
 
     @property
     def shape(self):
-        return tuple(hi - lo + 1 for lo, hi in self.extents)
+        shp = tuple(hi - lo + 1 for lo, hi in self.extents)
+        keep = _ext_keep(self.extents)
+        return shp if keep is None else (len(keep),) + shp[1:]
 
     @property
     def size(self):
@@ -211,10 +225,12 @@ def _grids(extents, names):
     """integer index grids, one per loop variable, broadcastable to the loop domain shape."""
     lv = {}
     nd = len(extents)
+    keep = _ext_keep(extents)
     for d, ((lo, hi), nm) in enumerate(zip(extents, names)):
+        vals = np.asarray(keep, dtype=np.int64) if (d == 0 and keep is not None) else np.arange(lo, hi + 1, dtype=np.int64)
         shp = [1] * nd
-        shp[d] = hi - lo + 1
-        lv[nm] = np.arange(lo, hi + 1, dtype=np.int64).reshape(shp)
+        shp[d] = vals.size
+        lv[nm] = vals.reshape(shp)
     return lv
 
 
@@ -293,6 +309,7 @@ class Lowering:
         self._bounds()
         self._fold_transformed_data()
         self._classify()
+        self._compact_unobserved_rows()
         if expand_picks:
             self._expand_data_picks()
         self._order_parameters()
@@ -420,6 +437,72 @@ class Lowering:
     # ---- D. classification -----------------------------------------------------------------------
     def _defs(self, name):
         return [s for s in self.stmts if s.name == name and s.kind != "tdata"]
+
+    def _compact_unobserved_rows(self):
+        """Rows of a partially observed plate without any observed cell: the parameters such a row owns (`b[i]` of a
+        patient whose times are all censored = missing) have no observed descendants, and the reference removes exactly
+        those ELEMENTS from the target (graphs.jl:27-71: Kidney has 43 parameters, not 46).  The observation statement
+        and the single-loop parameter statements it references through its outer loop variable are restricted to the
+        remaining rows; theta then numbers the remaining elements consecutively, as the reference does."""
+        for s in self.stmts:
+            if s.kind != "obs" or s.obs_mask is None or s.is_gq or not s.loops:
+                continue
+            m = np.asarray(s.obs_mask)
+            alive = m.reshape(m.shape[0], -1).any(axis=1)
+            if alive.all():
+                continue
+            i_var = s.loop_vars[0]
+            try:
+                exprs = [self._inline_for_scan(a) for a in s.node.dist.args]
+            except LoweringError:
+                continue
+            owned = []
+            for e in exprs:
+                for r in _subexprs(e):
+                    if isinstance(r, Index) and len(r.idx) == 1 and isinstance(r.idx[0], Var) and r.idx[0].name == i_var:
+                        for d in self._defs(r.name):
+                            if d.kind == "param" and not d.is_gq and len(d.loops) == 1 and tuple(d.extents) == tuple(s.extents[:1]) \
+                                    and isinstance(d.node.lhs, Index) and len(d.node.lhs.idx) == 1 \
+                                    and isinstance(d.node.lhs.idx[0], Var) and d not in owned:
+                                owned.append(d)
+            if not owned:
+                continue
+            # the rows' parameters must not feed anything else (they would have observed descendants there)
+            for d in owned:
+                for t in self.stmts:
+                    if t is s or t is d or t.kind == "tdata":
+                        continue
+                    body = t.node.rhs if isinstance(t.node, Det) else t.node.dist
+                    if d.name in free_vars(body) and not (isinstance(t.node, Det) and not t.is_gq and t.name in
+                                                         {v for a in s.node.dist.args for v in free_vars(a)}):
+                        raise LoweringError(f"'{d.name}' feeds more than the partially observed plate '{s.name}': rows without "
+                                            "observations cannot be dropped")
+            lo = s.extents[0][0]
+            keep = lo + np.nonzero(alive)[0]
+            for t in [s] + owned:
+                e = Ext(t.extents)
+                e.keep = keep
+                t.extents = e
+            s.obs_mask = m[alive]
+
+    def _inline_for_scan(self, e):
+        """references reachable from an expression through the logical statements it names (one level of names is enough
+        for the scan: loop-variable subscripts are carried through substitution by `_inline` when the plan exists; before
+        that only the statement graph is known)"""
+        out = [e]
+        seen = set()
+        todo = [e]
+        while todo:
+            x = todo.pop()
+            for v in free_vars(x):
+                if v in seen:
+                    continue
+                seen.add(v)
+                for d in self._defs(v):
+                    if d.kind == "logical":
+                        out.append(d.node.rhs)
+                        todo.append(d.node.rhs)
+        return Call("__scan__", tuple(out))
 
     def _expand_data_picks(self):
         """`beta.dis[disease[i]]`: an element of a SHORT parameter vector picked by a data index (the factor-level idiom of
@@ -1148,6 +1231,8 @@ class Lowering:
             except LoweringError:
                 firsts = set()
             if firsts == {s.loop_vars[1]}:
+                if _ext_keep(s.extents) is not None:
+                    raise LoweringError("a plate with dropped rows cannot have its loops swapped")
                 s = replace(s, loops=s.loops[::-1], extents=s.extents[::-1])
         lv_names = s.loop_vars
         shape = s.shape
@@ -1756,7 +1841,7 @@ class Lowering:
         # statement's loop nest must be a prefix of the observation's with identical extents
         if len(d.loops) > len(obs.loops) or not d.loops:
             raise LoweringError(f"'{name}': unsupported nesting")
-        if d.extents != obs.extents[:len(d.loops)]:
+        if d.extents != obs.extents[:len(d.loops)] or not np.array_equal(_ext_keep(d.extents), _ext_keep(obs.extents)):
             raise LoweringError(f"'{name}': loop ranges differ from the observation plate's")
         dl = d.node.lhs
         if not isinstance(dl, Index) or len(dl.idx) != len(d.loops) or len(idx) != len(dl.idx):

@@ -222,15 +222,21 @@ def test_partially_observed_with_children_is_refused():
         jbugs.lower(text, {"N": 3, "x": np.array([0.1, np.nan, 0.3]), "y": np.ones(3)})
 
 
-def test_kidney_is_refused_not_mis_evaluated(fixtures):
+def test_kidney_drops_the_rows_without_observations(fixtures):
     """Kidney: b[14], b[19], b[36] have no observed descendants (both of the patient's times are censored = missing), so
-    the reference takes exactly those ELEMENTS out of theta (43 parameters, the oracle agrees); a plate cannot leave
-    holes in a parameter vector, and lowering all 46 would evaluate a different model"""
+    the reference takes exactly those ELEMENTS out of theta: 43 parameters, not 46.  The plate and the statement of b
+    are compacted to the remaining 35 rows."""
     fx = fixtures["kidney"]
-    gm = go.compile(jbugs.examples.KIDNEY, fx["data"], fx["inits"])
+    gm = go.compile(jbugs.examples.KIDNEY, fx["data"], fx["inits"]).use_generated_order()
     assert gm.D == 43 and "b[14]" not in gm.param_names()
-    with pytest.raises(jbugs.LoweringError, match="without any observed cell"):
-        jbugs.lower(jbugs.examples.KIDNEY, fx["data"])
+    plan, lw = jbugs.lower(jbugs.examples.KIDNEY, fx["data"])
+    assert plan.D == 43 and lw.param_names() == gm.param_names()
+    assert (plan.plates[0].N, plan.plates[0].T, plan.plates[0].n_real) == (35, 2, 58)
+    # a row's parameter that also feeds something else cannot be dropped
+    text = jbugs.examples.KIDNEY.replace("sigma <- 1 / sqrt(tau)", "sigma <- 1 / sqrt(tau)\n    for (i in 1:N) { z[i] ~ dnorm(b[i], 1) }")
+    data = dict(fx["data"], z=np.zeros(38))
+    with pytest.raises(jbugs.LoweringError):
+        jbugs.lower(text, data)
 
 
 def test_factor_levels_picked_by_a_data_index():

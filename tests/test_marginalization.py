@@ -239,6 +239,23 @@ def test_random_thetas_node_oracle_vs_plan(name):
     check_c_port(plan, gm, theta)
 
 
+def test_edge_cases_without_latents():
+    """auto_marginalization.jl:592-652: a model without discrete latents, and one whose discrete nodes are all observed,
+    evaluate under the marginalising mode exactly as without it"""
+    text = "model { mu ~ dnorm(0, 0.01)\n sigma ~ dexp(1)\n tau <- 1 / (sigma * sigma)\n for (i in 1:N) { y[i] ~ dnorm(mu, tau) } }"
+    data = {"N": 3, "y": np.array([1.0, 2.0, 3.0])}
+    plan, lw = jbugs.lower(text, data, marginalize=True)
+    plain, _ = jbugs.lower(text, data)
+    assert plan.D == 2 and plan.to_bytes() == plain.to_bytes()
+    text2 = "model { p ~ dbeta(1, 1)\n for (i in 1:N) { x[i] ~ dbern(p) } }"
+    data2 = {"N": 5, "x": np.array([1.0, 0.0, 1.0, 1.0, 0.0])}
+    plan2, _ = jbugs.lower(text2, data2, marginalize=True)
+    assert plan2.D == 1
+    lp, _, st = COracle(plan2).eval_batch(np.zeros((1, 1)))
+    expected = S.beta(1, 1).logpdf(0.5) + 3 * np.log(0.5) + 2 * np.log(0.5) + np.log(0.25)
+    assert st[0] == 0 and lp[0] == pytest.approx(expected, abs=1e-10)
+
+
 def test_unsupported_shapes_raise():
     hmm = """model {
       z[1] ~ dcat(p0[1:2])
