@@ -1097,7 +1097,7 @@ static int ensure_workspace(jbugs_plan* p, long long C) {
             int best = 1;
             double best_eff = 0.0;
             for (int s = 1; s <= 96; ++s) {
-                if (s > 1 && Nloc / s < 8 * DG_BK) break;
+                if (s > 1 && Nloc / s < 8 * DgBwd::BK) break;
                 const long long ctas = out_tiles * s, waves = (ctas + p->num_sms - 1) / p->num_sms;
                 const double eff = (double)ctas / (double)(waves * p->num_sms);
                 if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
@@ -1292,7 +1292,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
             bw.op.M = dn.P; bw.op.N = C; bw.op.K = Nloc;
             bw.op.vec_ok = x_vec;
             bw.Gp = p->d_Gp; bw.ldg = ldg;
-            bw.k_per_split = ((Nloc + p->dense_splits - 1) / p->dense_splits + DG_BK - 1) / DG_BK * DG_BK;
+            bw.k_per_split = ((Nloc + p->dense_splits - 1) / p->dense_splits + DgBwd::BK - 1) / DgBwd::BK * DgBwd::BK;
             dense_bwd_kernel<<<dim3(col_blocks, (unsigned)((dn.P + DG_BM - 1) / DG_BM), (unsigned)p->dense_splits), DgBwd::THREADS, DgBwd::SMEM_BYTES, st>>>(bw);
             p->launches++;
             if (sharded) {

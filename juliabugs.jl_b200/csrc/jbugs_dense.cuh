@@ -22,28 +22,32 @@
 
 namespace jbugs {
 
-constexpr int DG_BN = 128, DG_BK = 16, DG_STAGES = 3;
+#ifndef JB_DENSE_BWD_BK
+#define JB_DENSE_BWD_BK 32  // slab depth of the reverse GEMM (16: round 1; 32 halves the barriers per k)
+#endif
+constexpr int DG_BN = 128, DG_STAGES = 3;
 constexpr int DG_LDB = DG_BN + 4;   // Bs[k][n]
 constexpr int DG_TM = 4, DG_TN = 4;  // MMA tiles per warp (32 x 32 warp tile)
 
 // CTA shape: BM x 128 x 16 with BM / 32 x 4 warps.  The reverse GEMM uses 128 x 128 (16 warps, one CTA per SM: 86 % of
 // the DMMA pipe); the forward GEMM uses 64 x 128 (8 warps, TWO CTAs per SM) so that the FP64 epilogue of one CTA --
 // ~15 % of a tile's time, K = P is short -- runs under the DMMA main loop of the other.
-template <int BM_>
+template <int BM_, int BK_>
 struct DgCfg {
     static constexpr int BM = BM_;
+    static constexpr int BK = BK_;  // depth of one shared-memory slab
     static constexpr int THREADS = (BM_ / 32) * 4 * 32;
     static constexpr int WM = BM_ / 32;
     static constexpr int LDA_M = BM_ + 4;   // As[k][m]   (A is M-major in memory: forward GEMM)
-    static constexpr int LDA_K = DG_BK + 4; // As[m][k]   (A is K-major in memory: reverse GEMM)
-    static constexpr int A_DOUBLES = (DG_BK * LDA_M > BM_ * LDA_K) ? DG_BK * LDA_M : BM_ * LDA_K;
-    static constexpr int STAGE_DOUBLES = A_DOUBLES + DG_BK * DG_LDB;
+    static constexpr int LDA_K = BK_ + 4; // As[m][k]   (A is K-major in memory: reverse GEMM)
+    static constexpr int A_DOUBLES = (BK_ * LDA_M > BM_ * LDA_K) ? BK_ * LDA_M : BM_ * LDA_K;
+    static constexpr int STAGE_DOUBLES = A_DOUBLES + BK_ * DG_LDB;
     static constexpr size_t SMEM_BYTES = (size_t)DG_STAGES * STAGE_DOUBLES * sizeof(double);
-    static constexpr int A_CH = BM_ * DG_BK / 2 / THREADS;    // 16-byte chunks of A per thread and slab
-    static constexpr int B_CH = DG_BK * DG_BN / 2 / THREADS;  // 16-byte chunks of B per thread and slab
+    static constexpr int A_CH = BM_ * BK_ / 2 / THREADS;    // 16-byte chunks of A per thread and slab
+    static constexpr int B_CH = BK_ * DG_BN / 2 / THREADS;  // 16-byte chunks of B per thread and slab
 };
-using DgFwd = DgCfg<64>;
-using DgBwd = DgCfg<128>;
+using DgFwd = DgCfg<64, 16>;
+using DgBwd = DgCfg<128, JB_DENSE_BWD_BK>;
 constexpr int DG_BM = DgBwd::BM;          // row tile of the reverse GEMM (over P)
 constexpr int DG_FWD_BM = DgFwd::BM;      // row tile of the forward GEMM (over observations)
 
@@ -75,15 +79,15 @@ __device__ __forceinline__ void dg_load_stage_edge(const DenseOperands& op, doub
                                                    long long k0, long long k_end, int tid) {
     double* As = stage;
     double* Bs = stage + Cfg::A_DOUBLES;
-    for (int q = tid; q < DG_BK * Cfg::BM; q += Cfg::THREADS) {
-        const int kk = A_MMAJOR ? q / Cfg::BM : q % DG_BK;
-        const int m = A_MMAJOR ? q % Cfg::BM : q / DG_BK;
+    for (int q = tid; q < Cfg::BK * Cfg::BM; q += Cfg::THREADS) {
+        const int kk = A_MMAJOR ? q / Cfg::BM : q % Cfg::BK;
+        const int m = A_MMAJOR ? q % Cfg::BM : q / Cfg::BK;
         double* dst = A_MMAJOR ? As + kk * Cfg::LDA_M + m : As + m * Cfg::LDA_K + kk;
         const bool ok = (m0 + m < op.M) && (k0 + kk < k_end);
         if (ok) cp_async8(dst, A_MMAJOR ? op.A + (m0 + m) + op.lda * (k0 + kk) : op.A + (k0 + kk) + op.lda * (m0 + m));
         else *dst = 0.0;
     }
-    for (int q = tid; q < DG_BK * DG_BN; q += Cfg::THREADS) {
+    for (int q = tid; q < Cfg::BK * DG_BN; q += Cfg::THREADS) {
         const int kk = q / DG_BN, n = q % DG_BN;
         const bool ok = (n0 + n < op.N) && (k0 + kk < k_end);
         if (ok) cp_async8(Bs + kk * DG_LDB + n, op.B + (k0 + kk) * op.ldb + (n0 + n));
@@ -111,7 +115,7 @@ __device__ __forceinline__ DgFastPtrs<Cfg> dg_fast_init(const DenseOperands& op,
             f.a[h] = op.A + (m0 + m) + op.lda * (k0 + kk);
             f.sa[h] = kk * Cfg::LDA_M + m;
         } else {
-            const int m = q / (DG_BK / 2), kk = (q % (DG_BK / 2)) * 2;
+            const int m = q / (Cfg::BK / 2), kk = (q % (Cfg::BK / 2)) * 2;
             f.a[h] = op.A + (k0 + kk) + op.lda * (m0 + m);
             f.sa[h] = m * Cfg::LDA_K + kk;
         }
@@ -123,8 +127,8 @@ __device__ __forceinline__ DgFastPtrs<Cfg> dg_fast_init(const DenseOperands& op,
         f.b[h] = op.B + (k0 + kb) * op.ldb + (n0 + n);
         f.sb[h] = Cfg::A_DOUBLES + kb * DG_LDB + n;
     }
-    f.a_step = A_MMAJOR ? op.lda * DG_BK : DG_BK;
-    f.b_step = op.ldb * DG_BK;
+    f.a_step = A_MMAJOR ? op.lda * Cfg::BK : Cfg::BK;
+    f.b_step = op.ldb * Cfg::BK;
     return f;
 }
 
@@ -149,15 +153,15 @@ __device__ __forceinline__ void dg_mainloop(const DenseOperands& op, double* sme
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;  // (BM / 32) x 4 warps
     const int fr = lane >> 2, fk = lane & 3;  // fragment row / k index
-    const long long nk = (k_end - k_begin + DG_BK - 1) / DG_BK;
+    const long long nk = (k_end - k_begin + Cfg::BK - 1) / Cfg::BK;
     // interior tile with aligned operands: every slab but a ragged last one goes through the fast loader
     const bool interior = op.vec_ok && (m0 + Cfg::BM <= op.M) && (n0 + DG_BN <= op.N) && (((k_begin & 1) == 0) || A_MMAJOR);
-    const long long nk_fast = interior ? (k_end - k_begin) / DG_BK : 0;
+    const long long nk_fast = interior ? (k_end - k_begin) / Cfg::BK : 0;
     DgFastPtrs<Cfg> fp = dg_fast_init<A_MMAJOR, Cfg>(op, m0, n0, k_begin, tid);
     auto load = [&](long long slab) {
         double* stage = smem + (slab % DG_STAGES) * Cfg::STAGE_DOUBLES;
         if (slab < nk_fast) dg_fast_load<Cfg>(fp, stage);
-        else dg_load_stage_edge<A_MMAJOR, Cfg>(op, stage, m0, n0, k_begin + slab * DG_BK, k_end, tid);
+        else dg_load_stage_edge<A_MMAJOR, Cfg>(op, stage, m0, n0, k_begin + slab * Cfg::BK, k_end, tid);
     };
     for (int s = 0; s < DG_STAGES - 1; ++s) {
         if (s < nk) load(s);
@@ -172,7 +176,7 @@ __device__ __forceinline__ void dg_mainloop(const DenseOperands& op, double* sme
         const double* As = smem + (kt % DG_STAGES) * Cfg::STAGE_DOUBLES;
         const double* Bs = As + Cfg::A_DOUBLES;
 #pragma unroll
-        for (int ks = 0; ks < DG_BK / 4; ++ks) {
+        for (int ks = 0; ks < Cfg::BK / 4; ++ks) {
             double a[DG_TM], b[DG_TN];
 #pragma unroll
             for (int tm = 0; tm < DG_TM; ++tm) {
