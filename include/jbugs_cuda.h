@@ -168,7 +168,9 @@ int jbugs_plan_describe(const jbugs_plan* plan, char* buf, size_t nbuf);
  * kernel headers are embedded in this library, so neither nvcc nor a source tree is needed).  Cubins are cached
  * in `cache_dir` (NULL: $JBUGS_JIT_CACHE, $XDG_CACHE_HOME/jbugs_jit or ~/.cache/jbugs_jit; "none": no cache),
  * created 0700 and used only if owned by the caller and not writable by others.  Returns JBUGS_ERR_UNSUPPORTED
- * when libnvrtc cannot be loaded; nothing changes then.  jbugs_jit_last_compile_seconds: time NVRTC took in
+ * when libnvrtc cannot be loaded; nothing changes then.  Tiered: the call returns with a quick-to-compile variant of
+ * each kernel (~3 s cold) and a worker thread compiles the best variant, which takes over at a later evaluation
+ * (jbugs_plan_describe shows `..._quick_variant` until then).  jbugs_jit_last_compile_seconds: time NVRTC took in
  * the last call (0 when every kernel came from the cache). */
 int jbugs_plan_specialize(jbugs_plan* plan, const char* cache_dir);
 double jbugs_jit_last_compile_seconds(void);

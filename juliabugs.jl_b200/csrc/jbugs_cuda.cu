@@ -98,6 +98,7 @@ struct PlateRt {
 };
 static cudaError_t jit_launch(JitKernels& jk, JBUGS_LAUNCH_PARAMS);
 static void jit_free(JitKernels* jk);
+static bool jit_is_best(const JitKernels* jk);
 struct JitJob;
 static void jit_job_free(JitJob* j);
 static int jit_poll(jbugs_plan* p);
@@ -127,6 +128,9 @@ struct jbugs_plan_s {
     std::vector<char> uploaded;
     std::vector<PlateRt> rt;
     JitJob* jit_job = nullptr;  // asynchronous run-time specialisation under way (jbugs_jit.inc)
+    std::vector<struct JitKernels*> jit_retired;  // quick variants replaced by better ones (unloaded with the plan)
+    std::string jit_cache_dir;  // cache directory of the last specialise call (the background upgrade uses the same)
+    bool jit_cache_dir_set = false;
     std::vector<long long> shard_i0, shard_i1;
     std::vector<char> shard_set;  // jbugs_plan_set_shard was called for the plate (else it is replicated on every rank)
     GlobalsParams gp{};
@@ -723,6 +727,7 @@ extern "C" int jbugs_plan_destroy(jbugs_plan* p) {
     jbugs_comm_destroy(p);
     for (void* d : p->d_slots) cudaFree(d);
     jit_job_free(p->jit_job);  // (waits for the worker thread)
+    for (auto* jk : p->jit_retired) jit_free(jk);
     for (auto& r : p->rt) {
         cudaFree(r.d_xtape);
         jit_free(r.jit);
@@ -885,7 +890,8 @@ extern "C" int jbugs_plan_describe(const jbugs_plan* p, char* buf, size_t nbuf) 
         const auto& r = p->rt[k];
         snprintf(line, sizeof line, "plate %zu: N=%lld T=%lld kernel=%s tiles=%lld tile=%lld gref=%d\n", k, r.pp.v.N, r.pp.v.T,
                  ((r.variant == 0 || r.variant == g_xspec) && r.jit && r.jit_valid && !p->force_dynamic)
-                     ? (r.variant == 0 ? "specialised_at_run_time" : "expression_tape_specialised_at_run_time") : spec_name(r.variant),
+                     ? (r.variant == 0 ? (jit_is_best(r.jit) ? "specialised_at_run_time" : "specialised_at_run_time_quick_variant")
+                                       : "expression_tape_specialised_at_run_time") : spec_name(r.variant),
                  r.n_tiles, r.pp.v.tile, r.pp.sh.n_gref);
         s += line;
     }

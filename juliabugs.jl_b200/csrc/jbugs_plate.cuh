@@ -640,6 +640,41 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
 // cp.async.bulk + mbarrier where aligned (a separate instantiation: the cp.async-only kernel carries none of it)
 // GRAD = false: a forward-only instantiation for `logdensity` without the gradient (the adjoint arithmetic is dead
 // code then and the kernel reads theta only); built for the large-plate specs, selected when want_grad == 0
+__device__ __forceinline__ void copy_chain_state(ChainState& d, const ChainState& s) {
+#pragma unroll
+    for (int k = 0; k < MAX_GREF; ++k) { d.gv[k] = s.gv[k]; d.ga[k] = s.ga[k]; }
+#pragma unroll
+    for (int l = 0; l < MAX_LOC; ++l) {
+        d.lx[l] = s.lx[l]; d.la[l] = s.la[l]; d.pre_lg[l] = s.pre_lg[l]; d.pre_dg[l] = s.pre_dg[l]; d.pre_lb[l] = s.pre_lb[l];
+    }
+    d.sat = s.sat;
+}
+__device__ __forceinline__ void copy_fused_acc(FusedAcc& d, const FusedAcc& s) {
+    d.ss = s.ss;
+#pragma unroll
+    for (int t = 0; t < MAX_GT; ++t) d.sg[t] = s.sg[t];
+#pragma unroll
+    for (int l = 0; l < MAX_LOC; ++l) { d.pss[l] = s.pss[l]; d.ps[l] = s.ps[l]; d.pd[l] = s.pd[l]; }
+}
+
+// one group of a short last block (see plate_body): everything the group loop carries, by value
+struct TailState {
+    ChainState st;
+    FusedAcc fa;
+    double lp;
+    long long pos[MAX_LOC];
+    bool bad;
+};
+template <class S>
+__device__ __noinline__ TailState tail_group(const PlateParams& P, StageView sv, int g, long long i, int T, const double* __restrict__ th,
+                                             double* __restrict__ gr, long long ld, bool store, double obs_tau, TailState ts) {
+    const S sp(P.sh);
+    GroupLoads<1, PreObs<S>::TS> one;
+    load_groups<S, 1>(sp, P.v, i, th, ld, ts.pos, one);
+    ts.bad |= eval_groups<S, 1>(sp, P.v, sv, g, i, T, th, gr, ld, store, obs_tau, ts.pos, one, ts.st, ts.fa, ts.lp);
+    return ts;
+}
+
 // the body of plate_kernel: one CTA = BLK chains x tile `tile` of the plate's groups (also the middle part of
 // fused_small_kernel, jbugs_kernels.cuh)
 template <class S, int BLK, bool TMA, bool GRAD>
@@ -777,12 +812,34 @@ __device__ __forceinline__ void plate_body(const PlateParams& P, const double* _
                 bad |= eval_groups<S, U>(sp, V, sv, g, i, T, th, gr, ld, store, obs_tau, pos, gl_cur, st, fa, lp);
             }
         }
+#if !defined(__CUDACC_RTC__) || defined(JB_INLINE_TAIL)
         if (U > 1)
             for (; g < cnt; ++g) {
                 GroupLoads<1, PreObs<S>::TS> one;
                 load_groups<S, 1>(sp, V, i0 + g, th, ld, pos, one);
                 bad |= eval_groups<S, 1>(sp, V, sv, g, i0 + g, T, th, gr, ld, store, obs_tau, pos, one, st, fa, lp);
             }
+#else
+        if (U > 1 && g < cnt) {
+            // run-time compiled kernels (NVRTC): the groups of a short last block go one at a time through a NON-inlined
+            // copy of the body, state by value (the hot loop's registers stay registers).  A second inlined copy of the
+            // body cost NVVM 9 of the 12 s a kernel took to compile; the in-tree kernels keep it (their ptxas budgets are
+            // pinned by a test, and nobody waits for their compilation)
+            // (element by element: an aggregate copy of `st` / `fa` would keep the hot loop's state in local memory)
+            TailState ts;
+            copy_chain_state(ts.st, st);
+            copy_fused_acc(ts.fa, fa);
+            ts.lp = lp; ts.bad = bad;
+#pragma unroll
+            for (int l = 0; l < MAX_LOC; ++l) ts.pos[l] = pos[l];
+            for (; g < cnt; ++g) ts = tail_group<S>(P, sv, g, i0 + g, T, th, gr, ld, store, obs_tau, ts);
+            copy_chain_state(st, ts.st);
+            copy_fused_acc(fa, ts.fa);
+            lp = ts.lp; bad = ts.bad;
+#pragma unroll
+            for (int l = 0; l < MAX_LOC; ++l) pos[l] = ts.pos[l];
+        }
+#endif
         // the next chunk (issued at the top of this iteration) must have landed before it is read; the barrier also
         // protects the stage just consumed from the refill issued at the top of the next iteration
         stage_ok &= stage_wait<TMA>(next_bulk, &mbar[cur ^ 1], (parity_bits >> (cur ^ 1)) & 1u);

@@ -9,7 +9,7 @@ data, alpha, beta = synth_rats(N)
 data["z"] = np.random.default_rng(3).standard_normal(N)
 text = jbugs.examples.RATS.replace("mu[i, j] <- alpha[i] + beta[i] * (x[j] - xbar)", "mu[i, j] <- alpha[i] + beta[i] * (x[j] - xbar) + gam * z[i]") \
                           .replace("alpha0 <- alpha.c - xbar * beta.c", "alpha0 <- alpha.c - xbar * beta.c\n    gam ~ dnorm(0.0, 1.0E-2)")
-m = jbugs.compile(text, data)
+m = jbugs.compile(text, data, evaluation_mode=jbugs.UseCUDABatch(specialize=False))
 cp = m.cuda
 D = m.plan.D
 names = m.lowering.param_names(limit=10)[:8] if False else None
@@ -31,6 +31,14 @@ def run(tag, reps):
     print(tag, cp.describe().splitlines()[1].split("kernel=")[1].split()[0], "%.2f ms" % (dt * 1e3), "%.3e obs-evals/s" % (5 * N * C / dt), "hbm frac %.3f" % (16.0 * C * D / dt / 6457.4e9))
     return lp.clone()
 a = run("interpreter ", 2)
-t = time.time(); cp.specialize(); print("specialise: %.1f s" % (time.time() - t))
+t = time.time(); cp.specialize("none"); print("specialise: %.1f s" % (time.time() - t))
 b2 = run("specialised ", 10)
 print("max rel diff of logp", float(((a - b2).abs() / a.abs()).max()), "all finite", bool(torch.isfinite(b2).all()))
+# the best variant arrives from the worker thread: eval_raw with flags = 0 is the polling entry point
+t = time.time()
+while "quick_variant" in cp.describe() and time.time() - t < 120:
+    time.sleep(0.5)
+    cp.eval_raw(theta.data_ptr(), ld, C, 0, lp.data_ptr(), grad.data_ptr(), st.data_ptr(), True, 0, None)
+print("best variant adopted after %.1f s" % (time.time() - t))
+b3 = run("upgraded    ", 10)
+print("max rel diff of logp", float(((a - b3).abs() / a.abs()).max()))

@@ -59,9 +59,19 @@ def test_cold_compile_time_and_cache(tmp_path):
     assert "specialised_at_run_time" in cp.describe()
     assert cp.last_compile_seconds() > 0.0
     print(f"cold specialisation: {cold:.2f} s (NVRTC {cp.last_compile_seconds():.2f} s)")
-    assert cold < 60.0, f"cold specialisation took {cold:.2f} s"   # NVVM's optimiser on the unrolled kernel body; see DESIGN
+    assert cold < 5.0, f"cold specialisation took {cold:.2f} s"   # (2.8 s measured: the quick variant, three widths in parallel)
+    theta0 = random_thetas(np.zeros(m.plan.D), 130, seed=2, scale=0.05)
+    _check(cp, COracle(m.plan), theta0)                              # the quick variant is a correct kernel in its own right
     assert stat.S_IMODE(os.stat(cache).st_mode) == 0o700
-    assert len(list(cache.glob("plate_*.cubin"))) == 3
+    assert len(list(cache.glob("plate_*.cubin"))) >= 3
+    # tiered: the call returned with the quick-to-compile variant (non-inlined remainder groups); the best variant is
+    # compiled on a worker thread and takes over at a later evaluation
+    deadline = time.perf_counter() + 120
+    while "quick_variant" in cp.describe() and time.perf_counter() < deadline:
+        time.sleep(0.25)
+        cp.eval_host(np.zeros((m.plan.D, 8)))
+    assert "quick_variant" not in cp.describe() and "specialised_at_run_time" in cp.describe()
+    assert len(list(cache.glob("plate_*.cubin"))) == 6
     theta = random_thetas(np.zeros(m.plan.D), 130, seed=2, scale=0.05)
     _check(cp, COracle(m.plan), theta)
     m2 = jbugs.compile(text, data)
