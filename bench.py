@@ -520,7 +520,8 @@ def e2e(ctx, args, cp, theta, grad, lp_host, n_obs, D, C, K):
     from jbugs import cuda as jcuda
     dist, world, dev = ctx.dist, ctx.world, ctx.dev
     stream = ctx.stream.cuda_stream
-    Ce = min(args.e2e_chains or (1024 if world == 1 else 512), C)
+    # slab size: 2 x 16 GB of pinned host memory per rank at one GPU; less per rank when several ranks share the host
+    Ce = min(args.e2e_chains or (1024 if world == 1 else (512 if world == 2 else 256)), C)
     while Ce > 64 and 2 * 8 * D * Ce > (40 << 30):
         Ce //= 2
     n_slabs = (C + Ce - 1) // Ce

@@ -49,6 +49,12 @@ def cases():
     X = np.asfortranarray(rng.standard_normal((300, 7)))
     y = (rng.random(300) < 0.5).astype(float)
     yield "dense_logistic_300x7", jbugs.examples.DENSE_LOGISTIC, {"N": 300, "P": 7, "X": X, "y": y}, {}
+    # marginalised plates (has_obs == 3): the reference's mixture test models (J/test/model/auto_marginalization.jl)
+    import test_marginalization as tm
+    yield "gmm2_marginalised", tm.GMM2 % (0.3, 0.7), {"N": 4, "y": np.array([-1.5, 2.3, -2.1, 1.8])}, {"marginalize": True}
+    yield "gmm3_marginalised", tm.GMM3, {"N": 3, "y": np.array([-2.5, 0.5, 3.2])}, {"marginalize": True}
+    yield "gmm_partially_observed_latent", tm.GMM_SHARED, {"N": 4, "y": np.array([1.0, 2.0, -1.0, 3.0]),
+                                                          "z": np.array([2.0, np.nan, 1.0, np.nan])}, {"marginalize": True}
 
 
 def record(plan, lw):
