@@ -164,8 +164,8 @@ class ClockSampler:
 def cpu_baseline(plan, th0, n_obs, budget_s=15.0, seed=7, cores=None):
     """the C restatement of the reference evaluator on the host cores, one chain per thread."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    from c_oracle import COracle
-    co = COracle(plan)
+    from c_oracle import COracle, native_lib
+    co = COracle(plan, native=True)   # compiled here with -O3 -march=native: the strongest build of the port
     # every host core this process may run on; not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
     if cores is None:
         try:
@@ -189,8 +189,8 @@ def cpu_baseline(plan, th0, n_obs, budget_s=15.0, seed=7, cores=None):
         C = cores
     return {"value": n_obs * C / t1, "unit": UNIT, "cores": cores, "kind": "port", "seconds": t1,
             "sample": f"{C} chains x {n_obs} obs, one chain per thread, {t1:.2f} s",
-            "note": "C restatement of the reference's generated evaluator (oracle/jbugs_oracle.c, gcc -O2 "
-                    "-ffp-contract=off, analytic gradient) -- NOT JuliaBUGS + Mooncake itself (Julia is not installed)"}
+            "note": "C restatement of the reference's generated evaluator (oracle/jbugs_oracle.c, " + native_lib()[1] +
+                    ", analytic gradient) -- NOT JuliaBUGS + Mooncake itself (Julia is not installed)"}
 
 
 # ----------------------------------------------------------------------------------- one workload on the GPU(s)

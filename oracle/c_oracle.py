@@ -27,7 +27,12 @@ def build(force=False):
 def lib():
     global _LIB
     if _LIB is None:
-        L = ctypes.CDLL(build())
+        _LIB = _bind(ctypes.CDLL(build()))
+    return _LIB
+
+
+def _bind(L):
+    if True:
         L.jbo_plan_create.restype = ctypes.c_void_p
         L.jbo_plan_create.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
         L.jbo_plan_destroy.argtypes = [ctypes.c_void_p]
@@ -38,15 +43,35 @@ def lib():
         L.jbo_eval_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.jbo_max_threads.restype = ctypes.c_int
-        _LIB = L
-    return _LIB
+    return L
+
+
+_NATIVE = None
+NATIVE_FLAGS = ["-O3", "-march=native", "-fPIC", "-fopenmp", "-std=gnu11", "-fno-fast-math"]
+
+
+def native_lib():
+    """the same source compiled ON THIS MACHINE with -O3 -march=native (FMA contraction allowed): the strongest build of
+    the CPU port, used only as bench.py's timed baseline (the checker stays the strict -O2 -ffp-contract=off build, whose
+    results do not depend on the host).  Falls back to the checker build when there is no compiler."""
+    global _NATIVE
+    if _NATIVE is None:
+        import tempfile
+        try:
+            out = os.path.join(tempfile.mkdtemp(prefix="jbugs_oracle_native_"), "libjbugs_oracle_native.so")
+            subprocess.check_call(["gcc"] + NATIVE_FLAGS + ["-shared", "-o", out, os.path.join(_HERE, "jbugs_oracle.c"), "-lm"],
+                                  stderr=subprocess.DEVNULL)
+            _NATIVE = (_bind(ctypes.CDLL(out)), " ".join(["gcc"] + NATIVE_FLAGS))
+        except Exception:
+            _NATIVE = (lib(), "gcc -O2 -ffp-contract=off (no compiler on this box for the native build)")
+    return _NATIVE
 
 
 class COracle:
     """Evaluates a `jbugs.plan.Plan` on the CPU, one theta per thread."""
 
-    def __init__(self, plan):
-        self.L = lib()
+    def __init__(self, plan, native=False):
+        self.L = native_lib()[0] if native else lib()
         blob = plan.to_bytes()
         self._blob = ctypes.create_string_buffer(blob, len(blob))
         self.h = self.L.jbo_plan_create(self._blob, len(blob))
