@@ -41,7 +41,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "logdensity+gradient obs-evals/s"
 UNIT = "obs-evals/s"
-DEFAULT_CHAINS = {"rats": 4096, "seeds": 256, "pumps": 8192, "epil": 8192, "dense": 1024}
+DEFAULT_CHAINS = {"rats": 4096, "seeds": 256, "pumps": 8192, "epil": 8192, "dense": 1024, "rats_variant": 1024, "mixture": 1024}
 
 
 def log(*a):
@@ -93,6 +93,47 @@ def make_workload(name, groups, dev=None):
         y = yd.cpu().numpy()
         X = np.empty((Pn, N), dtype=np.float64).T  # placeholder (never touched): shape and layout only
         return ex.DENSE_LOGISTIC, {"N": N, "P": Pn, "X": X, "y": y}, th0, desc, {"dense|X": Xd}
+    if name == "rats_variant":
+        # a model WITHOUT an in-tree kernel (the Rats plate with one more regression term on a group-level covariate):
+        # it runs the interpreter until run-time specialisation (NVRTC, tiered) has compiled its kernel
+        N = groups or 1_000_000
+        data, alpha, beta = synth_rats(N)
+        data["z"] = np.random.default_rng(7).standard_normal(N)
+        text = ex.RATS.replace("mu[i, j] <- alpha[i] + beta[i] * (x[j] - xbar)", "mu[i, j] <- alpha[i] + beta[i] * (x[j] - xbar) + gam * z[i]")
+        text = text.replace("alpha.c ~ dnorm(0.0, 1.0E-6)", "alpha.c ~ dnorm(0.0, 1.0E-6)\n    gam ~ dnorm(0.0, 0.01)")
+        import jbugs
+        names = jbugs.lower(text, {k: (v[:4] if isinstance(v, np.ndarray) and v.shape[:1] == (N,) else v) for k, v in dict(data, N=4).items()})[1].param_names()
+        ng = sum(1 for n in names if "[" not in n)
+        th0 = np.empty(2 * N + ng)
+        start = {"beta.tau": np.log(4.0), "beta.c": 6.2, "alpha.tau": np.log(1 / 196.0), "alpha.c": 242.0, "tau.c": np.log(1 / 36.0), "gam": 0.0}
+        th0[:ng] = [start[n] for n in names[:ng]]
+        first = names[ng].split("[")[0]
+        th0[ng::2] = beta if first == "beta" else alpha
+        th0[ng + 1::2] = alpha if first == "beta" else beta
+        return text, data, th0, f"rats + one regression term (no in-tree kernel; specialised at run time) N={N} T=5", {}
+    if name == "mixture":
+        # two-component normal mixture, the discrete latents summed out inside an expression-tape kernel (compiled at run time)
+        N = groups or 2_000_000
+        rng = np.random.default_rng(2)
+        z = rng.random(N) < 0.3
+        y = np.where(z, rng.normal(-2, 1.0, N), rng.normal(2, 0.7, N))
+        text = """model {
+  w[1] <- 0.3
+  w[2] <- 0.7
+  mu[1] ~ dnorm(-2, 0.04)
+  mu[2] ~ dnorm(2, 0.04)
+  sigma[1] ~ dexp(1)
+  sigma[2] ~ dexp(1)
+  for (k in 1:2) { tau[k] <- 1 / (sigma[k] * sigma[k]) }
+  for (i in 1:N) {
+    z[i] ~ dcat(w[1:2])
+    y[i] ~ dnorm(mu[z[i]], tau[z[i]])
+  }
+}"""
+        import jbugs
+        names = jbugs.lower(text, {"N": 4, "y": y[:4]}, marginalize=True)[1].param_names()
+        start = {"sigma[1]": 0.0, "sigma[2]": np.log(0.7), "mu[2]": 2.0, "mu[1]": -2.0}
+        return text, {"N": N, "y": y}, np.array([start[n] for n in names]), f"normal mixture, latents summed out (tape kernel compiled at run time) N={N}", {}
     if name in ("pumps", "epil"):
         # BASELINE.json config 5: the shipped fixtures, a large ensemble of independent chains (chain-sharded)
         fx = json.load(open(os.path.join(ROOT, "tests", "golden", "examples_vol1.json")))[name]
@@ -226,13 +267,13 @@ def measure(name, ctx, args, K, W, C, primary):
     shard = (args.shard if primary and args.shard else {"seeds": "obs", "dense": "obs"}.get(name, "chains"))
     model_text, data, th0, desc, dev_slots = make_workload(name, args.groups if primary else 0, dev)
     t0 = time.time()
-    model = jbugs.compile(model_text, data)
+    model = jbugs.compile(model_text, data, evaluation_mode=(jbugs.UseAutoMarginalization(device=ctx.local_rank, specialize=False)
+                                                             if name == "mixture" else jbugs.UseCUDABatch(device=ctx.local_rank, specialize=False)))
     plan = model.plan
     n_obs = plan.n_obs()
     D = plan.D
     log(f"[bench] lowered {desc}: D={D} obs={n_obs} in {time.time() - t0:.1f}s")
     obs_sharded = shard == "obs" and world > 1
-    model = jbugs.set_evaluation_mode(model, jbugs.UseCUDABatch(device=ctx.local_rank))
     cp = jcuda.CudaPlan(plan, device=ctx.local_rank, upload=False)
     model._cuda = cp
     for k, slot in enumerate(plan.data):
@@ -253,6 +294,13 @@ def measure(name, ctx, args, K, W, C, primary):
         for kv in filter(None, args.opt.split(",")):
             k, v = kv.split("=")
             cp.set_option(k, int(v))
+    jit = None
+    if name in ("rats_variant", "mixture"):
+        # run-time specialisation, tiered: the call returns with the quick variant, the best one follows from a worker thread
+        t_j = time.time()
+        cp.specialize("none")
+        t_quick = time.time() - t_j
+        jit = {"quick_variant_s": t_quick, "nvrtc_s": cp.last_compile_seconds()}
     local_groups = [pl.N for pl in plan.plates]
     dense_rows = plan.dense[0].N if plan.dense else 0
     if obs_sharded:
@@ -298,6 +346,15 @@ def measure(name, ctx, args, K, W, C, primary):
         cp.eval_raw(theta.data_ptr(), ld, C, 0, logp.data_ptr(), grad.data_ptr(), status.data_ptr(), want_grad, flags, stream)
 
     step(0)  # first call also builds the one-off data constants
+    if jit is not None:
+        # wait for the best variant before anything is timed (a synchronous evaluation is the adoption point)
+        t_j = time.time()
+        while "quick_variant" in cp.describe() and time.time() - t_j < 90:
+            time.sleep(0.25)
+            step(0)
+        jit["best_variant_after_s"] = time.time() - t_j
+        jit["kernel"] = cp.describe().splitlines()[1].split("kernel=")[1].split()[0]
+        config["run_time_specialisation"] = jit
     log("[bench] " + cp.describe().replace("\n", " | "))
     for _ in range(W):
         step(0)
@@ -604,7 +661,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configurations")
-    ap.add_argument("--secondary", default="seeds,dense,pumps,epil")
+    ap.add_argument("--secondary", default="seeds,dense,pumps,epil,rats_variant,mixture")
     ap.add_argument("--dynamic", type=int, default=0, help="1 = force the interpreter kernel")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--tma", type=int, default=-1, help="0 = stage plate data with cp.async only (A/B against the TMA path)")
@@ -690,7 +747,7 @@ def main():
     if not args.no_secondary and not args.groups and not args.chains:
         sec = []
         for nm in [s for s in args.secondary.split(",") if s and s != args.workload]:
-            Ks = {"seeds": 20, "dense": 3, "pumps": 50, "epil": 50}.get(nm, 10)
+            Ks = {"seeds": 20, "dense": 3, "pumps": 50, "epil": 50, "rats_variant": 40, "mixture": 10}.get(nm, 10)
             try:
                 o, _, _, _ = measure(nm, ctx, args, Ks, 3, DEFAULT_CHAINS[nm], primary=False)
                 sec.append({k: o[k] for k in ("value", "unit", "ms_per_step", "ms_per_step_p50", "ms_per_step_p95", "steps",
