@@ -724,6 +724,7 @@ extern "C" int jbugs_comm_destroy(jbugs_plan* p) {
 extern "C" int jbugs_plan_destroy(jbugs_plan* p) {
     if (!p) return JBUGS_OK;
     cudaSetDevice(p->device);
+    cudaDeviceSynchronize();  // asynchronous evaluations may still be running on the plan's buffers and kernels
     jbugs_comm_destroy(p);
     for (void* d : p->d_slots) cudaFree(d);
     jit_job_free(p->jit_job);  // (waits for the worker thread)

@@ -289,3 +289,28 @@ def test_logprior_loglikelihood_and_temperature(fixtures, name):
     assert rel_err(lpt, lp1) < 1e-13 and grad_err(gt, g1) < 1e-12
     r1 = jbugs.evaluate_with_values(m, theta[:, 0], temperature=T)
     assert r1["tempered_logjoint"] == pytest.approx(r1["logprior"] + T * r1["loglikelihood"], rel=1e-14)
+
+
+def test_asynchronous_host_calls_run_as_one_pipeline(fixtures):
+    """JBUGS_EVAL_ASYNC with HOST buffers: consecutive calls only enqueue (copy-in / kernels / copy-out of one call overlap
+    the next); after jbugs_plan_synchronize every call's results are in its own host buffers and equal the blocking call's"""
+    import ctypes
+    from helpers import synth_rats
+    data, alpha, beta = synth_rats(3000)
+    m = jbugs.compile(jbugs.examples.RATS, data)
+    cp = m.cuda
+    D = m.plan.D
+    th0 = np.zeros(D)
+    th0[:5] = [np.log(4.0), 6.2, np.log(1 / 196.0), 242.0, np.log(1 / 36.0)]
+    th0[5::2], th0[6::2] = beta, alpha
+    C = 96
+    thetas = [np.ascontiguousarray(random_thetas(th0, C, seed=s, scale=0.05)) for s in range(3)]
+    want = [cp.eval_host(t, layout="chain_fast") for t in thetas]
+    lps = [np.full(C, np.nan) for _ in thetas]
+    grads = [np.full((D, C), np.nan) for _ in thetas]
+    sts = [np.full(C, -1, dtype=np.int32) for _ in thetas]
+    for t, lp, g, st in zip(thetas, lps, grads, sts):
+        cp.eval_raw(t.ctypes.data, C, C, 0, lp.ctypes.data, g.ctypes.data, st.ctypes.data, True, 1, None)
+    cp.synchronize()
+    for (lp0, g0, st0), lp, g, st in zip(want, lps, grads, sts):
+        assert np.array_equal(lp, lp0) and np.array_equal(g, g0) and np.array_equal(st, st0)
