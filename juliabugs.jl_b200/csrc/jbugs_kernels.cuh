@@ -130,7 +130,13 @@ struct DynSpec {
     static constexpr bool STATIC = false;
     static constexpr int FUSED = 0;
     static constexpr int UNROLL = 1;
-    static constexpr int MIN_BLOCKS = 2;
+    // occupancy of the interpreter (round 2 A/B, profiles/r2_interp_ab.txt): 4 CTAs of 128 per SM at 128 registers with
+    // ~600 bytes of spills beat 2 CTAs at 254 registers -- Rats variant 10^6 x 5 x 1024: 468 -> 299 ms, Epil 8192 chains
+    // 392 -> 260 us, Pumps 47.6 -> 49.3 us; 6 and 8 CTAs lose again (309 / 322 ms)
+#ifndef JB_DYN_MINB
+#define JB_DYN_MINB 4
+#endif
+    static constexpr int MIN_BLOCKS = JB_DYN_MINB;
     static constexpr int T_STATIC = 0;  // inner extent read at run time
     static constexpr bool PREFETCH = false;
     static constexpr bool OBS_LOCALS = true;  // unknown at compile time
@@ -172,6 +178,7 @@ struct DynSpec {
 // per-thread value / adjoint arrays of the tape -- 2 KB of local memory -- are not part of every interpreter launch)
 struct XSpec : DynSpec {
     static constexpr bool XTAPE = true;
+    static constexpr int MIN_BLOCKS = 2;  // (the tape's value / adjoint arrays live in local memory anyway: keep the registers)
     __device__ __forceinline__ explicit XSpec(const PlateShape& sh) : DynSpec(sh) {}
     __device__ __forceinline__ int n_x() const { return s.n_x; }
     __device__ __forceinline__ int n_states() const { return s.n_states; }

@@ -8,6 +8,7 @@ C = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 for name, text in (("pumps", jbugs.examples.PUMPS), ("epil", jbugs.examples.EPIL)):
     m = jbugs.compile(text, arr(fx[name]["data"]), arr(fx[name]["inits"]))
     cp = m.cuda
+    if __import__("os").environ.get("JB_DYNAMIC"): cp.set_option("dynamic", 1)
     D = m.plan.D
     th0 = jbugs.getparams(m); th0 = np.where(np.isfinite(th0), th0, 0.0)
     theta = torch.from_numpy(th0)[:, None].cuda() + 0.02 * torch.randn((D, C), dtype=torch.float64, device='cuda')
