@@ -99,3 +99,52 @@ def test_dense_full_width_gemm_tiles():
     logp, status, theta, grad, desc = _device_eval(m, th0, C, seed=7, scale=0.02)
     assert (status == 0).all() and np.all(np.isfinite(logp))
     _compare_sample(m, theta, grad, logp, [0, 127])
+
+
+def test_generic_models_at_full_size_through_run_time_specialisation():
+    """the two bench workloads WITHOUT an in-tree kernel, at the sizes bench.py times them (128-wide CTAs), on the kernels
+    that run-time specialisation compiles: a Rats plate with one more regression term (quick variant first, then the best
+    one from the worker thread -- both checked) and a mixture whose latents are summed out by a compiled tape kernel"""
+    import time
+    import torch
+    from scipy import stats as S
+    from scipy.special import logsumexp
+    sys_path = __import__("sys").path
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    if root not in sys_path:
+        sys_path.insert(0, root)
+    import bench
+    # ---- Rats variant, 10^6 x 5 x 128 chains
+    text, data, th0, _, _ = bench.make_workload("rats_variant", 0)
+    m = jbugs.compile(text, data, evaluation_mode=jbugs.UseCUDABatch(specialize=False))
+    m.cuda.specialize("none")
+    logp, status, theta, grad, desc = _device_eval(m, th0, 128, seed=5, scale=0.02)
+    assert "specialised_at_run_time" in desc and (status == 0).all()
+    _compare_sample(m, theta, grad, logp, [0, 127])
+    deadline = time.time() + 120
+    while "quick_variant" in m.cuda.describe() and time.time() < deadline:
+        time.sleep(0.5)
+        m.cuda.eval_host(np.ascontiguousarray(theta[:, :2].cpu().numpy()))
+    assert "quick_variant" not in m.cuda.describe()
+    logp2, status2, theta2, grad2, desc2 = _device_eval(m, th0, 128, seed=5, scale=0.02)
+    assert rel_err(logp2, logp) < 1e-13          # the two variants are the same arithmetic in the same order
+    _compare_sample(m, theta2, grad2, logp2, [1, 64])
+    del theta, grad, theta2, grad2
+    torch.cuda.empty_cache()
+    # ---- mixture, 2 * 10^6 observations x 128 chains: closed form (log-sum-exp over components per observation)
+    text, data, th0, _, _ = bench.make_workload("mixture", 0)
+    mm = jbugs.compile(text, data, evaluation_mode=jbugs.UseAutoMarginalization(specialize=False))
+    mm.cuda.specialize("none")
+    logp, status, theta, grad, desc = _device_eval(mm, th0, 128, seed=6, scale=0.02)
+    assert "expression_tape_specialised_at_run_time" in desc and (status == 0).all()
+    names = mm.lowering.param_names()
+    ix = {n: i for i, n in enumerate(names)}
+    y = data["y"]
+    for c in (0, 77):
+        th = theta[:, c].cpu().numpy()
+        mu = [th[ix["mu[1]"]], th[ix["mu[2]"]]]
+        sg = [np.exp(th[ix["sigma[1]"]]), np.exp(th[ix["sigma[2]"]])]
+        ll = logsumexp(np.stack([np.log(w) + S.norm(mu[k], sg[k]).logpdf(y) for k, w in enumerate((0.3, 0.7))]), axis=0).sum()
+        pr = S.norm(-2, 5).logpdf(mu[0]) + S.norm(2, 5).logpdf(mu[1]) + sum(S.expon().logpdf(s) + np.log(s) for s in sg)
+        assert logp[c] == pytest.approx(ll + pr, rel=1e-11)
+    _compare_sample(mm, theta, grad, logp, [3, 100])
