@@ -770,6 +770,8 @@ __device__ __forceinline__ void plate_body(const PlateParams& P, const double* _
     int cur = 0;
     GroupLoads<U, PreObs<S>::TS> gl_cur;
     bool have_cur = false;
+    int tail_g = 0, tail_cnt = 0, tail_stage = 0;  // (run-time compiled kernels: remainder groups of the last chunk)
+    long long tail_i0 = 0;
     // SMPF: two [U][MAX_LOC][BLK] tables behind the staging buffers
     double* const pf_base = stage0 + 2 * stage_doubles;
     int pf_cur = 0;
@@ -820,25 +822,9 @@ __device__ __forceinline__ void plate_body(const PlateParams& P, const double* _
                 bad |= eval_groups<S, 1>(sp, V, sv, g, i0 + g, T, th, gr, ld, store, obs_tau, pos, one, st, fa, lp);
             }
 #else
-        if (U > 1 && g < cnt) {
-            // run-time compiled kernels (NVRTC): the groups of a short last block go one at a time through a NON-inlined
-            // copy of the body, state by value (the hot loop's registers stay registers).  A second inlined copy of the
-            // body cost NVVM 9 of the 12 s a kernel took to compile; the in-tree kernels keep it (their ptxas budgets are
-            // pinned by a test, and nobody waits for their compilation)
-            // (element by element: an aggregate copy of `st` / `fa` would keep the hot loop's state in local memory)
-            TailState ts;
-            copy_chain_state(ts.st, st);
-            copy_fused_acc(ts.fa, fa);
-            ts.lp = lp; ts.bad = bad;
-#pragma unroll
-            for (int l = 0; l < MAX_LOC; ++l) ts.pos[l] = pos[l];
-            for (; g < cnt; ++g) ts = tail_group<S>(P, sv, g, i0 + g, T, th, gr, ld, store, obs_tau, ts);
-            copy_chain_state(st, ts.st);
-            copy_fused_acc(fa, ts.fa);
-            lp = ts.lp; bad = ts.bad;
-#pragma unroll
-            for (int l = 0; l < MAX_LOC; ++l) pos[l] = ts.pos[l];
-        }
+        // run-time compiled kernels (NVRTC): the groups of a short last block (only the LAST chunk of a tile can have one)
+        // are evaluated after the chunk loop, see below
+        if (U > 1 && g < cnt) { tail_g = g; tail_cnt = cnt; tail_i0 = i0; tail_stage = cur; }
 #endif
         // the next chunk (issued at the top of this iteration) must have landed before it is read; the barrier also
         // protects the stage just consumed from the refill issued at the top of the next iteration
@@ -848,6 +834,28 @@ __device__ __forceinline__ void plate_body(const PlateParams& P, const double* _
         cur ^= 1;
     }
     bad |= !stage_ok;
+#if defined(__CUDACC_RTC__) && !defined(JB_INLINE_TAIL)
+    if (U > 1 && tail_cnt > 0) {
+        // They go one at a time through a NON-inlined copy of the body, state by value, OUTSIDE the loop nest so that the
+        // hot loop's registers stay registers.  A second inlined copy of the body cost NVVM 9 of the 12 s a kernel took to
+        // compile; the in-tree kernels keep it (their ptxas budgets are pinned by a test, nobody waits for their
+        // compilation).  The last chunk's staging buffer is still intact: nothing was staged after it.
+        StageView sv;
+        sv.chunk = stage0 + tail_stage * stage_doubles;
+        sv.jreg = jreg;
+        TailState ts;
+        copy_chain_state(ts.st, st);
+        copy_fused_acc(ts.fa, fa);
+        ts.lp = lp; ts.bad = bad;
+#pragma unroll
+        for (int l = 0; l < MAX_LOC; ++l) ts.pos[l] = pos[l];
+#pragma unroll 1
+        for (int g = tail_g; g < tail_cnt; ++g) ts = tail_group<S>(P, sv, g, tail_i0 + g, T, th, gr, ld, store, obs_tau, ts);
+        copy_chain_state(st, ts.st);
+        copy_fused_acc(fa, ts.fa);
+        lp = ts.lp; bad = ts.bad;
+    }
+#endif
 
     // expand the sufficient statistics of the fused paths
     const double n_obs = (double)((ie - ib) * V.T);
