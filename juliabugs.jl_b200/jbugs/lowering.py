@@ -1011,6 +1011,27 @@ class Lowering:
                     for d in self._defs(r.name):
                         if d.kind == "param" and len(d.loops) == 1 and d.extents == s.extents[1:] and d.size <= 10:
                             found.add(d.sid)
+        # coefficient vectors per group (theta[i, k] ~ dnorm(mu[k], tau[k]) for k in 1:3, referenced column by column as
+        # theta[i, 1], theta[i, 2], ...): each column becomes a local of the plate (_slice_local_index) whose prior
+        # arguments are elements of the hyper-parameter vectors -- globals
+        referenced_cols = set()
+        for t in self.stmts:
+            if t.kind == "tdata":
+                continue
+            body = t.node.rhs if isinstance(t.node, Det) else t.node.dist
+            for r in _subexprs(body):
+                if isinstance(r, Index) and len(r.idx) == 2 and self._is_data(r.idx[1], ()) and not self._is_data(r.idx[0], ()):
+                    referenced_cols.add(r.name)
+        for d in self.stmts:
+            if d.kind == "param" and not d.is_gq and len(d.loops) == 2 and d.name in referenced_cols \
+                    and d.extents[1][1] - d.extents[1][0] + 1 <= P.MAX_LOC:
+                kvar = d.loop_vars[1]
+                for a in d.node.dist.args:
+                    for r in _subexprs(a):
+                        if isinstance(r, Index) and len(r.idx) == 1 and isinstance(r.idx[0], Var) and r.idx[0].name == kvar:
+                            for h in self._defs(r.name):
+                                if h.kind == "param" and h.loops and not h.is_gq and h.size <= 48:
+                                    found.add(h.sid)
         # parameter vectors subscripted by a discrete latent that is summed out (mixtures: mu[z[i]], sigma[z[i]])
         latents = {d.name for d in self.stmts if d.kind == "latent"}
         if latents:
@@ -1826,6 +1847,9 @@ class Lowering:
 
     def _local_index(self, plate: P.Plate, obs: Stmt, ref, used_locals) -> int:
         _, name, idx = ref
+        sl = self._slice_of(obs, name, idx)
+        if sl is not None:
+            return self._slice_local_index(plate, obs, name, sl, used_locals)
         for k, l in enumerate(plate.locals):
             if l.name == name:
                 return k
@@ -1866,6 +1890,70 @@ class Lowering:
                                     -1 if idx_slot is None else idx_slot))
         used_locals.add(d.sid)
         return len(plate.locals) - 1
+
+
+# ---- coefficient vectors per group: theta[i, 1], theta[i, 2], theta[i, 3] of `for k in 1:3: theta[i, k] ~ dnorm(mu[k], tau[k])`
+def _slice_methods():
+    def _slice_of(self, obs: Stmt, name, idx):
+        """(statement, c) when `name[v, c]` references column c (a constant) of a parameter statement with loops (v, k),
+        v the observation's outer loop variable and k a short inner loop: each column is a group-level local"""
+        if len(idx) != 2 or not obs.loops or not (isinstance(idx[0], Var) and idx[0].name == obs.loop_vars[0]):
+            return None
+        if not self._is_data(idx[1], ()):
+            return None
+        defs = [d for d in self._defs(name) if d.kind == "param"]
+        if len(defs) != 1 or len(defs[0].loops) != 2:
+            return None
+        d = defs[0]
+        lhs = d.node.lhs
+        if not (isinstance(lhs, Index) and len(lhs.idx) == 2 and all(isinstance(i, Var) for i in lhs.idx)
+                and tuple(i.name for i in lhs.idx) == d.loop_vars):
+            return None
+        c = int(self.de.ev(idx[1], {}))
+        (klo, khi) = d.extents[1]
+        if not (klo <= c <= khi) or khi - klo + 1 > P.MAX_LOC:
+            return None
+        return d, c
+
+    def _slice_local_index(self, plate: P.Plate, obs: Stmt, name, sl, used_locals) -> int:
+        d, c = sl
+        lname = f"{name}[,{c}]"
+        for k, l in enumerate(plate.locals):
+            if l.name == lname:
+                return k
+        if d.is_gq:
+            raise LoweringError(f"'{name}' feeds an observation but was classified as generated quantity")
+        if d.sid in used_locals:
+            raise LoweringError(f"'{name}' is a parent of more than one observation plate")
+        if tuple(d.extents[:1]) != tuple(obs.extents[:1]) or not np.array_equal(_ext_keep(d.extents), _ext_keep(obs.extents)):
+            raise LoweringError(f"'{name}': loop ranges differ from the observation plate's")
+        fam = self._family(d.node.dist)
+        tidx = self.theta_index(d)
+        klo, khi = d.extents[1]
+        kvar = d.loop_vars[1]
+        # every column becomes a local of this plate at once: the prior of a column nobody references still belongs to the target
+        for cc in range(klo, khi + 1):
+            args = [_subst(a, {kvar: Num(float(cc), True)}) for a in d.node.dist.args]
+            tr, lb, ub = self._transform_of(fam, args)
+            base, si, _, idx_slot = _affine_or_index(tidx[:, cc - klo])
+            if idx_slot is not None:
+                idx_slot = self._slot(f"theta_index|{name}[,{cc}]", np.ascontiguousarray(tidx[:, cc - klo]).astype(np.int64), rank=1,
+                                      dim0=tidx.shape[0])
+            self._cur_extents = d.extents[:1] if _ext_keep(d.extents) is None else d.extents
+            one = replace(d, loops=d.loops[:1], extents=d.extents if _ext_keep(d.extents) is not None else d.extents[:1])
+            pargs = [self._scalar_arg(a, one.loop_vars, (tidx.shape[0],), one.loop_vars) for a in args]
+            self._cur_extents = obs.extents
+            if len(plate.locals) >= P.MAX_LOC:
+                raise LoweringError(f"more than {P.MAX_LOC} local parameters in one plate")
+            plate.locals.append(P.Local(f"{name}[,{cc}]", P.LEVEL_GROUP, tr, base, si, 0, fam, pargs, lb, ub,
+                                        -1 if idx_slot is None else idx_slot))
+        used_locals.add(d.sid)
+        return next(k for k, l in enumerate(plate.locals) if l.name == lname)
+
+    return _slice_of, _slice_local_index
+
+
+Lowering._slice_of, Lowering._slice_local_index = _slice_methods()
 
 
 def _affine_or_index(tidx: np.ndarray):

@@ -41,6 +41,7 @@ OP_IDENTITY, OP_EXP, OP_LOGISTIC, OP_CEXPEXP, OP_PHI, OP_LOG, OP_SQRT, OP_NEG = 
 OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW = 16, 17, 18, 19, 20
 OP_LEAF, OP_SELECT, OP_PICK_K = 32, 33, 34   # expression tapes only
 MAX_XOPS = 64
+MAX_LOC = 4    # local parameters per plate (csrc/jbugs_kernels.cuh)
 LINK_OF = {"exp": OP_EXP, "logistic": OP_LOGISTIC, "ilogit": OP_LOGISTIC, "cexpexp": OP_CEXPEXP,
            "icloglog": OP_CEXPEXP, "phi": OP_PHI}
 UNARY_OF = dict(LINK_OF, log=OP_LOG, sqrt=OP_SQRT)

@@ -24,6 +24,7 @@ ZOO = [
     ("air", ex.AIR, "air", "inits"),                  # a latent covariate times a coefficient
     ("leuk", ex.LEUK, "leuk", "inits"),               # Y[i,j] * exp(beta * Z[i]) * dL0[j] as a Poisson mean
     ("mice", ex.MICE, "mice", "inits"),               # censored Weibull: the censored cells are missing, hence outside the target
+    ("orange", ex.ORANGE, "orange", "inits"),         # vol. 2: a coefficient vector per group, theta[i, 1:3], column by column
     ("kidney", ex.KIDNEY, "kidney", "inits"),         # + rows without any observed cell dropped (their b[i] leave theta), factor levels by data index
 ]
 
