@@ -641,8 +641,8 @@ class Lowering:
                 # (the reference evaluates the pmf at theta's value); summed out under UseAutoMarginalization
                 if not self.marginalize:
                     continue
-                if s.node.dist.fn != "dcat":
-                    raise LoweringError(f"'{s.name}': only dcat latents are summed out")
+                if s.node.dist.fn not in ("dcat", "dbern"):
+                    raise LoweringError(f"'{s.name}': only dcat and dbern latents are summed out")
                 s.kind = "latent"
                 if s.zobs is not None:
                     self.de.unknown.add(s.name)
@@ -1358,13 +1358,16 @@ class Lowering:
         lhs_idx = d.node.lhs.idx if isinstance(d.node.lhs, Index) else ()
         if tuple(_show(a) for a in idx) != tuple(_show(a) for a in lhs_idx):
             raise LoweringError(f"'{ie.name}' must be referenced with the subscripts of its own statement")
-        wa = d.node.dist.args[0]
-        if not (isinstance(wa, Index) and isinstance(wa.idx[-1], Range) and self._is_data(wa.idx[-1].lo, ()) and
-                self._is_data(wa.idx[-1].hi, ()) and int(self.de.ev(wa.idx[-1].lo, {})) == 1):
-            raise LoweringError("the latent's dcat needs a probability vector w[..., 1:K] with constant K")
-        K = int(self.de.ev(wa.idx[-1].hi, {}))
-        if not 1 <= K <= 16:
-            raise LoweringError("between 1 and 16 states can be summed out per observation")
+        if d.node.dist.fn == "dbern":
+            K = 2   # states 0, 1 (value of state k: k); a dcat latent has the states 1..K (value of state k: k + 1)
+        else:
+            wa = d.node.dist.args[0]
+            if not (isinstance(wa, Index) and isinstance(wa.idx[-1], Range) and self._is_data(wa.idx[-1].lo, ()) and
+                    self._is_data(wa.idx[-1].hi, ()) and int(self.de.ev(wa.idx[-1].lo, {})) == 1):
+                raise LoweringError("the latent's dcat needs a probability vector w[..., 1:K] with constant K")
+            K = int(self.de.ev(wa.idx[-1].hi, {}))
+            if not 1 <= K <= 16:
+                raise LoweringError("between 1 and 16 states can be summed out per observation")
         if self._latent is not None and self._latent[0].sid != d.sid:
             raise LoweringError("one discrete latent per observation plate")
         self._latent = (d, K)
@@ -1430,8 +1433,20 @@ class Lowering:
             self.de.lenient = True
             try:
                 zref = z.node.lhs if isinstance(z.node.lhs, Index) else Var(z.name)
-                pk = Index(wa.name, wa.idx[:-1] + (zref,))
-                plate.logprior_slot = self._tape(Call("log", (pk,)), s, plate, tape, memo, used_locals)
+                if z.node.dist.fn == "dbern":
+                    # log p(z = 0) = log(1 - theta), log p(z = 1) = log(theta): two candidates picked by the state
+                    cands = [self._tape(Call("log", (BinOp("-", Num(1.0), wa),)), s, plate, tape, memo, used_locals),
+                             self._tape(Call("log", (wa,)), s, plate, tape, memo, used_locals)]
+                    first = len(tape)
+                    for sl in cands:
+                        tape.append(P.XOp(P.OP_IDENTITY, sl))
+                    tape.append(P.XOp(P.OP_PICK_K, first))
+                    if len(tape) > P.MAX_XOPS:
+                        raise LoweringError(f"the predictor needs more than {P.MAX_XOPS} tape ops")
+                    plate.logprior_slot = len(tape) - 1
+                else:
+                    pk = Index(wa.name, wa.idx[:-1] + (zref,))
+                    plate.logprior_slot = self._tape(Call("log", (pk,)), s, plate, tape, memo, used_locals)
             finally:
                 self.de.lenient = False
             plate.n_states = K
@@ -1502,8 +1517,42 @@ class Lowering:
             return push(P.XOp(P.OP_LEAF, leaf=self._data_arg(e, lv_names, shape, lv_names)))
         if isinstance(e, Var):
             return push(P.XOp(P.OP_LEAF, leaf=P.Arg.gval(self._gval_of(e.name))))
+        if isinstance(e, (Index, Var)) and self._latent_ref(e, s) is not None:
+            # the latent's own value in arithmetic (mu + delta * z[i]): a constant per state
+            z, K = self._latent_ref(e, s)
+            v0 = 0 if z.node.dist.fn == "dbern" else 1
+            first = len(tape)
+            for k in range(K):
+                tape.append(P.XOp(P.OP_LEAF, leaf=P.Arg.const(float(v0 + k))))
+            if len(tape) + 1 > P.MAX_XOPS:
+                raise LoweringError(f"the predictor needs more than {P.MAX_XOPS} tape ops")
+            return push(P.XOp(P.OP_PICK_K, first))
         if isinstance(e, Index):
             lat = [q for q, ie in enumerate(e.idx) if self._latent_ref(ie, s) is not None]
+            if not lat:
+                # a subscript that is a FUNCTION of the latent (state1[i] <- state[i] + 1; P[state1[i]]): evaluate it per state
+                for q, ie in enumerate(e.idx):
+                    if isinstance(ie, (Range, Colon)) or self._is_data(ie, lv_names):
+                        continue
+                    ie2 = self._inline(ie)
+                    refs = [r for r in _subexprs(ie2) if isinstance(r, (Index, Var)) and self._latent_ref(r, s) is not None]
+                    if not refs:
+                        continue
+                    z, K = self._latent_ref(refs[0], s)
+                    v0 = 0 if z.node.dist.fn == "dbern" else 1
+                    slots = []
+                    for k in range(K):
+                        sub = _replace(ie2, refs[0], Num(float(v0 + k), True))
+                        if not self._is_data(sub, ()):
+                            raise LoweringError("a subscript built from the discrete latent must not depend on anything else that varies")
+                        cidx = Num(float(int(self.de.ev(sub, {}))), True)
+                        slots.append(rec(self._inline(Index(e.name, e.idx[:q] + (cidx,) + e.idx[q + 1:]))))
+                    first = len(tape)
+                    for sl in slots:
+                        tape.append(P.XOp(P.OP_IDENTITY, sl))
+                    if len(tape) + 1 > P.MAX_XOPS:
+                        raise LoweringError(f"the predictor needs more than {P.MAX_XOPS} tape ops")
+                    return push(P.XOp(P.OP_PICK_K, first))
             if lat:
                 # name[.., z[i], ..] with z a discrete latent that is summed out: the K candidates name[.., k, ..] in
                 # consecutive slots (identity copies gather them), picked by the state
@@ -1986,6 +2035,21 @@ def _subexprs(e):
         yield from _subexprs(e.b)
     elif isinstance(e, Neg):
         yield from _subexprs(e.a)
+
+
+def _replace(e, target, new):
+    """`e` with every occurrence of the sub-expression `target` replaced by `new`"""
+    if e == target:
+        return new
+    if isinstance(e, Index):
+        return Index(e.name, tuple(_replace(i, target, new) for i in e.idx))
+    if isinstance(e, Neg):
+        return Neg(_replace(e.a, target, new))
+    if isinstance(e, BinOp):
+        return BinOp(e.op, _replace(e.a, target, new), _replace(e.b, target, new))
+    if isinstance(e, Call):
+        return Call(e.fn, tuple(_replace(a, target, new) for a in e.args))
+    return e
 
 
 def _subst(e, sub):

@@ -732,7 +732,7 @@ class GraphModel:
     # ---- UseAutoMarginalization (evaluation.jl:739-961) ------------------------------------------------------
     def _is_latent(self, nd):
         return (nd.is_stochastic and not nd.is_observed and self.var_type[nd.vid] != "GeneratedQuantity"
-                and nd.stmt.dist.fn == "dcat")
+                and nd.stmt.dist.fn in ("dcat", "dbern"))
 
     def marginal_param_names(self):
         """the continuous parameters, in `sorted_nodes` order: theta of the marginalised model"""
@@ -777,7 +777,8 @@ class GraphModel:
                 return pr, lk + d.logpdf(M, self._get_env(env, nd))
             if self._is_latent(nd):
                 priors, joints = [], []
-                for val in range(1, len(d.p) + 1):
+                # the support of the finite discrete node (evaluation.jl:860-890 enumerates `support(dist)`)
+                for val in (range(1, len(d.p) + 1) if isinstance(d, dists.Categorical) else (0, 1)):
                     env2 = dict(env)
                     env2[nd.name] = env2[nd.name].copy() if isinstance(env2[nd.name], np.ndarray) else env2[nd.name]
                     self._set(env2, nd.name, nd.idx, float(val))

@@ -347,3 +347,68 @@ def test_cuda_large_mixture_against_closed_form():
     lp0, g0, _ = COracle(m.plan).eval_batch(theta[:, :4])
     scale = np.maximum(np.abs(g0), 1e-4 * np.abs(g0).max(axis=0, keepdims=True))
     assert np.max(np.abs(g[:, :4] - g0) / scale) < 1e-10
+
+
+# ---- Bernoulli latents: the support {0, 1} summed out like a two-state dcat (evaluation.jl:860-890 enumerates the
+# support of any finite discrete node).  The latent may enter arithmetic directly, or through a derived subscript
+# (`s[i] <- z[i] + 1; mu[s[i]]`, the idiom of the Cervix example, J/src/BUGSExamples/Volume_2/08_Cervix.jl:5-10)
+BERN_ARITH = """model {
+  p ~ dbeta(2, 3)
+  mu0 ~ dnorm(-2, 0.04)
+  delta ~ dnorm(4, 0.04)
+  for (i in 1:N) {
+    z[i] ~ dbern(p)
+    y[i] ~ dnorm(mu0 + delta * z[i], 1.5)
+  }
+}"""
+
+BERN_SUBSCRIPT = """model {
+  mu[1] ~ dnorm(-2, 0.04)
+  mu[2] ~ dnorm(2, 0.04)
+  for (i in 1:N) {
+    z[i] ~ dbern(q[i])
+    s[i] <- z[i] + 1
+    y[i] ~ dnorm(mu[s[i]], 1.5)
+  }
+}"""
+
+
+def _bern_cases(N=5):
+    rng = np.random.default_rng(23)
+    y = 2.0 * rng.standard_normal(N)
+    return {"bern_arith": (BERN_ARITH, {"N": N, "y": y}),
+            "bern_subscript": (BERN_SUBSCRIPT, {"N": N, "y": y, "q": 0.1 + 0.8 * rng.random(N)})}
+
+
+@pytest.mark.parametrize("name", ["bern_arith", "bern_subscript"])
+def test_bernoulli_latents_node_oracle_vs_plan(name):
+    text, data = _bern_cases()[name]
+    plan, gm = lowered(text, data)
+    rng = np.random.default_rng(4)
+    theta = 0.4 * rng.standard_normal((plan.D, 4))
+    lp, _ = check_c_port(plan, gm, theta)
+    if name == "bern_subscript":   # closed form: a two-component mixture with per-observation weights
+        for c in range(4):
+            mu = theta[:, c]       # generated order: mu[1], mu[2]
+            names = gm.marginal_param_names()
+            m1, m2 = mu[names.index("mu[1]")], mu[names.index("mu[2]")]
+            sd = 1 / np.sqrt(1.5)
+            ll = sum(logsumexp([np.log(1 - q) + S.norm(m1, sd).logpdf(yi), np.log(q) + S.norm(m2, sd).logpdf(yi)])
+                     for yi, q in zip(data["y"], data["q"]))
+            pr = S.norm(-2, 5).logpdf(m1) + S.norm(2, 5).logpdf(m2)
+            assert lp[c] == pytest.approx(ll + pr, abs=1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["bern_arith", "bern_subscript"])
+def test_cuda_bernoulli_latents(name):
+    text, data = _bern_cases(N=41)[name]
+    m = jbugs.compile(text, data, evaluation_mode=jbugs.UseAutoMarginalization())
+    rng = np.random.default_rng(6)
+    theta = 0.4 * rng.standard_normal((m.plan.D, 70))
+    lp, g, st = m.cuda.eval_host(theta, layout="param_fast")
+    lp0, g0, st0 = COracle(m.plan).eval_batch(theta)
+    assert (st == 0).all() and (st0 == 0).all()
+    assert np.max(np.abs(lp - lp0) / np.maximum(1.0, np.abs(lp0))) < 1e-12
+    scale = np.maximum(np.abs(g0), 1e-4 * np.abs(g0).max(axis=0, keepdims=True))
+    assert np.max(np.abs(g - g0) / scale) < 1e-10
