@@ -462,7 +462,34 @@ model {
 }
 """
 
+# vol. 2, Cervix: a case-control study with errors in covariates.  x[i] (true exposure) is observed for the first 115
+# subjects only; the missing x[i] are finite discrete nodes -- parameters with the identity bijector in the reference's
+# UseGraph / generated modes (outside the plate class), summed out under UseAutoMarginalization
+CERVIX = """
+model {
+    for (i in 1:N) {
+        x[i] ~ dbern(q)
+        logit(p[i]) <- beta0C + beta * x[i]
+        d[i] ~ dbern(p[i])
+        x1[i] <- x[i] + 1
+        d1[i] <- d[i] + 1
+        w[i] ~ dbern(phi[x1[i], d1[i]])
+    }
+    q ~ dunif(0.0, 1.0)
+    beta0C ~ dnorm(0.0, 0.00001)
+    beta ~ dnorm(0.0, 0.00001)
+    for (j in 1:2) {
+        for (k in 1:2) {
+            phi[j, k] ~ dunif(0.0, 1.0)
+        }
+    }
+    gamma1 <- 1 / (1 + (1 + exp(beta0C + beta)) / (1 + exp(beta0C)) * (1 - q) / q)
+    gamma2 <- 1 / (1 + (1 + exp(-beta0C - beta)) / (1 + exp(-beta0C)) * (1 - q) / q)
+}
+"""
+
 MODELS = {
+    "cervix": CERVIX,
     "orange": ORANGE,
     "mice": MICE,
     "kidney": KIDNEY,

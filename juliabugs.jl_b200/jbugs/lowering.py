@@ -359,6 +359,14 @@ class Lowering:
         return lhs.idx
 
     def _fold_transformed_data(self):
+        if self.marginalize:
+            # a partially observed discrete latent is not data: what is computed from it (s[i] <- z[i] + 1) stays a
+            # logical statement, evaluated per state of the latent
+            for s in self.stmts:
+                arr = self.data.get(s.name)
+                if (isinstance(s.node, Stoch) and s.node.dist.fn in ("dcat", "dbern") and isinstance(arr, np.ndarray)
+                        and np.isnan(arr).any() and not np.isnan(arr).all()):
+                    self.de.unknown.add(s.name)
         changed = True
         while changed:
             changed = False
@@ -611,11 +619,13 @@ class Lowering:
                     miss = np.isnan(np.broadcast_to(sub, s.shape))
                     if miss.all():
                         s.kind = "param"
-                    elif miss.any() and s.node.dist.fn == "dcat" and self.marginalize:
+                    elif miss.any() and s.node.dist.fn in ("dcat", "dbern") and self.marginalize:
                         # a partially observed discrete latent (auto_marginalization.jl:391-462): the missing cells are
-                        # summed out, the observed ones take the branch of their value
+                        # summed out, the observed ones take the branch of their value.  Recorded as state number + 1
+                        # (0 = missing): a dcat value k is state k - 1, a dbern value v is state v
                         s.kind = "param"
-                        s.zobs = np.where(miss, 0.0, np.broadcast_to(sub, s.shape)).astype(np.float64)
+                        shift = 1.0 if s.node.dist.fn == "dbern" else 0.0
+                        s.zobs = np.where(miss, 0.0, np.broadcast_to(sub, s.shape) + shift).astype(np.float64)
                     elif miss.any():
                         # the missing cells are unobserved stochastic nodes.  When nothing depends on the variable they
                         # have no observed descendants: generated quantities, outside the target (graphs.jl:27-71; the
@@ -1035,11 +1045,21 @@ class Lowering:
         # parameter vectors subscripted by a discrete latent that is summed out (mixtures: mu[z[i]], sigma[z[i]])
         latents = {d.name for d in self.stmts if d.kind == "latent"}
         if latents:
+            def mentions_latent(i):
+                """the subscript is the latent itself or computed from it (x1[i] <- x[i] + 1; phi[x1[i], ..])"""
+                if isinstance(i, (Range, Colon)):
+                    return False
+                try:
+                    i = self._inline(i)
+                except LoweringError:
+                    return False
+                return any(isinstance(r, (Index, Var)) and r.name in latents for r in _subexprs(i))
+
             def walk_latent(e, via=False):
                 """`via`: e sits inside the definition of a looped logical node that is itself selected by the latent
                 (tau[k] <- 1 / (sigma[k] * sigma[k]) referenced as tau[z[i]]): its looped parameters are selected too"""
                 if isinstance(e, Index):
-                    if via or any(isinstance(i, (Index, Var)) and i.name in latents for i in e.idx):
+                    if via or any(mentions_latent(i) for i in e.idx):
                         for d in self._defs(e.name):
                             if d.kind == "param" and d.loops and not d.is_gq:
                                 if d.size > 48:
@@ -1169,10 +1189,27 @@ class Lowering:
         used_locals = set(vec)
         merged = set()
         obs_stmts = [s for s in self.stmt_order if s.kind == "obs"]
+        # observation statements hanging off the same summed-out latent (Cervix: d[i] and w[i] both depend on x[i]) are
+        # ONE cell of the sum over its states: the first is the plate's observation, the others are folded into the
+        # state's log weight (_sibling_logpdf)
+        self._latent_sibs: Dict[int, List[Stmt]] = {}
+        folded = set()
+        if self.marginalize:
+            by_latent: Dict[int, List[Stmt]] = {}
+            for s in obs_stmts:
+                if not s.is_gq:
+                    for zs in self._latents_of(s):
+                        by_latent.setdefault(zs, []).append(s)
+            for ch in by_latent.values():
+                if len(ch) > 1:
+                    if ch[0].sid in self._latent_sibs or any(t.sid in folded for t in ch) or ch[0].sid in folded:
+                        raise LoweringError("observations shared between two discrete latents are outside the plate class")
+                    self._latent_sibs[ch[0].sid] = ch[1:]
+                    folded.update(t.sid for t in ch[1:])
         for s in obs_stmts:
-            if s.sid in merged:
+            if s.sid in merged or s.sid in folded:
                 continue
-            sibs = self._siblings(s, [t for t in obs_stmts if t.sid not in merged and t.sid != s.sid])
+            sibs = self._siblings(s, [t for t in obs_stmts if t.sid not in merged and t.sid != s.sid and t.sid not in folded])
             if sibs:
                 merged.update(t.sid for t in sibs)
                 pl = self._build_merged_plate([s] + sibs, used_locals)
@@ -1187,6 +1224,47 @@ class Lowering:
                     f"parameter '{s.name}' is not a direct parent of an observation plate "
                     "(latent-only layers are outside the plate class)")
         self.plan.param_names = None
+
+    def _latents_of(self, s: Stmt):
+        """sids of the summed-out latent statements the arguments of observation statement `s` depend on"""
+        latents = {d.name: d.sid for d in self.stmts if d.kind == "latent"}
+        out = []
+        if not latents:
+            return out
+        for a in s.node.dist.args:
+            try:
+                e = self._inline(a)
+            except LoweringError:
+                continue
+            for r in _subexprs(e):
+                if isinstance(r, (Index, Var)) and r.name in latents and latents[r.name] not in out:
+                    out.append(latents[r.name])
+        return out
+
+    def _sibling_logpdf(self, t: Stmt, s: Stmt):
+        """log density of observation statement `t` -- a second child of the latent summed out in the plate of `s` -- as
+        an expression for the tape (one cell, the latent at one state).  Closed forms of Appendix A; the argument
+        checks of the family (DomainError in the reference) are not reproduced for a folded statement."""
+        if t.loops != s.loops or t.ragged or t.obs_mask is not None or t.censor is not None:
+            raise LoweringError(f"'{t.name}': a second observation of a summed-out latent must be fully observed and "
+                                "share the loop nest of the first")
+        y = t.node.lhs if isinstance(t.node.lhs, Index) else Var(t.node.lhs.name)
+        fn, a = t.node.dist.fn, t.node.dist.args
+        one = Num(1.0)
+        if fn == "dbern":
+            return Call("__select__", (y, Call("log", (a[0],)), Call("log", (BinOp("-", one, a[0]),))))
+        if fn == "dbin":
+            norm = BinOp("-", BinOp("-", Call("loggam", (BinOp("+", a[1], one),)), Call("loggam", (BinOp("+", y, one),))),
+                         Call("loggam", (BinOp("+", BinOp("-", a[1], y), one),)))
+            return BinOp("+", BinOp("+", BinOp("*", y, Call("log", (a[0],))),
+                                    BinOp("*", BinOp("-", a[1], y), Call("log", (BinOp("-", one, a[0]),)))), norm)
+        if fn == "dnorm":
+            r = BinOp("-", y, a[0])
+            return BinOp("-", BinOp("-", BinOp("*", Num(0.5), Call("log", (a[1],))),
+                                    BinOp("*", BinOp("*", Num(0.5), a[1]), BinOp("*", r, r))), Num(0.5 * math.log(2.0 * math.pi)))
+        if fn == "dpois":
+            return BinOp("-", BinOp("-", BinOp("*", y, Call("log", (a[0],))), a[0]), Call("logfact", (y,)))
+        raise LoweringError(f"'{t.name}': a second observation of a summed-out latent must be dbern, dbin, dnorm or dpois")
 
     # ---- gtape ---------------------------------------------------------------------------------------------
     def _emit_gtape(self, name, e):
@@ -1447,6 +1525,13 @@ class Lowering:
                 else:
                     pk = Index(wa.name, wa.idx[:-1] + (zref,))
                     plate.logprior_slot = self._tape(Call("log", (pk,)), s, plate, tape, memo, used_locals)
+                for t in self._latent_sibs.get(s.sid, ()):
+                    sl = self._tape(self._inline(self._sibling_logpdf(t, s)), s, plate, tape, memo, used_locals)
+                    tape.append(P.XOp(P.OP_ADD, plate.logprior_slot, sl))
+                    if len(tape) > P.MAX_XOPS:
+                        raise LoweringError(f"the predictor needs more than {P.MAX_XOPS} tape ops")
+                    plate.logprior_slot = len(tape) - 1
+                    plate.name += f" + {t.name}~{t.node.dist.fn}"
             finally:
                 self.de.lenient = False
             plate.n_states = K
@@ -1468,6 +1553,8 @@ class Lowering:
             plate.name += f", {z.name} summed out over {K} states"
             used_locals.add(z.sid)
             self._latent = None
+        elif self._latent_sibs.get(s.sid):
+            raise LoweringError(f"'{s.name}': internal: the shared latent was not found while taping")
         plate.xops = tape
         self._apply_obs_mask(plate, s)
         return plate
@@ -1573,6 +1660,9 @@ class Lowering:
             ref = ("l", e.name, e.idx)
             if self._is_gvec_ref(s, ref):
                 return push(P.XOp(P.OP_LEAF, leaf=P.Arg(P.ARG_GVEC_J, self._gval_ids[f"{e.name}[{s.extents[1][0]}]"])))
+            picked = self._global_pick(e, s)
+            if picked is not None:
+                return rec(picked)
             return push(P.XOp(P.OP_LEAF, leaf=P.Arg.local(self._local_index(plate, s, ref, used_locals))))
         if isinstance(e, Neg):
             return push(P.XOp(P.OP_NEG, rec(e.a)))
@@ -1587,6 +1677,36 @@ class Lowering:
             if e.fn in P.UNARY_OF and len(e.args) == 1:
                 return push(P.XOp(P.UNARY_OF[e.fn], rec(e.args[0])))
         raise LoweringError(f"unsupported expression in a predictor: {_show(e)}")
+
+    def _global_pick(self, e: Index, s: Stmt):
+        """`phi[2, d1[i]]`: an element of a short parameter array whose elements are globals, picked by data subscripts
+        that vary over the plate -> nested selects over the index tuples that occur (conditions are 0/1 data leaves)"""
+        if not any(k.startswith(e.name + "[") for k in self._gval_ids):
+            return None
+        if any(isinstance(i, (Range, Colon)) or not self._is_data(i, s.loop_vars) for i in e.idx):
+            return None
+        lv = _grids(s.extents, s.loop_vars)
+        cols = [np.broadcast_to(np.asarray(self.de.ev(i, lv), dtype=np.float64), s.shape).ravel() for i in e.idx]
+        seen = np.ones(cols[0].shape, bool) if s.obs_mask is None else np.asarray(s.obs_mask).ravel()
+        if np.isnan(np.stack(cols)[:, seen]).any():
+            raise LoweringError(f"'{_show(e)}': a subscript is missing for an observed cell")
+        tuples = sorted(set(zip(*[c[seen].astype(np.int64) for c in cols])))
+        if not tuples or len(tuples) > 8:
+            raise LoweringError(f"'{_show(e)}': too many distinct elements picked by data subscripts")
+        out = None
+        for t in tuples:
+            elem = Index(e.name, tuple(Num(float(v), True) for v in t))
+            if self._elem_label(elem) not in self._gval_ids:
+                raise LoweringError(f"'{_show(elem)}' is not a parameter element")
+            if out is None:
+                out = elem
+                continue
+            cond = None
+            for i, v in zip(e.idx, t):
+                c = Call("equals", (i, Num(float(v), True)))
+                cond = c if cond is None else BinOp("*", cond, c)
+            out = Call("__select__", (cond, elem, out))
+        return out
 
     # ---- random effects picked by a data index: y[i] ~ f(... + b[group[i]] ...) -------------------------------------
     def _gather_index(self, s: Stmt, lin: _Lin):

@@ -45,7 +45,7 @@ FILES = {
 }
 # Volume 2 examples used by the expression-plate tests (written to examples_vol2.json)
 REF2 = "/root/reference/JuliaBUGS/src/BUGSExamples/Volume_2"
-FILES2 = {"dugongs": "01_Dugongs.jl", "air": "07_Air.jl", "orange": "02_Orange_trees.jl"}
+FILES2 = {"dugongs": "01_Dugongs.jl", "air": "07_Air.jl", "orange": "02_Orange_trees.jl", "cervix": "08_Cervix.jl"}
 TUPLES = re.compile(r"^(data|inits\w*|inits_alternative\w*)\s*=\s*\(", re.M)
 
 # golden constants: JuliaBUGS/test/model/evaluation.jl:355-379 (rtol 1e-6 in the reference test)

@@ -137,3 +137,19 @@ def test_marginalised_mixture_tape_compiles():
         after = cp.eval_host(theta)
         assert np.max(np.abs(after[0] - before[0]) / np.maximum(1.0, np.abs(before[0]))) < 1e-12
         _check(cp, COracle(m.plan), theta)
+
+
+def test_cervix_tape_compiles():
+    """Cervix under UseAutoMarginalization: Bernoulli latents with a folded second child, selects on data leaves and
+    PICK_K in one tape -- interpreter == generated straight-line code == C restatement"""
+    from jbugs import examples as ex
+    from test_marginalization import _cervix_data
+    m = jbugs.compile(ex.CERVIX, _cervix_data(), evaluation_mode=jbugs.UseAutoMarginalization())
+    cp = m.cuda
+    theta = 0.5 * np.random.default_rng(5).standard_normal((m.plan.D, 70))
+    before = cp.eval_host(theta)
+    cp.specialize()
+    assert "expression_tape_specialised_at_run_time" in cp.describe()
+    after = cp.eval_host(theta)
+    assert np.max(np.abs(after[0] - before[0]) / np.maximum(1.0, np.abs(before[0]))) < 1e-12
+    _check(cp, COracle(m.plan), theta)

@@ -412,3 +412,100 @@ def test_cuda_bernoulli_latents(name):
     assert np.max(np.abs(lp - lp0) / np.maximum(1.0, np.abs(lp0))) < 1e-12
     scale = np.maximum(np.abs(g0), 1e-4 * np.abs(g0).max(axis=0, keepdims=True))
     assert np.max(np.abs(g - g0) / scale) < 1e-10
+
+
+# ---- Cervix (vol. 2): the true exposure x[i] is observed for 115 of 2044 subjects; the missing ones are Bernoulli
+# latents with TWO observed children each (d[i] through the logistic model, w[i] through phi[x[i] + 1, d[i] + 1]).
+# The second child is folded into the state's log weight, so a cell is still one sum over the latent's states.
+def _cervix_data(sel=None):
+    import json
+    import os
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "examples_vol2.json")))["cervix"]["data"]
+    full = {k: (np.array(v, dtype=float) if isinstance(v, list) else v) for k, v in fx.items()}
+    if sel is None:
+        return full
+    return {"N": len(sel), **{k: full[k][sel] for k in ("x", "d", "w")}}
+
+
+def _cervix_closed_form(data, names, theta):
+    """log joint in unconstrained space, written from the model text: per subject sum over x in {0, 1} (or the observed x)"""
+    ix = {n: i for i, n in enumerate(names)}
+    sig = lambda v: 1.0 / (1.0 + np.exp(-v))   # noqa: E731
+    q = sig(theta[ix["q"]])
+    phi = np.array([[sig(theta[ix[f"phi[{j},{k}]"]]) for k in (1, 2)] for j in (1, 2)])
+    b0, b = theta[ix["beta0C"]], theta[ix["beta"]]
+    x, d, w = data["x"], data["d"].astype(int), data["w"].astype(int)
+    terms = []
+    for xv in (0, 1):
+        p = sig(b0 + b * xv)
+        lt = (np.log(q) if xv else np.log1p(-q)) + np.where(d == 1, np.log(p), np.log1p(-p)) \
+            + np.where(w == 1, np.log(phi[xv, d]), np.log1p(-phi[xv, d]))
+        terms.append(np.where(np.isnan(x) | (x == xv), lt, -np.inf))
+    lik = logsumexp(np.stack(terms), axis=0).sum()
+    prior = S.norm(0, np.sqrt(1e5)).logpdf(b0) + S.norm(0, np.sqrt(1e5)).logpdf(b)   # the five dunif(0, 1) priors are 0
+    logjac = sum(np.log(v) + np.log1p(-v) for v in [q] + list(phi.ravel()))
+    return lik + prior + logjac
+
+
+def test_cervix_subset_against_the_node_oracle():
+    from jbugs import examples as ex
+    sel = np.r_[0:3, 40:43, 200:203, 2040:2043]   # 6 observed exposures, 6 latent ones
+    data = _cervix_data(sel)
+    plan, gm = lowered(ex.CERVIX, data)
+    assert plan.D == 7 and len(plan.plates) == 1
+    rng = np.random.default_rng(0)
+    theta = 0.4 * rng.standard_normal((plan.D, 3))
+    lp, _ = check_c_port(plan, gm, theta)
+    names = gm.marginal_param_names()
+    for c in range(3):
+        assert lp[c] == pytest.approx(_cervix_closed_form(data, names, theta[:, c]), abs=1e-10)
+
+
+def test_cervix_full_size_closed_form():
+    from jbugs import examples as ex
+    data = _cervix_data()
+    plan, lw = jbugs.lower(ex.CERVIX, data, marginalize=True)
+    names = lw.param_names()
+    assert sorted(names) == sorted(["q", "beta0C", "beta", "phi[1,1]", "phi[1,2]", "phi[2,1]", "phi[2,2]"])
+    with pytest.raises(jbugs.LoweringError):
+        jbugs.lower(ex.CERVIX, data)   # without marginalisation the 1929 missing x[i] are discrete entries of theta
+    rng = np.random.default_rng(1)
+    theta = 0.5 * rng.standard_normal((plan.D, 4))
+    lp, g, st = COracle(plan).eval_batch(theta)
+    assert (st == 0).all()
+    for c in range(4):
+        assert lp[c] == pytest.approx(_cervix_closed_form(data, names, theta[:, c]), rel=1e-12)
+    # gradient against central differences of the closed form (auto_marginalization.jl:654-703 checks the same way)
+    h = 1e-6
+    for k in range(plan.D):
+        e = np.zeros(plan.D)
+        e[k] = h
+        fd = (_cervix_closed_form(data, names, theta[:, 0] + e) - _cervix_closed_form(data, names, theta[:, 0] - e)) / (2 * h)
+        assert g[k, 0] == pytest.approx(fd, rel=1e-5, abs=1e-5)
+
+
+def test_partially_observed_bernoulli_latent():
+    rng = np.random.default_rng(9)
+    y = 2.0 * rng.standard_normal(5)
+    z = np.array([1.0, np.nan, 0.0, np.nan, np.nan])
+    for text, data in ((BERN_ARITH, {"N": 5, "y": y, "z": z}),
+                       (BERN_SUBSCRIPT, {"N": 5, "y": y, "q": 0.1 + 0.8 * rng.random(5), "z": z})):
+        plan, gm = lowered(text, data)
+        check_c_port(plan, gm, 0.4 * rng.standard_normal((plan.D, 3)))
+
+
+@pytest.mark.gpu
+def test_cuda_cervix():
+    from jbugs import examples as ex
+    data = _cervix_data()
+    m = jbugs.compile(ex.CERVIX, data, evaluation_mode=jbugs.UseAutoMarginalization())
+    rng = np.random.default_rng(8)
+    theta = 0.5 * rng.standard_normal((m.plan.D, 200))
+    lp, g, st = m.cuda.eval_host(theta, layout="param_fast")
+    lp0, g0, st0 = COracle(m.plan).eval_batch(theta)
+    assert (st == 0).all() and (st0 == 0).all()
+    assert np.max(np.abs(lp - lp0) / np.maximum(1.0, np.abs(lp0))) < 1e-12
+    scale = np.maximum(np.abs(g0), 1e-4 * np.abs(g0).max(axis=0, keepdims=True))
+    assert np.max(np.abs(g - g0) / scale) < 1e-10
+    names = m.lowering.param_names()
+    assert lp[0] == pytest.approx(_cervix_closed_form(data, names, theta[:, 0]), rel=1e-12)
