@@ -71,7 +71,7 @@ include("lower_to_plan.jl")
 using .JBugsLowering
 
 """
-    UseCUDABatch(; device=0)
+    UseCUDABatch(; device=0, marginalize=false)
 
 New `EvaluationMode`: the model is lowered at statement/plate granularity to a flat kernel plan
 (`include/jbugs_plan.h`) and evaluated by libjbugs_cuda for a whole batch of chains per launch.
@@ -83,10 +83,11 @@ mode object, and with it the plan handle, is dropped exactly where the generated
 """
 mutable struct UseCUDABatch <: EvaluationMode
     device::Int
+    marginalize::Bool      # the reference's UseAutoMarginalization on the device: dcat / dbern latents summed out per cell
     handle::Union{Nothing,PlanHandle}
     plan::Union{Nothing,JBugsLowering.Plan}
 end
-UseCUDABatch(; device=0) = UseCUDABatch(device, nothing, nothing)
+UseCUDABatch(; device=0, marginalize=false) = UseCUDABatch(device, marginalize, nothing, nothing)
 
 _label(vn) = replace(string(vn), " " => "")          # "Y[1, 2]" -> "Y[1,2]", the label format of the lowering
 
@@ -99,7 +100,7 @@ the reconstructed program into plate records.  Observed / parameter / generated-
 `model.graph_evaluation_data` (src/model/bugsmodel.jl:118-246), data from `model.data` and the transformed data the
 reference folded into `model.evaluation_env` (src/JuliaBUGS.jl:175-187).
 """
-function lower_to_plan(model::BUGSModel)
+function lower_to_plan(model::BUGSModel; marginalize::Bool=false)
     gd = model.graph_evaluation_data
     lowered, reconstructed = JuliaBUGS._generate_lowered_model_def(
         model.model_def, model.g, model.evaluation_env;
@@ -136,14 +137,14 @@ function lower_to_plan(model::BUGSModel)
     for (k, v) in pairs(model.data)
         data[k] = tofloat(v)
     end
-    plan, _ = JBugsLowering.lower_program(reconstructed, data, node_info; transformed=model.transformed)
+    plan, _ = JBugsLowering.lower_program(reconstructed, data, node_info; transformed=model.transformed, marginalize=marginalize)
     return plan, reconstructed
 end
 
 function plan_handle(model::BUGSModel)
     mode = model.evaluation_mode::UseCUDABatch
     if mode.handle === nothing
-        plan, _ = lower_to_plan(model)
+        plan, _ = lower_to_plan(model; marginalize=mode.marginalize)
         h = PlanHandle(JBugsLowering.to_bytes(plan), mode.device)
         foreach(((k, sl),) -> upload!(h, k - 1, sl.values), enumerate(plan.data))
         mode.handle, mode.plan = h, plan
@@ -155,7 +156,7 @@ end
 # generated mode does (src/model/bugsmodel.jl:770-799) so that getparams / dimension / chain naming follow the plan's
 # theta layout.  Works in both spaces: `settrans(model, false)` gives identity transforms in the plan.
 function JuliaBUGS.set_evaluation_mode(model::BUGSModel, mode::UseCUDABatch)
-    _, reconstructed = lower_to_plan(model)
+    _, reconstructed = lower_to_plan(model; marginalize=mode.marginalize)
     pass = JuliaBUGS.CollectSortedNodes(model.evaluation_env)
     JuliaBUGS.analyze_block(pass, reconstructed)
     gd = model.graph_evaluation_data
@@ -164,14 +165,21 @@ function JuliaBUGS.set_evaluation_mode(model::BUGSModel, mode::UseCUDABatch)
                                                  generated_quantities=Set(gd.generated_quantities),
                                                  fixed_parameters=Set(gd.fixed_parameters))
     model = JuliaBUGS.BangBang.setproperty!!(model, :graph_evaluation_data, new_gd)
+    if mode.marginalize
+        # the reference's own marginalising mode first (bugsmodel.jl:802-873): it fills `marginalization_cache` for the new
+        # node order -- dimension / getparams then count the continuous parameters only, in the plan's theta order
+        model = JuliaBUGS.set_evaluation_mode(model, JuliaBUGS.UseAutoMarginalization())
+        model.evaluation_mode isa JuliaBUGS.UseAutoMarginalization ||
+            throw(JBugsLowering.LoweringError("the reference could not prepare auto-marginalisation for this model"))
+    end
     # (the same call the reference ends its own set_evaluation_mode with, bugsmodel.jl:876)
-    return JuliaBUGS.BangBang.setproperty!!(model, :evaluation_mode, UseCUDABatch(mode.device, nothing, nothing))
+    return JuliaBUGS.BangBang.setproperty!!(model, :evaluation_mode, UseCUDABatch(mode.device, mode.marginalize, nothing, nothing))
 end
 
 # set_observed_values! keeps the structure (abstractppl.jl:872-888): re-lower for the new values, re-upload, do not re-plan
 function reupload!(model::BUGSModel)
     h = plan_handle(model)
-    plan, _ = lower_to_plan(model)
+    plan, _ = lower_to_plan(model; marginalize=model.evaluation_mode.marginalize)
     JBugsLowering.to_bytes(plan) == JBugsLowering.to_bytes(model.evaluation_mode.plan) ||
         error("the new observations change the structure of the plan (e.g. the missingness pattern): set the evaluation mode again")
     foreach(((k, sl),) -> upload!(h, k - 1, sl.values), enumerate(plan.data))

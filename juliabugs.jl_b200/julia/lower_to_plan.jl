@@ -41,12 +41,12 @@ const FAM_BETABIN = 18   # dbetabin(a, b, n): the third argument (n) is a consta
 const DISCRETE = Set([6, 7, 8, 13, 16, 17, 18])
 const TR_IDENTITY, TR_LOG, TR_LOGIT = 0, 1, 2
 const OP_IDENTITY, OP_EXP, OP_LOGISTIC, OP_CEXPEXP, OP_PHI, OP_LOG, OP_SQRT, OP_NEG = 0:7
-const OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_LEAF, OP_SELECT = 16, 17, 18, 19, 20, 32, 33
+const OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_LEAF, OP_SELECT, OP_PICK_K = 16, 17, 18, 19, 20, 32, 33, 34
 const LINK_OF = Dict(:exp => OP_EXP, :logistic => OP_LOGISTIC, :ilogit => OP_LOGISTIC, :cexpexp => OP_CEXPEXP,
                      :icloglog => OP_CEXPEXP, :phi => OP_PHI)
 const UNARY_OF = merge(LINK_OF, Dict(:log => OP_LOG, :sqrt => OP_SQRT))
 const LEVEL_GROUP, LEVEL_OBS = 0, 1
-const MAX_LINK, MAX_XOPS = 4, 64
+const MAX_LINK, MAX_XOPS, MAX_STATES = 4, 64, 16
 
 struct Arg
     kind::UInt32
@@ -81,9 +81,12 @@ XOp(op, a=0, b=0, c=0) = XOp(op, a, b, c, ZERO_ARG)
 mutable struct Plate
     N::Int; T::Int; locals::Vector{Local}; terms::Vector{Term}; link::Vector{Int}; family::Int; eta_arg::Int
     has_obs::Bool; y::Arg; aux::Vector{Arg}; name::String; n_real::Int; weight::Union{Nothing,Arg}; xops::Vector{XOp}
+    n_states::Int        # > 0: one finite discrete latent per observation is summed out (has_obs == 3)
+    logprior_slot::Int   # tape slot of log p(z = k) (+ the log densities of the latent's further observed children)
+    zobs_slot::Int       # tape slot of a data leaf with the latent's observed state + 1 per cell (0 = missing); -1: none
 end
 Plate(N, T; family=0, eta_arg=0, has_obs=true, name="") =
-    Plate(N, T, Local[], Term[], Int[], family, eta_arg, has_obs, ZERO_ARG, Arg[], name, -1, nothing, XOp[])
+    Plate(N, T, Local[], Term[], Int[], family, eta_arg, has_obs, ZERO_ARG, Arg[], name, -1, nothing, XOp[], 0, -1, -1)
 struct Dense
     N::Int; P::Int; theta_base::Int; theta_stride::Int; x_slot::Int; y_slot::Int; n_slot::Int; family::Int; link::Int
 end
@@ -130,10 +133,15 @@ function to_bytes(p::Plan)::Vector{UInt8}
         write(io, htol(UInt32(is_x ? ix : it))); write(io, htol(UInt32(is_x ? length(pl.xops) : length(pl.terms))))
         write(io, htol(UInt32(length(pl.link))))
         for q in 1:MAX_LINK
-            write(io, htol(UInt32(q <= length(pl.link) ? pl.link[q] : OP_IDENTITY)))
+            v = q <= length(pl.link) ? pl.link[q] : OP_IDENTITY
+            if pl.n_states > 0       # has_obs == 3 (plan.py to_bytes): link[0] = log-prior slot, link[1] = observed-state slot + 1
+                q == 1 && (v = pl.logprior_slot)
+                q == 2 && (v = pl.zobs_slot + 1)
+            end
+            write(io, htol(UInt32(v)))
         end
-        write(io, htol(UInt32(pl.family))); write(io, htol(UInt32(pl.eta_arg)))
-        write(io, htol(UInt32(pl.has_obs ? (is_x ? 2 : 1) : 0)))
+        write(io, htol(UInt32(pl.family))); write(io, htol(UInt32(pl.n_states > 0 ? pl.n_states : pl.eta_arg)))
+        write(io, htol(UInt32(pl.has_obs ? (is_x ? (pl.n_states > 0 ? 3 : 2) : 1) : 0)))
         wr(io, pl.y)
         aux = pl.weight === nothing ? pl.aux : vcat((vcat(pl.aux, [ZERO_ARG, ZERO_ARG]))[1:2], [pl.weight])
         wr3(io, aux)
@@ -175,6 +183,7 @@ mutable struct Stmt
     is_gq::Bool
     ragged::Bool
     obs_mask::Union{Nothing,Array{Bool}}
+    zobs::Union{Nothing,Array{Float64}}       # a discrete latent being summed out, partially observed: state number + 1 per cell, 0 = missing
 end
 name_of(s::Stmt) = s.lhs isa Symbol ? s.lhs : s.lhs.args[1]
 lhs_idx(s::Stmt) = s.lhs isa Symbol ? Any[] : s.lhs.args[2:end]
@@ -217,9 +226,9 @@ function flatten!(out::Vector{Stmt}, block, loops)
             #  bounds and keeps the inner distribution; not ported to this file yet -- refuse rather than mis-evaluate)
             (st.args[3] isa Expr && st.args[3].head == :call && st.args[3].args[1] in (:censored, :truncated)) &&
                 fail("censored / truncated statements are lowered by the Python front end only")
-            push!(out, Stmt(length(out) + 1, true, st.args[2], binarize(st.args[3]), loops, Tuple{Int,Int}[], :none, false, false, nothing))
+            push!(out, Stmt(length(out) + 1, true, st.args[2], binarize(st.args[3]), loops, Tuple{Int,Int}[], :none, false, false, nothing, nothing))
         elseif st isa Expr && st.head == :(=)
-            push!(out, Stmt(length(out) + 1, false, st.args[1], binarize(st.args[2]), loops, Tuple{Int,Int}[], :none, false, false, nothing))
+            push!(out, Stmt(length(out) + 1, false, st.args[1], binarize(st.args[2]), loops, Tuple{Int,Int}[], :none, false, false, nothing, nothing))
         else
             fail("unsupported statement $(st)")
         end
@@ -252,8 +261,10 @@ end
 mutable struct DataEval
     data::Dict{Symbol,Any}
     lenient::Bool          # clamp out-of-range / missing subscripts (case-split leaves, lowering.py:139-146)
+    unknown::Set{Symbol}   # arrays that are partly data, partly unknown (a partially observed discrete latent): not data
 end
-known(de::DataEval, e, lvs=Symbol[]) = all(v -> haskey(de.data, v) || v in lvs, free_vars(e))
+DataEval(data, lenient) = DataEval(data, lenient, Set{Symbol}())
+known(de::DataEval, e, lvs=Symbol[]) = all(v -> (haskey(de.data, v) && !(v in de.unknown)) || v in lvs, free_vars(e))
 logistic(x) = 1 / (1 + exp(-x))
 function ev(de::DataEval, e, lv::Dict{Symbol,Int})
     e isa Number && return Float64(e)
@@ -307,11 +318,14 @@ function ev(de::DataEval, e, lv::Dict{Symbol,Int})
         f == :__le__ && return a[1] <= a[2] ? 1.0 : 0.0
         f == :__and__ && return (a[1] != 0 && a[2] != 0) ? 1.0 : 0.0
         f == :phi && return 0.5 * erfc_(-a[1] / sqrt(2.0))
+        f == :loggam && return lgamma_(a[1])
+        f == :logfact && return lgamma_(a[1] + 1.0)
         fail("function $(f) is not supported in data expressions")
     end
     fail("cannot evaluate $(e)")
 end
 erfc_(x) = ccall(:erfc, Float64, (Float64,), x)     # libm; avoids a SpecialFunctions dependency in this file
+lgamma_(x) = ccall(:lgamma, Float64, (Float64,), x)
 
 "values of `e` over the loop domain `extents` (column-major Julia array, one axis per loop variable)"
 function grid(de::DataEval, e, lvs::Vector{Symbol}, extents)
@@ -337,6 +351,9 @@ mutable struct Lowering
     slot_ids::Dict{String,Int}
     gval_ids::Dict{String,Int}
     cur_extents::Vector{Tuple{Int,Int}}
+    marginalize::Bool                                  # UseAutoMarginalization: finite discrete latents are summed out, not in theta
+    latent::Any                                        # (statement of the latent summed out in the plate being built, K) | nothing
+    latent_sibs::Dict{Int,Vector{Stmt}}                # sid of a plate's observation -> further observed children of its latent
 end
 
 label(name, idx) = isempty(idx) ? string(name) : string(name, "[", join(idx, ","), "]")
@@ -368,7 +385,21 @@ function classify!(lw::Lowering)
         else
             s.ragged && fail("stochastic statement '$(name_of(s))' in a loop with ragged bounds")
             obs = grid_flags(lw, s)
-            if all(obs)
+            fn = s.rhs.args[1]
+            if lw.marginalize && !all(obs) && (fn == :dcat || fn == :dbern)
+                # an unobserved finite discrete node: summed out (lowering.py _classify).  Partially observed
+                # (auto_marginalization.jl:391-462): the observed cells take the branch of their value, recorded as
+                # state number + 1 (a dcat value k is state k - 1, a dbern value v is state v)
+                s.kind = :latent
+                if any(obs)
+                    vals = grid(lw.de, s.lhs, loop_vars(s), s.extents)
+                    s.zobs = [obs[k] ? vals[k] + (fn == :dbern ? 1.0 : 0.0) : 0.0 for k in eachindex(vals)]
+                    s.zobs = reshape(s.zobs, size(vals))
+                    push!(lw.de.unknown, name_of(s))
+                end
+            elseif lw.marginalize && !all(obs) && fn == :dbin
+                fail("'$(name_of(s))': only dcat and dbern latents are summed out")
+            elseif all(obs)
                 s.kind = :obs
             elseif !any(obs)
                 s.kind = :param
@@ -388,7 +419,7 @@ function classify!(lw::Lowering)
     end
     # generated quantities: a statement all of whose instances the reference classified as GeneratedQuantity
     for s in lw.stmts
-        (s.kind == :param || s.kind == :logical) || continue
+        (s.kind == :param || s.kind == :logical || s.kind == :latent) || continue
         s.ragged && continue
         s.is_gq = all(instances(lw, s)) do lab
             info = get(lw.node_info, lab, nothing)
@@ -762,7 +793,61 @@ function vector_globals(lw::Lowering)
             end
         end
     end
+    # (3) parameter vectors subscripted by a discrete latent that is summed out, directly (mu[z[i]]) or through a derived
+    # subscript (x1[i] = x[i] + 1; phi[x1[i], d1[i]]), and the looped parameters behind a logical vector selected that way
+    latents = Set{Symbol}(name_of(d) for d in lw.stmts if d.kind == :latent)
+    if !isempty(latents)
+        function mentions_latent(i)
+            (is_range(i) || is_colon(i)) && return false
+            e = try
+                inline(lw, i)
+            catch err
+                err isa LoweringError || rethrow()
+                return false
+            end
+            return any(r -> (r isa Symbol ? r : r.args[1]) in latents, latent_candidates(e))
+        end
+        function walk_latent(e, via::Bool)
+            if is_ref(e)
+                if via || any(mentions_latent, e.args[2:end])
+                    for d in defs(lw, e.args[1])
+                        if looped_param(d)
+                            size_of(d) > 48 && fail("'$(e.args[1])' has too many elements to expand into scalar globals")
+                            push!(found, d.sid)
+                        elseif d.kind == :logical && !isempty(d.loops)
+                            walk_latent(d.rhs, true)
+                        end
+                    end
+                end
+                foreach(i -> walk_latent(i, false), e.args[2:end])
+            elseif e isa Expr && e.head == :call
+                foreach(a -> walk_latent(a, via), e.args[2:end])
+            end
+        end
+        for s in lw.stmts
+            (s.kind == :obs && !s.is_gq) && foreach(a -> walk_latent(a, false), s.rhs.args[2:end])
+        end
+    end
     return found
+end
+
+"every symbol and `name[...]` reference inside `e` (candidates for a reference to a latent), subscripts included"
+function latent_candidates(e, acc=Any[])
+    if e isa Symbol
+        push!(acc, e)
+    elseif is_ref(e)
+        push!(acc, e)
+        foreach(i -> latent_candidates(i, acc), e.args[2:end])
+    elseif e isa Expr && e.head == :call
+        foreach(a -> latent_candidates(a, acc), e.args[2:end])
+    end
+    return acc
+end
+"`e` with every occurrence of the sub-expression `target` replaced by `new`"
+function replace_sub(e, target, new)
+    e == target && return new
+    e isa Expr || return e
+    return Expr(e.head, Any[k == 1 && (e.head == :call || e.head == :ref) ? a : replace_sub(a, target, new) for (k, a) in enumerate(e.args)]...)
 end
 
 # ---- one plate (lowering.py _build_plate ...) ------------------------------------------------------------------------------------
@@ -843,7 +928,7 @@ function build_linear_plate!(lw::Lowering, s0::Stmt, used::Set{Int})
         end
         if firsts == Set{Any}([loop_vars(s)[2]])
             s = Stmt(s.sid, s.stoch, s.lhs, s.rhs, reverse(s.loops), reverse(s.extents), s.kind, s.is_gq, s.ragged,
-                     s.obs_mask === nothing ? nothing : permutedims(s.obs_mask))
+                     s.obs_mask === nothing ? nothing : permutedims(s.obs_mask), s.zobs === nothing ? nothing : permutedims(s.zobs))
         end
     end
     lvs, shp = loop_vars(s), shape_of(s)
@@ -918,9 +1003,14 @@ end
 function build_xplate!(lw::Lowering, s::Stmt, fam, used::Set{Int})
     lvs, shp = loop_vars(s), shape_of(s)
     lw.cur_extents = s.extents
-    isempty(shp) && fail("a scalar observation with a non-linear predictor is outside the plate class")
-    plate = Plate(shp[1], length(shp) == 2 ? shp[2] : 1; family=fam, eta_arg=0, name="$(name_of(s))~$(s.rhs.args[1]) (expression tape)")
-    plate.y = data_arg(lw, s.lhs, lvs, shp)
+    plate = Plate(isempty(shp) ? 1 : shp[1], length(shp) == 2 ? shp[2] : 1; family=fam, eta_arg=0,
+                  name="$(name_of(s))~$(s.rhs.args[1]) (expression tape)")
+    if isempty(shp)
+        # a scalar observation (y ~ dnorm(mu + delta[z], tau)): a plate of one cell
+        plate.y = Arg(ARG_DATA_I, slot!(lw, "scalar_obs|$(name_of(s))", [Float64(ev(lw.de, s.lhs, Dict{Symbol,Int}()))]))
+    else
+        plate.y = data_arg(lw, s.lhs, lvs, shp)
+    end
     plate.y.kind in (ARG_CONST, ARG_ONE, ARG_DATA_J) && fail("observation does not vary over its plate")
     args = Any[s.rhs.args[2:end]...]
     if fam == FAM_CATEGORICAL
@@ -930,6 +1020,7 @@ function build_xplate!(lw::Lowering, s::Stmt, fam, used::Set{Int})
         args = Any[Expr(:ref, pa.args[1:(end - 1)]..., s.lhs)]      # p[.., y]: the element picked by the observed category
     end
     tape, memo = XOp[], Dict{String,Int}()
+    lw.latent = nothing      # (statement of the discrete latent summed out in this plate, K), found while taping
     lw.de.lenient = true
     try
         for a in args
@@ -947,9 +1038,146 @@ function build_xplate!(lw::Lowering, s::Stmt, fam, used::Set{Int})
     end
     ((fam == FAM_T || fam == FAM_BETABIN) && plate.aux[3].kind != ARG_CONST) && fail("the degrees of freedom of dt must be a constant")
     isempty(tape) && fail("internal: an expression plate without a tape")
+    if lw.latent !== nothing
+        z, K = lw.latent
+        wa = z.rhs.args[2]
+        push_raw(op::XOp) = (push!(tape, op); length(tape) > MAX_XOPS && fail("the predictor needs more than $(MAX_XOPS) tape ops"); length(tape) - 1)
+        lw.de.lenient = true
+        try
+            if z.rhs.args[1] == :dbern
+                # log p(z = 0) = log(1 - theta), log p(z = 1) = log(theta): two candidates picked by the state
+                c0 = tape!(lw, Expr(:call, :log, Expr(:call, :-, 1.0, wa)), s, plate, tape, memo, used)
+                c1 = tape!(lw, Expr(:call, :log, wa), s, plate, tape, memo, used)
+                first = length(tape)
+                push_raw(XOp(OP_IDENTITY, c0)); push_raw(XOp(OP_IDENTITY, c1))
+                plate.logprior_slot = push_raw(XOp(OP_PICK_K, first))
+            else
+                # log p(z = k): the latent's own dcat(w[1:K]) picked at the state
+                pk = Expr(:ref, wa.args[1:(end - 1)]..., z.lhs)
+                plate.logprior_slot = tape!(lw, Expr(:call, :log, pk), s, plate, tape, memo, used)
+            end
+            for t in get(lw.latent_sibs, s.sid, Stmt[])
+                sl = tape!(lw, inline(lw, sibling_logpdf(t, s)), s, plate, tape, memo, used)
+                plate.logprior_slot = push_raw(XOp(OP_ADD, plate.logprior_slot, sl))
+                plate.name *= " + $(name_of(t))~$(t.rhs.args[1])"
+            end
+        finally
+            lw.de.lenient = false
+        end
+        plate.n_states = K
+        if z.zobs !== nothing
+            (length(z.loops) in (1, 2) && length(z.loops) == length(s.loops)) ||
+                fail("'$(name_of(z))': a partially observed latent must be indexed like its observation")
+            zo = z.zobs
+            any(v -> v != floor(v) || v < 0 || v > K, zo) && fail("'$(name_of(z))': observed states must be integers in 1..$(K)")
+            leaf = ndims(zo) == 1 ? Arg(ARG_DATA_I, slot!(lw, "latent_obs|$(name_of(z))", copy(zo))) :
+                   Arg(ARG_DATA_IJ, slot!(lw, "latent_obs|$(name_of(z))", copy(zo); rank=2, dim0=size(zo, 1)))
+            plate.zobs_slot = push_raw(XOp(OP_LEAF, 0, 0, 0, leaf))
+        end
+        plate.name *= ", $(name_of(z)) summed out over $(K) states"
+        push!(used, z.sid)
+        lw.latent = nothing
+    elseif !isempty(get(lw.latent_sibs, s.sid, Stmt[]))
+        fail("'$(name_of(s))': internal: the shared latent was not found while taping")
+    end
     plate.xops = tape
     apply_obs_mask!(lw, plate, s)
     return plate
+end
+
+"(latent statement, K) when `ie` is a reference `z[i]` / `z` to a discrete latent of this plate that is being summed out, else nothing (lowering.py _latent_ref)"
+function latent_ref(lw::Lowering, ie, s::Stmt)
+    (ie isa Symbol || is_ref(ie)) || return nothing
+    nm = ie isa Symbol ? ie : ie.args[1]
+    ds = [d for d in defs(lw, nm) if d.kind == :latent]
+    isempty(ds) && return nothing
+    d = ds[1]
+    (length(ds) == 1 && length(d.loops) <= length(s.loops) && d.loops == s.loops[1:length(d.loops)] && !d.is_gq) ||
+        fail("'$(nm)': a discrete latent must share the loop nest of the observation it selects for")
+    idx = ie isa Symbol ? Any[] : ie.args[2:end]
+    string.(idx) == string.(lhs_idx(d)) || fail("'$(nm)' must be referenced with the subscripts of its own statement")
+    K = 2   # dbern: states 0, 1 (value of state k: k); a dcat latent has the states 1..K (value of state k: k + 1)
+    if d.rhs.args[1] != :dbern
+        wa = d.rhs.args[2]
+        (is_ref(wa) && is_range(wa.args[end]) && is_data(lw, wa.args[end].args[2], Symbol[]) && is_data(lw, wa.args[end].args[3], Symbol[]) &&
+         Int(ev(lw.de, wa.args[end].args[2], Dict{Symbol,Int}())) == 1) ||
+            fail("the latent's dcat needs a probability vector w[..., 1:K] with constant K")
+        K = Int(ev(lw.de, wa.args[end].args[3], Dict{Symbol,Int}()))
+        1 <= K <= MAX_STATES || fail("between 1 and $(MAX_STATES) states can be summed out per observation")
+    end
+    (lw.latent !== nothing && lw.latent[1].sid != d.sid) && fail("one discrete latent per observation plate")
+    lw.latent = (d, K)
+    return d, K
+end
+
+"sids of the summed-out latent statements the arguments of observation statement `s` depend on (lowering.py _latents_of)"
+function latents_of(lw::Lowering, s::Stmt)
+    latents = Dict{Symbol,Int}(name_of(d) => d.sid for d in lw.stmts if d.kind == :latent)
+    out = Int[]
+    isempty(latents) && return out
+    for a in s.rhs.args[2:end]
+        e = try
+            inline(lw, a)
+        catch err
+            err isa LoweringError || rethrow()
+            continue
+        end
+        for r in latent_candidates(e)
+            nm = r isa Symbol ? r : r.args[1]
+            (haskey(latents, nm) && !(latents[nm] in out)) && push!(out, latents[nm])
+        end
+    end
+    return out
+end
+
+"""log density of observation statement `t` -- a second child of the latent summed out in the plate of `s` -- as an
+expression for the tape (lowering.py _sibling_logpdf); the family's argument checks are not reproduced for a folded statement"""
+function sibling_logpdf(t::Stmt, s::Stmt)
+    (t.loops == s.loops && !t.ragged && t.obs_mask === nothing) ||
+        fail("'$(name_of(t))': a second observation of a summed-out latent must be fully observed and share the loop nest of the first")
+    y, fn, a = t.lhs, t.rhs.args[1], t.rhs.args[2:end]
+    c(f, xs...) = Expr(:call, f, xs...)
+    fn == :dbern && return c(:__select__, y, c(:log, a[1]), c(:log, c(:-, 1.0, a[1])))
+    if fn == :dbin
+        norm = c(:-, c(:-, c(:loggam, c(:+, a[2], 1.0)), c(:loggam, c(:+, y, 1.0))), c(:loggam, c(:+, c(:-, a[2], y), 1.0)))
+        return c(:+, c(:+, c(:*, y, c(:log, a[1])), c(:*, c(:-, a[2], y), c(:log, c(:-, 1.0, a[1])))), norm)
+    end
+    if fn == :dnorm
+        r = c(:-, y, a[1])
+        return c(:-, c(:-, c(:*, 0.5, c(:log, a[2])), c(:*, c(:*, 0.5, a[2]), c(:*, r, r))), 0.5 * log(2.0 * pi))
+    end
+    fn == :dpois && return c(:-, c(:-, c(:*, y, c(:log, a[1])), a[1]), c(:logfact, y))
+    fail("'$(name_of(t))': a second observation of a summed-out latent must be dbern, dbin, dnorm or dpois")
+end
+
+"""`phi[2, d1[i]]`: an element of a short parameter array whose elements are globals, picked by data subscripts that vary
+over the plate -> nested selects over the index tuples that occur (lowering.py _global_pick)"""
+function global_pick(lw::Lowering, e, s::Stmt)
+    prefix = string(e.args[1], "[")
+    any(k -> startswith(k, prefix), keys(lw.gval_ids)) || return nothing
+    lvs = loop_vars(s)
+    any(i -> is_range(i) || is_colon(i) || !is_data(lw, i, lvs), e.args[2:end]) && return nothing
+    cols = [vec(grid(lw.de, i, lvs, s.extents)) for i in e.args[2:end]]
+    seen = s.obs_mask === nothing ? trues(length(cols[1])) : vec(s.obs_mask)
+    any(col -> any(isnan, col[seen]), cols) && fail("'$(e)': a subscript is missing for an observed cell")
+    tuples = sort(unique([Tuple(Int(col[k]) for col in cols) for k in eachindex(seen) if seen[k]]))
+    (isempty(tuples) || length(tuples) > 8) && fail("'$(e)': too many distinct elements picked by data subscripts")
+    out = nothing
+    for t in tuples
+        elem = Expr(:ref, e.args[1], (Float64(v) for v in t)...)
+        haskey(lw.gval_ids, something(elem_label(lw, elem), "")) || fail("'$(elem)' is not a parameter element")
+        if out === nothing
+            out = elem
+            continue
+        end
+        cond = nothing
+        for (i, v) in zip(e.args[2:end], t)
+            ci = Expr(:call, :equals, i, Float64(v))
+            cond = cond === nothing ? ci : Expr(:call, :*, cond, ci)
+        end
+        out = Expr(:call, :__select__, cond, elem, out)
+    end
+    return out
 end
 
 "append the ops computing `e` for one cell of the plate (common subexpressions shared); returns the 0-based slot"
@@ -983,13 +1211,60 @@ function tape!(lw::Lowering, e, s::Stmt, plate::Plate, tape::Vector{XOp}, memo::
     end
     is_call(e, :__nodef__) && return push_op(XOp(OP_LEAF, 0, 0, 0, const_arg(NaN)))
     is_data(lw, e, lvs) && return push_op(XOp(OP_LEAF, 0, 0, 0, data_arg(lw, e, lvs, shp)))
+    # K candidate slots gathered into consecutive identity copies behind a PICK_K op
+    function pick_k(slots::Vector{Int})
+        first = length(tape)
+        for sl in slots
+            push!(tape, XOp(OP_IDENTITY, sl))
+        end
+        return push_op(XOp(OP_PICK_K, first))
+    end
+    if lw.marginalize && (e isa Symbol || is_ref(e)) && latent_ref(lw, e, s) !== nothing
+        # the latent's own value in arithmetic (mu + delta * z[i]): a constant per state
+        z, K = latent_ref(lw, e, s)
+        v0 = z.rhs.args[1] == :dbern ? 0 : 1
+        first = length(tape)
+        for k in 0:(K - 1)
+            push!(tape, XOp(OP_LEAF, 0, 0, 0, const_arg(Float64(v0 + k))))
+        end
+        return push_op(XOp(OP_PICK_K, first))
+    end
     e isa Symbol && return push_op(XOp(OP_LEAF, 0, 0, 0, Arg(ARG_GVAL, gval_of(lw, string(e)))))
     if is_ref(e)
+        idx = e.args[2:end]
+        if lw.marginalize
+            lat = [q for (q, ie) in enumerate(idx) if latent_ref(lw, ie, s) !== nothing]
+            length(lat) > 1 && fail("a reference may use the discrete latent in one subscript only")
+            if length(lat) == 1
+                # name[.., z[i], ..]: the K candidates name[.., k, ..] in consecutive slots, picked by the state
+                z, K = latent_ref(lw, idx[lat[1]], s)
+                return pick_k(Int[rec(inline(lw, Expr(:ref, e.args[1], idx[1:(lat[1] - 1)]..., Float64(k), idx[(lat[1] + 1):end]...))) for k in 1:K])
+            end
+            # a subscript that is a FUNCTION of the latent (x1[i] = x[i] + 1; phi[x1[i], ..]): evaluated per state
+            for (q, ie) in enumerate(idx)
+                (is_range(ie) || is_colon(ie) || is_data(lw, ie, lvs)) && continue
+                ie2 = inline(lw, ie)
+                refs = [r for r in latent_candidates(ie2) if latent_ref(lw, r, s) !== nothing]
+                isempty(refs) && continue
+                z, K = latent_ref(lw, refs[1], s)
+                v0 = z.rhs.args[1] == :dbern ? 0 : 1
+                slots = Int[]
+                for k in 0:(K - 1)
+                    sub = replace_sub(ie2, refs[1], Float64(v0 + k))
+                    is_data(lw, sub, Symbol[]) || fail("a subscript built from the discrete latent must not depend on anything else that varies")
+                    cidx = Float64(Int(ev(lw.de, sub, Dict{Symbol,Int}())))
+                    push!(slots, rec(inline(lw, Expr(:ref, e.args[1], idx[1:(q - 1)]..., cidx, idx[(q + 1):end]...))))
+                end
+                return pick_k(slots)
+            end
+        end
         lab = elem_label(lw, e)
         lab !== nothing && haskey(lw.gval_ids, lab) && return push_op(XOp(OP_LEAF, 0, 0, 0, Arg(ARG_GVAL, lw.gval_ids[lab])))
         ref = (:l, e.args[1], e.args[2:end])
         is_gvec_ref(lw, s, ref) &&
             return push_op(XOp(OP_LEAF, 0, 0, 0, Arg(ARG_GVEC_J, lw.gval_ids[label(e.args[1], [s.extents[2][1]])])))
+        picked = global_pick(lw, e, s)
+        picked !== nothing && return (memo[key] = rec(picked))
         return push_op(XOp(OP_LEAF, 0, 0, 0, Arg(ARG_LOCAL, local_index!(lw, plate, s, ref, used))))
     end
     is_neg(e) && return push_op(XOp(OP_NEG, rec(e.args[2])))
@@ -1287,9 +1562,32 @@ function build_plan!(lw::Lowering)
     used = Set{Int}(vec_sids)
     merged = Set{Int}()
     obs_stmts = [s for s in lw.stmts if s.kind == :obs]
+    # observation statements hanging off the same summed-out latent are ONE cell of the sum over its states: the first is
+    # the plate's observation, the others are folded into the state's log weight (sibling_logpdf)
+    empty!(lw.latent_sibs)
+    folded = Set{Int}()
+    if lw.marginalize
+        by_latent = Dict{Int,Vector{Stmt}}()
+        order = Int[]
+        for s in obs_stmts
+            s.is_gq && continue
+            for zs in latents_of(lw, s)
+                haskey(by_latent, zs) || (by_latent[zs] = Stmt[]; push!(order, zs))
+                push!(by_latent[zs], s)
+            end
+        end
+        for zs in order
+            ch = by_latent[zs]
+            length(ch) > 1 || continue
+            (haskey(lw.latent_sibs, ch[1].sid) || any(t -> t.sid in folded, ch)) &&
+                fail("observations shared between two discrete latents are outside the plate class")
+            lw.latent_sibs[ch[1].sid] = ch[2:end]
+            union!(folded, [t.sid for t in ch[2:end]])
+        end
+    end
     for s in obs_stmts
-        s.sid in merged && continue
-        sibs = siblings(lw, s, [t for t in obs_stmts if !(t.sid in merged) && t.sid != s.sid])
+        (s.sid in merged || s.sid in folded) && continue
+        sibs = siblings(lw, s, [t for t in obs_stmts if !(t.sid in merged) && t.sid != s.sid && !(t.sid in folded)])
         pl = if !isempty(sibs)
             union!(merged, [t.sid for t in sibs])
             build_merged_plate!(lw, vcat([s], sibs), used)
@@ -1310,13 +1608,16 @@ end
 
 `program`: the reconstructed model definition (second return value of `JuliaBUGS._generate_lowered_model_def`);
 `data`: data and transformed data by symbol (arrays with `missing`/NaN for unobserved cells); `node_info`: per
-variable label `(is_stochastic, is_observed, is_generated_quantity)` from `model.graph_evaluation_data`.
+variable label `(is_stochastic, is_observed, is_generated_quantity)` from `model.graph_evaluation_data`;
+`marginalize`: the reference's `UseAutoMarginalization` (evaluation.jl:739-961) -- unobserved `dcat` / `dbern` nodes are
+summed out per observation cell instead of being entries of theta (lowering.py, `marginalize=True`).
 """
-function lower_program(program::Expr, data::Dict{Symbol,Any}, node_info::Dict{String,Tuple{Bool,Bool,Bool}}; transformed::Bool=true)
+function lower_program(program::Expr, data::Dict{Symbol,Any}, node_info::Dict{String,Tuple{Bool,Bool,Bool}};
+                       transformed::Bool=true, marginalize::Bool=false)
     stmts = flatten!(Stmt[], program, Tuple{Symbol,Any,Any}[])
     lw = Lowering(stmts, DataEval(data, false), transformed, node_info, Dict{Int,Tuple{Int,Vector{Int}}}(), 0,
                   Plan(0, transformed, Global[], GOp[], DataSlot[], Plate[], Dense[]), Dict{String,Int}(), Dict{String,Int}(),
-                  Tuple{Int,Int}[])
+                  Tuple{Int,Int}[], marginalize, nothing, Dict{Int,Vector{Stmt}}())
     bounds!(lw)
     classify!(lw)
     order_parameters!(lw)

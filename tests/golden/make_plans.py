@@ -55,6 +55,14 @@ def cases():
     yield "gmm3_marginalised", tm.GMM3, {"N": 3, "y": np.array([-2.5, 0.5, 3.2])}, {"marginalize": True}
     yield "gmm_partially_observed_latent", tm.GMM_SHARED, {"N": 4, "y": np.array([1.0, 2.0, -1.0, 3.0]),
                                                           "z": np.array([2.0, np.nan, 1.0, np.nan])}, {"marginalize": True}
+    # Bernoulli latents: in arithmetic, behind a derived subscript and partially observed; Cervix (vol. 2) at full size
+    # -- two observed children per latent, a parameter array picked by a latent-derived and a data subscript
+    rng = np.random.default_rng(23)
+    y5 = 2.0 * rng.standard_normal(5)
+    yield "bern_latent_arith", tm.BERN_ARITH, {"N": 5, "y": y5}, {"marginalize": True}
+    yield "bern_latent_subscript_partially_observed", tm.BERN_SUBSCRIPT, {
+        "N": 5, "y": y5, "q": 0.1 + 0.8 * rng.random(5), "z": np.array([1.0, np.nan, 0.0, np.nan, np.nan])}, {"marginalize": True}
+    yield "cervix_marginalised", jbugs.examples.CERVIX, tm._cervix_data(), {"marginalize": True}
 
 
 def record(plan, lw):
