@@ -66,6 +66,7 @@ class Stmt:
     obs_mask: object = None        # partially observed statement: boolean array over the loop domain (True = observed)
     zobs: object = None            # discrete latent being summed out, partially observed: its value per cell, 0 = missing
     censor: object = None          # (lower, upper) expressions of `dist(...) C(lower, upper)`; Var("nothing") = no bound
+    trunc: object = None           # (lower, upper) expressions of `dist(...) T(lower, upper)` (truncated prior of a scalar parameter)
 
     @property
     def name(self):
@@ -98,8 +99,12 @@ def _flatten(stmts, loops=(), out=None):
         elif isinstance(s, Stoch) and s.dist.fn in ("censored", "truncated"):
             # dist(...) C(lower, upper): the statement keeps the inner distribution; the bounds are checked against the
             # observed values once the statement is classified (Lowering._check_censoring)
-            if s.dist.fn == "truncated" or len(s.dist.args) != 3 or not isinstance(s.dist.args[0], Call):
-                raise LoweringError("truncated distributions (T(,)) are outside the plate class")
+            if len(s.dist.args) != 3 or not isinstance(s.dist.args[0], Call):
+                raise LoweringError("malformed censoring / truncation suffix")
+            if s.dist.fn == "truncated":
+                # dist(...) T(lower, upper): the bounds become the support of a scalar parameter's prior (_truncation)
+                out.append(Stmt(len(out) + 1, Stoch(s.lhs, s.dist.args[0]), loops, trunc=(s.dist.args[1], s.dist.args[2])))
+                continue
             out.append(Stmt(len(out) + 1, Stoch(s.lhs, s.dist.args[0]), loops, censor=(s.dist.args[1], s.dist.args[2])))
         else:
             out.append(Stmt(len(out) + 1, s, loops))
@@ -1138,6 +1143,38 @@ class Lowering:
             return P.TR_LOG, lb, ub
         return P.TR_IDENTITY, lb, ub
 
+    def _truncation(self, s: Stmt, fam, dargs, sub):
+        """`x ~ dnorm(mu, tau) T(lower, upper)` (truncated(...), bugs_parser.jl:470-500) for a scalar parameter with
+        constant arguments and bounds: the bounds are the prior's support -- they pick the bijector like any bounded
+        support (Bijectors: log for a lower bound, scaled logit for both) -- and mark the global as truncated for the
+        evaluators, which fold the normaliser log(cdf(upper) - cdf(lower)) into the prior's constant
+        (include/jbugs_plan.h, jbugs_global.lb / ub)."""
+        if fam != P.FAM_NORMAL:
+            raise LoweringError(f"'{s.name}': T(,) is lowered for dnorm priors only")
+        if not self.transformed:
+            raise LoweringError(f"'{s.name}': truncated priors are evaluated in transformed space only")
+        if not all(self._is_data(a, ()) for a in dargs):
+            raise LoweringError(f"'{s.name}': a truncated prior needs constant arguments")
+        bounds = []
+        for b, none in zip(s.trunc, (-np.inf, np.inf)):
+            if isinstance(b, Var) and b.name == "nothing":
+                bounds.append(none)
+                continue
+            b = _subst(b, sub)
+            if not self._is_data(b, ()):
+                raise LoweringError(f"'{s.name}': truncation bounds must be constants")
+            bounds.append(float(self.de.ev(b, {})))
+        lb, ub = bounds
+        if not lb < ub:
+            raise LoweringError(f"'{s.name}': truncation needs lower < upper")
+        if math.isfinite(lb) and math.isfinite(ub):
+            return P.TR_LOGIT, lb, ub
+        if math.isfinite(lb):
+            return P.TR_LOG, lb, ub
+        if math.isfinite(ub):
+            return P.TR_UPPER, lb, ub
+        return P.TR_IDENTITY, lb, ub
+
     def _family(self, call: Call):
         if call.fn not in P.FAMILY_OF:
             raise LoweringError(f"distribution {call.fn} is outside the supported univariate families")
@@ -1158,6 +1195,10 @@ class Lowering:
         # (label, statement, loop-variable substitution): scalar parameters, plus the elements of small parameter
         # vectors that observation statements reference with constant subscripts (beta[1] * z[i, 1] + ...)
         vec = self._vector_globals()
+        for s in self.stmts:
+            if s.trunc is not None and s.kind != "tdata" and not (s.kind == "param" and not s.is_gq and (not s.loops or s.sid in vec)):
+                raise LoweringError(f"'{s.name}': T(,) is lowered for scalar parameters only (not for observations, "
+                                    "generated quantities or the parameters of a plate)")
         gitems = []
         for s in self.stmt_order:
             if s.kind != "param" or s.is_gq:
@@ -1180,6 +1221,8 @@ class Lowering:
             fam = self._family(s.node.dist)
             dargs = [_subst(a, sub) for a in s.node.dist.args]
             tr, lb, ub = self._transform_of(fam, dargs)
+            if s.trunc is not None:
+                tr, lb, ub = self._truncation(s, fam, dargs, sub)
             self.plan.globals.append(P.Global(lab, int(self.theta_index(s).ravel()[k]), tr, fam, [], lb, ub))
         for s in scalar_logicals:
             self._emit_gtape(self._labels_for(s)[0], s.node.rhs)

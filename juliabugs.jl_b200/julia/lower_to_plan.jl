@@ -39,7 +39,7 @@ const FAM_GAMMA, FAM_EXPONENTIAL, FAM_UNIFORM, FAM_BETA, FAM_LOGNORMAL = 1, 2, 3
 const FAM_BERNOULLI, FAM_BINOMIAL, FAM_FLAT, FAM_WEIBULL, FAM_CHISQ, FAM_T, FAM_CATEGORICAL = 6, 7, 9, 12, 14, 15, 17
 const FAM_BETABIN = 18   # dbetabin(a, b, n): the third argument (n) is a constant, like dt's degrees of freedom
 const DISCRETE = Set([6, 7, 8, 13, 16, 17, 18])
-const TR_IDENTITY, TR_LOG, TR_LOGIT = 0, 1, 2
+const TR_IDENTITY, TR_LOG, TR_LOGIT, TR_UPPER = 0, 1, 2, 3
 const OP_IDENTITY, OP_EXP, OP_LOGISTIC, OP_CEXPEXP, OP_PHI, OP_LOG, OP_SQRT, OP_NEG = 0:7
 const OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_LEAF, OP_SELECT, OP_PICK_K = 16, 17, 18, 19, 20, 32, 33, 34
 const LINK_OF = Dict(:exp => OP_EXP, :logistic => OP_LOGISTIC, :ilogit => OP_LOGISTIC, :cexpexp => OP_CEXPEXP,
@@ -184,6 +184,7 @@ mutable struct Stmt
     ragged::Bool
     obs_mask::Union{Nothing,Array{Bool}}
     zobs::Union{Nothing,Array{Float64}}       # a discrete latent being summed out, partially observed: state number + 1 per cell, 0 = missing
+    trunc::Any                                # (lower, upper) of `truncated(dist, lower, upper)` (BUGS T(,)) | nothing
 end
 name_of(s::Stmt) = s.lhs isa Symbol ? s.lhs : s.lhs.args[1]
 lhs_idx(s::Stmt) = s.lhs isa Symbol ? Any[] : s.lhs.args[2:end]
@@ -222,13 +223,22 @@ function flatten!(out::Vector{Stmt}, block, loops)
         elseif st isa Expr && st.head == :block
             flatten!(out, st, loops)
         elseif st isa Expr && st.head == :call && st.args[1] == :~
-            # (censored(dist, lower, upper) / truncated(...): jbugs/lowering.py checks the observed values against the
-            #  bounds and keeps the inner distribution; not ported to this file yet -- refuse rather than mis-evaluate)
-            (st.args[3] isa Expr && st.args[3].head == :call && st.args[3].args[1] in (:censored, :truncated)) &&
-                fail("censored / truncated statements are lowered by the Python front end only")
-            push!(out, Stmt(length(out) + 1, true, st.args[2], binarize(st.args[3]), loops, Tuple{Int,Int}[], :none, false, false, nothing, nothing))
+            # (censored(dist, lower, upper): jbugs/lowering.py checks the observed values against the bounds and keeps
+            #  the inner distribution; not ported to this file yet -- refuse rather than mis-evaluate)
+            (st.args[3] isa Expr && st.args[3].head == :call && st.args[3].args[1] == :censored) &&
+                fail("censored statements are lowered by the Python front end only")
+            if st.args[3] isa Expr && st.args[3].head == :call && st.args[3].args[1] == :truncated
+                # truncated(dist(...), lower, upper): the statement keeps the inner distribution, the bounds become the
+                # support of a scalar parameter's prior (truncation, below)
+                length(st.args[3].args) == 4 || fail("malformed truncated(...)")
+                inner, lo, hi = st.args[3].args[2:4]
+                push!(out, Stmt(length(out) + 1, true, st.args[2], binarize(inner), loops, Tuple{Int,Int}[], :none, false, false,
+                                nothing, nothing, (binarize(lo), binarize(hi))))
+                continue
+            end
+            push!(out, Stmt(length(out) + 1, true, st.args[2], binarize(st.args[3]), loops, Tuple{Int,Int}[], :none, false, false, nothing, nothing, nothing))
         elseif st isa Expr && st.head == :(=)
-            push!(out, Stmt(length(out) + 1, false, st.args[1], binarize(st.args[2]), loops, Tuple{Int,Int}[], :none, false, false, nothing, nothing))
+            push!(out, Stmt(length(out) + 1, false, st.args[1], binarize(st.args[2]), loops, Tuple{Int,Int}[], :none, false, false, nothing, nothing, nothing))
         else
             fail("unsupported statement $(st)")
         end
@@ -677,6 +687,30 @@ function transform_of(lw::Lowering, fam, args)
     isfinite(lb) && return TR_LOG, lb, ub
     return TR_IDENTITY, lb, ub
 end
+"""`x ~ truncated(dnorm(mu, tau), lower, upper)` for a scalar parameter with constant arguments and bounds (lowering.py
+_truncation): the bounds are the prior's support and pick the bijector; the evaluators fold log(cdf(upper) - cdf(lower))
+into the prior's constant (include/jbugs_plan.h, jbugs_global.lb / ub)"""
+function truncation(lw::Lowering, s::Stmt, fam, dargs, sub)
+    fam == FAM_NORMAL || fail("'$(name_of(s))': T(,) is lowered for dnorm priors only")
+    lw.transformed || fail("'$(name_of(s))': truncated priors are evaluated in transformed space only")
+    all(a -> is_data(lw, a, Symbol[]), dargs) || fail("'$(name_of(s))': a truncated prior needs constant arguments")
+    bounds = Float64[]
+    for (b, none) in zip(s.trunc, (-Inf, Inf))
+        if b === :nothing || b === nothing
+            push!(bounds, none)
+            continue
+        end
+        b = subst(b, sub)
+        is_data(lw, b, Symbol[]) || fail("'$(name_of(s))': truncation bounds must be constants")
+        push!(bounds, Float64(ev(lw.de, b, Dict{Symbol,Int}())))
+    end
+    lb, ub = bounds
+    lb < ub || fail("'$(name_of(s))': truncation needs lower < upper")
+    isfinite(lb) && isfinite(ub) && return TR_LOGIT, lb, ub
+    isfinite(lb) && return TR_LOG, lb, ub
+    isfinite(ub) && return TR_UPPER, lb, ub
+    return TR_IDENTITY, lb, ub
+end
 function family(lw::Lowering, call)
     f = call.args[1]
     haskey(FAMILY_OF, f) || fail("distribution $(f) is outside the supported univariate families")
@@ -928,7 +962,7 @@ function build_linear_plate!(lw::Lowering, s0::Stmt, used::Set{Int})
         end
         if firsts == Set{Any}([loop_vars(s)[2]])
             s = Stmt(s.sid, s.stoch, s.lhs, s.rhs, reverse(s.loops), reverse(s.extents), s.kind, s.is_gq, s.ragged,
-                     s.obs_mask === nothing ? nothing : permutedims(s.obs_mask), s.zobs === nothing ? nothing : permutedims(s.zobs))
+                     s.obs_mask === nothing ? nothing : permutedims(s.obs_mask), s.zobs === nothing ? nothing : permutedims(s.zobs), s.trunc)
         end
     end
     lvs, shp = loop_vars(s), shape_of(s)
@@ -1529,6 +1563,10 @@ end
 function build_plan!(lw::Lowering)
     lw.plan = Plan(lw.D, lw.transformed, Global[], GOp[], DataSlot[], Plate[], Dense[])
     vec_sids = vector_globals(lw)
+    for s in lw.stmts
+        (s.trunc !== nothing && !(s.kind == :param && !s.is_gq && (isempty(s.loops) || s.sid in vec_sids))) &&
+            fail("'$(name_of(s))': T(,) is lowered for scalar parameters only (not for observations, generated quantities or the parameters of a plate)")
+    end
     gitems = Tuple{String,Stmt,Dict{Symbol,Any},Int}[]
     for s in lw.stmts
         (s.kind == :param && !s.is_gq) || continue
@@ -1551,6 +1589,7 @@ function build_plan!(lw::Lowering)
         fam = family(lw, s.rhs)
         dargs = Any[subst(a, sub) for a in s.rhs.args[2:end]]
         tr, lb, ub = transform_of(lw, fam, dargs)
+        s.trunc === nothing || ((tr, lb, ub) = truncation(lw, s, fam, dargs, sub))
         push!(lw.plan.globals, Global(lab, vec(theta_index(lw, s))[k], tr, fam, Arg[], lb, ub))
     end
     for s in scalar_logicals

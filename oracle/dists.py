@@ -367,8 +367,41 @@ class Censored(Dist):
         return self.inner.logpdf(M, x)
 
 
+class TruncatedNormal(Dist):
+    """`truncated(dnorm(mu, tau), lower, upper)` (Distributions.truncated; the BUGS suffix T(lower, upper),
+    bugs_parser.jl:470-500): logpdf(x) = logpdf_Normal(x) - log(cdf(upper) - cdf(lower)) inside the bounds, -Inf outside;
+    the support -- hence the bijector -- is [lower, upper].  The normaliser is written for constant mu, tau and bounds
+    (half-normal / truncated-normal priors, e.g. Magnesium's `tau.sqrd[6] ~ dnorm(0, p0) T(0,)`); it needs the normal
+    cdf, computed from erfc on the side of the smaller tail so that the difference does not cancel."""
+
+    def __init__(self, M, inner, lower, upper):
+        if not isinstance(inner, Normal):
+            raise NotImplementedError("T(,) is restated for dnorm only")
+        for v in (inner.mu, inner.sigma, lower, upper):
+            if not isinstance(v, (int, float)):
+                raise NotImplementedError("T(,) needs constant arguments and bounds")
+        self.inner, self.lower, self.upper = inner, float(lower), float(upper)
+        _check(self.lower < self.upper, "truncated requires lower < upper")
+        a, b = (self.lower - inner.mu) / inner.sigma, (self.upper - inner.mu) / inner.sigma
+        sf = lambda z: 0.5 * math.erfc(z / math.sqrt(2.0))     # noqa: E731  upper tail
+        cdf = lambda z: 0.5 * math.erfc(-z / math.sqrt(2.0))   # noqa: E731
+        mass = (sf(a) - sf(b)) if a > 0 else (cdf(b) - cdf(a))
+        self.logz = math.log(mass)
+
+    def support(self):
+        return (self.lower, self.upper)
+
+    def logpdf(self, M, x):
+        xv = _val(x)
+        if xv < self.lower or xv > self.upper:
+            return -M.inf
+        return self.inner.logpdf(M, x) - self.logz
+
+
 def make_dist(M, name, args):
     """BUGS distribution call -> distribution object (BUGSPrimitives/distributions.jl)."""
+    if name.startswith("truncated:"):
+        return TruncatedNormal(M, make_dist(M, name.split(":", 1)[1], args[:-2]), args[-2], args[-1])
     if name.startswith("censored:"):
         return Censored(M, make_dist(M, name.split(":", 1)[1], args[:-2]), args[-2], args[-1])
     if name == "dnorm":

@@ -247,12 +247,10 @@ def _flatten_bounds(stmts):
         if isinstance(s, For):
             out.append(For(s.var, s.lo, s.hi, _flatten_bounds(s.body)))
         elif isinstance(s, Stoch) and s.dist.fn in ("censored", "truncated"):
-            if s.dist.fn == "truncated":
-                raise NotImplementedError("truncated distributions (T(,)) are not part of the oracle")
             inner, lo, hi = s.dist.args
             lo = Num(-math.inf, False) if lo == Var("nothing") else lo
             hi = Num(math.inf, False) if hi == Var("nothing") else hi
-            out.append(Stoch(s.lhs, Call("censored:" + inner.fn, tuple(inner.args) + (lo, hi))))
+            out.append(Stoch(s.lhs, Call(s.dist.fn + ":" + inner.fn, tuple(inner.args) + (lo, hi))))
         else:
             out.append(s)
     return tuple(out)

@@ -407,6 +407,13 @@ static inline int64_t local_slot(const jbo_plan* p, const jbugs_local* l, int64_
     return l->theta_base + l->stride_i * i + l->stride_j * j;
 }
 
+/* log(Phi((ub - mu) sqrt(tau)) - Phi((lb - mu) sqrt(tau))), from erfc on the side of the smaller tail */
+static double truncnorm_logmass(double mu, double tau, double lb, double ub) {
+    const double sd = sqrt(1.0 / tau), a = (lb - mu) / sd, b = (ub - mu) / sd, r2 = sqrt(2.0);
+    const double mass = a > 0 ? 0.5 * erfc(a / r2) - 0.5 * erfc(b / r2) : 0.5 * erfc(-b / r2) - 0.5 * erfc(-a / r2);
+    return log(mass);
+}
+
 /* returns 0 ok, 1 domain error */
 static int eval_chain(const jbo_plan* p, chain_io io, int want_grad, double* logp_out) {
     double gval[MAXG], gadj[MAXG], gdxdy[MAXG], gdlj[MAXG];
@@ -451,6 +458,13 @@ static int eval_chain(const jbo_plan* p, chain_io io, int want_grad, double* log
         logp += lp;
         gadj[h] += dx;
         for (int q = 0; q < 3; ++q) argadj(&g->args[q], da[q], gadj, NULL);
+        /* truncated(dnorm(mu, tau), lb, ub) (the BUGS suffix T(lb, ub)): a dnorm global whose support bounds are
+           narrower than the real line; literal arguments only (checked at plan creation), so the normaliser
+           log(cdf(ub) - cdf(lb)) is a constant.  Outside the bounds (possible in untransformed space only): -Inf */
+        if (g->family == JBUGS_FAM_NORMAL && g->lb < g->ub && (isfinite(g->lb) || isfinite(g->ub))) {
+            if (gval[h] < g->lb || gval[h] > g->ub) return 1;
+            logp -= truncnorm_logmass(a[0], a[1], g->lb, g->ub);
+        }
     }
     /* plates */
     for (uint32_t pi = 0; pi < p->h.n_plates; ++pi) {

@@ -1,0 +1,98 @@
+"""Truncated priors, the BUGS suffix `T(lower, upper)` (`truncated(dist, lower, upper)`: J/src/parser/bugs_parser.jl:470-500;
+Magnesium's `tau.sqrd[6] ~ dnorm(0, p0) T(0, )`, J/src/BUGSExamples/Volume_1/06_Magnesium.jl:63): half-normal and
+truncated-normal priors of scalar parameters with constant arguments.  The bounds are the prior's support (bijector),
+the normaliser log(cdf(upper) - cdf(lower)) a constant: scipy.stats.truncnorm == per-node oracle == lowered plan through
+the C restatement == CUDA."""
+import numpy as np
+import pytest
+from scipy import stats as S
+
+import graph_oracle as go
+import jbugs
+from c_oracle import COracle
+from conftest import grad_err
+
+TEXT = """model {
+  s2 ~ dnorm(0, 0.25) T(0, )
+  m ~ dnorm(1, 4) T(-1, 2.5)
+  u ~ dnorm(0, 1) T(, 0.5)
+  for (k in 1:2) { c[k] ~ dnorm(3, 0.5) T(2, ) }
+  for (i in 1:N) { y[i] ~ dnorm(m + u + c[1] * x[i] + c[2], s2) }
+}"""
+rng = np.random.default_rng(31)
+DATA = {"N": 6, "y": rng.standard_normal(6) + 4.0, "x": rng.standard_normal(6)}
+
+
+def closed_form(names, theta):
+    """log joint in unconstrained space from scipy's truncated normal + the bijectors' log-Jacobians"""
+    ix = {n: i for i, n in enumerate(names)}
+    t = {n: theta[i] for n, i in ix.items()}
+    s2 = np.exp(t["s2"])
+    sg = 1.0 / (1.0 + np.exp(-t["m"]))
+    m = -1.0 + 3.5 * sg
+    u = 0.5 - np.exp(t["u"])
+    c = [2.0 + np.exp(t[f"c[{k}]"]) for k in (1, 2)]
+    lp = S.truncnorm(0, np.inf, loc=0, scale=2.0).logpdf(s2) + t["s2"]
+    lp += S.truncnorm((-1 - 1) / 0.5, (2.5 - 1) / 0.5, loc=1, scale=0.5).logpdf(m) + np.log((m + 1) * (2.5 - m) / 3.5)
+    lp += S.truncnorm(-np.inf, 0.5, loc=0, scale=1.0).logpdf(u) + t["u"]
+    sd = 1 / np.sqrt(0.5)
+    for k in (0, 1):
+        lp += S.truncnorm((2 - 3) / sd, np.inf, loc=3, scale=sd).logpdf(c[k]) + t[f"c[{k + 1}]"]
+    lp += S.norm(m + u + c[0] * DATA["x"] + c[1], 1 / np.sqrt(s2)).logpdf(DATA["y"]).sum()
+    return lp
+
+
+def test_oracle_and_plan_against_scipy():
+    gm = go.compile(TEXT, DATA, {}).use_generated_order()
+    plan, lw = jbugs.lower(TEXT, DATA)
+    names = lw.param_names()
+    assert names == gm.param_names() and plan.D == 5
+    theta = 0.7 * np.random.default_rng(2).standard_normal((plan.D, 5))
+    lp, g, st = COracle(plan).eval_batch(theta)
+    assert (st == 0).all()
+    for c in range(theta.shape[1]):
+        l0, g0 = gm.logdensity_and_gradient(theta[:, c])
+        assert l0 == pytest.approx(closed_form(names, theta[:, c]), abs=1e-11)
+        assert lp[c] == pytest.approx(l0, abs=1e-11)
+        assert grad_err(g[:, c], g0) < 1e-10
+
+
+def test_support_bounds_drive_the_bijector():
+    plan, lw = jbugs.lower(TEXT, DATA)
+    by = {g.name: g for g in plan.globals}
+    assert (by["s2"].transform, by["s2"].lb, by["s2"].ub) == (jbugs.plan.TR_LOG, 0.0, np.inf)
+    assert (by["m"].transform, by["m"].lb, by["m"].ub) == (jbugs.plan.TR_LOGIT, -1.0, 2.5)
+    assert (by["u"].transform, by["u"].lb, by["u"].ub) == (jbugs.plan.TR_UPPER, -np.inf, 0.5)
+    assert by["c[2]"].transform == jbugs.plan.TR_LOG and by["c[2]"].lb == 2.0
+
+
+@pytest.mark.parametrize("text", [
+    "model { a ~ dgamma(2, 1) T(0.5, )\n for (i in 1:N) { y[i] ~ dnorm(a, 1) } }",               # only dnorm is lowered
+    "model { t ~ dgamma(1, 1)\n a ~ dnorm(0, t) T(0, )\n for (i in 1:N) { y[i] ~ dnorm(a, 1) } }",   # argument is a parameter
+    "model { a ~ dnorm(0, 1)\n for (i in 1:N) { y[i] ~ dnorm(a, 1) T(0, ) } }",                  # truncated observation
+    "model { for (i in 1:N) { b[i] ~ dnorm(0, 1) T(0, )\n y[i] ~ dnorm(b[i], 1) } }",            # parameter of a plate
+])
+def test_what_is_not_lowered_raises(text):
+    # (N = 20: a short vector b[1:6] would be written out element by element as six truncated scalar parameters by the
+    # second reading of the lowering, which is fine)
+    with pytest.raises(jbugs.LoweringError):
+        jbugs.lower(text, {"N": 20, "y": np.linspace(-1.0, 1.0, 20)})
+
+
+def test_untransformed_space_is_refused():
+    with pytest.raises(jbugs.LoweringError):
+        jbugs.lower(TEXT, DATA, transformed=False)
+
+
+@pytest.mark.gpu
+def test_cuda_matches_c_port_and_scipy():
+    m = jbugs.compile(TEXT, DATA)
+    names = m.lowering.param_names()
+    theta = 0.7 * np.random.default_rng(3).standard_normal((m.plan.D, 70))
+    lp, g, st = m.cuda.eval_host(theta, layout="param_fast")
+    lp0, g0, st0 = COracle(m.plan).eval_batch(theta)
+    assert (st == 0).all() and (st0 == 0).all()
+    assert np.max(np.abs(lp - lp0) / np.maximum(1.0, np.abs(lp0))) < 1e-12
+    scale = np.maximum(np.abs(g0), 1e-4 * np.abs(g0).max(axis=0, keepdims=True))
+    assert np.max(np.abs(g - g0) / scale) < 1e-10
+    assert lp[0] == pytest.approx(closed_form(names, theta[:, 0]), abs=1e-10)
