@@ -488,7 +488,56 @@ model {
 }
 """
 
+# vol. 1, Magnesium: one meta-analysis under six priors for the between-study variance.  The `rtx[j, k] <- rt[k]` lines
+# are the double-definition idiom (the data transformation makes rtx / rcx observed); prior 6 is a half-normal, T(0, )
+MAGNESIUM = """
+model {
+    for (j in 1:6) {
+        mu[j] ~ dunif(-10, 10)
+        odds.ratio[j] <- exp(mu[j])
+        for (k in 1:8) {
+            theta[j, k] ~ dnorm(mu[j], inv.tau.sqrd[j])
+            rtx[j, k] ~ dbin(pt[j, k], nt[k])
+            rtx[j, k] <- rt[k]
+            rcx[j, k] ~ dbin(pc[j, k], nc[k])
+            rcx[j, k] <- rc[k]
+            logit(pt[j, k]) <- theta[j, k] + phi[j, k]
+            phi[j, k] <- logit(pc[j, k])
+            pc[j, k] ~ dunif(0, 1)
+        }
+    }
+    for (k in 1:8) {
+        y[k] <- log(((rt[k] + 0.5) / (nt[k] - rt[k] + 0.5)) / ((rc[k] + 0.5) / (nc[k] - rc[k] + 0.5)))
+        sigma.sqrd[k] <- 1 / (rt[k] + 0.5) + 1 / (nt[k] - rt[k] + 0.5) + 1 / (rc[k] + 0.5) + 1 / (nc[k] - rc[k] + 0.5)
+        prec.sqrd[k] <- 1 / sigma.sqrd[k]
+    }
+    s0.sqrd <- 1 / mean(prec.sqrd[1:8])
+    inv.tau.sqrd[1] ~ dgamma(0.001, 0.001)
+    tau.sqrd[1] <- 1 / inv.tau.sqrd[1]
+    tau[1] <- sqrt(tau.sqrd[1])
+    tau.sqrd[2] ~ dunif(0, 50)
+    tau[2] <- sqrt(tau.sqrd[2])
+    inv.tau.sqrd[2] <- 1 / tau.sqrd[2]
+    tau[3] ~ dunif(0, 50)
+    tau.sqrd[3] <- tau[3] * tau[3]
+    inv.tau.sqrd[3] <- 1 / tau.sqrd[3]
+    B0 ~ dunif(0, 1)
+    tau.sqrd[4] <- s0.sqrd * (1 - B0) / B0
+    tau[4] <- sqrt(tau.sqrd[4])
+    inv.tau.sqrd[4] <- 1 / tau.sqrd[4]
+    D0 ~ dunif(0, 1)
+    tau[5] <- sqrt(s0.sqrd) * (1 - D0) / D0
+    tau.sqrd[5] <- tau[5] * tau[5]
+    inv.tau.sqrd[5] <- 1 / tau.sqrd[5]
+    p0 <- phi(0.75) / s0.sqrd
+    tau.sqrd[6] ~ dnorm(0, p0) T(0, )
+    tau[6] <- sqrt(tau.sqrd[6])
+    inv.tau.sqrd[6] <- 1 / tau.sqrd[6]
+}
+"""
+
 MODELS = {
+    "magnesium": MAGNESIUM,
     "cervix": CERVIX,
     "orange": ORANGE,
     "mice": MICE,

@@ -127,7 +127,7 @@ def generated_quantities(lowering: Lowering, draws: Dict[str, np.ndarray], seed:
     for s in lw.stmts:
         if s.kind != "param" or s.is_gq:
             continue
-        labels = lw._labels_for(s)
+        labels = lw._labels_for(s, public=True)   # the names of the chain's columns
         if not all(l in draws for l in labels):
             continue
         if isinstance(s.node.lhs, Var):

@@ -294,19 +294,145 @@ class Lowering:
                 v = float(v)
             self.data[k] = v
         self.theta_order = theta_order
+        self._renamed: Dict[str, tuple] = {}   # names made by unrolling an outer loop -> (original name, position, value)
         try:
             self._lower_all(expand_picks=False)
         except LoweringError as first:
+            # (the parameter order of the program as written -- the reference's generated order -- when the first reading
+            # got as far as ordering its statements: the third reading must keep it)
+            try:
+                order_as_written = self.param_names() if hasattr(self, "theta_map") and self.D <= 100_000 else None
+            except Exception:
+                order_as_written = None
             # second reading: short parameter vectors picked by a data index written out as indicator sums (Kidney-style
             # factor levels); the gathered plate (b[school[i]]) stays the first choice
             try:
                 self._lower_all(expand_picks=True)
             except LoweringError as second:
+                # third reading: short outer loops around an inner loop written out iteration by iteration (Magnesium:
+                # `for j in 1:6` enumerates six priors, each iteration a model of its own over the studies k)
+                unrolled = self._unroll_outer_loops(self.stmts_ast)
+                if unrolled is not None and (self.theta_order is not None or order_as_written is not None):
+                    keep, keep_order = self.stmts_ast, self.theta_order
+                    try:
+                        self.stmts_ast = unrolled
+                        if self.theta_order is None:
+                            self.theta_order = order_as_written
+                        self._lower_all(expand_picks=False)
+                        return
+                    except LoweringError as third:
+                        self.stmts_ast, self._renamed, self.theta_order = keep, {}, keep_order
+                        raise LoweringError(f"{first} (with short outer loops written out: {third})") from None
+                    except Exception:
+                        self.stmts_ast, self._renamed, self.theta_order = keep, {}, keep_order
+                        raise first from None
                 if str(second) == str(first):
                     raise first from None
                 raise LoweringError(f"{first} (with data-index picks of short parameter vectors written out: {second})") from None
             except Exception:
                 raise first from None
+
+    def _unroll_outer_loops(self, stmts):
+        """top-level loops of at most 8 iterations that contain another loop, written out: the loop variable becomes a
+        constant, and every array DEFINED inside the loop with the loop variable as a plain subscript becomes one array
+        per iteration with that subscript dropped (`theta[j, k]` -> `theta<0:3>[k]`; labels map back, _labels_for), so
+        that each iteration is an ordinary model over the inner loop.  None when nothing applies or when such an array
+        is referenced in any other way (from outside the loop, or with another subscript in that position)."""
+        def has_inner(body):
+            return any(isinstance(b, For) for b in body)
+
+        def names_defined(body, acc):
+            for b in body:
+                if isinstance(b, For):
+                    names_defined(b.body, acc)
+                else:
+                    acc.append(b.lhs)
+            return acc
+
+        def all_exprs(body):
+            for b in body:
+                if isinstance(b, For):
+                    yield b.lo
+                    yield b.hi
+                    yield from all_exprs(b.body)
+                else:
+                    yield b.lhs
+                    yield b.rhs if isinstance(b, Det) else b.dist
+
+        de = DataEval(self.data)
+        out, did = [], False
+        renamed: Dict[str, tuple] = {}
+        for st in stmts:
+            if not (isinstance(st, For) and has_inner(st.body) and de.known(st.lo) and de.known(st.hi)):
+                out.append(st)
+                continue
+            lo, hi = int(de.ev(st.lo, {})), int(de.ev(st.hi, {}))
+            if not 1 <= hi - lo + 1 <= 8:
+                out.append(st)
+                continue
+            # arrays defined in the body, and the position of the loop variable in their subscripts
+            pos: Dict[str, int] = {}
+            for lhs in names_defined(st.body, []):
+                if isinstance(lhs, Index):
+                    qs = [q for q, i in enumerate(lhs.idx) if isinstance(i, Var) and i.name == st.var]
+                    if len(qs) != 1 or pos.setdefault(lhs.name, qs[0]) != qs[0]:
+                        return None
+                else:
+                    return None   # a scalar assigned inside a loop
+            others = [o for o in stmts if o is not st]
+            for e in all_exprs(others):
+                for r in _subexprs(e):
+                    if isinstance(r, (Index, Var)) and r.name in pos:
+                        return None
+            for e in all_exprs(st.body):
+                for r in _subexprs(e):
+                    if isinstance(r, Var) and r.name in pos:
+                        return None
+                    if isinstance(r, Index) and r.name in pos:
+                        q = pos[r.name]
+                        if q >= len(r.idx) or not (isinstance(r.idx[q], Var) and r.idx[q].name == st.var):
+                            return None
+
+            def rewrite(e, v):
+                if isinstance(e, Index):
+                    idx = tuple(rewrite(i, v) for i in e.idx)
+                    if e.name in pos:
+                        q = pos[e.name]
+                        new = f"{e.name}<{q}:{v}>"
+                        renamed[new] = (e.name, q, v)
+                        rest = idx[:q] + idx[q + 1:]
+                        return Index(new, rest) if rest else Var(new)
+                    return Index(e.name, idx)
+                if isinstance(e, Var):
+                    return Num(float(v), True) if e.name == st.var else e
+                if isinstance(e, Neg):
+                    return Neg(rewrite(e.a, v))
+                if isinstance(e, BinOp):
+                    return BinOp(e.op, rewrite(e.a, v), rewrite(e.b, v))
+                if isinstance(e, Call):
+                    return Call(e.fn, tuple(rewrite(a, v) for a in e.args))
+                if isinstance(e, Range):
+                    return Range(rewrite(e.lo, v), rewrite(e.hi, v))
+                return e
+
+            def rewrite_body(body, v):
+                res = []
+                for b in body:
+                    if isinstance(b, For):
+                        res.append(For(b.var, rewrite(b.lo, v), rewrite(b.hi, v), rewrite_body(b.body, v)))
+                    elif isinstance(b, Det):
+                        res.append(Det(rewrite(b.lhs, v), rewrite(b.rhs, v)))
+                    else:
+                        res.append(Stoch(rewrite(b.lhs, v), rewrite(b.dist, v)))
+                return tuple(res)
+
+            for v in range(lo, hi + 1):
+                out.extend(rewrite_body(st.body, v))
+            did = True
+        if not did:
+            return None
+        self._renamed = renamed
+        return tuple(out)
 
     def _lower_all(self, expand_picks: bool):
         self.de = DataEval(self.data)
@@ -673,6 +799,8 @@ class Lowering:
             rhs = s.node.rhs if isinstance(s.node, Det) else s.node.dist
             for v in free_vars(rhs):
                 for parent in by_name.get(v, []):
+                    if not self._may_reference(rhs, s, parent):
+                        continue   # tau[2] <- sqrt(tau.sqrd[2]) does not depend on the statement tau.sqrd[3] <- tau[3] * tau[3]
                     if parent.sid != s.sid:
                         self.children[parent.sid].add(s.sid)
                     elif s.kind in ("param", "logical", "latent"):
@@ -710,6 +838,43 @@ class Lowering:
                 elif s.kind == "logical":
                     s.is_gq = not any(by_sid[c].kind == "param" or not by_sid[c].is_gq
                                       for c in self.children[s.sid])
+
+    def _const_lhs(self, s: Stmt):
+        """the constant subscripts of a loop-free statement `name[c1, c2] ...` as a tuple, else None"""
+        lhs = s.node.lhs
+        if s.loops or not isinstance(lhs, Index) or any(isinstance(i, (Range, Colon)) or not self._is_data(i, ()) for i in lhs.idx):
+            return None
+        return tuple(int(self.de.ev(i, {})) for i in lhs.idx)
+
+    def _may_reference(self, rhs, s: Stmt, parent: Stmt) -> bool:
+        """can an expression of statement `s` read an element that statement `parent` defines?  Element-wise definitions
+        (Magnesium: inv.tau.sqrd[1] ~ ..., inv.tau.sqrd[2] <- 1 / tau.sqrd[2], ...) are told apart by their constant
+        subscripts; everything else depends by name, as the statement-level graph of the reference's lowering does"""
+        want = self._const_lhs(parent)
+        if want is None:
+            return True
+        for r in _subexprs(rhs):
+            if isinstance(r, Var) and r.name == parent.name:
+                return True
+            if isinstance(r, Index) and r.name == parent.name:
+                if len(r.idx) != len(want):
+                    return True
+                hit = True
+                for i, w in zip(r.idx, want):
+                    if isinstance(i, (Range, Colon)):
+                        continue
+                    if self._is_data(i, ()):
+                        if int(self.de.ev(i, {})) != w:
+                            hit = False
+                            break
+                    elif self._is_data(i, s.loop_vars) and s.extents and not s.ragged:
+                        vals = np.asarray(self.de.ev(i, _grids(s.extents, s.loop_vars)))
+                        if not np.any(vals == w):
+                            hit = False
+                            break
+                if hit:
+                    return True
+        return False
 
     # ---- E. parameter order -----------------------------------------------------------------------
     @staticmethod
@@ -782,19 +947,24 @@ class Lowering:
             have = set()
             for s in self.stmts:
                 if s.sid in self.theta_map:
-                    have.update(self._labels_for(s))
+                    have.update(self._labels_for(s, public=True))
             extra = set(order) - have
             if extra:
                 raise LoweringError(f"theta_order names unknown parameters: {sorted(extra)[:5]}")
 
     # ---- labels ----------------------------------------------------------------------------------------
-    def _labels_for(self, s: Stmt):
-        """variable labels of a parameter statement's instances in iteration order (small models only)."""
+    def _labels_for(self, s: Stmt, public=False):
+        """variable labels of a parameter statement's instances in iteration order (small models only); `public`: the
+        names a user sees (param_names, theta_order) -- arrays split by _unroll_outer_loops get their subscript back"""
         lhs = s.node.lhs
+        orig = self._renamed.get(lhs.name) if public else None
         if isinstance(lhs, Var):
-            return [lhs.name]
+            return [lhs.name] if orig is None else [f"{orig[0]}[{orig[2]}]"]
         lv = _grids(s.extents, s.loop_vars)
         idx = [np.broadcast_to(np.asarray(self.de.ev(ie, lv)), s.shape).ravel() for ie in lhs.idx]
+        if orig is not None:
+            idx = idx[:orig[1]] + [np.full(s.size, orig[2])] + idx[orig[1]:]
+            return [f"{orig[0]}[{','.join(str(int(i[k])) for i in idx)}]" for k in range(s.size)]
         return [f"{lhs.name}[{','.join(str(int(i[k])) for i in idx)}]" for k in range(s.size)]
 
     def param_names(self, limit=2_000_000):
@@ -805,7 +975,7 @@ class Lowering:
             if s.sid not in self.theta_map:
                 continue
             idx = self.theta_index(s).ravel()
-            for lab, t in zip(self._labels_for(s), idx):
+            for lab, t in zip(self._labels_for(s, public=True), idx):
                 names[int(t)] = lab
         return names
 
@@ -823,7 +993,7 @@ class Lowering:
 
     def _theta_index_custom(self, s: Stmt):
         pos = {lab: k for k, lab in enumerate(self.theta_order)}
-        labs = self._labels_for(s)
+        labs = self._labels_for(s, public=True)
         try:
             return np.asarray([pos[l] for l in labs], dtype=np.int64).reshape(s.shape if s.shape else ())
         except KeyError as e:
@@ -1253,9 +1423,14 @@ class Lowering:
             if s.sid in merged or s.sid in folded:
                 continue
             sibs = self._siblings(s, [t for t in obs_stmts if t.sid not in merged and t.sid != s.sid and t.sid not in folded])
+            xsibs = [] if sibs else self._xsiblings(s, [t for t in obs_stmts if t.sid not in merged and t.sid != s.sid
+                                                              and t.sid not in folded])
             if sibs:
                 merged.update(t.sid for t in sibs)
                 pl = self._build_merged_plate([s] + sibs, used_locals)
+            elif xsibs:
+                merged.update(t.sid for t in xsibs)
+                pl = self._build_merged_xplate([s] + xsibs, used_locals)
             else:
                 pl = self._build_plate(s, used_locals)
             if pl is not None:
@@ -1719,6 +1894,11 @@ class Lowering:
                 return push(P.XOp(P.OP_POW, ia, ib))
             if e.fn in P.UNARY_OF and len(e.args) == 1:
                 return push(P.XOp(P.UNARY_OF[e.fn], rec(e.args[0])))
+            if e.fn == "logit" and len(e.args) == 1:
+                # LogExpFunctions.logit(x) = log(x / (1 - x)), written out in tape arithmetic
+                x = e.args[0]
+                memo[key] = rec(Call("log", (BinOp("/", x, BinOp("-", Num(1.0), x)),)))
+                return memo[key]
         raise LoweringError(f"unsupported expression in a predictor: {_show(e)}")
 
     def _global_pick(self, e: Index, s: Stmt):
@@ -1913,6 +2093,82 @@ class Lowering:
                 mine |= refs
                 grew = True
         return sibs
+
+    def _loop_param_refs(self, s: Stmt):
+        """names of the parameter statements of `s`'s own loop that its (inlined) arguments reference"""
+        out = set()
+        try:
+            exprs = [self._inline(a) for a in s.node.dist.args]
+        except LoweringError:
+            return out
+        for e in exprs:
+            for r in _subexprs(e):
+                if isinstance(r, Index) and any(d.kind == "param" and not d.is_gq and d.loops == s.loops for d in self._defs(r.name)):
+                    out.add(r.name)
+        return out
+
+    def _xsiblings(self, s: Stmt, others):
+        """observation statements of the same single loop and family as `s` that share a parameter of that loop with it
+        when their predictors are NOT all linear (Magnesium: rcx[k] ~ dbin(pc[k], nc[k]) next to
+        rtx[k] ~ dbin(logistic(theta[k] + logit(pc[k])), nt[k])): the columns of one N x K expression plate"""
+        if len(s.loops) != 1 or s.obs_mask is not None or s.censor is not None:
+            return []
+        mine = self._loop_param_refs(s)
+        if not mine:
+            return []
+        sibs, grew = [], True
+        while grew:
+            grew = False
+            for t in others:
+                if t in sibs or t.loops != s.loops or t.obs_mask is not None or t.censor is not None:
+                    continue
+                refs = self._loop_param_refs(t)
+                if not (refs & mine):
+                    continue
+                if t.node.dist.fn != s.node.dist.fn:
+                    raise LoweringError(f"'{s.name}' and '{t.name}' share a parameter of their loop but differ in family")
+                sibs.append(t)
+                mine |= refs
+                grew = True
+        return sibs
+
+    def _build_merged_xplate(self, stmts, used_locals) -> P.Plate:
+        """K observation statements of one loop as ONE expression plate with K cells per group: a synthetic inner loop
+        runs over the statements, every argument that is not data becomes a nested select on the statement number (a
+        0/1 data leaf of the tape), data arguments and the observations are stacked into N x K arrays"""
+        s0 = stmts[0]
+        N, K = s0.shape[0], len(stmts)
+        lv = _grids(s0.extents, s0.loop_vars)
+        col = "__stmt__"
+        names = "+".join(t.name for t in stmts)
+        ivar = Var(s0.loop_vars[0])
+
+        def stacked(key, exprs):
+            M = np.empty((s0.extents[0][1], K))   # addressed with the loop variable's own values (1-based)
+            M[:] = np.nan
+            for k, e in enumerate(exprs):
+                M[s0.extents[0][0] - 1:, k] = np.broadcast_to(np.asarray(self.de.ev(e, lv), dtype=np.float64), (N,))
+            self.data[key] = M
+            return Index(key, (ivar, Var(col)))
+
+        fn = s0.node.dist.fn
+        nargs = len(s0.node.dist.args)
+        args = []
+        for q in range(nargs):
+            exprs = [self._inline(t.node.dist.args[q]) for t in stmts]
+            if all(self._is_data(e, s0.loop_vars) for e in exprs):
+                args.append(stacked(f"__merged|{names}|arg{q}", exprs))
+                continue
+            e = exprs[0]
+            for k in range(1, K):
+                e = Call("__select__", (Call("equals", (Var(col), Num(float(k + 1), True))), exprs[k], e))
+            args.append(e)
+        ylhs = stacked(f"__merged|{names}|y", [t.node.lhs if isinstance(t.node.lhs, Index) else Var(t.node.lhs.name) for t in stmts])
+        syn = Stmt(s0.sid, Stoch(ylhs, Call(fn, tuple(args))), s0.loops + ((col, Num(1.0, True), Num(float(K), True)),),
+                   extents=s0.extents + ((1, K),), kind="obs")
+        plate = self._build_xplate(syn, self._family(syn.node.dist), used_locals)
+        plate.name = f"{names}~{fn} (merged expression tape)"
+        return plate
 
     def _columns_arg(self, key, cols, N) -> P.Arg:
         """an argument that takes the value cols[k][i] in column k: CONST, DATA_J (constant in i), DATA_I

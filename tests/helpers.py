@@ -25,14 +25,20 @@ ZOO = [
     ("leuk", ex.LEUK, "leuk", "inits"),               # Y[i,j] * exp(beta * Z[i]) * dL0[j] as a Poisson mean
     ("mice", ex.MICE, "mice", "inits"),               # censored Weibull: the censored cells are missing, hence outside the target
     ("orange", ex.ORANGE, "orange", "inits"),         # vol. 2: a coefficient vector per group, theta[i, 1:3], column by column
-    ("kidney", ex.KIDNEY, "kidney", "inits"),         # + rows without any observed cell dropped (their b[i] leave theta), factor levels by data index
+    ("kidney", ex.KIDNEY, "kidney", "inits"),
+    # six priors enumerated by a short outer loop (written out iteration by iteration), two observation statements per
+    # study sharing pc[j, k] with a non-linear predictor (one merged expression plate per prior), a half-normal T(0, )
+    ("magnesium", ex.MAGNESIUM, "magnesium", "inits"),         # + rows without any observed cell dropped (their b[i] leave theta), factor levels by data index
 ]
 
 
 def start_theta(name, D, graph_model=None):
     """a finite starting point in unconstrained space for each example."""
     if graph_model is not None:
-        th = graph_model.getparams()
+        try:
+            th = graph_model.getparams()
+        except ZeroDivisionError:   # partial inits (Magnesium): a derived precision is 1 / 0 at the zero-filled start
+            th = np.full(D, np.nan)
         if np.all(np.isfinite(th)):
             return th
     return np.zeros(D)
