@@ -428,6 +428,13 @@ class Lowering:
 
             for v in range(lo, hi + 1):
                 out.extend(rewrite_body(st.body, v))
+                # data of a split array (observations y[j, k]; partly observed arrays keep their NaN): one slice per iteration
+                for name, q in pos.items():
+                    arr = self.data.get(name)
+                    if isinstance(arr, np.ndarray):
+                        if q >= arr.ndim or v > arr.shape[q]:
+                            return None
+                        self.data[f"{name}<{q}:{v}>"] = np.take(arr, v - 1, axis=q) if arr.ndim > 1 else float(arr[v - 1])
             did = True
         if not did:
             return None
@@ -1124,6 +1131,14 @@ class Lowering:
             return P.Arg.gval(self._gval_ids[e.name])
         if isinstance(e, Index) and self._elem_label(e) in self._gval_ids:
             return P.Arg.gval(self._gval_ids[self._elem_label(e)])
+        if isinstance(e, Index) and self._elem_label(e) is not None and isinstance(self.data.get(e.name), np.ndarray):
+            # a data element of an array that is partly parameters (prec[3] <- 0.7 next to prec[1] ~ dgamma(...))
+            try:
+                v = float(self.data[e.name][tuple(int(self.de.ev(i, {})) - 1 for i in e.idx)])
+            except IndexError:
+                v = float("nan")
+            if not math.isnan(v):
+                return P.Arg.const(v)
         raise LoweringError(f"distribution argument {e!r} must be a constant, data, or a scalar parameter")
 
     def _elem_label(self, e) -> Optional[str]:

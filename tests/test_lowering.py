@@ -267,3 +267,71 @@ def test_factor_levels_picked_by_a_data_index():
     data["t.cen"][0, 0] = data["t"][0, 0]
     with pytest.raises(jbugs.LoweringError, match="censoring bounds"):
         jbugs.lower(text, data)
+
+
+# ---- third reading: short outer loops written out, sibling statements with non-linear predictors merged ---------------
+OUTER_LINEAR = """model {
+  prec[1] ~ dgamma(2, 1)
+  s[2] ~ dunif(0.5, 3)
+  prec[2] <- 1 / (s[2] * s[2])
+  prec[3] <- 0.7
+  for (j in 1:3) {
+    m[j] ~ dnorm(0, prec[j])
+    for (k in 1:K) {
+      th[j, k] ~ dnorm(m[j], 2.0)
+      y[j, k] ~ dpois(lam[j, k])
+      log(lam[j, k]) <- th[j, k] + b * x[k]
+    }
+  }
+  b ~ dnorm(0, 1)
+}"""
+
+OUTER_SIBLINGS = """model {
+  for (j in 1:2) {
+    mu[j] ~ dnorm(0, 0.5)
+    for (k in 1:K) {
+      d[j, k] ~ dnorm(mu[j], 1.5)
+      p0[j, k] ~ dbeta(2, 3)
+      r0[j, k] ~ dbin(p0[j, k], n[k])
+      r1[j, k] ~ dbin(p1[j, k], n[k])
+      logit(p1[j, k]) <- d[j, k] + logit(p0[j, k])
+    }
+  }
+}"""
+
+
+@pytest.mark.parametrize("which", ["linear", "siblings"])
+def test_short_outer_loops_are_written_out(which):
+    rng = np.random.default_rng(17)
+    K = 5
+    if which == "linear":
+        text = OUTER_LINEAR
+        data = {"K": K, "x": rng.standard_normal(K), "y": rng.poisson(2.0, (3, K)).astype(float)}
+    else:
+        text = OUTER_SIBLINGS
+        n = rng.integers(5, 20, K).astype(float)
+        data = {"K": K, "n": n, "r0": rng.binomial(n.astype(int), 0.3, (2, K)).astype(float),
+                "r1": rng.binomial(n.astype(int), 0.5, (2, K)).astype(float)}
+    gm = go.compile(text, data, {}).use_generated_order()
+    plan, lw = jbugs.lower(text, data)
+    assert lw.param_names() == gm.param_names()          # theta keeps the order of the program as written
+    assert not any("<" in n for n in lw.param_names())   # public labels carry the dropped subscript again
+    theta = 0.3 * rng.standard_normal((plan.D, 4))
+    lp, g, st = COracle(plan).eval_batch(theta)
+    for c in range(4):
+        l0, g0 = gm.logdensity_and_gradient(theta[:, c])
+        assert st[c] == 0 and abs(lp[c] - l0) <= 1e-11 * max(1.0, abs(l0))
+        assert grad_err(g[:, c], g0) < 1e-10
+    if which == "siblings":
+        assert len(plan.plates) == 2 and all(p.T == 2 and p.xops for p in plan.plates)   # one merged plate per iteration
+
+
+def test_arrays_used_outside_their_outer_loop_are_not_split():
+    text = """model {
+      for (j in 1:2) { m[j] ~ dnorm(0, 1)
+        for (k in 1:K) { th[j, k] ~ dnorm(m[j], 1)
+                         y[j, k] ~ dnorm(th[j, k], 1) } }
+      z ~ dnorm(th[1, 2], 1)
+    }"""
+    with pytest.raises(jbugs.LoweringError):
+        jbugs.lower(text, {"K": 3, "y": np.zeros((2, 3)), "z": 0.5})
