@@ -1314,6 +1314,11 @@ function tape!(lw::Lowering, e, s::Stmt, plate::Plate, tape::Vector{XOp}, memo::
             return push_op(XOp(OP_POW, ia, ib))
         end
         haskey(UNARY_OF, f) && length(e.args) == 2 && return push_op(XOp(UNARY_OF[f], rec(e.args[2])))
+        if f == :logit && length(e.args) == 2
+            # LogExpFunctions.logit(x) = log(x / (1 - x)), written out in tape arithmetic (lowering.py _tape)
+            x = e.args[2]
+            return (memo[key] = rec(Expr(:call, :log, Expr(:call, :/, x, Expr(:call, :-, 1.0, x)))))
+        end
     end
     fail("unsupported expression in a predictor: $(e)")
 end
