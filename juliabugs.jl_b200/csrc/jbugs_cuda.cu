@@ -321,7 +321,10 @@ static int build_locals_and_finish(jbugs_plan* p, int k, std::vector<int>& gref,
         if ((L[l].family == JBUGS_FAM_T || L[l].family == JBUGS_FAM_BETABIN) && L[l].args[2].kind != JBUGS_ARG_CONST && L[l].args[2].kind != JBUGS_ARG_ONE)
             return fail(JBUGS_ERR_UNSUPPORTED, "plate %d local %d: the degrees of freedom of dt must be a constant", k, l);
     }
-    if ((int)gref.size() > MAX_GREF) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d references more than %d global values", k, MAX_GREF);
+    // expression plates (XSpec, compiled tape kernels) keep MAX_GREF global values per chain, the interpreter of
+    // linear-predictor plates MAX_GREF_LINEAR (DynSpec::NG_MAX)
+    const int gref_cap = (p->plates[k].has_obs == 2 || p->plates[k].has_obs == 3) ? MAX_GREF : MAX_GREF_LINEAR;
+    if ((int)gref.size() > gref_cap) return fail(JBUGS_ERR_UNSUPPORTED, "plate %d references more than %d global values", k, gref_cap);
     sh.n_gref = (int)gref.size();
     for (int q = 0; q < MAX_GREF; ++q) V.gref[q] = q < (int)gref.size() ? gref[q] : 0;
     V.i0 = p->shard_i0[k]; V.i1 = p->shard_i1[k];

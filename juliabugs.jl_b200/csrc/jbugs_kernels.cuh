@@ -30,7 +30,8 @@ namespace jbugs {
 constexpr int MAX_GT = 8;                        // terms whose coefficient is a global value
 constexpr int MAX_LOC = 4;                       // local parameters of a plate
 constexpr int MAX_TERMS = MAX_GT + MAX_LOC + 1;  // + optional data offset
-constexpr int MAX_GREF = 12;                     // distinct global values a plate references
+constexpr int MAX_GREF = 24;                     // distinct global values a plate references (expression plates, compiled kernels)
+constexpr int MAX_GREF_LINEAR = 12;              // ... a linear-predictor plate run by the interpreter (DynSpec keeps 12 in registers)
 constexpr int MAX_GVALS = 64;                    // globals + gtape results of a plan
 constexpr int BLOCK = 128;                       // chains per CTA
 constexpr int CHAIN_OK = 0, CHAIN_DOMAIN = 1;    // JBUGS_CHAIN_OK / JBUGS_CHAIN_DOMAIN of jbugs_cuda.h (checked in jbugs_cuda.cu)
@@ -148,6 +149,9 @@ struct DynSpec {
     // parameter layout is one for all instantiations).  A static spec knows its counts: the front end then emits nl / kg
     // copies of each loop body instead of MAX_LOC / MAX_GT guarded ones for the optimiser to throw away.
     static constexpr int NL_MAX = MAX_LOC, KG_MAX = MAX_GT;
+    // entries of ChainState::gv / ga this instantiation touches: the interpreter of linear-predictor plates keeps 12 (the
+    // select chains of pick / bump and the register file are sized by it), expression plates and compiled kernels 24
+    static constexpr int NG_MAX = MAX_GREF_LINEAR;
     static constexpr int L2PF = 0;            // no L2 prefetch of theta rows
     __device__ __forceinline__ bool prior_fused(int) const { return false; }
     __device__ __forceinline__ bool prior_mu_zero(int) const { return false; }
@@ -178,6 +182,7 @@ struct DynSpec {
 // per-thread value / adjoint arrays of the tape -- 2 KB of local memory -- are not part of every interpreter launch)
 struct XSpec : DynSpec {
     static constexpr bool XTAPE = true;
+    static constexpr int NG_MAX = MAX_GREF;
     static constexpr int MIN_BLOCKS = 2;  // (the tape's value / adjoint arrays live in local memory anyway: keep the registers)
     __device__ __forceinline__ explicit XSpec(const PlateShape& sh) : DynSpec(sh) {}
     __device__ __forceinline__ int n_x() const { return s.n_x; }
@@ -217,6 +222,7 @@ template <class Desc>
 struct StaticSpec {
     using D = Desc;
     static constexpr int NL_MAX = Desc::sh().nl, KG_MAX = Desc::sh().kg;
+    static constexpr int NG_MAX = MAX_GREF;   // (indices are compile-time constants here: unused entries disappear)
     static constexpr bool XGEN = desc_xgen<Desc>::value;
     // FP64-bound plates: the theta rows of the NEXT block of UNROLL groups travel global -> shared with cp.async while
     // this block is evaluated (no registers held across the block, unlike PREFETCH); group-level locals with affine
@@ -285,6 +291,21 @@ __device__ __forceinline__ void bump(double (&a)[N], int id, double d) {
 #pragma unroll
     for (int k = 0; k < N; ++k) a[k] += (k == id) ? d : 0.0;
 }
+// the same over the first M entries only (M = S::NG_MAX: the entries an instantiation uses)
+template <int M, int N>
+__device__ __forceinline__ double pick_n(const double (&a)[N], int id) {
+    static_assert(M <= N, "pick_n");
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) v = (k == id) ? a[k] : v;
+    return v;
+}
+template <int M, int N>
+__device__ __forceinline__ void bump_n(double (&a)[N], int id, double d) {
+    static_assert(M <= N, "bump_n");
+#pragma unroll
+    for (int k = 0; k < M; ++k) a[k] += (k == id) ? d : 0.0;
+}
 
 struct ChainState {
     double gv[MAX_GREF];  // referenced global values
@@ -308,13 +329,13 @@ struct StageView {
 };
 
 // g = group index inside the staged chunk, j = inner index.  SS: take the stream offset from the (compile-time) shape
-template <bool SS = false>
+template <bool SS = false, int NG = MAX_GREF>
 __device__ __forceinline__ double arg_value(ArgS s, const ArgV& v, const ChainState& st, const StageView& sv, int g, int j) {
     const int soff = SS ? s.soff : v.soff;
     switch (s.kind) {
     case JBUGS_ARG_CONST: return v.value;
     case JBUGS_ARG_ONE: return 1.0;
-    case JBUGS_ARG_GVAL: return pick(st.gv, s.id);
+    case JBUGS_ARG_GVAL: return pick_n<NG>(st.gv, s.id);
     case JBUGS_ARG_LOCAL: return pick(st.lx, s.id);
     case JBUGS_ARG_DATA_I: return sv.chunk[soff + g];
     case JBUGS_ARG_DATA_J: return sv.jreg[soff + j];
@@ -323,8 +344,9 @@ __device__ __forceinline__ double arg_value(ArgS s, const ArgV& v, const ChainSt
     }
 }
 
+template <int NG = MAX_GREF>
 __device__ __forceinline__ void arg_adjoint(ArgS s, ChainState& st, double d) {
-    if (s.kind == JBUGS_ARG_GVAL) bump(st.ga, s.id, d);
+    if (s.kind == JBUGS_ARG_GVAL) bump_n<NG>(st.ga, s.id, d);
     else if (s.kind == JBUGS_ARG_LOCAL) bump(st.la, s.id, d);
 }
 

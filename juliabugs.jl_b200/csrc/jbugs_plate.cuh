@@ -149,8 +149,8 @@ template <class S>
 __device__ __forceinline__ bool local_prior(const S& sp, const PlateVals& V, int l, const StageView& sv, int g, int j,
                                             ChainState& st, FusedAcc& fa, double& lp) {
     const LocalV& L = V.loc[l];
-    const double a0 = arg_value<S::SOFF>(sp.loc_arg(l, 0), L.args[0], st, sv, g, j);
-    const double a1 = arg_value<S::SOFF>(sp.loc_arg(l, 1), L.args[1], st, sv, g, j);
+    const double a0 = arg_value<S::SOFF, S::NG_MAX>(sp.loc_arg(l, 0), L.args[0], st, sv, g, j);
+    const double a1 = arg_value<S::SOFF, S::NG_MAX>(sp.loc_arg(l, 1), L.args[1], st, sv, g, j);
     if (sp.prior_fused(l)) {
         // dnorm(mu, tau) with chain-invariant arguments: keep sufficient statistics, expand at tile end.  The adjoint
         // -tau (x - mu) is applied where the gradient is stored (eval_groups: one fma with the likelihood's part).
@@ -170,16 +170,16 @@ __device__ __forceinline__ bool local_prior(const S& sp, const PlateVals& V, int
         const double x = st.lx[l], lx = log(x);
         lp += x < 0.0 ? -dev_inf() : (fma(a0, st.pre_lb[l], -st.pre_lg[l]) + (a0 == 1.0 ? 0.0 : (a0 - 1.0) * lx) - a1 * x);
         st.la[l] += (a0 - 1.0) / x - a1;
-        arg_adjoint(sp.loc_arg(l, 0), st, st.pre_lb[l] - st.pre_dg[l] + lx);
-        arg_adjoint(sp.loc_arg(l, 1), st, a0 / a1 - x);
+        arg_adjoint<S::NG_MAX>(sp.loc_arg(l, 0), st, st.pre_lb[l] - st.pre_dg[l] + lx);
+        arg_adjoint<S::NG_MAX>(sp.loc_arg(l, 1), st, a0 / a1 - x);
         return !(a0 > 0.0) || !(a1 > 0.0);
     }
     FamOut o;
     const bool bad = fam_eval(sp.loc_family(l), st.lx[l], a0, a1, o, L.args[2].value);
     lp += o.lp;
     st.la[l] += o.dx;
-    arg_adjoint(sp.loc_arg(l, 0), st, o.da0);
-    arg_adjoint(sp.loc_arg(l, 1), st, o.da1);
+    arg_adjoint<S::NG_MAX>(sp.loc_arg(l, 0), st, o.da0);
+    arg_adjoint<S::NG_MAX>(sp.loc_arg(l, 1), st, o.da1);
     return bad;
 }
 
@@ -191,16 +191,16 @@ __device__ __forceinline__ double predictor(const S& sp, const PlateVals& V, con
 #pragma unroll
     for (int t = 0; t < S::KG_MAX; ++t)
         if (t < sp.kg()) {
-            cv[t] = arg_value<S::SOFF>(sp.cov(t), V.cov[t], st, sv, g, j);
+            cv[t] = arg_value<S::SOFF, S::NG_MAX>(sp.cov(t), V.cov[t], st, sv, g, j);
             eta = fma(st.gv[t], cv[t], eta);
         }
 #pragma unroll
     for (int l = 0; l < S::NL_MAX; ++l)
         if (l < sp.nl()) {
-            cv[MAX_GT + l] = arg_value<S::SOFF>(sp.cov(sp.kg() + l), V.cov[sp.kg() + l], st, sv, g, j);
+            cv[MAX_GT + l] = arg_value<S::SOFF, S::NG_MAX>(sp.cov(sp.kg() + l), V.cov[sp.kg() + l], st, sv, g, j);
             eta = fma(st.lx[l], cv[MAX_GT + l], eta);
         }
-    if (sp.has_off()) eta += arg_value<S::SOFF>(sp.cov(sp.kg() + sp.nl()), V.cov[sp.kg() + sp.nl()], st, sv, g, j);
+    if (sp.has_off()) eta += arg_value<S::SOFF, S::NG_MAX>(sp.cov(sp.kg() + sp.nl()), V.cov[sp.kg() + sp.nl()], st, sv, g, j);
     return eta;
 }
 
@@ -362,11 +362,11 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
                                         ChainState& st, FusedAcc& fa, double (&sl)[MAX_LOC], double& lp) {
     double cv[MAX_TERMS];
     bool bad = false;
-    if (sp.has_w() && arg_value<S::SOFF>(sp.aux(2), V.aux[2], st, sv, g, j) == 0.0) return false;  // padded cell: no observation
+    if (sp.has_w() && arg_value<S::SOFF, S::NG_MAX>(sp.aux(2), V.aux[2], st, sv, g, j) == 0.0) return false;  // padded cell: no observation
     if constexpr (S::XTAPE) return observe_tape(sp, V, sv, g, j, st, lp);
     if constexpr (S::XGEN) return S::D::observe_gen(sp, V, sv, g, j, st, lp);
     const double eta = predictor(sp, V, sv, g, j, st, cv);
-    const double yv = arg_value<S::SOFF>(sp.y(), V.y, st, sv, g, j);
+    const double yv = arg_value<S::SOFF, S::NG_MAX>(sp.y(), V.y, st, sv, g, j);
 
     if constexpr (S::FUSED == FUSED_NORMAL_IDENTITY) {
         // y ~ dnorm(eta, tau), tau chain-invariant: d/d eta = tau * r; tau is factored out of every sum
@@ -385,7 +385,7 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
     if constexpr (S::FUSED == FUSED_BINOMIAL_LOGIT || S::FUSED == FUSED_BERNOULLI_LOGIT) {
         // k ~ dbin(logistic(eta), n): branch-free, selects and range tests on the integer pipe (binomial_logit);
         // the saturated tails are fixed up once per unrolled block of groups (eval_groups), not per observation
-        const double n = S::FUSED == FUSED_BERNOULLI_LOGIT ? 1.0 : arg_value<S::SOFF>(sp.aux(1), V.aux[1], st, sv, g, j);
+        const double n = S::FUSED == FUSED_BERNOULLI_LOGIT ? 1.0 : arg_value<S::SOFF, S::NG_MAX>(sp.aux(1), V.aux[1], st, sv, g, j);
         binomial_logit(eta, yv, n, lp, deta, st.sat);
     } else if constexpr (S::FUSED == FUSED_POISSON_LOG) {
         // k ~ dpois(exp(eta)): k * eta - exp(eta); -lgamma(k+1) goes to obs_const
@@ -409,7 +409,7 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
             lp += xlogy(yv, v) - v;
             deta = ((yv == 0.0 ? 0.0 : yv / v) - 1.0) * dv;
         } else {
-            const double n = S::FUSED == FUSED_BERNOULLI_LINK ? 1.0 : arg_value<S::SOFF>(sp.aux(1), V.aux[1], st, sv, g, j);
+            const double n = S::FUSED == FUSED_BERNOULLI_LINK ? 1.0 : arg_value<S::SOFF, S::NG_MAX>(sp.aux(1), V.aux[1], st, sv, g, j);
             const double m = n - yv;
             bad |= !(v >= 0.0 && v <= 1.0);
             lp += xlogy(yv, v) + xlog1py(m, -v);
@@ -426,14 +426,14 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
                 dv *= d;
             }
         const int ea = sp.eta_arg();
-        const double a0 = ea == 0 ? v : arg_value<S::SOFF>(sp.aux(0), V.aux[0], st, sv, g, j);
-        const double a1 = ea == 1 ? v : arg_value<S::SOFF>(sp.aux(1), V.aux[1], st, sv, g, j);
+        const double a0 = ea == 0 ? v : arg_value<S::SOFF, S::NG_MAX>(sp.aux(0), V.aux[0], st, sv, g, j);
+        const double a1 = ea == 1 ? v : arg_value<S::SOFF, S::NG_MAX>(sp.aux(1), V.aux[1], st, sv, g, j);
         FamOut o;
         bad |= fam_eval(sp.family(), yv, a0, a1, o, V.aux[2].value);
         lp += o.lp;
         deta = (ea == 0 ? o.da0 : o.da1) * dv;
-        if (ea != 0) arg_adjoint(sp.aux(0), st, o.da0);
-        if (ea != 1) arg_adjoint(sp.aux(1), st, o.da1);
+        if (ea != 0) arg_adjoint<S::NG_MAX>(sp.aux(0), st, o.da0);
+        if (ea != 1) arg_adjoint<S::NG_MAX>(sp.aux(1), st, o.da1);
     }
 #pragma unroll
     for (int t = 0; t < S::KG_MAX; ++t)
@@ -448,7 +448,7 @@ __device__ __forceinline__ bool observe(const S& sp, const PlateVals& V, const S
 template <class S>
 __device__ __forceinline__ double prior_tau(const S& sp, const PlateVals& V, int l, const ChainState& st) {
     const ArgS a1 = sp.loc_arg(l, 1);
-    return a1.kind == JBUGS_ARG_GVAL ? pick(st.gv, a1.id) : (a1.kind == JBUGS_ARG_ONE ? 1.0 : V.loc[l].args[1].value);
+    return a1.kind == JBUGS_ARG_GVAL ? pick_n<S::NG_MAX>(st.gv, a1.id) : (a1.kind == JBUGS_ARG_ONE ? 1.0 : V.loc[l].args[1].value);
 }
 
 // raw theta values (and row offsets) of the group-level locals of UU consecutive groups; when the inner extent is
@@ -624,11 +624,11 @@ __device__ __forceinline__ bool eval_groups(const S& sp, const PlateVals& V, con
                         const long long o = sp.loc_has_idx(l) ? local_slot(sp, V, l, i + u, j) * ld : opos[l] + j * V.loc[l].step_j;
                         local_enter(sp, V, l, th[o], st, d0, d1, dummy);
                     }
-                if (sp.has_w() && arg_value<S::SOFF>(sp.aux(2), V.aux[2], st, sv, g + u, j) == 0.0) continue;
+                if (sp.has_w() && arg_value<S::SOFF, S::NG_MAX>(sp.aux(2), V.aux[2], st, sv, g + u, j) == 0.0) continue;
                 double cv[MAX_TERMS];
                 const double eta = predictor(sp, V, sv, g + u, j, st, cv);
-                const double yv = arg_value<S::SOFF>(sp.y(), V.y, st, sv, g + u, j);
-                const double n = S::FUSED == FUSED_BERNOULLI_LOGIT ? 1.0 : arg_value<S::SOFF>(sp.aux(1), V.aux[1], st, sv, g + u, j);
+                const double yv = arg_value<S::SOFF, S::NG_MAX>(sp.y(), V.y, st, sv, g + u, j);
+                const double n = S::FUSED == FUSED_BERNOULLI_LOGIT ? 1.0 : arg_value<S::SOFF, S::NG_MAX>(sp.aux(1), V.aux[1], st, sv, g + u, j);
                 if (logit_tail_is_inf(eta, yv, n)) lp = -dev_inf();
             }
         }
@@ -726,7 +726,7 @@ __device__ __forceinline__ void plate_body(const PlateParams& P, const double* _
     pdl_wait();  // everything above (parameters, first data chunk in flight) may overlap the prologue kernel
     ChainState st;
 #pragma unroll
-    for (int k = 0; k < MAX_GREF; ++k) {
+    for (int k = 0; k < S::NG_MAX; ++k) {
         st.gv[k] = (k < sp.n_gref()) ? gvals[(long long)V.gref[k] * ldg + c] : 0.0;
         st.ga[k] = 0.0;
     }
@@ -735,8 +735,8 @@ __device__ __forceinline__ void plate_body(const PlateParams& P, const double* _
         if (l < sp.nl() && sp.loc_family(l) == JBUGS_FAM_GAMMA && arg_invariant(sp.loc_arg(l, 0)) &&
             arg_invariant(sp.loc_arg(l, 1))) {
             const ArgS s0 = sp.loc_arg(l, 0), s1 = sp.loc_arg(l, 1);
-            const double a0 = s0.kind == JBUGS_ARG_GVAL ? pick(st.gv, s0.id) : (s0.kind == JBUGS_ARG_ONE ? 1.0 : V.loc[l].args[0].value);
-            const double a1 = s1.kind == JBUGS_ARG_GVAL ? pick(st.gv, s1.id) : (s1.kind == JBUGS_ARG_ONE ? 1.0 : V.loc[l].args[1].value);
+            const double a0 = s0.kind == JBUGS_ARG_GVAL ? pick_n<S::NG_MAX>(st.gv, s0.id) : (s0.kind == JBUGS_ARG_ONE ? 1.0 : V.loc[l].args[0].value);
+            const double a1 = s1.kind == JBUGS_ARG_GVAL ? pick_n<S::NG_MAX>(st.gv, s1.id) : (s1.kind == JBUGS_ARG_ONE ? 1.0 : V.loc[l].args[1].value);
             st.pre_lg[l] = lgamma(a0);
             st.pre_dg[l] = digamma(a0);
             st.pre_lb[l] = log(a1);
@@ -753,7 +753,7 @@ __device__ __forceinline__ void plate_body(const PlateParams& P, const double* _
     bool bad = false;
     // precision of a fused normal observation (chain-invariant by construction of the spec)
     const double obs_tau = (S::FUSED == FUSED_NORMAL_IDENTITY)
-                               ? (sp.aux(1).kind == JBUGS_ARG_GVAL ? pick(st.gv, sp.aux(1).id) : V.aux[1].value)
+                               ? (sp.aux(1).kind == JBUGS_ARG_GVAL ? pick_n<S::NG_MAX>(st.gv, sp.aux(1).id) : V.aux[1].value)
                                : 0.0;
     const double* __restrict__ th = theta + c;
     double* __restrict__ gr = grad + c;
@@ -864,7 +864,7 @@ __device__ __forceinline__ void plate_body(const PlateParams& P, const double* _
         const double tau = obs_tau;
         bad |= tau < 0.0;
         lp += n_obs * (0.5 * log(tau) - 0.5 * kLog2Pi) - 0.5 * tau * fa.ss;
-        if (tg) bump(st.ga, sp.aux(1).id, n_obs * 0.5 / tau - 0.5 * fa.ss);
+        if (tg) bump_n<S::NG_MAX>(st.ga, sp.aux(1).id, n_obs * 0.5 / tau - 0.5 * fa.ss);
 #pragma unroll
         for (int t = 0; t < S::KG_MAX; ++t)
             if (t < sp.kg()) st.ga[t] = fma(tau, fa.sg[t], st.ga[t]);
@@ -878,8 +878,8 @@ __device__ __forceinline__ void plate_body(const PlateParams& P, const double* _
             const double cnt = (double)((ie - ib) * (sp.loc_level(l) == JBUGS_LEVEL_OBS ? V.T : 1));
             bad |= tau < 0.0;
             lp += cnt * (0.5 * log(tau) - 0.5 * kLog2Pi) - 0.5 * tau * fa.pss[l];
-            if (a0.kind == JBUGS_ARG_GVAL) bump(st.ga, a0.id, tau * fa.ps[l]);
-            if (a1.kind == JBUGS_ARG_GVAL) bump(st.ga, a1.id, cnt * 0.5 / tau - 0.5 * fa.pss[l]);
+            if (a0.kind == JBUGS_ARG_GVAL) bump_n<S::NG_MAX>(st.ga, a0.id, tau * fa.ps[l]);
+            if (a1.kind == JBUGS_ARG_GVAL) bump_n<S::NG_MAX>(st.ga, a1.id, cnt * 0.5 / tau - 0.5 * fa.pss[l]);
         }
 
     if (!active) return;
@@ -888,7 +888,7 @@ __device__ __forceinline__ void plate_body(const PlateParams& P, const double* _
     out[0] = lp;
     if (GRAD)
 #pragma unroll
-        for (int k = 0; k < MAX_GREF; ++k)
+        for (int k = 0; k < S::NG_MAX; ++k)
             if (k < sp.n_gref()) out[(long long)(1 + k) * ldg] = st.ga[k];
     if (bad) atomicOr(flags + c, 1);
 }

@@ -509,3 +509,48 @@ def test_cuda_cervix():
     assert np.max(np.abs(g - g0) / scale) < 1e-10
     names = m.lowering.param_names()
     assert lp[0] == pytest.approx(_cervix_closed_form(data, names, theta[:, 0]), rel=1e-12)
+
+
+# ---- wider mixtures: an expression plate keeps up to 24 global values per chain (MAX_GREF), so eight components with
+# their own means and standard deviations (16 referenced globals) fit; linear-predictor plates keep 12
+def _gmm_k(K, N=120, seed=0):
+    text = ("model {\n" + "".join(f"  w[{k}] <- {1.0 / K}\n" for k in range(1, K + 1)) +
+            f"  for (k in 1:{K}) {{ mu[k] ~ dnorm(0, 0.04)\n    sigma[k] ~ dexp(1)\n    tau[k] <- 1 / (sigma[k] * sigma[k]) }}\n"
+            f"  for (i in 1:N) {{ z[i] ~ dcat(w[1:{K}])\n    y[i] ~ dnorm(mu[z[i]], tau[z[i]]) }}\n}}")
+    rng = np.random.default_rng(seed)
+    y = rng.normal(rng.integers(0, K, N) * 2.0 - K + 1, 0.5)
+    return text, {"N": N, "y": y}
+
+
+def test_eight_component_mixture_plan_against_closed_form():
+    text, data = _gmm_k(8)
+    plan, lw = jbugs.lower(text, data, marginalize=True)
+    names = lw.param_names()
+    assert plan.D == 16
+    rng = np.random.default_rng(1)
+    theta = 0.3 * rng.standard_normal((16, 3))
+    lp, _, st = COracle(plan).eval_batch(theta)
+    ix = {n: i for i, n in enumerate(names)}
+    for c in range(3):
+        mus = [theta[ix[f"mu[{k}]"], c] for k in range(1, 9)]
+        sgs = [np.exp(theta[ix[f"sigma[{k}]"], c]) for k in range(1, 9)]
+        e = mixture_loglik(data["y"], [1 / 8] * 8, mus, sgs)
+        e += sum(S.norm(0, 5).logpdf(m) for m in mus) + sum(S.expon().logpdf(s) + np.log(s) for s in sgs)
+        assert st[c] == 0 and lp[c] == pytest.approx(e, rel=1e-12)
+
+
+@pytest.mark.gpu
+def test_cuda_eight_component_mixture():
+    text, data = _gmm_k(8)
+    m = jbugs.compile(text, data, evaluation_mode=jbugs.UseAutoMarginalization())
+    theta = 0.3 * np.random.default_rng(2).standard_normal((m.plan.D, 70))
+    lp0, g0, _ = COracle(m.plan).eval_batch(theta)
+    for compiled in (False, True):
+        if compiled:
+            m.cuda.specialize()
+            assert "expression_tape_specialised_at_run_time" in m.cuda.describe()
+        lp, g, st = m.cuda.eval_host(theta, layout="param_fast")
+        assert (st == 0).all()
+        assert np.max(np.abs(lp - lp0) / np.maximum(1.0, np.abs(lp0))) < 1e-12
+        scale = np.maximum(np.abs(g0), 1e-4 * np.abs(g0).max(axis=0, keepdims=True))
+        assert np.max(np.abs(g - g0) / scale) < 1e-10
