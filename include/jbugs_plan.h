@@ -115,8 +115,12 @@ enum jbugs_op {
     /* expression tapes only */
     JBUGS_OP_LEAF = 32,  /* value of `leaf`: CONST | ONE | GVAL | GVEC_J | LOCAL | DATA_I | DATA_J | DATA_IJ */
     JBUGS_OP_SELECT = 33,/* v[a] != 0 ? v[b] : v[c]  (a: a 0/1 data leaf; no adjoint flows into a)          */
-    JBUGS_OP_PICK_K = 34 /* v[a + k], k = the state of the plate's marginalised discrete latent (has_obs == 3):
+    JBUGS_OP_PICK_K = 34,/* v[a + k], k = the state of the plate's marginalised discrete latent (has_obs == 3):
                             slots a .. a + K - 1 hold the K candidates (`mu[z[i]]` -> mu[1], ..., mu[K])         */
+    JBUGS_OP_GVEC_AT = 35/* gval[leaf.id + (int) v[a]]: an element of a short parameter vector whose elements are the
+                            consecutive global values leaf.id .. leaf.id + leaf.value - 1, picked by the 0-based index
+                            in tape slot a (a data leaf): the frailty `b[pair[i]]` of LeukFr inside an expression plate.
+                            The adjoint goes to the picked element; none flows into the index                       */
 };
 
 /* ---- expression tape of a plate whose predictor is not linear in the parameters -----------------------------

@@ -375,17 +375,21 @@ static int build_xplate(jbugs_plan* p, int k) {
     std::vector<int> gref;
     const int n_gv = (int)(p->h.n_globals + p->h.n_gtape);
     // parameter vectors indexed by the inner index first: their T elements must sit in consecutive gref positions
-    for (int q = 0; q < nx; ++q)
-        if (X[q].op == JBUGS_OP_LEAF && X[q].leaf.kind == JBUGS_ARG_GVEC_J) {
+    // (the same for a vector picked by a data index, JBUGS_OP_GVEC_AT: leaf.value elements from leaf.id)
+    for (int q = 0; q < nx; ++q) {
+        const bool by_j = X[q].op == JBUGS_OP_LEAF && X[q].leaf.kind == JBUGS_ARG_GVEC_J, by_idx = X[q].op == JBUGS_OP_GVEC_AT;
+        if (by_j || by_idx) {
             const int base = X[q].leaf.id;
-            if (base < 0 || base + pl.T > n_gv) return fail(JBUGS_ERR_INVALID, "plate %d: parameter vector out of range", k);
+            const long long cnt = by_j ? pl.T : (long long)X[q].leaf.value;
+            if (base < 0 || cnt < 1 || base + cnt > n_gv) return fail(JBUGS_ERR_INVALID, "plate %d: parameter vector out of range", k);
             if (std::find(gref.begin(), gref.end(), base) == gref.end()) {
-                for (long long e = 0; e < pl.T; ++e)
+                for (long long e = 0; e < cnt; ++e)
                     if (std::find(gref.begin(), gref.end(), base + (int)e) != gref.end())
                         return fail(JBUGS_ERR_UNSUPPORTED, "plate %d: overlapping parameter vectors in one tape", k);
-                for (long long e = 0; e < pl.T; ++e) gref.push_back(base + (int)e);
+                for (long long e = 0; e < cnt; ++e) gref.push_back(base + (int)e);
             }
         }
+    }
     std::vector<XOpDev> tape((size_t)nx);
     int rc;
     for (int q = 0; q < nx; ++q) {
@@ -410,6 +414,13 @@ static int build_xplate(jbugs_plan* p, int k) {
             if (o.a >= q || o.b >= q || o.c >= q) return fail(JBUGS_ERR_INVALID, "plate %d: tape op %d looks forward", k, q);
         } else if (X[q].op == JBUGS_OP_PICK_K) {
             if (K < 1 || (int)o.a + K > q) return fail(JBUGS_ERR_INVALID, "plate %d: tape op %d picks outside the tape or without a latent", k, q);
+        } else if (X[q].op == JBUGS_OP_GVEC_AT) {
+            const jbugs_xop& ix = X[o.a < q ? o.a : 0];
+            if (o.a >= q || ix.op != JBUGS_OP_LEAF ||
+                (ix.leaf.kind != JBUGS_ARG_DATA_I && ix.leaf.kind != JBUGS_ARG_DATA_J && ix.leaf.kind != JBUGS_ARG_DATA_IJ))
+                return fail(JBUGS_ERR_INVALID, "plate %d: tape op %d needs a data leaf as its index", k, q);
+            o.id = (int)(std::find(gref.begin(), gref.end(), X[q].leaf.id) - gref.begin());
+            o.value = X[q].leaf.value;
         } else if (unary || binary) {
             if (o.a >= q || (binary && o.b >= q)) return fail(JBUGS_ERR_INVALID, "plate %d: tape op %d looks forward", k, q);
             if (unary && X[q].op > JBUGS_OP_NEG) return fail(JBUGS_ERR_INVALID, "plate %d: unknown tape op %u", k, X[q].op);

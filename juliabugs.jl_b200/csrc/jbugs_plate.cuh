@@ -234,6 +234,8 @@ __device__ __noinline__ bool tape_forward(const S& sp, const PlateVals& V, const
             v[k] = v[o.a] != 0.0 ? v[o.b] : v[o.c];
         } else if (o.op == JBUGS_OP_PICK_K) {
             v[k] = v[o.a + state];
+        } else if (o.op == JBUGS_OP_GVEC_AT) {
+            v[k] = pick(st.gv, o.id + (int)v[o.a]);  // (an index outside the vector selects nothing: 0)
         } else if (o.op < 16) {
             bad |= unary_op(o.op, v[o.a], v[k], d1[k]);
         } else {
@@ -295,6 +297,8 @@ __device__ __noinline__ void tape_reverse(const S& sp, const PlateVals& V, int j
             w[v[o.a] != 0.0 ? o.b : o.c] += wk;
         } else if (o.op == JBUGS_OP_PICK_K) {
             w[o.a + state] += wk;
+        } else if (o.op == JBUGS_OP_GVEC_AT) {
+            bump(st.ga, o.id + (int)v[o.a], wk);
         } else {
             w[o.a] += wk * d1[k];
             if (o.op >= 16) w[o.b] += wk * d2[k];

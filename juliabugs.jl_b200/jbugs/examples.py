@@ -400,6 +400,40 @@ model {
 }
 """
 
+# LeukFr: the Cox model of Leuk with a frailty per matched pair, b[pair[i]] -- a random effect picked by a data index of
+# the inner loop variable inside a predictor that is not linear in the parameters
+LEUKFR = """
+model {
+    for (i in 1:N) {
+        for (j in 1:T) {
+            Y[i, j] <- step(obs.t[i] - t[j] + eps)
+            dN[i, j] <- Y[i, j] * step(t[j + 1] - obs.t[i] - eps) * fail[i]
+        }
+    }
+    for (j in 1:T) {
+        for (i in 1:N) {
+            dN[i, j] ~ dpois(Idt[i, j])
+            Idt[i, j] <- Y[i, j] * exp(beta * Z[i] + b[pair[i]]) * dL0[j]
+        }
+        dL0[j] ~ dgamma(mu[j], c)
+        mu[j] <- dL0.star[j] * c
+        S.treat[j] <- pow(exp(-sum(dL0[1:j])), exp(beta * -0.5))
+        S.placebo[j] <- pow(exp(-sum(dL0[1:j])), exp(beta * 0.5))
+    }
+    for (k in 1:Npairs) {
+        b[k] ~ dnorm(0.0, tau)
+    }
+    tau ~ dgamma(0.001, 0.001)
+    sigma <- sqrt(1 / tau)
+    c <- 0.001
+    r <- 0.1
+    for (j in 1:T) {
+        dL0.star[j] <- r * (t[j + 1] - t[j])
+    }
+    beta ~ dnorm(0.0, 0.000001)
+}
+"""
+
 MICE = """
 model {
     for (i in 1:M) {
@@ -537,6 +571,7 @@ model {
 """
 
 MODELS = {
+    "leukfr": LEUKFR,
     "magnesium": MAGNESIUM,
     "cervix": CERVIX,
     "orange": ORANGE,

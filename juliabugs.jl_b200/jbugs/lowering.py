@@ -1211,6 +1211,15 @@ class Lowering:
                     for d in self._defs(r.name):
                         if d.kind == "param" and len(d.loops) == 1 and d.extents == s.extents[1:] and d.size <= 10:
                             found.add(d.sid)
+            # ... and vectors picked through a data index of the inner loop variable next to parameters indexed by the outer
+            # one (LeukFr: exp(beta * Z[i] + b[pair[i]]) * dL0[j]): read on the tape as gval[base + index] (OP_GVEC_AT)
+            if outer:
+                for r in prm:
+                    if len(r.idx) == 1 and not isinstance(r.idx[0], (Var, Range, Colon)) and self._is_data(r.idx[0], s.loop_vars) \
+                            and not self._is_data(r.idx[0], ()) and s.loop_vars[0] not in free_vars(r.idx[0]):
+                        for d in self._defs(r.name):
+                            if d.kind == "param" and len(d.loops) == 1 and d.size <= 22:
+                                found.add(d.sid)
         # coefficient vectors per group (theta[i, k] ~ dnorm(mu[k], tau[k]) for k in 1:3, referenced column by column as
         # theta[i, 1], theta[i, 2], ...): each column becomes a local of the plate (_slice_local_index) whose prior
         # arguments are elements of the hyper-parameter vectors -- globals
@@ -1893,6 +1902,15 @@ class Lowering:
             ref = ("l", e.name, e.idx)
             if self._is_gvec_ref(s, ref):
                 return push(P.XOp(P.OP_LEAF, leaf=P.Arg(P.ARG_GVEC_J, self._gval_ids[f"{e.name}[{s.extents[1][0]}]"])))
+            at = self._gvec_at(e, s)
+            if at is not None:
+                # b[pair[i]]: an element of a parameter vector (consecutive global values) picked by a data index
+                base, cnt, idx0 = at
+                ia = rec(idx0)
+                if tape[ia].op == P.OP_LEAF and tape[ia].leaf.kind in (P.ARG_CONST, P.ARG_ONE):
+                    k0 = int(1.0 if tape[ia].leaf.kind == P.ARG_ONE else tape[ia].leaf.value)   # the same element everywhere
+                    return push(P.XOp(P.OP_LEAF, leaf=P.Arg.gval(base + k0)))
+                return push(P.XOp(P.OP_GVEC_AT, ia, leaf=P.Arg(P.ARG_GVAL, base, float(cnt))))
             picked = self._global_pick(e, s)
             if picked is not None:
                 return rec(picked)
@@ -1915,6 +1933,27 @@ class Lowering:
                 memo[key] = rec(Call("log", (BinOp("/", x, BinOp("-", Num(1.0), x)),)))
                 return memo[key]
         raise LoweringError(f"unsupported expression in a predictor: {_show(e)}")
+
+    def _gvec_at(self, e: Index, s: Stmt):
+        """(first global value slot, number of elements, 0-based index expression) when `e` is `name[idx]` with `name` a
+        parameter vector whose elements were expanded into consecutive globals and `idx` a data expression that varies
+        over the plate (LeukFr's frailty b[pair[i]]), else None"""
+        if len(e.idx) != 1 or isinstance(e.idx[0], (Range, Colon)) or not self._is_data(e.idx[0], s.loop_vars) \
+                or self._is_data(e.idx[0], ()):
+            return None
+        ds = [d for d in self._defs(e.name) if d.kind == "param" and not d.is_gq]
+        if len(ds) != 1 or len(ds[0].loops) != 1:
+            return None
+        lo, hi = ds[0].extents[0]
+        ids = [self._gval_ids.get(f"{e.name}[{k}]") for k in range(lo, hi + 1)]
+        if any(i is None for i in ids) or ids != list(range(ids[0], ids[0] + len(ids))):
+            return None
+        lv = _grids(s.extents, s.loop_vars)
+        vals = np.broadcast_to(np.asarray(self.de.ev(e.idx[0], lv), dtype=np.float64), s.shape)
+        seen = np.ones(vals.shape, bool) if s.obs_mask is None else np.asarray(s.obs_mask)
+        if np.any(np.isnan(vals[seen])) or np.any(vals[seen] != np.floor(vals[seen])) or vals[seen].min() < lo or vals[seen].max() > hi:
+            raise LoweringError(f"'{_show(e)}': the data index leaves the parameter vector")
+        return ids[0], len(ids), BinOp("-", e.idx[0], Num(float(lo), True))
 
     def _global_pick(self, e: Index, s: Stmt):
         """`phi[2, d1[i]]`: an element of a short parameter array whose elements are globals, picked by data subscripts

@@ -39,7 +39,7 @@ TR_IDENTITY, TR_LOG, TR_LOGIT, TR_UPPER = range(4)
 # enum jbugs_op
 OP_IDENTITY, OP_EXP, OP_LOGISTIC, OP_CEXPEXP, OP_PHI, OP_LOG, OP_SQRT, OP_NEG = range(8)
 OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW = 16, 17, 18, 19, 20
-OP_LEAF, OP_SELECT, OP_PICK_K = 32, 33, 34   # expression tapes only
+OP_LEAF, OP_SELECT, OP_PICK_K, OP_GVEC_AT = 32, 33, 34, 35   # expression tapes only
 MAX_XOPS = 64
 MAX_LOC = 4    # local parameters per plate (csrc/jbugs_kernels.cuh)
 LINK_OF = {"exp": OP_EXP, "logistic": OP_LOGISTIC, "ilogit": OP_LOGISTIC, "cexpexp": OP_CEXPEXP,

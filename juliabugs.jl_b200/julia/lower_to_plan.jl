@@ -42,6 +42,7 @@ const DISCRETE = Set([6, 7, 8, 13, 16, 17, 18])
 const TR_IDENTITY, TR_LOG, TR_LOGIT, TR_UPPER = 0, 1, 2, 3
 const OP_IDENTITY, OP_EXP, OP_LOGISTIC, OP_CEXPEXP, OP_PHI, OP_LOG, OP_SQRT, OP_NEG = 0:7
 const OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_LEAF, OP_SELECT, OP_PICK_K = 16, 17, 18, 19, 20, 32, 33, 34
+const OP_GVEC_AT = 35   # gval[leaf.id + Int(v[a])] (jbugs_plan.h); emitted by the Python pass only so far (LeukFr's b[pair[i]])
 const LINK_OF = Dict(:exp => OP_EXP, :logistic => OP_LOGISTIC, :ilogit => OP_LOGISTIC, :cexpexp => OP_CEXPEXP,
                      :icloglog => OP_CEXPEXP, :phi => OP_PHI)
 const UNARY_OF = merge(LINK_OF, Dict(:log => OP_LOG, :sqrt => OP_SQRT))

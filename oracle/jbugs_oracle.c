@@ -544,6 +544,12 @@ static int eval_chain(const jbo_plan* p, chain_io io, int want_grad, double* log
                                 if (o->op == JBUGS_OP_LEAF) { v[q] = argval(p, &o->leaf, gval, lx, i, j, N); continue; }
                                 if (o->op == JBUGS_OP_SELECT) { v[q] = v[o->a] != 0.0 ? v[o->b] : v[o->c]; continue; }
                                 if (o->op == JBUGS_OP_PICK_K) { v[q] = v[o->a + k]; continue; }
+                                if (o->op == JBUGS_OP_GVEC_AT) {
+                                    const int e = (int)v[o->a];
+                                    if (e < 0 || e >= (int)o->leaf.value) return 1;  /* an index outside the vector */
+                                    v[q] = gval[o->leaf.id + e];
+                                    continue;
+                                }
                                 const double a = v[o->a];
                                 if (o->op < 16) {
                                     if (unary(o->op, a, &v[q], &d1[q])) return 1;
@@ -587,6 +593,8 @@ static int eval_chain(const jbo_plan* p, chain_io io, int want_grad, double* log
                                     w[v[o->a] != 0.0 ? o->b : o->c] += w[q];
                                 } else if (o->op == JBUGS_OP_PICK_K) {
                                     w[o->a + k] += w[q];
+                                } else if (o->op == JBUGS_OP_GVEC_AT) {
+                                    gadj[o->leaf.id + (int)v[o->a]] += w[q];
                                 } else {
                                     w[o->a] += w[q] * d1[q];
                                     if (o->op >= 16) w[o->b] += w[q] * d2[q];

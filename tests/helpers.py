@@ -28,7 +28,10 @@ ZOO = [
     ("kidney", ex.KIDNEY, "kidney", "inits"),
     # six priors enumerated by a short outer loop (written out iteration by iteration), two observation statements per
     # study sharing pc[j, k] with a non-linear predictor (one merged expression plate per prior), a half-normal T(0, )
-    ("magnesium", ex.MAGNESIUM, "magnesium", "inits"),         # + rows without any observed cell dropped (their b[i] leave theta), factor levels by data index
+    ("magnesium", ex.MAGNESIUM, "magnesium", "inits"),
+    # a frailty per matched pair, b[pair[i]], inside the Cox model's non-linear predictor: a parameter vector picked by a
+    # data index on the tape (OP_GVEC_AT), 23 global values referenced by one expression plate
+    ("leukfr", ex.LEUKFR, "leukfr", "inits"),         # + rows without any observed cell dropped (their b[i] leave theta), factor levels by data index
 ]
 
 

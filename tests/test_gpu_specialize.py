@@ -101,7 +101,7 @@ def test_cold_compile_time_and_cache(tmp_path):
     assert m3.cuda.last_compile_seconds() > 0.0 and not list(shared.glob("*.cubin"))
 
 
-@pytest.mark.parametrize("name", ["bones", "dugongs", "lsat", "air", "leuk", "magnesium"])
+@pytest.mark.parametrize("name", ["bones", "dugongs", "lsat", "air", "leuk", "magnesium", "leukfr"])
 def test_expression_tapes_compile_to_straight_line_code(fixtures, name):
     """expression plates: the tape written out as code (registers instead of the interpreter's local-memory arrays)"""
     from helpers import ZOO, start_theta
