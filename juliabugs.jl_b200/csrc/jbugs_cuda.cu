@@ -554,7 +554,7 @@ static int refresh_obs_const(jbugs_plan* p, int k, cudaStream_t st) {
 // kernel variant of a plate: expression plates run the tape interpreter; everything else a static spec whose shape is
 // identical, else the generic interpreter (variant 0; also when the caller forces it)
 static int pick_variant(const jbugs_plan* p, const PlateRt& r, long long T) {
-    if (r.pp.sh.n_x > 0) return g_xspec;
+    if (r.pp.sh.n_x > 0) return r.pp.sh.n_gref > MAX_GREF_LINEAR ? g_xwspec : g_xspec;
     return p->force_dynamic ? 0 : select_spec(r.pp.sh, T);
 }
 
@@ -919,7 +919,7 @@ extern "C" int jbugs_plan_describe(const jbugs_plan* p, char* buf, size_t nbuf) 
     for (size_t k = 0; k < p->rt.size(); ++k) {
         const auto& r = p->rt[k];
         snprintf(line, sizeof line, "plate %zu: N=%lld T=%lld kernel=%s tiles=%lld tile=%lld gref=%d\n", k, r.pp.v.N, r.pp.v.T,
-                 ((r.variant == 0 || r.variant == g_xspec) && r.jit && r.jit_valid && !p->force_dynamic)
+                 ((r.variant == 0 || is_tape_variant(r.variant)) && r.jit && r.jit_valid && !p->force_dynamic)
                      ? (r.variant == 0 ? (jit_is_best(r.jit) ? "specialised_at_run_time" : "specialised_at_run_time_quick_variant")
                                        : "expression_tape_specialised_at_run_time") : spec_name(r.variant),
                  r.n_tiles, r.pp.v.tile, r.pp.sh.n_gref);
@@ -1202,7 +1202,7 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
     if (p->one_launch && p->rt.size() == 1 && p->dense.empty() && !(p->comm && p->nranks > 1) && !p->timing && p->parts == 0 &&
         p->h.D <= 4096 && p->rt[0].n_tiles <= 64 && p->rt[0].pp.v.i1 > p->rt[0].pp.v.i0) {
         PlateRt& r = p->rt[0];
-        const bool jit = (r.variant == 0 || r.variant == g_xspec) && r.jit && r.jit_valid && !p->force_dynamic;
+        const bool jit = (r.variant == 0 || is_tape_variant(r.variant)) && r.jit && r.jit_valid && !p->force_dynamic;
         const fused_launch_fn fn = jit ? nullptr : g_specs[r.variant].one_launch;
         if (fn) {
             FusedParams fq;
@@ -1257,12 +1257,12 @@ static int eval_device(jbugs_plan* p, const double* theta, long long ld, long lo
             pp.v.loc[l].step_i = pp.v.loc[l].si * ld;
             pp.v.loc[l].step_j = pp.v.loc[l].sj * ld;
         }
-        bool jit = (r.variant == 0 || r.variant == g_xspec) && r.jit && r.jit_valid && !p->force_dynamic;
+        bool jit = (r.variant == 0 || is_tape_variant(r.variant)) && r.jit && r.jit_valid && !p->force_dynamic;
         int variant = r.variant;
         if (p->parts == 1) {
             // prior part only: the interpreter with the observation switched off (has_obs = 0 is a run-time shape field)
             jit = false;
-            variant = pp.sh.n_x > 0 ? g_xspec : 0;
+            variant = pp.sh.n_x > 0 ? (pp.sh.n_gref > MAX_GREF_LINEAR ? g_xwspec : g_xspec) : 0;
             pp.sh.has_obs = 0;
             fp.p[k].obs_const = 0.0;
         }

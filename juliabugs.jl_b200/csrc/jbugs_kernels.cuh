@@ -182,13 +182,19 @@ struct DynSpec {
 // per-thread value / adjoint arrays of the tape -- 2 KB of local memory -- are not part of every interpreter launch)
 struct XSpec : DynSpec {
     static constexpr bool XTAPE = true;
-    static constexpr int NG_MAX = MAX_GREF;
     static constexpr int MIN_BLOCKS = 2;  // (the tape's value / adjoint arrays live in local memory anyway: keep the registers)
     __device__ __forceinline__ explicit XSpec(const PlateShape& sh) : DynSpec(sh) {}
     __device__ __forceinline__ int n_x() const { return s.n_x; }
     __device__ __forceinline__ int n_states() const { return s.n_states; }
     __device__ __forceinline__ int lp_slot() const { return s.lp_slot; }
     __device__ __forceinline__ int zobs_slot() const { return s.zobs_slot; }
+};
+
+// ... and the same for tapes that reference more than MAX_GREF_LINEAR global values (LeukFr's 21 frailties, a mixture of
+// eight components): the wide select chains and the larger per-chain state cost the narrow interpreter a quarter of its speed
+struct XWSpec : XSpec {
+    static constexpr int NG_MAX = MAX_GREF;
+    __device__ __forceinline__ explicit XWSpec(const PlateShape& sh) : XSpec(sh) {}
 };
 
 // fused observation paths (family x link pairs with a hand-derived forward+reverse)

@@ -204,12 +204,13 @@ __device__ __forceinline__ double predictor(const S& sp, const PlateVals& V, con
     return eta;
 }
 
+template <int NG>
 __device__ __forceinline__ double tape_leaf(const XOpDev& o, const StageView& sv, int g, int j, const ChainState& st) {
     switch (o.kind) {
     case JBUGS_ARG_CONST: return o.value;
     case JBUGS_ARG_ONE: return 1.0;
-    case JBUGS_ARG_GVAL: return pick(st.gv, o.id);
-    case JBUGS_ARG_GVEC_J: return pick(st.gv, o.id + j);
+    case JBUGS_ARG_GVAL: return pick_n<NG>(st.gv, o.id);
+    case JBUGS_ARG_GVEC_J: return pick_n<NG>(st.gv, o.id + j);
     case JBUGS_ARG_LOCAL: return pick(st.lx, o.id);
     case JBUGS_ARG_DATA_I: return sv.chunk[o.soff + g];
     case JBUGS_ARG_DATA_J: return sv.jreg[o.soff + j];
@@ -229,13 +230,13 @@ __device__ __noinline__ bool tape_forward(const S& sp, const PlateVals& V, const
         const XOpDev o = V.xtape[k];
         d1[k] = 0.0; d2[k] = 0.0;
         if (o.op == JBUGS_OP_LEAF) {
-            v[k] = tape_leaf(o, sv, g, j, st);
+            v[k] = tape_leaf<S::NG_MAX>(o, sv, g, j, st);
         } else if (o.op == JBUGS_OP_SELECT) {
             v[k] = v[o.a] != 0.0 ? v[o.b] : v[o.c];
         } else if (o.op == JBUGS_OP_PICK_K) {
             v[k] = v[o.a + state];
         } else if (o.op == JBUGS_OP_GVEC_AT) {
-            v[k] = pick(st.gv, o.id + (int)v[o.a]);  // (an index outside the vector selects nothing: 0)
+            v[k] = pick_n<S::NG_MAX>(st.gv, o.id + (int)v[o.a]);  // (an index outside the vector selects nothing: 0)
         } else if (o.op < 16) {
             bad |= unary_op(o.op, v[o.a], v[k], d1[k]);
         } else {
@@ -264,7 +265,7 @@ __device__ __noinline__ bool tape_family(const S& sp, const PlateVals& V, const 
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const ArgS s = sp.aux(q);
-        a[q] = s.kind == JBUGS_ARG_XVAL ? v[s.id] : arg_value(s, V.aux[q], st, sv, g, j);
+        a[q] = s.kind == JBUGS_ARG_XVAL ? v[s.id] : arg_value<false, S::NG_MAX>(s, V.aux[q], st, sv, g, j);
     }
     FamOut o;
     const bool bad = fam_eval(sp.family(), yv, a[0], a[1], o, V.aux[2].value);
@@ -275,7 +276,7 @@ __device__ __noinline__ bool tape_family(const S& sp, const PlateVals& V, const 
             const ArgS s = sp.aux(q);
             const double da = r * (q == 0 ? o.da0 : o.da1);
             if (s.kind == JBUGS_ARG_XVAL) w[s.id] += da;
-            else arg_adjoint(s, st, da);
+            else arg_adjoint<S::NG_MAX>(s, st, da);
         }
     }
     return bad;
@@ -290,15 +291,15 @@ __device__ __noinline__ void tape_reverse(const S& sp, const PlateVals& V, int j
         if (wk == 0.0) continue;
         const XOpDev o = V.xtape[k];
         if (o.op == JBUGS_OP_LEAF) {
-            if (o.kind == JBUGS_ARG_GVAL) bump(st.ga, o.id, wk);
-            else if (o.kind == JBUGS_ARG_GVEC_J) bump(st.ga, o.id + j, wk);
+            if (o.kind == JBUGS_ARG_GVAL) bump_n<S::NG_MAX>(st.ga, o.id, wk);
+            else if (o.kind == JBUGS_ARG_GVEC_J) bump_n<S::NG_MAX>(st.ga, o.id + j, wk);
             else if (o.kind == JBUGS_ARG_LOCAL) bump(st.la, o.id, wk);
         } else if (o.op == JBUGS_OP_SELECT) {
             w[v[o.a] != 0.0 ? o.b : o.c] += wk;
         } else if (o.op == JBUGS_OP_PICK_K) {
             w[o.a + state] += wk;
         } else if (o.op == JBUGS_OP_GVEC_AT) {
-            bump(st.ga, o.id + (int)v[o.a], wk);
+            bump_n<S::NG_MAX>(st.ga, o.id + (int)v[o.a], wk);
         } else {
             w[o.a] += wk * d1[k];
             if (o.op >= 16) w[o.b] += wk * d2[k];
@@ -317,7 +318,7 @@ __device__ __noinline__ bool observe_tape(const S& sp, const PlateVals& V, const
     double v[JBUGS_MAX_XOPS], w[JBUGS_MAX_XOPS], d1[JBUGS_MAX_XOPS], d2[JBUGS_MAX_XOPS];
     const int nx = sp.n_x();
     const int K = sp.n_states();
-    const double yv = arg_value(sp.y(), V.y, st, sv, g, j);
+    const double yv = arg_value<false, S::NG_MAX>(sp.y(), V.y, st, sv, g, j);
     bool bad = false;
     double l1;
     if (K <= 0) {
@@ -331,7 +332,7 @@ __device__ __noinline__ bool observe_tape(const S& sp, const PlateVals& V, const
     double branch[JBUGS_MAX_STATES];
     const int lps = sp.lp_slot();
     // a partially observed latent: an observed cell (state > 0 in the data leaf) takes the branch of its value only
-    const int zo = sp.zobs_slot() >= 0 ? (int)tape_leaf(V.xtape[sp.zobs_slot()], sv, g, j, st) : 0;
+    const int zo = sp.zobs_slot() >= 0 ? (int)tape_leaf<S::NG_MAX>(V.xtape[sp.zobs_slot()], sv, g, j, st) : 0;
     double mx = -dev_inf();
     for (int k = 0; k < K; ++k) {
         if (zo > 0 && k != zo - 1) { branch[k] = -dev_inf(); continue; }

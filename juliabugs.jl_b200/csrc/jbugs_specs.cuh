@@ -39,6 +39,7 @@ cudaError_t launch_fused_epil_t4(JBUGS_FUSED_PARAMS);
 // defined in spec_dyn.cu / spec_rats.cu / spec_glm.cu / spec_epil.cu
 cudaError_t launch_dyn(JBUGS_LAUNCH_PARAMS);
 cudaError_t launch_x(JBUGS_LAUNCH_PARAMS);  // expression-tape interpreter (XSpec)
+cudaError_t launch_xw(JBUGS_LAUNCH_PARAMS); // ... for tapes that reference more than MAX_GREF_LINEAR global values (XWSpec)
 cudaError_t launch_rats_t5(JBUGS_LAUNCH_PARAMS);
 cudaError_t launch_rats(JBUGS_LAUNCH_PARAMS);
 cudaError_t launch_seeds(JBUGS_LAUNCH_PARAMS);
@@ -71,9 +72,12 @@ static const SpecEntry g_specs[] = {
     {"epil_poisson_log", &launch_epil, &EpilDesc<0>::matches, EpilDesc<0>::FUSED, &launch_fused_epil, 0},
     {"pumps_poisson_gamma", &launch_pumps, &PumpsDesc::matches, PumpsDesc::FUSED, &launch_fused_pumps, 0},
     {"expression_tape", &launch_x, &match_never, FUSED_NONE, nullptr, 0},
+    {"expression_tape_wide", &launch_xw, &match_never, FUSED_NONE, nullptr, 0},
 };
 static const int g_num_specs = (int)(sizeof(g_specs) / sizeof(g_specs[0]));
-static const int g_xspec = g_num_specs - 1;  // the tape interpreter: selected by the plate kind, never by shape
+static const int g_xspec = g_num_specs - 2;   // the tape interpreter: selected by the plate kind, never by shape
+static const int g_xwspec = g_num_specs - 1;  // ... when the tape references more than MAX_GREF_LINEAR global values
+static inline bool is_tape_variant(int v) { return v == g_xspec || v == g_xwspec; }
 
 static int select_spec(const PlateShape& sh, long long T) {
     for (int k = 1; k < g_num_specs; ++k)

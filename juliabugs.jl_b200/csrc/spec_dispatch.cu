@@ -32,6 +32,7 @@ namespace jbugs {
     }
 JB_DISPATCH(launch_dyn)
 JB_DISPATCH(launch_x)
+JB_DISPATCH(launch_xw)
 JB_DISPATCH_NG(launch_rats_t5)
 JB_DISPATCH(launch_rats)
 JB_DISPATCH_NG(launch_seeds)

@@ -64,8 +64,9 @@ class UseCUDABatch(EvaluationMode):
 class UseAutoMarginalization(UseCUDABatch):
     """`UseAutoMarginalization()` (bugsmodel.jl:803-876, evaluation.jl:739-961) on the CUDA path: unobserved finite
     discrete nodes (`z[i] ~ dcat(w[1:K])` selecting the parameters of `y[i]`) are summed out inside the plate kernel,
-    theta holds the continuous parameters only.  The plate class covers one latent per observation cell (mixtures);
-    chained latents (HMMs) raise `LoweringError`."""
+    theta holds the continuous parameters only.  The plate class covers one latent per observation cell -- `dcat` or
+    `dbern`, possibly partially observed, with any number of observed children (mixtures, Cervix); chained latents
+    (HMMs) raise `LoweringError`."""
 
 
 class LogDensityOrder:

@@ -31,7 +31,7 @@ rng = np.random.default_rng(1)
 N = 2_000_000
 z = rng.random(N) < 0.3
 y = np.where(z, rng.normal(-2, 1.0, N), rng.normal(2, 0.7, N))
-m = jbugs.compile(GMM2 % (0.3, 0.7), {"N": N, "y": y}, evaluation_mode=jbugs.UseAutoMarginalization())
+m = jbugs.compile(GMM2 % (0.3, 0.7), {"N": N, "y": y}, evaluation_mode=jbugs.UseAutoMarginalization(specialize=False))
 names = m.lowering.param_names()
 vals = {"sigma[1]": 0.0, "sigma[2]": np.log(0.7), "mu[2]": 2.0, "mu[1]": -2.0}
 bench(m, np.array([vals[n] for n in names]), 1024, N, 0.0, "gmm2 2e6 x 1024")
@@ -54,7 +54,7 @@ text = """model {
 x = np.linspace(1.0, 30.0, T)
 a = rng.normal(2.6, 0.2, Ng)
 Y = a[:, None] - 1.0 * 0.87 ** x[None, :] + rng.normal(0, 0.1, (Ng, T))
-m2 = jbugs.compile(text, {"N": Ng, "T": T, "x": x, "y": Y})
+m2 = jbugs.compile(text, {"N": Ng, "T": T, "x": x, "y": Y}, evaluation_mode=jbugs.UseCUDABatch(specialize=False))
 names = m2.lowering.param_names()
 th = np.zeros(m2.plan.D)
 for k, n in enumerate(names):
