@@ -48,15 +48,32 @@ class _DrawEval(DataEval):
                         raise LoweringError("loop-dependent index range over a parameter array")
                     idx.append(slice(int(lo) - 1, int(hi)))
                 else:
-                    if self.has_draws(ie):
-                        raise LoweringError("array index depends on a parameter")
                     iv = np.asarray(self.ev(ie, lv))
+                    if self.has_draws(ie):
+                        # an index that varies from draw to draw (mu[z[i]] with z a recovered discrete latent)
+                        idx.append(np.broadcast_to(iv, iv.shape[:-1] + (self.S,)).astype(np.int64) - 1)
+                        continue
                     if iv.ndim:
                         iv = iv[..., 0]  # grids carry a trailing unit axis for the draws
                     idx.append(iv.astype(np.int64) - 1)
             if any(isinstance(i, slice) for i in idx) and any(isinstance(i, np.ndarray) and i.ndim for i in idx):
                 raise LoweringError("mixed slice / loop index over a parameter array")
+            if any(isinstance(i, np.ndarray) and i.ndim and i.shape[-1:] == (self.S,) and self.has_draws(ie)
+                   for i, ie in zip(idx, e.idx)):
+                full = [np.asarray(i)[..., None] if not (isinstance(i, np.ndarray) and i.ndim and i.shape[-1:] == (self.S,)
+                                                           and self.has_draws(ie)) else i for i, ie in zip(idx, e.idx)]
+                return arr[tuple(full) + (np.arange(self.S),)]
             return arr[tuple(idx)]
+        if isinstance(e, Index) and e.name not in self.draws and any(
+                not isinstance(ie, (Colon, Range)) and self.has_draws(ie) for ie in e.idx):
+            arr = np.asarray(self.data[e.name])
+            idx = []
+            for ie in e.idx:
+                if isinstance(ie, (Colon, Range)):
+                    raise LoweringError("slice of a data array next to a draw-dependent index")
+                iv = np.asarray(self.ev(ie, lv))
+                idx.append(np.broadcast_to(iv, np.broadcast_shapes(iv.shape, (self.S,))).astype(np.int64) - 1)
+            return arr[tuple(np.broadcast_arrays(*idx))]
         if isinstance(e, Call) and e.fn in ("mean", "sum", "sd", "inprod") and self.has_draws(e):
             args = [np.asarray(self.ev(a, lv), dtype=np.float64) for a in e.args]
             flat = [a.reshape(-1, self.S) if a.shape[-1:] == (self.S,) and self.has_draws(x) else a.reshape(-1, 1)
@@ -110,6 +127,81 @@ def _sample(rng, fn, args, shape):
     raise LoweringError(f"forward sampling of {fn} is not provided")
 
 
+def _logpdf(fn, y, a):
+    """log density of the observation families a summed-out latent's children may have (Appendix A parameterisations)"""
+    from scipy import special as sp
+    if fn == "dnorm":
+        return 0.5 * np.log(a[1]) - 0.5 * a[1] * (y - a[0]) ** 2 - 0.5 * np.log(2.0 * np.pi)
+    if fn == "dpois":
+        return y * np.log(a[0]) - a[0] - sp.gammaln(y + 1.0)
+    if fn == "dbern":
+        return np.where(y != 0, np.log(a[0]), np.log1p(-a[0]))
+    if fn == "dbin":
+        return (sp.gammaln(a[1] + 1.0) - sp.gammaln(y + 1.0) - sp.gammaln(a[1] - y + 1.0)
+                + sp.xlogy(y, a[0]) + sp.xlog1py(a[1] - y, -a[0]))
+    if fn == "dgamma":
+        return a[0] * np.log(a[1]) - sp.gammaln(a[0]) + (a[0] - 1.0) * np.log(y) - a[1] * y
+    if fn == "dexp":
+        return np.log(a[0]) - a[0] * y
+    if fn == "dlnorm":
+        return 0.5 * np.log(a[1]) - 0.5 * a[1] * (np.log(y) - a[0]) ** 2 - 0.5 * np.log(2.0 * np.pi) - np.log(y)
+    raise LoweringError(f"recovering a summed-out latent below a {fn} observation is not provided")
+
+
+def _recover_latents(lw: Lowering, de: "_DrawEval", env, S, rng, out):
+    """`forward_sample_generated_quantities!!` for a marginalised model (J/src/model/evaluation.jl:354-378 with the
+    latent-recovery step the reference's test pins, J/test/model/auto_marginalization.jl:975-1041): every summed-out
+    latent is drawn from p(z | theta, y) -- per cell proportional to p(z = k) * prod_children p(y_child | z = k), the
+    weights the plate kernel sums -- so that generated quantities depending on it can be forward-sampled."""
+    for z in lw.stmts:
+        if z.kind != "latent" or z.is_gq:
+            continue
+        fn = z.node.dist.fn
+        lv = {k: v[..., None] for k, v in _grids(z.extents, z.loop_vars).items()}
+        shape = tuple(z.shape) + (S,)
+        if fn == "dbern":
+            states = [0.0, 1.0]
+        else:
+            wa = z.node.dist.args[0]
+            states = [float(k) for k in range(1, int(lw.de.ev(wa.idx[-1].hi, {})) + 1)]
+        children = [t for t in lw.stmts if t.kind == "obs" and not t.is_gq and z.sid in lw._latents_of(t)]
+        if any(t.loops != z.loops for t in children):
+            raise LoweringError(f"'{z.name}': its observations must share its loop nest")
+        logw = []
+        for val in states:
+            env[z.name] = np.full((tuple(hi for _, hi in z.extents) or ()) + (S,), val) if z.loops else np.full(S, val)
+            if fn == "dbern":
+                p = np.broadcast_to(np.asarray(de.ev(lw._inline(z.node.dist.args[0]), lv), dtype=np.float64), shape)
+                lp = np.log(p) if val == 1.0 else np.log1p(-p)
+            else:
+                wa = z.node.dist.args[0]
+                zref = z.node.lhs if isinstance(z.node.lhs, Index) else Var(z.name)
+                lp = np.log(np.broadcast_to(np.asarray(de.ev(lw._inline(Index(wa.name, wa.idx[:-1] + (zref,))), lv),
+                                                       dtype=np.float64), shape))
+            for t in children:
+                a = [np.broadcast_to(np.asarray(de.ev(lw._inline(x), lv), dtype=np.float64), shape) for x in t.node.dist.args]
+                yl = t.node.lhs if isinstance(t.node.lhs, Index) else Var(t.name)
+                y = np.broadcast_to(np.asarray(lw.de.ev(yl, _grids(t.extents, t.loop_vars)), dtype=np.float64)[..., None], shape)
+                lp = lp + _logpdf(t.node.dist.fn, y, a)
+            logw.append(lp)
+        logw = np.stack(logw)                                   # (K,) + dims + (S,)
+        logw -= logw.max(axis=0, keepdims=True)
+        cdf = np.cumsum(np.exp(logw), axis=0)
+        u = rng.random(shape) * cdf[-1]
+        pick = (u[None] > cdf).sum(axis=0).clip(0, len(states) - 1)
+        zval = np.asarray(states)[pick]
+        if z.zobs is not None:                                  # observed cells keep their value (state number + 1 recorded)
+            obs = np.asarray(z.zobs)[..., None]
+            zval = np.where(obs > 0, np.asarray(states)[np.clip(obs.astype(np.int64) - 1, 0, len(states) - 1)], zval)
+        if z.loops:
+            cur = np.full(tuple(hi for _, hi in z.extents) + (S,), np.nan)
+            cur[tuple(slice(lo - 1, hi) for lo, hi in z.extents)] = zval
+            env[z.name] = cur
+        else:
+            env[z.name] = zval.reshape(S)
+        out[z.name] = env[z.name]
+
+
 def generated_quantities(lowering: Lowering, draws: Dict[str, np.ndarray], seed: int = 0,
                          only_gq: bool = True) -> Dict[str, np.ndarray]:
     """`draws[label]` = array of S draws (any shape, flattened) for parameter labels such as 'tau' or 'beta[2]'
@@ -149,6 +241,8 @@ def generated_quantities(lowering: Lowering, draws: Dict[str, np.ndarray], seed:
         env[s.name] = cur
     de = _DrawEval(lw.data, env, S)
     out: Dict[str, np.ndarray] = {}
+    if getattr(lw, "marginalize", False):
+        _recover_latents(lw, de, env, S, rng, out)
     pending = [s for s in lw.stmts if s.kind == "logical" or (s.kind == "param" and s.is_gq)]
     progress = True
     while pending and progress:

@@ -74,6 +74,9 @@ class Chains:
         monitored parameters for every draw at once (reference: J/src/model/abstractmcmc.jl:92-110).
         `device=True`: the lowered program on the GPU (jbugs/gq_device.py, one thread per draw) instead of numpy on
         the host; the monitored rows must cover the parameters the quantities read."""
+        if self._gq is None and device and any(s.kind == "latent" for s in self.model.lowering.stmts):
+            raise ValueError("a marginalised model recovers its summed-out latents from p(z | theta, y) on the host: "
+                             "call generated_quantities(device=False)")
         if self._gq is None and device:
             from .gq_device import DeviceGQ
             dq = DeviceGQ(self.model.lowering, device=self.model.evaluation_mode.device, only_gq=True)

@@ -554,3 +554,62 @@ def test_cuda_eight_component_mixture():
         assert np.max(np.abs(lp - lp0) / np.maximum(1.0, np.abs(lp0))) < 1e-12
         scale = np.maximum(np.abs(g0), 1e-4 * np.abs(g0).max(axis=0, keepdims=True))
         assert np.max(np.abs(g - g0) / scale) < 1e-10
+
+
+# ---- generated quantities of a marginalised model: the summed-out latents are recovered from p(z | theta, y) before
+# quantities that depend on them are forward-sampled (J/test/model/auto_marginalization.jl:975-1041, "case 3"; the
+# reference pins the empirical distribution of the recovered latents and E[g] against the analytic posterior)
+GMM_GQ = """model {
+  w[1] <- 0.3
+  w[2] <- 0.7
+  mu[1] ~ dnorm(-2, 0.04)
+  mu[2] ~ dnorm(2, 0.04)
+  for (i in 1:N) {
+    z[i] ~ dcat(w[1:2])
+    y[i] ~ dnorm(mu[z[i]], 1.0)
+  }
+  g ~ dnorm(mu[z[1]], 1)
+}"""
+
+
+def test_recovered_latents_follow_their_posterior():
+    from jbugs import gq
+    data = {"N": 3, "y": np.array([-0.3, 0.6, 0.1])}
+    plan, lw = jbugs.lower(GMM_GQ, data, marginalize=True)
+    assert sorted(lw.param_names()) == ["mu[1]", "mu[2]"]        # g is a generated quantity, z is summed out
+    n, mu = 40000, [-0.5, 1.0]
+    out = gq.generated_quantities(lw, {"mu[1]": np.full(n, mu[0]), "mu[2]": np.full(n, mu[1])}, seed=1)
+    assert out["z"].shape == (3, n) and out["g"].shape == (n,)
+    post = []
+    for i, y in enumerate(data["y"]):
+        w = np.array([0.3 * S.norm(mu[0], 1).pdf(y), 0.7 * S.norm(mu[1], 1).pdf(y)])
+        post.append(w / w.sum())
+        assert abs((out["z"][i] == 2).mean() - post[-1][1]) < 0.02     # the reference's tolerance
+    assert set(np.unique(out["z"])) == {1.0, 2.0}
+    assert out["g"].mean() == pytest.approx(post[0] @ np.array(mu), abs=0.05)
+
+
+def test_recovered_bernoulli_latents_with_two_children():
+    """Cervix subset: x[i] | theta, d[i], w[i]; observed exposures keep their values"""
+    from jbugs import examples as ex
+    from jbugs import gq
+    sel = np.r_[0:3, 40:43, 200:203, 2040:2043]
+    data = _cervix_data(sel)
+    plan, lw = jbugs.lower(ex.CERVIX, data, marginalize=True)
+    n = 30000
+    val = {"q": 0.4, "beta0C": -0.3, "beta": 0.9, "phi[1,1]": 0.2, "phi[1,2]": 0.35, "phi[2,1]": 0.6, "phi[2,2]": 0.8}
+    out = gq.generated_quantities(lw, {k: np.full(n, v) for k, v in val.items()}, seed=3)
+    x = out["x"]
+    sig = lambda v: 1.0 / (1.0 + np.exp(-v))   # noqa: E731
+    for i in range(len(sel)):
+        if not np.isnan(data["x"][i]):
+            assert (x[i] == data["x"][i]).all()
+            continue
+        d, w = int(data["d"][i]), int(data["w"][i])
+        wt = []
+        for xv in (0, 1):
+            p = sig(val["beta0C"] + val["beta"] * xv)
+            ph = val[f"phi[{xv + 1},{d + 1}]"]
+            wt.append((val["q"] if xv else 1 - val["q"]) * (p if d else 1 - p) * (ph if w else 1 - ph))
+        assert abs((x[i] == 1).mean() - wt[1] / sum(wt)) < 0.02
+    assert "gamma1" in out and out["gamma1"].shape == (n,)
