@@ -613,3 +613,26 @@ def test_recovered_bernoulli_latents_with_two_children():
             wt.append((val["q"] if xv else 1 - val["q"]) * (p if d else 1 - p) * (ph if w else 1 - ph))
         assert abs((x[i] == 1).mean() - wt[1] / sum(wt)) < 0.02
     assert "gamma1" in out and out["gamma1"].shape == (n,)
+
+
+@pytest.mark.gpu
+def test_nuts_on_a_marginalised_mixture_and_latent_recovery():
+    """auto_marginalization.jl:747-813 (AutoMarg + NUTS runs, fewer dimensions than the graph model, finite draws) on the
+    device sampler, plus what the CPU reference cannot afford in a smoke test: the posterior means, and the recovered
+    latents classifying the observations"""
+    import jbugs.hmc as hmc
+    rng = np.random.default_rng(42)
+    y = np.concatenate([rng.normal(-2, 1, 50), rng.normal(2, 1, 50)])
+    m = jbugs.compile(GMM2 % (0.3, 0.7), {"N": 100, "y": y}, evaluation_mode=jbugs.UseAutoMarginalization())
+    assert jbugs.LogDensityProblems.dimension(m) == 4          # the graph model has 104
+    names = m.lowering.param_names()
+    init = theta_by_name(names, {"mu[1]": -2.0, "mu[2]": 2.0, "sigma[1]": 0.0, "sigma[2]": 0.0})
+    ch = hmc.sample(m, hmc.NUTS(max_depth=6), n_samples=200, n_adapts=200, n_chains=64, seed=7, init=init)
+    assert np.isfinite(ch.samples).all() and np.abs(ch.samples).max() < 20
+    assert ch.mean("mu[1]") == pytest.approx(y[:50].mean(), abs=0.5)
+    assert ch.mean("mu[2]") == pytest.approx(y[50:].mean(), abs=0.5)
+    gq = ch.generated_quantities()
+    z = gq["z"].reshape(100, -1)
+    assert (z[:50] == 1).mean() > 0.85 and (z[50:] == 2).mean() > 0.85
+    with pytest.raises(ValueError):
+        hmc.sample(m, hmc.NUTS(max_depth=4), n_samples=5, n_adapts=5, n_chains=32, init=init).generated_quantities(device=True)
