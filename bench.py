@@ -661,7 +661,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configurations")
-    ap.add_argument("--secondary", default="seeds,dense,pumps,epil,rats_variant,mixture")
+    ap.add_argument("--secondary", default="seeds,seeds_c64,dense,pumps,epil,rats_variant,mixture")
     ap.add_argument("--dynamic", type=int, default=0, help="1 = force the interpreter kernel")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--tma", type=int, default=-1, help="0 = stage plate data with cp.async only (A/B against the TMA path)")
@@ -747,9 +747,12 @@ def main():
     if not args.no_secondary and not args.groups and not args.chains:
         sec = []
         for nm in [s for s in args.secondary.split(",") if s and s != args.workload]:
-            Ks = {"seeds": 20, "dense": 3, "pumps": 50, "epil": 50, "rats_variant": 40, "mixture": 10}.get(nm, 10)
+            Ks = {"seeds": 20, "seeds_c64": 40, "dense": 3, "pumps": 50, "epil": 50, "rats_variant": 40, "mixture": 10}.get(nm, 10)
             try:
-                o, _, _, _ = measure(nm, ctx, args, Ks, 3, DEFAULT_CHAINS[nm], primary=False)
+                if nm == "seeds_c64":   # BASELINE config 3 leaves the chain count open (64 or 256): both are reported
+                    o, _, _, _ = measure("seeds", ctx, args, Ks, 3, 64, primary=False)
+                else:
+                    o, _, _, _ = measure(nm, ctx, args, Ks, 3, DEFAULT_CHAINS[nm], primary=False)
                 sec.append({k: o[k] for k in ("value", "unit", "ms_per_step", "ms_per_step_p50", "ms_per_step_p95", "steps",
                                               "warmup", "scaling", "config", "clocks", "roofline", "gpu_launches")})
                 sec[-1]["name"] = nm
