@@ -636,3 +636,60 @@ def test_nuts_on_a_marginalised_mixture_and_latent_recovery():
     assert (z[:50] == 1).mean() > 0.85 and (z[50:] == 2).mean() > 0.85
     with pytest.raises(ValueError):
         hmc.sample(m, hmc.NUTS(max_depth=4), n_samples=5, n_adapts=5, n_chains=32, init=init).generated_quantities(device=True)
+
+
+# ---- every family a latent's further observed child may have (folded into the state's log weight as tape arithmetic)
+def _two_children(kind):
+    second = {"dnorm": "c[i] ~ dnorm(a[z[i]], 2.0)",
+              "dpois": "c[i] ~ dpois(lam[i])\n    log(lam[i]) <- a[z[i]]",
+              "dbin": "c[i] ~ dbin(pr[i], n[i])\n    logit(pr[i]) <- a[z[i]]",
+              "dbern": "c[i] ~ dbern(pr[i])\n    logit(pr[i]) <- a[z[i]]"}[kind]
+    text = f"""model {{
+  w[1] <- 0.4
+  w[2] <- 0.6
+  mu[1] ~ dnorm(-1, 0.25)
+  mu[2] ~ dnorm(1, 0.25)
+  a[1] ~ dnorm(0, 1)
+  a[2] ~ dnorm(0.5, 1)
+  for (i in 1:N) {{
+    z[i] ~ dcat(w[1:2])
+    y[i] ~ dnorm(mu[z[i]], 1.5)
+    {second}
+  }}
+}}"""
+    rng = np.random.default_rng(5)
+    N = 5
+    data = {"N": N, "y": rng.standard_normal(N)}
+    if kind == "dnorm":
+        data["c"] = rng.standard_normal(N)
+    elif kind == "dpois":
+        data["c"] = rng.poisson(1.5, N).astype(float)
+    elif kind == "dbin":
+        data["n"] = rng.integers(3, 9, N).astype(float)
+        data["c"] = rng.binomial(data["n"].astype(int), 0.5).astype(float)
+    else:
+        data["c"] = rng.integers(0, 2, N).astype(float)
+    return text, data
+
+
+@pytest.mark.parametrize("kind", ["dnorm", "dpois", "dbin", "dbern"])
+def test_second_child_families_against_the_node_oracle(kind):
+    text, data = _two_children(kind)
+    plan, gm = lowered(text, data)
+    assert len(plan.plates) == 1 and plan.D == 4
+    theta = 0.5 * np.random.default_rng(8).standard_normal((plan.D, 4))
+    check_c_port(plan, gm, theta)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["dnorm", "dpois", "dbin", "dbern"])
+def test_cuda_second_child_families(kind):
+    text, data = _two_children(kind)
+    m = jbugs.compile(text, data, evaluation_mode=jbugs.UseAutoMarginalization())
+    theta = 0.5 * np.random.default_rng(9).standard_normal((m.plan.D, 70))
+    lp0, g0, _ = COracle(m.plan).eval_batch(theta)
+    lp, g, st = m.cuda.eval_host(theta, layout="param_fast")
+    assert (st == 0).all()
+    assert np.max(np.abs(lp - lp0) / np.maximum(1.0, np.abs(lp0))) < 1e-12
+    scale = np.maximum(np.abs(g0), 1e-4 * np.abs(g0).max(axis=0, keepdims=True))
+    assert np.max(np.abs(g - g0) / scale) < 1e-10
