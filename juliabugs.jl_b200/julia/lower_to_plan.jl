@@ -42,7 +42,7 @@ const DISCRETE = Set([6, 7, 8, 13, 16, 17, 18])
 const TR_IDENTITY, TR_LOG, TR_LOGIT, TR_UPPER = 0, 1, 2, 3
 const OP_IDENTITY, OP_EXP, OP_LOGISTIC, OP_CEXPEXP, OP_PHI, OP_LOG, OP_SQRT, OP_NEG = 0:7
 const OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_LEAF, OP_SELECT, OP_PICK_K = 16, 17, 18, 19, 20, 32, 33, 34
-const OP_GVEC_AT = 35   # gval[leaf.id + Int(v[a])] (jbugs_plan.h); emitted by the Python pass only so far (LeukFr's b[pair[i]])
+const OP_GVEC_AT = 35   # gval[leaf.id + Int(v[a])] (jbugs_plan.h): LeukFr's b[pair[i]] inside an expression plate
 const LINK_OF = Dict(:exp => OP_EXP, :logistic => OP_LOGISTIC, :ilogit => OP_LOGISTIC, :cexpexp => OP_CEXPEXP,
                      :icloglog => OP_CEXPEXP, :phi => OP_PHI)
 const UNARY_OF = merge(LINK_OF, Dict(:log => OP_LOG, :sqrt => OP_SQRT))
@@ -805,6 +805,17 @@ function vector_globals(lw::Lowering)
                 end
             end
         end
+        # ... and vectors picked through a data index of the inner loop variable next to parameters indexed by the outer
+        # one (LeukFr: exp(beta * Z[i] + b[pair[i]]) * dL0[j]): read on the tape as gval[base + index] (OP_GVEC_AT)
+        if !isempty(outer)
+            for r in prm
+                (length(r.args) == 2 && !(r.args[2] isa Symbol) && !is_range(r.args[2]) && !is_colon(r.args[2]) &&
+                 is_data(lw, r.args[2], lv) && !is_data(lw, r.args[2], Symbol[]) && !(lv[1] in free_vars(r.args[2]))) || continue
+                for d in defs(lw, r.args[1])
+                    (d.kind == :param && length(d.loops) == 1 && size_of(d) <= 22) && push!(found, d.sid)
+                end
+            end
+        end
     end
     # (2) elements referenced with constant subscripts by an observation or a scalar logical node (Stacks: beta[1] * z[i,1])
     for s in lw.stmts
@@ -1185,6 +1196,26 @@ function sibling_logpdf(t::Stmt, s::Stmt)
     fail("'$(name_of(t))': a second observation of a summed-out latent must be dbern, dbin, dnorm or dpois")
 end
 
+"""(first global value slot, number of elements, 0-based index expression) when `e` is `name[idx]` with `name` a parameter
+vector whose elements were expanded into consecutive globals and `idx` a data expression that varies over the plate
+(lowering.py _gvec_at), else nothing"""
+function gvec_at(lw::Lowering, e, s::Stmt)
+    lvs = loop_vars(s)
+    idx = e.args[2:end]
+    (length(idx) == 1 && !is_range(idx[1]) && !is_colon(idx[1]) && is_data(lw, idx[1], lvs) && !is_data(lw, idx[1], Symbol[])) || return nothing
+    ds = [d for d in defs(lw, e.args[1]) if d.kind == :param && !d.is_gq]
+    (length(ds) == 1 && length(ds[1].loops) == 1) || return nothing
+    lo, hi = ds[1].extents[1]
+    ids = [get(lw.gval_ids, label(e.args[1], [k]), -1) for k in lo:hi]
+    (all(>=(0), ids) && ids == collect(ids[1]:(ids[1] + length(ids) - 1))) || return nothing
+    vals = grid(lw.de, idx[1], lvs, s.extents)
+    seen = s.obs_mask === nothing ? trues(size(vals)) : s.obs_mask
+    v = vals[seen]
+    (any(isnan, v) || any(x -> x != floor(x), v) || minimum(v) < lo || maximum(v) > hi) &&
+        fail("'$(e)': the data index leaves the parameter vector")
+    return ids[1], length(ids), Expr(:call, :-, idx[1], Float64(lo))
+end
+
 """`phi[2, d1[i]]`: an element of a short parameter array whose elements are globals, picked by data subscripts that vary
 over the plate -> nested selects over the index tuples that occur (lowering.py _global_pick)"""
 function global_pick(lw::Lowering, e, s::Stmt)
@@ -1298,6 +1329,18 @@ function tape!(lw::Lowering, e, s::Stmt, plate::Plate, tape::Vector{XOp}, memo::
         ref = (:l, e.args[1], e.args[2:end])
         is_gvec_ref(lw, s, ref) &&
             return push_op(XOp(OP_LEAF, 0, 0, 0, Arg(ARG_GVEC_J, lw.gval_ids[label(e.args[1], [s.extents[2][1]])])))
+        at = gvec_at(lw, e, s)
+        if at !== nothing
+            # b[pair[i]]: an element of a parameter vector (consecutive global values) picked by a data index
+            base, cnt, idx0 = at
+            ia = rec(idx0)
+            lf = tape[ia + 1]
+            if lf.op == OP_LEAF && lf.leaf.kind in (ARG_CONST, ARG_ONE)      # the same element everywhere
+                k0 = Int(lf.leaf.kind == ARG_ONE ? 1.0 : lf.leaf.value)
+                return push_op(XOp(OP_LEAF, 0, 0, 0, Arg(ARG_GVAL, base + k0)))
+            end
+            return push_op(XOp(OP_GVEC_AT, ia, 0, 0, Arg(ARG_GVAL, Int32(base), Float64(cnt))))
+        end
         picked = global_pick(lw, e, s)
         picked !== nothing && return (memo[key] = rec(picked))
         return push_op(XOp(OP_LEAF, 0, 0, 0, Arg(ARG_LOCAL, local_index!(lw, plate, s, ref, used))))
