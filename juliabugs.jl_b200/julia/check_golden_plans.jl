@@ -20,7 +20,7 @@ const EXAMPLES = Dict("rats" => :rats, "pumps" => :pumps, "dogs" => :dogs, "seed
                       "surgical_realistic" => :surgical_realistic, "surgical_simple" => :surgical_simple, "epil" => :epil,
                       "blockers" => :blockers, "oxford" => :oxford, "salm" => :salm, "equiv" => :equiv, "dyes" => :dyes,
                       "stacks" => :stacks, "bones" => :bones, "dugongs" => :dugongs, "lsat" => :lsat, "air" => :air,
-                      "leuk" => :leuk)
+                      "leuk" => :leuk, "leukfr" => :leukfr)
 
 # plans lowered with `marginalize=true` (the reference's UseAutoMarginalization): Cervix sums its 1929 missing x[i] out
 const MARGINALISED = Dict("cervix_marginalised" => :cervix)
