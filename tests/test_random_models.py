@@ -112,3 +112,43 @@ def test_nonlinear_random_model_cuda_matches_c_oracle(seed):
     theta = random_thetas(np.zeros(m.plan.D), 70, seed=seed, scale=0.3)
     _check(m.cuda, COracle(m.plan), theta)
     _check(m.cuda, COracle(m.plan), theta, layout="param_fast")
+
+
+def _truncate_a_prior(text, seed):
+    """the random model with the prior of its intercept replaced by a truncated normal (one, two or upper-only bounds)"""
+    import re
+    bounds = ["T(-1.5, 2.0)", "T(0, )", "T(, 1.2)"][seed % 3]
+    new, n = re.subn(r"(\n  b0 ~ )[a-z]+\([^)]*\)", rf"\1dnorm(0.3, 1.5) {bounds}", text, count=1)
+    return new if n else None
+
+
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_random_model_with_a_truncated_prior(seed):
+    text, data, desc = make(seed)
+    text = _truncate_a_prior(text, seed)
+    if text is None:
+        pytest.skip("no intercept in this model")
+    gm = go.compile(text, data).use_generated_order()
+    plan, lw = jbugs.lower(text, data)
+    assert lw.param_names() == gm.param_names(), desc
+    theta = random_thetas(np.zeros(plan.D), 3, seed=seed, scale=0.3)
+    lp, g, st = COracle(plan).eval_batch(theta)
+    for c in range(3):
+        lp_g, g_g = gm.logdensity_and_gradient(theta[:, c])
+        if not np.isfinite(lp_g):
+            assert lp[c] == lp_g, desc
+            continue
+        assert st[c] == 0 and abs(lp[c] - lp_g) <= 1e-11 * max(1.0, abs(lp_g)), (desc, text)
+        assert grad_err(g[:, c], g_g) < 1e-10, (desc, text)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_random_model_with_a_truncated_prior_cuda(seed):
+    from test_gpu_parity import _check
+    text, data, desc = make(seed)
+    text = _truncate_a_prior(text, seed)
+    if text is None:
+        pytest.skip("no intercept in this model")
+    m = jbugs.compile(text, data)
+    _check(m.cuda, COracle(m.plan), random_thetas(np.zeros(m.plan.D), 37, seed=seed, scale=0.3))
