@@ -142,10 +142,11 @@ typedef struct jbugs_global {
     int64_t theta_idx;  /* slot in theta                                             */
     uint32_t transform; /* jbugs_transform (IDENTITY for every slot when !transformed) */
     uint32_t family;    /* prior                                                      */
-    double lb, ub;      /* support bounds used by the transform.  A dnorm whose bounds are narrower than
-                           the real line is truncated(dnorm(mu, tau), lb, ub) -- BUGS `dnorm(mu, tau) T(lb, ub)`,
-                           bugs_parser.jl:470-500: literal arguments only, the normaliser
-                           log(cdf(ub) - cdf(lb)) is folded into the prior's constant              */
+    double lb, ub;      /* support bounds used by the transform.  A prior whose bounds are narrower than the
+                           natural support of its family is truncated(dist(args), lb, ub) -- BUGS
+                           `dist(args) T(lb, ub)`, bugs_parser.jl:470-500: literal arguments only, the
+                           normaliser log(cdf(ub) - cdf(lb)) is folded into the prior's constant
+                           (jbugs_trunc.h lists the families)                                        */
     jbugs_arg args[3];  /* prior arguments: CONST | GVAL (of an earlier global/gtape) */
 } jbugs_global;         /* 80 bytes */
 

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/jbugs_cuda.h"
+#include "../../include/jbugs_trunc.h"
 #define JBUGS_HOST_TU
 #include "jbugs_kernels.cuh"
 #include "jbugs_obsconst.cuh"
@@ -682,20 +683,17 @@ extern "C" int jbugs_plan_create(const void* blob, size_t nbytes, int device, jb
                 p->gp.cst[k] = a0 * std::log(a1) - std::lgamma(a0);
             }
         }
-        // truncated(dnorm(mu, tau), lb, ub) (BUGS: dnorm(mu, tau) T(lb, ub)): a dnorm global whose support bounds are
-        // narrower than the real line.  The bounds already steer the bijector; the normaliser log(cdf(ub) - cdf(lb)) is a
-        // constant for literal arguments and joins the host-folded part of the prior.
-        if (g.family == JBUGS_FAM_NORMAL && g.lb < g.ub && (std::isfinite(g.lb) || std::isfinite(g.ub))) {
-            if (p->gp.fast[k] != JBUGS_FAM_NORMAL + 1)
-                return destroy(fail(JBUGS_ERR_UNSUPPORTED, "global %u: a truncated dnorm needs literal arguments", k));
+        // truncated(dist(args), lb, ub) (BUGS: dist(args) T(lb, ub)): a global whose support bounds are narrower than the
+        // natural support of its family (include/jbugs_trunc.h).  The bounds already steer the bijector; the normaliser
+        // log(cdf(ub) - cdf(lb)) is a constant for literal arguments and joins the host-folded part of the prior (a prior
+        // with parameter-valued arguments and narrowed bounds is refused by the lowering).
+        if (lit(g.args[0]) && lit(g.args[1]) && jbugs_is_truncated(g.family, val(g.args[0]), val(g.args[1]), g.lb, g.ub) == 1) {
             if (!p->gp.transformed)
                 return destroy(fail(JBUGS_ERR_UNSUPPORTED, "global %u: truncated priors are evaluated in transformed space only "
                                                            "(the support check of the untransformed value is not on the device)", k));
-            const double a0 = p->gp.g[k].args[0].value, a1 = p->gp.g[k].args[1].value;
-            const double sd = std::sqrt(1.0 / a1), za = (g.lb - a0) / sd, zb = (g.ub - a0) / sd, r2 = std::sqrt(2.0);
-            const double mass = za > 0 ? 0.5 * std::erfc(za / r2) - 0.5 * std::erfc(zb / r2)
-                                       : 0.5 * std::erfc(-zb / r2) - 0.5 * std::erfc(-za / r2);
-            p->gp.cst[k] -= std::log(mass);
+            const double lm = jbugs_trunc_logmass(g.family, val(g.args[0]), val(g.args[1]), g.lb, g.ub);
+            if (!std::isfinite(lm)) return destroy(fail(JBUGS_ERR_INVALID, "global %u: the truncation bounds hold no mass", k));
+            p->gp.cst[k] -= lm;
         }
     }
     for (uint32_t k = 0; k < h.n_gtape; ++k) p->tp.op[k] = p->gtape[k];

@@ -541,7 +541,7 @@ __device__ __forceinline__ void finalize_body(const GlobalsParams& G, const GTap
         }
         FamOut o;
         bad |= fam_eval((int)g.family, gv[h], garg(g.args[0], gv), garg(g.args[1], gv), o, garg(g.args[2], gv));
-        lp += o.lp;
+        lp += o.lp + G.cst[h];  // (cst: 0, or minus the log mass of a truncated prior with literal arguments)
         ga[h] += o.dx;
         if (g.args[0].kind == JBUGS_ARG_GVAL) ga[g.args[0].id] += o.da0;
         if (g.args[1].kind == JBUGS_ARG_GVAL) ga[g.args[1].id] += o.da1;

@@ -1343,8 +1343,10 @@ class Lowering:
         support (Bijectors: log for a lower bound, scaled logit for both) -- and mark the global as truncated for the
         evaluators, which fold the normaliser log(cdf(upper) - cdf(lower)) into the prior's constant
         (include/jbugs_plan.h, jbugs_global.lb / ub)."""
-        if fam != P.FAM_NORMAL:
-            raise LoweringError(f"'{s.name}': T(,) is lowered for dnorm priors only")
+        if fam not in (P.FAM_NORMAL, P.FAM_LOGNORMAL, P.FAM_LOGISTIC, P.FAM_LAPLACE, P.FAM_EXPONENTIAL, P.FAM_GAMMA,
+                       P.FAM_WEIBULL, P.FAM_CHISQ, P.FAM_UNIFORM):
+            raise LoweringError(f"'{s.name}': T(,) is lowered for dnorm, dlnorm, dlogis, ddexp, dexp, dgamma, dweib, dchisqr "
+                                "and dunif priors")
         if not self.transformed:
             raise LoweringError(f"'{s.name}': truncated priors are evaluated in transformed space only")
         if not all(self._is_data(a, ()) for a in dargs):
@@ -1358,9 +1360,10 @@ class Lowering:
             if not self._is_data(b, ()):
                 raise LoweringError(f"'{s.name}': truncation bounds must be constants")
             bounds.append(float(self.de.ev(b, {})))
-        lb, ub = bounds
+        _, nlo, nhi = self._transform_of(fam, dargs)          # the family's own support
+        lb, ub = max(bounds[0], nlo), min(bounds[1], nhi)
         if not lb < ub:
-            raise LoweringError(f"'{s.name}': truncation needs lower < upper")
+            raise LoweringError(f"'{s.name}': truncation needs lower < upper inside the support of the distribution")
         if math.isfinite(lb) and math.isfinite(ub):
             return P.TR_LOGIT, lb, ub
         if math.isfinite(lb):

@@ -37,6 +37,7 @@ const FAMILY_NARGS = Dict(0 => 2, 1 => 2, 2 => 1, 3 => 2, 4 => 2, 5 => 2, 6 => 1
                           12 => 2, 13 => 2, 14 => 1, 15 => 3, 16 => 1, 17 => 1, 18 => 3)
 const FAM_GAMMA, FAM_EXPONENTIAL, FAM_UNIFORM, FAM_BETA, FAM_LOGNORMAL = 1, 2, 3, 4, 5
 const FAM_BERNOULLI, FAM_BINOMIAL, FAM_FLAT, FAM_WEIBULL, FAM_CHISQ, FAM_T, FAM_CATEGORICAL = 6, 7, 9, 12, 14, 15, 17
+const FAM_NORMAL, FAM_LOGISTIC, FAM_LAPLACE = 0, 10, 11
 const FAM_BETABIN = 18   # dbetabin(a, b, n): the third argument (n) is a constant, like dt's degrees of freedom
 const DISCRETE = Set([6, 7, 8, 13, 16, 17, 18])
 const TR_IDENTITY, TR_LOG, TR_LOGIT, TR_UPPER = 0, 1, 2, 3
@@ -692,7 +693,8 @@ end
 _truncation): the bounds are the prior's support and pick the bijector; the evaluators fold log(cdf(upper) - cdf(lower))
 into the prior's constant (include/jbugs_plan.h, jbugs_global.lb / ub)"""
 function truncation(lw::Lowering, s::Stmt, fam, dargs, sub)
-    fam == FAM_NORMAL || fail("'$(name_of(s))': T(,) is lowered for dnorm priors only")
+    fam in (FAM_NORMAL, FAM_LOGNORMAL, FAM_LOGISTIC, FAM_LAPLACE, FAM_EXPONENTIAL, FAM_GAMMA, FAM_WEIBULL, FAM_CHISQ, FAM_UNIFORM) ||
+        fail("'$(name_of(s))': T(,) is lowered for dnorm, dlnorm, dlogis, ddexp, dexp, dgamma, dweib, dchisqr and dunif priors")
     lw.transformed || fail("'$(name_of(s))': truncated priors are evaluated in transformed space only")
     all(a -> is_data(lw, a, Symbol[]), dargs) || fail("'$(name_of(s))': a truncated prior needs constant arguments")
     bounds = Float64[]
@@ -705,8 +707,9 @@ function truncation(lw::Lowering, s::Stmt, fam, dargs, sub)
         is_data(lw, b, Symbol[]) || fail("'$(name_of(s))': truncation bounds must be constants")
         push!(bounds, Float64(ev(lw.de, b, Dict{Symbol,Int}())))
     end
-    lb, ub = bounds
-    lb < ub || fail("'$(name_of(s))': truncation needs lower < upper")
+    _, nlo, nhi = transform_of(lw, fam, dargs)        # the family's own support
+    lb, ub = max(bounds[1], nlo), min(bounds[2], nhi)
+    lb < ub || fail("'$(name_of(s))': truncation needs lower < upper inside the support of the distribution")
     isfinite(lb) && isfinite(ub) && return TR_LOGIT, lb, ub
     isfinite(lb) && return TR_LOG, lb, ub
     isfinite(ub) && return TR_UPPER, lb, ub

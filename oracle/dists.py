@@ -367,25 +367,50 @@ class Censored(Dist):
         return self.inner.logpdf(M, x)
 
 
+def _scipy_frozen(inner):
+    """scipy.stats twin of an oracle distribution with constant arguments (for the cdf of a truncated prior)"""
+    from scipy import stats as S
+    const = lambda *vs: all(isinstance(v, (int, float)) for v in vs)   # noqa: E731
+    if isinstance(inner, Normal) and const(inner.mu, inner.sigma):
+        return S.norm(inner.mu, inner.sigma)
+    if isinstance(inner, LogNormal) and const(inner.mu, inner.sigma):
+        return S.lognorm(s=inner.sigma, scale=math.exp(inner.mu))
+    if isinstance(inner, Logistic) and const(inner.mu, inner.s):
+        return S.logistic(inner.mu, inner.s)
+    if isinstance(inner, Laplace) and const(inner.mu, inner.b):
+        return S.laplace(inner.mu, inner.b)
+    if isinstance(inner, Exponential) and const(inner.theta):
+        return S.expon(scale=inner.theta)
+    if isinstance(inner, Gamma) and const(inner.k, inner.theta):
+        return S.gamma(inner.k, scale=inner.theta)
+    if isinstance(inner, Weibull) and const(inner.a, inner.theta):
+        return S.weibull_min(inner.a, scale=inner.theta)
+    if isinstance(inner, Chisq) and const(inner.k):
+        return S.chi2(inner.k)
+    if isinstance(inner, Uniform) and const(inner.a, inner.b):
+        return S.uniform(inner.a, inner.b - inner.a)
+    raise NotImplementedError("T(,) is restated for dnorm, dlnorm, dlogis, ddexp, dexp, dgamma, dweib, dchisqr and dunif "
+                              "with constant arguments")
+
+
 class TruncatedNormal(Dist):
-    """`truncated(dnorm(mu, tau), lower, upper)` (Distributions.truncated; the BUGS suffix T(lower, upper),
-    bugs_parser.jl:470-500): logpdf(x) = logpdf_Normal(x) - log(cdf(upper) - cdf(lower)) inside the bounds, -Inf outside;
-    the support -- hence the bijector -- is [lower, upper].  The normaliser is written for constant mu, tau and bounds
-    (half-normal / truncated-normal priors, e.g. Magnesium's `tau.sqrd[6] ~ dnorm(0, p0) T(0,)`); it needs the normal
-    cdf, computed from erfc on the side of the smaller tail so that the difference does not cancel."""
+    """`truncated(dist(args), lower, upper)` (Distributions.truncated; the BUGS suffix T(lower, upper),
+    bugs_parser.jl:470-500): logpdf(x) = logpdf_inner(x) - log(cdf(upper) - cdf(lower)) inside the bounds, -Inf outside;
+    the support -- hence the bijector -- is the intersection of [lower, upper] with the inner support.  The normaliser
+    is written for constant arguments and bounds (half-normal / truncated priors, e.g. Magnesium's
+    `tau.sqrd[6] ~ dnorm(0, p0) T(0,)`); it comes from scipy's cdf / sf on the side where the difference does not
+    cancel -- an implementation independent of the product's include/jbugs_trunc.h.  (The class keeps the name it had
+    when only dnorm was restated.)"""
 
     def __init__(self, M, inner, lower, upper):
-        if not isinstance(inner, Normal):
-            raise NotImplementedError("T(,) is restated for dnorm only")
-        for v in (inner.mu, inner.sigma, lower, upper):
+        for v in (lower, upper):
             if not isinstance(v, (int, float)):
-                raise NotImplementedError("T(,) needs constant arguments and bounds")
-        self.inner, self.lower, self.upper = inner, float(lower), float(upper)
+                raise NotImplementedError("T(,) needs constant bounds")
+        fz = _scipy_frozen(inner)
+        lo, hi = inner.support()
+        self.inner, self.lower, self.upper = inner, max(float(lower), float(lo)), min(float(upper), float(hi))
         _check(self.lower < self.upper, "truncated requires lower < upper")
-        a, b = (self.lower - inner.mu) / inner.sigma, (self.upper - inner.mu) / inner.sigma
-        sf = lambda z: 0.5 * math.erfc(z / math.sqrt(2.0))     # noqa: E731  upper tail
-        cdf = lambda z: 0.5 * math.erfc(-z / math.sqrt(2.0))   # noqa: E731
-        mass = (sf(a) - sf(b)) if a > 0 else (cdf(b) - cdf(a))
+        mass = (fz.sf(self.lower) - fz.sf(self.upper)) if fz.cdf(self.lower) > 0.5 else (fz.cdf(self.upper) - fz.cdf(self.lower))
         self.logz = math.log(mass)
 
     def support(self):

@@ -32,6 +32,7 @@
 #endif
 
 #include "../include/jbugs_plan.h"
+#include "../include/jbugs_trunc.h"
 
 #define LOG2PI 1.8378770664093454835606594728112
 #define LOGISTIC_LOWER (-744.4400719213812)
@@ -407,13 +408,6 @@ static inline int64_t local_slot(const jbo_plan* p, const jbugs_local* l, int64_
     return l->theta_base + l->stride_i * i + l->stride_j * j;
 }
 
-/* log(Phi((ub - mu) sqrt(tau)) - Phi((lb - mu) sqrt(tau))), from erfc on the side of the smaller tail */
-static double truncnorm_logmass(double mu, double tau, double lb, double ub) {
-    const double sd = sqrt(1.0 / tau), a = (lb - mu) / sd, b = (ub - mu) / sd, r2 = sqrt(2.0);
-    const double mass = a > 0 ? 0.5 * erfc(a / r2) - 0.5 * erfc(b / r2) : 0.5 * erfc(-b / r2) - 0.5 * erfc(-a / r2);
-    return log(mass);
-}
-
 /* returns 0 ok, 1 domain error */
 static int eval_chain(const jbo_plan* p, chain_io io, int want_grad, double* logp_out) {
     double gval[MAXG], gadj[MAXG], gdxdy[MAXG], gdlj[MAXG];
@@ -458,12 +452,13 @@ static int eval_chain(const jbo_plan* p, chain_io io, int want_grad, double* log
         logp += lp;
         gadj[h] += dx;
         for (int q = 0; q < 3; ++q) argadj(&g->args[q], da[q], gadj, NULL);
-        /* truncated(dnorm(mu, tau), lb, ub) (the BUGS suffix T(lb, ub)): a dnorm global whose support bounds are
-           narrower than the real line; literal arguments only (checked at plan creation), so the normaliser
-           log(cdf(ub) - cdf(lb)) is a constant.  Outside the bounds (possible in untransformed space only): -Inf */
-        if (g->family == JBUGS_FAM_NORMAL && g->lb < g->ub && (isfinite(g->lb) || isfinite(g->ub))) {
+        /* truncated(dist(args), lb, ub) (the BUGS suffix T(lb, ub)): a global whose support bounds are narrower than
+           the natural support of its family (include/jbugs_trunc.h); literal arguments only (checked at plan creation),
+           so the normaliser log(cdf(ub) - cdf(lb)) is a constant.  Outside the bounds (possible in untransformed space
+           only): -Inf */
+        if (jbugs_is_truncated(g->family, a[0], a[1], g->lb, g->ub) == 1) {
             if (gval[h] < g->lb || gval[h] > g->ub) return 1;
-            logp -= truncnorm_logmass(a[0], a[1], g->lb, g->ub);
+            logp -= jbugs_trunc_logmass(g->family, a[0], a[1], g->lb, g->ub);
         }
     }
     /* plates */

@@ -67,7 +67,7 @@ def test_support_bounds_drive_the_bijector():
 
 
 @pytest.mark.parametrize("text", [
-    "model { a ~ dgamma(2, 1) T(0.5, )\n for (i in 1:N) { y[i] ~ dnorm(a, 1) } }",               # only dnorm is lowered
+    "model { a ~ dbeta(2, 2) T(0.2, )\n for (i in 1:N) { y[i] ~ dnorm(a, 1) } }",                # dbeta has no elementary cdf here
     "model { t ~ dgamma(1, 1)\n a ~ dnorm(0, t) T(0, )\n for (i in 1:N) { y[i] ~ dnorm(a, 1) } }",   # argument is a parameter
     "model { a ~ dnorm(0, 1)\n for (i in 1:N) { y[i] ~ dnorm(a, 1) T(0, ) } }",                  # truncated observation
     "model { for (i in 1:N) { b[i] ~ dnorm(0, 1) T(0, )\n y[i] ~ dnorm(b[i], 1) } }",            # parameter of a plate
@@ -96,3 +96,68 @@ def test_cuda_matches_c_port_and_scipy():
     scale = np.maximum(np.abs(g0), 1e-4 * np.abs(g0).max(axis=0, keepdims=True))
     assert np.max(np.abs(g - g0) / scale) < 1e-10
     assert lp[0] == pytest.approx(closed_form(names, theta[:, 0]), abs=1e-10)
+
+
+# ---- every family whose truncation is provided (include/jbugs_trunc.h), against scipy's own truncation
+FAMILIES = {
+    # BUGS prior, bounds, scipy distribution, (bijector of the truncated support: value and log-Jacobian from theta)
+    "dgamma": ("dgamma(2.5, 1.5) T(0.4, 3.0)", S.gamma(2.5, scale=1 / 1.5), (0.4, 3.0)),
+    "dgamma_lower": ("dgamma(0.7, 0.5) T(1.0, )", S.gamma(0.7, scale=2.0), (1.0, np.inf)),
+    "dexp": ("dexp(0.8) T(, 2.5)", S.expon(scale=1 / 0.8), (0.0, 2.5)),
+    "dlnorm": ("dlnorm(0.2, 2.0) T(0.5, 4.0)", S.lognorm(s=1 / np.sqrt(2.0), scale=np.exp(0.2)), (0.5, 4.0)),
+    "dlogis": ("dlogis(0.5, 1.5) T(-1.0, )", S.logistic(0.5, 1 / np.sqrt(1.5)), (-1.0, np.inf)),
+    "ddexp": ("ddexp(0.0, 2.0) T(-0.5, 1.5)", S.laplace(0.0, 1 / np.sqrt(2.0)), (-0.5, 1.5)),
+    "dweib": ("dweib(1.7, 0.6) T(0.3, )", S.weibull_min(1.7, scale=1 / 0.6), (0.3, np.inf)),
+    "dchisqr": ("dchisqr(3) T(, 6.0)", S.chi2(3), (0.0, 6.0)),
+    "dunif": ("dunif(-2, 5) T(0, 3)", S.uniform(-2, 7), (0.0, 3.0)),
+    "dnorm_far_tail": ("dnorm(0, 1) T(6.0, )", S.norm(0, 1), (6.0, np.inf)),
+}
+
+
+def _single(prior):
+    return f"model {{ a ~ {prior}\n for (i in 1:N) {{ y[i] ~ dnorm(a, 2.0) }} }}"
+
+
+def _value_and_logjac(theta, lb, ub):
+    if np.isfinite(lb) and np.isfinite(ub):
+        sg = 1.0 / (1.0 + np.exp(-theta))
+        x = lb + (ub - lb) * sg
+        return x, np.log((x - lb) * (ub - x) / (ub - lb))
+    if np.isfinite(lb):
+        return lb + np.exp(theta), theta
+    return ub - np.exp(theta), theta
+
+
+@pytest.mark.parametrize("name", sorted(FAMILIES))
+def test_truncated_families_against_scipy(name):
+    prior, dist, (lb, ub) = FAMILIES[name]
+    data = {"N": 3, "y": np.array([0.8, 1.4, 1.1]) + (6.0 if name == "dnorm_far_tail" else 0.0)}
+    text = _single(prior)
+    gm = go.compile(text, data, {}).use_generated_order()
+    plan, lw = jbugs.lower(text, data)
+    g = plan.globals[0]
+    assert (g.lb, g.ub) == (lb, ub)
+    theta = np.array([[-0.7, 0.1, 0.9]])
+    lp, gr, st = COracle(plan).eval_batch(theta)
+    mass = (dist.sf(lb) - dist.sf(ub)) if dist.cdf(lb) > 0.5 else (dist.cdf(ub) - dist.cdf(lb))
+    for c in range(3):
+        x, lj = _value_and_logjac(theta[0, c], lb, ub)
+        expect = dist.logpdf(x) - np.log(mass) + lj + S.norm(x, 1 / np.sqrt(2.0)).logpdf(data["y"]).sum()
+        l0, g0 = gm.logdensity_and_gradient(theta[:, c])
+        assert l0 == pytest.approx(expect, abs=1e-10)
+        assert st[c] == 0 and lp[c] == pytest.approx(l0, abs=1e-10)
+        assert grad_err(gr[:, c], g0) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(FAMILIES))
+def test_truncated_families_cuda(name):
+    prior, dist, (lb, ub) = FAMILIES[name]
+    data = {"N": 3, "y": np.array([0.8, 1.4, 1.1]) + (6.0 if name == "dnorm_far_tail" else 0.0)}
+    m = jbugs.compile(_single(prior), data)
+    theta = np.linspace(-1.5, 1.5, 64)[None, :]
+    lp, g, st = m.cuda.eval_host(theta, layout="param_fast")
+    lp0, g0, st0 = COracle(m.plan).eval_batch(theta)
+    assert (st == 0).all() and (st0 == 0).all()
+    assert np.max(np.abs(lp - lp0) / np.maximum(1.0, np.abs(lp0))) < 1e-12
+    assert np.max(np.abs(g - g0) / np.maximum(np.abs(g0), 1e-4 * np.abs(g0).max())) < 1e-10
