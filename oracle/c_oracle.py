@@ -18,9 +18,18 @@ _LIB = None
 def build(force=False):
     so = os.path.join(_HERE, "libjbugs_oracle.so")
     src = os.path.join(_HERE, "jbugs_oracle.c")
-    hdr = os.path.join(_HERE, "..", "include", "jbugs_plan.h")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    hdrs = [os.path.join(_HERE, "..", "include", h) for h in ("jbugs_plan.h", "jbugs_trunc.h")]
+
+    def stale():
+        return not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in [src] + hdrs)
+
+    if force or stale():
+        # several pytest-xdist workers may get here at once: one rebuilds, the others wait for the lock and find it done
+        import fcntl
+        with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            if force or stale():
+                subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
     return so
 
 
