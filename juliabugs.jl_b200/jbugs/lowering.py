@@ -1819,6 +1819,19 @@ class Lowering:
 
         lv_names, shape = s.loop_vars, s.shape
         rec = lambda x: self._tape(x, s, plate, tape, memo, used_locals)  # noqa: E731
+        if isinstance(e, (Neg, BinOp, Call)):
+            # a sub-expression of globals and constants only (tau[k] <- 1 / (sigma[k] * sigma[k]) behind tau[z[i]],
+            # log(1 - q)) does not vary over the plate: it becomes a scalar logical node on the gtape -- evaluated once
+            # per chain in the prologue, its adjoint reversed once in finalize -- and the tape reads its value
+            only, has = self._global_only(e)
+            if only and has:
+                n_gt = len(self.plan.gtape)
+                try:
+                    a = self._gexpr(e)
+                except LoweringError:
+                    del self.plan.gtape[n_gt:]
+                else:
+                    return push(P.XOp(P.OP_LEAF, leaf=a))
         if isinstance(e, Call) and e.fn == "__select__":
             cond, a, b = e.args
             lv = _grids(s.extents, lv_names)
@@ -1936,6 +1949,27 @@ class Lowering:
                 memo[key] = rec(Call("log", (BinOp("/", x, BinOp("-", Num(1.0), x)),)))
                 return memo[key]
         raise LoweringError(f"unsupported expression in a predictor: {_show(e)}")
+
+    def _global_only(self, e):
+        """(every leaf of `e` is a global value or a constant, at least one is a global value)"""
+        if isinstance(e, Num):
+            return True, False
+        if isinstance(e, Var):
+            return (True, True) if e.name in self._gval_ids else (self._is_data(e, ()), False)
+        if isinstance(e, Index):
+            lab = self._elem_label(e)
+            if lab is not None and lab in self._gval_ids:
+                return True, True
+            return (not any(isinstance(i, (Range, Colon)) for i in e.idx) and self._is_data(e, ())), False
+        if isinstance(e, Neg):
+            return self._global_only(e.a)
+        if isinstance(e, BinOp):
+            a, b = self._global_only(e.a), self._global_only(e.b)
+            return a[0] and b[0], a[1] or b[1]
+        if isinstance(e, Call) and (e.fn in P.UNARY_OF or e.fn == "pow") and e.args:
+            rs = [self._global_only(a) for a in e.args]
+            return all(r[0] for r in rs), any(r[1] for r in rs)
+        return False, False
 
     def _gvec_at(self, e: Index, s: Stmt):
         """(first global value slot, number of elements, 0-based index expression) when `e` is `name[idx]` with `name` a

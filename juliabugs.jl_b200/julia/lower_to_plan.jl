@@ -1199,6 +1199,25 @@ function sibling_logpdf(t::Stmt, s::Stmt)
     fail("'$(name_of(t))': a second observation of a summed-out latent must be dbern, dbin, dnorm or dpois")
 end
 
+"(every leaf of `e` is a global value or a constant, at least one is a global value) (lowering.py _global_only)"
+function global_only(lw::Lowering, e)
+    e isa Number && return true, false
+    if e isa Symbol
+        haskey(lw.gval_ids, string(e)) && return true, true
+        return is_data(lw, e, Symbol[]), false
+    end
+    if is_ref(e)
+        lab = elem_label(lw, e)
+        (lab !== nothing && haskey(lw.gval_ids, lab)) && return true, true
+        return (!any(i -> is_range(i) || is_colon(i), e.args[2:end]) && is_data(lw, e, Symbol[])), false
+    end
+    if e isa Expr && e.head == :call && (is_neg(e) || is_binop(e) || e.args[1] == :pow || haskey(UNARY_OF, e.args[1])) && length(e.args) >= 2
+        rs = [global_only(lw, a) for a in e.args[2:end]]
+        return all(r -> r[1], rs), any(r -> r[2], rs)
+    end
+    return false, false
+end
+
 """(first global value slot, number of elements, 0-based index expression) when `e` is `name[idx]` with `name` a parameter
 vector whose elements were expanded into consecutive globals and `idx` a data expression that varies over the plate
 (lowering.py _gvec_at), else nothing"""
@@ -1261,6 +1280,22 @@ function tape!(lw::Lowering, e, s::Stmt, plate::Plate, tape::Vector{XOp}, memo::
     end
     lvs, shp = loop_vars(s), shape_of(s)
     rec(x) = tape!(lw, x, s, plate, tape, memo, used)
+    if e isa Expr && e.head == :call
+        # a sub-expression of globals and constants only (log(1 - q)) does not vary over the plate: it becomes a scalar
+        # logical node on the gtape -- once per chain in the prologue -- and the tape reads its value (lowering.py _tape)
+        only, has = global_only(lw, e)
+        if only && has
+            n_gt = length(lw.plan.gtape)
+            a = try
+                gexpr(lw, e)
+            catch err
+                err isa LoweringError || rethrow()
+                resize!(lw.plan.gtape, n_gt)
+                nothing
+            end
+            a === nothing || return push_op(XOp(OP_LEAF, 0, 0, 0, a))
+        end
+    end
     if is_call(e, :__select__)
         cond, a, b = e.args[2:4]
         m = grid(lw.de, cond, lvs, s.extents) .!= 0
