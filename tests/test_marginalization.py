@@ -693,3 +693,88 @@ def test_cuda_second_child_families(kind):
     assert np.max(np.abs(lp - lp0) / np.maximum(1.0, np.abs(lp0))) < 1e-12
     scale = np.maximum(np.abs(g0), 1e-4 * np.abs(g0).max(axis=0, keepdims=True))
     assert np.max(np.abs(g - g0) / scale) < 1e-10
+
+
+# ---- randomly assembled marginalised models: latent kind x number of states x observation family x optional second child
+# x partial observation, node-oracle recursion == plan through the C restatement (and CUDA below)
+def _random_marginalised(seed):
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.integers(3, 6))
+    bern = bool(rng.integers(0, 2))
+    K = 2 if bern else int(rng.integers(2, 4))
+    fam = ["dnorm", "dpois", "dbern"][int(rng.integers(0, 3))]
+    child = [None, "dnorm", "dpois", "dbin"][int(rng.integers(0, 4))]
+    partial = bool(rng.integers(0, 2))
+    weights_param = bool(rng.integers(0, 2)) and K == 2
+    lines = ["model {"]
+    if bern:
+        lines.append("  p ~ dbeta(2, 2)" if weights_param else "  p <- 0.35")
+        zdef, zidx = "z[i] ~ dbern(p)", "s[i]"
+    else:
+        if weights_param:
+            lines += ["  p ~ dbeta(2, 2)", "  w[1] <- p", "  w[2] <- 1 - p"]
+        else:
+            cuts = np.sort(rng.choice(np.arange(100, 900), K - 1, replace=False))
+            w = np.diff(np.r_[0, cuts, 1000])          # integers summing to 1000: three-digit weights summing to 1 exactly
+            lines += [f"  w[{k + 1}] <- 0.{w[k]:03d}" for k in range(K)]
+        zdef, zidx = f"z[i] ~ dcat(w[1:{K}])", "z[i]"
+    lines += [f"  a[{k + 1}] ~ dnorm({k - 0.5:.1f}, 0.5)" for k in range(K)]
+    lines.append("  b ~ dnorm(0, 1)")
+    lines.append("  for (i in 1:N) {")
+    lines.append("    " + zdef)
+    if bern:
+        lines.append("    s[i] <- z[i] + 1")
+    if fam == "dnorm":
+        lines.append(f"    y[i] ~ dnorm(a[{zidx}] + b * x[i], 1.3)")
+    elif fam == "dpois":
+        lines += [f"    y[i] ~ dpois(lam[i])", f"    log(lam[i]) <- a[{zidx}] + b * x[i]"]
+    else:
+        lines += [f"    y[i] ~ dbern(q[i])", f"    logit(q[i]) <- a[{zidx}] + b * x[i]"]
+    if child == "dnorm":
+        lines.append(f"    c[i] ~ dnorm(b * a[{zidx}], 2.0)")
+    elif child == "dpois":
+        lines += ["    c[i] ~ dpois(nu[i])", f"    log(nu[i]) <- 0.5 * a[{zidx}]"]
+    elif child == "dbin":
+        lines += ["    c[i] ~ dbin(r[i], m[i])", f"    logit(r[i]) <- a[{zidx}] - b"]
+    lines += ["  }", "}"]
+    data = {"N": N, "x": rng.standard_normal(N)}
+    data["y"] = {"dnorm": rng.standard_normal(N), "dpois": rng.poisson(1.5, N).astype(float),
+                 "dbern": rng.integers(0, 2, N).astype(float)}[fam]
+    if child == "dnorm":
+        data["c"] = rng.standard_normal(N)
+    elif child == "dpois":
+        data["c"] = rng.poisson(1.0, N).astype(float)
+    elif child == "dbin":
+        data["m"] = rng.integers(2, 7, N).astype(float)
+        data["c"] = rng.binomial(data["m"].astype(int), 0.4).astype(float)
+    if partial:
+        z = np.full(N, np.nan)
+        z[0] = float(rng.integers(0, 2)) if bern else float(rng.integers(1, K + 1))
+        data["z"] = z
+    return "\n".join(lines), data, f"bern={bern} K={K} fam={fam} child={child} partial={partial} wparam={weights_param}"
+
+
+@pytest.mark.parametrize("seed", list(range(32)))
+def test_random_marginalised_model_against_the_node_oracle(seed):
+    text, data, desc = _random_marginalised(seed)
+    plan, gm = lowered(text, data)
+    theta = 0.5 * np.random.default_rng(seed).standard_normal((plan.D, 3))
+    lp, g, st = COracle(plan).eval_batch(theta)
+    for c in range(3):
+        l0, g0 = gm.marginal_logdensity_and_gradient(theta[:, c])
+        assert st[c] == 0 and abs(lp[c] - l0) <= 1e-11 * max(1.0, abs(l0)), (desc, text)
+        assert grad_err(g[:, c], g0) < 1e-10, (desc, text)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_random_marginalised_model_cuda(seed):
+    text, data, desc = _random_marginalised(seed)
+    m = jbugs.compile(text, data, evaluation_mode=jbugs.UseAutoMarginalization())
+    theta = 0.5 * np.random.default_rng(seed).standard_normal((m.plan.D, 40))
+    lp0, g0, st0 = COracle(m.plan).eval_batch(theta)
+    lp, g, st = m.cuda.eval_host(theta, layout="param_fast")
+    assert (st == 0).all() and (st0 == 0).all(), desc
+    assert np.max(np.abs(lp - lp0) / np.maximum(1.0, np.abs(lp0))) < 1e-12, desc
+    scale = np.maximum(np.abs(g0), 1e-4 * np.abs(g0).max(axis=0, keepdims=True))
+    assert np.max(np.abs(g - g0) / scale) < 1e-10, desc
