@@ -285,4 +285,26 @@ def generated_quantities(lowering: Lowering, draws: Dict[str, np.ndarray], seed:
                 env[lhs.name] = cur
             if s.is_gq or not only_gq:
                 out[s.name] = env[s.name]
+    return _restore_split_arrays(lw, out)
+
+
+def _restore_split_arrays(lw: Lowering, out):
+    """arrays the lowering split when it wrote a short outer loop out (`odds.ratio<0:3>`, Lowering._unroll_outer_loops) come
+    back under their own name with the dropped axis in place"""
+    renamed = getattr(lw, "_renamed", None)
+    if not renamed or not any(k in renamed for k in out):
+        return out
+    groups: Dict[str, list] = {}
+    for k in list(out):
+        if k in renamed:
+            orig, q, v = renamed[k]
+            groups.setdefault(orig, []).append((q, v, out.pop(k)))
+    for orig, parts in groups.items():
+        q = parts[0][0]
+        top = max(v for _, v, _ in parts)
+        shp = np.broadcast_shapes(*[np.shape(a) for _, _, a in parts])
+        full = np.full(shp[:q] + (top,) + shp[q:], np.nan)
+        for _, v, a in parts:
+            full[(slice(None),) * q + (v - 1,)] = np.broadcast_to(a, shp)
+        out[orig] = full
     return out

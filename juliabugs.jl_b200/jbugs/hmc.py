@@ -157,6 +157,32 @@ def _constrain(tr, lb, ub, y):
     return y
 
 
+def monitor_table(model: BUGSModel, monitor: Optional[Sequence[str]] = None):
+    """(names, name -> (theta slot, bijector code, lb, ub)) of the parameters a run records: every scalar parameter by
+    default, else the labels asked for ('tau', 'beta[2]', 'alpha[17]').  Names are the PUBLIC labels: a model whose short
+    outer loop was written out by the lowering (Magnesium) keeps `mu[3]`, `theta[3,5]` although its plan calls them
+    `mu<0:3>`, `theta<0:3>[5]`."""
+    lw = model.lowering
+    public = {}
+    for st in lw.stmts:
+        if st.kind == "param" and not st.is_gq and (st.sid in lw.theta_map or lw.theta_order is not None) and st.size <= 100_000:
+            public.update(zip(lw._labels_for(st), lw._labels_for(st, public=True)))
+    by_name = {public.get(g.name, g.name): (g.theta_idx, g.transform, g.lb, g.ub) for g in model.plan.globals}
+    names = list(by_name) if monitor is None else list(monitor)
+    if any(n not in by_name for n in names):
+        # elements of plate-level parameters: slot from the theta map, bijector from the plate's local record
+        slot = {lab: k for k, lab in enumerate(lw.param_names())}
+        tr = {l.name: (l.transform, l.lb, l.ub) for pl in model.plan.plates for l in pl.locals}
+        internal = {b: a for a, b in public.items()}
+        for n in names:
+            if n not in by_name:
+                base = internal.get(n, n).partition("[")[0]
+                if n not in slot or base not in tr:
+                    raise KeyError(f"'{n}' is not a parameter of the model")
+                by_name[n] = (slot[n],) + tr[base]
+    return names, by_name
+
+
 def sample(model: BUGSModel, sampler, n_samples: int, n_adapts: int = 500, n_chains: int = 256, seed: int = 1234,
            monitor: Optional[Sequence[str]] = None, init: Optional[np.ndarray] = None, specialize: bool = False) -> Chains:
     """`AbstractMCMC.sample(model, sampler, n_samples; n_adapts, ...)` for `n_chains` lock-step chains.
@@ -166,19 +192,7 @@ def sample(model: BUGSModel, sampler, n_samples: int, n_adapts: int = 500, n_cha
     cp = model.cuda
     if specialize:
         cp.specialize()   # a kernel for this model's plate shapes (nvcc at run time, cached): worth it for long runs
-    names = [g.name for g in model.plan.globals] if monitor is None else list(monitor)
-    by_name = {g.name: (g.theta_idx, g.transform, g.lb, g.ub) for g in model.plan.globals}
-    if any(n not in by_name for n in names):
-        # elements of plate-level parameters: slot from the theta map, bijector from the plate's local record
-        lw = model.lowering
-        slot = {lab: k for k, lab in enumerate(lw.param_names())}
-        tr = {l.name: (l.transform, l.lb, l.ub) for pl in model.plan.plates for l in pl.locals}
-        for n in names:
-            if n not in by_name:
-                base = n.partition("[")[0]
-                if n not in slot or base not in tr:
-                    raise KeyError(f"'{n}' is not a parameter of the model")
-                by_name[n] = (slot[n],) + tr[base]
+    names, by_name = monitor_table(model, monitor)
     rows = np.array([by_name[n][0] for n in names], dtype=np.int64)
     th0 = np.ascontiguousarray(getparams(model) if init is None else init, dtype=np.float64)
     th0 = np.where(np.isfinite(th0), th0, 0.0)

@@ -335,3 +335,33 @@ def test_arrays_used_outside_their_outer_loop_are_not_split():
     }"""
     with pytest.raises(jbugs.LoweringError):
         jbugs.lower(text, {"K": 3, "y": np.zeros((2, 3)), "z": 0.5})
+
+
+def test_unrolled_model_keeps_its_public_names(fixtures):
+    """Magnesium is lowered with its outer loop written out (arrays split per iteration inside the plan); what a user sees
+    -- parameter names, the sampler's monitor table, generated quantities -- carries the names of the model text"""
+    import jbugs.hmc as hmc
+    from jbugs import examples as ex, gq
+    data = fixtures["magnesium"]["data"]
+    plan, lw = jbugs.lower(ex.MAGNESIUM, data)
+    pn = lw.param_names()
+    assert "theta[3,5]" in pn and not any("<" in n for n in pn)
+
+    class M:   # (the table needs the plan and the lowering only: no device)
+        pass
+    m = M()
+    m.plan, m.lowering = plan, lw
+    names, by = hmc.monitor_table(m)
+    assert {"mu[1]", "mu[6]", "B0", "D0", "tau[3]"} <= set(names) and not any("<" in n for n in names)
+    names, by = hmc.monitor_table(m, ["mu[3]", "theta[3,5]", "pc[6,8]"])
+    assert [pn[by[n][0]] for n in names] == ["mu[3]", "theta[3,5]", "pc[6,8]"]
+    assert by["pc[6,8]"][1] == P.TR_LOGIT and by["theta[3,5]"][1] == P.TR_IDENTITY
+    with pytest.raises(KeyError):
+        hmc.monitor_table(m, ["theta[7,1]"])
+    rng = np.random.default_rng(0)
+    S = 5
+    draws = {n: (rng.uniform(0.1, 0.9, S) if n.startswith(("pc", "B0", "D0")) else
+                 rng.uniform(0.5, 2.0, S) if n.startswith(("tau", "inv.tau")) else rng.standard_normal(S)) for n in pn}
+    out = gq.generated_quantities(lw, draws)
+    assert out["odds.ratio"].shape == (6, S)
+    assert np.allclose(out["odds.ratio"][2], np.exp(draws["mu[3]"]))
