@@ -49,10 +49,52 @@ static inline void jbugs_gamma_pq(double a, double x, double* p, double* q) {
     }
 }
 
+/* regularised incomplete beta function I = I_x(a, b) and its complement J = 1 - I: Lentz continued fraction, entered from
+   the side on which it converges fast (x below the mean: I directly; above: J directly through I_{1-x}(b, a)), so the
+   smaller of the two is the one computed without cancellation */
+static inline double jbugs_betacf(double a, double b, double x) {
+    const double tiny = 1e-300, qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0, d = 1.0 - qab * x / qap;
+    if (fabs(d) < tiny) d = tiny;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m < 5000; ++m) {
+        const double m2 = 2.0 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d; if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c; if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d; if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c; if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    return h;
+}
+
+static inline void jbugs_beta_ij(double a, double b, double x, double* i, double* j) {
+    if (!(x > 0.0)) { *i = 0.0; *j = 1.0; return; }
+    if (!(x < 1.0)) { *i = 1.0; *j = 0.0; return; }
+    const double bt = exp(lgamma(a + b) - lgamma(a) - lgamma(b) + a * log(x) + b * log1p(-x));
+    if (x < (a + 1.0) / (a + b + 2.0)) {
+        *i = bt * jbugs_betacf(a, b, x) / a;
+        *j = 1.0 - *i;
+    } else {
+        *j = bt * jbugs_betacf(b, a, 1.0 - x) / b;
+        *i = 1.0 - *j;
+    }
+}
+
 /* natural support of a family with these arguments; 0 when the family is one whose truncation is provided */
 static inline int jbugs_natural_support(unsigned fam, double a0, double a1, double* lo, double* hi) {
     switch (fam) {
-    case JBUGS_FAM_NORMAL: case JBUGS_FAM_LOGISTIC: case JBUGS_FAM_LAPLACE: *lo = -INFINITY; *hi = INFINITY; return 0;
+    case JBUGS_FAM_NORMAL: case JBUGS_FAM_LOGISTIC: case JBUGS_FAM_LAPLACE: case JBUGS_FAM_T:
+        *lo = -INFINITY; *hi = INFINITY; return 0;
+    case JBUGS_FAM_BETA: *lo = 0.0; *hi = 1.0; return 0;
     case JBUGS_FAM_GAMMA: case JBUGS_FAM_EXPONENTIAL: case JBUGS_FAM_LOGNORMAL: case JBUGS_FAM_WEIBULL: case JBUGS_FAM_CHISQ:
         *lo = 0.0; *hi = INFINITY; return 0;
     case JBUGS_FAM_UNIFORM: *lo = a0; *hi = a1; return 0;
@@ -60,8 +102,8 @@ static inline int jbugs_natural_support(unsigned fam, double a0, double a1, doub
     }
 }
 
-/* lower tail F(x) and upper tail S(x) */
-static inline void jbugs_tails(unsigned fam, double a0, double a1, double x, double* F, double* S) {
+/* lower tail F(x) and upper tail S(x); a2: the third argument of the family (dt's degrees of freedom), else unused */
+static inline void jbugs_tails(unsigned fam, double a0, double a1, double a2, double x, double* F, double* S) {
     switch (fam) {
     case JBUGS_FAM_NORMAL: { /* dnorm(mu, tau) */
         const double z = (x - a0) * sqrt(a1) / sqrt(2.0);
@@ -91,6 +133,15 @@ static inline void jbugs_tails(unsigned fam, double a0, double a1, double x, dou
     }
     case JBUGS_FAM_GAMMA: jbugs_gamma_pq(a0, a1 * x, F, S); return;        /* dgamma(shape, rate) */
     case JBUGS_FAM_CHISQ: jbugs_gamma_pq(0.5 * a0, 0.5 * x, F, S); return;  /* dchisqr(k) */
+    case JBUGS_FAM_BETA: jbugs_beta_ij(a0, a1, x, F, S); return;            /* dbeta(a, b) */
+    case JBUGS_FAM_T: { /* dt(mu, tau, nu): P(|T| > |z|) = I_{nu / (nu + z^2)}(nu / 2, 1 / 2), z = (x - mu) sqrt(tau) */
+        const double z = (x - a0) * sqrt(a1);
+        double i, j;
+        if (isinf(z)) { *F = z > 0.0 ? 1.0 : 0.0; *S = 1.0 - *F; return; }
+        jbugs_beta_ij(0.5 * a2, 0.5, a2 / (a2 + z * z), &i, &j);
+        if (z > 0.0) { *S = 0.5 * i; *F = 1.0 - *S; } else { *F = 0.5 * i; *S = 1.0 - *F; }
+        return;
+    }
     case JBUGS_FAM_UNIFORM: {
         const double u = x <= a0 ? 0.0 : (x >= a1 ? 1.0 : (x - a0) / (a1 - a0));
         *F = u; *S = 1.0 - u; return;
@@ -109,10 +160,10 @@ static inline int jbugs_is_truncated(unsigned fam, double a0, double a1, double 
 }
 
 /* log(cdf(ub) - cdf(lb)), from the tails on the side where the difference does not cancel */
-static inline double jbugs_trunc_logmass(unsigned fam, double a0, double a1, double lb, double ub) {
+static inline double jbugs_trunc_logmass(unsigned fam, double a0, double a1, double a2, double lb, double ub) {
     double Fl = 0.0, Sl = 1.0, Fu = 1.0, Su = 0.0;
-    if (isfinite(lb)) jbugs_tails(fam, a0, a1, lb, &Fl, &Sl);
-    if (isfinite(ub)) jbugs_tails(fam, a0, a1, ub, &Fu, &Su);
+    if (isfinite(lb)) jbugs_tails(fam, a0, a1, a2, lb, &Fl, &Sl);
+    if (isfinite(ub)) jbugs_tails(fam, a0, a1, a2, ub, &Fu, &Su);
     const double mass = Fl > 0.5 ? Sl - Su : Fu - Fl;
     return log(mass);
 }

@@ -691,7 +691,10 @@ extern "C" int jbugs_plan_create(const void* blob, size_t nbytes, int device, jb
             if (!p->gp.transformed)
                 return destroy(fail(JBUGS_ERR_UNSUPPORTED, "global %u: truncated priors are evaluated in transformed space only "
                                                            "(the support check of the untransformed value is not on the device)", k));
-            const double lm = jbugs_trunc_logmass(g.family, val(g.args[0]), val(g.args[1]), g.lb, g.ub);
+            if (g.family == JBUGS_FAM_T && !lit(g.args[2]))
+                return destroy(fail(JBUGS_ERR_UNSUPPORTED, "global %u: a truncated dt prior needs literal degrees of freedom", k));
+            const double a2 = lit(g.args[2]) ? val(g.args[2]) : 0.0;   // (dt's degrees of freedom; unused by the two-argument families)
+            const double lm = jbugs_trunc_logmass(g.family, val(g.args[0]), val(g.args[1]), a2, g.lb, g.ub);
             if (!std::isfinite(lm)) return destroy(fail(JBUGS_ERR_INVALID, "global %u: the truncation bounds hold no mass", k));
             p->gp.cst[k] -= lm;
         }

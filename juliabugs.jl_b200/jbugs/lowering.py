@@ -1344,9 +1344,9 @@ class Lowering:
         evaluators, which fold the normaliser log(cdf(upper) - cdf(lower)) into the prior's constant
         (include/jbugs_plan.h, jbugs_global.lb / ub)."""
         if fam not in (P.FAM_NORMAL, P.FAM_LOGNORMAL, P.FAM_LOGISTIC, P.FAM_LAPLACE, P.FAM_EXPONENTIAL, P.FAM_GAMMA,
-                       P.FAM_WEIBULL, P.FAM_CHISQ, P.FAM_UNIFORM):
-            raise LoweringError(f"'{s.name}': T(,) is lowered for dnorm, dlnorm, dlogis, ddexp, dexp, dgamma, dweib, dchisqr "
-                                "and dunif priors")
+                       P.FAM_WEIBULL, P.FAM_CHISQ, P.FAM_UNIFORM, P.FAM_BETA, P.FAM_T):
+            raise LoweringError(f"'{s.name}': T(,) is lowered for dnorm, dlnorm, dlogis, ddexp, dexp, dgamma, dweib, dchisqr, "
+                                "dunif, dbeta and dt priors")
         if not self.transformed:
             raise LoweringError(f"'{s.name}': truncated priors are evaluated in transformed space only")
         if not all(self._is_data(a, ()) for a in dargs):

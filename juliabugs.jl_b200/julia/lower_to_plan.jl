@@ -693,8 +693,9 @@ end
 _truncation): the bounds are the prior's support and pick the bijector; the evaluators fold log(cdf(upper) - cdf(lower))
 into the prior's constant (include/jbugs_plan.h, jbugs_global.lb / ub)"""
 function truncation(lw::Lowering, s::Stmt, fam, dargs, sub)
-    fam in (FAM_NORMAL, FAM_LOGNORMAL, FAM_LOGISTIC, FAM_LAPLACE, FAM_EXPONENTIAL, FAM_GAMMA, FAM_WEIBULL, FAM_CHISQ, FAM_UNIFORM) ||
-        fail("'$(name_of(s))': T(,) is lowered for dnorm, dlnorm, dlogis, ddexp, dexp, dgamma, dweib, dchisqr and dunif priors")
+    fam in (FAM_NORMAL, FAM_LOGNORMAL, FAM_LOGISTIC, FAM_LAPLACE, FAM_EXPONENTIAL, FAM_GAMMA, FAM_WEIBULL, FAM_CHISQ, FAM_UNIFORM,
+            FAM_BETA, FAM_T) ||
+        fail("'$(name_of(s))': T(,) is lowered for dnorm, dlnorm, dlogis, ddexp, dexp, dgamma, dweib, dchisqr, dunif, dbeta and dt priors")
     lw.transformed || fail("'$(name_of(s))': truncated priors are evaluated in transformed space only")
     all(a -> is_data(lw, a, Symbol[]), dargs) || fail("'$(name_of(s))': a truncated prior needs constant arguments")
     bounds = Float64[]

@@ -389,8 +389,12 @@ def _scipy_frozen(inner):
         return S.chi2(inner.k)
     if isinstance(inner, Uniform) and const(inner.a, inner.b):
         return S.uniform(inner.a, inner.b - inner.a)
-    raise NotImplementedError("T(,) is restated for dnorm, dlnorm, dlogis, ddexp, dexp, dgamma, dweib, dchisqr and dunif "
-                              "with constant arguments")
+    if isinstance(inner, Beta) and const(inner.a, inner.b):
+        return S.beta(inner.a, inner.b)
+    if isinstance(inner, TDistShiftedScaled) and const(inner.mu, inner.sigma, inner.nu):
+        return S.t(inner.nu, loc=inner.mu, scale=inner.sigma)
+    raise NotImplementedError("T(,) is restated for dnorm, dlnorm, dlogis, ddexp, dexp, dgamma, dweib, dchisqr, dunif, dbeta "
+                              "and dt with constant arguments")
 
 
 class TruncatedNormal(Dist):

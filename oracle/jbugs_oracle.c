@@ -458,7 +458,7 @@ static int eval_chain(const jbo_plan* p, chain_io io, int want_grad, double* log
            only): -Inf */
         if (jbugs_is_truncated(g->family, a[0], a[1], g->lb, g->ub) == 1) {
             if (gval[h] < g->lb || gval[h] > g->ub) return 1;
-            logp -= jbugs_trunc_logmass(g->family, a[0], a[1], g->lb, g->ub);
+            logp -= jbugs_trunc_logmass(g->family, a[0], a[1], a[2], g->lb, g->ub);
         }
     }
     /* plates */

@@ -365,3 +365,31 @@ def test_unrolled_model_keeps_its_public_names(fixtures):
     out = gq.generated_quantities(lw, draws)
     assert out["odds.ratio"].shape == (6, S)
     assert np.allclose(out["odds.ratio"][2], np.exp(draws["mu[3]"]))
+
+
+def test_monitor_table_of_the_sampler_test_models(fixtures):
+    """the sampler's monitor table (names -> theta slot, bijector, bounds) for the models tests/test_gpu_hmc.py samples,
+    written out independently: globals under their plan names in plan order; elements of plate-level parameters from the
+    theta map and the plate's local record.  (No device: the table needs the plan and the lowering only.)"""
+    import jbugs.hmc as hmc
+    from jbugs import examples as ex
+
+    def expected(m, monitor):
+        by = {g.name: (g.theta_idx, g.transform, g.lb, g.ub) for g in m.plan.globals}
+        names = [g.name for g in m.plan.globals] if monitor is None else list(monitor)
+        slot = {lab: k for k, lab in enumerate(m.lowering.param_names())}
+        tr = {l.name: (l.transform, l.lb, l.ub) for pl in m.plan.plates for l in pl.locals}
+        for n in names:
+            if n not in by:
+                by[n] = (slot[n],) + tr[n.partition("[")[0]]
+        return names, {n: by[n] for n in names}
+
+    cases = [(ex.SEEDS, "seeds", None), (ex.RATS, "rats", None), (ex.STACKS, "stacks", None),
+             (ex.PUMPS, "pumps", ["alpha", "beta", "theta[1]", "theta[10]"]), (ex.RATS, "rats", ["alpha[17]", "beta[2]", "tau.c"])]
+    for text, name, monitor in cases:
+        m = jbugs.compile(text, fixtures[name]["data"], fixtures[name]["inits"])
+        names, by = hmc.monitor_table(m, monitor)
+        names0, by0 = expected(m, monitor)
+        assert names == names0 and {n: by[n] for n in names} == by0
+    m = jbugs.compile(ex.BEETLES % "probit", ex.BEETLES_DATA, {"alpha.star": 0.0, "beta": 0.0})
+    assert hmc.monitor_table(m)[0] == [g.name for g in m.plan.globals]

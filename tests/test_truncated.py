@@ -67,7 +67,7 @@ def test_support_bounds_drive_the_bijector():
 
 
 @pytest.mark.parametrize("text", [
-    "model { a ~ dbeta(2, 2) T(0.2, )\n for (i in 1:N) { y[i] ~ dnorm(a, 1) } }",                # dbeta has no elementary cdf here
+    "model { a ~ dpois(2) T(1, )\n for (i in 1:N) { y[i] ~ dnorm(a, 1) } }",                     # a discrete prior
     "model { t ~ dgamma(1, 1)\n a ~ dnorm(0, t) T(0, )\n for (i in 1:N) { y[i] ~ dnorm(a, 1) } }",   # argument is a parameter
     "model { a ~ dnorm(0, 1)\n for (i in 1:N) { y[i] ~ dnorm(a, 1) T(0, ) } }",                  # truncated observation
     "model { for (i in 1:N) { b[i] ~ dnorm(0, 1) T(0, )\n y[i] ~ dnorm(b[i], 1) } }",            # parameter of a plate
@@ -110,6 +110,13 @@ FAMILIES = {
     "dweib": ("dweib(1.7, 0.6) T(0.3, )", S.weibull_min(1.7, scale=1 / 0.6), (0.3, np.inf)),
     "dchisqr": ("dchisqr(3) T(, 6.0)", S.chi2(3), (0.0, 6.0)),
     "dunif": ("dunif(-2, 5) T(0, 3)", S.uniform(-2, 7), (0.0, 3.0)),
+    # (regularised incomplete beta function: jbugs_beta_ij)
+    "dbeta": ("dbeta(2.5, 4.0) T(0.2, 0.9)", S.beta(2.5, 4.0), (0.2, 0.9)),
+    "dbeta_lower": ("dbeta(0.6, 0.8) T(0.7, )", S.beta(0.6, 0.8), (0.7, 1.0)),
+    "dbeta_far_tail": ("dbeta(30, 2) T(, 0.3)", S.beta(30, 2), (0.0, 0.3)),
+    "dt": ("dt(0.5, 2.0, 4) T(-1.0, 3.0)", S.t(4, loc=0.5, scale=1 / np.sqrt(2.0)), (-1.0, 3.0)),
+    "dt_half": ("dt(0, 1.0, 3) T(0, )", S.t(3), (0.0, np.inf)),                       # the half-t prior of scale parameters
+    "dt_far_tail": ("dt(0, 1.0, 2.5) T(, -40.0)", S.t(2.5), (-np.inf, -40.0)),
     "dnorm_far_tail": ("dnorm(0, 1) T(6.0, )", S.norm(0, 1), (6.0, np.inf)),
 }
 
