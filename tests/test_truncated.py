@@ -168,3 +168,45 @@ def test_truncated_families_cuda(name):
     assert (st == 0).all() and (st0 == 0).all()
     assert np.max(np.abs(lp - lp0) / np.maximum(1.0, np.abs(lp0))) < 1e-12
     assert np.max(np.abs(g - g0) / np.maximum(np.abs(g0), 1e-4 * np.abs(g0).max())) < 1e-10
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_beta_and_t_truncations_against_scipy(seed):
+    """the regularised incomplete beta function of include/jbugs_trunc.h over random shapes, scales and bounds (both
+    entry sides of the continued fraction, shapes below and above 1, bounds in either tail): C port == node oracle ==
+    scipy's cdf / sf, value and gradient"""
+    rng = np.random.default_rng(1000 + seed)
+    if seed % 2 == 0:
+        a, b = np.round(rng.uniform(0.3, 12.0, 2), 3)
+        dist = S.beta(a, b)
+        q = np.sort(rng.uniform(0.02, 0.98, 2))
+        lo, hi = np.round(dist.ppf(q), 4)
+        name = f"dbeta({a}, {b})"
+        nat = (0.0, 1.0)
+    else:
+        mu, tau, nu = np.round(rng.uniform(-2, 2), 3), np.round(rng.uniform(0.2, 5.0), 3), np.round(rng.uniform(0.8, 30.0), 2)
+        dist = S.t(nu, loc=mu, scale=1 / np.sqrt(tau))
+        q = np.sort(rng.uniform(0.001, 0.999, 2))
+        lo, hi = np.round(dist.ppf(q), 3)
+        name = f"dt({mu}, {tau}, {nu})"
+        nat = (-np.inf, np.inf)
+    if hi <= lo:
+        hi = lo + 0.05
+    which = seed % 3    # two-sided, lower only, upper only
+    prior, lb, ub = [(f"{name} T({lo}, {hi})", lo, hi), (f"{name} T({lo}, )", lo, nat[1]), (f"{name} T(, {hi})", nat[0], hi)][which]
+    data = {"N": 3, "y": np.array([0.3, -0.2, 0.6]) + 0.5 * (lo + hi)}
+    text = _single(prior)
+    gm = go.compile(text, data, {}).use_generated_order()
+    plan, lw = jbugs.lower(text, data)
+    g = plan.globals[0]
+    assert (g.lb, g.ub) == (lb, ub)
+    theta = np.array([[-1.1, 0.2, 1.3]])
+    lp, gr, st = COracle(plan).eval_batch(theta)
+    mass = (dist.sf(lb) - dist.sf(ub)) if dist.cdf(lb) > 0.5 else (dist.cdf(ub) - dist.cdf(lb))
+    for c in range(3):
+        x, lj = _value_and_logjac(theta[0, c], lb, ub)
+        expect = dist.logpdf(x) - np.log(mass) + lj + S.norm(x, 1 / np.sqrt(2.0)).logpdf(data["y"]).sum()
+        l0, g0 = gm.logdensity_and_gradient(theta[:, c])
+        assert l0 == pytest.approx(expect, abs=1e-9, rel=1e-11)
+        assert st[c] == 0 and lp[c] == pytest.approx(l0, abs=1e-9, rel=1e-11)
+        assert grad_err(gr[:, c], g0) < 1e-10
