@@ -63,6 +63,17 @@ def cases():
     yield "bern_latent_subscript_partially_observed", tm.BERN_SUBSCRIPT, {
         "N": 5, "y": y5, "q": 0.1 + 0.8 * rng.random(5), "z": np.array([1.0, np.nan, 0.0, np.nan, np.nan])}, {"marginalize": True}
     yield "cervix_marginalised", jbugs.examples.CERVIX, tm._cervix_data(), {"marginalize": True}
+    # truncated priors, T(lower, upper): every bijector the bounds can pick, and the families whose mass needs the
+    # incomplete gamma / beta functions (include/jbugs_trunc.h)
+    yield "truncated_priors", """model {
+      s ~ dnorm(0, 0.25) T(0, )
+      m ~ dnorm(1, 4) T(-1, 2.5)
+      u ~ dlogis(0, 1) T(, 0.5)
+      g ~ dgamma(2.5, 1.5) T(0.4, 3.0)
+      b ~ dbeta(2.5, 4.0) T(0.2, 0.9)
+      h ~ dt(0, 1.0, 3) T(0, )
+      for (i in 1:N) { y[i] ~ dnorm(m + u + b * x[i], s + g + h) }
+    }""", {"N": 6, "y": np.array([0.3, 1.1, -0.4, 2.0, 0.8, 1.5]), "x": np.linspace(-1.0, 1.0, 6)}, {}
 
 
 def record(plan, lw):
